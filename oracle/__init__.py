@@ -1,0 +1,31 @@
+"""CPU oracle for the FlowKet VMC inner loop -- TEST INFRASTRUCTURE ONLY.
+
+This package is a CPU restatement (numpy + torch-CPU) of the reference's
+algorithm for the hot path named in BASELINE.json `north_star`:
+autoregressive sampling -> find_conn -> local energy -> gradients / SR.
+
+Rules (enforced by tests/test_no_oracle_in_product.py):
+  * only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline /
+    `--impl reference` legs may import anything from here;
+  * nothing under `flowket_b200/` imports it; the product path has no CPU
+    fallback and fails loudly when the CUDA library is missing.
+
+Pinning status (see DESIGN.md "Oracle"):
+  * operators / local energy / exact-enumeration conventions: PINNED against the
+    reference's own numpy code imported from /root/reference (fixtures in
+    tests/golden/, generator oracle/make_golden.py) and against the
+    exact-diagonalisation constants embedded in the reference's examples.
+  * network half (Keras graph; TensorFlow is not installable here): restated
+    from the reference sources cited per function; pinned by the reference's
+    own property tests (normalisation, incremental == full) and end-to-end by
+    the reference's pretrained Keras weight files
+    (experiments/weights/ising_*.h5 -> published energies).  Bit-level parity
+    with TF's unseeded `tf.multinomial` stream is "parity unpinned"; the
+    pinned sampling contract is the explicit-uniform rule of
+    deepar/samplers/autoregressive.py:37-44.
+  * J1J2 connection *order* (netket, un-vendored, unpinned version): "parity
+    unpinned"; values pinned by the ED constant of
+    examples/j1j2_2d_monte_carlo_4.py:43.
+  * real-parameter SR for ConvNetAutoregressive2D has no reference
+    implementation: "parity unpinned" (algebra pinned by the complex tests).
+"""

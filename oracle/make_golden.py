@@ -1,0 +1,117 @@
+"""Generate tests/golden/*.npz by running the REFERENCE's own numpy code (read-only /root/reference).
+
+TEST INFRASTRUCTURE ONLY.  Run once in the build container (`python -m oracle.make_golden`);
+the vectors are committed because /root/reference does not exist on the GPU box.
+
+The reference's root package imports TensorFlow (src/flowket/__init__.py:1-3), which is not installed;
+registering stub parent packages with the right __path__ lets the TF-free sub-modules load unmodified
+(SURVEY.md appendix C).  Nothing is copied from the reference: only its outputs are stored.
+"""
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+
+REF = '/root/reference/src/flowket'
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+
+def load_reference():
+    def stub(name, path):
+        m = types.ModuleType(name)
+        m.__path__ = [path]
+        sys.modules[name] = m
+    stub('flowket', REF)
+    stub('flowket.observables', REF + '/observables')
+    ops = importlib.import_module('flowket.operators')
+    mc = importlib.import_module('flowket.observables.monte_carlo')
+    ex = importlib.import_module('flowket.exact.utils')
+    return ops, mc, ex
+
+
+def main():
+    ops, mc, ex = load_reference()
+    os.makedirs(OUT, exist_ok=True)
+    rng = np.random.default_rng(20261017)
+    out = {}
+
+    # ---- find_conn fixtures --------------------------------------------------------------
+    cases = [
+        ('heis_2d_obc', lambda: ops.Heisenberg(hilbert_state_shape=[4, 5], pbc=False), (4, 5)),
+        ('heis_2d_pbc', lambda: ops.Heisenberg(hilbert_state_shape=[4, 4], pbc=True), (4, 4)),
+        ('heis_2d_obc_norot', lambda: ops.Heisenberg(hilbert_state_shape=[3, 4], pbc=False, unitary_rotation=False), (3, 4)),
+        ('heis_1d_pbc', lambda: ops.Heisenberg(hilbert_state_shape=[7], pbc=True), (7,)),
+        ('heis_1d_obc', lambda: ops.Heisenberg(hilbert_state_shape=[6], pbc=False), (6,)),
+        ('heis_2d_10x10_obc', lambda: ops.Heisenberg(hilbert_state_shape=[10, 10], pbc=False), (10, 10)),
+        ('ising_2d_obc', lambda: ops.Ising(hilbert_state_shape=[4, 4], pbc=False, h=3.0), (4, 4)),
+        ('ising_2d_pbc', lambda: ops.Ising(hilbert_state_shape=[3, 5], pbc=True, h=0.7, j=1.3), (3, 5)),
+        ('ising_1d_obc', lambda: ops.Ising(hilbert_state_shape=[9], pbc=False, h=3.0), (9,)),
+        ('ising_1d_pbc', lambda: ops.Ising(hilbert_state_shape=[8], pbc=True, h=2.0), (8,)),
+    ]
+    for name, make, shape in cases:
+        B = 6 if name != 'heis_2d_10x10_obc' else 3
+        sigma = rng.choice([-1, 1], size=(B,) + shape).astype(np.int8)
+        op = make()
+        conn, mel, use = op.find_conn(sigma.astype(np.float64) if name.startswith('heis') else sigma.astype(np.int64))
+        out[name + '/sigma'] = sigma
+        out[name + '/conn'] = np.asarray(conn).astype(np.int8)
+        out[name + '/mel'] = np.asarray(mel, np.float64)
+        out[name + '/use'] = np.asarray(use, bool)
+        out[name + '/max_conn'] = np.int64(op.max_number_of_local_connections)
+
+    # ---- local energy with a synthetic wave function (vector_to_machine) --------------------
+    for name, make, shape in [
+        ('eloc_heis_2d_obc', lambda: ops.Heisenberg(hilbert_state_shape=[3, 4], pbc=False), (3, 4)),
+        ('eloc_heis_1d_pbc', lambda: ops.Heisenberg(hilbert_state_shape=[7], pbc=True), (7,)),
+        ('eloc_ising_2d_obc', lambda: ops.Ising(hilbert_state_shape=[3, 4], pbc=False, h=3.0), (3, 4)),
+    ]:
+        n = int(np.prod(shape))
+        vec = (rng.normal(size=2 ** n) * 0.3 + 1j * rng.normal(size=2 ** n) * 0.5).astype(np.complex64)
+        psi = ex.vector_to_machine(vec)
+        sigma = rng.choice([-1, 1], size=(16,) + shape).astype(np.int8)
+        obs = mc.Observable(make())
+        lv = obs.local_values(psi, sigma.astype(np.float64))
+        out[name + '/sigma'] = sigma
+        out[name + '/log_psi_vector'] = vec
+        out[name + '/local_values'] = np.asarray(lv, np.complex128)
+
+    # hand-written fixture of tests/test_variational.py:22-34 (balanced == unbalanced) evaluated by the reference
+    sample = np.array([[1, 1, 1, -1, -1, -1, -1], [1, 1, 1, -1, 1, -1, -1], [1, -1, 1, 1, -1, -1, -1]])
+    local_connections = rng.choice([-1, 1], size=(5, 3, 7))
+    local_connections[0] = sample
+    hamiltonian_values = np.array([[2.0, 7j + 8, 0.0, 0.0, 3], [0.0, 0.0, 0.0, 0.0, -1.0], [5.0, 3j, 0.0, -2, 9]]).T
+    all_use_conn = np.array([[True, True, False, False, True], [True, False, False, False, True],
+                             [True, True, False, True, True]]).T
+    vec = (rng.normal(size=2 ** 7) * 0.3 + 1j * rng.normal(size=2 ** 7) * 0.5).astype(np.complex64)
+    obs = mc.Observable(ops.Heisenberg(hilbert_state_shape=(7,)))
+    obs.operator.hilbert_state_shape = (7,)
+    unb = obs.local_values_optimized_for_unbalanced_local_connections(ex.vector_to_machine(vec), local_connections,
+                                                                      hamiltonian_values, all_use_conn)
+    bal = obs.local_values_optimized_for_balanced_local_connections(ex.vector_to_machine(vec), local_connections,
+                                                                    hamiltonian_values)
+    out['handmade/local_connections'] = local_connections.astype(np.int8)
+    out['handmade/hamiltonian_values'] = hamiltonian_values
+    out['handmade/all_use_conn'] = all_use_conn
+    out['handmade/log_psi_vector'] = vec
+    out['handmade/unbalanced'] = np.asarray(unb)
+    out['handmade/balanced'] = np.asarray(bal)
+
+    # ---- bit conventions -------------------------------------------------------------------
+    dec = np.arange(32)
+    out['bits/binary'] = ex.decimal_array_to_binary_array(dec.copy(), 5, False).astype(np.int8)
+    out['bits/decimal'] = ex.binary_array_to_decimal_array(out['bits/binary'].astype(np.int64)).astype(np.int64)
+
+    # ---- exact-diagonalisation anchors embedded in the reference's scripts --------------------
+    out['ed/ising_4x4_obc_h3'] = np.float64(-50.18662388277671)        # examples/basic_autoregressive_2d.py:39
+    out['ed/ising_1d16_obc_h3'] = np.float64(-49.257706531889006)      # examples/basic_autoregressive_exact_gradient.py:38
+    out['ed/j1j2_4x4_obc_j2_0.5'] = np.float64(-30.022227800323677)    # examples/j1j2_2d_monte_carlo_4.py:43
+    out['ed/heis_1d20_pbc'] = np.float64(-35.6175461195)               # examples/complex_ops_autoregressive_heisenberg_1d.py:57
+
+    np.savez_compressed(os.path.join(OUT, 'reference_numpy_half.npz'), **out)
+    print('wrote', os.path.join(OUT, 'reference_numpy_half.npz'), len(out), 'arrays')
+
+
+if __name__ == '__main__':
+    main()
