@@ -1,0 +1,43 @@
+// Machine handle: the layer program of an autoregressive machine + its device-resident weights.
+#pragma once
+#include "fk_common.cuh"
+
+struct fk_net {
+  int kind, H, W, depth, C, k, max_dil, flags;
+  int sites;
+  std::vector<fk::ConvOp> ops;
+  std::vector<fk::BufferInfo> bufs;   // virtual buffers (unique per producer)
+  int n_phys;                         // physical slots in inference mode (liveness-based reuse)
+  int phys_channels;                  // channel count of a physical slot (max over buffers)
+  int in_buf, logits_buf;
+  int64_t num_params;                 // raw trainable parameters
+  int64_t num_eff;                    // effective weights + biases
+  float* d_params;                    // raw parameters            [num_params]
+  float* d_weff;                      // effective weights/biases  [num_eff]   w: [t][ci][co]
+  float* d_weffT;                     // transposed kernels        [num_eff]   w: [t][co][ci]
+  void* d_optable;                    // device copy of the per-op parameter mapping
+  int64_t train_floats_per_cfg;       // sum over virtual buffers of channels * sites
+  // tensor-core engine (ConvNetAutoregressive2D only): bf16 UMMA-canonical weight image
+  void* d_tc_weights;
+  int64_t tc_weight_bytes;
+  bool params_set;
+};
+
+namespace fk {
+
+// runs the layer program on `n` configurations.  `bufs[v]` = device pointer of virtual buffer v.
+int run_forward(fk_net* net, const int8_t* sigma, int64_t n, float* const* buf_ptrs, cudaStream_t s);
+// fills `ptrs` (size net->bufs.size()) for inference mode (physical slots) from a workspace base
+void assign_infer_buffers(const fk_net* net, float* base, int64_t n, std::vector<float*>& ptrs);
+int64_t infer_floats_per_cfg(const fk_net* net);
+
+int launch_lncosh(const float* pre, float* out, int cout, long long npos, cudaStream_t s);
+
+// tensor-core engine (fk_tc.cu)
+int tc_supported(const fk_net* net);
+int tc_pack_weights(fk_net* net, cudaStream_t s);
+int64_t tc_log_psi_workspace_bytes(const fk_net* net, int64_t n);
+int tc_log_psi(fk_net* net, const int8_t* sigma, int64_t n, float* log_psi_out, void* ws, int64_t ws_bytes,
+               cudaStream_t s);
+
+}  // namespace fk

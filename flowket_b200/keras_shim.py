@@ -1,0 +1,79 @@
+"""Minimal stand-ins for the two tf.keras objects FlowKet scripts touch on this path:
+`Input(shape, dtype)` and `Model(inputs, outputs)` with `.predict/.input_shape/.get_weights/...`
+("machine" row).  No Keras, no TensorFlow: `predict` runs the CUDA layer program."""
+import numpy as np
+
+from . import _lib
+
+
+class Input(object):
+    def __init__(self, shape, dtype='int8', name=None):
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = dtype
+        self.name = name or 'input_1'
+
+
+class Model(object):
+    def __init__(self, inputs, outputs, name=None):
+        from .machines.abstract_machine import SymbolicOutput
+        if isinstance(inputs, (list, tuple)):
+            inputs = inputs[0]
+        if isinstance(outputs, (list, tuple)):
+            outputs = outputs[0]
+        if not isinstance(outputs, SymbolicOutput):
+            raise TypeError('Model(outputs=...) must be a machine output such as machine.predictions')
+        if outputs.machine.keras_input_layer is not inputs:
+            raise ValueError('Model inputs do not match the machine input layer')
+        self.input = inputs
+        self.output = outputs
+        self.machine = outputs.machine
+        self.output_kind = outputs.kind
+        self.name = name or 'model'
+        self.engine = _lib.FK_ENGINE_FP32   # wave-function engine used by predict / local energy
+
+    # ---- shape / weights (Keras names) ----------------------------------------------------------------
+    @property
+    def input_shape(self):
+        return (None,) + self.input.shape
+
+    @property
+    def input_names(self):
+        return [self.input.name]
+
+    @property
+    def output_shape(self):
+        return (None, 1) if self.output_kind == 'predictions' else (None,) + self.input.shape + (2,)
+
+    @property
+    def weights(self):
+        return [name for name, _, _ in self.machine.weight_specs()]
+
+    def count_params(self):
+        return self.machine.count_params()
+
+    def get_weights(self):
+        return self.machine.get_weights()
+
+    def set_weights(self, weights):
+        self.machine.set_weights(weights)
+
+    def save_weights(self, path):
+        np.savez(path, **{'w%04d' % i: w for i, w in enumerate(self.get_weights())})
+
+    def load_weights(self, path):
+        if str(path).endswith('.h5'):
+            from .utils.keras_h5 import read_keras_weights
+            self.set_weights(read_keras_weights(path, self.machine.weight_specs()))
+            return
+        with np.load(path if str(path).endswith('.npz') else str(path) + '.npz') as f:
+            self.set_weights([f['w%04d' % i] for i in range(len(f.files))])
+
+    # ---- evaluation --------------------------------------------------------------------------------------
+    def predict_device(self, x, batch_size=None):
+        """torch CUDA tensor: complex64 [n,1] (predictions) or fp32 [n,*shape,2] (conditional_log_probs)."""
+        return self.machine.evaluate(self.output_kind, x, batch_size=batch_size, engine=self.engine)
+
+    def predict(self, x, batch_size=None, **_unused):
+        return self.predict_device(x, batch_size=batch_size).cpu().numpy()
+
+    __call__ = predict

@@ -1,0 +1,50 @@
+"""Multi-GPU VMC: replaces HorovodVariationalMonteCarlo (flowket/optimization/horovod_variational_monte_carlo.py:10-26).
+
+One process per GPU (torchrun); every rank samples and evaluates its own shard; ONE fp64 allreduce(sum) of
+{sum Re E_loc, sum Im E_loc, sum (Re E_loc)^2, count} replaces Horovod's two scalar averages, so the mean is a
+true global mean (sum / count), independent of the number of ranks, and the variance is reduced too."""
+import numpy
+
+from .variational_monte_carlo import VariationalMonteCarlo
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if (dist.is_available() and dist.is_initialized()) else None
+
+
+class DistributedVariationalMonteCarlo(VariationalMonteCarlo):
+    def __init__(self, model, operator, sampler, **kwargs):
+        super(DistributedVariationalMonteCarlo, self).__init__(model, operator, sampler, **kwargs)
+        dist = _dist()
+        self.world_size = dist.get_world_size() if dist else 1
+        self.rank = dist.get_rank() if dist else 0
+        self.global_batch_size = self.batch_size * self.world_size
+
+    @staticmethod
+    def reduce_stats(local_energy):
+        """local complex E_loc array -> (global mean, global var(Re), global count) via one allreduce."""
+        import torch
+        lv = numpy.asarray(local_energy)
+        stats = torch.tensor([lv.real.sum(), lv.imag.sum(), (lv.real ** 2).sum(), float(lv.size)], dtype=torch.float64)
+        dist = _dist()
+        if dist is not None:
+            if dist.get_backend() == 'nccl':
+                stats = stats.cuda()
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+            stats = stats.cpu()
+        s_re, s_im, s_sq, n = [float(v) for v in stats]
+        mean = complex(s_re / n, s_im / n)
+        return mean, s_sq / n - (s_re / n) ** 2, int(n)
+
+    def _update_batch_local_energy(self):
+        _, _, self.current_local_energy = self._estimate()
+        self.current_energy, self.current_local_energy_variance, self.global_count = \
+            self.reduce_stats(self.current_local_energy)
+
+    def next_batch(self):
+        batch, _ = super(DistributedVariationalMonteCarlo, self).next_batch()
+        return batch, self.loss_coefficients() / self.global_batch_size
+
+
+HorovodVariationalMonteCarlo = DistributedVariationalMonteCarlo

@@ -1,0 +1,80 @@
+"""Thin host loop standing in for Keras `fit_generator` + `train_on_batch` on this path
+(SURVEY.md section 3.1): pull a mini-batch (sigma, y) from the generator, differentiate
+loss_for_energy_minimization on the device (fk_grad_weighted), allreduce, apply the update.
+
+Keras' mean over the mini-batch (optimization/loss.py:4-5 + Keras reduction) is kept: grad = (1/mb) * sum_b ...
+Gradients of the `update_params_frequency` mini-batches of one batch are summed before the update, like
+convert_to_accumulate_gradient_optimizer (optimizers/accumulate_gradient_optimizer.py:54-82)."""
+import numpy as np
+
+
+def allreduce_sum_(tensor):
+    """In-place sum over ranks (NCCL on CUDA tensors, gloo on CPU tensors); no-op without torch.distributed."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(tensor, op=dist.ReduceOp.SUM)
+    return tensor
+
+
+class SGD(object):
+    def __init__(self, lr=0.01):
+        self.lr = lr
+
+    def step(self, params, grad):
+        params.add_(grad, alpha=-self.lr)
+
+
+class Adam(object):
+    """Adam with Keras defaults (epsilon 1e-7); the paper runs use beta_1 = beta_2 = 0.9 (experiments/train.py:52)."""
+
+    def __init__(self, lr=0.001, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        self.lr, self.beta_1, self.beta_2, self.epsilon = lr, beta_1, beta_2, epsilon
+        self.t, self.m, self.v = 0, None, None
+
+    def step(self, params, grad):
+        import torch
+        if self.m is None:
+            self.m, self.v = torch.zeros_like(params), torch.zeros_like(params)
+        self.t += 1
+        self.m.mul_(self.beta_1).add_(grad, alpha=1 - self.beta_1)
+        self.v.mul_(self.beta_2).addcmul_(grad, grad, value=1 - self.beta_2)
+        lr_t = self.lr * np.sqrt(1 - self.beta_2 ** self.t) / (1 - self.beta_1 ** self.t)
+        params.addcdiv_(self.m, self.v.sqrt().add_(self.epsilon), value=-lr_t)
+
+
+class Trainer(object):
+    def __init__(self, model, generator, optimizer, distributed=False):
+        self.model, self.generator, self.optimizer, self.distributed = model, generator, optimizer, distributed
+        self.machine = model.machine
+        self.history = []
+
+    def gradient(self, x, y):
+        """(1/mb) d/dtheta sum_b 2 Re(log psi_b y_b) on the device."""
+        import torch
+        net = self.machine.device_net()
+        sigma = net.to_sigma(x)
+        y_t = torch.as_tensor(np.asarray(y, np.complex64)) if not hasattr(y, 'is_cuda') else y
+        return net.grad_weighted(sigma, y_t) / float(sigma.shape[0])
+
+    def train_step(self):
+        """One parameter update = `update_params_frequency` mini-batches of the generator."""
+        gen = self.generator
+        freq = getattr(gen, 'update_params_frequency', 1)
+        grad = None
+        for _ in range(freq):
+            x, y = next(gen)
+            g = self.gradient(x, y)
+            grad = g if grad is None else grad.add_(g)
+        if self.distributed:
+            allreduce_sum_(grad)
+        params = self.machine.flat_params_device()
+        self.optimizer.step(params, grad)
+        self.machine.params_updated()
+        energy = getattr(gen, 'current_energy', None)
+        self.history.append(energy)
+        return energy
+
+    def fit(self, steps):
+        for _ in range(steps):
+            self.train_step()
+        return self.history
