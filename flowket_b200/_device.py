@@ -53,7 +53,7 @@ class DeviceNet(object):
             t = x.to(device=self.device)
         else:
             t = torch.from_numpy(np.ascontiguousarray(np.asarray(x).astype(np.int8, copy=False))).to(self.device)
-        return t.to(torch.int8).reshape(t.shape[0], -1).contiguous()
+        return t.to(torch.int8).reshape(t.shape[0], self.sites).contiguous()
 
     # ---- entry points -----------------------------------------------------------------------------------
     def set_params(self, flat):
