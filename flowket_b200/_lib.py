@@ -33,6 +33,7 @@ class FkOperator(ctypes.Structure):
 SIGNATURES = {
     'fk_last_error': (ctypes.c_char_p, []),
     'fk_version': (c_int, []),
+    'fk_launch_count': (c_int64, []),
     'fk_net_create': (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     'fk_net_destroy': (c_int, [c_void_p]),
     'fk_net_num_params': (c_int, [c_void_p, ctypes.POINTER(c_int64)]),

@@ -29,7 +29,12 @@ void set_error(const char* fmt, ...);
     }                              \
   } while (0)
 
-#define FK_CHECK_LAUNCH() FK_CHECK_CUDA(cudaGetLastError())
+void count_launch();
+#define FK_CHECK_LAUNCH()               \
+  do {                                  \
+    fk::count_launch();                 \
+    FK_CHECK_CUDA(cudaGetLastError());  \
+  } while (0)
 
 constexpr int ACT_NONE = 0;
 constexpr int ACT_RELU = 1;

@@ -8,12 +8,16 @@
 #include <stdarg.h>
 
 #include <algorithm>
+#include <atomic>
 
 #include "fk_net.cuh"
 
 namespace fk {
 
 static thread_local char g_error[1024] = "";
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -401,6 +405,7 @@ using namespace fk;
 // ------------------------------------------------------------------------------------------------
 extern "C" const char* fk_last_error(void) { return fk::g_error; }
 extern "C" int fk_version(void) { return 100; }
+extern "C" int64_t fk_launch_count(void) { return fk::g_launches.load(); }
 
 extern "C" int fk_net_create(fk_net_t** out, int kind, int H, int W, int depth, int channels, int kernel_size,
                              int max_dilation, int flags) {

@@ -79,6 +79,8 @@ typedef struct {
 
 const char* fk_last_error(void);
 int fk_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py reports it as gpu_launches) */
+int64_t fk_launch_count(void);
 
 /* ---- machine ------------------------------------------------------------------------------------
  * Replaces the Keras graph built by ConvNetAutoregressive2D.__init__ (machines/conv_net_autoregressive_2D.py:11-74),
