@@ -286,7 +286,7 @@ def run_gpu(args):
     line = {
         'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'bf16' if args.engine == 'tc' else 'f32', 'data': 'synthetic',
+        'dtype': 'f16 operands / f32 accumulate' if args.engine == 'tc' else 'f32', 'data': 'synthetic',
         'config': workload_config(args, world),
         'phases_ms': {k: float(np.min(v)) for k, v in phase_ms.items()},
         'sampling_samples_per_s': B * world / (float(np.min(phase_ms['sample'])) * 1e-3),

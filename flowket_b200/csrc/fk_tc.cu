@@ -1,12 +1,664 @@
-// tensor-core engine placeholder (replaced by the tcgen05 fused network kernel)
+// Tensor-core engine: the whole ConvNetAutoregressive2D forward (all 2*depth-2 blocks + head + log-space
+// normalisation + one-hot combine) of a configuration in ONE persistent kernel on tcgen05 tensor cores.
+//
+//   * activations never leave the SM: fp16 tiles in shared memory in the UMMA canonical K-major / no-swizzle
+//     layout [channel group of 8][padded position][8 channels]; a conv tap is a *shifted view* of the same
+//     tile (descriptor start address + tap offset * 16 B), so the 3x3 / 1x3 / shifted 1x1 masked convolutions
+//     are implicit GEMMs with M = 128 padded positions, N = 32 (or 16), K = 16 per tcgen05.mma, no im2col;
+//   * accumulators live in TMEM; 128 epilogue threads (one TMEM lane = one lattice position each) apply
+//     bias / residual / relu / zero-padding mask, round to fp16 and write the next layer's operand tile;
+//   * weights: one pre-packed fp16 image per block (UMMA canonical layout), double-buffered in shared memory
+//     and streamed from L2 with cp.async.bulk + mbarrier complete_tx while the previous block computes;
+//   * two independent pipelines (256 threads) per CTA process two configurations; while one pipeline's
+//     epilogue runs, the other's MMAs occupy the tensor core;
+//   * the last epilogue fuses the head: logits -> log-space normalisation -> select by sigma -> sum over sites.
+//
+// Semantics: machines/conv_net_autoregressive_2D.py:24-74, machines/abstract_machine.py:31-57,
+// deepar/layers/autoregressive.py:7-22 (same wiring as the fp32 layer program in fk_net.cu).
+// Numerics: fp16 operands (11-bit significand: 8x tighter than bf16 at the same tensor-core rate; activations are
+// O(1) post-relu values, conversions saturate), fp32 accumulation / bias / residual / normalisation.
+// Tolerance stated in DESIGN.md and tests/test_gpu_tc.py.
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
 #include "fk_net.cuh"
+
 namespace fk {
-int tc_supported(const fk_net* net) { (void)net; return 0; }
-int tc_pack_weights(fk_net* net, cudaStream_t s) { (void)net; (void)s; return 0; }
-int64_t tc_log_psi_workspace_bytes(const fk_net* net, int64_t n) { (void)net; (void)n; return 256; }
-int tc_log_psi(fk_net* net, const int8_t* sigma, int64_t n, float* out, void* ws, int64_t ws_bytes, cudaStream_t s) {
-  (void)net; (void)sigma; (void)n; (void)out; (void)ws; (void)ws_bytes; (void)s;
-  set_error("tensor-core engine not built");
-  return 1;
+
+constexpr int IMG_V = 0;              // 9 taps x 2 k-steps x 1024 B   (N = 32)
+constexpr int IMG_X = 18432;          // 3 x 2 x 1024 B
+constexpr int IMG_XX = 24576;         // 2 k-steps x 512 B             (N = 16)
+constexpr int IMG_Y = 25600;          // 2 x 512 B
+constexpr int IMG_H = 26624;          // 9 x 2 x 1024 B
+constexpr int IMG_BIAS = 45056;       // 128 floats: V[32] X[32] XX[16] Y[16] H[32]
+constexpr int IMG_HEAD = 45568;       // 2 x 512 B (N = 16, columns 0..3 used)
+constexpr int IMG_HEAD_BIAS = 46592;  // 16 floats
+constexpr int IMG_BYTES = 46656;
+constexpr int TC_SLOTS = 5;
+
+struct TcBlockDesc {
+  int8_t in_v, in_h, out_a, out_r, res_v, x1, c, out_h, res_h, last, pad0, pad1;
+};
+
+struct TcPackDesc {
+  long long w[5], b[5];  // V, X, XX, Y, H offsets into the effective-weight buffer
+  long long w_head, b_head;
+  int cin;               // 1 for the first block
+};
+
+// ---- weight packing: fp32 effective weights [tap][ci][co] -> fp16 UMMA canonical K-major B tiles -----------
+__global__ void tc_pack_kernel(const float* __restrict__ weff, const TcPackDesc* __restrict__ pd,
+                               uint8_t* __restrict__ images) {
+  const TcPackDesc d = pd[blockIdx.x];
+  uint8_t* img = images + (size_t)blockIdx.x * IMG_BYTES;
+  __half* w16 = reinterpret_cast<__half*>(img);
+  // region table: (byte offset, taps, N, op index, cin)
+  const int reg_off[6] = {IMG_V, IMG_X, IMG_XX, IMG_Y, IMG_H, IMG_HEAD};
+  const int reg_taps[6] = {9, 3, 1, 1, 9, 1};
+  const int reg_n[6] = {32, 32, 16, 16, 32, 16};
+  for (int r = 0; r < 6; ++r) {
+    const int N = reg_n[r], taps = reg_taps[r];
+    const int cin = (r == 0 || r == 1) ? d.cin : 32;
+    const int nreal = (r == 5) ? 4 : N;
+    const long long woff = (r == 5) ? d.w_head : d.w[r];
+    const int total = taps * 2 * 2 * N * 8;  // (tap, kstep, kgroup, n, e)
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+      const int el = e & 7;
+      const int n = (e >> 3) % N;
+      const int g = ((e >> 3) / N) & 1;
+      const int ks = ((e >> 3) / N / 2) & 1;
+      const int tap = (e >> 3) / N / 4;
+      const int ci = ks * 16 + g * 8 + el;
+      float v = 0.f;
+      if (ci < cin && n < nreal) v = weff[woff + ((long long)tap * cin + ci) * nreal + n];
+      w16[reg_off[r] / 2 + e] = __float2half_rn(v);
+    }
+  }
+  float* bias = reinterpret_cast<float*>(img + IMG_BIAS);
+  const int boff[5] = {0, 32, 64, 80, 96}, bn[5] = {32, 32, 16, 16, 32};
+  for (int r = 0; r < 5; ++r)
+    for (int i = threadIdx.x; i < bn[r]; i += blockDim.x) bias[boff[r] + i] = weff[d.b[r] + i];
+  float* hb = reinterpret_cast<float*>(img + IMG_HEAD_BIAS);
+  for (int i = threadIdx.x; i < 16; i += blockDim.x) hb[i] = i < 4 ? weff[d.b_head + i] : 0.f;
 }
+
+// ---- PTX helpers ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();  // a lost arrival must abort the kernel, never hang the GPU
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B, rows 16 B apart;
+// LBO = distance between the two K halves of one MMA, SBO = distance between 8-row groups (both in 16 B units)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo16, uint32_t sbo16) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(lbo16 & 0x3FFF) << 16) | ((uint64_t)(sbo16 & 0x3FFF) << 32) |
+         (1ull << 46);
+}
+// instruction descriptor: D = F32 (c_format 1), A = B = F16 (a/b_format 0), both K-major, M = 128
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// two fp32 -> packed fp16x2 (round to nearest, saturating to +-65504 instead of overflowing to inf)
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ void unpack_h8(const uint4& q, float* f) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+    const float2 t = __half22float2(h);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+struct TcArgs {
+  const uint8_t* images;
+  const TcBlockDesc* desc;
+  const int8_t* sigma;
+  float* out;
+  long long n;
+  int H, W, P, nb, T, npos, p_first, np, tmem_cols;
+};
+
+constexpr int TC_MAX_T = 3;
+
+__global__ void __launch_bounds__(256, 1) tc_forward_kernel(TcArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x;
+  const int pipe = tid >> 7, ltid = tid & 127, warp = tid >> 5, lane = tid & 31;
+  const int buf_bytes = 64 * a.npos;  // 4 channel groups x npos x 16 B
+  uint8_t* wbuf = smem;
+  uint8_t* act0 = smem + 2 * IMG_BYTES;
+  uint8_t* tail = act0 + (size_t)a.np * TC_SLOTS * buf_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);          // [0,1] weights, [2,3] per-pipeline MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 64);
+  float* red = reinterpret_cast<float*>(tail + 128);            // [np][4 warps][2]
+  TcBlockDesc* sdesc = reinterpret_cast<TcBlockDesc*>(tail + 256);
+
+  const uint32_t wbar0 = smem_u32(&bars[0]);
+  const uint32_t mbar = smem_u32(&bars[2 + pipe]);
+
+  if (tid == 32) {  // (not warp 0: it must reach the .sync.aligned TMEM allocation converged)
+    mbar_init(wbar0, 1);
+    mbar_init(wbar0 + 8, 1);
+    for (int p = 0; p < a.np; ++p) mbar_init(smem_u32(&bars[2 + p]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)a.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < a.nb; i += blockDim.x) sdesc[i] = a.desc[i];
+  {  // zero every activation tile once: padding rows / slack positions are never written afterwards
+    uint4* z = reinterpret_cast<uint4*>(act0);
+    const int n16 = a.np * TC_SLOTS * buf_bytes / 16;
+    for (int i = tid; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_pipe = tmem_base + (uint32_t)(pipe * a.T * 128);
+  const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+
+  const long long groups = (a.n + a.np - 1) / a.np;  // configuration groups (one per CTA iteration)
+  if (tid == 0 && (long long)blockIdx.x < groups) {
+    mbar_expect_tx(wbar0, IMG_BYTES);
+    bulk_g2s(smem_u32(wbuf), a.images, IMG_BYTES, wbar0);
+    mbar_expect_tx(wbar0 + 8, IMG_BYTES);
+    bulk_g2s(smem_u32(wbuf + IMG_BYTES), a.images + (size_t)(1 % a.nb) * IMG_BYTES, IMG_BYTES, wbar0 + 8);
+  }
+
+  uint8_t* act = act0 + (size_t)pipe * TC_SLOTS * buf_bytes;
+  const uint32_t act_s = smem_u32(act);
+  const int HW = a.H * a.W;
+  const uint32_t idesc32 = make_idesc(32), idesc16 = make_idesc(16);
+
+  // geometry of this thread's rows (one per M tile)
+  int pos[TC_MAX_T], site[TC_MAX_T];
+#pragma unroll
+  for (int t = 0; t < TC_MAX_T; ++t) {
+    pos[t] = a.p_first + t * 128 + ltid;
+    const int r = pos[t] / a.P - 2, c = pos[t] % a.P - 2;
+    site[t] = (t < a.T && c >= 0 && r < a.H) ? r * a.W + c : -1;
+  }
+
+  uint32_t mma_phase = 0;
+  long long step = 0;  // weight-pipeline step: block (step % nb) lives in buffer (step & 1)
+
+  // epilogue store of 32 channels of one position
+  auto store_row = [&](int slot, int p, const float* v) {
+    uint8_t* base = act + (size_t)slot * buf_bytes + (size_t)p * 16;
+#pragma unroll
+    for (int cg = 0; cg < 4; ++cg) {
+      uint4 q;
+      q.x = pack_h2(v[8 * cg + 0], v[8 * cg + 1]);
+      q.y = pack_h2(v[8 * cg + 2], v[8 * cg + 3]);
+      q.z = pack_h2(v[8 * cg + 4], v[8 * cg + 5]);
+      q.w = pack_h2(v[8 * cg + 6], v[8 * cg + 7]);
+      *reinterpret_cast<uint4*>(base + (size_t)cg * a.npos * 16) = q;
+    }
+  };
+  auto load_row = [&](int slot, int p, float* v) {
+    const uint8_t* base = act + (size_t)slot * buf_bytes + (size_t)p * 16;
+#pragma unroll
+    for (int cg = 0; cg < 4; ++cg) {
+      const uint4 q = *reinterpret_cast<const uint4*>(base + (size_t)cg * a.npos * 16);
+      unpack_h8(q, v + 8 * cg);
+    }
+  };
+  // one conv: `taps` shifted views of slot `src`, 2 k-steps each, accumulated into TMEM columns col0..col0+N
+  auto issue_conv = [&](int src, const int* offs, int taps, uint32_t wsm, int nout, uint32_t col0) {
+    const uint32_t idesc = nout == 32 ? idesc32 : idesc16;
+    const uint32_t wstep = nout * 32;  // bytes per (tap, k-step) weight tile
+    for (int t = 0; t < a.T; ++t) {
+      const uint32_t d_tmem = tm_pipe + (uint32_t)(t * 128) + col0;
+      uint32_t acc = 0;
+      for (int tap = 0; tap < taps; ++tap) {
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint32_t a_addr = act_s + (uint32_t)src * buf_bytes +
+                                  (uint32_t)((ks * 2) * a.npos + a.p_first + t * 128 + offs[tap]) * 16u;
+          const uint32_t b_addr = wsm + (uint32_t)(tap * 2 + ks) * wstep;
+          umma_f16(d_tmem, make_desc(a_addr, a.npos, 8), make_desc(b_addr, nout, 8), idesc, acc);
+          acc = 1;
+        }
+      }
+    }
+  };
+
+  for (long long it = 0;; ++it) {
+    const long long group = it * gridDim.x + blockIdx.x;
+    if (group >= groups) break;
+    const long long cfg = group * a.np + pipe;
+    const bool active = cfg < a.n;
+    const bool more = (group + gridDim.x) < groups;
+
+    // ---- input embedding: channel 0 = sigma, channels 1..31 = 0, padding positions = 0
+    float sig[TC_MAX_T];
+    {
+      const int in_slot = sdesc[0].in_v;
+#pragma unroll
+      for (int t = 0; t < TC_MAX_T; ++t) {
+        if (t >= a.T) break;
+        sig[t] = (active && site[t] >= 0) ? (float)a.sigma[cfg * HW + site[t]] : 0.f;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        v[0] = sig[t];
+        store_row(in_slot, pos[t], v);
+      }
+    }
+    fence_proxy_async();
+    named_sync(1 + pipe, 128);
+
+    for (int b = 0; b < a.nb; ++b, ++step) {
+      const TcBlockDesc d = sdesc[b];
+      const uint32_t wsel = (uint32_t)(step & 1);
+      mbar_wait(wbar0 + 8 * wsel, (uint32_t)((step >> 1) & 1));
+      const uint8_t* wimg = wbuf + (size_t)wsel * IMG_BYTES;
+      const uint32_t wimg_s = smem_u32(wimg);
+      const float* bias = reinterpret_cast<const float*>(wimg + IMG_BIAS);
+
+      // ================= phase 1: 1x3 conv on h (cols 0..31) and 3x3 conv on v (cols 32..63)
+      if (ltid == 0) {
+        tc_fence_after();
+        int offs[9];
+        offs[0] = -2; offs[1] = -1; offs[2] = 0;
+        issue_conv(d.in_h, offs, 3, wimg_s + IMG_X, 32, 0);
+        for (int i = 0; i < 3; ++i)
+          for (int j = 0; j < 3; ++j) offs[i * 3 + j] = (i - 2) * a.P + (j - 1);
+        issue_conv(d.in_v, offs, 9, wimg_s + IMG_V, 32, 32);
+        umma_commit(mbar);
+      }
+      mbar_wait(mbar, mma_phase);
+      mma_phase ^= 1;
+      tc_fence_after();
+#pragma unroll
+      for (int t = 0; t < TC_MAX_T; ++t) {
+        if (t >= a.T) break;
+        float v[32];
+        tmem_ld32(tm_pipe + lane_sel + (uint32_t)(t * 128) + 0, v);
+        if (site[t] >= 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bias[32 + i], 0.f);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        store_row(d.x1, pos[t], v);
+        tmem_ld32(tm_pipe + lane_sel + (uint32_t)(t * 128) + 32, v);
+        if (site[t] >= 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += bias[i];
+          if (d.out_r >= 0) {
+            float r[32];
+            load_row(d.res_v, pos[t], r);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = fmaxf(r[i] + v[i], 0.f);
+            store_row(d.out_r, pos[t], r);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          if (d.out_r >= 0) store_row(d.out_r, pos[t], v);
+        }
+        store_row(d.out_a, pos[t], v);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      named_sync(1 + pipe, 128);
+
+      // ================= phase 2: the two 1x1 convs (C -> C/2): x1 (RightShift in the last block) and
+      //                   DownShift(relu(v')) -> concat tensor (cols 64..95)
+      if (ltid == 0) {
+        tc_fence_after();
+        int off1[1] = {d.last ? -1 : 0};
+        issue_conv(d.x1, off1, 1, wimg_s + IMG_XX, 16, 64);
+        int off2[1] = {-a.P};
+        issue_conv(d.out_a, off2, 1, wimg_s + IMG_Y, 16, 80);
+        umma_commit(mbar);
+      }
+      mbar_wait(mbar, mma_phase);
+      mma_phase ^= 1;
+      tc_fence_after();
+#pragma unroll
+      for (int t = 0; t < TC_MAX_T; ++t) {
+        if (t >= a.T) break;
+        float v[32];
+        tmem_ld32(tm_pipe + lane_sel + (uint32_t)(t * 128) + 64, v);
+        if (site[t] >= 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bias[64 + i], 0.f);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        store_row(d.c, pos[t], v);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      named_sync(1 + pipe, 128);
+
+      // ================= phase 3: 3x3 conv on the concat tensor (cols 96..127), residual, relu
+      if (ltid == 0) {
+        tc_fence_after();
+        int offs[9];
+        for (int i = 0; i < 3; ++i)
+          for (int j = 0; j < 3; ++j) offs[i * 3 + j] = (i - 2) * a.P + (j - 2);
+        issue_conv(d.c, offs, 9, wimg_s + IMG_H, 32, 96);
+        umma_commit(mbar);
+      }
+      mbar_wait(mbar, mma_phase);
+      mma_phase ^= 1;
+      tc_fence_after();
+#pragma unroll
+      for (int t = 0; t < TC_MAX_T; ++t) {
+        if (t >= a.T) break;
+        float v[32];
+        tmem_ld32(tm_pipe + lane_sel + (uint32_t)(t * 128) + 96, v);
+        if (site[t] >= 0) {
+          if (d.res_h >= 0) {
+            float r[32];
+            load_row(d.res_h, pos[t], r);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += r[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bias[96 + i], 0.f);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        }
+        store_row(d.out_h, pos[t], v);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      named_sync(1 + pipe, 128);
+
+      // ================= phase 4 (last block): head 1x1 conv (C -> 4) + normalisation + combine
+      if (d.last) {
+        const float* hb = reinterpret_cast<const float*>(wimg + IMG_HEAD_BIAS);
+        if (ltid == 0) {
+          tc_fence_after();
+          int off0[1] = {0};
+          issue_conv(d.out_h, off0, 1, wimg_s + IMG_HEAD, 16, 0);
+          umma_commit(mbar);
+        }
+        mbar_wait(mbar, mma_phase);
+        mma_phase ^= 1;
+        tc_fence_after();
+        float sre = 0.f, sim = 0.f;
+#pragma unroll
+        for (int t = 0; t < TC_MAX_T; ++t) {
+          if (t >= a.T) break;
+          float v[16];
+          tmem_ld16(tm_pipe + lane_sel + (uint32_t)(t * 128) + 0, v);
+          if (site[t] >= 0) {
+            const float re0 = v[0] + hb[0], re1 = v[1] + hb[1], im0 = v[2] + hb[2], im1 = v[3] + hb[3];
+            const float x = 2.f * re0, y = 2.f * re1;
+            const float m = fmaxf(x, y);
+            const float half_lse = 0.5f * (m + logf(expf(x - m) + expf(y - m)));
+            const bool up = sig[t] > 0.f;  // class 0 <-> sigma = +1
+            sre += (up ? re0 : re1) - half_lse;
+            sim += up ? im0 : im1;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          sre += __shfl_xor_sync(0xffffffffu, sre, o);
+          sim += __shfl_xor_sync(0xffffffffu, sim, o);
+        }
+        if (lane == 0) {
+          red[(pipe * 4 + (warp & 3)) * 2 + 0] = sre;
+          red[(pipe * 4 + (warp & 3)) * 2 + 1] = sim;
+        }
+        tc_fence_before();
+        named_sync(1 + pipe, 128);
+        if (ltid == 0 && active) {
+          float r0 = 0.f, r1 = 0.f;
+          for (int w = 0; w < 4; ++w) {
+            r0 += red[(pipe * 4 + w) * 2 + 0];
+            r1 += red[(pipe * 4 + w) * 2 + 1];
+          }
+          a.out[2 * cfg + 0] = r0;
+          a.out[2 * cfg + 1] = r1;
+        }
+      }
+
+      // ================= end of block: both pipelines are done with this weight image -> refill it
+      __syncthreads();
+      if (tid == 0) {
+        const long long nxt = step + 2;
+        const bool need = (b + 2 < a.nb) || more;
+        if (need) {
+          mbar_expect_tx(wbar0 + 8 * wsel, IMG_BYTES);
+          bulk_g2s(smem_u32(wbuf + (size_t)wsel * IMG_BYTES), a.images + (size_t)(nxt % a.nb) * IMG_BYTES, IMG_BYTES,
+                   wbar0 + 8 * wsel);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+struct TcGeometry {
+  int P, p_first, T, npos, np, tmem_cols;
+  size_t smem_bytes;
+  bool ok;
+};
+
+static TcGeometry tc_geometry(const fk_net* net) {
+  TcGeometry g;
+  g.P = net->W + 2;
+  g.p_first = 2 * g.P + 2;
+  const int p_last = (net->H + 1) * g.P + net->W + 1;  // position of site (H-1, W-1)
+  g.T = (p_last - g.p_first + 1 + 127) / 128;
+  g.npos = ((g.p_first + g.T * 128 + 2) + 7) / 8 * 8;
+  const size_t buf = (size_t)64 * g.npos;
+  const size_t tail = 256 + sizeof(TcBlockDesc) * (size_t)(2 * net->depth - 2) + 64;
+  g.np = 2;
+  g.ok = g.T <= TC_MAX_T;
+  for (;;) {
+    g.smem_bytes = 2 * (size_t)IMG_BYTES + (size_t)g.np * TC_SLOTS * buf + tail;
+    const int cols = g.np * g.T * 128;
+    if (g.smem_bytes <= 227 * 1024 && cols <= 512) break;
+    if (g.np == 1) { g.ok = false; break; }
+    g.np = 1;
+  }
+  int cols = g.np * g.T * 128;
+  g.tmem_cols = cols <= 128 ? 128 : (cols <= 256 ? 256 : 512);
+  return g;
+}
+
+int tc_supported(const fk_net* net) {
+  if (net->kind != FK_NET_CONV2D || net->C != 32 || net->k != 3) return 0;
+  return tc_geometry(net).ok ? 1 : 0;
+}
+
+// device buffer layout: [nb weight images][nb TcBlockDesc][nb TcPackDesc], each region 256 B aligned
+static size_t align256z(size_t x) { return (x + 255) / 256 * 256; }
+static size_t tc_desc_offset(int nb) { return align256z((size_t)nb * IMG_BYTES); }
+static size_t tc_pack_offset(int nb) { return tc_desc_offset(nb) + align256z(sizeof(TcBlockDesc) * nb); }
+
+int tc_pack_weights(fk_net* net, cudaStream_t s) {
+  const int nb = 2 * net->depth - 2;
+  const size_t total = tc_pack_offset(nb) + sizeof(TcPackDesc) * nb;
+  if (!net->d_tc_weights) {
+    FK_CHECK_CUDA(cudaMalloc(&net->d_tc_weights, total));
+    net->tc_weight_bytes = (int64_t)total;
+    // residual / buffer wiring -> shared-memory slots (reference counting; residual adds are done in place)
+    std::vector<TcBlockDesc> desc(nb);
+    int rc[TC_SLOTS] = {0, 0, 0, 0, 0};
+    auto get = [&]() {
+      for (int i = 0; i < TC_SLOTS; ++i)
+        if (rc[i] == 0) { rc[i] = 1; return i; }
+      return -1;
+    };
+    const int in = get();
+    rc[in]++;
+    int v = in, h = in, v_pair = -1, h_pair = -1;
+    for (int b = 0; b < nb; ++b) {
+      const bool last = (b == nb - 1);
+      const bool res2 = (b >= 2 && b % 2 == 0 && !last);
+      if (b % 2 == 1 && !last) { v_pair = v; h_pair = h; rc[v]++; rc[h]++; }
+      TcBlockDesc d;
+      d.in_v = (int8_t)v; d.in_h = (int8_t)h; d.last = last ? 1 : 0; d.pad0 = d.pad1 = 0;
+      const int x1 = get();
+      rc[h]--;
+      const int a1 = get();
+      d.out_r = d.res_v = (int8_t)(res2 ? v_pair : -1);
+      rc[v]--;
+      const int c = get();
+      rc[x1]--;
+      int v_next = a1;
+      if (res2) { rc[a1]--; v_next = v_pair; }
+      int hn;
+      if (res2) { hn = h_pair; d.res_h = (int8_t)h_pair; } else { hn = get(); d.res_h = -1; }
+      rc[c]--;
+      FK_REQUIRE(x1 >= 0 && a1 >= 0 && c >= 0 && hn >= 0, "tc_pack_weights: out of shared-memory activation slots");
+      d.x1 = (int8_t)x1; d.out_a = (int8_t)a1; d.c = (int8_t)c; d.out_h = (int8_t)hn;
+      desc[b] = d;
+      v = v_next; h = hn;
+    }
+    FK_CHECK_CUDA(cudaMemcpy((uint8_t*)net->d_tc_weights + tc_desc_offset(nb), desc.data(), sizeof(TcBlockDesc) * nb,
+                             cudaMemcpyHostToDevice));
+    std::vector<TcPackDesc> pd(nb);
+    for (int b = 0; b < nb; ++b) {
+      const ConvOp* o = &net->ops[5 * b];
+      // program order per block: V, X, XX, Y, H
+      for (int r = 0; r < 5; ++r) { pd[b].w[r] = o[r].w_off; pd[b].b[r] = o[r].b_off; }
+      pd[b].w_head = net->ops.back().w_off; pd[b].b_head = net->ops.back().b_off;
+      pd[b].cin = b == 0 ? 1 : 32;
+    }
+    FK_CHECK_CUDA(cudaMemcpy((uint8_t*)net->d_tc_weights + tc_pack_offset(nb), pd.data(), sizeof(TcPackDesc) * nb,
+                             cudaMemcpyHostToDevice));
+  }
+  const TcPackDesc* d_pd = reinterpret_cast<const TcPackDesc*>((uint8_t*)net->d_tc_weights + tc_pack_offset(nb));
+  tc_pack_kernel<<<nb, 256, 0, s>>>(net->d_weff, d_pd, (uint8_t*)net->d_tc_weights);
+  FK_CHECK_LAUNCH();
+  return 0;
+}
+
+int64_t tc_log_psi_workspace_bytes(const fk_net* net, int64_t n) {
+  (void)net; (void)n;
+  return 256;  // activations live in shared memory / TMEM
+}
+
+int tc_log_psi(fk_net* net, const int8_t* sigma, int64_t n, float* log_psi_out, void* ws, int64_t ws_bytes,
+               cudaStream_t s) {
+  (void)ws; (void)ws_bytes;
+  FK_REQUIRE(net->params_set && net->d_tc_weights, "tensor-core weights were never packed (fk_net_set_params)");
+  if (n == 0) return 0;
+  const TcGeometry g = tc_geometry(net);
+  FK_REQUIRE(g.ok, "tensor-core engine: lattice %dx%d does not fit the shared-memory / TMEM budget", net->H, net->W);
+  const int nb = 2 * net->depth - 2;
+  TcArgs a;
+  a.images = (const uint8_t*)net->d_tc_weights;
+  a.desc = reinterpret_cast<const TcBlockDesc*>((const uint8_t*)net->d_tc_weights + tc_desc_offset(nb));
+  a.sigma = sigma; a.out = log_psi_out; a.n = n;
+  a.H = net->H; a.W = net->W; a.P = g.P; a.nb = nb; a.T = g.T; a.npos = g.npos; a.p_first = g.p_first; a.np = g.np;
+  a.tmem_cols = g.tmem_cols;
+  int dev = 0, sms = 148;
+  FK_CHECK_CUDA(cudaGetDevice(&dev));
+  FK_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long groups = (n + g.np - 1) / g.np;
+  const unsigned grid = (unsigned)std::min<long long>(groups, sms);
+  FK_CHECK_CUDA(cudaFuncSetAttribute(tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+  tc_forward_kernel<<<grid, 128 * g.np, g.smem_bytes, s>>>(a);
+  FK_CHECK_LAUNCH();
+  return 0;
+}
+
 }  // namespace fk

@@ -52,7 +52,7 @@ typedef struct fk_net fk_net_t; /* opaque machine handle */
 
 /* precision / engine selector for the wave-function evaluations of fk_local_energy and fk_log_psi */
 #define FK_ENGINE_FP32 0 /* CUDA-core fp32: the 1e-5 parity contract                                   */
-#define FK_ENGINE_TC 1   /* tcgen05 bf16 tensor-core fused network (ConvNetAutoregressive2D, C = 32)  */
+#define FK_ENGINE_TC 1   /* tcgen05 fp16-operand / fp32-accumulate tensor-core fused network (ConvNetAutoregressive2D, C = 32)  */
 
 typedef struct {
   int32_t site_a;    /* flattened (C-order) site index                       */
