@@ -9,8 +9,9 @@
 //     bias / residual / relu / zero-padding mask, round to fp16 and write the next layer's operand tile;
 //   * weights: one pre-packed fp16 image per block (UMMA canonical layout), double-buffered in shared memory
 //     and streamed from L2 with cp.async.bulk + mbarrier complete_tx while the previous block computes;
-//   * two independent pipelines (256 threads) per CTA process two configurations; while one pipeline's
-//     epilogue runs, the other's MMAs occupy the tensor core;
+//   * up to three independent pipelines (128 threads each) per CTA process one configuration each; while one
+//     pipeline's epilogue runs, the others' MMAs occupy the tensor core; a producer warp refills the weight ring
+//     through full/empty mbarriers, so the pipelines never synchronise with each other;
 //   * the last epilogue fuses the head: logits -> log-space normalisation -> select by sigma -> sum over sites.
 //
 // Semantics: machines/conv_net_autoregressive_2D.py:24-74, machines/abstract_machine.py:31-57,
@@ -35,7 +36,7 @@ constexpr int IMG_BIAS = 45056;       // 128 floats: V[32] X[32] XX[16] Y[16] H[
 constexpr int IMG_HEAD = 45568;       // 2 x 512 B (N = 16, columns 0..3 used)
 constexpr int IMG_HEAD_BIAS = 46592;  // 16 floats
 constexpr int IMG_BYTES = 46656;
-constexpr int TC_SLOTS = 5;
+constexpr int TC_SLOTS = 4;
 
 struct TcBlockDesc {
   int8_t in_v, in_h, out_a, out_r, res_v, x1, c, out_h, res_h, last, pad0, pad1;
@@ -200,28 +201,43 @@ struct TcArgs {
 };
 
 constexpr int TC_MAX_T = 3;
+constexpr int TC_MAX_NP = 3;
 
-__global__ void __launch_bounds__(256, 1) tc_forward_kernel(TcArgs a) {
+// Thread layout: np pipelines x 128 threads (one configuration each) + 1 producer warp (weight images).
+// Barriers: full[2] (weights landed, tx-count), empty[2] (np arrivals: every pipeline is done with the image),
+//           mma[np] (tcgen05.commit of the pipeline's current phase).
+__global__ void __launch_bounds__(TC_MAX_NP * 128 + 32, 1) tc_forward_kernel(TcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
-  const int pipe = tid >> 7, ltid = tid & 127, warp = tid >> 5, lane = tid & 31;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int pipe = tid >> 7, ltid = tid & 127;
+  const bool is_producer = warp == a.np * 4;
   const int buf_bytes = 64 * a.npos;  // 4 channel groups x npos x 16 B
   uint8_t* wbuf = smem;
   uint8_t* act0 = smem + 2 * IMG_BYTES;
   uint8_t* tail = act0 + (size_t)a.np * TC_SLOTS * buf_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);          // [0,1] weights, [2,3] per-pipeline MMA
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);           // full[0..1], empty[2..3], mma[4..6]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 64);
-  float* red = reinterpret_cast<float*>(tail + 128);            // [np][4 warps][2]
-  TcBlockDesc* sdesc = reinterpret_cast<TcBlockDesc*>(tail + 256);
+  float* red = reinterpret_cast<float*>(tail + 128);             // [np][4 warps][2]
+  int* taps = reinterpret_cast<int*>(tail + 256);                // tap offsets in positions: V[9] H[9] X[3]
+  TcBlockDesc* sdesc = reinterpret_cast<TcBlockDesc*>(tail + 384);
 
-  const uint32_t wbar0 = smem_u32(&bars[0]);
-  const uint32_t mbar = smem_u32(&bars[2 + pipe]);
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2]);
+  const uint32_t mbar = smem_u32(&bars[4 + (is_producer ? 0 : pipe)]);
 
   if (tid == 32) {  // (not warp 0: it must reach the .sync.aligned TMEM allocation converged)
-    mbar_init(wbar0, 1);
-    mbar_init(wbar0 + 8, 1);
-    for (int p = 0; p < a.np; ++p) mbar_init(smem_u32(&bars[2 + p]), 1);
+    mbar_init(full0, 1);
+    mbar_init(full0 + 8, 1);
+    mbar_init(empty0, a.np);
+    mbar_init(empty0 + 8, a.np);
+    for (int p = 0; p < a.np; ++p) mbar_init(smem_u32(&bars[4 + p]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        taps[i * 3 + j] = (i - 2) * a.P + (j - 1);      // 3x3 on the vertical stack: pad top 2, left 1, right 1
+        taps[9 + i * 3 + j] = (i - 2) * a.P + (j - 2);  // 3x3 on the concat tensor: pad top 2, left 2
+      }
+    for (int j = 0; j < 3; ++j) taps[18 + j] = j - 2;   // 1x3 on the horizontal stack: pad left 2
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -240,286 +256,278 @@ __global__ void __launch_bounds__(256, 1) tc_forward_kernel(TcArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_pipe = tmem_base + (uint32_t)(pipe * a.T * 128);
-  const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
 
   const long long groups = (a.n + a.np - 1) / a.np;  // configuration groups (one per CTA iteration)
-  if (tid == 0 && (long long)blockIdx.x < groups) {
-    mbar_expect_tx(wbar0, IMG_BYTES);
-    bulk_g2s(smem_u32(wbuf), a.images, IMG_BYTES, wbar0);
-    mbar_expect_tx(wbar0 + 8, IMG_BYTES);
-    bulk_g2s(smem_u32(wbuf + IMG_BYTES), a.images + (size_t)(1 % a.nb) * IMG_BYTES, IMG_BYTES, wbar0 + 8);
-  }
+  const long long my_iters = (long long)blockIdx.x < groups ? (groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-  uint8_t* act = act0 + (size_t)pipe * TC_SLOTS * buf_bytes;
-  const uint32_t act_s = smem_u32(act);
-  const int HW = a.H * a.W;
-  const uint32_t idesc32 = make_idesc(32), idesc16 = make_idesc(16);
-
-  // geometry of this thread's rows (one per M tile)
-  int pos[TC_MAX_T], site[TC_MAX_T];
-#pragma unroll
-  for (int t = 0; t < TC_MAX_T; ++t) {
-    pos[t] = a.p_first + t * 128 + ltid;
-    const int r = pos[t] / a.P - 2, c = pos[t] % a.P - 2;
-    site[t] = (t < a.T && c >= 0 && r < a.H) ? r * a.W + c : -1;
-  }
-
-  uint32_t mma_phase = 0;
-  long long step = 0;  // weight-pipeline step: block (step % nb) lives in buffer (step & 1)
-
-  // epilogue store of 32 channels of one position
-  auto store_row = [&](int slot, int p, const float* v) {
-    uint8_t* base = act + (size_t)slot * buf_bytes + (size_t)p * 16;
-#pragma unroll
-    for (int cg = 0; cg < 4; ++cg) {
-      uint4 q;
-      q.x = pack_h2(v[8 * cg + 0], v[8 * cg + 1]);
-      q.y = pack_h2(v[8 * cg + 2], v[8 * cg + 3]);
-      q.z = pack_h2(v[8 * cg + 4], v[8 * cg + 5]);
-      q.w = pack_h2(v[8 * cg + 6], v[8 * cg + 7]);
-      *reinterpret_cast<uint4*>(base + (size_t)cg * a.npos * 16) = q;
+  if (is_producer) {
+    // =============================== weight producer ===============================
+    const long long total = my_iters * a.nb;
+    for (long long s = 0; s < total; ++s) {   // whole warp walks the loop (it must reach the final barrier converged)
+      if (lane == 0) {
+        const uint32_t sel = (uint32_t)(s & 1);
+        if (s >= 2) mbar_wait(empty0 + 8 * sel, (uint32_t)(((s >> 1) - 1) & 1));
+        mbar_expect_tx(full0 + 8 * sel, IMG_BYTES);
+        bulk_g2s(smem_u32(wbuf + (size_t)sel * IMG_BYTES), a.images + (size_t)(s % a.nb) * IMG_BYTES, IMG_BYTES,
+                 full0 + 8 * sel);
+      }
+      __syncwarp();
     }
-  };
-  auto load_row = [&](int slot, int p, float* v) {
-    const uint8_t* base = act + (size_t)slot * buf_bytes + (size_t)p * 16;
+  } else {
+    // =============================== compute pipelines ===============================
+    const uint32_t tm_pipe = tmem_base + (uint32_t)(pipe * a.T * 128);
+    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+    uint8_t* act = act0 + (size_t)pipe * TC_SLOTS * buf_bytes;
+    const uint32_t act16 = smem_u32(act) >> 4;      // everything below is in 16-byte units
+    const uint32_t buf16 = 4u * (uint32_t)a.npos;
+    const uint32_t kstep16 = 2u * (uint32_t)a.npos;  // two channel groups per k-step
+    const int HW = a.H * a.W;
+    const uint32_t idesc32 = make_idesc(32), idesc16 = make_idesc(16);
+    const uint64_t adesc0 = make_desc(0, a.npos, 8);
+    const uint64_t bdesc32 = make_desc(0, 32, 8), bdesc16 = make_desc(0, 16, 8);
+    const int bar_id = 1 + pipe;
+
+    int pos[TC_MAX_T], site[TC_MAX_T];
 #pragma unroll
-    for (int cg = 0; cg < 4; ++cg) {
-      const uint4 q = *reinterpret_cast<const uint4*>(base + (size_t)cg * a.npos * 16);
-      unpack_h8(q, v + 8 * cg);
+    for (int t = 0; t < TC_MAX_T; ++t) {
+      pos[t] = a.p_first + t * 128 + ltid;
+      const int r = pos[t] / a.P - 2, c = pos[t] % a.P - 2;
+      site[t] = (t < a.T && c >= 0 && r < a.H) ? r * a.W + c : -1;
     }
-  };
-  // one conv: `taps` shifted views of slot `src`, 2 k-steps each, accumulated into TMEM columns col0..col0+N
-  auto issue_conv = [&](int src, const int* offs, int taps, uint32_t wsm, int nout, uint32_t col0) {
-    const uint32_t idesc = nout == 32 ? idesc32 : idesc16;
-    const uint32_t wstep = nout * 32;  // bytes per (tap, k-step) weight tile
-    for (int t = 0; t < a.T; ++t) {
-      const uint32_t d_tmem = tm_pipe + (uint32_t)(t * 128) + col0;
-      uint32_t acc = 0;
-      for (int tap = 0; tap < taps; ++tap) {
+
+    auto store_row = [&](int slot, int p, const float* v) {
+      uint8_t* base = act + (size_t)slot * buf_bytes + (size_t)p * 16;
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const uint32_t a_addr = act_s + (uint32_t)src * buf_bytes +
-                                  (uint32_t)((ks * 2) * a.npos + a.p_first + t * 128 + offs[tap]) * 16u;
-          const uint32_t b_addr = wsm + (uint32_t)(tap * 2 + ks) * wstep;
-          umma_f16(d_tmem, make_desc(a_addr, a.npos, 8), make_desc(b_addr, nout, 8), idesc, acc);
+      for (int cg = 0; cg < 4; ++cg) {
+        uint4 q;
+        q.x = pack_h2(v[8 * cg + 0], v[8 * cg + 1]);
+        q.y = pack_h2(v[8 * cg + 2], v[8 * cg + 3]);
+        q.z = pack_h2(v[8 * cg + 4], v[8 * cg + 5]);
+        q.w = pack_h2(v[8 * cg + 6], v[8 * cg + 7]);
+        *reinterpret_cast<uint4*>(base + (size_t)cg * a.npos * 16) = q;
+      }
+    };
+    auto load_row = [&](int slot, int p, float* v) {
+      const uint8_t* base = act + (size_t)slot * buf_bytes + (size_t)p * 16;
+#pragma unroll
+      for (int cg = 0; cg < 4; ++cg) {
+        const uint4 q = *reinterpret_cast<const uint4*>(base + (size_t)cg * a.npos * 16);
+        unpack_h8(q, v + 8 * cg);
+      }
+    };
+    // one conv = NTAPS shifted views of slot `src` x 2 k-steps, accumulated into TMEM columns col0..col0+N.
+    // Descriptors differ only in the 14-bit start-address field, so each MMA costs a couple of integer adds.
+    auto issue_conv = [&](int src, const int* tap_off, int ntaps, int shift, uint32_t w16, bool n32, uint32_t col0) {
+      const uint32_t idesc = n32 ? idesc32 : idesc16;
+      const uint64_t bd0 = (n32 ? bdesc32 : bdesc16) + w16;
+      const uint32_t wstep = n32 ? 64u : 32u;  // 16-byte units per (tap, k-step) weight tile
+      for (int t = 0; t < a.T; ++t) {
+        const uint32_t d_tmem = tm_pipe + (uint32_t)(t * 128) + col0;
+        const uint64_t ad0 = adesc0 + (uint64_t)(act16 + (uint32_t)src * buf16 + (uint32_t)(a.p_first + t * 128 + shift));
+        uint32_t acc = 0;
+        for (int tap = 0; tap < ntaps; ++tap) {
+          const uint64_t ad = ad0 + (uint64_t)(int64_t)(tap_off ? tap_off[tap] : 0);
+          const uint64_t bd = bd0 + (uint64_t)(tap * 2) * wstep;
+          umma_f16(d_tmem, ad, bd, idesc, acc);
+          umma_f16(d_tmem, ad + kstep16, bd + wstep, idesc, 1u);
           acc = 1;
         }
       }
-    }
-  };
+    };
 
-  for (long long it = 0;; ++it) {
-    const long long group = it * gridDim.x + blockIdx.x;
-    if (group >= groups) break;
-    const long long cfg = group * a.np + pipe;
-    const bool active = cfg < a.n;
-    const bool more = (group + gridDim.x) < groups;
+    uint32_t mma_phase = 0;
+    long long step = 0;  // weight-pipeline step: block (step % nb) lives in buffer (step & 1)
 
-    // ---- input embedding: channel 0 = sigma, channels 1..31 = 0, padding positions = 0
-    float sig[TC_MAX_T];
-    {
-      const int in_slot = sdesc[0].in_v;
-#pragma unroll
-      for (int t = 0; t < TC_MAX_T; ++t) {
-        if (t >= a.T) break;
-        sig[t] = (active && site[t] >= 0) ? (float)a.sigma[cfg * HW + site[t]] : 0.f;
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0.f;
-        v[0] = sig[t];
-        store_row(in_slot, pos[t], v);
-      }
-    }
-    fence_proxy_async();
-    named_sync(1 + pipe, 128);
+    for (long long it = 0; it < my_iters; ++it) {
+      const long long group = it * gridDim.x + blockIdx.x;
+      const long long cfg = group * a.np + pipe;
+      const bool active = cfg < a.n;
 
-    for (int b = 0; b < a.nb; ++b, ++step) {
-      const TcBlockDesc d = sdesc[b];
-      const uint32_t wsel = (uint32_t)(step & 1);
-      mbar_wait(wbar0 + 8 * wsel, (uint32_t)((step >> 1) & 1));
-      const uint8_t* wimg = wbuf + (size_t)wsel * IMG_BYTES;
-      const uint32_t wimg_s = smem_u32(wimg);
-      const float* bias = reinterpret_cast<const float*>(wimg + IMG_BIAS);
-
-      // ================= phase 1: 1x3 conv on h (cols 0..31) and 3x3 conv on v (cols 32..63)
-      if (ltid == 0) {
-        tc_fence_after();
-        int offs[9];
-        offs[0] = -2; offs[1] = -1; offs[2] = 0;
-        issue_conv(d.in_h, offs, 3, wimg_s + IMG_X, 32, 0);
-        for (int i = 0; i < 3; ++i)
-          for (int j = 0; j < 3; ++j) offs[i * 3 + j] = (i - 2) * a.P + (j - 1);
-        issue_conv(d.in_v, offs, 9, wimg_s + IMG_V, 32, 32);
-        umma_commit(mbar);
-      }
-      mbar_wait(mbar, mma_phase);
-      mma_phase ^= 1;
-      tc_fence_after();
+      // ---- input embedding: channel 0 = sigma, channels 1..31 = 0, padding positions = 0
+      float sig[TC_MAX_T];
+      {
+        const int in_slot = sdesc[0].in_v;
 #pragma unroll
-      for (int t = 0; t < TC_MAX_T; ++t) {
-        if (t >= a.T) break;
-        float v[32];
-        tmem_ld32(tm_pipe + lane_sel + (uint32_t)(t * 128) + 0, v);
-        if (site[t] >= 0) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bias[32 + i], 0.f);
-        } else {
+        for (int t = 0; t < TC_MAX_T; ++t) {
+          if (t >= a.T) break;
+          sig[t] = (active && site[t] >= 0) ? (float)a.sigma[cfg * HW + site[t]] : 0.f;
+          float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          v[0] = sig[t];
+          store_row(in_slot, pos[t], v);
         }
-        store_row(d.x1, pos[t], v);
-        tmem_ld32(tm_pipe + lane_sel + (uint32_t)(t * 128) + 32, v);
-        if (site[t] >= 0) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += bias[i];
-          if (d.out_r >= 0) {
-            float r[32];
-            load_row(d.res_v, pos[t], r);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = fmaxf(r[i] + v[i], 0.f);
-            store_row(d.out_r, pos[t], r);
-          }
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0.f;
-          if (d.out_r >= 0) store_row(d.out_r, pos[t], v);
-        }
-        store_row(d.out_a, pos[t], v);
       }
       fence_proxy_async();
-      tc_fence_before();
-      named_sync(1 + pipe, 128);
+      named_sync(bar_id, 128);
 
-      // ================= phase 2: the two 1x1 convs (C -> C/2): x1 (RightShift in the last block) and
-      //                   DownShift(relu(v')) -> concat tensor (cols 64..95)
-      if (ltid == 0) {
-        tc_fence_after();
-        int off1[1] = {d.last ? -1 : 0};
-        issue_conv(d.x1, off1, 1, wimg_s + IMG_XX, 16, 64);
-        int off2[1] = {-a.P};
-        issue_conv(d.out_a, off2, 1, wimg_s + IMG_Y, 16, 80);
-        umma_commit(mbar);
-      }
-      mbar_wait(mbar, mma_phase);
-      mma_phase ^= 1;
-      tc_fence_after();
-#pragma unroll
-      for (int t = 0; t < TC_MAX_T; ++t) {
-        if (t >= a.T) break;
-        float v[32];
-        tmem_ld32(tm_pipe + lane_sel + (uint32_t)(t * 128) + 64, v);
-        if (site[t] >= 0) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bias[64 + i], 0.f);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0.f;
-        }
-        store_row(d.c, pos[t], v);
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      named_sync(1 + pipe, 128);
+      for (int b = 0; b < a.nb; ++b, ++step) {
+        const TcBlockDesc d = sdesc[b];
+        const uint32_t wsel = (uint32_t)(step & 1);
+        mbar_wait(full0 + 8 * wsel, (uint32_t)((step >> 1) & 1));
+        const uint8_t* wimg = wbuf + (size_t)wsel * IMG_BYTES;
+        const uint32_t wimg16 = smem_u32(wimg) >> 4;
+        const float* bias = reinterpret_cast<const float*>(wimg + IMG_BIAS);
 
-      // ================= phase 3: 3x3 conv on the concat tensor (cols 96..127), residual, relu
-      if (ltid == 0) {
-        tc_fence_after();
-        int offs[9];
-        for (int i = 0; i < 3; ++i)
-          for (int j = 0; j < 3; ++j) offs[i * 3 + j] = (i - 2) * a.P + (j - 2);
-        issue_conv(d.c, offs, 9, wimg_s + IMG_H, 32, 96);
-        umma_commit(mbar);
-      }
-      mbar_wait(mbar, mma_phase);
-      mma_phase ^= 1;
-      tc_fence_after();
-#pragma unroll
-      for (int t = 0; t < TC_MAX_T; ++t) {
-        if (t >= a.T) break;
-        float v[32];
-        tmem_ld32(tm_pipe + lane_sel + (uint32_t)(t * 128) + 96, v);
-        if (site[t] >= 0) {
-          if (d.res_h >= 0) {
-            float r[32];
-            load_row(d.res_h, pos[t], r);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += r[i];
-          }
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bias[96 + i], 0.f);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0.f;
-        }
-        store_row(d.out_h, pos[t], v);
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      named_sync(1 + pipe, 128);
-
-      // ================= phase 4 (last block): head 1x1 conv (C -> 4) + normalisation + combine
-      if (d.last) {
-        const float* hb = reinterpret_cast<const float*>(wimg + IMG_HEAD_BIAS);
+        // ================= phase 1: 1x3 conv on h (cols 0..31) and 3x3 conv on v (cols 32..63)
         if (ltid == 0) {
           tc_fence_after();
-          int off0[1] = {0};
-          issue_conv(d.out_h, off0, 1, wimg_s + IMG_HEAD, 16, 0);
+          issue_conv(d.in_h, taps + 18, 3, 0, wimg16 + IMG_X / 16, true, 0);
+          issue_conv(d.in_v, taps, 9, 0, wimg16 + IMG_V / 16, true, 32);
           umma_commit(mbar);
         }
         mbar_wait(mbar, mma_phase);
         mma_phase ^= 1;
         tc_fence_after();
-        float sre = 0.f, sim = 0.f;
 #pragma unroll
         for (int t = 0; t < TC_MAX_T; ++t) {
           if (t >= a.T) break;
-          float v[16];
-          tmem_ld16(tm_pipe + lane_sel + (uint32_t)(t * 128) + 0, v);
+          float v[32];
+          tmem_ld32(tm_pipe + lane_sel + (uint32_t)(t * 128) + 0, v);
           if (site[t] >= 0) {
-            const float re0 = v[0] + hb[0], re1 = v[1] + hb[1], im0 = v[2] + hb[2], im1 = v[3] + hb[3];
-            const float x = 2.f * re0, y = 2.f * re1;
-            const float m = fmaxf(x, y);
-            const float half_lse = 0.5f * (m + logf(expf(x - m) + expf(y - m)));
-            const bool up = sig[t] > 0.f;  // class 0 <-> sigma = +1
-            sre += (up ? re0 : re1) - half_lse;
-            sim += up ? im0 : im1;
-          }
-        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          sre += __shfl_xor_sync(0xffffffffu, sre, o);
-          sim += __shfl_xor_sync(0xffffffffu, sim, o);
-        }
-        if (lane == 0) {
-          red[(pipe * 4 + (warp & 3)) * 2 + 0] = sre;
-          red[(pipe * 4 + (warp & 3)) * 2 + 1] = sim;
-        }
-        tc_fence_before();
-        named_sync(1 + pipe, 128);
-        if (ltid == 0 && active) {
-          float r0 = 0.f, r1 = 0.f;
-          for (int w = 0; w < 4; ++w) {
-            r0 += red[(pipe * 4 + w) * 2 + 0];
-            r1 += red[(pipe * 4 + w) * 2 + 1];
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bias[32 + i], 0.f);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
           }
-          a.out[2 * cfg + 0] = r0;
-          a.out[2 * cfg + 1] = r1;
+          store_row(d.x1, pos[t], v);
+          tmem_ld32(tm_pipe + lane_sel + (uint32_t)(t * 128) + 32, v);
+          if (site[t] >= 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += bias[i];
+            if (d.out_r >= 0) {
+              float r[32];
+              load_row(d.res_v, pos[t], r);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r[i] = fmaxf(r[i] + v[i], 0.f);
+              store_row(d.out_r, pos[t], r);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            if (d.out_r >= 0) store_row(d.out_r, pos[t], v);
+          }
+          store_row(d.out_a, pos[t], v);
         }
-      }
+        fence_proxy_async();
+        tc_fence_before();
+        named_sync(bar_id, 128);
 
-      // ================= end of block: both pipelines are done with this weight image -> refill it
-      __syncthreads();
-      if (tid == 0) {
-        const long long nxt = step + 2;
-        const bool need = (b + 2 < a.nb) || more;
-        if (need) {
-          mbar_expect_tx(wbar0 + 8 * wsel, IMG_BYTES);
-          bulk_g2s(smem_u32(wbuf + (size_t)wsel * IMG_BYTES), a.images + (size_t)(nxt % a.nb) * IMG_BYTES, IMG_BYTES,
-                   wbar0 + 8 * wsel);
+        // ================= phase 2: the two 1x1 convs (C -> C/2): x1 (RightShift in the last block) and
+        //                   DownShift(relu(v')) -> concat tensor (cols 64..95)
+        if (ltid == 0) {
+          tc_fence_after();
+          issue_conv(d.x1, nullptr, 1, d.last ? -1 : 0, wimg16 + IMG_XX / 16, false, 64);
+          issue_conv(d.out_a, nullptr, 1, -a.P, wimg16 + IMG_Y / 16, false, 80);
+          umma_commit(mbar);
         }
+        mbar_wait(mbar, mma_phase);
+        mma_phase ^= 1;
+        tc_fence_after();
+#pragma unroll
+        for (int t = 0; t < TC_MAX_T; ++t) {
+          if (t >= a.T) break;
+          float v[32];
+          tmem_ld32(tm_pipe + lane_sel + (uint32_t)(t * 128) + 64, v);
+          if (site[t] >= 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bias[64 + i], 0.f);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          }
+          store_row(d.c, pos[t], v);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        named_sync(bar_id, 128);
+
+        // ================= phase 3: 3x3 conv on the concat tensor (cols 96..127), residual, relu
+        if (ltid == 0) {
+          tc_fence_after();
+          issue_conv(d.c, taps + 9, 9, 0, wimg16 + IMG_H / 16, true, 96);
+          umma_commit(mbar);
+        }
+        mbar_wait(mbar, mma_phase);
+        mma_phase ^= 1;
+        tc_fence_after();
+#pragma unroll
+        for (int t = 0; t < TC_MAX_T; ++t) {
+          if (t >= a.T) break;
+          float v[32];
+          tmem_ld32(tm_pipe + lane_sel + (uint32_t)(t * 128) + 96, v);
+          if (site[t] >= 0) {
+            if (d.res_h >= 0) {
+              float r[32];
+              load_row(d.res_h, pos[t], r);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] += r[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bias[96 + i], 0.f);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          }
+          store_row(d.out_h, pos[t], v);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        named_sync(bar_id, 128);
+
+        // ================= phase 4 (last block): head 1x1 conv (C -> 4) + normalisation + combine
+        if (d.last) {
+          const float* hb = reinterpret_cast<const float*>(wimg + IMG_HEAD_BIAS);
+          if (ltid == 0) {
+            tc_fence_after();
+            issue_conv(d.out_h, nullptr, 1, 0, wimg16 + IMG_HEAD / 16, false, 0);
+            umma_commit(mbar);
+          }
+          mbar_wait(mbar, mma_phase);
+          mma_phase ^= 1;
+          tc_fence_after();
+          float sre = 0.f, sim = 0.f;
+#pragma unroll
+          for (int t = 0; t < TC_MAX_T; ++t) {
+            if (t >= a.T) break;
+            float v[16];
+            tmem_ld16(tm_pipe + lane_sel + (uint32_t)(t * 128) + 0, v);
+            if (site[t] >= 0) {
+              const float re0 = v[0] + hb[0], re1 = v[1] + hb[1], im0 = v[2] + hb[2], im1 = v[3] + hb[3];
+              const float x = 2.f * re0, y = 2.f * re1;
+              const float m = fmaxf(x, y);
+              const float half_lse = 0.5f * (m + logf(expf(x - m) + expf(y - m)));
+              const bool up = sig[t] > 0.f;  // class 0 <-> sigma = +1
+              sre += (up ? re0 : re1) - half_lse;
+              sim += up ? im0 : im1;
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            sre += __shfl_xor_sync(0xffffffffu, sre, o);
+            sim += __shfl_xor_sync(0xffffffffu, sim, o);
+          }
+          if (lane == 0) {
+            red[(pipe * 4 + (warp & 3)) * 2 + 0] = sre;
+            red[(pipe * 4 + (warp & 3)) * 2 + 1] = sim;
+          }
+          tc_fence_before();
+          named_sync(bar_id, 128);
+          if (ltid == 0 && active) {
+            float r0 = 0.f, r1 = 0.f;
+            for (int w = 0; w < 4; ++w) {
+              r0 += red[(pipe * 4 + w) * 2 + 0];
+              r1 += red[(pipe * 4 + w) * 2 + 1];
+            }
+            a.out[2 * cfg + 0] = r0;
+            a.out[2 * cfg + 1] = r1;
+          }
+        }
+        // this pipeline is done with the weight image (all MMAs retired, all bias reads behind the barrier)
+        if (ltid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8 * wsel) : "memory");
       }
     }
   }
@@ -547,15 +555,15 @@ static TcGeometry tc_geometry(const fk_net* net) {
   g.T = (p_last - g.p_first + 1 + 127) / 128;
   g.npos = ((g.p_first + g.T * 128 + 2) + 7) / 8 * 8;
   const size_t buf = (size_t)64 * g.npos;
-  const size_t tail = 256 + sizeof(TcBlockDesc) * (size_t)(2 * net->depth - 2) + 64;
-  g.np = 2;
+  const size_t tail = 384 + sizeof(TcBlockDesc) * (size_t)(2 * net->depth - 2) + 64;
+  g.np = TC_MAX_NP;
   g.ok = g.T <= TC_MAX_T;
   for (;;) {
     g.smem_bytes = 2 * (size_t)IMG_BYTES + (size_t)g.np * TC_SLOTS * buf + tail;
     const int cols = g.np * g.T * 128;
     if (g.smem_bytes <= 227 * 1024 && cols <= 512) break;
     if (g.np == 1) { g.ok = false; break; }
-    g.np = 1;
+    g.np -= 1;
   }
   int cols = g.np * g.T * 128;
   g.tmem_cols = cols <= 128 ? 128 : (cols <= 256 ? 256 : 512);
@@ -580,7 +588,10 @@ int tc_pack_weights(fk_net* net, cudaStream_t s) {
     net->tc_weight_bytes = (int64_t)total;
     // residual / buffer wiring -> shared-memory slots (reference counting; residual adds are done in place)
     std::vector<TcBlockDesc> desc(nb);
-    int rc[TC_SLOTS] = {0, 0, 0, 0, 0};
+    // In-place rules (safe because an epilogue thread only touches its own position and every MMA of the
+    // phase has retired before the epilogue starts): x1 may overwrite h, relu(v') may overwrite v, the concat
+    // tensor overwrites x1, h' overwrites the concat tensor (or the pair input when it carries the residual).
+    int rc[TC_SLOTS] = {0, 0, 0, 0};
     auto get = [&]() {
       for (int i = 0; i < TC_SLOTS; ++i)
         if (rc[i] == 0) { rc[i] = 1; return i; }
@@ -595,19 +606,19 @@ int tc_pack_weights(fk_net* net, cudaStream_t s) {
       if (b % 2 == 1 && !last) { v_pair = v; h_pair = h; rc[v]++; rc[h]++; }
       TcBlockDesc d;
       d.in_v = (int8_t)v; d.in_h = (int8_t)h; d.last = last ? 1 : 0; d.pad0 = d.pad1 = 0;
-      const int x1 = get();
-      rc[h]--;
-      const int a1 = get();
+      int x1;
+      if (rc[h] == 1) { x1 = h; } else { x1 = get(); rc[h]--; }
+      int a1;
+      if (rc[v] == 1) { a1 = v; } else { a1 = get(); rc[v]--; }
+      FK_REQUIRE(x1 >= 0 && a1 >= 0, "tc_pack_weights: out of shared-memory activation slots");
       d.out_r = d.res_v = (int8_t)(res2 ? v_pair : -1);
-      rc[v]--;
-      const int c = get();
-      rc[x1]--;
-      int v_next = a1;
-      if (res2) { rc[a1]--; v_next = v_pair; }
-      int hn;
-      if (res2) { hn = h_pair; d.res_h = (int8_t)h_pair; } else { hn = get(); d.res_h = -1; }
-      rc[c]--;
-      FK_REQUIRE(x1 >= 0 && a1 >= 0 && c >= 0 && hn >= 0, "tc_pack_weights: out of shared-memory activation slots");
+      const int c = x1;
+      int v_next = a1, hn = c;
+      d.res_h = -1;
+      if (res2) {
+        rc[a1]--; v_next = v_pair;            // relu(v') only feeds the 1x1 conv; the residual sum replaces the pair input
+        rc[c]--; hn = h_pair; d.res_h = (int8_t)h_pair;
+      }
       d.x1 = (int8_t)x1; d.out_a = (int8_t)a1; d.c = (int8_t)c; d.out_h = (int8_t)hn;
       desc[b] = d;
       v = v_next; h = hn;
@@ -656,7 +667,7 @@ int tc_log_psi(fk_net* net, const int8_t* sigma, int64_t n, float* log_psi_out, 
   const long long groups = (n + g.np - 1) / g.np;
   const unsigned grid = (unsigned)std::min<long long>(groups, sms);
   FK_CHECK_CUDA(cudaFuncSetAttribute(tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-  tc_forward_kernel<<<grid, 128 * g.np, g.smem_bytes, s>>>(a);
+  tc_forward_kernel<<<grid, 128 * g.np + 32, g.smem_bytes, s>>>(a);
   FK_CHECK_LAUNCH();
   return 0;
 }
