@@ -206,97 +206,94 @@ int launch_dz(const float* g_out, int g_cs, int g_coff, const float* out, int ou
 }
 
 // ------------------------------------------------------------------------------------------------
-// weight gradient.  grid = (ntaps, chunks); thread tile 4 (ci) x 4 (co); positions staged 32 at a time.
+// weight gradient:  dW[t][ci][co] (+)= sum_{cfg, p} in(cfg, p + delta_t)[ci] * dz(cfg, p)[co],  db[co] (+)= sum dz.
+// A CTA walks a run of configurations; per configuration the (zero-padded) input tile and the dz tile are
+// staged in shared memory, so a tap is a constant offset into the tile (no bounds checks in the inner loop).
+// Thread (ci, co-group of 4) keeps the [taps][4] slice of dW in registers: per position 1 LDS.128 (dz) +
+// taps x (1 LDS + 4 FFMA).  grid = (config chunks, ci tiles of 32, co tiles of 32).
 // ------------------------------------------------------------------------------------------------
 struct DwArgs {
   const float* in; int in_cs; int cin;
   const float* dz; int cout;
-  int ntaps; int dh[MAX_TAPS]; int dw[MAX_TAPS];
-  int H, W; long long npos; long long chunk;
+  int ntaps; int toff[MAX_TAPS];   // tap offsets inside the padded tile (in positions)
+  int H, W, Pw, tile_pos, org;      // padded pitch, padded tile size, tile index of lattice site (0,0)
+  long long n; int cfgs_per_cta;
   float* dW; float* db; int per_sample; long long out_stride;
 };
 
+template <int NTAPS>
 __global__ void __launch_bounds__(256) dw_kernel(DwArgs a) {
-  constexpr int PP = 32, MAXC = 64;
-  __shared__ __align__(16) float Is[PP][MAXC];
-  __shared__ __align__(16) float Ds[PP][MAXC];
+  extern __shared__ __align__(16) float dw_smem[];
+  float* In = dw_smem;                           // [tile_pos][32]
+  float* Dz = dw_smem + (size_t)a.tile_pos * 32;  // [sites][32]
   const int tid = threadIdx.x;
-  const int t = blockIdx.x;
-  const long long pbeg = (long long)blockIdx.y * a.chunk;
-  long long pend = pbeg + a.chunk;
-  if (pend > a.npos) pend = a.npos;
-  const int HW = a.H * a.W;
-  const int cin4 = (a.cin + 3) / 4, cout4 = (a.cout + 3) / 4;
-  const int cinp = cin4 * 4, coutp = cout4 * 4;
-  const bool active = tid < cin4 * cout4;
-  const int ci0 = active ? (tid / cout4) * 4 : 0, co0 = active ? (tid % cout4) * 4 : 0;
-  float acc[4][4];
-  float bacc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  const int dh = a.dh[t], dw = a.dw[t];
+  const int ci_l = tid >> 3, cg = tid & 7;
+  const int ci0 = blockIdx.y * 32, co0 = blockIdx.z * 32;
+  const int sites = a.H * a.W;
+  const bool ci_ok = ci0 + ci_l < a.cin;
+  for (int e = tid; e < a.tile_pos * 32; e += 256) In[e] = 0.f;   // padding stays zero for the whole kernel
 
-  for (long long pb = pbeg; pb < pend; pb += PP) {
-    for (int e = tid; e < PP * cinp; e += 256) {
-      const int pp = e / cinp, ci = e - pp * cinp;
-      const long long p = pb + pp;
-      float v = 0.f;
-      if (p < pend && ci < a.cin) {
-        const long long n = p / HW;
-        const int rem = (int)(p - n * HW);
-        const int ii = rem / a.W + dh, jj = rem % a.W + dw;
-        if (ii >= 0 && ii < a.H && jj >= 0 && jj < a.W) v = __ldg(a.in + (n * HW + ii * a.W + jj) * a.in_cs + ci);
-      }
-      Is[pp][ci] = v;
-    }
-    for (int e = tid; e < PP * coutp; e += 256) {
-      const int pp = e / coutp, co = e - pp * coutp;
-      const long long p = pb + pp;
-      Ds[pp][co] = (p < pend && co < a.cout) ? __ldg(a.dz + p * a.cout + co) : 0.f;
+  float acc[NTAPS][4];
+#pragma unroll
+  for (int t = 0; t < NTAPS; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+  float bacc[4] = {0.f, 0.f, 0.f, 0.f};
+  int toff[NTAPS];
+#pragma unroll
+  for (int t = 0; t < NTAPS; ++t) toff[t] = a.toff[t] * 32 + ci_l;
+
+  const long long c_beg = (long long)blockIdx.x * a.cfgs_per_cta;
+  long long c_end = c_beg + a.cfgs_per_cta;
+  if (c_end > a.n) c_end = a.n;
+  for (long long cfg = c_beg; cfg < c_end; ++cfg) {
+    __syncthreads();
+    const float* gin = a.in + cfg * sites * a.in_cs;
+    const float* gdz = a.dz + cfg * sites * a.cout;
+    for (int e = tid; e < sites * 32; e += 256) {
+      const int p = e >> 5, c = e & 31;
+      const int i = p / a.W, j = p - i * a.W;
+      In[(a.org + i * a.Pw + j) * 32 + c] = (ci0 + c < a.cin) ? gin[(long long)p * a.in_cs + ci0 + c] : 0.f;
+      Dz[e] = (co0 + c < a.cout) ? gdz[(long long)p * a.cout + co0 + c] : 0.f;
     }
     __syncthreads();
-    if (active) {
-#pragma unroll 4
-      for (int pp = 0; pp < PP; ++pp) {
-        const float4 iv = *reinterpret_cast<const float4*>(&Is[pp][ci0]);
-        const float4 dv = *reinterpret_cast<const float4*>(&Ds[pp][co0]);
-        const float ia[4] = {iv.x, iv.y, iv.z, iv.w};
-        const float da[4] = {dv.x, dv.y, dv.z, dv.w};
+    if (ci_ok) {
+      for (int i = 0; i < a.H; ++i) {
+        const float* in_row = In + (a.org + i * a.Pw) * 32;
+        const float* dz_row = Dz + i * a.W * 32 + cg * 4;
+        for (int j = 0; j < a.W; ++j) {
+          const float4 d = *reinterpret_cast<const float4*>(dz_row + j * 32);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ia[i], da[j], acc[i][j]);
-        if (ci0 == 0) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) bacc[j] += da[j];
+          for (int t = 0; t < NTAPS; ++t) {
+            const float x = in_row[j * 32 + toff[t]];
+            acc[t][0] = fmaf(x, d.x, acc[t][0]);
+            acc[t][1] = fmaf(x, d.y, acc[t][1]);
+            acc[t][2] = fmaf(x, d.z, acc[t][2]);
+            acc[t][3] = fmaf(x, d.w, acc[t][3]);
+          }
+          if (ci_l == 0) { bacc[0] += d.x; bacc[1] += d.y; bacc[2] += d.z; bacc[3] += d.w; }
         }
       }
     }
-    __syncthreads();
   }
-  if (!active) return;
-  float* dWo = a.dW + (a.per_sample ? (long long)blockIdx.y * a.out_stride : 0);
-  float* dbo = a.db ? a.db + (a.per_sample ? (long long)blockIdx.y * a.out_stride : 0) : nullptr;
+  float* dWo = a.dW + (a.per_sample ? (long long)blockIdx.x * a.out_stride : 0);
+  if (ci_ok) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int ci = ci0 + i;
-    if (ci >= a.cin) continue;
+    for (int t = 0; t < NTAPS; ++t) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int co = co0 + j;
-      if (co >= a.cout) continue;
-      float* ptr = dWo + ((long long)t * a.cin + ci) * a.cout + co;
-      if (a.per_sample) *ptr = acc[i][j]; else atomicAdd(ptr, acc[i][j]);
+      for (int c = 0; c < 4; ++c) {
+        const int co = co0 + cg * 4 + c;
+        if (co >= a.cout) continue;
+        float* ptr = dWo + ((long long)t * a.cin + ci0 + ci_l) * a.cout + co;
+        if (a.per_sample) *ptr = acc[t][c]; else atomicAdd(ptr, acc[t][c]);
+      }
     }
   }
-  if (dbo && t == 0 && ci0 == 0) {
+  if (a.db && blockIdx.y == 0 && ci_l == 0) {
+    float* dbo = a.db + (a.per_sample ? (long long)blockIdx.x * a.out_stride : 0);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int co = co0 + j;
+    for (int c = 0; c < 4; ++c) {
+      const int co = co0 + cg * 4 + c;
       if (co >= a.cout) continue;
-      if (a.per_sample) dbo[co] = bacc[j]; else atomicAdd(dbo + co, bacc[j]);
+      if (a.per_sample) dbo[co] = bacc[c]; else atomicAdd(dbo + co, bacc[c]);
     }
   }
 }
@@ -305,20 +302,43 @@ int launch_dw(const float* in, int in_cs, int cin, const float* dz, int cout, in
               const int* dw, int H, int W, long long n, float* dW, float* db, int per_sample,
               long long out_stride, cudaStream_t s) {
   if (n == 0) return 0;
-  FK_REQUIRE(cin <= 64 && cout <= 64, "launch_dw: cin/cout > 64 not supported (cin=%d cout=%d)", cin, cout);
   DwArgs a;
   a.in = in; a.in_cs = in_cs; a.cin = cin; a.dz = dz; a.cout = cout; a.ntaps = ntaps;
-  for (int t = 0; t < ntaps; ++t) { a.dh[t] = dh[t]; a.dw[t] = dw[t]; }
-  a.H = H; a.W = W; a.npos = n * H * W;
-  a.per_sample = per_sample; a.out_stride = out_stride; a.dW = dW; a.db = db;
-  if (per_sample) {
-    a.chunk = (long long)H * W;
-  } else {
-    a.chunk = 4096;
+  int min_h = 0, max_h = 0, min_w = 0, max_w = 0;
+  for (int t = 0; t < ntaps; ++t) {
+    min_h = dh[t] < min_h ? dh[t] : min_h; max_h = dh[t] > max_h ? dh[t] : max_h;
+    min_w = dw[t] < min_w ? dw[t] : min_w; max_w = dw[t] > max_w ? dw[t] : max_w;
   }
-  const long long chunks = (a.npos + a.chunk - 1) / a.chunk;
-  FK_REQUIRE(chunks <= 65535, "launch_dw: too many position chunks (%lld); lower the gradient chunk size", chunks);
-  dw_kernel<<<dim3(ntaps, (unsigned)chunks), 256, 0, s>>>(a);
+  a.H = H; a.W = W;
+  a.Pw = W + (max_w - min_w);
+  const int rows = H + (max_h - min_h);
+  a.tile_pos = rows * a.Pw + (max_w - min_w) + 1;
+  a.org = (-min_h) * a.Pw + (-min_w);
+  for (int t = 0; t < ntaps; ++t) a.toff[t] = dh[t] * a.Pw + dw[t];
+  a.n = n; a.dW = dW; a.db = db; a.per_sample = per_sample; a.out_stride = out_stride;
+  if (per_sample) {
+    a.cfgs_per_cta = 1;
+  } else {
+    long long per = (n + 148 * 4 - 1) / (148 * 4);   // ~2 waves of 2 resident CTAs per SM
+    a.cfgs_per_cta = (int)(per < 1 ? 1 : (per > 64 ? 64 : per));
+  }
+  const long long gx = (n + a.cfgs_per_cta - 1) / a.cfgs_per_cta;
+  FK_REQUIRE(gx <= 0x7fffffffLL, "launch_dw: grid too large");
+  const size_t smem = ((size_t)a.tile_pos + (size_t)H * W) * 32 * sizeof(float);
+  FK_REQUIRE(smem <= 200 * 1024, "launch_dw: lattice too large for the shared-memory tile (%zu bytes)", smem);
+  const dim3 grid((unsigned)gx, (unsigned)((cin + 31) / 32), (unsigned)((cout + 31) / 32));
+#define FK_DW_CASE(NT)                                                                                         \
+  case NT:                                                                                                     \
+    FK_CHECK_CUDA(cudaFuncSetAttribute(dw_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    dw_kernel<NT><<<grid, 256, smem, s>>>(a);                                                                  \
+    break;
+  switch (ntaps) {
+    FK_DW_CASE(1) FK_DW_CASE(2) FK_DW_CASE(3) FK_DW_CASE(4) FK_DW_CASE(5) FK_DW_CASE(6) FK_DW_CASE(7) FK_DW_CASE(8)
+    FK_DW_CASE(9)
+    default:
+      FK_REQUIRE(false, "launch_dw: unsupported number of taps %d", ntaps);
+  }
+#undef FK_DW_CASE
   FK_CHECK_LAUNCH();
   return 0;
 }
