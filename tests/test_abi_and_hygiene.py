@@ -1,0 +1,76 @@
+"""CPU tier: the C-ABI library loads and exports every symbol include/flowket_b200.h declares (no compute
+calls), the product never imports the oracle, and there is no CPU fallback."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, 'include', 'flowket_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(fk_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__
+    __graft_entry__.build()
+    from flowket_b200 import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    symbols = _header_symbols()
+    assert len(symbols) >= 20
+    for name in symbols:
+        assert hasattr(lib, name), 'libflowket_b200.so does not export %s' % name
+    assert set(symbols) == set(_lib.SIGNATURES), 'ctypes signature table out of sync with the header'
+    assert _lib.load().fk_version() >= 100
+
+
+def test_library_is_sm100a_with_tcgen05():
+    """the shipped binary contains sm_100a SASS with tcgen05 MMAs, TMEM loads and bulk async copies"""
+    from flowket_b200 import _lib
+    out = subprocess.run(['cuobjdump', '-sass', _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert 'sm_100a' in out
+    for mnemonic in ('UTCHMMA', 'LDTM', 'UBLKCP'):
+        assert mnemonic in out, mnemonic
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'flowket_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), os.path.join(dirpath, f)
+                if f.endswith('.py'):   # (C++ comments cite reference file:line; Python must never read the tree)
+                    assert '/root/reference' not in text, os.path.join(dirpath, f)
+
+
+def test_no_cpu_fallback():
+    """without a CUDA device the product path fails loudly instead of computing on the host"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('needs a CPU-only box')
+    from flowket_b200 import Input, Model, FlowketB200Error
+    from flowket_b200.machines import ConvNetAutoregressive2D
+    from flowket_b200.operators import Heisenberg
+    from flowket_b200.samplers import FastAutoregressiveSampler
+    inp = Input(shape=(4, 4))
+    machine = ConvNetAutoregressive2D(inp, depth=3, num_of_channels=8)
+    model = Model(inp, machine.predictions)
+    with pytest.raises(FlowketB200Error):
+        model.predict([[[1] * 4] * 4])
+    with pytest.raises(FlowketB200Error):
+        next(FastAutoregressiveSampler(Model(inp, machine.conditional_log_probs), 4))
+    with pytest.raises(FlowketB200Error):
+        Heisenberg(hilbert_state_shape=[4, 4], pbc=False).find_conn([[[1] * 4] * 4])
+
+
+def test_missing_library_is_reported(tmp_path):
+    from flowket_b200 import _lib
+    with pytest.raises(_lib.FlowketB200Error):
+        _lib.load(str(tmp_path / 'does_not_exist.so'))

@@ -1,0 +1,56 @@
+"""CPU tier: the N > 1 path (energy-statistics allreduce, gradient allreduce, sample sharding) with
+world_size-2 gloo processes."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from flowket_b200.optimization import DistributedVariationalMonteCarlo
+    from flowket_b200.optimizers import allreduce_sum_
+    rng = np.random.default_rng(123)
+    full = rng.normal(size=64) * 3 - 20 + 1j * rng.normal(size=64) * 0.1     # the global batch of local energies
+    shard = full[rank * 32:(rank + 1) * 32]
+    mean, var, count = DistributedVariationalMonteCarlo.reduce_stats(shard)
+    g = torch.full((5,), float(rank + 1))
+    allreduce_sum_(g)
+    out[rank] = (mean, var, count, g.tolist(), complex(full.mean()), float(np.var(full.real)))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_energy_statistics_and_gradient_allreduce():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, 29651, out), nprocs=world, join=True)
+    for rank in range(world):
+        mean, var, count, g, want_mean, want_var = out[rank]
+        assert count == 64
+        assert mean == pytest.approx(want_mean, rel=1e-12)     # a true global mean: sum / count, not a mean of means
+        assert var == pytest.approx(want_var, rel=1e-10)
+        assert g == [3.0] * 5
+
+
+def test_philox_shard_offsets_partition_the_global_batch():
+    """rank r draws global sample indices [r*B, (r+1)*B): the host bookkeeping of the sampler"""
+    from flowket_b200 import Input, Model
+    from flowket_b200.machines import ConvNetAutoregressive2D
+    from flowket_b200.samplers import FastAutoregressiveSampler
+    inp = Input(shape=(4, 4))
+    cond = Model(inp, ConvNetAutoregressive2D(inp, depth=2, num_of_channels=8).conditional_log_probs)
+    offs = [FastAutoregressiveSampler(cond, 32, seed=7, sample_offset=r * 32).sample_offset for r in range(4)]
+    assert offs == [0, 32, 64, 96]
+    s = FastAutoregressiveSampler(cond, 100, mini_batch_size=32)
+    assert s._effective_batch() == 96          # batch % mini_batch samples are dropped (fast_autoregressive.py:31-33)
+    assert s.copy_with_new_batch_size(16).batch_size == 16

@@ -1,0 +1,190 @@
+"""GPU tier: the orchestration objects (VariationalMonteCarlo, ExactVariational, Trainer, SR) against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import exact as oexact
+from oracle import local_energy as oeloc
+from oracle import nets, operators as oops, sr as osr
+from tests.helpers import make_pair, random_sigma
+
+pytestmark = pytest.mark.gpu
+
+
+def test_variational_monte_carlo_attributes_and_coefficients():
+    """same attribute names / return values as optimization/variational_monte_carlo.py:15-50"""
+    from flowket_b200.operators import Heisenberg
+    from flowket_b200.samplers import FastAutoregressiveSampler
+    from flowket_b200.optimization import VariationalMonteCarlo
+    shape = (4, 4)
+    model, cond, spec, params = make_pair('conv2d', shape, 3, 32, seed=1)
+    sampler = FastAutoregressiveSampler(cond, 48)
+    vmc = VariationalMonteCarlo(model, Heisenberg(hilbert_state_shape=list(shape), pbc=False), sampler, mini_batch_size=16)
+    assert vmc.update_params_frequency == 3
+    x, y = next(vmc)
+    assert x.shape == (16, 4, 4) and y.shape == (16,) and x.dtype == np.int8
+    for attr in ('current_batch', 'current_energy', 'current_local_energy_variance', 'current_local_energy',
+                 'wave_function', 'sampler', 'batch_size', 'mini_batch_size', 'start_time', 'sampling_end_time',
+                 'local_energy_end_time'):
+        assert hasattr(vmc, attr), attr
+    sigma = vmc.current_batch
+    want = oeloc.local_values(oops.OracleOperator('heisenberg', shape, pbc=False),
+                              lambda c: nets.log_psi_numpy(spec, params, c), sigma.astype(np.float64))
+    assert np.abs(vmc.current_local_energy - want).max() / np.abs(want).max() < 1e-5
+    assert vmc.current_energy == pytest.approx(np.mean(want), rel=1e-5)
+    assert vmc.current_local_energy_variance == pytest.approx(np.var(want.real), rel=1e-4)
+    coeff = oeloc.loss_coefficients(want, want.mean(), 48)
+    assert np.abs(y - coeff[:16]).max() < 1e-5 * np.abs(coeff).max() + 1e-9
+    # the wave_function callable of the reference protocol still works (Observable generic route)
+    e2 = vmc.energy_observable.local_values(vmc.wave_function, sigma)
+    assert np.abs(e2 - want).max() / np.abs(want).max() < 1e-5
+
+
+@pytest.mark.parametrize('opkind,opkw,shape,kind,depth,ch', [
+    ('ising', dict(pbc=False, h=3.0), (4, 4), 'conv2d', 3, 16),
+    ('heisenberg', dict(pbc=True), (12,), 'conv1d', 5, 16),
+    ('j1j2', dict(pbc=False, j2=0.5), (4, 3), 'conv2d', 2, 8),
+])
+def test_exact_variational_matches_oracle(opkind, opkw, shape, kind, depth, ch):
+    from flowket_b200.optimization import ExactVariational
+    from tests.test_gpu_parity import _product_operator
+    model, _, spec, params = make_pair(kind, shape, depth, ch, seed=4)
+    ev = ExactVariational(model, _product_operator(opkind, shape, opkw), batch_size=2 ** 10)
+    ev.machine_updated()
+    oop = oops.OracleOperator(opkind, shape, **opkw)
+    oev = oexact.ExactVariationalOracle(lambda s: nets.log_psi_numpy(spec, params, s)[:, 0], oop, shape, 2 ** 10)
+    oev.machine_updated()
+    assert ev.num_of_states == 2 ** int(np.prod(shape))
+    assert ev.energy_observable.current_energy == pytest.approx(oev.current_energy, rel=2e-5)
+    assert np.abs(ev.probs - oev.probs).max() < 1e-5 * oev.probs.max()
+    assert ev.energy_observable.current_local_energy_variance == pytest.approx(oev.current_local_energy_variance, rel=1e-3)
+    assert np.linalg.norm(ev.energy_grad_coefficients - oev.energy_grad_coefficients) < \
+        2e-5 * np.linalg.norm(oev.energy_grad_coefficients)
+    with pytest.raises(Exception):
+        ExactVariational(model, _product_operator(opkind, shape, opkw), batch_size=1000)
+
+
+def test_exact_equals_monte_carlo_energy():
+    """tests/test_variational.py:49-66 of the reference: MC energy == exact energy within the MC error bar."""
+    from flowket_b200.operators import Heisenberg
+    from flowket_b200.samplers import FastAutoregressiveSampler
+    from flowket_b200.optimization import ExactVariational, VariationalMonteCarlo
+    shape = (3, 4)
+    model, cond, _, _ = make_pair('conv2d', shape, 3, 32, seed=6)
+    op = Heisenberg(hilbert_state_shape=list(shape), pbc=False)
+    ev = ExactVariational(model, op, 2 ** 12)
+    ev.machine_updated()
+    exact_e = ev.energy_observable.current_energy.real
+    var = ev.energy_observable.current_local_energy_variance
+    B, iters = 4096, 4
+    vmc = VariationalMonteCarlo(model, op, FastAutoregressiveSampler(cond, B, seed=11))
+    energies = []
+    for _ in range(iters):
+        vmc.next_batch()
+        energies.append(vmc.current_energy.real)
+    sigma_mc = np.sqrt(var / (B * iters))
+    assert abs(np.mean(energies) - exact_e) < 4 * sigma_mc
+
+
+def test_complex_sr_matches_oracle():
+    from flowket_b200.optimizers import ComplexValuesStochasticReconfiguration
+    shape = (10,)
+    model, _, spec, params = make_pair('cconv1d', shape, 3, 8, seed=3)
+    B = 64
+    sigma = random_sigma(B, shape, seed=8)
+    rng = np.random.default_rng(0)
+    eloc = rng.normal(size=B) + 1j * rng.normal(size=B)
+    y_true = np.conj(eloc - eloc.mean()) / B
+    # oracle: complex Jacobian assembled pairwise from (real, imag) variables
+    O_re = nets.per_sample_gradients(spec, params, sigma, 'real').numpy()
+    offs = np.cumsum([0] + [int(p.numel()) for p in params])
+    re_idx = np.concatenate([np.arange(offs[i], offs[i + 1]) for i in range(0, len(params), 4)] +
+                            [np.arange(offs[i + 2], offs[i + 3]) for i in range(0, len(params), 4)])
+    im_idx = np.concatenate([np.arange(offs[i + 1], offs[i + 2]) for i in range(0, len(params), 4)] +
+                            [np.arange(offs[i + 3], offs[i + 4]) for i in range(0, len(params), 4)])
+    for iterative in (False, True):
+        sr = ComplexValuesStochasticReconfiguration(model, diag_shift=0.05, iterative_solver=iterative,
+                                                    conjugate_gradient_tol=1e-7, iterative_solver_max_iterations=2000)
+        got = sr.compute_update(sigma, y_true).cpu().numpy()
+        re, im = [t.cpu().numpy() for t in sr._complex_index('cpu')]
+        O = O_re[:, re] + 1j * O_re[:, im]
+        Ob = osr.centre(O)
+        want = osr.solve_direct(Ob, osr.energy_grad(Ob, y_true), 0.05)
+        assert np.linalg.norm(got - want) / np.linalg.norm(want) < 2e-4, iterative
+    # and the update moves the parameters as W <- W - lr * delta
+    before = model.machine.flat_params_numpy()
+    delta = sr.step(sigma, y_true).cpu().numpy()
+    after = model.machine.flat_params_numpy()
+    W0 = before[re] - 1j * before[im]
+    W1 = after[re] - 1j * after[im]
+    assert np.allclose(W1, W0 - sr.lr * delta, atol=1e-6)
+
+
+def test_real_sr_matches_oracle():
+    from flowket_b200.optimizers import StochasticReconfiguration
+    shape = (4, 4)
+    model, _, spec, params = make_pair('conv2d', shape, 2, 8, seed=5, weights_normalization=False)
+    B = 96
+    sigma = random_sigma(B, shape, seed=9)
+    rng = np.random.default_rng(1)
+    eloc = rng.normal(size=B) * 2 - 10 + 1j * rng.normal(size=B)
+    O_re = nets.per_sample_gradients(spec, params, sigma, 'real').numpy()
+    O_im = nets.per_sample_gradients(spec, params, sigma, 'imag').numpy()
+    S, F = osr.real_sr_system(O_re, O_im, eloc, 0.05)
+    want = np.linalg.solve(S, F)
+    for iterative in (False, True):
+        sr = StochasticReconfiguration(model, diag_shift=0.05, iterative_solver=iterative, conjugate_gradient_tol=1e-7,
+                                       iterative_solver_max_iterations=5000)
+        got = sr.compute_update(sigma, eloc).cpu().numpy()
+        assert np.linalg.norm(got - want) / np.linalg.norm(want) < 5e-4, iterative
+
+
+def test_sr_gram_kernel():
+    from flowket_b200._device import sr_gram
+    rng = np.random.default_rng(2)
+    A = torch.from_numpy(rng.normal(size=(300, 97)).astype(np.float32)).cuda()
+    G1 = sr_gram(A, transpose_a=True).cpu().numpy()
+    G2 = sr_gram(A, transpose_a=False).cpu().numpy()
+    An = A.cpu().numpy().astype(np.float64)
+    assert np.abs(G1 - An.T @ An).max() < 1e-4 * np.abs(An.T @ An).max()
+    assert np.abs(G2 - An @ An.T).max() < 1e-4 * np.abs(An @ An.T).max()
+
+
+def test_training_lowers_the_energy_towards_exact_diagonalisation():
+    """Ising 4x4 OBC h=3 (cfg 1 anchor: ED -50.18662388277671, examples/basic_autoregressive_2d.py:39):
+    exact-gradient Adam steps must move the variational energy monotonically-ish towards the ED value and stay
+    above it (variational principle)."""
+    from flowket_b200.operators import Ising
+    from flowket_b200.optimization import ExactVariational
+    from flowket_b200.optimizers import Adam, Trainer
+    from flowket_b200 import Input, Model
+    from flowket_b200.machines import ConvNetAutoregressive2D
+    inp = Input(shape=(4, 4), dtype='int8')
+    machine = ConvNetAutoregressive2D(inp, depth=3, num_of_channels=16, weights_normalization=False, seed=0)
+    model = Model(inp, machine.predictions)
+    ev = ExactVariational(model, Ising(hilbert_state_shape=[4, 4], pbc=False, h=3.0), batch_size=2 ** 14)
+    gen = ev.to_generator()
+    opt = Adam(lr=3e-3, beta_1=0.9, beta_2=0.999)
+
+    class ExactGen(object):
+        update_params_frequency = ev.num_of_batch_until_full_cycle
+
+        def __next__(self_inner):
+            return next(gen)
+    trainer = Trainer(model, ExactGen(), opt)
+    # Keras averages the loss over the mini-batch; the exact coefficients already carry p(s): undo the 1/mb
+    energies = []
+    for step in range(120):
+        grad = None
+        for _ in range(ev.num_of_batch_until_full_cycle):
+            x, y = next(gen)
+            g = trainer.gradient(x, y) * x.shape[0]
+            grad = g if grad is None else grad + g
+        opt.step(machine.flat_params_device(), grad)
+        machine.params_updated()
+        energies.append(ev.energy_observable.current_energy.real)
+    e_ed = -50.18662388277671
+    print('exact-gradient training: E0 = %.6f -> E = %.6f (ED %.6f)' % (energies[0], energies[-1], e_ed))
+    assert energies[-1] < energies[0]
+    assert all(e > e_ed - 1e-6 for e in energies)             # variational principle
+    assert abs(energies[-1] - e_ed) / abs(e_ed) < 5e-4        # ground-state energy of the 4x4 lattice vs ED

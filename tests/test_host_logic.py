@@ -1,0 +1,168 @@
+"""CPU tier: host-side mirror of the reference interface (no device calls)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nets, operators as oops
+
+
+def test_parameter_layout_matches_oracle_and_survey():
+    from flowket_b200 import Input, Model
+    from flowket_b200.machines import ConvNetAutoregressive2D, SimpleConvNetAutoregressive1D, \
+        ComplexValuesSimpleConvNetAutoregressive1D
+    m = ConvNetAutoregressive2D(Input(shape=(10, 10)), depth=20, num_of_channels=32)
+    assert m.count_params() == 849156 + 4864
+    m2 = ConvNetAutoregressive2D(Input(shape=(10, 10)), depth=20, num_of_channels=32, weights_normalization=False)
+    assert m2.count_params() == 849156
+    spec = nets.Conv2DSpec(10, 10, 20, 32)
+    assert [tuple(s) for _, s, _ in m.weight_specs()] == [tuple(p.shape) for p in nets.init_params(spec)]
+    # Keras layer names of the pretrained files: weight_normalization[_k]/{kernel,bias,g}:0, k = 0..89, conv2d_90
+    m10 = ConvNetAutoregressive2D(Input(shape=(12, 12)), depth=10, num_of_channels=32)
+    names = [n for n, _, _ in m10.weight_specs()]
+    assert names[0] == 'weight_normalization/kernel:0' and 'weight_normalization_89/g:0' in names
+    assert names[-2:] == ['conv2d_90/kernel:0', 'conv2d_90/bias:0']
+    m1 = SimpleConvNetAutoregressive1D(Input(shape=(20,)), depth=8, num_of_channels=64, max_dilation_rate=4,
+                                       weights_normalization=False)
+    assert m1.count_params() == nets.num_params(nets.Conv1DSpec(20, 8, 64, max_dilation_rate=4, weights_normalization=False))
+    mc = ComplexValuesSimpleConvNetAutoregressive1D(Input(shape=(36,)), depth=8, num_of_channels=32, max_dilation_rate=4)
+    assert mc.count_params() == 2 * 18818                           # SURVEY appendix B, cfg 4 (complex count)
+    model = Model(inputs=m.keras_input_layer, outputs=m.predictions)
+    assert model.input_shape == (None, 10, 10) and model.output_shape == (None, 1)
+
+
+def test_initial_weights_weight_norm_identity():
+    """CopyNormaInitializer: with g0 = log|v| (exp norm) the effective kernel equals v at init."""
+    from flowket_b200 import Input
+    from flowket_b200.machines import ConvNetAutoregressive2D
+    m = ConvNetAutoregressive2D(Input(shape=(4, 4)), depth=3, num_of_channels=8, seed=3)
+    w = m.initial_weights(3)
+    specs = m.weight_specs()
+    v, g = w[0], w[2]
+    assert specs[2][0].endswith('/g:0')
+    eff = v / np.sqrt((v.reshape(-1, v.shape[-1]) ** 2).sum(0)) * np.exp(g)
+    assert np.allclose(eff, v, rtol=1e-5)
+    m.set_weights(w)
+    back = m.get_weights()
+    assert all(np.array_equal(a, b) for a, b in zip(w, back))
+    with pytest.raises(ValueError):
+        m.set_weights(w[:-1])
+
+
+def test_operator_term_tables_match_oracle_on_host():
+    """the device term tables (built on the host) reproduce the oracle's find_conn when interpreted in numpy"""
+    from flowket_b200 import _lib
+    import flowket_b200.operators as ops
+    rng = np.random.default_rng(0)
+    cases = [(ops.Heisenberg(hilbert_state_shape=[4, 5], pbc=False), 'heisenberg', (4, 5), dict(pbc=False)),
+             (ops.Heisenberg(hilbert_state_shape=[4, 4], pbc=True), 'heisenberg', (4, 4), dict(pbc=True)),
+             (ops.Heisenberg(hilbert_state_shape=[7], pbc=True), 'heisenberg', (7,), dict(pbc=True)),
+             (ops.Ising(hilbert_state_shape=[3, 5], pbc=True, h=0.5), 'ising', (3, 5), dict(pbc=True, h=0.5)),
+             (ops.Ising(hilbert_state_shape=[9], pbc=False, h=3.0), 'ising', (9,), dict(pbc=False, h=3.0)),
+             (ops.J1J2((4, 4), j2=0.5), 'j1j2', (4, 4), dict(j2=0.5))]
+    for op, kind, shape, kw in cases:
+        terms, kind_id, compact, _ = op.terms()
+        sigma = rng.choice([-1, 1], size=(5,) + shape)
+        conn, mel, use = oops.OracleOperator(kind, shape, **kw).find_conn(sigma)
+        assert op.max_number_of_local_connections == conn.shape[0]
+        flat = sigma.reshape(5, -1)
+        for b in range(5):
+            diag, nxt = 0.0, 1
+            for (a, c, k, slot, dc, oc) in terms:
+                sb = flat[b, c] if c >= 0 else 0
+                if k != _lib.FK_TERM_FLIP:
+                    diag += dc * flat[b, a] * sb
+                if k == _lib.FK_TERM_DIAG:
+                    continue
+                used = (flat[b, a] != flat[b, c]) if k == _lib.FK_TERM_EXCHANGE else True
+                if compact:
+                    if not used:
+                        continue
+                    slot = nxt
+                    nxt += 1
+                new = flat[b].copy()
+                if k == _lib.FK_TERM_EXCHANGE:
+                    new[a], new[c] = flat[b, c], flat[b, a]
+                else:
+                    new[a] = -new[a]
+                assert np.array_equal(conn[slot, b].reshape(-1), new)
+                assert bool(use[slot, b]) == bool(used)
+                assert mel[slot, b] == (oc if used else 0.0)
+            assert mel[0, b] == pytest.approx(diag)
+
+
+def test_mini_batch_generator_and_sampler_bookkeeping():
+    from flowket_b200.optimization import MiniBatchGenerator
+    from flowket_b200.samplers import Sampler
+
+    class Gen(MiniBatchGenerator):
+        calls = 0
+
+        def next_batch(self):
+            Gen.calls += 1
+            return np.arange(10)[:, None] + 100 * Gen.calls, np.arange(10)
+
+    g = Gen(10, 4)
+    assert g.update_params_frequency == 3
+    x, y = next(g)
+    assert x[:, 0].tolist() == [100, 101, 102, 103]
+    next(g)
+    x, _ = next(g)           # 8 + 4 > 10 -> a new batch is drawn (mini_batch_generator.py:27-32)
+    assert Gen.calls == 2 and x[0, 0] == 200
+    assert Gen(4, 16).mini_batch_size == 4
+
+    class S(Sampler):
+        def __next__(self):
+            return None
+    s = S((3,), 8, mini_batch_size=32)
+    assert s.mini_batch_size == 8 and s.batch_size == 8
+
+
+def test_exact_utils_conventions(golden):
+    from flowket_b200.exact import utils
+    b = utils.decimal_array_to_binary_array(np.arange(32), 5, False)
+    assert np.array_equal(b.astype(np.int8), golden['bits/binary'])
+    assert np.array_equal(utils.binary_array_to_decimal_array(b), golden['bits/decimal'])
+    assert utils.binary_to_decimal(utils.decimal_to_binary(19, 6)) == 19
+    vec = np.arange(32) * (1 + 1j)
+    assert np.array_equal(utils.vector_to_machine(vec)(b[[3, 7]])[:, 0], vec[[3, 7]])
+
+
+def test_observable_generic_route_matches_reference_golden(golden):
+    """Observable's host formulas (the route used for arbitrary psi callables) against the reference's outputs;
+    find_conn is taken from the oracle here because there is no GPU in this tier."""
+    from flowket_b200.observables.monte_carlo import Observable
+    from flowket_b200.exact.utils import vector_to_machine
+    obs = Observable(operator=None)
+    psi = vector_to_machine(golden['handmade/log_psi_vector'])
+    conn = golden['handmade/local_connections'].astype(np.float64)
+    mel, use = golden['handmade/hamiltonian_values'], golden['handmade/all_use_conn']
+    unb = obs.local_values_optimized_for_unbalanced_local_connections(psi, conn, mel, use)
+    bal = obs.local_values_optimized_for_balanced_local_connections(psi, conn, mel)
+    assert np.allclose(unb, golden['handmade/unbalanced'], rtol=1e-12)
+    assert np.allclose(bal, golden['handmade/balanced'], rtol=1e-12)
+
+
+def test_sr_algebra_against_pinv():
+    """tests/test_stochastic_reconfiguration.py:32-72 of the reference (direct and CG, tol 1e-6, lambda 0.01):
+    solve vs SVD pseudo-inverse of the hand-built S, on a random centred complex Jacobian (host torch path)."""
+    from flowket_b200.optimizers import conjugate_gradient
+    from oracle import sr as osr
+    rng = np.random.default_rng(1)
+    B, P, lam = 128, 16, 0.01
+    O = rng.normal(size=(B, P)) + 1j * rng.normal(size=(B, P))
+    Ob = osr.centre(O)
+    rhs = rng.normal(size=P) + 1j * rng.normal(size=P)
+    want = np.linalg.pinv(osr.s_matrix(Ob, lam)) @ rhs
+    assert np.linalg.norm(osr.solve_direct(Ob, rhs, lam) - want) / np.linalg.norm(want) < 1e-5
+    x, it, _ = osr.solve_iterative(Ob, rhs, lam, tol=1e-6, max_iter=None)
+    assert np.linalg.norm(x - want) / np.linalg.norm(want) < 1e-5
+    Ot = torch.from_numpy(Ob)
+    xt, _, _ = conjugate_gradient(lambda v: Ot.conj().T @ (Ot @ v) / B + lam * v, torch.from_numpy(rhs), 1e-6, None)
+    assert np.linalg.norm(xt.numpy() - want) / np.linalg.norm(want) < 1e-5
+
+
+def test_lncosh_known_answers():
+    """tests/test_tensorflow_complex_numbers_ops.py:6-33 of the reference (oracle restatement, complex128)."""
+    for z in [2, 3j, 1 + 7j, 10 - 3j, -6]:
+        zt = torch.tensor([z], dtype=torch.complex128)
+        assert abs((nets.lncosh(zt) - torch.log(torch.cosh(zt))).item()) < 1e-8
