@@ -110,10 +110,17 @@ __device__ __forceinline__ void load_act_tile(float (*dst)[LDS_A], const float* 
 
 template <int NT>
 __device__ __forceinline__ void load_w_tile(float (*dst)[SC], const float* __restrict__ src, int cin, int cout) {
-  // src: [cin][cout] row-major -> dst[k][co]
-  for (int e = threadIdx.x; e < cin * cout; e += NT) {
-    const int k = e / cout, co = e - k * cout;
-    dst[k][co] = __ldg(src + e);
+  // src: [cin][cout] row-major (cout = 32 or 16, 16-byte aligned rows) -> dst[k][co]; 128-bit loads, no division
+  if (cout == SC) {
+    for (int e = threadIdx.x; e < cin * (SC / 4); e += NT) {
+      const int k = e >> 3, q = e & 7;
+      *reinterpret_cast<float4*>(&dst[k][4 * q]) = __ldg(reinterpret_cast<const float4*>(src) + e);
+    }
+  } else {  // cout == 16
+    for (int e = threadIdx.x; e < cin * (SC / 8); e += NT) {
+      const int k = e >> 2, q = e & 3;
+      *reinterpret_cast<float4*>(&dst[k][4 * q]) = __ldg(reinterpret_cast<const float4*>(src) + e);
+    }
   }
 }
 
@@ -356,14 +363,16 @@ __global__ void __launch_bounds__(8 * S / RS) sample2d_kernel(SampleArgs a) {
         __syncthreads();
       }
     }
-    // ---- (3) vertical stack of row i, all blocks, all columns
+    // ---- (3) vertical stack of row i, all blocks, all columns (weights of a block staged once per row)
     for (int b = 0; b < nb; ++b) {
       const BlockW bw = a.blocks[b];
       const int cin = cm.cin_of(b);
       const float4 bv4 = *reinterpret_cast<const float4*>(wf + bw.bV + co0);
       const float bias[4] = {bv4.x, bv4.y, bv4.z, bv4.w};
+      for (int t = 0; t < 9; ++t) load_w_tile<NT>(sm.Bw[t], wf + bw.wV + (long long)t * cin * SC, cin, SC);
       for (int j = 0; j < W; ++j) {
         int nt = 0;
+        int wt[9];
         for (int di = 0; di < 3; ++di) {
           const int row = i - 2 + di;
           if (row < 0) continue;
@@ -371,15 +380,14 @@ __global__ void __launch_bounds__(8 * S / RS) sample2d_kernel(SampleArgs a) {
             const int col = j - 1 + dj;
             if (col < 0 || col >= W) continue;
             load_act_tile<S, NT>(sm.A[nt], cache + cm.vin(b, row % 3, col), cin);
-            load_w_tile<NT>(sm.Bw[nt], wf + bw.wV + (long long)(di * 3 + dj) * cin * SC, cin, SC);
-            ++nt;
+            wt[nt++] = di * 3 + dj;
           }
         }
         __syncthreads();
         float acc[RS][4];
 #pragma unroll
         for (int r = 0; r < RS; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
-        for (int t = 0; t < nt; ++t) mma_tap<S, RS>(sm.A[t], sm.Bw[t], cin, s0, co0, acc);
+        for (int t = 0; t < nt; ++t) mma_tap<S, RS>(sm.A[t], sm.Bw[wt[t]], cin, s0, co0, acc);
         // a_b(i, j) = relu(v'), vin_{b+1}(i, j) = relu(v' [+ pair input])
         store_next_tile(cache + cm.a(b, j), nullptr, acc, bias);
         if (b + 1 < nb) {
