@@ -103,8 +103,160 @@ __global__ void __launch_bounds__(128) conv_kernel(ConvLaunch a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fast path of the gathered convolution for cin % 32 == 0 (every conv of the residual stack):
+// CTA tile 128 positions x TN channels, 256 threads, thread tile 4 positions x TN/8 channels.  The K loop walks
+// (tap, 32-channel slice) chunks; both operands are staged with 16-byte cp.async (zero-fill for taps that fall
+// outside the lattice), double-buffered, and read back with 128-bit loads along K: per 4 k-steps a thread
+// issues 4 + TN/8 LDS.128 for 16*TN/8 FFMA.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int TN>
+__global__ void __launch_bounds__(256) conv_fast_kernel(ConvLaunch a) {
+  constexpr int TM = 128, KC = 32, LDA = KC + 4, CPT = TN / 8;
+  extern __shared__ __align__(16) float conv_smem[];
+  float (*As)[TM][LDA] = reinterpret_cast<float (*)[TM][LDA]>(conv_smem);                      // [2][TM][LDA]
+  float (*Bs)[KC][TN] = reinterpret_cast<float (*)[KC][TN]>(conv_smem + 2 * TM * LDA);          // [2][KC][TN]
+  __shared__ int s_base[TM];   // flattened position of the configuration's site (0,0), or -1
+  __shared__ short s_i[TM], s_j[TM];
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 7, ty = tid >> 3;   // 8 channel groups x 32 position groups
+  const long long p0 = (long long)blockIdx.x * TM;
+  const int co0 = blockIdx.y * TN;
+  const int HW = a.H * a.W;
+  if (tid < TM) {
+    const long long p = p0 + tid;
+    if (p < a.npos) {
+      const long long n = p / HW;
+      const int rem = (int)(p - n * HW);
+      s_base[tid] = (int)(n * HW);
+      s_i[tid] = (short)(rem / a.W);
+      s_j[tid] = (short)(rem % a.W);
+    } else {
+      s_base[tid] = -1; s_i[tid] = 0; s_j[tid] = 0;
+    }
+  }
+  __syncthreads();
+
+  const int slices = a.cin / KC;
+  const int nchunks = a.ntaps * slices;
+  auto stage = [&](int chunk, int buf) {
+    const int t = chunk / slices, c0 = (chunk - t * slices) * KC;
+    const int dh = a.dh[t], dw = a.dw[t];
+    // A: 128 positions x 8 float4
+#pragma unroll
+    for (int it = 0; it < (TM * 8) / 256; ++it) {
+      const int e = tid + it * 256;
+      const int pos = e >> 3, q = e & 7;
+      const int ii = s_i[pos] + dh, jj = s_j[pos] + dw;
+      const bool ok = s_base[pos] >= 0 && ii >= 0 && ii < a.H && jj >= 0 && jj < a.W;
+      const float* src = ok ? a.in + ((long long)s_base[pos] + ii * a.W + jj) * a.in_cs + c0 + 4 * q : a.in;
+      cp_async16(&As[buf][pos][4 * q], src, ok ? 16 : 0);
+    }
+    // B: 32 k x TN channels
+    for (int e = tid; e < KC * TN / 4; e += 256) {
+      const int kk = e / (TN / 4), q = e - kk * (TN / 4);
+      const int co = co0 + 4 * q;
+      const bool ok = co < a.cout;   // cout % 4 == 0 on this path
+      const float* src = ok ? a.w + ((long long)(t * a.cin + c0 + kk)) * a.cout + co : a.w;
+      cp_async16(&Bs[buf][kk][4 * q], src, ok ? 16 : 0);
+    }
+    cp_async_commit();
+  };
+
+  float acc[4][CPT];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) acc[r][c] = 0.f;
+
+  stage(0, 0);
+  for (int chunk = 0; chunk < nchunks; ++chunk) {
+    const int buf = chunk & 1;
+    if (chunk + 1 < nchunks) {
+      stage(chunk + 1, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k4 = 0; k4 < KC; k4 += 4) {
+      float4 av[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) av[r] = *reinterpret_cast<const float4*>(&As[buf][ty + 32 * r][k4]);
+#pragma unroll
+      for (int kq = 0; kq < 4; ++kq) {
+        float bv[CPT];
+#pragma unroll
+        for (int c4 = 0; c4 < CPT; c4 += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][k4 + kq][tx * CPT + c4]);
+          bv[c4] = b4.x; bv[c4 + 1] = b4.y; bv[c4 + 2] = b4.z; bv[c4 + 3] = b4.w;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float x = kq == 0 ? av[r].x : (kq == 1 ? av[r].y : (kq == 2 ? av[r].z : av[r].w));
+#pragma unroll
+          for (int c = 0; c < CPT; ++c) acc[r][c] = fmaf(x, bv[c], acc[r][c]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int pos = ty + 32 * r;
+    const long long p = p0 + pos;
+    if (p >= a.npos) continue;
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      const int co = co0 + tx * CPT + c;
+      if (co >= a.cout) continue;
+      float z = acc[r][c];
+      float* optr = a.out + p * a.out_cs + a.out_coff + co;
+      if (a.accumulate) {
+        *optr += z;
+        continue;
+      }
+      if (a.bias) z += __ldg(a.bias + co);
+      if (a.pre) a.pre[p * a.pre_cs + co] = z;
+      if (a.out2) a.out2[p * a.out2_cs + co] = fmaxf(z, 0.f);
+      if (a.res) z += a.res[p * a.res_cs + co];
+      if (a.act == ACT_RELU) z = fmaxf(z, 0.f);
+      *optr = z;
+    }
+  }
+}
+
 int launch_conv(const ConvLaunch& a, cudaStream_t s) {
   if (a.npos == 0) return 0;
+  const bool fast = (a.cin % 32 == 0) && (a.cout % 4 == 0) && (a.in_cs % 4 == 0) && a.cout >= 32 &&
+                    ((reinterpret_cast<uintptr_t>(a.in) | reinterpret_cast<uintptr_t>(a.w)) % 16 == 0);
+  if (fast) {
+    const unsigned gx = (unsigned)((a.npos + 127) / 128);
+    if (a.cout <= 32) {
+      constexpr int smem = (2 * 128 * 36 + 2 * 32 * 32) * 4;
+      static bool once32 = false;
+      if (!once32) { FK_CHECK_CUDA(cudaFuncSetAttribute(conv_fast_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); once32 = true; }
+      conv_fast_kernel<32><<<dim3(gx, 1), 256, smem, s>>>(a);
+    } else {
+      constexpr int smem = (2 * 128 * 36 + 2 * 32 * 64) * 4;
+      static bool once64 = false;
+      if (!once64) { FK_CHECK_CUDA(cudaFuncSetAttribute(conv_fast_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); once64 = true; }
+      conv_fast_kernel<64><<<dim3(gx, (a.cout + 63) / 64), 256, smem, s>>>(a);
+    }
+    FK_CHECK_LAUNCH();
+    return 0;
+  }
   const unsigned gx = (unsigned)((a.npos + 63) / 64);
   if (a.cout <= 16) {
     conv_kernel<16><<<dim3(gx, 1), 128, 0, s>>>(a);
