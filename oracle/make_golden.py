@@ -113,5 +113,25 @@ def main():
     print('wrote', os.path.join(OUT, 'reference_numpy_half.npz'), len(out), 'arrays')
 
 
-if __name__ == '__main__':
+if __name__ == '__main__' and len(sys.argv) == 1:
     main()
+
+
+def export_pretrained_weights():
+    """tests/golden/ising_12x12_gamma3_keras_weights.npz: the reference's pretrained Keras weights
+    experiments/weights/ising_3.h5 (Ising 12x12 OBC, Gamma = 3, depth 10 / 32 channels, weight-normalised), read with
+    the repository's pure-Python HDF5 reader and stored in Keras layer-creation order.  Published evaluation
+    (experiments/README.md:43-47): E = -457.0420317, variance 0.000821, |Mz| = 0.1622 (symmetrised psi)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from flowket_b200 import Input
+    from flowket_b200.machines import ConvNetAutoregressive2D
+    from flowket_b200.utils.keras_h5 import read_keras_weights
+    m = ConvNetAutoregressive2D(Input(shape=(12, 12)), depth=10, num_of_channels=32)
+    w = read_keras_weights('/root/reference/experiments/weights/ising_3.h5', m.weight_specs())
+    path = os.path.join(OUT, 'ising_12x12_gamma3_keras_weights.npz')
+    np.savez_compressed(path, **{'w%04d' % i: a for i, a in enumerate(w)})
+    print('wrote', path, sum(a.size for a in w), 'parameters')
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'weights':
+    export_pretrained_weights()

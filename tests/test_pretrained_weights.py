@@ -1,0 +1,74 @@
+"""End-to-end pin of the network half against the REFERENCE'S OWN TRAINED WEIGHTS:
+experiments/weights/ising_3.h5 (Ising 12x12 OBC, Gamma = 3) -> published energy -457.0420317 / reference ground
+state -457.039 (experiments/README.md:43-47, experiments/ising_runner.py:27-31).  A wrong mask, shift, tap order,
+weight-norm or head convention would miss this by tens of energy units."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FIXTURE = os.path.join(ROOT, 'tests', 'golden', 'ising_12x12_gamma3_keras_weights.npz')
+E_PUBLISHED, E_GROUND = -457.0420317, -457.039
+
+
+def _weights():
+    with np.load(FIXTURE) as f:
+        return [f['w%04d' % i] for i in range(len(f.files))]
+
+
+def test_oracle_reproduces_published_energy_with_reference_weights():
+    from oracle import nets, sampler as osampler, operators as oops, local_energy as oeloc
+    torch.set_num_threads(os.cpu_count())
+    spec = nets.Conv2DSpec(12, 12, 10, 32)
+    params = [torch.from_numpy(w) for w in _weights()]
+    assert [tuple(p.shape) for p in params] == [tuple(p.shape) for p in nets.init_params(spec)]
+    u = np.random.default_rng(0).random((12, 12, 12))
+    sigma, _ = osampler.IncrementalSampler2D(spec, params).sample(u)
+    op = oops.OracleOperator('ising', (12, 12), pbc=False, h=3.0)
+    lv = oeloc.local_values(op, lambda c: nets.log_psi_numpy(spec, params, c, batch_size=512), sigma.astype(np.float64))
+    assert abs(lv.real.mean() - E_GROUND) < 0.15          # 12 samples, per-sample std ~0.08
+    assert lv.real.std() < 0.3 and abs(lv.imag).max() < 0.2
+
+
+def test_h5_reader_matches_fixture():
+    path = '/root/reference/experiments/weights/ising_3.h5'
+    if not os.path.exists(path):
+        pytest.skip('reference tree not present (GPU box)')
+    from flowket_b200 import Input, Model
+    from flowket_b200.machines import ConvNetAutoregressive2D
+    inp = Input(shape=(12, 12))
+    m = ConvNetAutoregressive2D(inp, depth=10, num_of_channels=32)
+    model = Model(inp, m.predictions)
+    model.load_weights(path)                         # Keras HDF5 through the pure-Python reader
+    for a, b in zip(model.get_weights(), _weights()):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('engine', ['fp32', 'tc'])
+def test_product_reproduces_published_energy_with_reference_weights(engine):
+    from flowket_b200 import Input, Model, FK_ENGINE_TC, FK_ENGINE_FP32
+    from flowket_b200.machines import ConvNetAutoregressive2D
+    from flowket_b200.operators import Ising
+    from flowket_b200.samplers import FastAutoregressiveSampler
+    from flowket_b200.optimization import VariationalMonteCarlo
+    inp = Input(shape=(12, 12), dtype='int8')
+    machine = ConvNetAutoregressive2D(inp, depth=10, num_of_channels=32)
+    model = Model(inp, machine.predictions)
+    model.set_weights(_weights())
+    model.engine = FK_ENGINE_TC if engine == 'tc' else FK_ENGINE_FP32
+    cond = Model(inp, machine.conditional_log_probs)
+    B = 2 ** 12
+    vmc = VariationalMonteCarlo(model, Ising(hilbert_state_shape=[12, 12], pbc=False, h=3.0),
+                                FastAutoregressiveSampler(cond, B, seed=5))
+    sigma, _ = vmc.next_batch()
+    e, var = vmc.current_energy.real, vmc.current_local_energy_variance
+    mz = np.abs(sigma.reshape(B, -1).mean(axis=1)).mean()
+    print('engine %s: E = %.5f (published %.5f, ground state %.3f), var = %.5f, |Mz| = %.4f' % (
+        engine, e, E_PUBLISHED, E_GROUND, var, mz))
+    assert abs(e - E_GROUND) < 0.02
+    assert e > E_GROUND - 0.02                       # variational (up to the MC error bar)
+    assert var < 0.05
+    assert abs(mz - 0.1622) < 0.03                    # published |Mz| at Gamma = 3
