@@ -90,15 +90,23 @@ class DeviceNet(object):
                                                   _lib.stream_ptr()))
         return out
 
-    def sample(self, batch_size, uniforms=None, seed=0, sample_offset=0, naive=False, return_p0=False):
+    def sample(self, batch_size, uniforms=None, seed=0, sample_offset=0, naive=False, return_p0=False,
+               engine=_lib.FK_ENGINE_FP32):
         torch = self.torch
         sigma = torch.empty((batch_size, self.sites), dtype=torch.int8, device=self.device)
         p0 = torch.empty((batch_size, self.sites), dtype=torch.float32, device=self.device) if return_p0 else None
         if uniforms is not None:
             uniforms = uniforms.to(device=self.device, dtype=torch.float64).reshape(batch_size, self.sites).contiguous()
-        size_fn = self.lib.fk_sample_naive_workspace_bytes if naive else self.lib.fk_sample_workspace_bytes
-        fn = self.lib.fk_sample_naive if naive else self.lib.fk_sample
-        ws = self.workspace('sample', size_fn(self.handle, batch_size))
+        if naive:
+            size_fn, fn = self.lib.fk_sample_naive_workspace_bytes, self.lib.fk_sample_naive
+        elif engine == _lib.FK_ENGINE_TC:
+            size_fn, fn = self.lib.fk_sample_tc_workspace_bytes, self.lib.fk_sample_tc
+        else:
+            size_fn, fn = self.lib.fk_sample_workspace_bytes, self.lib.fk_sample
+        nbytes = size_fn(self.handle, batch_size)
+        if nbytes < 0:
+            raise _lib.FlowketB200Error('the tensor-core sampler supports ConvNetAutoregressive2D with 32 channels only')
+        ws = self.workspace('sample', nbytes)
         with torch.cuda.device(self.device):
             _lib.check(fn(self.handle, _ptr(uniforms), seed, sample_offset, batch_size, _ptr(sigma), _ptr(p0), _ptr(ws),
                           ws.numel(), _lib.stream_ptr()))

@@ -44,6 +44,9 @@ SIGNATURES = {
     'fk_sample_workspace_bytes': (c_int64, [c_void_p, c_int64]),
     'fk_sample': (c_int, [c_void_p, c_void_p, c_uint64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
                           c_void_p]),
+    'fk_sample_tc_workspace_bytes': (c_int64, [c_void_p, c_int64]),
+    'fk_sample_tc': (c_int, [c_void_p, c_void_p, c_uint64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
+                             c_void_p]),
     'fk_sample_naive_workspace_bytes': (c_int64, [c_void_p, c_int64]),
     'fk_sample_naive': (c_int, [c_void_p, c_void_p, c_uint64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                 c_int64, c_void_p]),

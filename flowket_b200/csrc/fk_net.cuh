@@ -40,4 +40,9 @@ int64_t tc_log_psi_workspace_bytes(const fk_net* net, int64_t n);
 int tc_log_psi(fk_net* net, const int8_t* sigma, int64_t n, float* log_psi_out, void* ws, int64_t ws_bytes,
                cudaStream_t s);
 
+// tensor-core sampler (fk_tc_sample.cu)
+int64_t tc_sample_workspace_bytes(const fk_net* net, int64_t B);
+int tc_sample(fk_net* net, const double* uniforms, uint64_t seed, int64_t sample_offset, int64_t B, int8_t* sigma_out,
+              float* p0_out, void* ws, int64_t ws_bytes, cudaStream_t s);
+
 }  // namespace fk

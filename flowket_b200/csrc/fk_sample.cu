@@ -499,3 +499,17 @@ extern "C" int fk_sample(fk_net_t* net, const double* uniforms, uint64_t seed, i
   if (S == 32) return launch_sample2d<32, 1>(a, ctas, s);
   return launch_sample2d<16, 1>(a, ctas, s);
 }
+
+// tensor-core engine of the incremental sampler (fk_tc_sample.cu)
+extern "C" int64_t fk_sample_tc_workspace_bytes(const fk_net_t* net, int64_t B) {
+  if (!net) return -1;
+  if (!tc_supported(net)) return -1;
+  return tc_sample_workspace_bytes(net, std::max<int64_t>(B, 1));
+}
+
+extern "C" int fk_sample_tc(fk_net_t* net, const double* uniforms, uint64_t seed, int64_t sample_offset, int64_t B,
+                            int8_t* sigma_out, float* p0_out, void* ws, int64_t ws_bytes, void* stream) {
+  FK_REQUIRE(net && sigma_out && ws, "fk_sample_tc: NULL argument");
+  FK_REQUIRE(tc_supported(net), "fk_sample_tc: the tensor-core engine supports ConvNetAutoregressive2D with 32 channels, kernel 3 only");
+  return tc_sample(net, uniforms, seed, sample_offset, B, sigma_out, p0_out, ws, ws_bytes, (cudaStream_t)stream);
+}

@@ -34,7 +34,7 @@ class _DeviceAutoregressiveSampler(Sampler):
     naive = False
 
     def __init__(self, conditional_log_probs_machine, batch_size, mini_batch_size=None, seed=1234, sample_offset=0,
-                 **kwargs):
+                 engine=None, **kwargs):
         super(_DeviceAutoregressiveSampler, self).__init__(
             input_size=conditional_log_probs_machine.input_shape[1:], batch_size=batch_size,
             mini_batch_size=mini_batch_size)
@@ -42,6 +42,7 @@ class _DeviceAutoregressiveSampler(Sampler):
         self.machine = conditional_log_probs_machine.machine
         self.seed = seed
         self.sample_offset = sample_offset   # global index of this rank's first sample (multi-GPU sharding)
+        self.engine = engine                 # None: follow the model's engine; FK_ENGINE_FP32 / FK_ENGINE_TC
         self._draws = 0
         self.last_p0 = None
 
@@ -66,8 +67,11 @@ class _DeviceAutoregressiveSampler(Sampler):
             import torch
             uniforms = torch.as_tensor(np.asarray(uniforms, np.float64)) if not hasattr(uniforms, 'is_cuda') else uniforms
             B = uniforms.shape[0]
+        engine = getattr(self, 'engine', None)
+        if engine is None:
+            engine = getattr(self.conditional_log_probs_machine, 'engine', 0)
         res = net.sample(B, uniforms=uniforms, seed=self.seed + self._draws, sample_offset=self.sample_offset,
-                         naive=self.naive, return_p0=return_p0)
+                         naive=self.naive, return_p0=return_p0, engine=engine)
         self._draws += 1
         if return_p0:
             sigma, self.last_p0 = res

@@ -114,6 +114,13 @@ int64_t fk_sample_workspace_bytes(const fk_net_t* net, int64_t B);
 int fk_sample(fk_net_t* net, const double* uniforms, uint64_t seed, int64_t sample_offset, int64_t B,
               int8_t* sigma_out, float* p0_out, void* ws, int64_t ws_bytes, void* stream);
 
+/* Same sampler on the tcgen05 tensor cores (fp16 operands / fp32 accumulation; ConvNetAutoregressive2D, C = 32, k = 3):
+ * M = 128 samples per CTA, caches as fp16 UMMA tiles.  Statistically exact sampling from the fp16-evaluated network;
+ * spins agree with fk_sample except where |p0 - u| is within the fp16 error of p0. */
+int64_t fk_sample_tc_workspace_bytes(const fk_net_t* net, int64_t B);
+int fk_sample_tc(fk_net_t* net, const double* uniforms, uint64_t seed, int64_t sample_offset, int64_t B,
+                 int8_t* sigma_out, float* p0_out, void* ws, int64_t ws_bytes, void* stream);
+
 /* AutoregressiveSampler.__next__ (deepar/samplers/autoregressive.py:29-48; +-1 variant samplers/__init__.py:8-14):
  * one full forward per site in raster order, unsampled sites hold 0.  Works for every machine kind;
  * workspace = fk_sample_naive_workspace_bytes. */

@@ -46,3 +46,54 @@ def test_tc_local_energy():
     print('E_loc: max rel |tc - fp32| =', rel.max(), 'mean', rel.mean())
     assert rel.max() < 5e-2
     assert abs(etc.mean() - e32.mean()) / abs(e32.mean()) < 5e-3
+
+
+@pytest.mark.parametrize('shape,depth,B', [((4, 5), 3, 300), ((10, 10), 5, 200), ((6, 6), 20, 128)])
+def test_tc_sampler_matches_fp32_sampler_given_uniforms(shape, depth, B):
+    """Same uniforms -> same spins, except where |p0 - u| is inside the fp16 error of p0 (then the first differing
+    site must be such a near-tie); p0 of the agreeing prefix within 5e-3."""
+    from flowket_b200 import FK_ENGINE_TC, FK_ENGINE_FP32
+    from flowket_b200.samplers import FastAutoregressiveSampler
+    model, cond, spec, params = make_pair('conv2d', shape, depth, 32, seed=31)
+    u = np.random.RandomState(4).random_sample((B,) + shape)
+    s32 = FastAutoregressiveSampler(cond, B, engine=FK_ENGINE_FP32)
+    ref = s32.next_device(uniforms=u, return_p0=True).cpu().numpy().reshape(B, -1)
+    p_ref = s32.last_p0.cpu().numpy()
+    stc = FastAutoregressiveSampler(cond, B, engine=FK_ENGINE_TC)
+    got = stc.next_device(uniforms=u, return_p0=True).cpu().numpy().reshape(B, -1)
+    p_got = stc.last_p0.cpu().numpy()
+    uf = u.reshape(B, -1)
+    assert set(np.unique(got)) <= {-1, 1}
+    n_diff_samples = 0
+    worst = 0.0
+    for b in range(B):
+        diff = np.flatnonzero(got[b] != ref[b])
+        upto = diff[0] if len(diff) else got.shape[1] - 1
+        worst = max(worst, np.abs(p_got[b, :upto + 1] - p_ref[b, :upto + 1]).max())
+        if len(diff):
+            n_diff_samples += 1
+            assert abs(p_ref[b, diff[0]] - uf[b, diff[0]]) < 5e-3, (b, diff[0], p_ref[b, diff[0]], uf[b, diff[0]])
+    print('tc sampler', shape, depth, ': samples differing', n_diff_samples, '/', B, ' max |dp0| on agreeing prefix', worst)
+    assert worst < 5e-3
+    assert n_diff_samples <= max(2, 0.15 * B)
+
+
+def test_tc_sampler_distribution_and_shards():
+    """histogram of TC samples vs exact |psi|^2 (fp64 oracle) and shard invariance of the Philox stream"""
+    from flowket_b200 import FK_ENGINE_TC
+    from flowket_b200.samplers import FastAutoregressiveSampler
+    from oracle import exact as oexact
+    shape = (4, 3)
+    model, cond, spec, params = make_pair('conv2d', shape, 2, 32, seed=8)
+    full = FastAutoregressiveSampler(cond, 256, seed=77, engine=FK_ENGINE_TC).next_device().cpu().numpy()
+    hi = FastAutoregressiveSampler(cond, 128, seed=77, sample_offset=128, engine=FK_ENGINE_TC).next_device().cpu().numpy()
+    assert np.array_equal(full[128:], hi)
+    n = 2 ** 16
+    s = FastAutoregressiveSampler(cond, n, seed=3, engine=FK_ENGINE_TC).next_device().cpu().numpy().reshape(n, -1)
+    idx = oexact.states_to_index(s)
+    states = oexact.all_states(12).reshape((-1,) + shape)
+    probs = np.exp(2.0 * nets.log_psi_numpy(spec, params, states)[:, 0].real)
+    counts = np.bincount(idx, minlength=4096)
+    expected = n * probs
+    z = (((counts - expected) ** 2 - counts) / np.maximum(expected, 1e-12))[expected > 1e-3].sum()
+    assert z <= 3.0 * np.sqrt(n)
