@@ -145,6 +145,8 @@ def workload_config(args, world):
                         'batch %d per GPU (BASELINE.json configs[2])' % args.batch_per_gpu,
             'lattice': [H, W], 'depth': DEPTH, 'channels': CHANNELS, 'global_batch': args.batch_per_gpu * world,
             'batch_per_gpu': args.batch_per_gpu, 'engine': args.engine,
+            'precision': ('tcgen05: fp16 operands, fp32 accumulation (sampling, E_loc); gradient fp32 CUDA cores'
+                          if args.engine == 'tc' else 'fp32 CUDA cores'),
             'parallelism': 'samples sharded over %d GPU(s); allreduce of energy statistics and flat gradient' % world,
             'l2_policy': 'per-step working set (activation workspaces, several GB) is much larger than the 126 MB L2'}
 
@@ -179,6 +181,7 @@ def run_gpu(args):
     model = Model(inputs=inp, outputs=machine.predictions)
     model.engine = engine
     cond = Model(inputs=inp, outputs=machine.conditional_log_probs)
+    cond.engine = engine          # the sampler follows the engine of the conditional-log-probs model
     net = machine.device_net()
     if world > 1:   # rank-0 broadcast of the initial variables (BroadcastGlobalVariablesCallback(0))
         dist.broadcast(machine.flat_params_device(), src=0)
@@ -286,7 +289,7 @@ def run_gpu(args):
     line = {
         'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f16 operands / f32 accumulate' if args.engine == 'tc' else 'f32', 'data': 'synthetic',
+        'dtype': 'f16' if args.engine == 'tc' else 'f32', 'data': 'synthetic',
         'config': workload_config(args, world),
         'phases_ms': {k: float(np.min(v)) for k, v in phase_ms.items()},
         'sampling_samples_per_s': B * world / (float(np.min(phase_ms['sample'])) * 1e-3),
@@ -320,7 +323,9 @@ def main():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--engine', default=os.environ.get('FK_BENCH_ENGINE', 'fp32'), choices=['fp32', 'tc'])
+    ap.add_argument('--engine', default=os.environ.get('FK_BENCH_ENGINE', 'tc'), choices=['fp32', 'tc'],
+                    help='tc: tcgen05 engines for sampling and E_loc (fp16 operands / fp32 accumulate; gradient stays fp32); '
+                         'fp32: CUDA-core exact engines everywhere')
     ap.add_argument('--batch-per-gpu', type=int, default=8192)
     ap.add_argument('--cpu-batch', type=int, default=8)
     ap.add_argument('--no-cpu-baseline', action='store_true')
