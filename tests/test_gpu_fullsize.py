@@ -1,0 +1,106 @@
+"""GPU tier, BASELINE.json full sizes (Heisenberg 10x10 OBC, ConvNetAutoregressive2D depth 20 / 32 channels,
+batch 8192): size-independent properties, because the oracle cannot evaluate these sizes in seconds."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+H = W = 10
+B = 8192
+
+
+def _machine(seed=0, zero=False):
+    from flowket_b200 import Input, Model
+    from flowket_b200.machines import ConvNetAutoregressive2D
+    inp = Input(shape=(H, W), dtype='int8')
+    m = ConvNetAutoregressive2D(inp, depth=20, num_of_channels=32, seed=seed)
+    if zero:
+        m.set_weights([np.zeros(s, np.float32) if not n.endswith('/g:0') else np.zeros(s, np.float32)
+                       for n, s, _ in m.weight_specs()])
+    return inp, m, Model(inp, m.predictions), Model(inp, m.conditional_log_probs)
+
+
+def _bond_sums(sigma):
+    s = sigma.astype(np.int64)
+    zz = (s[:, :-1, :] * s[:, 1:, :]).sum(axis=(1, 2)) + (s[:, :, :-1] * s[:, :, 1:]).sum(axis=(1, 2))
+    anti = ((s[:, :-1, :] != s[:, 1:, :]).sum(axis=(1, 2)) + (s[:, :, :-1] != s[:, :, 1:]).sum(axis=(1, 2)))
+    return zz, anti
+
+
+@pytest.mark.parametrize('engine', ['fp32', 'tc'])
+def test_local_energy_of_the_uniform_state_closed_form(engine):
+    """all weights zero -> psi is constant -> E_loc(sigma) = sum_bonds s_a s_b - 2 * #antiparallel bonds (Marshall sign),
+    an exact integer: checks count/scan/generation/ratio/segmented-sum at the full batch for both engines."""
+    from flowket_b200 import FK_ENGINE_TC, FK_ENGINE_FP32
+    from flowket_b200.operators import Heisenberg
+    from flowket_b200.observables.monte_carlo import Observable
+    inp, m, model, cond = _machine(zero=True)
+    model.engine = FK_ENGINE_TC if engine == 'tc' else FK_ENGINE_FP32
+    sigma = np.random.RandomState(0).choice([-1, 1], size=(B, H, W)).astype(np.int8)
+    obs = Observable(Heisenberg(hilbert_state_shape=[H, W], pbc=False))
+    eloc = obs.local_values(model, sigma)
+    zz, anti = _bond_sums(sigma)
+    assert obs.last_num_connections == int(anti.sum()) + B            # self + one per anti-parallel bond
+    assert np.array_equal(np.round(eloc.real).astype(np.int64), zz - 2 * anti)
+    assert np.abs(eloc.real - np.round(eloc.real)).max() < 1e-3 and np.abs(eloc.imag).max() < 1e-3
+    lp = model.predict(sigma[:256])[:, 0]
+    assert np.allclose(lp.real, -0.5 * H * W * np.log(2.0), atol=1e-3)
+
+
+@pytest.mark.parametrize('engine', ['fp32', 'tc'])
+def test_sampler_probabilities_multiply_to_psi_squared(engine):
+    """ancestral sampling identity at full size: prod_s p(sigma_s | sigma_<s) reported by the sampler equals
+    |psi(sigma)|^2 from the full forward (ties the incremental caches to the full network for all 8192 samples)."""
+    from flowket_b200 import FK_ENGINE_TC, FK_ENGINE_FP32
+    from flowket_b200.samplers import FastAutoregressiveSampler
+    inp, m, model, cond = _machine(seed=3)
+    eng = FK_ENGINE_TC if engine == 'tc' else FK_ENGINE_FP32
+    sampler = FastAutoregressiveSampler(cond, B, seed=11, engine=eng)
+    sigma = sampler.next_device(return_p0=True)
+    p0 = sampler.last_p0.double().reshape(B, -1)
+    s = sigma.reshape(B, -1)
+    logp = torch.where(s > 0, torch.log(p0), torch.log1p(-p0)).sum(dim=1).cpu().numpy()
+    assert set(np.unique(s.cpu().numpy())) == {-1, 1}
+    model.engine = FK_ENGINE_FP32
+    lp = model.predict(sigma.cpu().numpy())[:, 0]
+    tol = 2e-3 if engine == 'fp32' else 0.15     # fp16 caches: |d log p| ~ 1e-3 per site, 100 sites
+    assert np.abs(logp - 2.0 * lp.real).max() < tol
+    # Philox shard invariance at full size: two half batches == the full batch
+    lo = FastAutoregressiveSampler(cond, B // 2, seed=11, engine=eng).next_device()
+    hi = FastAutoregressiveSampler(cond, B // 2, seed=11, sample_offset=B // 2, engine=eng).next_device()
+    assert torch.equal(torch.cat([lo, hi]), sigma)
+
+
+def test_tc_and_fp32_wave_functions_agree_on_connected_configurations():
+    from flowket_b200 import FK_ENGINE_TC, FK_ENGINE_FP32
+    from flowket_b200.operators import Heisenberg
+    from flowket_b200.observables.monte_carlo import Observable
+    inp, m, model, cond = _machine(seed=5)
+    sigma = np.random.RandomState(1).choice([-1, 1], size=(512, H, W)).astype(np.int8)
+    obs = Observable(Heisenberg(hilbert_state_shape=[H, W], pbc=False))
+    model.engine = FK_ENGINE_FP32
+    e32 = obs.local_values(model, sigma)
+    model.engine = FK_ENGINE_TC
+    etc = obs.local_values(model, sigma)
+    rel = np.abs(etc - e32) / np.abs(e32)
+    assert rel.max() < 5e-2 and abs(etc.mean() - e32.mean()) / abs(e32.mean()) < 2e-3
+
+
+def test_gradient_linearity_and_per_sample_consistency():
+    """grad(y1 + y2) = grad(y1) + grad(y2); sum_b 2 Re(y_b O_b) from per-sample Jacobians = weighted gradient."""
+    inp, m, model, cond = _machine(seed=7)
+    net = m.device_net()
+    rng = np.random.RandomState(2)
+    n = 1024
+    sigma = net.to_sigma(rng.choice([-1, 1], size=(n, H, W)).astype(np.int8))
+    y1 = torch.from_numpy((rng.normal(size=n) + 1j * rng.normal(size=n)).astype(np.complex64))
+    y2 = torch.from_numpy((rng.normal(size=n) + 1j * rng.normal(size=n)).astype(np.complex64))
+    g1, g2, g12 = net.grad_weighted(sigma, y1), net.grad_weighted(sigma, y2), net.grad_weighted(sigma, y1 + y2)
+    assert torch.linalg.vector_norm(g12 - g1 - g2) / torch.linalg.vector_norm(g12) < 2e-5
+    k = 16
+    O_re, O_im = net.grad_per_sample(sigma[:k], imag=True)
+    yk = y1[:k].cuda()
+    want = 2.0 * (O_re.double().T @ yk.real.double() - O_im.double().T @ yk.imag.double())
+    got = net.grad_weighted(sigma[:k], y1[:k]).double()
+    assert torch.linalg.vector_norm(got - want) / torch.linalg.vector_norm(want) < 2e-5
