@@ -145,7 +145,7 @@ def workload_config(args, world):
                         'batch %d per GPU (BASELINE.json configs[2])' % args.batch_per_gpu,
             'lattice': [H, W], 'depth': DEPTH, 'channels': CHANNELS, 'global_batch': args.batch_per_gpu * world,
             'batch_per_gpu': args.batch_per_gpu, 'engine': args.engine,
-            'precision': ('tcgen05: fp16 operands, fp32 accumulation (sampling, E_loc); gradient fp32 CUDA cores'
+            'precision': ('tcgen05: fp16 operands, fp32 accumulation (sampling, E_loc, gradient with power-of-two loss scaling)'
                           if args.engine == 'tc' else 'fp32 CUDA cores'),
             'parallelism': 'samples sharded over %d GPU(s); allreduce of energy statistics and flat gradient' % world,
             'l2_policy': 'per-step working set (activation workspaces, several GB) is much larger than the 126 MB L2'}
@@ -206,7 +206,7 @@ def run_gpu(args):
             dist.all_reduce(stats)
         mean = torch.complex(stats[0], stats[1]) / stats[3]
         y = (torch.conj(eloc - mean) / (B * world)).to(torch.complex64)
-        grad = net.grad_weighted(net.to_sigma(sigma), y) / float(B)
+        grad = net.grad_weighted(net.to_sigma(sigma), y, engine=engine) / float(B)
         if world > 1:
             dist.all_reduce(grad)
         opt.step(machine.flat_params_device(), grad)
@@ -324,7 +324,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--engine', default=os.environ.get('FK_BENCH_ENGINE', 'tc'), choices=['fp32', 'tc'],
-                    help='tc: tcgen05 engines for sampling and E_loc (fp16 operands / fp32 accumulate; gradient stays fp32); '
+                    help='tc: tcgen05 engines for sampling, E_loc and the gradient (fp16 operands / fp32 accumulate); '
                          'fp32: CUDA-core exact engines everywhere')
     ap.add_argument('--batch-per-gpu', type=int, default=8192)
     ap.add_argument('--cpu-batch', type=int, default=8)

@@ -128,16 +128,24 @@ class DeviceNet(object):
                                                     _lib.stream_ptr()))
         return torch.view_as_complex(eloc), stats, n_conn.value
 
-    def grad_weighted(self, sigma, y):
+    def grad_weighted(self, sigma, y, engine=_lib.FK_ENGINE_FP32):
         """sum_b 2 Re(log psi_b y_b) differentiated w.r.t. the flat parameter vector; y complex64 [B]"""
         torch = self.torch
         B = sigma.shape[0]
         y2 = torch.view_as_real(y.to(device=self.device, dtype=torch.complex64).contiguous()).contiguous()
         grad = torch.empty(self.num_params, dtype=torch.float32, device=self.device)
-        ws = self.workspace('grad', self.lib.fk_grad_workspace_bytes(self.handle, B, 0))
+        if engine == _lib.FK_ENGINE_TC:
+            nbytes = self.lib.fk_grad_weighted_tc_workspace_bytes(self.handle, B)
+            if nbytes < 0:
+                raise _lib.FlowketB200Error('the tensor-core gradient supports ConvNetAutoregressive2D (32 channels, '
+                                            'kernel 3) on lattices up to 10x10')
+            ws = self.workspace('grad_tc', nbytes)
+            fn = self.lib.fk_grad_weighted_tc
+        else:
+            ws = self.workspace('grad', self.lib.fk_grad_workspace_bytes(self.handle, B, 0))
+            fn = self.lib.fk_grad_weighted
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.fk_grad_weighted(self.handle, _ptr(sigma), _ptr(y2), B, _ptr(grad), _ptr(ws), ws.numel(),
-                                                 _lib.stream_ptr()))
+            _lib.check(fn(self.handle, _ptr(sigma), _ptr(y2), B, _ptr(grad), _ptr(ws), ws.numel(), _lib.stream_ptr()))
         return grad
 
     def grad_per_sample(self, sigma, imag=True):

@@ -421,7 +421,7 @@ extern "C" int fk_net_create(fk_net_t** out, int kind, int H, int W, int depth, 
   net->kind = kind; net->H = H; net->W = W; net->depth = depth; net->C = channels; net->k = kernel_size;
   net->max_dil = max_dilation; net->flags = flags; net->sites = H * W;
   net->d_params = net->d_weff = net->d_weffT = nullptr; net->d_optable = nullptr;
-  net->d_tc_weights = nullptr; net->tc_weight_bytes = 0; net->params_set = false;
+  net->d_tc_weights = nullptr; net->tc_weight_bytes = 0; net->d_tc_bwd = nullptr; net->params_set = false;
   if (kind == FK_NET_CONV2D) build_conv2d(net);
   else if (kind == FK_NET_CONV1D) build_conv1d(net);
   else build_cconv1d(net);
@@ -454,6 +454,7 @@ extern "C" int fk_net_destroy(fk_net_t* net) {
   if (!net) return 0;
   cudaFree(net->d_params); cudaFree(net->d_weff); cudaFree(net->d_weffT); cudaFree(net->d_optable);
   cudaFree(net->d_tc_weights);
+  cudaFree(net->d_tc_bwd);
   delete net;
   return 0;
 }
@@ -474,6 +475,7 @@ extern "C" int fk_net_set_params(fk_net_t* net, const float* params, void* strea
   net->params_set = true;
   if (tc_supported(net)) {
     if (tc_pack_weights(net, s)) return 1;
+    if (tc_grad_supported(net) && tc_grad_pack_weights(net, s)) return 1;
   }
   return 0;
 }
@@ -611,6 +613,15 @@ static int grad_impl(fk_net* net, const int8_t* sigma, const float* y, int64_t B
   return 0;
 }
 
+namespace fk {
+int64_t grad_transform_launch(fk_net* net, const float* geff, float* graw, cudaStream_t s) {
+  grad_transform_kernel<<<dim3((unsigned)net->ops.size(), 1), 128, 0, s>>>((const OpParam*)net->d_optable, net->d_params, geff,
+                                                                           net->num_eff, graw, net->num_params);
+  FK_CHECK_LAUNCH();
+  return 0;
+}
+}  // namespace fk
+
 extern "C" int fk_grad_weighted(fk_net_t* net, const int8_t* sigma, const float* y, int64_t B, float* grad_out, void* ws,
                                 int64_t ws_bytes, void* stream) {
   FK_REQUIRE(net && sigma && y && grad_out && ws, "fk_grad_weighted: NULL argument");
@@ -621,4 +632,18 @@ extern "C" int fk_grad_per_sample(fk_net_t* net, const int8_t* sigma, int64_t B,
                                   int64_t ws_bytes, void* stream) {
   FK_REQUIRE(net && sigma && O_re && ws, "fk_grad_per_sample: NULL argument");
   return grad_impl(net, sigma, nullptr, B, nullptr, O_re, O_im, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+// tensor-core engine of the weighted gradient (fk_tc_grad.cu)
+extern "C" int64_t fk_grad_weighted_tc_workspace_bytes(const fk_net_t* net, int64_t B) {
+  if (!net || !tc_grad_supported(net)) return -1;
+  return tc_grad_workspace_bytes(net, B);
+}
+
+extern "C" int fk_grad_weighted_tc(fk_net_t* net, const int8_t* sigma, const float* y, int64_t B, float* grad_out, void* ws,
+                                   int64_t ws_bytes, void* stream) {
+  FK_REQUIRE(net && sigma && y && grad_out && ws, "fk_grad_weighted_tc: NULL argument");
+  FK_REQUIRE(tc_grad_supported(net), "fk_grad_weighted_tc: supports ConvNetAutoregressive2D, 32 channels, kernel 3, lattices that fit one M tile");
+  if (B == 0) return 0;
+  return tc_grad_weighted(net, sigma, y, B, grad_out, ws, ws_bytes, (cudaStream_t)stream);
 }

@@ -20,6 +20,7 @@ struct fk_net {
   // tensor-core engine (ConvNetAutoregressive2D only): bf16 UMMA-canonical weight image
   void* d_tc_weights;
   int64_t tc_weight_bytes;
+  void* d_tc_bwd;                     // transposed fp16 weight images of the tensor-core backward
   bool params_set;
 };
 
@@ -39,6 +40,19 @@ int tc_pack_weights(fk_net* net, cudaStream_t s);
 int64_t tc_log_psi_workspace_bytes(const fk_net* net, int64_t n);
 int tc_log_psi(fk_net* net, const int8_t* sigma, int64_t n, float* log_psi_out, void* ws, int64_t ws_bytes,
                cudaStream_t s);
+
+struct TcPublicGeometry { int P, p_first, npos, T, nb; };
+int tc_public_geometry(const fk_net* net, TcPublicGeometry* out);
+int tc_forward_launch(fk_net* net, const int8_t* sigma, int64_t n, float* log_psi_out, uint8_t* dump,
+                      uint32_t* dump_mask, float* dump_logits, cudaStream_t s);
+
+// tensor-core gradient (fk_tc_grad.cu)
+int tc_grad_supported(const fk_net* net);
+int tc_grad_pack_weights(fk_net* net, cudaStream_t s);
+int64_t tc_grad_workspace_bytes(const fk_net* net, int64_t B);
+int tc_grad_weighted(fk_net* net, const int8_t* sigma, const float* y, int64_t B, float* grad_out, void* ws,
+                     int64_t ws_bytes, cudaStream_t s);
+int64_t grad_transform_launch(fk_net* net, const float* geff, float* graw, cudaStream_t s);
 
 // tensor-core sampler (fk_tc_sample.cu)
 int64_t tc_sample_workspace_bytes(const fk_net* net, int64_t B);

@@ -81,8 +81,15 @@ struct TcArgs {
   float* out;
   long long n;
   int H, W, P, nb, T, npos, p_first, np, tmem_cols;
+  // activation dump for the tensor-core gradient (T == 1 only): fp16 tiles [cfg][nb*5 + 1][64*npos] in the shared-memory
+  // tile layout (tensor order per block: x1, relu(v'), residual v, concat, h_out; last tile = input), relu masks
+  // [cfg][nb][5][128] (bit c = channel c active, 0 on padding rows) and logits [cfg][128][4]
+  uint8_t* dump;
+  uint32_t* dump_mask;
+  float* dump_logits;
 };
 
+constexpr int TC_DUMP_TENSORS = 5;
 constexpr int TC_MAX_T = 3;
 constexpr int TC_MAX_NP = 3;
 
@@ -198,6 +205,31 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32, 1) tc_forward_kernel(TcA
         unpack_h8(q, v + 8 * cg);
       }
     };
+    // gradient dump: this thread's row of tile `tensor` of block `b` (fp16, tile layout) + its relu mask
+    auto dump_row = [&](long long cfg, int b, int tensor, const float* v, bool valid) {
+      const size_t tile_bytes = (size_t)64 * a.npos;
+      const int tile_idx = b < 0 ? a.nb * TC_DUMP_TENSORS : b * TC_DUMP_TENSORS + tensor;
+      uint8_t* tile = a.dump + ((size_t)cfg * (a.nb * TC_DUMP_TENSORS + 1) + tile_idx) * tile_bytes;
+      uint32_t mask = 0;
+#pragma unroll
+      for (int cg = 0; cg < 4; ++cg) {
+        uint4 q;
+        q.x = pack_h2(v[8 * cg + 0], v[8 * cg + 1]);
+        q.y = pack_h2(v[8 * cg + 2], v[8 * cg + 3]);
+        q.z = pack_h2(v[8 * cg + 4], v[8 * cg + 5]);
+        q.w = pack_h2(v[8 * cg + 6], v[8 * cg + 7]);
+        *reinterpret_cast<uint4*>(tile + ((size_t)cg * a.npos + pos[0]) * 16) = q;
+        // rows outside the computed range are never written by an epilogue: keep them zero for the dW gathers
+        if (ltid < a.p_first) *reinterpret_cast<uint4*>(tile + ((size_t)cg * a.npos + ltid) * 16) = make_uint4(0, 0, 0, 0);
+        if (ltid < a.npos - a.p_first - 128)
+          *reinterpret_cast<uint4*>(tile + ((size_t)cg * a.npos + a.p_first + 128 + ltid) * 16) = make_uint4(0, 0, 0, 0);
+      }
+      if (b >= 0) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) mask |= (valid && v[c] > 0.f) ? (1u << c) : 0u;
+        a.dump_mask[(((size_t)cfg * a.nb + b) * TC_DUMP_TENSORS + tensor) * 128 + ltid] = mask;
+      }
+    };
     // one conv = NTAPS shifted views of slot `src` x 2 k-steps, accumulated into TMEM columns col0..col0+N.
     // Descriptors differ only in the 14-bit start-address field, so each MMA costs a couple of integer adds.
     auto issue_conv = [&](int src, const int* tap_off, int ntaps, int shift, uint32_t w16, bool n32, uint32_t col0) {
@@ -239,6 +271,7 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32, 1) tc_forward_kernel(TcA
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
           v[0] = sig[t];
           store_row(in_slot, pos[t], v);
+          if (a.dump && active && t == 0) dump_row(cfg, -1, 0, v, site[t] >= 0);
         }
       }
       fence_proxy_async();
@@ -275,6 +308,7 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32, 1) tc_forward_kernel(TcA
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
           }
           store_row(d.x1, pos[t], v);
+          if (a.dump && active && t == 0) dump_row(cfg, b, 0, v, site[t] >= 0);
           tmem_ld32(tm_pipe + lane_sel + (uint32_t)(t * 128) + 32, v);
           if (site[t] >= 0) {
 #pragma unroll
@@ -285,15 +319,20 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32, 1) tc_forward_kernel(TcA
 #pragma unroll
               for (int i = 0; i < 32; ++i) r[i] = fmaxf(r[i] + v[i], 0.f);
               store_row(d.out_r, pos[t], r);
+              if (a.dump && active && t == 0) dump_row(cfg, b, 2, r, true);
             }
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
-            if (d.out_r >= 0) store_row(d.out_r, pos[t], v);
+            if (d.out_r >= 0) {
+              store_row(d.out_r, pos[t], v);
+              if (a.dump && active && t == 0) dump_row(cfg, b, 2, v, false);
+            }
           }
           store_row(d.out_a, pos[t], v);
+          if (a.dump && active && t == 0) dump_row(cfg, b, 1, v, site[t] >= 0);
         }
         fence_proxy_async();
         tc_fence_before();
@@ -323,6 +362,7 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32, 1) tc_forward_kernel(TcA
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
           }
           store_row(d.c, pos[t], v);
+          if (a.dump && active && t == 0) dump_row(cfg, b, 3, v, site[t] >= 0);
         }
         fence_proxy_async();
         tc_fence_before();
@@ -356,6 +396,7 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32, 1) tc_forward_kernel(TcA
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
           }
           store_row(d.out_h, pos[t], v);
+          if (a.dump && active && t == 0) dump_row(cfg, b, 4, v, site[t] >= 0);
         }
         fence_proxy_async();
         tc_fence_before();
@@ -380,6 +421,8 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32, 1) tc_forward_kernel(TcA
             tmem_ld16(tm_pipe + lane_sel + (uint32_t)(t * 128) + 0, v);
             if (site[t] >= 0) {
               const float re0 = v[0] + hb[0], re1 = v[1] + hb[1], im0 = v[2] + hb[2], im1 = v[3] + hb[3];
+              if (a.dump && active && t == 0)
+                *reinterpret_cast<float4*>(a.dump_logits + ((size_t)cfg * 128 + ltid) * 4) = make_float4(re0, re1, im0, im1);
               const float x = 2.f * re0, y = 2.f * re1;
               const float m = fmaxf(x, y);
               const float half_lse = 0.5f * (m + logf(expf(x - m) + expf(y - m)));
@@ -530,9 +573,20 @@ int64_t tc_log_psi_workspace_bytes(const fk_net* net, int64_t n) {
   return 256;  // activations live in shared memory / TMEM
 }
 
+int tc_public_geometry(const fk_net* net, TcPublicGeometry* out) {
+  const TcGeometry g = tc_geometry(net);
+  out->P = g.P; out->p_first = g.p_first; out->npos = g.npos; out->T = g.T; out->nb = 2 * net->depth - 2;
+  return g.ok ? 0 : 1;
+}
+
 int tc_log_psi(fk_net* net, const int8_t* sigma, int64_t n, float* log_psi_out, void* ws, int64_t ws_bytes,
                cudaStream_t s) {
   (void)ws; (void)ws_bytes;
+  return tc_forward_launch(net, sigma, n, log_psi_out, nullptr, nullptr, nullptr, s);
+}
+
+int tc_forward_launch(fk_net* net, const int8_t* sigma, int64_t n, float* log_psi_out, uint8_t* dump,
+                      uint32_t* dump_mask, float* dump_logits, cudaStream_t s) {
   FK_REQUIRE(net->params_set && net->d_tc_weights, "tensor-core weights were never packed (fk_net_set_params)");
   if (n == 0) return 0;
   const TcGeometry g = tc_geometry(net);
@@ -544,6 +598,8 @@ int tc_log_psi(fk_net* net, const int8_t* sigma, int64_t n, float* log_psi_out, 
   a.sigma = sigma; a.out = log_psi_out; a.n = n;
   a.H = net->H; a.W = net->W; a.P = g.P; a.nb = nb; a.T = g.T; a.npos = g.npos; a.p_first = g.p_first; a.np = g.np;
   a.tmem_cols = g.tmem_cols;
+  a.dump = dump; a.dump_mask = dump_mask; a.dump_logits = dump_logits;
+  FK_REQUIRE(dump == nullptr || g.T == 1, "tensor-core gradient: lattice needs more than one M tile");
   int dev = 0, sms = 148;
   FK_CHECK_CUDA(cudaGetDevice(&dev));
   FK_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

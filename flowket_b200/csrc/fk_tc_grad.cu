@@ -1,0 +1,711 @@
+// Tensor-core gradient of  L = sum_b 2 Re(log psi(sigma_b) y_b)  for ConvNetAutoregressive2D (C = 32, k = 3, one M tile).
+//
+//   1. tc_forward_kernel (fk_tc.cu) in dump mode: fp16 activation tiles, relu masks and logits of every block;
+//   2. tc_backward_kernel: backward-data through all blocks in ONE persistent kernel -- the gradient tiles are the A
+//      operands (shifted views with negated tap offsets), the transposed kernels the B operands, relu masks / residual
+//      fan-out / concat split in the epilogues; it writes the pre-activation gradients dz of every conv (fp16, scaled);
+//   3. tc_dw_kernel: dW[(ci), (tap, co)] = sum_{cfg, p} x(p + off_tap)[ci] dz(p)[co] as tcgen05 MMAs with the lattice
+//      positions as the K dimension (both operands MN-major views of the dumped tiles), accumulated over configurations
+//      in TMEM, flushed once per work item with atomics; biases by a small reduction kernel;
+//   4. grad_transform_kernel (fk_net.cu): effective-weight gradient -> raw (weight-normalised) parameter gradient.
+//
+// Numerics: fp16 operands, fp32 accumulation; the head gradient is scaled by a power of two (passed by the host) so
+// that the backward tiles stay in the fp16 normal range, and the scale is removed in fp32 at the end.
+// Semantics mirror run_backward() of fk_net.cu (the fp32 engine), which is the 1e-5 contract; tolerance of this
+// engine: tests/test_gpu_tc.py.
+#include <algorithm>
+#include <vector>
+
+#include "fk_net.cuh"
+#include "fk_tc_common.cuh"
+
+namespace fk {
+
+// transposed weight image of a block (bytes)
+constexpr int IMGB_HT = 0;          // 9 taps x 2 k-steps x 1024 B : B[n = concat ch][k = h' ch]
+constexpr int IMGB_XXT = 18432;     // 1024 B                      : B[n = x1 ch (32)][k = 16]
+constexpr int IMGB_YT = 19456;      // 1024 B                      : B[n = relu(v') ch (32)][k = 16]
+constexpr int IMGB_XT = 20480;      // 3 x 2 x 1024 B              : B[n = h ch][k = x1 ch]
+constexpr int IMGB_VT = 26624;      // 9 x 2 x 1024 B              : B[n = v ch][k = v' ch]
+constexpr int IMGB_HEAD = 45056;    // fp32 [32][4] head kernel
+constexpr int IMGB_BYTES = 45568;
+constexpr int DZ_TILE = 8192;       // compact dz tile [4 cg][128 rows][8 ch] fp16
+constexpr int NDUMP = 5;            // x1, relu(v'), residual v, concat, h_out
+
+struct BwdPackDesc {
+  long long w[5];      // V, X, XX, Y, H offsets into the effective-weight buffer
+  long long w_head;
+  int cin;
+};
+
+__global__ void tc_pack_bwd_kernel(const float* __restrict__ weff, const BwdPackDesc* __restrict__ pd,
+                                   uint8_t* __restrict__ images) {
+  const BwdPackDesc d = pd[blockIdx.x];
+  uint8_t* img = images + (size_t)blockIdx.x * IMGB_BYTES;
+  __half* w16 = reinterpret_cast<__half*>(img);
+  // regions: (byte offset, taps, k-steps, forward op, forward cin, forward cout); B[n = ci][k = co]
+  const int reg_off[5] = {IMGB_HT, IMGB_XXT, IMGB_YT, IMGB_XT, IMGB_VT};
+  const int reg_taps[5] = {9, 1, 1, 3, 9};
+  const int reg_ks[5] = {2, 1, 1, 2, 2};
+  const int reg_op[5] = {4, 2, 3, 1, 0};
+  const int reg_cout[5] = {32, 16, 16, 32, 32};
+  for (int r = 0; r < 5; ++r) {
+    const int cin = (reg_op[r] <= 1) ? d.cin : 32, cout = reg_cout[r];
+    const int total = reg_taps[r] * reg_ks[r] * 2 * 32 * 8;   // (tap, kstep, kgroup, n = 32, e)
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+      const int el = e & 7, n = (e >> 3) & 31, g = (e >> 8) & 1;
+      const int ks = (e >> 9) % reg_ks[r], tap = (e >> 9) / reg_ks[r];
+      const int co = ks * 16 + g * 8 + el;
+      float v = 0.f;
+      if (n < cin && co < cout) v = weff[d.w[reg_op[r]] + ((long long)tap * cin + n) * cout + co];
+      w16[reg_off[r] / 2 + e] = __float2half_rn(v);
+    }
+  }
+  float* hw = reinterpret_cast<float*>(img + IMGB_HEAD);
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) hw[i] = weff[d.w_head + i];   // [ci][4]
+}
+
+// ---- TMEM store ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+      "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+      "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+      "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+      "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// ================================================================================================================
+// backward-data kernel
+// ================================================================================================================
+struct BwdArgs {
+  const uint8_t* images;        // nb transposed weight images
+  const uint32_t* mask;         // [cfg][nb][5][128]
+  const float* logits;          // [cfg][128][4]
+  const int8_t* sigma;          // [cfg][H*W]
+  const float* coef;            // [cfg][2]: scaled (d L / d Re log psi, d L / d Im log psi)
+  uint8_t* dz;                  // [cfg][nb][4][DZ_TILE]
+  float* glog;                  // [cfg][128][4] scaled gradient w.r.t. the logits
+  long long n;
+  int H, W, P, nb, npos_g, p_first;
+};
+
+constexpr int BWD_NP = 2;
+
+__global__ void __launch_bounds__(BWD_NP * 128 + 32, 1) tc_backward_kernel(BwdArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int pipe = tid >> 7, ltid = tid & 127;
+  const bool is_producer = warp == BWD_NP * 4;
+  const int tile_bytes = 64 * a.npos_g;
+  uint8_t* wbuf = smem;
+  uint8_t* g0 = smem + 2 * IMGB_BYTES;                                   // BWD_NP x 4 gradient tiles
+  uint8_t* tail = g0 + (size_t)BWD_NP * 4 * tile_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);                    // full[0..1], empty[2..3], mma[4..5]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 64);
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2]);
+  const uint32_t mbar = smem_u32(&bars[4 + (is_producer ? 0 : pipe)]);
+
+  if (tid == 32) {
+    mbar_init(full0, 1); mbar_init(full0 + 8, 1);
+    mbar_init(empty0, BWD_NP); mbar_init(empty0 + 8, BWD_NP);
+    for (int p = 0; p < BWD_NP; ++p) mbar_init(smem_u32(&bars[4 + p]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {
+    uint4* z = reinterpret_cast<uint4*>(g0);
+    const int n16 = BWD_NP * 4 * tile_bytes / 16;
+    for (int i = tid; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long groups = (a.n + BWD_NP - 1) / BWD_NP;
+  const long long my_iters = (long long)blockIdx.x < groups ? (groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (is_producer) {
+    const long long total = my_iters * a.nb;
+    for (long long s = 0; s < total; ++s) {
+      if ((tid & 31) == 0) {
+        const uint32_t sel = (uint32_t)(s & 1);
+        if (s >= 2) mbar_wait(empty0 + 8 * sel, (uint32_t)(((s >> 1) - 1) & 1));
+        const int b = a.nb - 1 - (int)(s % a.nb);     // blocks in reverse
+        mbar_expect_tx(full0 + 8 * sel, IMGB_BYTES);
+        bulk_g2s(smem_u32(wbuf + (size_t)sel * IMGB_BYTES), a.images + (size_t)b * IMGB_BYTES, IMGB_BYTES, full0 + 8 * sel);
+      }
+      __syncwarp();
+    }
+  } else {
+    const uint32_t tm_d = tmem_base + (uint32_t)(pipe * 128);        // MMA accumulators: 64 columns
+    const uint32_t tm_ph = tm_d + 64, tm_pv = tm_d + 96;              // pending residual gradients (fp32)
+    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
+    uint8_t* gt = g0 + (size_t)pipe * 4 * tile_bytes;                 // tiles: 0 dzH, 1 dzc, 2 dzX, 3 dzV
+    const uint32_t gt16 = smem_u32(gt) >> 4, tile16 = (uint32_t)(tile_bytes >> 4);
+    const uint32_t kstep16 = 2u * (uint32_t)a.npos_g;
+    const int HW = a.H * a.W;
+    const uint32_t idesc32 = make_idesc(32);
+    const uint64_t adesc0 = make_desc(0, a.npos_g, 8);
+    const uint64_t bdesc32 = make_desc(0, 32, 8);
+    const int bar_id = 1 + pipe;
+    const int pos = a.p_first + ltid;
+    const int r_ = pos / a.P - 2, c_ = pos % a.P - 2;
+    const int site = (c_ >= 0 && r_ < a.H) ? r_ * a.W + c_ : -1;
+
+    bool write_global = true;
+    auto store_grad_row = [&](int tile, long long cfg, int b, const float* v) {
+      uint8_t* sbase = gt + (size_t)tile * tile_bytes + (size_t)pos * 16;
+      uint8_t* gbase = a.dz + (((size_t)cfg * a.nb + b) * 4 + tile) * DZ_TILE + (size_t)ltid * 16;
+#pragma unroll
+      for (int cg = 0; cg < 4; ++cg) {
+        uint4 q;
+        q.x = pack_h2(v[8 * cg + 0], v[8 * cg + 1]);
+        q.y = pack_h2(v[8 * cg + 2], v[8 * cg + 3]);
+        q.z = pack_h2(v[8 * cg + 4], v[8 * cg + 5]);
+        q.w = pack_h2(v[8 * cg + 6], v[8 * cg + 7]);
+        *reinterpret_cast<uint4*>(sbase + (size_t)cg * a.npos_g * 16) = q;
+        if (write_global) *reinterpret_cast<uint4*>(gbase + (size_t)cg * 2048) = q;
+      }
+    };
+    // D[col0..col0+32) (+)= sum over taps of view(tile, shift_t) x B_t   (K = 32: two k-steps; ksteps = 1: K = 16)
+    auto issue = [&](int tile, int cg_off, const int* shifts, int ntaps, int ksteps, uint32_t w16, uint32_t col0) {
+      const uint64_t ad0 = adesc0 + (uint64_t)(gt16 + (uint32_t)tile * tile16 + (uint32_t)cg_off * (uint32_t)a.npos_g + (uint32_t)a.p_first);
+      uint32_t acc = 0;
+      for (int t = 0; t < ntaps; ++t) {
+        const uint64_t ad = ad0 + (uint64_t)(int64_t)shifts[t];
+        const uint64_t bd = bdesc32 + w16 + (uint64_t)(t * ksteps) * 64;
+        umma_f16(tm_d + col0, ad, bd, idesc32, acc);
+        if (ksteps == 2) umma_f16(tm_d + col0, ad + kstep16, bd + 64, idesc32, 1u);
+        acc = 1;
+      }
+    };
+
+    uint32_t mma_phase = 0;
+    long long step = 0;
+    for (long long it = 0; it < my_iters; ++it) {
+      const long long group = it * gridDim.x + blockIdx.x;
+      const long long cfg = group * BWD_NP + pipe;
+      const bool active = cfg < a.n;
+      const long long cfgc = active ? cfg : 0;          // idle pipelines replay configuration 0 and write nothing
+      write_global = active;
+      float Gh[32], Gv[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { Gh[i] = 0.f; Gv[i] = 0.f; }
+      float g4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (site >= 0) {
+        const float4 lg = *reinterpret_cast<const float4*>(a.logits + ((size_t)cfgc * 128 + ltid) * 4);
+        const float x = 2.f * lg.x, y = 2.f * lg.y;
+        const float m = fmaxf(x, y);
+        const float ea = expf(x - m), eb = expf(y - m);
+        const float p0 = ea / (ea + eb), p1 = eb / (ea + eb);
+        const int sel = (1 - (int)a.sigma[cfgc * HW + site]) >> 1;
+        const float cr = a.coef[2 * cfgc], ci = a.coef[2 * cfgc + 1];
+        g4[0] = cr * ((sel == 0 ? 1.f : 0.f) - p0);
+        g4[1] = cr * ((sel == 1 ? 1.f : 0.f) - p1);
+        g4[2] = sel == 0 ? ci : 0.f;
+        g4[3] = sel == 1 ? ci : 0.f;
+      }
+      if (active) *reinterpret_cast<float4*>(a.glog + ((size_t)cfg * 128 + ltid) * 4) = make_float4(g4[0], g4[1], g4[2], g4[3]);
+
+      for (int kb = 0; kb < a.nb; ++kb, ++step) {
+        const int b = a.nb - 1 - kb;
+        const bool last = (b == a.nb - 1);
+        const bool res2 = (b >= 2 && (b % 2) == 0 && !last);
+        const bool fop = ((b % 2) == 1 && !last);          // first block of a residual pair
+        const uint32_t wsel = (uint32_t)(step & 1);
+        mbar_wait(full0 + 8 * wsel, (uint32_t)((step >> 1) & 1));
+        const uint8_t* wimg = wbuf + (size_t)wsel * IMGB_BYTES;
+        const uint32_t wimg16 = smem_u32(wimg) >> 4;
+        const uint32_t* mk = a.mask + (((size_t)cfgc * a.nb + b) * NDUMP) * 128 + ltid;
+        const uint32_t m_x1 = mk[0], m_a = mk[128], m_r = mk[256], m_c = mk[384], m_h = mk[512];
+        if (last) {   // gradient w.r.t. the head input: W_head^T g
+          const float* hw = reinterpret_cast<const float*>(wimg + IMGB_HEAD);
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            Gh[c] = hw[c * 4 + 0] * g4[0] + hw[c * 4 + 1] * g4[1] + hw[c * 4 + 2] * g4[2] + hw[c * 4 + 3] * g4[3];
+        }
+        // ---- phase 0: dz_H = G_h * [h_out > 0]; residual fan-out
+        {
+          float v[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[c] = (m_h >> c) & 1u ? Gh[c] : 0.f;
+          store_grad_row(0, cfgc, b, v);
+          if (res2) tmem_st32(tm_ph + lane_sel, v);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        named_sync(bar_id, 128);
+        // ---- phase 1: G_c = conv^T_H(dz_H)
+        if (ltid == 0) {
+          tc_fence_after();
+          int sh[9];
+          for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) sh[i * 3 + j] = (2 - i) * a.P + (2 - j);
+          issue(0, 0, sh, 9, 2, wimg16 + IMGB_HT / 16, 0);
+          umma_commit(mbar);
+        }
+        mbar_wait(mbar, mma_phase); mma_phase ^= 1;
+        tc_fence_after();
+        {
+          float v[32];
+          tmem_ld32(tm_d + lane_sel + 0, v);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[c] = (m_c >> c) & 1u ? v[c] : 0.f;
+          store_grad_row(1, cfgc, b, v);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        named_sync(bar_id, 128);
+        // ---- phase 2: G_x1 = dz_c[:, :16] W_XX^T (RightShift^T in the last block), G_a += shift(dz_c[:, 16:] W_Y^T)
+        if (ltid == 0) {
+          tc_fence_after();
+          int s1[1] = {last ? 1 : 0};
+          issue(1, 0, s1, 1, 1, wimg16 + IMGB_XXT / 16, 0);
+          int s2[1] = {a.P};
+          issue(1, 2, s2, 1, 1, wimg16 + IMGB_YT / 16, 32);
+          umma_commit(mbar);
+        }
+        mbar_wait(mbar, mma_phase); mma_phase ^= 1;
+        tc_fence_after();
+        {
+          float v[32];
+          tmem_ld32(tm_d + lane_sel + 0, v);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[c] = (m_x1 >> c) & 1u ? v[c] : 0.f;
+          store_grad_row(2, cfgc, b, v);
+          tmem_ld32(tm_d + lane_sel + 32, v);
+          if (res2) {
+            float pv[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              pv[c] = (m_r >> c) & 1u ? Gv[c] : 0.f;
+              v[c] = ((m_a >> c) & 1u ? v[c] : 0.f) + pv[c];
+            }
+            tmem_st32(tm_pv + lane_sel, pv);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] = (m_a >> c) & 1u ? v[c] + Gv[c] : 0.f;
+          }
+          store_grad_row(3, cfgc, b, v);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        named_sync(bar_id, 128);
+        // ---- phase 3: G_hin = conv^T_X(dz_X), G_vin = conv^T_V(dz_V)   (not needed below the first block)
+        if (b > 0) {
+          if (ltid == 0) {
+            tc_fence_after();
+            int sx[3] = {2, 1, 0};
+            issue(2, 0, sx, 3, 2, wimg16 + IMGB_XT / 16, 0);
+            int sv[9];
+            for (int i = 0; i < 3; ++i)
+              for (int j = 0; j < 3; ++j) sv[i * 3 + j] = (2 - i) * a.P + (1 - j);
+            issue(3, 0, sv, 9, 2, wimg16 + IMGB_VT / 16, 32);
+            umma_commit(mbar);
+          }
+          mbar_wait(mbar, mma_phase); mma_phase ^= 1;
+          tc_fence_after();
+          tmem_ld32(tm_d + lane_sel + 0, Gh);
+          tmem_ld32(tm_d + lane_sel + 32, Gv);
+          if (fop) {
+            float pd[32];
+            tmem_ld32(tm_ph + lane_sel, pd);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) Gh[c] += pd[c];
+            tmem_ld32(tm_pv + lane_sel, pd);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) Gv[c] += pd[c];
+          }
+          tc_fence_before();
+          named_sync(bar_id, 128);
+        }
+        if (ltid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8 * wsel) : "memory");
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+}
+
+// ================================================================================================================
+// weight-gradient kernel: positions are the K dimension
+// ================================================================================================================
+struct DwConv {
+  int x_tile;       // dump tile index of the conv input
+  int dz_tile;      // dz tile index (0..3) of the block
+  int dz_cg;        // first channel group of dz (0, or 2 for the relu(v') half of the concat gradient)
+  int ntaps, n;     // taps, output channels (32 or 16)
+  int off[9];       // position offsets of the taps (forward direction), including the p_first base
+  int col0;         // first TMEM column
+  int cin;          // forward input channels (1 for the first block's V and X convs)
+  long long w_off;  // offset of dW in the effective-weight gradient
+};
+struct DwUnit { int b, nconv; DwConv conv[3]; };
+
+struct DwArgs2 {
+  const uint8_t* dump; const uint8_t* dz; const DwUnit* units; float* geff;
+  long long n; int nb, npos, num_units, cfg_chunk;
+};
+
+constexpr int DW_STAGES = 3;
+
+__global__ void __launch_bounds__(128, 1) tc_dw_kernel(DwArgs2 a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int xt_bytes = 64 * a.npos;
+  const int stage_bytes = 3 * (xt_bytes + DZ_TILE);
+  uint8_t* tail = smem + (size_t)DW_STAGES * stage_bytes + 16 * a.npos * 16;   // slack: M rows 32..127 read past the tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);      // full[0..2], empty[3..5], done[6]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 64);
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[DW_STAGES]), done = smem_u32(&bars[2 * DW_STAGES]);
+  if (tid == 32) {
+    for (int i = 0; i < DW_STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {  // the slack region is read as garbage M rows: keep it finite
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    const int n16 = (DW_STAGES * stage_bytes + 16 * a.npos * 16) / 16;
+    for (int i = tid; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const size_t dump_cfg_bytes = (size_t)(a.nb * NDUMP + 1) * xt_bytes;
+  // A: x tile, MN-major: 8 channels contiguous (16 B), channel groups npos*16 B apart, positions 16 B apart,
+  //    groups of 8 positions 128 B apart.  B: dz tile, MN-major, channel groups 2048 B apart.
+  const uint64_t adesc0 = make_desc(0, 8, a.npos);
+  const uint64_t bdesc0 = make_desc(0, 8, 128);
+
+  const int chunks = (int)((a.n + a.cfg_chunk - 1) / a.cfg_chunk);
+  const int items = a.num_units * chunks;
+  uint32_t full_phase = 0, empty_phase = 0, done_phase = 0;   // bit i = parity of stage i
+  long long prod_count = 0, cons_count = 0;
+
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const DwUnit& u = a.units[item % a.num_units];
+    const long long c_beg = (long long)(item / a.num_units) * a.cfg_chunk;
+    const long long c_end = c_beg + a.cfg_chunk < a.n ? c_beg + a.cfg_chunk : a.n;
+    if (warp == 0) {
+      // ---- producer: one stage per configuration
+      for (long long cfg = c_beg; cfg < c_end; ++cfg) {
+        if (lane == 0) {
+          const int st = (int)(prod_count % DW_STAGES);
+          if (prod_count >= DW_STAGES) { mbar_wait(empty0 + 8 * st, (empty_phase >> st) & 1u); empty_phase ^= 1u << st; }
+          uint8_t* sb = smem + (size_t)st * stage_bytes;
+          mbar_expect_tx(full0 + 8 * st, (uint32_t)u.nconv * (xt_bytes + DZ_TILE));
+          for (int k = 0; k < u.nconv; ++k) {
+            bulk_g2s(smem_u32(sb + (size_t)k * xt_bytes), a.dump + (size_t)cfg * dump_cfg_bytes + (size_t)u.conv[k].x_tile * xt_bytes,
+                     xt_bytes, full0 + 8 * st);
+            bulk_g2s(smem_u32(sb + (size_t)3 * xt_bytes + (size_t)k * DZ_TILE),
+                     a.dz + (((size_t)cfg * a.nb + u.b) * 4 + u.conv[k].dz_tile) * DZ_TILE, DZ_TILE, full0 + 8 * st);
+          }
+          ++prod_count;
+        }
+        __syncwarp();
+      }
+      prod_count = __shfl_sync(0xffffffffu, prod_count, 0);
+      empty_phase = __shfl_sync(0xffffffffu, empty_phase, 0);
+    } else if (warp == 1) {
+      // ---- MMA issuer
+      for (long long cfg = c_beg; cfg < c_end; ++cfg) {
+        if (lane == 0) {
+          const int st = (int)(cons_count % DW_STAGES);
+          mbar_wait(full0 + 8 * st, (full_phase >> st) & 1u); full_phase ^= 1u << st;
+          tc_fence_after();
+          const uint32_t sb16 = smem_u32(smem + (size_t)st * stage_bytes) >> 4;
+          for (int k = 0; k < u.nconv; ++k) {
+            const DwConv& cv = u.conv[k];
+            const uint32_t idesc = make_idesc(cv.n) | (1u << 15) | (1u << 16);   // A and B MN-major
+            const uint32_t x16 = sb16 + (uint32_t)k * (uint32_t)(xt_bytes >> 4);
+            const uint32_t d16 = sb16 + (uint32_t)(3 * (xt_bytes >> 4)) + (uint32_t)k * (DZ_TILE >> 4) + (uint32_t)cv.dz_cg * 128u;
+            for (int t = 0; t < cv.ntaps; ++t) {
+              const uint32_t dcol = tmem + (uint32_t)(cv.col0 + t * cv.n);
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) {
+                const uint64_t ad = adesc0 + (uint64_t)(x16 + (uint32_t)(cv.off[t] + 16 * ks));
+                const uint64_t bd = bdesc0 + (uint64_t)(d16 + (uint32_t)(16 * ks));
+                umma_f16(dcol, ad, bd, idesc, (cfg > c_beg || ks > 0) ? 1u : 0u);
+              }
+            }
+          }
+          umma_commit(empty0 + 8 * st);                 // stage free when its MMAs retire
+          if (cfg + 1 == c_end) umma_commit(done);
+          ++cons_count;
+        }
+        __syncwarp();
+      }
+      cons_count = __shfl_sync(0xffffffffu, cons_count, 0);
+      full_phase = __shfl_sync(0xffffffffu, full_phase, 0);
+    }
+    // ---- flush: warp 0 owns TMEM lanes 0..31 = input channels
+    if (warp == 0) {
+      mbar_wait(done, done_phase); done_phase ^= 1;
+      tc_fence_after();
+      for (int k = 0; k < u.nconv; ++k) {
+        const DwConv& cv = u.conv[k];
+        for (int t = 0; t < cv.ntaps; ++t) {
+          float v[32];
+          if (cv.n == 32) {
+            tmem_ld32(tmem + (uint32_t)(cv.col0 + t * 32), v);
+          } else {
+            float h[16];
+            tmem_ld16(tmem + (uint32_t)(cv.col0 + t * 16), h);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = h[i];
+          }
+          if (lane < cv.cin) {
+            float* dst = a.geff + cv.w_off + ((long long)t * cv.cin + lane) * cv.n;
+            for (int co = 0; co < cv.n; ++co) atomicAdd(dst + co, v[co]);
+          }
+        }
+      }
+      tc_fence_before();
+    }
+    __syncthreads();   // the next item re-initialises the accumulators only after the flush
+    tc_fence_after();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// bias gradients: db[op][co] = sum_{cfg, rows} dz;  grid (nb * 4 dz tiles, splits)
+__global__ void tc_db_kernel(const uint8_t* __restrict__ dz, long long n, int nb, const long long* __restrict__ b_off,
+                             float* __restrict__ geff) {
+  // b_off: [nb][5] bias offsets of V, X, XX, Y, H in the effective-weight gradient
+  const int b = blockIdx.x >> 2, tile = blockIdx.x & 3;
+  const int ch = threadIdx.x & 31, part = threadIdx.x >> 5;    // 256 threads: 8 row groups x 32 channels
+  float acc = 0.f;
+  for (long long cfg = blockIdx.y; cfg < n; cfg += gridDim.y) {
+    const __half* t = reinterpret_cast<const __half*>(dz + (((size_t)cfg * nb + b) * 4 + tile) * DZ_TILE);
+    for (int r = part; r < 128; r += 8) acc += __half2float(t[((ch >> 3) * 128 + r) * 8 + (ch & 7)]);
+  }
+  __shared__ float red[8][32];
+  red[part][ch] = acc;
+  __syncthreads();
+  if (part == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i][ch];
+    // dz tiles: 0 dzH -> H bias; 1 dzc -> XX (ch 0..15), Y (16..31); 2 dzX -> X; 3 dzV -> V
+    long long off;
+    if (tile == 0) off = b_off[b * 5 + 4] + ch;
+    else if (tile == 1) off = ch < 16 ? b_off[b * 5 + 2] + ch : b_off[b * 5 + 3] + ch - 16;
+    else if (tile == 2) off = b_off[b * 5 + 1] + ch;
+    else off = b_off[b * 5 + 0] + ch;
+    atomicAdd(geff + off, s);
+  }
+}
+
+// head: dW_head[ci][k] = sum h_out_last[p][ci] g[p][k], db_head[k] = sum g[p][k]
+__global__ void tc_head_dw_kernel(const uint8_t* __restrict__ dump, const float* __restrict__ glog, long long n, int nb, int npos,
+                                  int p_first, long long w_off, long long b_off, float* __restrict__ geff) {
+  const int ci = threadIdx.x & 31, part = threadIdx.x >> 5;   // 256 threads
+  const size_t xt = (size_t)64 * npos, cfg_bytes = (size_t)(nb * NDUMP + 1) * xt;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, bacc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long cfg = blockIdx.x; cfg < n; cfg += gridDim.x) {
+    const __half* t = reinterpret_cast<const __half*>(dump + (size_t)cfg * cfg_bytes + (size_t)((nb - 1) * NDUMP + 4) * xt);
+    for (int r = part; r < 128; r += 8) {
+      const float4 g = *reinterpret_cast<const float4*>(glog + ((size_t)cfg * 128 + r) * 4);
+      const float h = __half2float(t[((size_t)(ci >> 3) * npos + p_first + r) * 8 + (ci & 7)]);
+      acc[0] += h * g.x; acc[1] += h * g.y; acc[2] += h * g.z; acc[3] += h * g.w;
+      if (ci == 0) { bacc[0] += g.x; bacc[1] += g.y; bacc[2] += g.z; bacc[3] += g.w; }
+    }
+  }
+  for (int k = 0; k < 4; ++k) {
+    atomicAdd(geff + w_off + ci * 4 + k, acc[k]);
+    if (ci == 0) atomicAdd(geff + b_off + k, bacc[k]);
+  }
+}
+
+// power-of-two loss scale chosen on the device: max |2 y| * scale <= 128 (head gradients in the fp16 normal range)
+__global__ void tc_absmax_kernel(const float* __restrict__ y, long long n2, unsigned int* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n2) atomicMax(out, __float_as_uint(fabsf(y[i])));
+}
+__global__ void tc_setscale_kernel(const unsigned int* __restrict__ absmax, float* __restrict__ scale) {
+  const float m = __uint_as_float(*absmax);
+  float s = 1.f;
+  if (m > 0.f && isfinite(m)) s = exp2f(fminf(fmaxf(floorf(log2f(64.f / m)), -60.f), 60.f));
+  scale[0] = s;
+  scale[1] = 1.f / s;
+}
+__global__ void tc_coef_kernel(const float* __restrict__ y, long long n, const float* __restrict__ scale, float* __restrict__ coef) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  coef[2 * i] = 2.f * y[2 * i] * scale[0];         // d L / d Re log psi
+  coef[2 * i + 1] = -2.f * y[2 * i + 1] * scale[0];  // d L / d Im log psi
+}
+__global__ void tc_scale_kernel(float* __restrict__ p, long long n, const float* __restrict__ scale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] *= scale[1];
+}
+
+// ================================================================================================================
+// host
+// ================================================================================================================
+int tc_grad_supported(const fk_net* net) {
+  if (!tc_supported(net)) return 0;
+  TcPublicGeometry g;
+  if (tc_public_geometry(net, &g)) return 0;
+  return g.T == 1 ? 1 : 0;
+}
+
+static size_t bwd_units_offset(int nb) { return ((size_t)nb * IMGB_BYTES + 255) / 256 * 256; }
+static size_t bwd_boff_offset(int nb) { return bwd_units_offset(nb) + ((size_t)2 * nb * sizeof(DwUnit) + 255) / 256 * 256; }
+static size_t bwd_pack_offset(int nb) { return bwd_boff_offset(nb) + ((size_t)nb * 5 * sizeof(long long) + 255) / 256 * 256; }
+
+int tc_grad_pack_weights(fk_net* net, cudaStream_t s) {
+  TcPublicGeometry g;
+  tc_public_geometry(net, &g);
+  const int nb = g.nb;
+  if (!net->d_tc_bwd) {
+    FK_CHECK_CUDA(cudaMalloc(&net->d_tc_bwd, bwd_pack_offset(nb) + sizeof(BwdPackDesc) * nb));
+    std::vector<BwdPackDesc> pd(nb);
+    std::vector<long long> boff(nb * 5);
+    std::vector<DwUnit> units(2 * nb);
+    auto res2 = [&](int b) { return b >= 2 && b % 2 == 0 && b != nb - 1; };
+    for (int b = 0; b < nb; ++b) {
+      const ConvOp* o = &net->ops[5 * b];
+      for (int r = 0; r < 5; ++r) { pd[b].w[r] = o[r].w_off; boff[b * 5 + r] = o[r].b_off; }
+      pd[b].w_head = net->ops.back().w_off;
+      pd[b].cin = b == 0 ? 1 : 32;
+      const bool last = b == nb - 1;
+      const int in_tile = nb * NDUMP;
+      const int vin = b == 0 ? in_tile : (res2(b - 1) ? (b - 1) * NDUMP + 2 : (b - 1) * NDUMP + 1);
+      const int hin = b == 0 ? in_tile : (b - 1) * NDUMP + 4;
+      DwUnit& A = units[2 * b];        // pass A: H, XX, Y
+      A.b = b; A.nconv = 3;
+      A.conv[0] = DwConv{b * NDUMP + 3, 0, 0, 9, 32, {0}, 0, 32, o[4].w_off};
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) A.conv[0].off[i * 3 + j] = g.p_first + (i - 2) * g.P + (j - 2);
+      A.conv[1] = DwConv{b * NDUMP + 0, 1, 0, 1, 16, {0}, 288, 32, o[2].w_off};
+      A.conv[1].off[0] = g.p_first + (last ? -1 : 0);
+      A.conv[2] = DwConv{b * NDUMP + 1, 1, 2, 1, 16, {0}, 304, 32, o[3].w_off};
+      A.conv[2].off[0] = g.p_first - g.P;
+      DwUnit& Bu = units[2 * b + 1];   // pass B: V, X
+      Bu.b = b; Bu.nconv = 2;
+      Bu.conv[0] = DwConv{vin, 3, 0, 9, 32, {0}, 0, pd[b].cin, o[0].w_off};
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Bu.conv[0].off[i * 3 + j] = g.p_first + (i - 2) * g.P + (j - 1);
+      Bu.conv[1] = DwConv{hin, 2, 0, 3, 32, {0}, 288, pd[b].cin, o[1].w_off};
+      for (int j = 0; j < 3; ++j) Bu.conv[1].off[j] = g.p_first + (j - 2);
+    }
+    uint8_t* base = (uint8_t*)net->d_tc_bwd;
+    FK_CHECK_CUDA(cudaMemcpy(base + bwd_units_offset(nb), units.data(), sizeof(DwUnit) * units.size(), cudaMemcpyHostToDevice));
+    FK_CHECK_CUDA(cudaMemcpy(base + bwd_boff_offset(nb), boff.data(), sizeof(long long) * boff.size(), cudaMemcpyHostToDevice));
+    FK_CHECK_CUDA(cudaMemcpy(base + bwd_pack_offset(nb), pd.data(), sizeof(BwdPackDesc) * nb, cudaMemcpyHostToDevice));
+  }
+  tc_pack_bwd_kernel<<<nb, 256, 0, s>>>(net->d_weff, reinterpret_cast<const BwdPackDesc*>((uint8_t*)net->d_tc_bwd + bwd_pack_offset(nb)),
+                                       (uint8_t*)net->d_tc_bwd);
+  FK_CHECK_LAUNCH();
+  return 0;
+}
+
+struct GradLayout { size_t dump, mask, logits, dz, glog, coef, geff, lp, scale, total; int64_t chunk; };
+
+static GradLayout grad_layout(const fk_net* net, int64_t chunk) {
+  TcPublicGeometry g;
+  tc_public_geometry(net, &g);
+  GradLayout L;
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  size_t o = 0;
+  L.scale = o; o = al(o + 64);
+  L.geff = o; o = al(o + sizeof(float) * net->num_eff);
+  L.dump = o; o = al(o + (size_t)chunk * (g.nb * NDUMP + 1) * 64 * g.npos);
+  L.mask = o; o = al(o + (size_t)chunk * g.nb * NDUMP * 128 * 4);
+  L.logits = o; o = al(o + (size_t)chunk * 128 * 16);
+  L.dz = o; o = al(o + (size_t)chunk * g.nb * 4 * DZ_TILE);
+  L.glog = o; o = al(o + (size_t)chunk * 128 * 16);
+  L.coef = o; o = al(o + (size_t)chunk * 8);
+  L.lp = o; o = al(o + (size_t)chunk * 8);
+  L.total = o; L.chunk = chunk;
+  return L;
+}
+
+int64_t tc_grad_workspace_bytes(const fk_net* net, int64_t B) {
+  return (int64_t)grad_layout(net, std::max<int64_t>(1, std::min<int64_t>(B, 2048))).total;
+}
+
+int tc_grad_weighted(fk_net* net, const int8_t* sigma, const float* y, int64_t B, float* grad_out, void* ws, int64_t ws_bytes,
+                     cudaStream_t s) {
+  FK_REQUIRE(net->params_set && net->d_tc_bwd, "tensor-core gradient weights were never packed (fk_net_set_params)");
+  TcPublicGeometry g;
+  tc_public_geometry(net, &g);
+  int64_t chunk = std::min<int64_t>(B, 2048);
+  while (chunk > 1 && (int64_t)grad_layout(net, chunk).total > ws_bytes) chunk /= 2;
+  const GradLayout L = grad_layout(net, chunk);
+  FK_REQUIRE((int64_t)L.total <= ws_bytes, "tensor-core gradient: workspace too small (%lld < %zu bytes)", (long long)ws_bytes, L.total);
+  uint8_t* base = (uint8_t*)ws;
+  float* geff = (float*)(base + L.geff);
+  FK_CHECK_CUDA(cudaMemsetAsync(geff, 0, sizeof(float) * net->num_eff, s));
+  unsigned int* absmax = (unsigned int*)(base + L.scale);
+  float* scale = (float*)(base + L.scale) + 4;
+  FK_CHECK_CUDA(cudaMemsetAsync(absmax, 0, 16, s));
+  tc_absmax_kernel<<<(unsigned)((2 * B + 255) / 256), 256, 0, s>>>(y, 2 * B, absmax);
+  FK_CHECK_LAUNCH();
+  tc_setscale_kernel<<<1, 1, 0, s>>>(absmax, scale);
+  FK_CHECK_LAUNCH();
+  const int nb = g.nb;
+  const int npos_g = ((g.p_first + 128 + 2 * g.P + 4) + 7) / 8 * 8;
+  int dev = 0, sms = 148;
+  FK_CHECK_CUDA(cudaGetDevice(&dev));
+  FK_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const size_t bwd_smem = 2 * (size_t)IMGB_BYTES + (size_t)BWD_NP * 4 * 64 * npos_g + 256;
+  const size_t dw_smem = (size_t)DW_STAGES * 3 * (64 * g.npos + DZ_TILE) + (size_t)16 * g.npos * 16 + 256;
+  FK_REQUIRE(bwd_smem <= 227 * 1024 && dw_smem <= 227 * 1024, "tensor-core gradient: lattice too large for shared memory");
+  FK_CHECK_CUDA(cudaFuncSetAttribute(tc_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem));
+  FK_CHECK_CUDA(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem));
+  const uint8_t* wb = (const uint8_t*)net->d_tc_bwd;
+  for (int64_t i = 0; i < B; i += chunk) {
+    const int64_t m = std::min(chunk, B - i);
+    const int8_t* sg = sigma + i * net->sites;
+    tc_coef_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(y + 2 * i, m, scale, (float*)(base + L.coef));
+    FK_CHECK_LAUNCH();
+    if (tc_forward_launch(net, sg, m, (float*)(base + L.lp), base + L.dump, (uint32_t*)(base + L.mask), (float*)(base + L.logits), s)) return 1;
+    BwdArgs ba;
+    ba.images = wb; ba.mask = (const uint32_t*)(base + L.mask); ba.logits = (const float*)(base + L.logits);
+    ba.sigma = sg; ba.coef = (const float*)(base + L.coef); ba.dz = base + L.dz; ba.glog = (float*)(base + L.glog);
+    ba.n = m; ba.H = net->H; ba.W = net->W; ba.P = g.P; ba.nb = nb; ba.npos_g = npos_g; ba.p_first = g.p_first;
+    const long long groups = (m + BWD_NP - 1) / BWD_NP;
+    tc_backward_kernel<<<(unsigned)std::min<long long>(groups, sms), BWD_NP * 128 + 32, bwd_smem, s>>>(ba);
+    FK_CHECK_LAUNCH();
+    DwArgs2 da;
+    da.dump = base + L.dump; da.dz = base + L.dz; da.units = reinterpret_cast<const DwUnit*>(wb + bwd_units_offset(nb));
+    da.geff = geff; da.n = m; da.nb = nb; da.npos = g.npos; da.num_units = 2 * nb;
+    da.cfg_chunk = (int)std::max<int64_t>(1, (m + 7) / 8);
+    const int items = da.num_units * (int)((m + da.cfg_chunk - 1) / da.cfg_chunk);
+    tc_dw_kernel<<<(unsigned)std::min(items, sms), 128, dw_smem, s>>>(da);
+    FK_CHECK_LAUNCH();
+    tc_db_kernel<<<dim3((unsigned)(nb * 4), 8), 256, 0, s>>>(base + L.dz, m, nb, reinterpret_cast<const long long*>(wb + bwd_boff_offset(nb)), geff);
+    FK_CHECK_LAUNCH();
+    tc_head_dw_kernel<<<64, 256, 0, s>>>(base + L.dump, (const float*)(base + L.glog), m, nb, g.npos, g.p_first,
+                                         net->ops.back().w_off, net->ops.back().b_off, geff);
+    FK_CHECK_LAUNCH();
+  }
+  tc_scale_kernel<<<(unsigned)((net->num_eff + 255) / 256), 256, 0, s>>>(geff, net->num_eff, scale);
+  FK_CHECK_LAUNCH();
+  if (grad_transform_launch(net, geff, grad_out, s)) return 1;
+  return 0;
+}
+
+}  // namespace fk

@@ -54,7 +54,7 @@ class Trainer(object):
         net = self.machine.device_net()
         sigma = net.to_sigma(x)
         y_t = torch.as_tensor(np.asarray(y, np.complex64)) if not hasattr(y, 'is_cuda') else y
-        return net.grad_weighted(sigma, y_t) / float(sigma.shape[0])
+        return net.grad_weighted(sigma, y_t, engine=getattr(self.model, 'engine', 0)) / float(sigma.shape[0])
 
     def train_step(self):
         """One parameter update = `update_params_frequency` mini-batches of the generator."""

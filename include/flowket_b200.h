@@ -155,6 +155,13 @@ int fk_grad_weighted(fk_net_t* net, const int8_t* sigma, const float* y, int64_t
 int fk_grad_per_sample(fk_net_t* net, const int8_t* sigma, int64_t B, float* O_re, float* O_im,
                        void* ws, int64_t ws_bytes, void* stream);
 
+/* fk_grad_weighted on the tcgen05 tensor cores (fp16 operands / fp32 accumulation, power-of-two loss scaling):
+ * forward with activation dump -> fused backward-data kernel -> weight gradients as MMAs over the lattice positions.
+ * ConvNetAutoregressive2D, C = 32, k = 3, lattices that fit one 128-row tile (up to 10x10). */
+int64_t fk_grad_weighted_tc_workspace_bytes(const fk_net_t* net, int64_t B);
+int fk_grad_weighted_tc(fk_net_t* net, const int8_t* sigma, const float* y, int64_t B, float* grad_out,
+                        void* ws, int64_t ws_bytes, void* stream);
+
 /* ---- stochastic reconfiguration: replaces the S-matrix algebra of
  * optimizers/stochastic_reconfiguration/optimizer.py:55-108.
  * fk_sr_gram: G[M,M] = A^T A (transpose_a=1, A is [K,M]) or A A^T (transpose_a=0, A is [M,K]),

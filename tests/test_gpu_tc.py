@@ -97,3 +97,31 @@ def test_tc_sampler_distribution_and_shards():
     expected = n * probs
     z = (((counts - expected) ** 2 - counts) / np.maximum(expected, 1e-12))[expected > 1e-3].sum()
     assert z <= 3.0 * np.sqrt(n)
+
+
+@pytest.mark.parametrize('shape,depth,B', [((4, 4), 2, 37), ((4, 5), 3, 64), ((6, 6), 5, 130), ((10, 10), 20, 96)])
+def test_tc_gradient_matches_fp32_gradient(shape, depth, B):
+    """tensor-core weighted gradient (fp16 operands, loss-scaled) vs the fp32 engine: stated tolerance 2e-2 in norm"""
+    from flowket_b200 import FK_ENGINE_TC, FK_ENGINE_FP32
+    model, _, spec, params = make_pair('conv2d', shape, depth, 32, seed=17)
+    net = model.machine.device_net()
+    sigma = net.to_sigma(random_sigma(B, shape, seed=5))
+    rng = np.random.RandomState(1)
+    y = torch.from_numpy(((rng.normal(size=B) + 1j * rng.normal(size=B)) / B).astype(np.complex64))
+    g32 = net.grad_weighted(sigma, y, engine=FK_ENGINE_FP32).cpu().numpy().astype(np.float64)
+    gtc = net.grad_weighted(sigma, y, engine=FK_ENGINE_TC).cpu().numpy().astype(np.float64)
+    rel = np.linalg.norm(gtc - g32) / np.linalg.norm(g32)
+    cos = (gtc @ g32) / (np.linalg.norm(gtc) * np.linalg.norm(g32))
+    # per-tensor breakdown helps to localise a wiring error
+    off, worst = 0, (0.0, '')
+    for name, shp, _ in model.machine.weight_specs():
+        n = int(np.prod(shp))
+        a, b = gtc[off:off + n], g32[off:off + n]
+        if np.linalg.norm(b) > 1e-12:
+            r = np.linalg.norm(a - b) / np.linalg.norm(b)
+            if r > worst[0]:
+                worst = (r, name)
+        off += n
+    print('tc gradient', shape, depth, 'rel err', rel, 'cos', cos, 'worst tensor', worst)
+    assert np.isfinite(gtc).all()
+    assert rel < 2e-2 and cos > 0.9995
