@@ -96,6 +96,7 @@ constexpr int TC_MAX_NP = 3;
 // Thread layout: np pipelines x 128 threads (one configuration each) + 1 producer warp (weight images).
 // Barriers: full[2] (weights landed, tx-count), empty[2] (np arrivals: every pipeline is done with the image),
 //           mma[np] (tcgen05.commit of the pipeline's current phase).
+template <bool DUMP>
 __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32, 1) tc_forward_kernel(TcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32, 1) tc_forward_kernel(TcA
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
           v[0] = sig[t];
           store_row(in_slot, pos[t], v);
-          if (a.dump && active && t == 0) dump_row(cfg, -1, 0, v, site[t] >= 0);
+          if (DUMP && active && t == 0) dump_row(cfg, -1, 0, v, site[t] >= 0);
         }
       }
       fence_proxy_async();
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32, 1) tc_forward_kernel(TcA
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
           }
           store_row(d.x1, pos[t], v);
-          if (a.dump && active && t == 0) dump_row(cfg, b, 0, v, site[t] >= 0);
+          if (DUMP && active && t == 0) dump_row(cfg, b, 0, v, site[t] >= 0);
           tmem_ld32(tm_pipe + lane_sel + (uint32_t)(t * 128) + 32, v);
           if (site[t] >= 0) {
 #pragma unroll
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32, 1) tc_forward_kernel(TcA
 #pragma unroll
               for (int i = 0; i < 32; ++i) r[i] = fmaxf(r[i] + v[i], 0.f);
               store_row(d.out_r, pos[t], r);
-              if (a.dump && active && t == 0) dump_row(cfg, b, 2, r, true);
+              if (DUMP && active && t == 0) dump_row(cfg, b, 2, r, true);
             }
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -328,11 +329,11 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32, 1) tc_forward_kernel(TcA
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
             if (d.out_r >= 0) {
               store_row(d.out_r, pos[t], v);
-              if (a.dump && active && t == 0) dump_row(cfg, b, 2, v, false);
+              if (DUMP && active && t == 0) dump_row(cfg, b, 2, v, false);
             }
           }
           store_row(d.out_a, pos[t], v);
-          if (a.dump && active && t == 0) dump_row(cfg, b, 1, v, site[t] >= 0);
+          if (DUMP && active && t == 0) dump_row(cfg, b, 1, v, site[t] >= 0);
         }
         fence_proxy_async();
         tc_fence_before();
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32, 1) tc_forward_kernel(TcA
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
           }
           store_row(d.c, pos[t], v);
-          if (a.dump && active && t == 0) dump_row(cfg, b, 3, v, site[t] >= 0);
+          if (DUMP && active && t == 0) dump_row(cfg, b, 3, v, site[t] >= 0);
         }
         fence_proxy_async();
         tc_fence_before();
@@ -396,7 +397,7 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32, 1) tc_forward_kernel(TcA
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
           }
           store_row(d.out_h, pos[t], v);
-          if (a.dump && active && t == 0) dump_row(cfg, b, 4, v, site[t] >= 0);
+          if (DUMP && active && t == 0) dump_row(cfg, b, 4, v, site[t] >= 0);
         }
         fence_proxy_async();
         tc_fence_before();
@@ -421,7 +422,7 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32, 1) tc_forward_kernel(TcA
             tmem_ld16(tm_pipe + lane_sel + (uint32_t)(t * 128) + 0, v);
             if (site[t] >= 0) {
               const float re0 = v[0] + hb[0], re1 = v[1] + hb[1], im0 = v[2] + hb[2], im1 = v[3] + hb[3];
-              if (a.dump && active && t == 0)
+              if (DUMP && active && t == 0)
                 *reinterpret_cast<float4*>(a.dump_logits + ((size_t)cfg * 128 + ltid) * 4) = make_float4(re0, re1, im0, im1);
               const float x = 2.f * re0, y = 2.f * re1;
               const float m = fmaxf(x, y);
@@ -605,8 +606,13 @@ int tc_forward_launch(fk_net* net, const int8_t* sigma, int64_t n, float* log_ps
   FK_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long groups = (n + g.np - 1) / g.np;
   const unsigned grid = (unsigned)std::min<long long>(groups, sms);
-  FK_CHECK_CUDA(cudaFuncSetAttribute(tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-  tc_forward_kernel<<<grid, 128 * g.np + 32, g.smem_bytes, s>>>(a);
+  if (dump) {
+    FK_CHECK_CUDA(cudaFuncSetAttribute(tc_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    tc_forward_kernel<true><<<grid, 128 * g.np + 32, g.smem_bytes, s>>>(a);
+  } else {
+    FK_CHECK_CUDA(cudaFuncSetAttribute(tc_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    tc_forward_kernel<false><<<grid, 128 * g.np + 32, g.smem_bytes, s>>>(a);
+  }
   FK_CHECK_LAUNCH();
   return 0;
 }
