@@ -63,12 +63,12 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
   uint8_t* xc = ltile + TS_NLOAD * TS_TILE;               // x1, then the concat tensor (in place)
   uint8_t* hring = xc + TS_TILE;                          // 3 tiles: horizontal-stack tile of the current site per block parity
   uint8_t* tail = hring + 3 * TS_TILE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);     // wfull[0..1], tfull[2], mma[3]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);     // wfull[0..1], tfull (x/a tiles)[2], mma[3], cfull (c / vertical tiles)[4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 64);
 
-  const uint32_t wfull0 = smem_u32(&bars[0]), tfull = smem_u32(&bars[2]), mbar = smem_u32(&bars[3]);
+  const uint32_t wfull0 = smem_u32(&bars[0]), tfull = smem_u32(&bars[2]), mbar = smem_u32(&bars[3]), cfull = smem_u32(&bars[4]);
   if (tid == 32) {
-    mbar_init(wfull0, 1); mbar_init(wfull0 + 8, 1); mbar_init(tfull, 1); mbar_init(mbar, 1);
+    mbar_init(wfull0, 1); mbar_init(wfull0 + 8, 1); mbar_init(tfull, 1); mbar_init(mbar, 1); mbar_init(cfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
   const uint32_t ltile16 = smem_u32(ltile) >> 4, xc16 = smem_u32(xc) >> 4, hring16 = smem_u32(hring) >> 4;
   constexpr uint32_t TILE16 = TS_TILE / 16, KSTEP16 = 256;
 
-  uint32_t mma_phase = 0, tile_phase = 0;
+  uint32_t mma_phase = 0, tile_phase = 0, c_phase = 0;
   long long step = 0;   // weight-ring step
 
   // ---- helpers ---------------------------------------------------------------------------------------------------
@@ -130,8 +130,12 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
     mma_phase ^= 1;
     tc_fence_after();
   };
-  auto end_phase = [&]() {   // epilogue writes (shared: generic -> async proxy; global: later bulk loads) are ordered
-    asm volatile("fence.proxy.async;" ::: "memory");
+  // Epilogue writes to shared memory feed the next MMA (generic -> async proxy): fenced every phase.  Writes to the
+  // global caches are only read back by cp.async.bulk one site later (horizontal stack) or one block later (vertical
+  // stack), so the much more expensive global proxy fence is issued once per site / once per vertical block.
+  auto end_phase = [&](bool global_fence = false) {
+    fence_proxy_async();
+    if (global_fence) asm volatile("fence.proxy.async.global;" ::: "memory");
     tc_fence_before();
     __syncthreads();
   };
@@ -156,58 +160,72 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
   if (tid == 0) { load_weights(0, image_of(0)); }
 
   // ================================================================================================================
+  // Loaded-tile slots of a horizontal step: 0..2 = 1x3 taps of the horizontal stack, 3 = relu(v')(i-1, j),
+  // 4..11 = the eight concat-tensor taps that come from the cache (the ninth is produced by the step itself).
+  // The x/a tiles of step k+1 are prefetched while step k runs its 3x3 conv; the concat tiles of step k are
+  // requested at the start of the step and only awaited before the 3x3 conv.
+  auto x_valid = [&](int b, int j, int t) -> bool {            // tap t of the 1x3 conv of block b at column j
+    const bool last = (b == nb - 1);
+    const int jc = last ? j - 1 : j;
+    return jc >= 0 && (jc - 2 + t) >= 0;
+  };
+  auto issue_xa = [&](int i, int j, int b) -> int {            // thread 0 only; returns the number of tiles requested
+    const bool last = (b == nb - 1);
+    const int jc = last ? j - 1 : j;
+    int n = 0;
+    for (int t = 0; t < 2; ++t) n += x_valid(b, j, t) ? 1 : 0;  // tap 2 (column jc) always comes from the h ring
+    if (i > 0) ++n;
+    if (n == 0) return 0;
+    mbar_expect_tx(tfull, (uint32_t)n * TS_TILE);
+    for (int t = 0; t < 2; ++t)
+      if (x_valid(b, j, t))
+        bulk_g2s(smem_u32(ltile + (size_t)t * TS_TILE), cache + (size_t)ts_hin(W, b, jc - 2 + t) * TS_TILE, TS_TILE, tfull);
+    if (i > 0) bulk_g2s(smem_u32(ltile + (size_t)3 * TS_TILE), cache + (size_t)ts_a(W, b, j) * TS_TILE, TS_TILE, tfull);
+    return n;
+  };
+  auto count_xa = [&](int i, int j, int b) -> int {
+    int n = 0;
+    for (int t = 0; t < 2; ++t) n += x_valid(b, j, t) ? 1 : 0;
+    return n + (i > 0 ? 1 : 0);
+  };
+
   for (int i = 0; i < H; ++i) {
+    bool xa_prefetched = false;
     for (int j = 0; j < W; ++j) {
       for (int kb = 0; kb < nb; ++kb, ++step) {
         const int b = kb == 0 ? nb - 1 : kb - 1;     // last block first (it produces sigma(i,j)), then blocks 0..nb-2
         const bool last = (b == nb - 1);
         const int jc = last ? j - 1 : j;             // RightShift: the last block evaluates its 1x3 conv one column to the left
         const uint32_t wsel = (uint32_t)(step & 1);
-        // ---- issue this step's cache-tile loads and prefetch the next weight image
-        int x_slot[3], a_slot = -1, c_slot[9];
-        {
-          int n = 0;
-          for (int t = 0; t < 3; ++t) {
-            const int col = jc - 2 + t;
-            x_slot[t] = -1;
-            if (col < 0 || jc < 0) continue;
-            if (!last && t == 2) { x_slot[t] = 100; continue; }   // the (i,j) tile is in the h ring
-            x_slot[t] = n++;
+        // ---- request this step's concat tiles, (first step of a row: also its x/a tiles), prefetch the next weight image
+        int nc = 0;
+        int c_slot[9];
+        for (int di = 0; di < 3; ++di)
+          for (int dj = 0; dj < 3; ++dj) {
+            const int row = i - 2 + di, col = j - 2 + dj;
+            c_slot[di * 3 + dj] = -1;
+            if (row < 0 || col < 0) continue;
+            if (di == 2 && dj == 2) { c_slot[8] = 100; continue; }   // produced by this step (xc tile)
+            c_slot[di * 3 + dj] = 4 + di * 3 + dj;
+            ++nc;
           }
-          if (i > 0) a_slot = n++;
-          for (int di = 0; di < 3; ++di)
-            for (int dj = 0; dj < 3; ++dj) {
-              const int row = i - 2 + di, col = j - 2 + dj;
-              c_slot[di * 3 + dj] = -1;
-              if (row < 0 || col < 0) continue;
-              if (di == 2 && dj == 2) { c_slot[8] = 100; continue; }   // produced by this step (xc tile)
-              c_slot[di * 3 + dj] = n++;
-            }
-          if (tid == 0) {
-            if (n > 0) {
-              mbar_expect_tx(tfull, (uint32_t)n * TS_TILE);
-              for (int t = 0; t < 3; ++t)
-                if (x_slot[t] >= 0 && x_slot[t] < 100)
-                  bulk_g2s(smem_u32(ltile + (size_t)x_slot[t] * TS_TILE), cache + (size_t)ts_hin(W, b, jc - 2 + t) * TS_TILE, TS_TILE, tfull);
-              if (a_slot >= 0)
-                bulk_g2s(smem_u32(ltile + (size_t)a_slot * TS_TILE), cache + (size_t)ts_a(W, b, j) * TS_TILE, TS_TILE, tfull);
-              for (int di = 0; di < 3; ++di)
-                for (int dj = 0; dj < 3; ++dj) {
-                  const int sl = c_slot[di * 3 + dj];
-                  if (sl >= 0 && sl < 100)
-                    bulk_g2s(smem_u32(ltile + (size_t)sl * TS_TILE),
-                             cache + (size_t)ts_c(W, b, (i - 2 + di) % 3, j - 2 + dj) * TS_TILE, TS_TILE, tfull);
-                }
-            }
-            if (step + 1 < total_steps) load_weights(step + 1, image_of(step + 1));
+        const int nxa = count_xa(i, j, b);
+        if (tid == 0) {
+          if (!xa_prefetched) issue_xa(i, j, b);
+          if (nc > 0) {
+            mbar_expect_tx(cfull, (uint32_t)nc * TS_TILE);
+            for (int t = 0; t < 8; ++t)
+              if (c_slot[t] >= 0)
+                bulk_g2s(smem_u32(ltile + (size_t)c_slot[t] * TS_TILE),
+                         cache + (size_t)ts_c(W, b, (i - 2 + t / 3) % 3, j - 2 + t % 3) * TS_TILE, TS_TILE, cfull);
           }
-          mbar_wait(wfull0 + 8 * wsel, (uint32_t)((step >> 1) & 1));
-          if (n > 0) { mbar_wait(tfull, tile_phase); tile_phase ^= 1; }
+          if (step + 1 < total_steps) load_weights(step + 1, image_of(step + 1));
         }
+        mbar_wait(wfull0 + 8 * wsel, (uint32_t)((step >> 1) & 1));
+        if (nxa > 0) { mbar_wait(tfull, tile_phase); tile_phase ^= 1; }
         const uint8_t* wimg = wbuf + (size_t)wsel * IMG_BYTES;
         const uint32_t wimg16 = smem_u32(wimg) >> 4;
         const float* bias = reinterpret_cast<const float*>(wimg + IMG_BIAS);
-        uint8_t* h_in = hring + (size_t)(b % 3) * TS_TILE;
         uint8_t* h_out = hring + (size_t)((b + 1) % 3) * TS_TILE;
         const uint8_t* h_res = hring + (size_t)((b + 2) % 3) * TS_TILE;   // (b-1) mod 3: the pair input at this site
         const bool res2 = (b >= 2 && (b % 2) == 0 && !last);
@@ -218,8 +236,9 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
           tc_fence_after();
           uint32_t acc = 0;
           for (int t = 0; t < 3; ++t) {
-            if (x_slot[t] < 0) continue;
-            const uint32_t tile16 = x_slot[t] == 100 ? hring16 + (uint32_t)(b % 3) * TILE16 : ltile16 + (uint32_t)x_slot[t] * TILE16;
+            if (t < 2 && !x_valid(b, j, t)) continue;
+            // tap 2 = column jc: the tile this CTA produced last (block b-1 at this site, or block nb-2 at the previous site)
+            const uint32_t tile16 = t == 2 ? hring16 + (uint32_t)(b % 3) * TILE16 : ltile16 + (uint32_t)t * TILE16;
             mma_tap(0, tile16, bdesc32 + wimg16 + IMG_X / 16 + (uint64_t)(t * 2) * 64, 64, idesc32, acc);
           }
         }
@@ -243,24 +262,32 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
           tc_fence_after();
           uint32_t acc = 0;
           mma_tap(32, xc16, bdesc16 + wimg16 + IMG_XX / 16, 32, idesc16, acc);
-          if (a_slot >= 0) {
+          if (i > 0) {
             acc = 0;
-            mma_tap(48, ltile16 + (uint32_t)a_slot * TILE16, bdesc16 + wimg16 + IMG_Y / 16, 32, idesc16, acc);
+            mma_tap(48, ltile16 + 3u * TILE16, bdesc16 + wimg16 + IMG_Y / 16, 32, idesc16, acc);
           }
         }
         commit_and_wait();
+        // the x/a slots are free now: prefetch the next step's x/a tiles (same row only; the vertical pass reuses the slots)
+        {
+          int ni = i, nj = j, nkb = kb + 1;
+          if (nkb == nb) { nkb = 0; ++nj; }
+          xa_prefetched = nj < W;
+          if (xa_prefetched && tid == 0) issue_xa(ni, nj, nkb == 0 ? nb - 1 : nkb - 1);
+        }
         {
           float v[32];
           tmem_ld32(tmem + lane_sel + 32, v);
 #pragma unroll
           for (int q = 0; q < 16; ++q) v[q] = fmaxf(v[q] + bias[64 + q], 0.f);
 #pragma unroll
-          for (int q = 16; q < 32; ++q) v[q] = fmaxf((a_slot >= 0 ? v[q] : 0.f) + bias[64 + q], 0.f);
+          for (int q = 16; q < 32; ++q) v[q] = fmaxf((i > 0 ? v[q] : 0.f) + bias[64 + q], 0.f);
           store_tile_row(xc, cache + (size_t)ts_c(W, b, i % 3, j) * TS_TILE, v);
         }
         end_phase();
 
         // ================= phase 3: 3x3 conv on the concat tensor -> h'
+        if (nc > 0) { mbar_wait(cfull, c_phase); c_phase ^= 1; }
         if (tid == 0) {
           tc_fence_after();
           uint32_t acc = 0;
@@ -284,7 +311,7 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
           for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q] + bias[96 + q], 0.f);
           store_tile_row(h_out, last ? nullptr : cache + (size_t)ts_hin(W, b + 1, j) * TS_TILE, v);
         }
-        end_phase();
+        end_phase(kb == nb - 1);   // end of the site: publish this site's cache tiles to the async proxy
 
         // ================= phase 4 (last block): head + normalisation + draw sigma(i,j)
         if (last) {
@@ -321,43 +348,51 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
         }
       }
     }
-    // ================= vertical stack of row i: all blocks, all columns
+    // ================= vertical stack of row i: all blocks, all columns.  Rolling window: slot = 4*row_tap + (column & 3);
+    // column j needs columns j-1..j+1, column j+2 and the residual tile of column j+1 are prefetched meanwhile.
     for (int b = 0; b < nb; ++b, ++step) {
       const uint32_t wsel = (uint32_t)(step & 1);
-      if (tid == 0 && step + 1 < total_steps) load_weights(step + 1, image_of(step + 1));
+      const bool res2 = (b >= 2 && (b % 2) == 0 && b != nb - 1);
+      auto issue_col = [&](int col, int res_col) {   // thread 0: the three row taps of `col` (+ residual tile of res_col)
+        int n = 0;
+        for (int di = 0; di < 3; ++di) n += (i - 2 + di >= 0 && col >= 0 && col < W) ? 1 : 0;
+        if (res2 && res_col >= 0 && res_col < W) ++n;
+        if (n == 0) return;
+        mbar_expect_tx(cfull, (uint32_t)n * TS_TILE);
+        if (col >= 0 && col < W)
+          for (int di = 0; di < 3; ++di)
+            if (i - 2 + di >= 0)
+              bulk_g2s(smem_u32(ltile + (size_t)(di * 4 + (col & 3)) * TS_TILE),
+                       cache + (size_t)ts_vin(W, b, (i - 2 + di) % 3, col) * TS_TILE, TS_TILE, cfull);
+        if (res2 && res_col >= 0 && res_col < W)
+          bulk_g2s(smem_u32(hring + (size_t)(1 + (res_col & 1)) * TS_TILE), cache + (size_t)ts_vin(W, b - 1, i % 3, res_col) * TS_TILE,
+                   TS_TILE, cfull);
+      };
+      if (tid == 0) {
+        if (step + 1 < total_steps) load_weights(step + 1, image_of(step + 1));
+        issue_col(0, 0);        // group "column 0": column 0 tiles + residual of column 0
+      }
       mbar_wait(wfull0 + 8 * wsel, (uint32_t)((step >> 1) & 1));
+      mbar_wait(cfull, c_phase); c_phase ^= 1;
+      if (tid == 0 && W > 1) issue_col(1, -1);   // column 1 is needed by column 0's right tap
+      if (W > 1) { mbar_wait(cfull, c_phase); c_phase ^= 1; }
       const uint8_t* wimg = wbuf + (size_t)wsel * IMG_BYTES;
       const uint32_t wimg16 = smem_u32(wimg) >> 4;
       const float* bias = reinterpret_cast<const float*>(wimg + IMG_BIAS);
-      const bool res2 = (b >= 2 && (b % 2) == 0 && b != nb - 1);
       for (int j = 0; j < W; ++j) {
-        int v_slot[9];
-        int n = 0;
-        for (int di = 0; di < 3; ++di)
-          for (int dj = 0; dj < 3; ++dj) {
-            const int row = i - 2 + di, col = j - 1 + dj;
-            v_slot[di * 3 + dj] = (row < 0 || col < 0 || col >= W) ? -1 : n++;
-          }
-        const int res_slot = res2 ? n++ : -1;
-        if (tid == 0) {
-          mbar_expect_tx(tfull, (uint32_t)n * TS_TILE);
-          for (int di = 0; di < 3; ++di)
-            for (int dj = 0; dj < 3; ++dj)
-              if (v_slot[di * 3 + dj] >= 0)
-                bulk_g2s(smem_u32(ltile + (size_t)v_slot[di * 3 + dj] * TS_TILE),
-                         cache + (size_t)ts_vin(W, b, (i - 2 + di) % 3, j - 1 + dj) * TS_TILE, TS_TILE, tfull);
-          if (res_slot >= 0)
-            bulk_g2s(smem_u32(ltile + (size_t)res_slot * TS_TILE), cache + (size_t)ts_vin(W, b - 1, i % 3, j) * TS_TILE, TS_TILE, tfull);
-        }
-        mbar_wait(tfull, tile_phase);
-        tile_phase ^= 1;
+        // prefetch: column j+2 (right tap of column j+1) and the residual tile of column j+1
+        const bool pre = (j + 2 < W) || (res2 && j + 1 < W);
+        if (tid == 0 && pre) issue_col(j + 2 < W ? j + 2 : -1, j + 1);
         if (tid == 0) {
           tc_fence_after();
           uint32_t acc = 0;
-          for (int t = 0; t < 9; ++t) {
-            if (v_slot[t] < 0) continue;
-            mma_tap(0, ltile16 + (uint32_t)v_slot[t] * TILE16, bdesc32 + wimg16 + IMG_V / 16 + (uint64_t)(t * 2) * 64, 64, idesc32, acc);
-          }
+          for (int di = 0; di < 3; ++di)
+            for (int dj = 0; dj < 3; ++dj) {
+              const int row = i - 2 + di, col = j - 1 + dj;
+              if (row < 0 || col < 0 || col >= W) continue;
+              mma_tap(0, ltile16 + (uint32_t)(di * 4 + (col & 3)) * TILE16,
+                      bdesc32 + wimg16 + IMG_V / 16 + (uint64_t)((di * 3 + dj) * 2) * 64, 64, idesc32, acc);
+            }
         }
         commit_and_wait();
         {
@@ -368,7 +403,7 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
           if (b + 1 < nb) {
             float r[32];
             if (res2) {
-              load_tile_row(ltile + (size_t)res_slot * TS_TILE, r);
+              load_tile_row(hring + (size_t)(1 + (j & 1)) * TS_TILE, r);
 #pragma unroll
               for (int q = 0; q < 32; ++q) r[q] = fmaxf(r[q] + v[q], 0.f);
             } else {
@@ -381,7 +416,8 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
           for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], 0.f);
           store_tile_row(nullptr, cache + (size_t)ts_a(W, b, j) * TS_TILE, v);
         }
-        end_phase();
+        end_phase(j == W - 1);     // the next block reads this block's output tiles
+        if (pre) { mbar_wait(cfull, c_phase); c_phase ^= 1; }
       }
     }
   }
