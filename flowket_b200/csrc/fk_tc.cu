@@ -93,35 +93,58 @@ constexpr int TC_DUMP_TENSORS = 5;
 constexpr int TC_MAX_T = 3;
 constexpr int TC_MAX_NP = 3;
 
-// Thread layout: np pipelines x 128 threads (one configuration each) + 1 producer warp (weight images).
-// Barriers: full[2] (weights landed, tx-count), empty[2] (np arrivals: every pipeline is done with the image),
-//           mma[np] (tcgen05.commit of the pipeline's current phase).
+#ifdef FK_TC_TRACE
+__device__ long long fk_tc_trace_buf[3 * 40 * 16];
+#define TRACE(slot) do { if (!DUMP && ltid == 0 && blockIdx.x == 0 && it == 3) fk_tc_trace_buf[(pipe * 40 + b) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define TRACE(slot) do {} while (0)
+#endif
+
+// Thread layout: np pipelines x 128 epilogue threads (one configuration each) + 1 producer warp (weight images)
+//                + TC_ISSUERS issuer warps (tcgen05.mma).
+// Why issuer warps (measured: tools/umma_bench*.cu and the clock64 trace of this kernel, tests/tools_tc_trace.py):
+// tcgen05.mma takes its descriptors from uniform registers.  Issued under `if (thread == 0)` inside an epilogue warp
+// the compiler wraps every MMA in a per-thread R2UR loop (>100 cycles per MMA, and the pipelines fall into lockstep:
+// all epilogues run together while the tensor pipe idles); a converged warp with one elected lane issues back-to-back,
+// and with two or more issuers in flight the pipe retires an N=32 MMA every 40 cycles -- the shared-memory operand
+// bandwidth (128 B/cycle).  The (block, phase, pipeline) turns are dealt round-robin to the issuers.
+// Barriers: full[2] (weights landed, tx-count), empty[2] (np*128 arrivals: every epilogue thread is done with the
+//           image), mma[np] (tcgen05.commit of the pipeline's current phase), ready[np] (128 arrivals: the operand
+//           tiles of the pipeline's next phase are written and fenced).
+constexpr int TC_ISSUERS = 3;   // measured on the 10x10 lattice: 2 -> 2.47, 3 -> 2.59, 4 -> 2.38 M configurations/s
 template <bool DUMP>
-__global__ void __launch_bounds__(TC_MAX_NP * 128 + 32, 1) tc_forward_kernel(TcArgs a) {
+__global__ void __launch_bounds__(TC_MAX_NP * 128 + 32 + TC_ISSUERS * 32, 1) tc_forward_kernel(TcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int pipe = tid >> 7, ltid = tid & 127;
   const bool is_producer = warp == a.np * 4;
+  const bool is_issuer = warp > a.np * 4;
   const int buf_bytes = 64 * a.npos;  // 4 channel groups x npos x 16 B
   uint8_t* wbuf = smem;
   uint8_t* act0 = smem + 2 * IMG_BYTES;
   uint8_t* tail = act0 + (size_t)a.np * TC_SLOTS * buf_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);           // full[0..1], empty[2..3], mma[4..6]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 64);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);           // full[0..1], empty[2..3], mma[4..6], ready[7..9]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 96);
+  volatile uint32_t* issued = reinterpret_cast<volatile uint32_t*>(tail + 104);   // [np] phases issued per pipeline
   float* red = reinterpret_cast<float*>(tail + 128);             // [np][4 warps][2]
   int* taps = reinterpret_cast<int*>(tail + 256);                // tap offsets in positions: V[9] H[9] X[3]
   TcBlockDesc* sdesc = reinterpret_cast<TcBlockDesc*>(tail + 384);
 
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2]);
-  const uint32_t mbar = smem_u32(&bars[4 + (is_producer ? 0 : pipe)]);
+  const uint32_t mbar = smem_u32(&bars[4 + ((is_producer || is_issuer) ? 0 : pipe)]);
+  const uint32_t rbar = smem_u32(&bars[7 + ((is_producer || is_issuer) ? 0 : pipe)]);
 
   if (tid == 32) {  // (not warp 0: it must reach the .sync.aligned TMEM allocation converged)
+    issued[0] = issued[1] = issued[2] = 0u;
     mbar_init(full0, 1);
     mbar_init(full0 + 8, 1);
-    mbar_init(empty0, a.np);
-    mbar_init(empty0 + 8, a.np);
-    for (int p = 0; p < a.np; ++p) mbar_init(smem_u32(&bars[4 + p]), 1);
+    mbar_init(empty0, a.np * 128);
+    mbar_init(empty0 + 8, a.np * 128);
+    for (int p = 0; p < a.np; ++p) {
+      mbar_init(smem_u32(&bars[4 + p]), 1);
+      mbar_init(smem_u32(&bars[7 + p]), 128);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int i = 0; i < 3; ++i)
       for (int j = 0; j < 3; ++j) {
@@ -164,8 +187,98 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32, 1) tc_forward_kernel(TcA
       }
       __syncwarp();
     }
+  } else if (is_issuer) {
+    // =============================== MMA issuers (whole warp walks the loops, one elected lane issues) ==========
+    // The (block, phase, pipeline) turns are dealt round-robin to the issuers.  Issuers run unordered with respect to
+    // each other except per pipeline: phase k+1 of a pipeline is looked at only after its phase k has been issued
+    // (issued[p] counter) -- otherwise the parity test of the ready barrier could alias two phases.
+    // Everything that feeds a descriptor goes through __shfl_sync(.., 0) once per turn so that the compiler keeps
+    // the per-tap arithmetic in uniform registers.
+    const int role = __shfl_sync(0xffffffffu, warp - (a.np * 4 + 1), 0);
+    const uint32_t buf16 = 4u * (uint32_t)a.npos, kstep16 = 2u * (uint32_t)a.npos;   // 16-byte units
+    const uint32_t idesc32 = make_idesc(32), idesc16 = make_idesc(16);
+    const uint32_t hi = 8u | (1u << 14);                         // SBO = 8 (x16 B), descriptor version bit 46
+    const uint32_t a_lbo = (uint32_t)a.npos << 16;               // LBO of the activation tiles
+    const uint32_t act16 = smem_u32(act0) >> 4;
+    const int P = a.P;
+    // one (tap, both k-steps) pair: A = view of the tile shifted by `off` positions, B = weight tiles of the tap
+    auto tap_pair = [&](uint32_t d_tmem, uint32_t a16, int off, uint32_t w16, bool n32, uint32_t acc) {
+      const uint32_t alo = ((a16 + (uint32_t)off) & 0x3FFFu) | a_lbo;
+      const uint32_t blo = (w16 & 0x3FFFu) | ((n32 ? 32u : 16u) << 16);
+      umma_f16_lohi(d_tmem, alo, blo, hi, n32 ? idesc32 : idesc16, acc);
+      umma_f16_lohi(d_tmem, alo + kstep16, blo + (n32 ? 64u : 32u), hi, n32 ? idesc32 : idesc16, 1u);
+    };
+    long long step = 0;
+    uint32_t turn = 0, phase_count = 0;
+    for (long long it = 0; it < my_iters; ++it) {
+      for (int b = 0; b < a.nb; ++b, ++step) {
+        const TcBlockDesc d = sdesc[b];
+        const uint32_t wsel = (uint32_t)(step & 1);
+        bool have_w = false;
+        const uint32_t wimg16 = __shfl_sync(0xffffffffu, smem_u32(wbuf + (size_t)wsel * IMG_BYTES) >> 4, 0);
+        const int last = __shfl_sync(0xffffffffu, d.last, 0);
+        const int nph = last ? 4 : 3;
+        for (int ph = 1; ph <= nph; ++ph, ++phase_count) {
+          // operand tiles of this phase
+          const uint32_t s0 = __shfl_sync(0xffffffffu, (uint32_t)(ph == 1 ? d.in_h : ph == 2 ? d.x1 : ph == 3 ? d.c : d.out_h), 0);
+          const uint32_t s1 = __shfl_sync(0xffffffffu, (uint32_t)(ph == 1 ? d.in_v : d.out_a), 0);
+          for (int p = 0; p < a.np; ++p, ++turn) {
+            if ((int)(turn % TC_ISSUERS) != role) continue;
+            if (!have_w) {
+              mbar_wait(full0 + 8 * wsel, (uint32_t)((step >> 1) & 1));
+              have_w = true;
+            }
+            if (TC_ISSUERS > 1) {
+              uint32_t spins = 0;
+              while (issued[p] < phase_count) {
+                if (++spins > (1u << 26)) __trap();
+              }
+            }
+            mbar_wait(smem_u32(&bars[7 + p]), phase_count & 1u);
+            tc_fence_after();
+            const uint32_t row00 = act16 + (uint32_t)(p * TC_SLOTS) * buf16 + (uint32_t)a.p_first;
+            const bool leader = elect_one();
+            for (int t = 0; t < a.T; ++t) {
+              const uint32_t dt = tmem_base + (uint32_t)((p * a.T + t) * 128);
+              const uint32_t a0 = row00 + (uint32_t)(t * 128) + s0 * buf16, a1 = row00 + (uint32_t)(t * 128) + s1 * buf16;
+              if (leader) {
+                if (ph == 1) {
+#pragma unroll
+                  for (int j = 0; j < 3; ++j)      // 1x3 on the horizontal stack: pad left 2
+                    tap_pair(dt + 0, a0, j - 2, wimg16 + IMG_X / 16 + 128 * j, true, j != 0);
+#pragma unroll
+                  for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)    // 3x3 on the vertical stack: pad top 2, left 1, right 1
+                      tap_pair(dt + 32, a1, (i - 2) * P + (j - 1), wimg16 + IMG_V / 16 + 128 * (i * 3 + j), true, (i | j) != 0);
+                } else if (ph == 2) {
+                  tap_pair(dt + 64, a0, last ? -1 : 0, wimg16 + IMG_XX / 16, false, 0u);
+                  tap_pair(dt + 80, a1, -P, wimg16 + IMG_Y / 16, false, 0u);
+                } else if (ph == 3) {
+#pragma unroll
+                  for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)    // 3x3 on the concat tensor: pad top 2, left 2
+                      tap_pair(dt + 96, a0, (i - 2) * P + (j - 2), wimg16 + IMG_H / 16 + 128 * (i * 3 + j), true, (i | j) != 0);
+                } else {
+                  tap_pair(dt + 0, a0, 0, wimg16 + IMG_HEAD / 16, false, 0u);
+                }
+              }
+            }
+            if (leader) {
+              umma_commit(smem_u32(&bars[4 + p]));
+              if (TC_ISSUERS > 1) {
+                __threadfence_block();
+                issued[p] = phase_count + 1u;
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
   } else {
-    // =============================== compute pipelines ===============================
+    // =============================== epilogue pipelines ===============================
     const uint32_t tm_pipe = tmem_base + (uint32_t)(pipe * a.T * 128);
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
     uint8_t* act = act0 + (size_t)pipe * TC_SLOTS * buf_bytes;
@@ -231,26 +344,6 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32, 1) tc_forward_kernel(TcA
         a.dump_mask[(((size_t)cfg * a.nb + b) * TC_DUMP_TENSORS + tensor) * 128 + ltid] = mask;
       }
     };
-    // one conv = NTAPS shifted views of slot `src` x 2 k-steps, accumulated into TMEM columns col0..col0+N.
-    // Descriptors differ only in the 14-bit start-address field, so each MMA costs a couple of integer adds.
-    auto issue_conv = [&](int src, const int* tap_off, int ntaps, int shift, uint32_t w16, bool n32, uint32_t col0) {
-      const uint32_t idesc = n32 ? idesc32 : idesc16;
-      const uint64_t bd0 = (n32 ? bdesc32 : bdesc16) + w16;
-      const uint32_t wstep = n32 ? 64u : 32u;  // 16-byte units per (tap, k-step) weight tile
-      for (int t = 0; t < a.T; ++t) {
-        const uint32_t d_tmem = tm_pipe + (uint32_t)(t * 128) + col0;
-        const uint64_t ad0 = adesc0 + (uint64_t)(act16 + (uint32_t)src * buf16 + (uint32_t)(a.p_first + t * 128 + shift));
-        uint32_t acc = 0;
-        for (int tap = 0; tap < ntaps; ++tap) {
-          const uint64_t ad = ad0 + (uint64_t)(int64_t)(tap_off ? tap_off[tap] : 0);
-          const uint64_t bd = bd0 + (uint64_t)(tap * 2) * wstep;
-          umma_f16(d_tmem, ad, bd, idesc, acc);
-          umma_f16(d_tmem, ad + kstep16, bd + wstep, idesc, 1u);
-          acc = 1;
-        }
-      }
-    };
-
     uint32_t mma_phase = 0;
     long long step = 0;  // weight-pipeline step: block (step % nb) lives in buffer (step & 1)
 
@@ -276,7 +369,8 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32, 1) tc_forward_kernel(TcA
         }
       }
       fence_proxy_async();
-      named_sync(bar_id, 128);
+      tc_fence_before();
+      mbar_arrive(rbar);   // operand tile of block 0 is ready
 
       for (int b = 0; b < a.nb; ++b, ++step) {
         const TcBlockDesc d = sdesc[b];
@@ -287,15 +381,11 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32, 1) tc_forward_kernel(TcA
         const float* bias = reinterpret_cast<const float*>(wimg + IMG_BIAS);
 
         // ================= phase 1: 1x3 conv on h (cols 0..31) and 3x3 conv on v (cols 32..63)
-        if (ltid == 0) {
-          tc_fence_after();
-          issue_conv(d.in_h, taps + 18, 3, 0, wimg16 + IMG_X / 16, true, 0);
-          issue_conv(d.in_v, taps, 9, 0, wimg16 + IMG_V / 16, true, 32);
-          umma_commit(mbar);
-        }
+        TRACE(0);
         mbar_wait(mbar, mma_phase);
         mma_phase ^= 1;
         tc_fence_after();
+        TRACE(2);
 #pragma unroll
         for (int t = 0; t < TC_MAX_T; ++t) {
           if (t >= a.T) break;
@@ -337,19 +427,15 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32, 1) tc_forward_kernel(TcA
         }
         fence_proxy_async();
         tc_fence_before();
-        named_sync(bar_id, 128);
+        mbar_arrive(rbar);
 
         // ================= phase 2: the two 1x1 convs (C -> C/2): x1 (RightShift in the last block) and
         //                   DownShift(relu(v')) -> concat tensor (cols 64..95)
-        if (ltid == 0) {
-          tc_fence_after();
-          issue_conv(d.x1, nullptr, 1, d.last ? -1 : 0, wimg16 + IMG_XX / 16, false, 64);
-          issue_conv(d.out_a, nullptr, 1, -a.P, wimg16 + IMG_Y / 16, false, 80);
-          umma_commit(mbar);
-        }
+        TRACE(3);
         mbar_wait(mbar, mma_phase);
         mma_phase ^= 1;
         tc_fence_after();
+        TRACE(5);
 #pragma unroll
         for (int t = 0; t < TC_MAX_T; ++t) {
           if (t >= a.T) break;
@@ -367,17 +453,14 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32, 1) tc_forward_kernel(TcA
         }
         fence_proxy_async();
         tc_fence_before();
-        named_sync(bar_id, 128);
+        mbar_arrive(rbar);
 
         // ================= phase 3: 3x3 conv on the concat tensor (cols 96..127), residual, relu
-        if (ltid == 0) {
-          tc_fence_after();
-          issue_conv(d.c, taps + 9, 9, 0, wimg16 + IMG_H / 16, true, 96);
-          umma_commit(mbar);
-        }
+        TRACE(6);
         mbar_wait(mbar, mma_phase);
         mma_phase ^= 1;
         tc_fence_after();
+        TRACE(8);
 #pragma unroll
         for (int t = 0; t < TC_MAX_T; ++t) {
           if (t >= a.T) break;
@@ -401,16 +484,12 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32, 1) tc_forward_kernel(TcA
         }
         fence_proxy_async();
         tc_fence_before();
-        named_sync(bar_id, 128);
+        mbar_arrive(rbar);
 
+        TRACE(9);
         // ================= phase 4 (last block): head 1x1 conv (C -> 4) + normalisation + combine
         if (d.last) {
           const float* hb = reinterpret_cast<const float*>(wimg + IMG_HEAD_BIAS);
-          if (ltid == 0) {
-            tc_fence_after();
-            issue_conv(d.out_h, nullptr, 1, 0, wimg16 + IMG_HEAD / 16, false, 0);
-            umma_commit(mbar);
-          }
           mbar_wait(mbar, mma_phase);
           mma_phase ^= 1;
           tc_fence_after();
@@ -453,8 +532,8 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32, 1) tc_forward_kernel(TcA
             a.out[2 * cfg + 1] = r1;
           }
         }
-        // this pipeline is done with the weight image (all MMAs retired, all bias reads behind the barrier)
-        if (ltid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8 * wsel) : "memory");
+        // this thread is done with the weight image (the block's MMAs have retired, its bias reads are behind it)
+        mbar_arrive(empty0 + 8 * wsel);
       }
     }
   }
@@ -608,13 +687,19 @@ int tc_forward_launch(fk_net* net, const int8_t* sigma, int64_t n, float* log_ps
   const unsigned grid = (unsigned)std::min<long long>(groups, sms);
   if (dump) {
     FK_CHECK_CUDA(cudaFuncSetAttribute(tc_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-    tc_forward_kernel<true><<<grid, 128 * g.np + 32, g.smem_bytes, s>>>(a);
+    tc_forward_kernel<true><<<grid, 128 * g.np + 32 + 32 * TC_ISSUERS, g.smem_bytes, s>>>(a);
   } else {
     FK_CHECK_CUDA(cudaFuncSetAttribute(tc_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-    tc_forward_kernel<false><<<grid, 128 * g.np + 32, g.smem_bytes, s>>>(a);
+    tc_forward_kernel<false><<<grid, 128 * g.np + 32 + 32 * TC_ISSUERS, g.smem_bytes, s>>>(a);
   }
   FK_CHECK_LAUNCH();
   return 0;
 }
 
 }  // namespace fk
+
+#ifdef FK_TC_TRACE
+extern "C" int fk_tc_trace_read(long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, fk::fk_tc_trace_buf, sizeof(long long) * 3 * 40 * 16);
+}
+#endif
