@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(BWD_NP * 128 + 32, 1) tc_backward_kernel(BwdAr
         tc_fence_before();
         named_sync(bar_id, 128);
         // ---- phase 1: G_c = conv^T_H(dz_H)
-        if (ltid == 0) {
+        if (ltid < 32 && elect_one()) {   // (elected lane of a converged warp: descriptors stay in uniform registers)
           tc_fence_after();
           int sh[9];
           for (int i = 0; i < 3; ++i)
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(BWD_NP * 128 + 32, 1) tc_backward_kernel(BwdAr
         tc_fence_before();
         named_sync(bar_id, 128);
         // ---- phase 2: G_x1 = dz_c[:, :16] W_XX^T (RightShift^T in the last block), G_a += shift(dz_c[:, 16:] W_Y^T)
-        if (ltid == 0) {
+        if (ltid < 32 && elect_one()) {   // (elected lane of a converged warp: descriptors stay in uniform registers)
           tc_fence_after();
           int s1[1] = {last ? 1 : 0};
           issue(1, 0, s1, 1, 1, wimg16 + IMGB_XXT / 16, 0);
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(BWD_NP * 128 + 32, 1) tc_backward_kernel(BwdAr
         named_sync(bar_id, 128);
         // ---- phase 3: G_hin = conv^T_X(dz_X), G_vin = conv^T_V(dz_V)   (not needed below the first block)
         if (b > 0) {
-          if (ltid == 0) {
+          if (ltid < 32 && elect_one()) {   // (elected lane of a converged warp: descriptors stay in uniform registers)
             tc_fence_after();
             int sx[3] = {2, 1, 0};
             issue(2, 0, sx, 3, 2, wimg16 + IMGB_XT / 16, 0);
@@ -428,9 +428,9 @@ __global__ void __launch_bounds__(128, 1) tc_dw_kernel(DwArgs2 a) {
       prod_count = __shfl_sync(0xffffffffu, prod_count, 0);
       empty_phase = __shfl_sync(0xffffffffu, empty_phase, 0);
     } else if (warp == 1) {
-      // ---- MMA issuer
+      // ---- MMA issuer (elected lane of the converged warp: the descriptors stay in uniform registers)
       for (long long cfg = c_beg; cfg < c_end; ++cfg) {
-        if (lane == 0) {
+        if (elect_one()) {
           const int st = (int)(cons_count % DW_STAGES);
           mbar_wait(full0 + 8 * st, (full_phase >> st) & 1u); full_phase ^= 1u << st;
           tc_fence_after();
@@ -456,8 +456,11 @@ __global__ void __launch_bounds__(128, 1) tc_dw_kernel(DwArgs2 a) {
         }
         __syncwarp();
       }
-      cons_count = __shfl_sync(0xffffffffu, cons_count, 0);
-      full_phase = __shfl_sync(0xffffffffu, full_phase, 0);
+      {
+        const int leader = __ffs(__ballot_sync(0xffffffffu, elect_one())) - 1;
+        cons_count = __shfl_sync(0xffffffffu, cons_count, leader);
+        full_phase = __shfl_sync(0xffffffffu, full_phase, leader);
+      }
     }
     // ---- flush: warp 0 owns TMEM lanes 0..31 = input channels
     if (warp == 0) {

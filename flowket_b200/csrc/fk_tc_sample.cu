@@ -58,6 +58,9 @@ __device__ __forceinline__ long long ts_c(int W, int b, int slot, int col) { ret
 __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
+  // MMA issue: whole warp 0 walks the (CTA-uniform) control flow and one elected lane issues -- under `if (tid == 0)`
+  // the compiler moves every descriptor through a per-thread R2UR loop (~100 cycles per tcgen05.mma)
+  const bool mma_warp = __shfl_sync(0xffffffffu, warp, 0) == 0;
   uint8_t* wbuf = smem;                                   // 2 weight images
   uint8_t* ltile = smem + 2 * IMG_BYTES;                  // TS_NLOAD loaded tiles
   uint8_t* xc = ltile + TS_NLOAD * TS_TILE;               // x1, then the concat tensor (in place)
@@ -120,12 +123,14 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
   // 2 k-steps of one tap: A = tile (16-byte units), B = weight tile
   auto mma_tap = [&](uint32_t d_col, uint32_t tile16, uint64_t bd, uint32_t wstep, uint32_t idesc, uint32_t& acc) {
     const uint64_t ad = adesc0 + (uint64_t)tile16;
-    umma_f16(tmem + d_col, ad, bd, idesc, acc);
-    umma_f16(tmem + d_col, ad + KSTEP16, bd + wstep, idesc, 1u);
+    if (elect_one()) {   // (called by the whole MMA warp: the descriptors stay in uniform registers)
+      umma_f16(tmem + d_col, ad, bd, idesc, acc);
+      umma_f16(tmem + d_col, ad + KSTEP16, bd + wstep, idesc, 1u);
+    }
     acc = 1;
   };
   auto commit_and_wait = [&]() {
-    if (tid == 0) umma_commit(mbar);
+    if (mma_warp && elect_one()) umma_commit(mbar);   // same elected lane as the MMAs
     mbar_wait(mbar, mma_phase);
     mma_phase ^= 1;
     tc_fence_after();
@@ -232,7 +237,7 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
 
         // ================= phase 1: 1x3 conv on the horizontal stack -> x1
         const bool have_x = jc >= 0;
-        if (tid == 0 && have_x) {
+        if (mma_warp && have_x) {
           tc_fence_after();
           uint32_t acc = 0;
           for (int t = 0; t < 3; ++t) {
@@ -258,7 +263,7 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
         end_phase();
 
         // ================= phase 2: 1x1 convs: x1 -> concat[0:16], DownShift(relu(v')) = a(i-1, j) -> concat[16:32]
-        if (tid == 0) {
+        if (mma_warp) {
           tc_fence_after();
           uint32_t acc = 0;
           mma_tap(32, xc16, bdesc16 + wimg16 + IMG_XX / 16, 32, idesc16, acc);
@@ -288,7 +293,7 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
 
         // ================= phase 3: 3x3 conv on the concat tensor -> h'
         if (nc > 0) { mbar_wait(cfull, c_phase); c_phase ^= 1; }
-        if (tid == 0) {
+        if (mma_warp) {
           tc_fence_after();
           uint32_t acc = 0;
           for (int t = 0; t < 9; ++t) {
@@ -316,7 +321,7 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
         // ================= phase 4 (last block): head + normalisation + draw sigma(i,j)
         if (last) {
           const float* hb = reinterpret_cast<const float*>(wimg + IMG_HEAD_BIAS);
-          if (tid == 0) {
+          if (mma_warp) {
             tc_fence_after();
             uint32_t acc = 0;
             mma_tap(96, hring16 + (uint32_t)((b + 1) % 3) * TILE16, bdesc16 + wimg16 + IMG_HEAD / 16, 32, idesc16, acc);
@@ -383,7 +388,7 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
         // prefetch: column j+2 (right tap of column j+1) and the residual tile of column j+1
         const bool pre = (j + 2 < W) || (res2 && j + 1 < W);
         if (tid == 0 && pre) issue_col(j + 2 < W ? j + 2 : -1, j + 1);
-        if (tid == 0) {
+        if (mma_warp) {
           tc_fence_after();
           uint32_t acc = 0;
           for (int di = 0; di < 3; ++di)
