@@ -72,6 +72,22 @@ __global__ void tc_pack_kernel(const float* __restrict__ weff, const TcPackDesc*
     for (int i = threadIdx.x; i < bn[r]; i += blockDim.x) bias[boff[r] + i] = weff[d.b[r] + i];
   float* hb = reinterpret_cast<float*>(img + IMG_HEAD_BIAS);
   for (int i = threadIdx.x; i < 16; i += blockDim.x) hb[i] = i < 4 ? weff[d.b_head + i] : 0.f;
+  // bias tiles (B operands of the bias MMAs): per output channel [hi, lo, 0 x 6] with hi + lo = bias to ~2^-22
+  for (int i = threadIdx.x; i < 144; i += blockDim.x) {
+    float bv;
+    int off;   // byte offset of the channel's 16-byte row
+    if (i < 32) { bv = weff[d.b[1] + i]; off = IMG_BT_XV + 16 * i; }                           // X -> columns 0..31
+    else if (i < 64) { bv = weff[d.b[0] + i - 32]; off = IMG_BT_XV + 16 * i; }                 // V -> columns 32..63
+    else if (i < 80) { bv = weff[d.b[2] + i - 64]; off = IMG_BT_XXY + 16 * (i - 64); }         // XX
+    else if (i < 96) { bv = weff[d.b[3] + i - 80]; off = IMG_BT_XXY + 16 * (i - 64); }         // Y
+    else if (i < 128) { bv = weff[d.b[4] + i - 96]; off = IMG_BT_H + 16 * (i - 96); }          // H
+    else { bv = (i - 128) < 4 ? weff[d.b_head + i - 128] : 0.f; off = IMG_BT_HEAD + 16 * (i - 128); }
+    const __half hi = __float2half_rn(bv);
+    const __half lo = __float2half_rn(bv - __half2float(hi));
+    __half* row = reinterpret_cast<__half*>(img + off);
+    row[0] = hi; row[1] = lo;
+    for (int k = 2; k < 8; ++k) row[k] = __float2half_rn(0.f);
+  }
 }
 
 struct TcArgs {
@@ -80,7 +96,7 @@ struct TcArgs {
   const int8_t* sigma;
   float* out;
   long long n;
-  int H, W, P, nb, T, npos, p_first, np, tmem_cols;
+  int H, W, P, nb, T, npos, p_first, np, tmem_cols, cst_off;
   // activation dump for the tensor-core gradient (T == 1 only): fp16 tiles [cfg][nb*5 + 1][64*npos] in the shared-memory
   // tile layout (tensor order per block: x1, relu(v'), residual v, concat, h_out; last tile = input), relu masks
   // [cfg][nb][5][128] (bit c = channel c active, 0 on padding rows) and logits [cfg][128][4]
@@ -130,6 +146,10 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32 + TC_ISSUERS * 32, 1) tc_
   float* red = reinterpret_cast<float*>(tail + 128);             // [np][4 warps][2]
   int* taps = reinterpret_cast<int*>(tail + 256);                // tap offsets in positions: V[9] H[9] X[3]
   TcBlockDesc* sdesc = reinterpret_cast<TcBlockDesc*>(tail + 384);
+  // A operand of the bias MMAs: 128 rows of [1, 1, 0 x 6] (first K half) + 2 KB of zeros (second K half of A and of the
+  // bias tiles).  Last region of the dynamic shared memory, so every LBO that points at the zeros is positive.
+  uint8_t* ones_tile = smem + a.cst_off;
+  uint8_t* zero_tile = ones_tile + 2048;
 
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2]);
   const uint32_t mbar = smem_u32(&bars[4 + ((is_producer || is_issuer) ? 0 : pipe)]);
@@ -160,6 +180,9 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32 + TC_ISSUERS * 32, 1) tc_
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = tid; i < a.nb; i += blockDim.x) sdesc[i] = a.desc[i];
+  for (int i = tid; i < 256; i += blockDim.x) {
+    reinterpret_cast<uint4*>(ones_tile)[i] = i < 128 ? make_uint4(0x3C003C00u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);   // fp16 1.0, 1.0
+  }
   {  // zero every activation tile once: padding rows / slack positions are never written afterwards
     uint4* z = reinterpret_cast<uint4*>(act0);
     const int n16 = a.np * TC_SLOTS * buf_bytes / 16;
@@ -208,6 +231,13 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32 + TC_ISSUERS * 32, 1) tc_
       umma_f16_lohi(d_tmem, alo, blo, hi, n32 ? idesc32 : idesc16, acc);
       umma_f16_lohi(d_tmem, alo + kstep16, blo + (n32 ? 64u : 32u), hi, n32 ? idesc32 : idesc16, 1u);
     };
+    // bias MMA: D[:, col0 .. col0+N) += ones x bias tile (one K=16 step; the second K halves are the zero tile)
+    const uint32_t ones16 = smem_u32(ones_tile) >> 4, zero16 = smem_u32(zero_tile) >> 4;
+    auto bias_mma = [&](uint32_t d_tmem, uint32_t bt16, int n) {
+      const uint32_t alo = ones16 | ((zero16 - ones16) << 16);
+      const uint32_t blo = (bt16 & 0x3FFFu) | (((zero16 - bt16) & 0x3FFFu) << 16);
+      umma_f16_lohi(d_tmem, alo, blo, hi, make_idesc(n), 1u);
+    };
     long long step = 0;
     uint32_t turn = 0, phase_count = 0;
     for (long long it = 0; it < my_iters; ++it) {
@@ -251,17 +281,21 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32 + TC_ISSUERS * 32, 1) tc_
 #pragma unroll
                     for (int j = 0; j < 3; ++j)    // 3x3 on the vertical stack: pad top 2, left 1, right 1
                       tap_pair(dt + 32, a1, (i - 2) * P + (j - 1), wimg16 + IMG_V / 16 + 128 * (i * 3 + j), true, (i | j) != 0);
+                  bias_mma(dt + 0, wimg16 + IMG_BT_XV / 16, 64);
                 } else if (ph == 2) {
                   tap_pair(dt + 64, a0, last ? -1 : 0, wimg16 + IMG_XX / 16, false, 0u);
                   tap_pair(dt + 80, a1, -P, wimg16 + IMG_Y / 16, false, 0u);
+                  bias_mma(dt + 64, wimg16 + IMG_BT_XXY / 16, 32);
                 } else if (ph == 3) {
 #pragma unroll
                   for (int i = 0; i < 3; ++i)
 #pragma unroll
                     for (int j = 0; j < 3; ++j)    // 3x3 on the concat tensor: pad top 2, left 2
                       tap_pair(dt + 96, a0, (i - 2) * P + (j - 2), wimg16 + IMG_H / 16 + 128 * (i * 3 + j), true, (i | j) != 0);
+                  bias_mma(dt + 96, wimg16 + IMG_BT_H / 16, 32);
                 } else {
                   tap_pair(dt + 0, a0, 0, wimg16 + IMG_HEAD / 16, false, 0u);
+                  bias_mma(dt + 0, wimg16 + IMG_BT_HEAD / 16, 16);
                 }
               }
             }
@@ -378,7 +412,6 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32 + TC_ISSUERS * 32, 1) tc_
         mbar_wait(full0 + 8 * wsel, (uint32_t)((step >> 1) & 1));
         const uint8_t* wimg = wbuf + (size_t)wsel * IMG_BYTES;
         const uint32_t wimg16 = smem_u32(wimg) >> 4;
-        const float* bias = reinterpret_cast<const float*>(wimg + IMG_BIAS);
 
         // ================= phase 1: 1x3 conv on h (cols 0..31) and 3x3 conv on v (cols 32..63)
         TRACE(0);
@@ -393,7 +426,7 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32 + TC_ISSUERS * 32, 1) tc_
           tmem_ld32(tm_pipe + lane_sel + (uint32_t)(t * 128) + 0, v);
           if (site[t] >= 0) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bias[32 + i], 0.f);
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -402,8 +435,6 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32 + TC_ISSUERS * 32, 1) tc_
           if (DUMP && active && t == 0) dump_row(cfg, b, 0, v, site[t] >= 0);
           tmem_ld32(tm_pipe + lane_sel + (uint32_t)(t * 128) + 32, v);
           if (site[t] >= 0) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += bias[i];
             if (d.out_r >= 0) {
               float r[32];
               load_row(d.res_v, pos[t], r);
@@ -443,7 +474,7 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32 + TC_ISSUERS * 32, 1) tc_
           tmem_ld32(tm_pipe + lane_sel + (uint32_t)(t * 128) + 64, v);
           if (site[t] >= 0) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bias[64 + i], 0.f);
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -474,7 +505,7 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32 + TC_ISSUERS * 32, 1) tc_
               for (int i = 0; i < 32; ++i) v[i] += r[i];
             }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bias[96 + i], 0.f);
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -489,7 +520,6 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32 + TC_ISSUERS * 32, 1) tc_
         TRACE(9);
         // ================= phase 4 (last block): head 1x1 conv (C -> 4) + normalisation + combine
         if (d.last) {
-          const float* hb = reinterpret_cast<const float*>(wimg + IMG_HEAD_BIAS);
           mbar_wait(mbar, mma_phase);
           mma_phase ^= 1;
           tc_fence_after();
@@ -500,7 +530,7 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32 + TC_ISSUERS * 32, 1) tc_
             float v[16];
             tmem_ld16(tm_pipe + lane_sel + (uint32_t)(t * 128) + 0, v);
             if (site[t] >= 0) {
-              const float re0 = v[0] + hb[0], re1 = v[1] + hb[1], im0 = v[2] + hb[2], im1 = v[3] + hb[3];
+              const float re0 = v[0], re1 = v[1], im0 = v[2], im1 = v[3];   // (head bias added by the bias MMA)
               if (DUMP && active && t == 0)
                 *reinterpret_cast<float4*>(a.dump_logits + ((size_t)cfg * 128 + ltid) * 4) = make_float4(re0, re1, im0, im1);
               const float x = 2.f * re0, y = 2.f * re1;
@@ -561,11 +591,11 @@ static TcGeometry tc_geometry(const fk_net* net) {
   g.T = (p_last - g.p_first + 1 + 127) / 128;
   g.npos = ((g.p_first + g.T * 128 + 2) + 7) / 8 * 8;
   const size_t buf = (size_t)64 * g.npos;
-  const size_t tail = 384 + sizeof(TcBlockDesc) * (size_t)(2 * net->depth - 2) + 64;
+  const size_t tail = (384 + sizeof(TcBlockDesc) * (size_t)(2 * net->depth - 2) + 64 + 127) / 128 * 128;
   g.np = TC_MAX_NP;
   g.ok = g.T <= TC_MAX_T;
   for (;;) {
-    g.smem_bytes = 2 * (size_t)IMG_BYTES + (size_t)g.np * TC_SLOTS * buf + tail;
+    g.smem_bytes = 2 * (size_t)IMG_BYTES + (size_t)g.np * TC_SLOTS * buf + tail + 4096;   // + ones / zero tiles
     const int cols = g.np * g.T * 128;
     if (g.smem_bytes <= 227 * 1024 && cols <= 512) break;
     if (g.np == 1) { g.ok = false; break; }
@@ -677,7 +707,7 @@ int tc_forward_launch(fk_net* net, const int8_t* sigma, int64_t n, float* log_ps
   a.desc = reinterpret_cast<const TcBlockDesc*>((const uint8_t*)net->d_tc_weights + tc_desc_offset(nb));
   a.sigma = sigma; a.out = log_psi_out; a.n = n;
   a.H = net->H; a.W = net->W; a.P = g.P; a.nb = nb; a.T = g.T; a.npos = g.npos; a.p_first = g.p_first; a.np = g.np;
-  a.tmem_cols = g.tmem_cols;
+  a.tmem_cols = g.tmem_cols; a.cst_off = (int)(g.smem_bytes - 4096);
   a.dump = dump; a.dump_mask = dump_mask; a.dump_logits = dump_logits;
   FK_REQUIRE(dump == nullptr || g.T == 1, "tensor-core gradient: lattice needs more than one M tile");
   int dev = 0, sms = 148;

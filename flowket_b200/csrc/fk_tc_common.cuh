@@ -13,7 +13,14 @@ constexpr int IMG_H = 26624;          // 9 x 2 x 1024 B
 constexpr int IMG_BIAS = 45056;       // 128 floats: V[32] X[32] XX[16] Y[16] H[32]
 constexpr int IMG_HEAD = 45568;       // 2 x 512 B (N = 16, columns 0..3 used)
 constexpr int IMG_HEAD_BIAS = 46592;  // 16 floats
-constexpr int IMG_BYTES = 46656;
+constexpr int IMG_CORE_BYTES = 46656; // everything above (what the sampler stages)
+// bias tiles for the forward kernel: the biases enter the accumulators through one extra K=16 MMA per phase
+// (A = a tile of ones, B = [hi, lo, 0 x 6] per output channel with hi + lo = bias split into two fp16), 16 B per channel
+constexpr int IMG_BT_XV = 46656;      // 64 channels: X conv | V conv   (TMEM columns 0..63)
+constexpr int IMG_BT_XXY = 47680;     // 32 channels: XX | Y            (columns 64..95)
+constexpr int IMG_BT_H = 48192;       // 32 channels: H conv            (columns 96..127)
+constexpr int IMG_BT_HEAD = 48704;    // 16 channels: head              (columns 0..15)
+constexpr int IMG_BYTES = 48960;      // stride between block images
 
 // ---- PTX helpers ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

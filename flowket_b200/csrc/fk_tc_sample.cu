@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
   // the compiler moves every descriptor through a per-thread R2UR loop (~100 cycles per tcgen05.mma)
   const bool mma_warp = __shfl_sync(0xffffffffu, warp, 0) == 0;
   uint8_t* wbuf = smem;                                   // 2 weight images
-  uint8_t* ltile = smem + 2 * IMG_BYTES;                  // TS_NLOAD loaded tiles
+  uint8_t* ltile = smem + 2 * IMG_CORE_BYTES;                  // TS_NLOAD loaded tiles
   uint8_t* xc = ltile + TS_NLOAD * TS_TILE;               // x1, then the concat tensor (in place)
   uint8_t* hring = xc + TS_TILE;                          // 3 tiles: horizontal-stack tile of the current site per block parity
   uint8_t* tail = hring + 3 * TS_TILE;
@@ -147,8 +147,8 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
   // weight ring: image `img` for ring step s
   auto load_weights = [&](long long s, int img) {
     const uint32_t sel = (uint32_t)(s & 1);
-    mbar_expect_tx(wfull0 + 8 * sel, IMG_BYTES);
-    bulk_g2s(smem_u32(wbuf + (size_t)sel * IMG_BYTES), a.images + (size_t)img * IMG_BYTES, IMG_BYTES, wfull0 + 8 * sel);
+    mbar_expect_tx(wfull0 + 8 * sel, IMG_CORE_BYTES);
+    bulk_g2s(smem_u32(wbuf + (size_t)sel * IMG_CORE_BYTES), a.images + (size_t)img * IMG_BYTES, IMG_CORE_BYTES, wfull0 + 8 * sel);
   };
   // image sequence of a row: for every column [nb-1, 0, 1, ..., nb-2], then the vertical pass [0..nb-1]
   auto image_of = [&](long long s) -> int {
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
         }
         mbar_wait(wfull0 + 8 * wsel, (uint32_t)((step >> 1) & 1));
         if (nxa > 0) { mbar_wait(tfull, tile_phase); tile_phase ^= 1; }
-        const uint8_t* wimg = wbuf + (size_t)wsel * IMG_BYTES;
+        const uint8_t* wimg = wbuf + (size_t)wsel * IMG_CORE_BYTES;
         const uint32_t wimg16 = smem_u32(wimg) >> 4;
         const float* bias = reinterpret_cast<const float*>(wimg + IMG_BIAS);
         uint8_t* h_out = hring + (size_t)((b + 1) % 3) * TS_TILE;
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
       mbar_wait(cfull, c_phase); c_phase ^= 1;
       if (tid == 0 && W > 1) issue_col(1, -1);   // column 1 is needed by column 0's right tap
       if (W > 1) { mbar_wait(cfull, c_phase); c_phase ^= 1; }
-      const uint8_t* wimg = wbuf + (size_t)wsel * IMG_BYTES;
+      const uint8_t* wimg = wbuf + (size_t)wsel * IMG_CORE_BYTES;
       const uint32_t wimg16 = smem_u32(wimg) >> 4;
       const float* bias = reinterpret_cast<const float*>(wimg + IMG_BIAS);
       for (int j = 0; j < W; ++j) {
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
 }
 
-constexpr size_t TS_SMEM = 2 * (size_t)IMG_BYTES + (size_t)(TS_NLOAD + 1 + 3) * TS_TILE + 128;
+constexpr size_t TS_SMEM = 2 * (size_t)IMG_CORE_BYTES + (size_t)(TS_NLOAD + 1 + 3) * TS_TILE + 128;
 
 int64_t tc_sample_workspace_bytes(const fk_net* net, int64_t B) {
   const int nb = 2 * net->depth - 2;
