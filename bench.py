@@ -304,7 +304,11 @@ def run_gpu(args):
                      'frac': achieved_tf / (pk['bf16_sustained'] or pk['bf16']), 'traffic': None,
                      'kernel': 'local-energy wave-function evaluations (%s engine)' % args.engine,
                      'peak_source': pk['source'] + ' bf16 sustained (kernel timed inside a long step)',
-                     'flops_per_launch': flops_eloc},
+                     'flops_per_launch': flops_eloc,
+                     # measured: with 32 output channels per MMA the forward kernel is bounded by the
+                     # shared-memory operand stream (128 B/cycle/SM), not by tensor math; ~300 KB per configuration and block
+                     'smem_roofline': {'bytes_per_cfg_block': 300e3, 'peak_bytes_per_cycle_per_sm': 128,
+                                       'frac': ((n_conn / (eloc_ms * 1e-3)) * 38 * 300e3 / (148 * 128 * 1.965e9)) if args.engine == 'tc' else None}},
     }
     if world == 1 and not args.no_cpu_baseline:
         cb = cpu_step_rate(args.cpu_batch, 2)

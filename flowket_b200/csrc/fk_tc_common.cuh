@@ -38,7 +38,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(0x989680u)   // suspend-time hint: sleep in hardware instead of spinning on issue slots
+      : "r"(bar), "r"(parity), "r"(20000u)   // suspend-time hint (ns): sleep in hardware instead of spinning on issue slots
       : "memory");
   return ok;
 }
@@ -55,9 +55,10 @@ __device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
   return ok;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();  // a lost arrival must abort the kernel, never hang the GPU
+    if (clock64() - t0 > 8000000000LL) __trap();  // ~4 s: a lost arrival must abort the kernel, never hang the GPU
   }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
