@@ -310,6 +310,35 @@ def run_gpu(args):
                      'smem_roofline': {'bytes_per_cfg_block': 300e3, 'peak_bytes_per_cycle_per_sm': 128,
                                        'frac': ((n_conn / (eloc_ms * 1e-3)) * 38 * 300e3 / (148 * 128 * 1.965e9)) if args.engine == 'tc' else None}},
     }
+    if world == 1 and not args.no_sr:
+        # The same step with stochastic reconfiguration instead of Adam (north_star: sample + local energy + SR): per-sample
+        # Jacobians of the 854 k parameters, sample-space Gram (2B x 2B, K = P) as one tensor-core GEMM, Cholesky, update.
+        try:
+            from flowket_b200.optimizers import StochasticReconfiguration
+            sr = StochasticReconfiguration(model, lr=0.01, diag_shift=0.05, sample_space=True, gram_dtype='bf16',
+                                           jacobian_chunk=512)
+            times = []
+            for i in range(3):
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                sigma = sampler.next_device()
+                eloc = obs.local_values_device(model, sigma)
+                sr.step(sigma, eloc)
+                machine.device_net()
+                e1.record()
+                torch.cuda.synchronize()
+                if i > 0:
+                    times.append(e0.elapsed_time(e1))
+            ms = float(np.mean(times))
+            line['sr_step'] = {'ms_per_step': ms, 'samples_per_s': B / (ms * 1e-3), 'sr_update_ms': dict(sr.last_timings_ms),
+                               'solver': 'sample space: delta = X^T (X X^T / B + lambda)^-1 e / B, X = [Re O; Im O] (2B x P), '
+                                         'bf16 Gram / fp32 accumulate, fp64 Cholesky',
+                               'peak_mem_gb': torch.cuda.max_memory_allocated() / 1e9}
+            del sr
+            torch.cuda.empty_cache()
+        except Exception as exc:  # the SR leg must never take the headline line down with it
+            line['sr_step'] = {'error': '%s: %s' % (type(exc).__name__, exc)}
     if world == 1 and not args.no_cpu_baseline:
         cb = cpu_step_rate(args.cpu_batch, 2)
         line['cpu_baseline'] = {'value': cb['value'], 'unit': 'samples/s', 'cores': cb['cores'], 'kind': 'port',
@@ -333,6 +362,7 @@ def main():
     ap.add_argument('--batch-per-gpu', type=int, default=8192)
     ap.add_argument('--cpu-batch', type=int, default=8)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-sr', action='store_true', help='skip the stochastic-reconfiguration variant of the step')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

@@ -133,19 +133,100 @@ class ComplexValuesStochasticReconfiguration(_SRBase):
 
 
 class StochasticReconfiguration(_SRBase):
-    """Real-parameter SR (ConvNetAutoregressive2D, SimpleConvNetAutoregressive1D)."""
+    """Real-parameter SR (ConvNetAutoregressive2D, SimpleConvNetAutoregressive1D).
+
+    With X = [Re Obar ; Im Obar] (2B x P) the system is (X^T X / B + lambda I) delta = X^T e' / B, e' = [Re(E - Ebar) ;
+    Im(E - Ebar)].  Three solvers, all the same delta:
+      * direct        P x P Gram through fk_sr_gram + Cholesky               (small machines, reference default shape)
+      * iterative     conjugate gradient on v -> X^T (X v) / B + lambda v    (linear_equations.py:34-137)
+      * sample space  delta = X^T (X X^T / B + lambda I)^-1 e' / B -- the push-through identity, exact, with a
+                      2B x 2B Gram whose K dimension is the parameter axis.  This is the form that fits the 850 k
+                      parameter machine of the headline configuration (P x P would be 2.9 TB): the Gram is one
+                      tensor-core GEMM (cuBLAS, bf16 operands / fp32 accumulation by default) + a Cholesky of size 2B.
+    `sample_space=None` picks the sample-space form when P > 2B."""
+
+    def __init__(self, model, sample_space=None, gram_dtype='bf16', jacobian_chunk=1024, **kwargs):
+        super(StochasticReconfiguration, self).__init__(model, **kwargs)
+        self.sample_space = sample_space
+        self.gram_dtype = gram_dtype
+        self.jacobian_chunk = jacobian_chunk
+        self.last_timings_ms = {}
+
+    def stacked_jacobian(self, sigma):
+        """X = [Re O ; Im O] (uncentred) as one [2B, P] fp32 device tensor, built in chunks of samples."""
+        import torch
+        net = self.machine.device_net()
+        sig = net.to_sigma(sigma)
+        B, P = sig.shape[0], net.num_params
+        X = torch.empty((2 * B, P), dtype=torch.float32, device=sig.device)
+        for b0 in range(0, B, self.jacobian_chunk):
+            b1 = min(B, b0 + self.jacobian_chunk)
+            O_re, O_im = net.grad_per_sample(sig[b0:b1], imag=True)
+            X[b0:b1] = O_re
+            X[B + b0:B + b1] = O_im
+            del O_re, O_im
+        return X
 
     def compute_update(self, sigma, local_energy):
         import torch
-        O_re, O_im = self.jacobian(sigma)
-        B = O_re.shape[0]
-        e = torch.as_tensor(np.asarray(local_energy, np.complex128)).to(O_re.device)
+        t = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        t[0].record()
+        X = self.stacked_jacobian(sigma)
+        B = X.shape[0] // 2
+        if torch.is_tensor(local_energy):
+            e = local_energy.to(device=X.device, dtype=torch.complex128)   # device-resident E_loc: no host round trip
+        else:
+            e = torch.as_tensor(np.asarray(local_energy, np.complex128)).to(X.device)
         e = e - e.mean()
-        R = (O_re - O_re.mean(dim=0, keepdim=True))
-        I = (O_im - O_im.mean(dim=0, keepdim=True))
-        F = (R.T @ e.real.float() + I.T @ e.imag.float()) / B          # Re(Obar^H (E - Ebar)) / B
-        stacked = torch.cat([R, I], dim=0)                             # Re(Obar^H Obar) = R^T R + I^T I
-        return self.solve(stacked, F) if not self.iterative_solver else self._solve_real(stacked, F, B)
+        X[:B] -= X[:B].mean(dim=0, keepdim=True)
+        X[B:] -= X[B:].mean(dim=0, keepdim=True)
+        ep = torch.cat([e.real, e.imag]).float()
+        t[1].record()
+        sample_space = self.sample_space if self.sample_space is not None else X.shape[1] > X.shape[0]
+        if sample_space:
+            delta = self._solve_sample_space(X, ep, B)
+        elif self.iterative_solver:
+            delta = self._solve_real(X, X.T @ ep / B, B)
+        else:
+            delta = self.solve(X, X.T @ ep / B)
+        t[2].record()
+        torch.cuda.synchronize()
+        self.last_timings_ms = {'jacobian': t[0].elapsed_time(t[1]), 'solve': t[1].elapsed_time(t[2])}
+        ev = getattr(self, '_solve_events', None)
+        if sample_space and ev is not None and self.gram_dtype != 'fp32':
+            self.last_timings_ms.update({'convert': ev[0].elapsed_time(ev[1]), 'gram': ev[1].elapsed_time(ev[2]),
+                                         'cholesky': ev[2].elapsed_time(ev[3])})
+        return delta
+
+    def _solve_sample_space(self, X, ep, B):
+        import torch
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        if self.gram_dtype == 'fp32':
+            T = X @ X.T
+        else:
+            dt = {'bf16': torch.bfloat16, 'fp16': torch.float16}[self.gram_dtype]
+            # scale to O(1) before rounding (fp16 range; harmless for bf16), undo on the fp32 result
+            rows = 1024   # row chunks: no second fp32 copy of X (56 GB at B = 8192 on the 850 k parameter machine)
+            scale = torch.stack([X[r:r + rows].abs().amax() for r in range(0, X.shape[0], rows)]).amax().clamp_min(1e-30)
+            P = X.shape[1]
+            P_pad = (P + 127) // 128 * 128     # 16-byte aligned rows: cuBLAS takes its slow path otherwise (4.7x here)
+            Xl = torch.empty((X.shape[0], P_pad), dtype=dt, device=X.device)
+            Xl[:, P:] = 0
+            for r in range(0, X.shape[0], rows):
+                Xl[r:r + rows, :P] = X[r:r + rows] / scale
+            ev[1].record()
+            T = torch.mm(Xl, Xl.T, out_dtype=torch.float32) * (scale * scale)
+            del Xl
+        ev[2].record()
+        T = T / B
+        T.diagonal().add_(self.diag_shift)
+        L = torch.linalg.cholesky(T.double())          # 2B x 2B, fp64: the Gram can be badly conditioned
+        w = torch.cholesky_solve((ep.double() / B).reshape(-1, 1), L).reshape(-1).float()
+        ev[3].record()
+        delta = X.T @ w
+        self._solve_events = ev
+        return delta
 
     def _solve_real(self, stacked, F, B):
         def apply(v):

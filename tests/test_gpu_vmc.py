@@ -134,9 +134,14 @@ def test_real_sr_matches_oracle():
     want = np.linalg.solve(S, F)
     for iterative in (False, True):
         sr = StochasticReconfiguration(model, diag_shift=0.05, iterative_solver=iterative, conjugate_gradient_tol=1e-7,
-                                       iterative_solver_max_iterations=5000)
+                                       iterative_solver_max_iterations=5000, sample_space=False)
         got = sr.compute_update(sigma, eloc).cpu().numpy()
         assert np.linalg.norm(got - want) / np.linalg.norm(want) < 5e-4, iterative
+    # sample-space form (2B x 2B Gram over the parameter axis): the same delta by the push-through identity
+    for gram_dtype, tol in (('fp32', 5e-4), ('bf16', 2e-2)):
+        sr = StochasticReconfiguration(model, diag_shift=0.05, sample_space=True, gram_dtype=gram_dtype, jacobian_chunk=40)
+        got = sr.compute_update(sigma, eloc).cpu().numpy()
+        assert np.linalg.norm(got - want) / np.linalg.norm(want) < tol, gram_dtype
 
 
 def test_sr_gram_kernel():
