@@ -148,15 +148,22 @@ class DeviceNet(object):
             _lib.check(fn(self.handle, _ptr(sigma), _ptr(y2), B, _ptr(grad), _ptr(ws), ws.numel(), _lib.stream_ptr()))
         return grad
 
-    def grad_per_sample(self, sigma, imag=True):
+    def grad_per_sample(self, sigma, imag=True, engine=_lib.FK_ENGINE_FP32):
         torch = self.torch
         B = sigma.shape[0]
         O_re = torch.empty((B, self.num_params), dtype=torch.float32, device=self.device)
         O_im = torch.empty((B, self.num_params), dtype=torch.float32, device=self.device) if imag else None
-        ws = self.workspace('grad_ps', self.lib.fk_grad_workspace_bytes(self.handle, B, 1))
+        if engine == _lib.FK_ENGINE_TC:
+            nbytes = self.lib.fk_grad_per_sample_tc_workspace_bytes(self.handle, B)
+            if nbytes < 0:
+                raise _lib.FlowketB200Error('tensor-core per-sample gradient: machine / lattice not supported')
+            ws = self.workspace('grad_ps_tc', nbytes)
+            fn = self.lib.fk_grad_per_sample_tc
+        else:
+            ws = self.workspace('grad_ps', self.lib.fk_grad_workspace_bytes(self.handle, B, 1))
+            fn = self.lib.fk_grad_per_sample
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.fk_grad_per_sample(self.handle, _ptr(sigma), B, _ptr(O_re), _ptr(O_im), _ptr(ws),
-                                                   ws.numel(), _lib.stream_ptr()))
+            _lib.check(fn(self.handle, _ptr(sigma), B, _ptr(O_re), _ptr(O_im), _ptr(ws), ws.numel(), _lib.stream_ptr()))
         return O_re, O_im
 
 

@@ -620,6 +620,16 @@ int64_t grad_transform_launch(fk_net* net, const float* geff, float* graw, cudaS
   FK_CHECK_LAUNCH();
   return 0;
 }
+int grad_transform_rows_launch(fk_net* net, const float* geff, float* graw, int64_t m, cudaStream_t s) {
+  for (int64_t r0 = 0; r0 < m; r0 += 32768) {   // grid.y limit
+    const int64_t rows = std::min<int64_t>(32768, m - r0);
+    grad_transform_kernel<<<dim3((unsigned)net->ops.size(), (unsigned)rows), 128, 0, s>>>(
+        (const OpParam*)net->d_optable, net->d_params, geff + r0 * net->num_eff, net->num_eff, graw + r0 * net->num_params,
+        net->num_params);
+    FK_CHECK_LAUNCH();
+  }
+  return 0;
+}
 }  // namespace fk
 
 extern "C" int fk_grad_weighted(fk_net_t* net, const int8_t* sigma, const float* y, int64_t B, float* grad_out, void* ws,
@@ -632,6 +642,20 @@ extern "C" int fk_grad_per_sample(fk_net_t* net, const int8_t* sigma, int64_t B,
                                   int64_t ws_bytes, void* stream) {
   FK_REQUIRE(net && sigma && O_re && ws, "fk_grad_per_sample: NULL argument");
   return grad_impl(net, sigma, nullptr, B, nullptr, O_re, O_im, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+// tensor-core engine of the per-sample Jacobians (fk_tc_grad.cu)
+extern "C" int64_t fk_grad_per_sample_tc_workspace_bytes(const fk_net_t* net, int64_t B) {
+  if (!net || !tc_grad_supported(net)) return -1;
+  return tc_grad_per_sample_workspace_bytes(net, B);
+}
+
+extern "C" int fk_grad_per_sample_tc(fk_net_t* net, const int8_t* sigma, int64_t B, float* O_re, float* O_im, void* ws,
+                                     int64_t ws_bytes, void* stream) {
+  FK_REQUIRE(net && sigma && O_re && ws, "fk_grad_per_sample_tc: NULL argument");
+  FK_REQUIRE(tc_grad_supported(net), "fk_grad_per_sample_tc: supports ConvNetAutoregressive2D, 32 channels, kernel 3, lattices that fit one M tile");
+  if (B == 0) return 0;
+  return tc_grad_per_sample(net, sigma, B, O_re, O_im, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 // tensor-core engine of the weighted gradient (fk_tc_grad.cu)

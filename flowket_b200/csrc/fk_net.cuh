@@ -53,6 +53,11 @@ int64_t tc_grad_workspace_bytes(const fk_net* net, int64_t B);
 int tc_grad_weighted(fk_net* net, const int8_t* sigma, const float* y, int64_t B, float* grad_out, void* ws,
                      int64_t ws_bytes, cudaStream_t s);
 int64_t grad_transform_launch(fk_net* net, const float* geff, float* graw, cudaStream_t s);
+// rows: geff [m][num_eff] -> graw [m][num_params]
+int grad_transform_rows_launch(fk_net* net, const float* geff, float* graw, int64_t m, cudaStream_t s);
+int64_t tc_grad_per_sample_workspace_bytes(const fk_net* net, int64_t B);
+int tc_grad_per_sample(fk_net* net, const int8_t* sigma, int64_t B, float* O_re, float* O_im, void* ws, int64_t ws_bytes,
+                       cudaStream_t s);
 
 // tensor-core sampler (fk_tc_sample.cu)
 int64_t tc_sample_workspace_bytes(const fk_net* net, int64_t B);

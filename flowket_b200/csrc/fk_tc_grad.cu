@@ -360,6 +360,10 @@ struct DwUnit { int b, nconv; DwConv conv[3]; };
 struct DwArgs2 {
   const uint8_t* dump; const uint8_t* dz; const DwUnit* units; float* geff;
   long long n; int nb, npos, num_units, cfg_chunk;
+  // per-sample Jacobians: cfg_chunk == 1 and every configuration writes its own row of geff (row_stride floats apart,
+  // plain stores, values multiplied by out_scale); row_stride == 0: one shared gradient, atomics
+  long long row_stride;
+  float out_scale;
 };
 
 constexpr int DW_STAGES = 3;
@@ -376,6 +380,7 @@ __global__ void __launch_bounds__(128, 1) tc_dw_kernel(DwArgs2 a) {
   if (tid == 32) {
     for (int i = 0; i < DW_STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
     mbar_init(done, 1);
+    mbar_init(smem_u32(&bars[2 * DW_STAGES + 1]), 1);   // tfree
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -400,17 +405,20 @@ __global__ void __launch_bounds__(128, 1) tc_dw_kernel(DwArgs2 a) {
 
   const int chunks = (int)((a.n + a.cfg_chunk - 1) / a.cfg_chunk);
   const int items = a.num_units * chunks;
-  uint32_t full_phase = 0, empty_phase = 0, done_phase = 0;   // bit i = parity of stage i
-  long long prod_count = 0, cons_count = 0;
-
-  for (int item = blockIdx.x; item < items; item += gridDim.x) {
-    const DwUnit& u = a.units[item % a.num_units];
-    const long long c_beg = (long long)(item / a.num_units) * a.cfg_chunk;
-    const long long c_end = c_beg + a.cfg_chunk < a.n ? c_beg + a.cfg_chunk : a.n;
-    if (warp == 0) {
-      // ---- producer: one stage per configuration
-      for (long long cfg = c_beg; cfg < c_end; ++cfg) {
-        if (lane == 0) {
+  // Three roles, each walking the same item list on its own: warp 2 loads (runs ahead through the stage ring), warp 1
+  // issues the MMAs of an item once the previous item's accumulators have been flushed (`tfree`), warp 0 (TMEM lanes
+  // 0..31 = input channels) flushes an item when its MMAs have retired (`done`).
+  const uint32_t tfree = smem_u32(&bars[2 * DW_STAGES + 1]);
+  if (warp == 2) {
+    // ---- producer: one stage per configuration
+    if (lane == 0) {
+      uint32_t empty_phase = 0;   // bit i = parity of stage i
+      long long prod_count = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const DwUnit u = a.units[item % a.num_units];   // by value: the asm memory clobbers / global stores would force reloads
+        const long long c_beg = (long long)(item / a.num_units) * a.cfg_chunk;
+        const long long c_end = c_beg + a.cfg_chunk < a.n ? c_beg + a.cfg_chunk : a.n;
+        for (long long cfg = c_beg; cfg < c_end; ++cfg) {
           const int st = (int)(prod_count % DW_STAGES);
           if (prod_count >= DW_STAGES) { mbar_wait(empty0 + 8 * st, (empty_phase >> st) & 1u); empty_phase ^= 1u << st; }
           uint8_t* sb = smem + (size_t)st * stage_bytes;
@@ -423,17 +431,24 @@ __global__ void __launch_bounds__(128, 1) tc_dw_kernel(DwArgs2 a) {
           }
           ++prod_count;
         }
-        __syncwarp();
       }
-      prod_count = __shfl_sync(0xffffffffu, prod_count, 0);
-      empty_phase = __shfl_sync(0xffffffffu, empty_phase, 0);
-    } else if (warp == 1) {
-      // ---- MMA issuer (elected lane of the converged warp: the descriptors stay in uniform registers)
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---- MMA issuer (elected lane of the converged warp: the descriptors stay in uniform registers)
+    uint32_t full_phase = 0;
+    long long cons_count = 0, item_count = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_count) {
+      const DwUnit u = a.units[item % a.num_units];   // by value: the asm memory clobbers / global stores would force reloads
+      const long long c_beg = (long long)(item / a.num_units) * a.cfg_chunk;
+      const long long c_end = c_beg + a.cfg_chunk < a.n ? c_beg + a.cfg_chunk : a.n;
+      mbar_wait(tfree, (uint32_t)((item_count & 1) ^ 1));   // previous item flushed (passes at once for the first item)
+      tc_fence_after();
       for (long long cfg = c_beg; cfg < c_end; ++cfg) {
+        const int st = (int)(cons_count % DW_STAGES);
+        mbar_wait(full0 + 8 * st, (full_phase >> st) & 1u); full_phase ^= 1u << st;
+        tc_fence_after();
         if (elect_one()) {
-          const int st = (int)(cons_count % DW_STAGES);
-          mbar_wait(full0 + 8 * st, (full_phase >> st) & 1u); full_phase ^= 1u << st;
-          tc_fence_after();
           const uint32_t sb16 = smem_u32(smem + (size_t)st * stage_bytes) >> 4;
           for (int k = 0; k < u.nconv; ++k) {
             const DwConv& cv = u.conv[k];
@@ -452,18 +467,17 @@ __global__ void __launch_bounds__(128, 1) tc_dw_kernel(DwArgs2 a) {
           }
           umma_commit(empty0 + 8 * st);                 // stage free when its MMAs retire
           if (cfg + 1 == c_end) umma_commit(done);
-          ++cons_count;
         }
         __syncwarp();
-      }
-      {
-        const int leader = __ffs(__ballot_sync(0xffffffffu, elect_one())) - 1;
-        cons_count = __shfl_sync(0xffffffffu, cons_count, leader);
-        full_phase = __shfl_sync(0xffffffffu, full_phase, leader);
+        ++cons_count;
       }
     }
+  } else if (warp == 0) {
     // ---- flush: warp 0 owns TMEM lanes 0..31 = input channels
-    if (warp == 0) {
+    uint32_t done_phase = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const DwUnit u = a.units[item % a.num_units];   // by value: the asm memory clobbers / global stores would force reloads
+      const long long c_beg = (long long)(item / a.num_units) * a.cfg_chunk;
       mbar_wait(done, done_phase); done_phase ^= 1;
       tc_fence_after();
       for (int k = 0; k < u.nconv; ++k) {
@@ -480,14 +494,21 @@ __global__ void __launch_bounds__(128, 1) tc_dw_kernel(DwArgs2 a) {
           }
           if (lane < cv.cin) {
             float* dst = a.geff + cv.w_off + ((long long)t * cv.cin + lane) * cv.n;
-            for (int co = 0; co < cv.n; ++co) atomicAdd(dst + co, v[co]);
+            if (a.row_stride == 0) {
+              for (int co = 0; co < cv.n; ++co) atomicAdd(dst + co, v[co]);
+            } else {   // (offsets and the row stride are multiples of 4 floats: checked on the host)
+              float4* d4 = reinterpret_cast<float4*>(dst + c_beg * a.row_stride);
+              for (int q = 0; q < cv.n / 4; ++q)
+                d4[q] = make_float4(v[4 * q] * a.out_scale, v[4 * q + 1] * a.out_scale, v[4 * q + 2] * a.out_scale,
+                                    v[4 * q + 3] * a.out_scale);
+            }
           }
         }
       }
       tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tfree);   // the accumulators may be overwritten
     }
-    __syncthreads();   // the next item re-initialises the accumulators only after the flush
-    tc_fence_after();
   }
   tc_fence_before();
   __syncthreads();
@@ -540,6 +561,70 @@ __global__ void tc_head_dw_kernel(const uint8_t* __restrict__ dump, const float*
     atomicAdd(geff + w_off + ci * 4 + k, acc[k]);
     if (ci == 0) atomicAdd(geff + b_off + k, bacc[k]);
   }
+}
+
+// per-sample variants (stochastic reconfiguration): one row of geff per configuration, plain stores
+__global__ void tc_db_ps_kernel(const uint8_t* __restrict__ dz, long long n, int nb, const long long* __restrict__ b_off,
+                                float* __restrict__ geff, long long row_stride, float out_scale) {
+  const int b = blockIdx.x >> 2, tile = blockIdx.x & 3;
+  const int ch = threadIdx.x & 31, part = threadIdx.x >> 5;    // 256 threads: 8 row groups x 32 channels
+  __shared__ float red[8][32];
+  for (long long cfg = blockIdx.y; cfg < n; cfg += gridDim.y) {
+    const __half* t = reinterpret_cast<const __half*>(dz + (((size_t)cfg * nb + b) * 4 + tile) * DZ_TILE);
+    float acc = 0.f;
+    for (int r = part; r < 128; r += 8) acc += __half2float(t[((ch >> 3) * 128 + r) * 8 + (ch & 7)]);
+    red[part][ch] = acc;
+    __syncthreads();
+    if (part == 0) {
+      float s = 0.f;
+      for (int i = 0; i < 8; ++i) s += red[i][ch];
+      long long off;
+      if (tile == 0) off = b_off[b * 5 + 4] + ch;
+      else if (tile == 1) off = ch < 16 ? b_off[b * 5 + 2] + ch : b_off[b * 5 + 3] + ch - 16;
+      else if (tile == 2) off = b_off[b * 5 + 1] + ch;
+      else off = b_off[b * 5 + 0] + ch;
+      geff[cfg * row_stride + off] = s * out_scale;
+    }
+    __syncthreads();
+  }
+}
+__global__ void tc_head_dw_ps_kernel(const uint8_t* __restrict__ dump, const float* __restrict__ glog, long long n, int nb, int npos,
+                                     int p_first, long long w_off, long long b_off, float* __restrict__ geff, long long row_stride,
+                                     float out_scale) {
+  const int ci = threadIdx.x & 31, part = threadIdx.x >> 5;   // 256 threads
+  const size_t xt = (size_t)64 * npos, cfg_bytes = (size_t)(nb * NDUMP + 1) * xt;
+  __shared__ float red[8][32][4], bred[8][4];
+  for (long long cfg = blockIdx.x; cfg < n; cfg += gridDim.x) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, bacc[4] = {0.f, 0.f, 0.f, 0.f};
+    const __half* t = reinterpret_cast<const __half*>(dump + (size_t)cfg * cfg_bytes + (size_t)((nb - 1) * NDUMP + 4) * xt);
+    for (int r = part; r < 128; r += 8) {
+      const float4 g = *reinterpret_cast<const float4*>(glog + ((size_t)cfg * 128 + r) * 4);
+      const float h = __half2float(t[((size_t)(ci >> 3) * npos + p_first + r) * 8 + (ci & 7)]);
+      acc[0] += h * g.x; acc[1] += h * g.y; acc[2] += h * g.z; acc[3] += h * g.w;
+      if (ci == 0) { bacc[0] += g.x; bacc[1] += g.y; bacc[2] += g.z; bacc[3] += g.w; }
+    }
+    for (int k = 0; k < 4; ++k) { red[part][ci][k] = acc[k]; if (ci == 0) bred[part][k] = bacc[k]; }
+    __syncthreads();
+    if (part == 0) {
+      for (int k = 0; k < 4; ++k) {
+        float sacc = 0.f;
+        for (int i = 0; i < 8; ++i) sacc += red[i][ci][k];
+        geff[cfg * row_stride + w_off + ci * 4 + k] = sacc * out_scale;
+      }
+      if (ci < 4) {
+        float sb = 0.f;
+        for (int i = 0; i < 8; ++i) sb += bred[i][ci];
+        geff[cfg * row_stride + b_off + ci] = sb * out_scale;
+      }
+    }
+    __syncthreads();
+  }
+}
+__global__ void tc_const_coef_kernel(long long n, float re, float im, float* __restrict__ coef) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  coef[2 * i] = re;
+  coef[2 * i + 1] = im;
 }
 
 // power-of-two loss scale chosen on the device: max |2 y| * scale <= 128 (head gradients in the fp16 normal range)
@@ -696,6 +781,7 @@ int tc_grad_weighted(fk_net* net, const int8_t* sigma, const float* y, int64_t B
     da.dump = base + L.dump; da.dz = base + L.dz; da.units = reinterpret_cast<const DwUnit*>(wb + bwd_units_offset(nb));
     da.geff = geff; da.n = m; da.nb = nb; da.npos = g.npos; da.num_units = 2 * nb;
     da.cfg_chunk = (int)std::max<int64_t>(1, (m + 7) / 8);
+    da.row_stride = 0; da.out_scale = 1.f;
     const int items = da.num_units * (int)((m + da.cfg_chunk - 1) / da.cfg_chunk);
     tc_dw_kernel<<<(unsigned)std::min(items, sms), 128, dw_smem, s>>>(da);
     FK_CHECK_LAUNCH();
@@ -708,6 +794,93 @@ int tc_grad_weighted(fk_net* net, const int8_t* sigma, const float* y, int64_t B
   tc_scale_kernel<<<(unsigned)((net->num_eff + 255) / 256), 256, 0, s>>>(geff, net->num_eff, scale);
   FK_CHECK_LAUNCH();
   if (grad_transform_launch(net, geff, grad_out, s)) return 1;
+  return 0;
+}
+
+// ---- per-sample Jacobians on the tensor cores: O_re[b] = d Re log psi(sigma_b) / d theta, O_im[b] = d Im log psi / d theta ----
+struct PsLayout { size_t geff, dump, mask, logits, dz, glog, coef, lp, total; };
+static PsLayout ps_layout(const fk_net* net, int64_t chunk) {
+  TcPublicGeometry g;
+  tc_public_geometry(net, &g);
+  PsLayout L;
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  size_t o = 0;
+  L.geff = o; o = al(o + sizeof(float) * (size_t)net->num_eff * chunk);
+  L.dump = o; o = al(o + (size_t)chunk * (g.nb * NDUMP + 1) * 64 * g.npos);
+  L.mask = o; o = al(o + (size_t)chunk * g.nb * NDUMP * 128 * 4);
+  L.logits = o; o = al(o + (size_t)chunk * 128 * 16);
+  L.dz = o; o = al(o + (size_t)chunk * g.nb * 4 * DZ_TILE);
+  L.glog = o; o = al(o + (size_t)chunk * 128 * 16);
+  L.coef = o; o = al(o + (size_t)chunk * 8);
+  L.lp = o; o = al(o + (size_t)chunk * 8);
+  L.total = o;
+  return L;
+}
+
+int64_t tc_grad_per_sample_workspace_bytes(const fk_net* net, int64_t B) {
+  return (int64_t)ps_layout(net, std::max<int64_t>(1, std::min<int64_t>(B, 512))).total;
+}
+
+int tc_grad_per_sample(fk_net* net, const int8_t* sigma, int64_t B, float* O_re, float* O_im, void* ws, int64_t ws_bytes,
+                       cudaStream_t s) {
+  FK_REQUIRE(net->params_set && net->d_tc_bwd, "tensor-core gradient weights were never packed (fk_net_set_params)");
+  FK_REQUIRE(net->num_eff % 4 == 0, "tensor-core per-sample gradient: effective-weight rows must be 16-byte aligned");
+  for (const ConvOp& op : net->ops)
+    FK_REQUIRE(op.w_off % 4 == 0, "tensor-core per-sample gradient: weight offsets must be 16-byte aligned");
+  TcPublicGeometry g;
+  tc_public_geometry(net, &g);
+  int64_t chunk = std::min<int64_t>(B, 512);
+  while (chunk > 1 && (int64_t)ps_layout(net, chunk).total > ws_bytes) chunk /= 2;
+  const PsLayout L = ps_layout(net, chunk);
+  FK_REQUIRE((int64_t)L.total <= ws_bytes, "tensor-core per-sample gradient: workspace too small (%lld < %zu bytes)",
+             (long long)ws_bytes, L.total);
+  uint8_t* base = (uint8_t*)ws;
+  float* geff = (float*)(base + L.geff);
+  const int nb = g.nb;
+  const int npos_g = ((g.p_first + 128 + 2 * g.P + 4) + 7) / 8 * 8;
+  int dev = 0, sms = 148;
+  FK_CHECK_CUDA(cudaGetDevice(&dev));
+  FK_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const size_t bwd_smem = 2 * (size_t)IMGB_BYTES + (size_t)BWD_NP * 4 * 64 * npos_g + 256;
+  const size_t dw_smem = (size_t)DW_STAGES * 3 * (64 * g.npos + DZ_TILE) + (size_t)16 * g.npos * 16 + 256;
+  FK_REQUIRE(bwd_smem <= 227 * 1024 && dw_smem <= 227 * 1024, "tensor-core gradient: lattice too large for shared memory");
+  FK_CHECK_CUDA(cudaFuncSetAttribute(tc_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem));
+  FK_CHECK_CUDA(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem));
+  const uint8_t* wb = (const uint8_t*)net->d_tc_bwd;
+  const float seed_scale = 64.f;   // power of two: unit seeds x 64 keep the head gradients in the fp16 normal range
+  for (int64_t i = 0; i < B; i += chunk) {
+    const int64_t m = std::min(chunk, B - i);
+    const int8_t* sg = sigma + i * net->sites;
+    if (tc_forward_launch(net, sg, m, (float*)(base + L.lp), base + L.dump, (uint32_t*)(base + L.mask), (float*)(base + L.logits), s)) return 1;
+    for (int pass = 0; pass < (O_im ? 2 : 1); ++pass) {
+      // coef = (dL/dRe log psi, dL/dIm log psi): (1, 0) gives d Re log psi / d theta, (0, 1) gives d Im log psi / d theta
+      tc_const_coef_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(m, pass == 0 ? seed_scale : 0.f, pass == 0 ? 0.f : seed_scale,
+                                                                        (float*)(base + L.coef));
+      FK_CHECK_LAUNCH();
+      BwdArgs ba;
+      ba.images = wb; ba.mask = (const uint32_t*)(base + L.mask); ba.logits = (const float*)(base + L.logits);
+      ba.sigma = sg; ba.coef = (const float*)(base + L.coef); ba.dz = base + L.dz; ba.glog = (float*)(base + L.glog);
+      ba.n = m; ba.H = net->H; ba.W = net->W; ba.P = g.P; ba.nb = nb; ba.npos_g = npos_g; ba.p_first = g.p_first;
+      const long long groups = (m + BWD_NP - 1) / BWD_NP;
+      tc_backward_kernel<<<(unsigned)std::min<long long>(groups, sms), BWD_NP * 128 + 32, bwd_smem, s>>>(ba);
+      FK_CHECK_LAUNCH();
+      DwArgs2 da;
+      da.dump = base + L.dump; da.dz = base + L.dz; da.units = reinterpret_cast<const DwUnit*>(wb + bwd_units_offset(nb));
+      da.geff = geff; da.n = m; da.nb = nb; da.npos = g.npos; da.num_units = 2 * nb;
+      da.cfg_chunk = 1; da.row_stride = net->num_eff; da.out_scale = 1.f / seed_scale;
+      const long long items = (long long)da.num_units * m;
+      tc_dw_kernel<<<(unsigned)std::min<long long>(items, sms), 128, dw_smem, s>>>(da);
+      FK_CHECK_LAUNCH();
+      tc_db_ps_kernel<<<dim3((unsigned)(nb * 4), (unsigned)std::min<int64_t>(m, 64)), 256, 0, s>>>(
+          base + L.dz, m, nb, reinterpret_cast<const long long*>(wb + bwd_boff_offset(nb)), geff, net->num_eff, 1.f / seed_scale);
+      FK_CHECK_LAUNCH();
+      tc_head_dw_ps_kernel<<<(unsigned)std::min<int64_t>(m, 1024), 256, 0, s>>>(
+          base + L.dump, (const float*)(base + L.glog), m, nb, g.npos, g.p_first, net->ops.back().w_off, net->ops.back().b_off, geff,
+          net->num_eff, 1.f / seed_scale);
+      FK_CHECK_LAUNCH();
+      if (grad_transform_rows_launch(net, geff, (pass == 0 ? O_re : O_im) + i * net->num_params, m, s)) return 1;
+    }
+  }
   return 0;
 }
 

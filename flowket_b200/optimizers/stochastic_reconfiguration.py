@@ -152,6 +152,14 @@ class StochasticReconfiguration(_SRBase):
         self.jacobian_chunk = jacobian_chunk
         self.last_timings_ms = {}
 
+    def _jacobian_engine(self, net):
+        """tensor-core Jacobians when the model asks for the tensor-core engine and the machine is supported"""
+        from .. import _lib
+        if getattr(self.model, 'engine', _lib.FK_ENGINE_FP32) == _lib.FK_ENGINE_TC and \
+                net.lib.fk_grad_per_sample_tc_workspace_bytes(net.handle, 1) >= 0:
+            return _lib.FK_ENGINE_TC
+        return _lib.FK_ENGINE_FP32
+
     def stacked_jacobian(self, sigma):
         """X = [Re O ; Im O] (uncentred) as one [2B, P] fp32 device tensor, built in chunks of samples."""
         import torch
@@ -161,7 +169,7 @@ class StochasticReconfiguration(_SRBase):
         X = torch.empty((2 * B, P), dtype=torch.float32, device=sig.device)
         for b0 in range(0, B, self.jacobian_chunk):
             b1 = min(B, b0 + self.jacobian_chunk)
-            O_re, O_im = net.grad_per_sample(sig[b0:b1], imag=True)
+            O_re, O_im = net.grad_per_sample(sig[b0:b1], imag=True, engine=self._jacobian_engine(net))
             X[b0:b1] = O_re
             X[B + b0:B + b1] = O_im
             del O_re, O_im
@@ -206,17 +214,22 @@ class StochasticReconfiguration(_SRBase):
             T = X @ X.T
         else:
             dt = {'bf16': torch.bfloat16, 'fp16': torch.float16}[self.gram_dtype]
-            # scale to O(1) before rounding (fp16 range; harmless for bf16), undo on the fp32 result
-            rows = 1024   # row chunks: no second fp32 copy of X (56 GB at B = 8192 on the 850 k parameter machine)
-            scale = torch.stack([X[r:r + rows].abs().amax() for r in range(0, X.shape[0], rows)]).amax().clamp_min(1e-30)
             P = X.shape[1]
             P_pad = (P + 127) // 128 * 128     # 16-byte aligned rows: cuBLAS takes its slow path otherwise (4.7x here)
             Xl = torch.empty((X.shape[0], P_pad), dtype=dt, device=X.device)
             Xl[:, P:] = 0
-            for r in range(0, X.shape[0], rows):
-                Xl[r:r + rows, :P] = X[r:r + rows] / scale
+            if dt == torch.bfloat16:
+                scale = torch.ones((), dtype=torch.float32, device=X.device)   # fp32 range: no scaling, one converting copy
+                Xl[:, :P].copy_(X)
+            else:
+                # fp16: scale to O(1) before rounding, undo on the fp32 result; row chunks so that no second fp32 copy
+                # of X exists (56 GB at B = 8192 on the 850 k parameter machine)
+                rows = 1024
+                scale = torch.stack([X[r:r + rows].abs().amax() for r in range(0, X.shape[0], rows)]).amax().clamp_min(1e-30)
+                for r in range(0, X.shape[0], rows):
+                    Xl[r:r + rows, :P] = X[r:r + rows] / scale
             ev[1].record()
-            T = torch.mm(Xl, Xl.T, out_dtype=torch.float32) * (scale * scale)
+            T = self._symmetric_gram(Xl) * (scale * scale)
             del Xl
         ev[2].record()
         T = T / B
@@ -227,6 +240,22 @@ class StochasticReconfiguration(_SRBase):
         delta = X.T @ w
         self._solve_events = ev
         return delta
+
+    @staticmethod
+    def _symmetric_gram(Xl, block=2048):
+        """Xl Xl^T in fp32 from low-precision rows, computing only the block upper triangle (the Gram is symmetric)"""
+        import torch
+        n = Xl.shape[0]
+        if n <= 2 * block:
+            return torch.mm(Xl, Xl.T, out_dtype=torch.float32)
+        T = torch.empty((n, n), dtype=torch.float32, device=Xl.device)
+        for i in range(0, n, block):
+            # one GEMM per block row: columns i.. only
+            blk = torch.mm(Xl[i:i + block], Xl[i:].T, out_dtype=torch.float32)
+            T[i:i + block, i:] = blk
+            if i + block < n:
+                T[i + block:, i:i + block] = blk[:, block:].T
+        return T
 
     def _solve_real(self, stacked, F, B):
         def apply(v):

@@ -162,6 +162,13 @@ int64_t fk_grad_weighted_tc_workspace_bytes(const fk_net_t* net, int64_t B);
 int fk_grad_weighted_tc(fk_net_t* net, const int8_t* sigma, const float* y, int64_t B, float* grad_out,
                         void* ws, int64_t ws_bytes, void* stream);
 
+/* fk_grad_per_sample on the tensor cores (same kernels, one row of the Jacobian per configuration): the input of the
+ * stochastic-reconfiguration contraction (optimizers/stochastic_reconfiguration/optimizer.py:33-124) for machines whose
+ * P x P matrix does not fit; same support envelope as fk_grad_weighted_tc. */
+int64_t fk_grad_per_sample_tc_workspace_bytes(const fk_net_t* net, int64_t B);
+int fk_grad_per_sample_tc(fk_net_t* net, const int8_t* sigma, int64_t B, float* O_re, float* O_im,
+                          void* ws, int64_t ws_bytes, void* stream);
+
 /* ---- stochastic reconfiguration: replaces the S-matrix algebra of
  * optimizers/stochastic_reconfiguration/optimizer.py:55-108.
  * fk_sr_gram: G[M,M] = A^T A (transpose_a=1, A is [K,M]) or A A^T (transpose_a=0, A is [M,K]),
