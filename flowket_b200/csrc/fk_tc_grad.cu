@@ -366,7 +366,48 @@ struct DwArgs2 {
   float out_scale;
 };
 
+// Flush of one tap's (ci, co) accumulator tile: TMEM lane = ci, N columns = co.  Compile-time N keeps the row in registers
+// (a runtime trip count turns v[] into local memory -- measured: 1400 cycles per tap).
+//   shared gradient: atomics;  per-sample row: the tile is contiguous in the row, so it is transposed through shared
+//   memory and written with 512 contiguous bytes per store instruction.
+template <int N>
+__device__ __forceinline__ void dw_flush_tap(uint32_t taddr, float* dst, int cin, int lane, bool per_sample, float out_scale,
+                                             float* stage) {
+  float v[N];
+  if (N == 32) tmem_ld32(taddr, reinterpret_cast<float(&)[32]>(v));
+  else tmem_ld16(taddr, reinterpret_cast<float(&)[16]>(v));
+  if (!per_sample) {
+    if (lane < cin) {
+#pragma unroll
+      for (int co = 0; co < N; ++co) atomicAdd(dst + (long long)lane * N + co, v[co]);
+    }
+  } else if (cin == 32) {
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q)
+      *reinterpret_cast<float4*>(stage + lane * 36 + 4 * q) =
+          make_float4(v[4 * q] * out_scale, v[4 * q + 1] * out_scale, v[4 * q + 2] * out_scale, v[4 * q + 3] * out_scale);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) {
+      const int e = i * 128 + lane * 4;
+      *reinterpret_cast<float4*>(dst + e) = *reinterpret_cast<const float4*>(stage + (e / N) * 36 + (e % N));
+    }
+    __syncwarp();
+  } else if (lane < cin) {   // first block: one input channel
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q)
+      reinterpret_cast<float4*>(dst + (long long)lane * N)[q] =
+          make_float4(v[4 * q] * out_scale, v[4 * q + 1] * out_scale, v[4 * q + 2] * out_scale, v[4 * q + 3] * out_scale);
+  }
+}
+
 constexpr int DW_STAGES = 3;
+#ifdef FK_DW_TRACE
+__device__ long long fk_dw_trace_buf[64 * 8];
+#define DWTRACE(i, k) do { if (blockIdx.x == 0 && (i) < 64 && (threadIdx.x & 31) == 0) fk_dw_trace_buf[(i) * 8 + (k)] = clock64(); } while (0)
+#else
+#define DWTRACE(i, k) do {} while (0)
+#endif
 
 __global__ void __launch_bounds__(128, 1) tc_dw_kernel(DwArgs2 a) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -376,6 +417,7 @@ __global__ void __launch_bounds__(128, 1) tc_dw_kernel(DwArgs2 a) {
   uint8_t* tail = smem + (size_t)DW_STAGES * stage_bytes + 16 * a.npos * 16;   // slack: M rows 32..127 read past the tile
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);      // full[0..2], empty[3..5], done[6]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 64);
+  float* flush_stage = reinterpret_cast<float*>(tail + 128);   // 32 x 36 floats: transpose buffer of the per-sample flush
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[DW_STAGES]), done = smem_u32(&bars[2 * DW_STAGES]);
   if (tid == 32) {
     for (int i = 0; i < DW_STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
@@ -442,71 +484,63 @@ __global__ void __launch_bounds__(128, 1) tc_dw_kernel(DwArgs2 a) {
       const DwUnit u = a.units[item % a.num_units];   // by value: the asm memory clobbers / global stores would force reloads
       const long long c_beg = (long long)(item / a.num_units) * a.cfg_chunk;
       const long long c_end = c_beg + a.cfg_chunk < a.n ? c_beg + a.cfg_chunk : a.n;
+      DWTRACE(item_count, 0);
       mbar_wait(tfree, (uint32_t)((item_count & 1) ^ 1));   // previous item flushed (passes at once for the first item)
       tc_fence_after();
+      DWTRACE(item_count, 1);
       for (long long cfg = c_beg; cfg < c_end; ++cfg) {
         const int st = (int)(cons_count % DW_STAGES);
         mbar_wait(full0 + 8 * st, (full_phase >> st) & 1u); full_phase ^= 1u << st;
         tc_fence_after();
+        DWTRACE(item_count, 2);
         if (elect_one()) {
           const uint32_t sb16 = smem_u32(smem + (size_t)st * stage_bytes) >> 4;
+          const uint32_t first = cfg > c_beg ? 1u : 0u;
           for (int k = 0; k < u.nconv; ++k) {
-            const DwConv& cv = u.conv[k];
-            const uint32_t idesc = make_idesc(cv.n) | (1u << 15) | (1u << 16);   // A and B MN-major
+            // (everything the MMA loop needs in registers: the asm memory clobber would reload it from the local copy)
+            const int ntaps = u.conv[k].ntaps, n = u.conv[k].n, col0 = u.conv[k].col0;
+            const uint32_t idesc = make_idesc(n) | (1u << 15) | (1u << 16);   // A and B MN-major
             const uint32_t x16 = sb16 + (uint32_t)k * (uint32_t)(xt_bytes >> 4);
-            const uint32_t d16 = sb16 + (uint32_t)(3 * (xt_bytes >> 4)) + (uint32_t)k * (DZ_TILE >> 4) + (uint32_t)cv.dz_cg * 128u;
-            for (int t = 0; t < cv.ntaps; ++t) {
-              const uint32_t dcol = tmem + (uint32_t)(cv.col0 + t * cv.n);
+            const uint64_t bd0 = bdesc0 + (uint64_t)(sb16 + (uint32_t)(3 * (xt_bytes >> 4)) + (uint32_t)k * (DZ_TILE >> 4) +
+                                                     (uint32_t)u.conv[k].dz_cg * 128u);
+            for (int t = 0; t < ntaps; ++t) {
+              const uint32_t dcol = tmem + (uint32_t)(col0 + t * n);
+              const uint64_t ad0 = adesc0 + (uint64_t)(x16 + (uint32_t)u.conv[k].off[t]);
+              umma_f16(dcol, ad0, bd0, idesc, first);
 #pragma unroll
-              for (int ks = 0; ks < 8; ++ks) {
-                const uint64_t ad = adesc0 + (uint64_t)(x16 + (uint32_t)(cv.off[t] + 16 * ks));
-                const uint64_t bd = bdesc0 + (uint64_t)(d16 + (uint32_t)(16 * ks));
-                umma_f16(dcol, ad, bd, idesc, (cfg > c_beg || ks > 0) ? 1u : 0u);
-              }
+              for (int ks = 1; ks < 8; ++ks) umma_f16(dcol, ad0 + (uint64_t)(16 * ks), bd0 + (uint64_t)(16 * ks), idesc, 1u);
             }
           }
           umma_commit(empty0 + 8 * st);                 // stage free when its MMAs retire
           if (cfg + 1 == c_end) umma_commit(done);
         }
         __syncwarp();
+        DWTRACE(item_count, 3);
         ++cons_count;
       }
     }
   } else if (warp == 0) {
     // ---- flush: warp 0 owns TMEM lanes 0..31 = input channels
     uint32_t done_phase = 0;
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    long long fitem = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++fitem) {
       const DwUnit u = a.units[item % a.num_units];   // by value: the asm memory clobbers / global stores would force reloads
       const long long c_beg = (long long)(item / a.num_units) * a.cfg_chunk;
       mbar_wait(done, done_phase); done_phase ^= 1;
       tc_fence_after();
+      DWTRACE(fitem, 4);
       for (int k = 0; k < u.nconv; ++k) {
-        const DwConv& cv = u.conv[k];
-        for (int t = 0; t < cv.ntaps; ++t) {
-          float v[32];
-          if (cv.n == 32) {
-            tmem_ld32(tmem + (uint32_t)(cv.col0 + t * 32), v);
-          } else {
-            float h[16];
-            tmem_ld16(tmem + (uint32_t)(cv.col0 + t * 16), h);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = h[i];
-          }
-          if (lane < cv.cin) {
-            float* dst = a.geff + cv.w_off + ((long long)t * cv.cin + lane) * cv.n;
-            if (a.row_stride == 0) {
-              for (int co = 0; co < cv.n; ++co) atomicAdd(dst + co, v[co]);
-            } else {   // (offsets and the row stride are multiples of 4 floats: checked on the host)
-              float4* d4 = reinterpret_cast<float4*>(dst + c_beg * a.row_stride);
-              for (int q = 0; q < cv.n / 4; ++q)
-                d4[q] = make_float4(v[4 * q] * a.out_scale, v[4 * q + 1] * a.out_scale, v[4 * q + 2] * a.out_scale,
-                                    v[4 * q + 3] * a.out_scale);
-            }
-          }
+        const int ntaps = u.conv[k].ntaps, n = u.conv[k].n, col0 = u.conv[k].col0, cin = u.conv[k].cin;
+        const long long w_off = u.conv[k].w_off;
+        for (int t = 0; t < ntaps; ++t) {
+          float* dst = a.geff + c_beg * a.row_stride + w_off + (long long)t * cin * n;   // (c_beg * 0 in the shared mode)
+          if (n == 32) dw_flush_tap<32>(tmem + (uint32_t)(col0 + t * 32), dst, cin, lane, a.row_stride != 0, a.out_scale, flush_stage);
+          else dw_flush_tap<16>(tmem + (uint32_t)(col0 + t * 16), dst, cin, lane, a.row_stride != 0, a.out_scale, flush_stage);
         }
       }
       tc_fence_before();
       __syncwarp();
+      DWTRACE(fitem, 5);
       if (lane == 0) mbar_arrive(tfree);   // the accumulators may be overwritten
     }
   }
@@ -759,7 +793,7 @@ int tc_grad_weighted(fk_net* net, const int8_t* sigma, const float* y, int64_t B
   FK_CHECK_CUDA(cudaGetDevice(&dev));
   FK_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const size_t bwd_smem = 2 * (size_t)IMGB_BYTES + (size_t)BWD_NP * 4 * 64 * npos_g + 256;
-  const size_t dw_smem = (size_t)DW_STAGES * 3 * (64 * g.npos + DZ_TILE) + (size_t)16 * g.npos * 16 + 256;
+  const size_t dw_smem = (size_t)DW_STAGES * 3 * (64 * g.npos + DZ_TILE) + (size_t)16 * g.npos * 16 + 256 + 4608;
   FK_REQUIRE(bwd_smem <= 227 * 1024 && dw_smem <= 227 * 1024, "tensor-core gradient: lattice too large for shared memory");
   FK_CHECK_CUDA(cudaFuncSetAttribute(tc_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem));
   FK_CHECK_CUDA(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem));
@@ -842,7 +876,7 @@ int tc_grad_per_sample(fk_net* net, const int8_t* sigma, int64_t B, float* O_re,
   FK_CHECK_CUDA(cudaGetDevice(&dev));
   FK_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const size_t bwd_smem = 2 * (size_t)IMGB_BYTES + (size_t)BWD_NP * 4 * 64 * npos_g + 256;
-  const size_t dw_smem = (size_t)DW_STAGES * 3 * (64 * g.npos + DZ_TILE) + (size_t)16 * g.npos * 16 + 256;
+  const size_t dw_smem = (size_t)DW_STAGES * 3 * (64 * g.npos + DZ_TILE) + (size_t)16 * g.npos * 16 + 256 + 4608;
   FK_REQUIRE(bwd_smem <= 227 * 1024 && dw_smem <= 227 * 1024, "tensor-core gradient: lattice too large for shared memory");
   FK_CHECK_CUDA(cudaFuncSetAttribute(tc_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem));
   FK_CHECK_CUDA(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem));
@@ -885,3 +919,9 @@ int tc_grad_per_sample(fk_net* net, const int8_t* sigma, int64_t B, float* O_re,
 }
 
 }  // namespace fk
+
+#ifdef FK_DW_TRACE
+extern "C" int fk_dw_trace_read(long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, fk::fk_dw_trace_buf, sizeof(long long) * 64 * 8);
+}
+#endif
