@@ -26,6 +26,16 @@ def _model_of(wave_function):
     return None
 
 
+def _ensemble_of(wave_function):
+    from ...machines.ensemble import EnsembleModel
+    if isinstance(wave_function, EnsembleModel):
+        return wave_function
+    if isinstance(wave_function, functools.partial):
+        return _ensemble_of(wave_function.func)
+    owner = getattr(wave_function, '__self__', None)
+    return owner if isinstance(owner, EnsembleModel) else None
+
+
 class Observable(BaseObservable):
     def __init__(self, operator):
         super(Observable, self).__init__()
@@ -40,6 +50,32 @@ class Observable(BaseObservable):
         sigma = net.to_sigma(configurations)
         eloc, stats, n_conn = net.local_energy(self.operator.device_desc(), sigma, engine=model.engine)
         self.last_stats, self.last_num_connections = stats, n_conn
+        return eloc
+
+    def local_values_device_generic(self, predict_device, configurations, chunk=1 << 18):
+        """Any device wave function (e.g. a symmetrisation ensemble): connections materialised on the device by
+        fk_find_conn, log psi of the used ones through `predict_device`, ratios in complex64 and the segmented sum in
+        complex128 with torch -- same numbers as the host protocol below, nothing leaves the GPU."""
+        import torch
+        conn, mel, use = self.operator.find_conn_device(configurations)       # [C,B,*shape], [C,B], [C,B]
+        C, B = mel.shape
+        shape = tuple(conn.shape[2:])
+        flat = conn.permute(1, 0, *range(2, conn.dim())).reshape((B * C,) + shape)     # sample-major: conn 0 first
+        used = use.t().reshape(-1)
+        idx = torch.nonzero(used, as_tuple=False).reshape(-1)
+        logs = torch.empty(idx.numel(), dtype=torch.complex64, device=flat.device)
+        for i in range(0, idx.numel(), chunk):
+            logs[i:i + chunk] = predict_device(flat[idx[i:i + chunk]]).reshape(-1)
+        counts = use.sum(dim=0)
+        starts = torch.cumsum(counts, 0) - counts
+        sample_of = torch.repeat_interleave(torch.arange(B, device=flat.device), counts)
+        ratios = torch.exp(logs - logs[starts][sample_of])                             # complex64, as the reference
+        weighted = mel.t().reshape(-1)[idx].to(torch.complex128) * ratios.to(torch.complex128)
+        eloc = torch.zeros(B, dtype=torch.complex128, device=flat.device)
+        eloc.index_add_(0, sample_of, weighted)
+        self.last_num_connections = int(idx.numel())
+        self.last_stats = torch.stack([eloc.real.sum(), eloc.imag.sum(), (eloc.real ** 2).sum(),
+                                       torch.tensor(float(B), dtype=torch.float64, device=flat.device)])
         return eloc
 
     # ---- generic route (reference protocol) ------------------------------------------------------------------
@@ -68,6 +104,9 @@ class Observable(BaseObservable):
         model = _model_of(wave_function)
         if model is not None:
             return self.local_values_device(model, configurations).cpu().numpy()
+        ensemble = _ensemble_of(wave_function)
+        if ensemble is not None:
+            return self.local_values_device_generic(ensemble.predict_device, configurations).cpu().numpy()
         local_connections, hamiltonian_values, all_use_conn = self.operator.find_conn(configurations)
         if all_use_conn.mean() < 0.95:
             return self.local_values_optimized_for_unbalanced_local_connections(

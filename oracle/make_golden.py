@@ -117,20 +117,25 @@ if __name__ == '__main__' and len(sys.argv) == 1:
     main()
 
 
+PRETRAINED = {'2': 'ising_2.h5', '2_5': 'ising_2_5.h5', '3': 'ising_3.h5', '3_5': 'ising_3_5.h5', '4': 'ising_4.h5'}
+
+
 def export_pretrained_weights():
-    """tests/golden/ising_12x12_gamma3_keras_weights.npz: the reference's pretrained Keras weights
-    experiments/weights/ising_3.h5 (Ising 12x12 OBC, Gamma = 3, depth 10 / 32 channels, weight-normalised), read with
-    the repository's pure-Python HDF5 reader and stored in Keras layer-creation order.  Published evaluation
-    (experiments/README.md:43-47): E = -457.0420317, variance 0.000821, |Mz| = 0.1622 (symmetrised psi)."""
+    """tests/golden/ising_12x12_gamma<G>_keras_weights.npz: the reference's pretrained Keras weights
+    experiments/weights/ising_<G>.h5 (Ising 12x12 OBC, Gamma = 2, 2.5, 3, 3.5, 4; depth 10 / 32 channels, weight-normalised),
+    read with the repository's pure-Python HDF5 reader and stored in Keras layer-creation order.  Published evaluation
+    (experiments/README.md:38-47, symmetrised psi, 2^15 samples): E = -346.9817926, -395.6618438, -457.0420317,
+    -524.5172088, -593.5389339."""
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from flowket_b200 import Input
     from flowket_b200.machines import ConvNetAutoregressive2D
     from flowket_b200.utils.keras_h5 import read_keras_weights
     m = ConvNetAutoregressive2D(Input(shape=(12, 12)), depth=10, num_of_channels=32)
-    w = read_keras_weights('/root/reference/experiments/weights/ising_3.h5', m.weight_specs())
-    path = os.path.join(OUT, 'ising_12x12_gamma3_keras_weights.npz')
-    np.savez_compressed(path, **{'w%04d' % i: a for i, a in enumerate(w)})
-    print('wrote', path, sum(a.size for a in w), 'parameters')
+    for tag, fname in PRETRAINED.items():
+        w = read_keras_weights('/root/reference/experiments/weights/' + fname, m.weight_specs())
+        path = os.path.join(OUT, 'ising_12x12_gamma%s_keras_weights.npz' % tag)
+        np.savez_compressed(path, **{'w%04d' % i: a for i, a in enumerate(w)})
+        print('wrote', path, sum(a.size for a in w), 'parameters')
 
 
 if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'weights':

@@ -193,3 +193,40 @@ def test_training_lowers_the_energy_towards_exact_diagonalisation():
     assert energies[-1] < energies[0]
     assert all(e > e_ed - 1e-6 for e in energies)             # variational principle
     assert abs(energies[-1] - e_ed) / abs(e_ed) < 5e-4        # ground-state energy of the 4x4 lattice vs ED
+
+
+def test_symmetrised_ensemble_matches_manual_combination_and_is_invariant():
+    """machines/ensemble.py: psi_sym from 16 forwards; E_loc through the device-generic route == host protocol route"""
+    from flowket_b200 import Input
+    from flowket_b200.machines import make_2d_obc_invariants, make_up_down_invariant
+    from flowket_b200.operators import Ising
+    from flowket_b200.observables.monte_carlo import Observable
+    shape = (4, 4)
+    model, _, spec, params = make_pair('conv2d', shape, 3, 8, seed=3)
+    inp = Input(shape=shape)
+    ens = make_up_down_invariant(inp, make_2d_obc_invariants(inp, model))
+    x = random_sigma(20, shape, seed=4)
+    got = ens.predict(x)[:, 0]
+    # manual: inner D4 ensemble for +x and -x, then the outer two-member ensemble (nested exactly like the reference)
+    def comb(vals):
+        vals = np.asarray(vals).T
+        re = 0.5 * np.log(np.exp(2 * vals.real).sum(axis=1)) - 0.5 * np.log(vals.shape[1])
+        return re + 1j * np.angle(np.exp(1j * vals.imag).mean(axis=1))
+    inner = []
+    for s in (1, -1):
+        imgs = [np.rot90(s * x, k, axes=(1, 2)) for k in range(4)]
+        imgs = imgs + [im[:, :, ::-1] for im in imgs]
+        inner.append(comb([nets.log_psi_numpy(spec, params, im.copy())[:, 0] for im in imgs]))
+    want = comb(inner)
+    assert np.allclose(got.real, want.real, atol=2e-4)
+    assert np.allclose(np.exp(1j * got.imag), np.exp(1j * want.imag), atol=2e-4)
+    # invariance under the group
+    for g in (lambda a: np.rot90(a, 1, axes=(1, 2)).copy(), lambda a: a[:, :, ::-1].copy(), lambda a: -a):
+        again = ens.predict(g(x))[:, 0]
+        assert np.allclose(again.real, got.real, atol=1e-4)
+    # local energies: device-generic route vs the reference's host protocol with the same callable
+    obs = Observable(Ising(hilbert_state_shape=list(shape), pbc=False, h=3.0))
+    e_dev = obs.local_values(ens.predict, x)
+    conn, mel, use = obs.operator.find_conn(x)
+    e_host = obs.local_values_optimized_for_balanced_local_connections(ens.predict, conn, mel)
+    assert np.allclose(e_dev, e_host, rtol=1e-4, atol=1e-4)

@@ -166,3 +166,33 @@ def test_lncosh_known_answers():
     for z in [2, 3j, 1 + 7j, 10 - 3j, -6]:
         zt = torch.tensor([z], dtype=torch.complex128)
         assert abs((nets.lncosh(zt) - torch.log(torch.cosh(zt))).item()) < 1e-8
+
+
+def test_ensemble_ops_match_the_reference_formulas():
+    """flowket/machines/ensemble.py:14-25 on a random [n, K] block of complex log-amplitudes"""
+    import torch
+    from flowket_b200.machines.ensemble import probabilistic_ensemble_op, average_ensemble_op
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(7, 8)) * 3 + 1j * rng.uniform(-3.1, 3.1, size=(7, 8))
+    got = probabilistic_ensemble_op(torch.from_numpy(x)).numpy()[:, 0]
+    re = 0.5 * np.log(np.exp(2 * x.real).sum(axis=1)) - 0.5 * np.log(8)
+    im = np.angle(np.exp(1j * x.imag).mean(axis=1))
+    assert np.allclose(got.real, re, atol=1e-12) and np.allclose(got.imag, im, atol=1e-12)
+    got = average_ensemble_op(torch.from_numpy(x)).numpy()[:, 0]
+    want = np.log(np.exp(x).mean(axis=1))
+    assert np.allclose(got.real, want.real, atol=1e-12) and np.allclose(np.exp(1j * got.imag), np.exp(1j * want.imag), atol=1e-12)
+
+
+def test_obc_ensemble_enumerates_the_dihedral_group():
+    import torch
+    from flowket_b200 import Input
+    from flowket_b200.machines.ensemble import make_2d_obc_invariants, make_up_down_invariant, make_pbc_invariants
+    inp = Input(shape=(4, 4))
+    ens = make_2d_obc_invariants(inp, predictions_model=None)
+    x = torch.arange(16, dtype=torch.int8).reshape(1, 4, 4)
+    images = {tuple(t(x).reshape(-1).tolist()) for t in ens.transforms}
+    a = x[0].numpy()
+    want = {tuple(np.rot90(f, k).reshape(-1).tolist()) for k in range(4) for f in (a, a[:, ::-1])}
+    assert len(ens.transforms) == 8 and images == want
+    assert make_up_down_invariant(inp, ens).ensemble_size == 16
+    assert len(make_pbc_invariants(inp, None, apply_also_obc_invariants=False).transforms) == 16

@@ -72,3 +72,20 @@ def test_product_reproduces_published_energy_with_reference_weights(engine):
     assert e > E_GROUND - 0.02                       # variational (up to the MC error bar)
     assert var < 0.05
     assert abs(mz - 0.1622) < 0.03                    # published |Mz| at Gamma = 3
+
+
+@pytest.mark.gpu
+def test_symmetrised_evaluation_reproduces_the_published_table_entry():
+    """experiments/README.md:38-47 (symmetrised psi, samples from the base net): Gamma = 3 -> -457.0420317, |Mz| 0.1622.
+    4096 samples on the tensor-core engine: standard error ~6e-4; all five rows at 2^15 samples are recorded in
+    profiles/r01_pretrained_ising_evaluation.jsonl (examples/evaluate_pretrained_ising.py)."""
+    import importlib.util
+    from flowket_b200 import FK_ENGINE_TC
+    spec = importlib.util.spec_from_file_location('evaluate_pretrained_ising',
+                                                  os.path.join(ROOT, 'examples', 'evaluate_pretrained_ising.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    r = mod.evaluate(3.0, 4096, FK_ENGINE_TC)
+    assert abs(r['energy'] - E_PUBLISHED) < 4e-3, r
+    assert abs(r['abs_mz'] - 0.1622390747) < 0.01, r
+    assert r['variance'] < 4e-3, r
