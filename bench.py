@@ -301,7 +301,10 @@ def run_gpu(args):
         'gpu_launches': int(launches),
         'clocks': clk,
         'roofline': {'bound': 'tensor', 'achieved': achieved_tf, 'peak': pk['bf16_sustained'] or pk['bf16'], 'unit': 'TFLOP/s',
-                     'frac': achieved_tf / (pk['bf16_sustained'] or pk['bf16']), 'traffic': None,
+                     'frac': achieved_tf / (pk['bf16_sustained'] or pk['bf16']),
+                     # dram__bytes_read + dram__bytes_write of one tc_forward_kernel launch (65 536 configurations), ncu capture
+                     # profiles/r01_ncu_tc_forward_v10.txt: the kernel lives in shared memory / TMEM, HBM sees the weights once
+                     'traffic': 8863232 if args.engine == 'tc' else None,
                      'kernel': 'local-energy wave-function evaluations (%s engine)' % args.engine,
                      'peak_source': pk['source'] + ' bf16 sustained (kernel timed inside a long step)',
                      'flops_per_launch': flops_eloc,

@@ -74,7 +74,53 @@ class Trainer(object):
         self.history.append(energy)
         return energy
 
-    def fit(self, steps):
+    def fit(self, steps, checkpoint_path=None, checkpoint_every_seconds=None):
+        """`steps` updates; with a path, a checkpoint every `checkpoint_every_seconds` of wall clock and at the end
+        (CheckpointByTime, callbacks/checkpoint.py:9-73)."""
+        import time
+        last = time.time()
         for _ in range(steps):
             self.train_step()
+            if checkpoint_path and checkpoint_every_seconds is not None and time.time() - last >= checkpoint_every_seconds:
+                self.save_checkpoint(checkpoint_path)
+                last = time.time()
+        if checkpoint_path:
+            self.save_checkpoint(checkpoint_path)
         return self.history
+
+    # ---- checkpoint / resume: weights + optimizer slots + sampler counter (callbacks/checkpoint.py:9-73 pickles the
+    #      optimizer state next to save_weights; here one .npz) ------------------------------------------------------
+    def save_checkpoint(self, path):
+        state = {'params': self.machine.flat_params_device().cpu().numpy(), 'steps': np.int64(len(self.history))}
+        opt = self.optimizer
+        state['opt_t'] = np.int64(getattr(opt, 't', 0))
+        for slot in ('m', 'v'):
+            if getattr(opt, slot, None) is not None:
+                state['opt_' + slot] = getattr(opt, slot).cpu().numpy()
+        sampler = getattr(self.generator, 'sampler', None)
+        if sampler is not None and hasattr(sampler, '_draws'):
+            state['sampler_draws'] = np.int64(sampler._draws)
+            state['sampler_seed'] = np.int64(sampler.seed)
+        tmp = str(path) + '.tmp.npz'
+        np.savez(tmp, **state)
+        import os
+        os.replace(tmp, str(path) if str(path).endswith('.npz') else str(path) + '.npz')
+
+    def load_checkpoint(self, path):
+        import torch
+        with np.load(str(path) if str(path).endswith('.npz') else str(path) + '.npz') as f:
+            params = self.machine.flat_params_device()
+            params.copy_(torch.from_numpy(f['params']).to(params.device))
+            self.machine.params_updated()
+            opt = self.optimizer
+            if hasattr(opt, 't'):
+                opt.t = int(f['opt_t'])
+            for slot in ('m', 'v'):
+                if 'opt_' + slot in f.files:
+                    setattr(opt, slot, torch.from_numpy(f['opt_' + slot]).to(params.device))
+            sampler = getattr(self.generator, 'sampler', None)
+            if sampler is not None and 'sampler_draws' in f.files:
+                sampler._draws = int(f['sampler_draws'])
+                sampler.seed = int(f['sampler_seed'])
+            self.history = [None] * int(f['steps'])
+        return self

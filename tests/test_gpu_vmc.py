@@ -230,3 +230,34 @@ def test_symmetrised_ensemble_matches_manual_combination_and_is_invariant():
     conn, mel, use = obs.operator.find_conn(x)
     e_host = obs.local_values_optimized_for_balanced_local_connections(ens.predict, conn, mel)
     assert np.allclose(e_dev, e_host, rtol=1e-4, atol=1e-4)
+
+
+def test_checkpoint_resume_continues_the_same_trajectory(tmp_path):
+    """Trainer.save_checkpoint / load_checkpoint (weights, Adam slots, sampler counter): 3 + 3 steps == 6 steps up to the
+    summation-order noise of the atomics in the gradient kernels (a lost Adam slot or sampler counter shifts the
+    parameters by ~lr = 1e-2)"""
+    from flowket_b200 import Input, Model
+    from flowket_b200.machines import ConvNetAutoregressive2D
+    from flowket_b200.operators import Heisenberg
+    from flowket_b200.samplers import FastAutoregressiveSampler
+    from flowket_b200.optimization import VariationalMonteCarlo
+    from flowket_b200.optimizers import Adam, Trainer
+
+    def build():
+        inp = Input(shape=(4, 4), dtype='int8')
+        m = ConvNetAutoregressive2D(inp, depth=3, num_of_channels=8, seed=11)
+        model = Model(inp, m.predictions)
+        cond = Model(inp, m.conditional_log_probs)
+        vmc = VariationalMonteCarlo(model, Heisenberg(hilbert_state_shape=[4, 4], pbc=False),
+                                    FastAutoregressiveSampler(cond, 64, seed=5))
+        return m, Trainer(model, vmc, Adam(lr=1e-2, beta_1=0.9, beta_2=0.9))
+
+    m_ref, t_ref = build()
+    t_ref.fit(6)
+    m_a, t_a = build()
+    t_a.fit(3, checkpoint_path=str(tmp_path / 'ckpt'))
+    m_b, t_b = build()
+    t_b.load_checkpoint(str(tmp_path / 'ckpt'))
+    t_b.fit(3)
+    assert (m_b.flat_params_device() - m_ref.flat_params_device()).abs().max().item() < 2e-4
+    assert abs(t_b.history[-1] - t_ref.history[-1]) < 1e-3
