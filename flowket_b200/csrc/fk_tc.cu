@@ -29,7 +29,7 @@ namespace fk {
 constexpr int TC_SLOTS = 4;
 
 struct TcBlockDesc {
-  int8_t in_v, in_h, out_a, out_r, res_v, x1, c, out_h, res_h, last, pad0, pad1;
+  int8_t in_v, in_h, out_a, out_r, res_v, x1, c, out_h, res_h, last, save_h, pad1;
 };
 
 struct TcPackDesc {
@@ -96,7 +96,7 @@ struct TcArgs {
   const int8_t* sigma;
   float* out;
   long long n;
-  int H, W, P, nb, T, npos, p_first, np, tmem_cols, cst_off;
+  int H, W, P, nb, T, npos, p_first, np, tmem_cols, cst_off, slots;
   // activation dump for the tensor-core gradient (T == 1 only): fp16 tiles [cfg][nb*5 + 1][64*npos] in the shared-memory
   // tile layout (tensor order per block: x1, relu(v'), residual v, concat, h_out; last tile = input), relu masks
   // [cfg][nb][5][128] (bit c = channel c active, 0 on padding rows) and logits [cfg][128][4]
@@ -128,8 +128,11 @@ __device__ long long fk_tc_trace_buf[3 * 40 * 16];
 //           image), mma[np] (tcgen05.commit of the pipeline's current phase), ready[np] (128 arrivals: the operand
 //           tiles of the pipeline's next phase are written and fenced).
 constexpr int TC_ISSUERS = 3;   // measured on the 10x10 lattice: 2 -> 2.47, 3 -> 2.59, 4 -> 2.38 M configurations/s
-template <bool DUMP>
-__global__ void __launch_bounds__(TC_MAX_NP * 128 + 32 + TC_ISSUERS * 32, 1) tc_forward_kernel(TcArgs a) {
+// HREG (two-tile lattices, e.g. 12x12): the horizontal stack's residual-pair input -- each epilogue thread's own rows,
+// 32 fp16 per tile -- lives in registers instead of a fourth shared-memory tile, so that two pipelines fit where one
+// did.  MAXNP sizes the launch bound (registers per thread): 3 pipelines -> 128 registers, 2 -> 168.
+template <bool DUMP, bool HREG, int MAXNP>
+__global__ void __launch_bounds__(MAXNP * 128 + 32 + TC_ISSUERS * 32, 1) tc_forward_kernel(TcArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32 + TC_ISSUERS * 32, 1) tc_
   const int buf_bytes = 64 * a.npos;  // 4 channel groups x npos x 16 B
   uint8_t* wbuf = smem;
   uint8_t* act0 = smem + 2 * IMG_BYTES;
-  uint8_t* tail = act0 + (size_t)a.np * TC_SLOTS * buf_bytes;
+  uint8_t* tail = act0 + (size_t)a.np * a.slots * buf_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);           // full[0..1], empty[2..3], mma[4..6], ready[7..9]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 96);
   volatile uint32_t* issued = reinterpret_cast<volatile uint32_t*>(tail + 104);   // [np] phases issued per pipeline
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32 + TC_ISSUERS * 32, 1) tc_
   }
   {  // zero every activation tile once: padding rows / slack positions are never written afterwards
     uint4* z = reinterpret_cast<uint4*>(act0);
-    const int n16 = a.np * TC_SLOTS * buf_bytes / 16;
+    const int n16 = a.np * a.slots * buf_bytes / 16;
     for (int i = tid; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
   }
   fence_proxy_async();
@@ -266,7 +269,7 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32 + TC_ISSUERS * 32, 1) tc_
             }
             mbar_wait(smem_u32(&bars[7 + p]), phase_count & 1u);
             tc_fence_after();
-            const uint32_t row00 = act16 + (uint32_t)(p * TC_SLOTS) * buf16 + (uint32_t)a.p_first;
+            const uint32_t row00 = act16 + (uint32_t)(p * a.slots) * buf16 + (uint32_t)a.p_first;
             const bool leader = elect_one();
             for (int t = 0; t < a.T; ++t) {
               const uint32_t dt = tmem_base + (uint32_t)((p * a.T + t) * 128);
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32 + TC_ISSUERS * 32, 1) tc_
     // =============================== epilogue pipelines ===============================
     const uint32_t tm_pipe = tmem_base + (uint32_t)(pipe * a.T * 128);
     const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
-    uint8_t* act = act0 + (size_t)pipe * TC_SLOTS * buf_bytes;
+    uint8_t* act = act0 + (size_t)pipe * a.slots * buf_bytes;
     const uint32_t act16 = smem_u32(act) >> 4;      // everything below is in 16-byte units
     const uint32_t buf16 = 4u * (uint32_t)a.npos;
     const uint32_t kstep16 = 2u * (uint32_t)a.npos;  // two channel groups per k-step
@@ -332,6 +335,13 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32 + TC_ISSUERS * 32, 1) tc_
       const int r = pos[t] / a.P - 2, c = pos[t] % a.P - 2;
       site[t] = (t < a.T && c >= 0 && r < a.H) ? r * a.W + c : -1;
     }
+
+    constexpr int HT = HREG ? 2 : 1;
+    uint32_t hres[HT][16];   // HREG: packed fp16 rows (one per tile) of the horizontal residual-pair input
+#pragma unroll
+    for (int t = 0; t < HT; ++t)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) hres[t][i] = 0u;
 
     auto store_row = [&](int slot, int p, const float* v) {
       uint8_t* base = act + (size_t)slot * buf_bytes + (size_t)p * 16;
@@ -500,7 +510,16 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32 + TC_ISSUERS * 32, 1) tc_
           if (site[t] >= 0) {
             if (d.res_h >= 0) {
               float r[32];
-              load_row(d.res_h, pos[t], r);
+              if (HREG) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hres[t < HT ? t : 0][i]));
+                  r[2 * i] = f.x;
+                  r[2 * i + 1] = f.y;
+                }
+              } else {
+                load_row(d.res_h, pos[t], r);
+              }
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] += r[i];
             }
@@ -511,6 +530,10 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32 + TC_ISSUERS * 32, 1) tc_
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
           }
           store_row(d.out_h, pos[t], v);
+          if (HREG && d.save_h && t < HT) {   // this block's output is the next pair's input: keep the stored fp16 values
+#pragma unroll
+            for (int i = 0; i < 16; ++i) hres[t < HT ? t : 0][i] = pack_h2(v[2 * i], v[2 * i + 1]);
+          }
           if (DUMP && active && t == 0) dump_row(cfg, b, 4, v, site[t] >= 0);
         }
         fence_proxy_async();
@@ -578,7 +601,8 @@ __global__ void __launch_bounds__(TC_MAX_NP * 128 + 32 + TC_ISSUERS * 32, 1) tc_
 
 // ---- host side ---------------------------------------------------------------------------------------------------
 struct TcGeometry {
-  int P, p_first, T, npos, np, tmem_cols;
+  int P, p_first, T, npos, np, tmem_cols, slots;
+  bool hreg;
   size_t smem_bytes;
   bool ok;
 };
@@ -592,15 +616,24 @@ static TcGeometry tc_geometry(const fk_net* net) {
   g.npos = ((g.p_first + g.T * 128 + 2) + 7) / 8 * 8;
   const size_t buf = (size_t)64 * g.npos;
   const size_t tail = (384 + sizeof(TcBlockDesc) * (size_t)(2 * net->depth - 2) + 64 + 127) / 128 * 128;
-  g.np = TC_MAX_NP;
   g.ok = g.T <= TC_MAX_T;
-  for (;;) {
-    g.smem_bytes = 2 * (size_t)IMG_BYTES + (size_t)g.np * TC_SLOTS * buf + tail + 4096;   // + ones / zero tiles
-    const int cols = g.np * g.T * 128;
-    if (g.smem_bytes <= 227 * 1024 && cols <= 512) break;
-    if (g.np == 1) { g.ok = false; break; }
-    g.np -= 1;
-  }
+  auto fit = [&](int slots, size_t* smem_out) {   // pipelines that fit with `slots` activation tiles each
+    for (int np = TC_MAX_NP; np >= 1; --np) {
+      const size_t smem = 2 * (size_t)IMG_BYTES + (size_t)np * slots * buf + tail + 4096;   // + ones / zero tiles
+      if (smem <= 227 * 1024 && np * g.T * 128 <= 512) { *smem_out = smem; return np; }
+    }
+    *smem_out = 0;
+    return 0;
+  };
+  size_t smem4 = 0, smem3 = 0;
+  const int np4 = fit(TC_SLOTS, &smem4);
+  const int np3 = g.T == 2 ? std::min(2, fit(TC_SLOTS - 1, &smem3)) : 0;   // register residual: two-tile lattices only
+  g.hreg = np3 > np4;
+  g.slots = g.hreg ? TC_SLOTS - 1 : TC_SLOTS;
+  g.np = g.hreg ? np3 : np4;
+  if (g.hreg) smem3 = 2 * (size_t)IMG_BYTES + (size_t)g.np * g.slots * buf + tail + 4096;
+  g.smem_bytes = g.hreg ? smem3 : smem4;
+  if (g.np == 0) { g.ok = false; g.np = 1; }
   int cols = g.np * g.T * 128;
   g.tmem_cols = cols <= 128 ? 128 : (cols <= 256 ? 256 : 512);
   return g;
@@ -627,9 +660,12 @@ int tc_pack_weights(fk_net* net, cudaStream_t s) {
     // In-place rules (safe because an epilogue thread only touches its own position and every MMA of the
     // phase has retired before the epilogue starts): x1 may overwrite h, relu(v') may overwrite v, the concat
     // tensor overwrites x1, h' overwrites the concat tensor (or the pair input when it carries the residual).
+    // With g.hreg the horizontal pair input is kept in registers by the epilogue threads (res_h is then only a flag
+    // and save_h marks the blocks whose output is a pair input), which frees one tile.
+    const TcGeometry g = tc_geometry(net);
     int rc[TC_SLOTS] = {0, 0, 0, 0};
     auto get = [&]() {
-      for (int i = 0; i < TC_SLOTS; ++i)
+      for (int i = 0; i < g.slots; ++i)
         if (rc[i] == 0) { rc[i] = 1; return i; }
       return -1;
     };
@@ -639,9 +675,13 @@ int tc_pack_weights(fk_net* net, cudaStream_t s) {
     for (int b = 0; b < nb; ++b) {
       const bool last = (b == nb - 1);
       const bool res2 = (b >= 2 && b % 2 == 0 && !last);
-      if (b % 2 == 1 && !last) { v_pair = v; h_pair = h; rc[v]++; rc[h]++; }
+      if (b % 2 == 1 && !last) {
+        v_pair = v; rc[v]++;
+        if (!g.hreg) { h_pair = h; rc[h]++; }
+      }
       TcBlockDesc d;
-      d.in_v = (int8_t)v; d.in_h = (int8_t)h; d.last = last ? 1 : 0; d.pad0 = d.pad1 = 0;
+      d.in_v = (int8_t)v; d.in_h = (int8_t)h; d.last = last ? 1 : 0; d.pad1 = 0;
+      d.save_h = (int8_t)((g.hreg && (b + 1) % 2 == 1 && b + 1 != nb - 1) ? 1 : 0);   // block b+1 pins its input
       int x1;
       if (rc[h] == 1) { x1 = h; } else { x1 = get(); rc[h]--; }
       int a1;
@@ -653,7 +693,8 @@ int tc_pack_weights(fk_net* net, cudaStream_t s) {
       d.res_h = -1;
       if (res2) {
         rc[a1]--; v_next = v_pair;            // relu(v') only feeds the 1x1 conv; the residual sum replaces the pair input
-        rc[c]--; hn = h_pair; d.res_h = (int8_t)h_pair;
+        if (g.hreg) { d.res_h = 0; }
+        else { rc[c]--; hn = h_pair; d.res_h = (int8_t)h_pair; }
       }
       d.x1 = (int8_t)x1; d.out_a = (int8_t)a1; d.c = (int8_t)c; d.out_h = (int8_t)hn;
       desc[b] = d;
@@ -707,7 +748,7 @@ int tc_forward_launch(fk_net* net, const int8_t* sigma, int64_t n, float* log_ps
   a.desc = reinterpret_cast<const TcBlockDesc*>((const uint8_t*)net->d_tc_weights + tc_desc_offset(nb));
   a.sigma = sigma; a.out = log_psi_out; a.n = n;
   a.H = net->H; a.W = net->W; a.P = g.P; a.nb = nb; a.T = g.T; a.npos = g.npos; a.p_first = g.p_first; a.np = g.np;
-  a.tmem_cols = g.tmem_cols; a.cst_off = (int)(g.smem_bytes - 4096);
+  a.tmem_cols = g.tmem_cols; a.cst_off = (int)(g.smem_bytes - 4096); a.slots = g.slots;
   a.dump = dump; a.dump_mask = dump_mask; a.dump_logits = dump_logits;
   FK_REQUIRE(dump == nullptr || g.T == 1, "tensor-core gradient: lattice needs more than one M tile");
   int dev = 0, sms = 148;
@@ -715,13 +756,17 @@ int tc_forward_launch(fk_net* net, const int8_t* sigma, int64_t n, float* log_ps
   FK_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long groups = (n + g.np - 1) / g.np;
   const unsigned grid = (unsigned)std::min<long long>(groups, sms);
-  if (dump) {
-    FK_CHECK_CUDA(cudaFuncSetAttribute(tc_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-    tc_forward_kernel<true><<<grid, 128 * g.np + 32 + 32 * TC_ISSUERS, g.smem_bytes, s>>>(a);
-  } else {
-    FK_CHECK_CUDA(cudaFuncSetAttribute(tc_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-    tc_forward_kernel<false><<<grid, 128 * g.np + 32 + 32 * TC_ISSUERS, g.smem_bytes, s>>>(a);
-  }
+  const unsigned threads = 128 * g.np + 32 + 32 * TC_ISSUERS;
+  auto launch = [&](auto kernel) -> int {
+    FK_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    kernel<<<grid, threads, g.smem_bytes, s>>>(a);
+    return 0;
+  };
+  int rc;
+  if (dump) rc = launch(tc_forward_kernel<true, false, TC_MAX_NP>);            // (the gradient dump exists for T == 1 only)
+  else if (g.hreg) rc = launch(tc_forward_kernel<false, true, 2>);
+  else rc = launch(tc_forward_kernel<false, false, TC_MAX_NP>);
+  if (rc) return rc;
   FK_CHECK_LAUNCH();
   return 0;
 }

@@ -12,7 +12,9 @@ pytestmark = pytest.mark.gpu
 # |log psi_tc - log psi_fp64| <= TOL_ABS + TOL_REL * |log psi|   (bf16 rounding of activations and weights)
 TOL_ABS, TOL_REL = 0.05, 2e-3
 
-CASES = [((4, 4), 3), ((6, 6), 4), ((10, 10), 5), ((10, 10), 20), ((12, 12), 3), ((16, 16), 2), ((5, 7), 2)]
+# (12, 12): two M tiles, register-resident residual input (two pipelines); (16, 16): three tiles, one pipeline
+CASES = [((4, 4), 3), ((6, 6), 4), ((10, 10), 5), ((10, 10), 20), ((12, 12), 3), ((12, 12), 10), ((16, 16), 2), ((5, 7), 2),
+         ((11, 12), 4)]
 
 
 @pytest.mark.parametrize('shape,depth', CASES)
