@@ -77,7 +77,7 @@ def main():
     inp = Input(shape=(20,))
     m = SimpleConvNetAutoregressive1D(inp, depth=8, num_of_channels=64, max_dilation_rate=4, weights_normalization=False, seed=0)
     r = vmc_phases(m, inp, Heisenberg(hilbert_state_shape=[20], pbc=True), 1024, FK_ENGINE_FP32)
-    r['config'] = 'cfg2: Heisenberg 1-D 20 PBC, SimpleConvNetAutoregressive1D d8 c64, batch 1024 (fp32 engine; N-forward sampler)'
+    r['config'] = 'cfg2: Heisenberg 1-D 20 PBC, SimpleConvNetAutoregressive1D d8 c64, batch 1024 (fp32 engine; incremental 1-D sampler)'
     out.append(r)
     # cfg 4: J1J2 6x6 OBC j2=0.5, complex 1-D machine over the raster-flattened lattice + complex SR
     inp = Input(shape=(36,))

@@ -413,6 +413,156 @@ static bool fast_sampler_supported(const fk_net* net) {
   return net->kind == FK_NET_CONV2D && net->C == SC && net->k == 3;
 }
 
+// ================================================================================================================
+// Incremental sampler for the 1-D machines (SimpleConvNetAutoregressive1D, ComplexValuesSimpleConvNetAutoregressive1D):
+// FastAutoregressiveSampler's activation reuse (deepar/samplers/fast_autoregressive.py:13-76 + the dependency graph
+// it builds) for causal, dilated 1-D stacks.  Every op of the layer program is causal along the chain (taps dw <= 0)
+// and the head looks one site back (DownShift), so site i needs:  head at position i (reads cached features of
+// position i-1) -> draw sigma_i -> every body op at position i (reads cached positions <= i).  Each (layer, position)
+// activation is computed exactly once; a CTA owns S samples for all sites and layers (no grid-wide synchronisation),
+// its caches (all buffers, all positions) are CTA-private global memory that stays in L2.
+// Arithmetic follows conv_kernel: fmaf over k = (tap, ci) in increasing order from 0, + bias, (pre), + residual, act.
+// ================================================================================================================
+struct Op1D {
+  int in_off, in_cs, cin;
+  int out_off, out_cs, out_coff, cout;
+  int res_off, res_cs;       // res_off < 0: no residual
+  int pre_off;               // lncosh ops: buffer of the pre-activation (channels = cout)
+  int act, ntaps;
+  int dw[MAX_TAPS];
+  long long w_off, b_off;
+};
+
+struct Sample1DArgs {
+  const float* weff;
+  const Op1D* ops;
+  int nops, N, in_off, in_cs, xs_floats;
+  float* cache;
+  long long cache_floats_per_cta;
+  const double* uniforms;
+  uint64_t seed;
+  long long sample_offset, B;
+  int8_t* sigma_out;
+  float* p0_out;
+};
+
+__device__ __forceinline__ float s1d_lse2(float a, float b) {
+  const float m = fmaxf(a, b);
+  return m + logf(expf(a - m) + expf(b - m));
+}
+__device__ __forceinline__ void s1d_lncosh(float x, float y, float& ore, float& oim) {   // == lncosh_c of fk_kernels.cu
+  const float ax = fabsf(x);
+  float s1, c1;
+  sincosf(y, &s1, &c1);
+  const float e1 = expf(x - ax), e2 = expf(-x - ax);
+  const float sr = (e1 + e2) * c1;
+  const float si = (e1 - e2) * s1;
+  ore = ax - 0.69314718055994530942f + logf(hypotf(sr, si));
+  oim = atan2f(si, sr);
+}
+
+template <int S>
+__global__ void __launch_bounds__(256) sample1d_kernel(Sample1DArgs a) {
+  extern __shared__ __align__(16) float xs[];   // [S][max taps x channels] | weights of the current op [K][cout]
+  float* wsm = xs + a.xs_floats;
+  float* cache = a.cache + (long long)blockIdx.x * a.cache_floats_per_cta;
+  const long long b0 = (long long)blockIdx.x * S;
+  const int tid = threadIdx.x, N = a.N;
+  // one op at one position for the S samples of this CTA; buffer layout [sample][position][channel]
+  auto eval = [&](const Op1D& op, int i) {
+    const float* w = a.weff + op.w_off;
+    const float* bias = a.weff + op.b_off;
+    const bool lncosh = op.act == ACT_LNCOSH;
+    // gather the S input vectors (taps x channels, zero padded) into shared memory, then one fmaf chain per output
+    const int K = op.ntaps * op.cin;
+    for (int e = tid; e < S * K; e += blockDim.x) {
+      const int sm = e / K, k = e - sm * K;
+      const int t = k / op.cin, ci = k - t * op.cin;
+      const int pos = i + op.dw[t];
+      xs[e] = (pos >= 0 && pos < N) ? cache[op.in_off + ((long long)sm * N + pos) * op.in_cs + ci] : 0.f;
+    }
+    // ... and the layer's weights [K][cout] (one coalesced pass; reading them inside the fmaf chain is latency-bound)
+    {
+      const int nw = K * op.cout;
+      if (((op.w_off | nw) & 3) == 0) {
+        const float4* w4 = reinterpret_cast<const float4*>(w);
+        float4* d4 = reinterpret_cast<float4*>(wsm);
+        for (int e = tid; e < nw / 4; e += blockDim.x) d4[e] = __ldg(w4 + e);
+      } else {
+        for (int e = tid; e < nw; e += blockDim.x) wsm[e] = __ldg(w + e);
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < S * op.cout; idx += blockDim.x) {
+      const int sm = idx / op.cout, co = idx - sm * op.cout;
+      const float* x = xs + sm * K;
+      const float* wt = wsm + co;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < K; ++k) acc = fmaf(x[k], wt[k * op.cout], acc);
+      float z = acc + __ldg(bias + co);
+      if (lncosh) {
+        cache[op.pre_off + ((long long)sm * N + i) * op.cout + co] = z;
+      } else {
+        if (op.res_off >= 0) z += cache[op.res_off + ((long long)sm * N + i) * op.res_cs + co];
+        if (op.act == ACT_RELU) z = fmaxf(z, 0.f);
+        cache[op.out_off + ((long long)sm * N + i) * op.out_cs + op.out_coff + co] = z;
+      }
+    }
+    if (lncosh) {   // complex pairs (c, c + half) of the pre-activation
+      __syncthreads();
+      const int half = op.cout / 2;
+      for (int idx = tid; idx < S * half; idx += blockDim.x) {
+        const int sm = idx / half, c = idx - sm * half;
+        const float* pre = cache + op.pre_off + ((long long)sm * N + i) * op.cout;
+        float ore, oim;
+        s1d_lncosh(pre[c], pre[half + c], ore, oim);
+        float* out = cache + op.out_off + ((long long)sm * N + i) * op.out_cs + op.out_coff;
+        out[c] = ore;
+        out[half + c] = oim;
+      }
+    }
+    __syncthreads();
+  };
+  const Op1D head = a.ops[a.nops - 1];
+  for (int i = 0; i < N; ++i) {
+    eval(head, i);
+    if (tid < S) {
+      const long long b = b0 + tid;
+      float sg = 0.f;
+      if (b < a.B) {
+        const float* l = cache + head.out_off + ((long long)tid * N + i) * head.out_cs;
+        const float half_lse = 0.5f * s1d_lse2(2.f * l[0], 2.f * l[1]);
+        const float p0 = expf(2.f * (l[0] - half_lse));
+        const double u = a.uniforms ? a.uniforms[b * N + i] : philox_uniform(a.seed, (uint64_t)(a.sample_offset + b), (uint32_t)i);
+        sg = ((double)p0 > u) ? 1.f : -1.f;
+        a.sigma_out[b * N + i] = (int8_t)sg;
+        if (a.p0_out) a.p0_out[b * N + i] = p0;
+      }
+      float* x = cache + a.in_off + ((long long)tid * N + i) * a.in_cs;
+      x[0] = sg;
+      for (int c = 1; c < a.in_cs; ++c) x[c] = 0.f;
+    }
+    __syncthreads();
+    for (int o = 0; o + 1 < a.nops; ++o) eval(a.ops[o], i);
+  }
+}
+
+constexpr int S1D = 8;
+
+static bool sampler1d_supported(const fk_net* net) {
+  if (net->kind == FK_NET_CONV2D || net->H != 1 || net->ops.size() < 2) return false;
+  for (size_t o = 0; o < net->ops.size(); ++o) {
+    const ConvOp& op = net->ops[o];
+    const bool head = o + 1 == net->ops.size();
+    if (op.out2_buf >= 0) return false;
+    if (head && (op.out_buf != net->logits_buf || op.act != ACT_NONE)) return false;
+    for (int t = 0; t < op.ntaps; ++t)
+      if (op.dh[t] != 0 || op.dw[t] > (head ? -1 : 0)) return false;   // causal body, head strictly in the past
+  }
+  return true;
+}
+
 static int pick_tile(int64_t B) {
   // enough CTAs to cover the 148 SMs, then the largest tile (weight re-use)
   if (B >= 148 * 64) return 64;
@@ -432,6 +582,10 @@ extern "C" int64_t fk_sample_workspace_bytes(const fk_net_t* net, int64_t B) {
     const int64_t ctas = (B + S - 1) / S;
     const int nb = 2 * net->depth - 2;
     return ctas * cache_floats_per_cta(S, net->W, nb) * 4 + sizeof(BlockW) * nb + 256;
+  }
+  if (sampler1d_supported(net)) {
+    const int64_t ctas = (B + S1D - 1) / S1D;
+    return ctas * net->train_floats_per_cfg * S1D * 4 + (int64_t)sizeof(Op1D) * (int64_t)net->ops.size() + 512;
   }
   return fk_sample_naive_workspace_bytes(net, B);
 }
@@ -470,6 +624,50 @@ extern "C" int fk_sample(fk_net_t* net, const double* uniforms, uint64_t seed, i
   FK_REQUIRE(net && sigma_out && ws, "fk_sample: NULL argument");
   FK_REQUIRE(net->params_set, "machine parameters were never set (fk_net_set_params)");
   if (B == 0) return 0;
+  if (!fast_sampler_supported(net) && sampler1d_supported(net)) {
+    cudaStream_t s1 = (cudaStream_t)stream;
+    const int64_t need1 = fk_sample_workspace_bytes(net, B);
+    FK_REQUIRE(ws_bytes >= need1, "fk_sample: workspace too small (%lld < %lld bytes)", (long long)ws_bytes, (long long)need1);
+    // buffer offsets inside a CTA's cache: every virtual buffer, [S][N][channels]
+    std::vector<long long> boff(net->bufs.size());
+    long long off = 0;
+    for (size_t v = 0; v < net->bufs.size(); ++v) { boff[v] = off; off += (long long)S1D * net->sites * net->bufs[v].channels; }
+    std::vector<Op1D> tab(net->ops.size());
+    for (size_t o = 0; o < net->ops.size(); ++o) {
+      const ConvOp& op = net->ops[o];
+      Op1D& t = tab[o];
+      t.in_off = (int)boff[op.in_buf]; t.in_cs = net->bufs[op.in_buf].channels; t.cin = op.cin;
+      t.out_off = (int)boff[op.out_buf]; t.out_cs = net->bufs[op.out_buf].channels; t.out_coff = op.out_coff; t.cout = op.cout;
+      t.res_off = op.res_buf >= 0 ? (int)boff[op.res_buf] : -1; t.res_cs = op.res_buf >= 0 ? net->bufs[op.res_buf].channels : 0;
+      t.pre_off = op.pre_buf >= 0 ? (int)boff[op.pre_buf] : -1;
+      FK_REQUIRE(op.act != ACT_LNCOSH || op.pre_buf >= 0, "lncosh op without a pre-activation buffer");
+      t.act = op.act; t.ntaps = op.ntaps;
+      for (int k = 0; k < op.ntaps; ++k) t.dw[k] = op.dw[k];
+      t.w_off = op.w_off; t.b_off = op.b_off;
+    }
+    Op1D* d_tab = (Op1D*)ws;
+    FK_CHECK_CUDA(cudaMemcpyAsync(d_tab, tab.data(), sizeof(Op1D) * tab.size(), cudaMemcpyHostToDevice, s1));
+    FK_CHECK_CUDA(cudaStreamSynchronize(s1));  // `tab` is a stack-lifetime host buffer
+    Sample1DArgs a;
+    a.weff = net->d_weff; a.ops = d_tab; a.nops = (int)tab.size(); a.N = net->sites;
+    a.in_off = (int)boff[net->in_buf]; a.in_cs = net->bufs[net->in_buf].channels;
+    a.cache = (float*)((char*)ws + (sizeof(Op1D) * tab.size() + 255) / 256 * 256);
+    a.cache_floats_per_cta = off;
+    a.uniforms = uniforms; a.seed = seed; a.sample_offset = sample_offset; a.B = B;
+    a.sigma_out = sigma_out; a.p0_out = p0_out;
+    int max_k = 1, max_w = 1;
+    for (const ConvOp& op : net->ops) {
+      max_k = std::max(max_k, op.ntaps * op.cin);
+      max_w = std::max(max_w, op.ntaps * op.cin * op.cout);
+    }
+    a.xs_floats = (S1D * max_k + 3) / 4 * 4;
+    const size_t smem_bytes = sizeof(float) * ((size_t)a.xs_floats + (size_t)max_w);
+    FK_REQUIRE(smem_bytes <= 200 * 1024, "1-D sampler: layer too wide for the shared-memory staging buffers");
+    FK_CHECK_CUDA(cudaFuncSetAttribute(sample1d_kernel<S1D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    sample1d_kernel<S1D><<<(unsigned)((B + S1D - 1) / S1D), 256, smem_bytes, s1>>>(a);
+    FK_CHECK_LAUNCH();
+    return 0;
+  }
   if (!fast_sampler_supported(net))
     return fk_sample_naive(net, uniforms, seed, sample_offset, B, sigma_out, p0_out, ws, ws_bytes, stream);
   cudaStream_t s = (cudaStream_t)stream;

@@ -109,7 +109,9 @@ int fk_cond_log_probs(fk_net_t* net, const int8_t* sigma, int64_t n, float* out,
  * with the explicit-uniform rule of AutoregressiveSampler (deepar/samplers/autoregressive.py:37-44):
  * sigma = +1 iff (double)expf(log p(class 0)) > u.  `uniforms` [B, sites] float64 or NULL; when NULL
  * u is Philox4x32-10(seed; counter = (sample_offset + b, site)) so results do not depend on the
- * number of GPUs.  p0_out (optional) receives p(class 0) per site. */
+ * number of GPUs.  p0_out (optional) receives p(class 0) per site.
+ * Cached incremental schedule (every (layer, site) activation computed once) for ConvNetAutoregressive2D (C = 32, k = 3)
+ * and for the causal 1-D machines (real dilated / skip, complex lncosh); other shapes use the N-forward schedule. */
 int64_t fk_sample_workspace_bytes(const fk_net_t* net, int64_t B);
 int fk_sample(fk_net_t* net, const double* uniforms, uint64_t seed, int64_t sample_offset, int64_t B,
               int8_t* sigma_out, float* p0_out, void* ws, int64_t ws_bytes, void* stream);

@@ -192,6 +192,36 @@ def test_sampler_1d_and_complex_given_uniforms():
         assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize('kind,shape,depth,ch,kw', [
+    ('conv1d', (20,), 8, 64, {'max_dilation_rate': 4, 'weights_normalization': False}),     # BASELINE configs[1]
+    ('conv1d', (16,), 7, 32, {}),
+    ('cconv1d', (36,), 5, 16, {}),                                                          # configs[3]: 6x6 flattened
+])
+def test_incremental_1d_sampler_equals_the_n_forward_sampler(kind, shape, depth, ch, kw):
+    """fk_sample on the 1-D machines is the cached incremental kernel (one evaluation per (layer, position));
+    AutoregressiveSampler is the N-forward schedule (autoregressive.py:29-48).  Same uniforms -> same spins and the
+    same conditional probabilities (both follow conv_kernel's summation order for these shapes up to fp32 noise)."""
+    from flowket_b200.samplers import FastAutoregressiveSampler, AutoregressiveSampler
+    model, cond_model, spec, params = make_pair(kind, shape, depth, ch, seed=4, **kw)
+    B = 77
+    u = np.random.RandomState(3).random_sample((B,) + shape)
+    fast = FastAutoregressiveSampler(cond_model, B)
+    got = fast.next_device(uniforms=u, return_p0=True).cpu().numpy()
+    p0_fast = fast.last_p0.cpu().numpy().reshape((B,) + shape)
+    naive = AutoregressiveSampler(cond_model, B)
+    ref = naive.next_device(uniforms=u, return_p0=True).cpu().numpy()
+    p0_naive = naive.last_p0.cpu().numpy().reshape((B,) + shape)
+    bad = np.argwhere(got != ref)
+    for idx in bad:   # a differing site must be a numerical tie at its first occurrence in the sample
+        first = tuple(bad[bad[:, 0] == idx[0]][0])
+        assert abs(p0_naive[first] - u[first]) < 1e-5, (first, p0_naive[first], u[first])
+    same = (got == ref).all(axis=1)
+    assert same.mean() > 0.95
+    assert np.abs(p0_fast[same] - p0_naive[same]).max() < 5e-6
+    want, _ = osampler.sample_with_uniforms(spec, params, u)
+    assert (got == want).all(axis=1).mean() > 0.95
+
+
 def test_sampler_philox_is_shard_invariant_and_distribution():
     """Philox counters are keyed by the global sample index: two half-batches == one full batch; and the
     histogram of the samples matches |psi|^2 (L1 test of tests/test_samplers.py:49-82, z <= sqrt(n))."""
