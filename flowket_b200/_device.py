@@ -167,17 +167,24 @@ class DeviceNet(object):
         return O_re, O_im
 
 
-def sr_gram(A, transpose_a):
-    """G = A^T A (transpose_a) or A A^T, fp32, on the device through fk_sr_gram."""
+def sr_gram(A, transpose_a, engine=_lib.FK_ENGINE_FP32, precise=True):
+    """G = A^T A (transpose_a) or A A^T on the device: fp32 CUDA-core kernel (fk_sr_gram) or the tcgen05 GEMM
+    (fk_sr_gram_tc; fp16 hi/lo operands when `precise`, fp32 accumulation)."""
     import torch
     lib = _lib.require_cuda()
     A = A.contiguous()
     rows, cols = A.shape
     M = cols if transpose_a else rows
     G = torch.empty((M, M), dtype=torch.float32, device=A.device)
-    nbytes = lib.fk_sr_gram_workspace_bytes(rows, cols, int(transpose_a))
-    ws = torch.empty(int(nbytes), dtype=torch.uint8, device=A.device)
     with torch.cuda.device(A.device):
-        _lib.check(lib.fk_sr_gram(_ptr(A), rows, cols, int(transpose_a), _ptr(G), _ptr(ws), ws.numel(),
-                                  _lib.stream_ptr()))
+        if engine == _lib.FK_ENGINE_TC:
+            nbytes = lib.fk_sr_gram_tc_workspace_bytes(rows, cols, int(transpose_a), int(bool(precise)))
+            ws = torch.empty(int(nbytes), dtype=torch.uint8, device=A.device)
+            _lib.check(lib.fk_sr_gram_tc(_ptr(A), rows, cols, int(transpose_a), int(bool(precise)), _ptr(G), _ptr(ws),
+                                         ws.numel(), _lib.stream_ptr()))
+        else:
+            nbytes = lib.fk_sr_gram_workspace_bytes(rows, cols, int(transpose_a))
+            ws = torch.empty(int(nbytes), dtype=torch.uint8, device=A.device)
+            _lib.check(lib.fk_sr_gram(_ptr(A), rows, cols, int(transpose_a), _ptr(G), _ptr(ws), ws.numel(),
+                                      _lib.stream_ptr()))
     return G

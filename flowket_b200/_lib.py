@@ -63,6 +63,8 @@ SIGNATURES = {
     'fk_grad_per_sample_tc': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     'fk_sr_gram_workspace_bytes': (c_int64, [c_int64, c_int64, c_int]),
     'fk_sr_gram': (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
+    'fk_sr_gram_tc_workspace_bytes': (c_int64, [c_int64, c_int64, c_int, c_int]),
+    'fk_sr_gram_tc': (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
 }
 
 

@@ -45,6 +45,11 @@ class _SRBase(object):
         self.conjugate_gradient_iterations = 0
         self.conjugate_gradient_residual_norm = 0.0
 
+    def _gram_engine(self):
+        """tcgen05 Gram (fp16 hi/lo operands, fp32 accumulation) when the model runs the tensor-core engine"""
+        from .. import _lib
+        return getattr(self.model, 'engine', _lib.FK_ENGINE_FP32)
+
     def jacobian(self, sigma):
         net = self.machine.device_net()
         return net.grad_per_sample(net.to_sigma(sigma), imag=True)
@@ -63,11 +68,11 @@ class _SRBase(object):
         if O_bar.is_complex():
             # Obar^H Obar = (R^T R + I^T I) + i (R^T I - I^T R): one real Gram of the stacked matrix [R | I]
             R, I = O_bar.real.contiguous().float(), O_bar.imag.contiguous().float()
-            G = sr_gram(torch.cat([R, I], dim=1), transpose_a=True)      # [2P, 2P]
+            G = sr_gram(torch.cat([R, I], dim=1), transpose_a=True, engine=self._gram_engine())      # [2P, 2P]
             P = R.shape[1]
             S = torch.complex(G[:P, :P] + G[P:, P:], G[:P, P:] - G[P:, :P]) / B
         else:
-            S = sr_gram(O_bar.float(), transpose_a=True) / B
+            S = sr_gram(O_bar.float(), transpose_a=True, engine=self._gram_engine()) / B
         S = S + self.diag_shift * torch.eye(S.shape[0], dtype=S.dtype, device=S.device)
         if self.use_cholesky:
             L = torch.linalg.cholesky(S)
@@ -268,7 +273,7 @@ class StochasticReconfiguration(_SRBase):
         import torch
         from .._device import sr_gram
         B = stacked.shape[0] // 2
-        S = sr_gram(stacked.float(), transpose_a=True) / B
+        S = sr_gram(stacked.float(), transpose_a=True, engine=self._gram_engine()) / B
         S = S + self.diag_shift * torch.eye(S.shape[0], dtype=S.dtype, device=S.device)
         L = torch.linalg.cholesky(S)
         return torch.cholesky_solve(rhs.reshape(-1, 1), L).reshape(-1)

@@ -179,6 +179,13 @@ int fk_sr_gram(const float* A, int64_t rows, int64_t cols, int transpose_a, floa
                int64_t ws_bytes, void* stream);
 int64_t fk_sr_gram_workspace_bytes(int64_t rows, int64_t cols, int transpose_a);
 
+/* The same contraction as a tcgen05 GEMM: X repacked to fp16 (precise != 0: hi + lo split, three MMAs per k-step, ~2^-21
+ * relative; precise == 0: one MMA, ~2^-11) with a power-of-two scale, fp32 accumulation in TMEM, upper block triangle
+ * computed and mirrored.  Workspace holds the repacked operands ((precise ? 4 : 2) bytes per padded element). */
+int64_t fk_sr_gram_tc_workspace_bytes(int64_t rows, int64_t cols, int transpose_a, int precise);
+int fk_sr_gram_tc(const float* A, int64_t rows, int64_t cols, int transpose_a, int precise, float* G, void* ws,
+                  int64_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

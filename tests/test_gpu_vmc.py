@@ -155,6 +155,26 @@ def test_sr_gram_kernel():
     assert np.abs(G2 - An @ An.T).max() < 1e-4 * np.abs(An @ An.T).max()
 
 
+@pytest.mark.parametrize('rows,cols,transpose_a', [(300, 97, True), (300, 97, False), (1024, 700, True), (64, 1000, False),
+                                                   (2048, 129, True)])
+def test_sr_gram_tensor_core_kernel(rows, cols, transpose_a):
+    """fk_sr_gram_tc: hi/lo fp16 operands -> 3e-5 of the largest entry (what is left is the truncating fp32 accumulation of
+    the tensor core, ~1e-6 per few hundred samples); single pass -> 2e-3"""
+    from flowket_b200._device import sr_gram
+    from flowket_b200 import FK_ENGINE_TC
+    rng = np.random.default_rng(3)
+    A = torch.from_numpy((rng.normal(size=(rows, cols)) * rng.uniform(0.01, 3.0, size=(1, cols) if transpose_a else (rows, 1))
+                          ).astype(np.float32)).cuda()
+    An = A.cpu().numpy().astype(np.float64)
+    want = An.T @ An if transpose_a else An @ An.T
+    got = sr_gram(A, transpose_a=transpose_a, engine=FK_ENGINE_TC, precise=True).cpu().numpy()
+    assert got.shape == want.shape and np.isfinite(got).all()
+    assert np.abs(got - want).max() < 3e-5 * np.abs(want).max()
+    assert np.array_equal(got, got.T)
+    fast = sr_gram(A, transpose_a=transpose_a, engine=FK_ENGINE_TC, precise=False).cpu().numpy()
+    assert np.abs(fast - want).max() < 2e-3 * np.abs(want).max()
+
+
 def test_training_lowers_the_energy_towards_exact_diagonalisation():
     """Ising 4x4 OBC h=3 (cfg 1 anchor: ED -50.18662388277671, examples/basic_autoregressive_2d.py:39):
     exact-gradient Adam steps must move the variational energy monotonically-ish towards the ED value and stay
