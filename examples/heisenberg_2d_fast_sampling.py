@@ -24,8 +24,13 @@ from flowket_b200.samplers import FastAutoregressiveSampler  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--steps', type=int, default=100)
-    ap.add_argument('--batch_size', type=int, default=1024, help='global batch (split over the ranks)')
+    ap.add_argument('--steps', type=int, nargs='+', default=[100], help='updates per stage')
+    ap.add_argument('--batch_size', type=int, nargs='+', default=[1024], help='global batch per stage (split over the ranks); '
+                    'staged schedules like experiments/heisenberg_runner.py: --steps 2500 400 --batch_size 1024 4096')
+    ap.add_argument('--beta_2', type=float, default=0.999, help='0.9 in the paper runs (experiments/train.py:52)')
+    ap.add_argument('--checkpoint', default=None, help='path of a resumable checkpoint (written every 60 s and at the end)')
+    ap.add_argument('--eval_samples', type=int, default=0, help='final energy estimate from this many fresh samples')
+    ap.add_argument('--print_every', type=int, default=10)
     ap.add_argument('--depth', type=int, default=20)
     ap.add_argument('--width', type=int, default=32)
     ap.add_argument('--lr', type=float, default=1e-3)
@@ -36,7 +41,8 @@ def main():
     torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
     if world > 1:
         dist.init_process_group('nccl')
-    batch = (args.batch_size + world - 1) // world
+    assert len(args.steps) == len(args.batch_size)
+    batch = (args.batch_size[0] + world - 1) // world
 
     inputs = Input(shape=(10, 10), dtype='int8')
     convnet = ConvNetAutoregressive2D(inputs, depth=args.depth, num_of_channels=args.width, weights_normalization=False, seed=0)
@@ -50,13 +56,46 @@ def main():
     operator = Heisenberg(hilbert_state_shape=(10, 10), pbc=False)
     vmc_cls = DistributedVariationalMonteCarlo if world > 1 else VariationalMonteCarlo
     variational_monte_carlo = vmc_cls(model, operator, sampler)
-    trainer = Trainer(model, variational_monte_carlo, Adam(lr=args.lr, beta_1=0.9, beta_2=0.999), distributed=world > 1)
+    trainer = Trainer(model, variational_monte_carlo, Adam(lr=args.lr, beta_1=0.9, beta_2=args.beta_2), distributed=world > 1)
+    if args.checkpoint and os.path.exists(args.checkpoint + '.npz'):
+        trainer.load_checkpoint(args.checkpoint)
+        if rank == 0:
+            print('resumed from %s at update %d' % (args.checkpoint, len(trainer.history)), flush=True)
+    resumed_updates = len(trainer.history)
     t0 = time.time()
-    for step in range(args.steps):
-        energy = trainer.train_step()
-        if rank == 0 and (step % 10 == 0 or step == args.steps - 1):
-            print('step %4d  energy %.4f  variance %.3f  (reference ground state -251.4624)  %.1f s' % (
-                step, energy.real, variational_monte_carlo.current_local_energy_variance, time.time() - t0), flush=True)
+    last_ckpt = time.time()
+    done = 0
+    for stage, (steps, global_batch) in enumerate(zip(args.steps, args.batch_size)):
+        stage_batch = (global_batch + world - 1) // world
+        if stage_batch != variational_monte_carlo.sampler.batch_size:   # staged schedule (experiments/train.py:99-101)
+            new_sampler = variational_monte_carlo.sampler.copy_with_new_batch_size(stage_batch)
+            new_sampler.sample_offset = rank * stage_batch
+            variational_monte_carlo.set_sampler(new_sampler)
+        for step in range(steps):
+            done += 1
+            if done <= resumed_updates:      # already applied before the checkpoint was written
+                continue
+            energy = trainer.train_step()
+            if rank == 0 and (step % args.print_every == 0 or step == steps - 1):
+                print('stage %d step %5d  batch %5d  energy %.4f  variance %.3f  (reference ground state -251.4624)  %.1f s' % (
+                    stage, step, global_batch, energy.real, variational_monte_carlo.current_local_energy_variance, time.time() - t0),
+                    flush=True)
+            if args.checkpoint and rank == 0 and time.time() - last_ckpt > 60:
+                trainer.save_checkpoint(args.checkpoint)
+                last_ckpt = time.time()
+    if args.checkpoint and rank == 0:
+        trainer.save_checkpoint(args.checkpoint)
+    if args.eval_samples and rank == 0:
+        import numpy as np
+        from flowket_b200.observables.monte_carlo import Observable
+        obs = Observable(operator)
+        ev = FastAutoregressiveSampler(conditional_log_probs_model, 8192, seed=99)
+        vals = []
+        for _ in range(max(1, args.eval_samples // 8192)):
+            vals.append(obs.local_values_device(model, ev.next_device()).real.cpu().numpy())
+        vals = np.concatenate(vals)
+        print('evaluation: %d samples  energy %.4f +- %.4f  variance %.3f  (reference ground state -251.4624, published -251.4536)' % (
+            len(vals), vals.mean(), vals.std() / np.sqrt(len(vals)), vals.var()), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
