@@ -33,9 +33,83 @@ def conjugate_gradient(apply, rhs, tol=1e-3, max_iter=200):
     return x, i, float(torch.linalg.vector_norm(r))
 
 
+def sr_delta(O, y_true, diag_shift=0.05, iterative_solver=False, conjugate_gradient_tol=1e-3, max_iterations=200,
+             distributed=False, gram=None, stats=None, y_over_global_batch=False):
+    """delta = (Obar^H Obar / B + lambda I)^-1 Obar^H conj(y)   for the rows `O` [B_local, P] (complex or real torch tensor, any
+    device) and `y_true` = conj(E_loc - E) / B_local of this rank (optimizer.py:33-124).
+    distributed: the batch is sharded over the ranks of torch.distributed -- the mean of O, the right-hand side and either the
+    P x P matrix (direct) or every matrix-vector product (CG) are summed over the ranks (NCCL on CUDA tensors, gloo on CPU);
+    every rank returns the same delta as a single process would on the concatenated batch.
+    y_over_global_batch: y_true is already divided by the global batch (DistributedVariationalMonteCarlo.next_batch) instead
+    of this rank's batch (the reference's per-rank convention).
+    gram: callable X [B, K] real -> X^T X (e.g. the device kernels); default torch matmul."""
+    import torch
+    from .trainer import allreduce_sum_
+    red = allreduce_sum_ if distributed else (lambda t: t)
+    B_local = O.shape[0]
+    B = int(red(torch.tensor([float(B_local)], dtype=torch.float64, device=O.device)).item())
+    mean = red(O.sum(dim=0)) / B
+    O_bar = O - mean
+    y = torch.as_tensor(y_true).to(device=O.device, dtype=O.dtype)
+    if not y_over_global_batch:
+        y = y * (float(B_local) / B)
+    F = red(O_bar.conj().T @ torch.conj(y))
+    if iterative_solver:
+        def apply(v):
+            return red(O_bar.conj().T @ (O_bar @ v)) / B + diag_shift * v
+        x, it, res = conjugate_gradient(apply, F, conjugate_gradient_tol, max_iterations)
+        if stats is not None:
+            stats['iterations'], stats['residual_norm'] = it, res
+        return x
+    if gram is None:
+        gram = lambda X: X.T @ X   # noqa: E731
+    if O_bar.is_complex():
+        # Obar^H Obar = (R^T R + I^T I) + i (R^T I - I^T R): one real Gram of the stacked matrix [R | I]
+        R, I = O_bar.real.contiguous(), O_bar.imag.contiguous()
+        G = red(gram(torch.cat([R, I], dim=1)))
+        P = R.shape[1]
+        S = torch.complex(G[:P, :P] + G[P:, P:], G[:P, P:] - G[P:, :P]) / B
+    else:
+        S = red(gram(O_bar)) / B
+    S = S + diag_shift * torch.eye(S.shape[0], dtype=S.dtype, device=S.device)
+    L = torch.linalg.cholesky(S)
+    return torch.cholesky_solve(F.reshape(-1, 1).to(S.dtype), L).reshape(-1)
+
+
+def real_sr_delta(R, I, e, diag_shift=0.05, iterative_solver=False, conjugate_gradient_tol=1e-3, max_iterations=200,
+                  distributed=False, gram=None, stats=None):
+    """Real-parameter SR for a complex log psi:  S = Re(Obar^H Obar)/B + lambda I = (Rbar^T Rbar + Ibar^T Ibar)/B + lambda I,
+    F = Re(Obar^H (E - Ebar))/B, with R = d Re log psi / d theta, I = d Im log psi / d theta [B_local, P] and the local
+    energies e [B_local] of this rank; `distributed` sums the means, F and S (or every CG product) over the ranks."""
+    import torch
+    from .trainer import allreduce_sum_
+    red = allreduce_sum_ if distributed else (lambda t: t)
+    B = int(red(torch.tensor([float(R.shape[0])], dtype=torch.float64, device=R.device)).item())
+    e = torch.as_tensor(e).to(device=R.device, dtype=torch.complex128)
+    e = e - red(e.sum().reshape(1)) / B
+    X = torch.cat([R - red(R.sum(dim=0)) / B, I - red(I.sum(dim=0)) / B], dim=0)
+    ep = torch.cat([e.real, e.imag]).to(X.dtype)
+    F = red(X.T @ ep) / B
+    if iterative_solver:
+        def apply(v):
+            return red(X.T @ (X @ v)) / B + diag_shift * v
+        x, it, res = conjugate_gradient(apply, F, conjugate_gradient_tol, max_iterations)
+        if stats is not None:
+            stats['iterations'], stats['residual_norm'] = it, res
+        return x
+    if gram is None:
+        gram = lambda Y: Y.T @ Y   # noqa: E731
+    S = red(gram(X)) / B
+    S = S + diag_shift * torch.eye(S.shape[0], dtype=S.dtype, device=S.device)
+    L = torch.linalg.cholesky(S)
+    return torch.cholesky_solve(F.reshape(-1, 1).to(S.dtype), L).reshape(-1)
+
+
 class _SRBase(object):
     def __init__(self, model, lr=0.01, diag_shift=0.05, iterative_solver=True, conjugate_gradient_tol=1e-3,
-                 iterative_solver_max_iterations=200, use_cholesky=True):
+                 iterative_solver_max_iterations=200, use_cholesky=True, distributed=False):
+        self.distributed = distributed      # samples sharded over the ranks: reductions of the SR system go over NCCL
+        self.y_over_global_batch = True     # y_true as produced by DistributedVariationalMonteCarlo.next_batch
         self.model, self.machine = model, model.machine
         self.lr, self.diag_shift = lr, diag_shift
         self.iterative_solver = iterative_solver
@@ -116,8 +190,18 @@ class ComplexValuesStochasticReconfiguration(_SRBase):
         """delta (complex [P_c]) for a batch; y_true = conj(E_loc - E)/B as produced by VariationalMonteCarlo."""
         import torch
         O = self.complex_jacobian(sigma)
-        O_bar = O - O.mean(dim=0, keepdim=True)
         y = torch.as_tensor(np.asarray(y_true, np.complex64)).to(O.device)
+        if self.distributed:
+            from .._device import sr_gram
+            stats = {}
+            delta = sr_delta(O, y, self.diag_shift, self.iterative_solver, self.conjugate_gradient_tol,
+                             self.iterative_solver_max_iterations, distributed=True,
+                             gram=lambda X: sr_gram(X.float(), transpose_a=True, engine=self._gram_engine()), stats=stats,
+                             y_over_global_batch=self.y_over_global_batch)
+            self.conjugate_gradient_iterations = stats.get('iterations', 0)
+            self.conjugate_gradient_residual_norm = stats.get('residual_norm', 0.0)
+            return delta
+        O_bar = O - O.mean(dim=0, keepdim=True)
         F = O_bar.conj().T @ torch.conj(y)
         return self.solve(O_bar, F)
 
@@ -182,6 +266,21 @@ class StochasticReconfiguration(_SRBase):
 
     def compute_update(self, sigma, local_energy):
         import torch
+        if self.distributed:
+            if self.sample_space:
+                raise NotImplementedError('sample-space SR builds the 2B x 2B Gram per rank; shard the batch with '
+                                          'sample_space=False (P x P system, reductions over NCCL) or run it on one GPU')
+            from .._device import sr_gram
+            net = self.machine.device_net()
+            R, I = net.grad_per_sample(net.to_sigma(sigma), imag=True, engine=self._jacobian_engine(net))
+            e = local_energy if torch.is_tensor(local_energy) else torch.as_tensor(np.asarray(local_energy, np.complex128))
+            stats = {}
+            delta = real_sr_delta(R, I, e, self.diag_shift, self.iterative_solver, self.conjugate_gradient_tol,
+                                  self.iterative_solver_max_iterations, distributed=True,
+                                  gram=lambda Y: sr_gram(Y.float(), transpose_a=True, engine=self._gram_engine()), stats=stats)
+            self.conjugate_gradient_iterations = stats.get('iterations', 0)
+            self.conjugate_gradient_residual_norm = stats.get('residual_norm', 0.0)
+            return delta
         t = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         t[0].record()
         X = self.stacked_jacobian(sigma)

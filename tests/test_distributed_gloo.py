@@ -54,3 +54,41 @@ def test_philox_shard_offsets_partition_the_global_batch():
     s = FastAutoregressiveSampler(cond, 100, mini_batch_size=32)
     assert s._effective_batch() == 96          # batch % mini_batch samples are dropped (fast_autoregressive.py:31-33)
     assert s.copy_with_new_batch_size(16).batch_size == 16
+
+
+def _sr_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from flowket_b200.optimizers import sr_delta, real_sr_delta
+    rng = np.random.default_rng(7)
+    B, P = 48, 11
+    O = torch.from_numpy(rng.normal(size=(B, P)) + 1j * rng.normal(size=(B, P)))
+    e = torch.from_numpy(rng.normal(size=B) * 2 - 5 + 1j * rng.normal(size=B))
+    lo, hi = (0, 20) if rank == 0 else (20, 48)          # ragged shards
+    res = {}
+    for iterative in (False, True):
+        # complex-parameter SR: y_true = conj(E_loc - E_global) / B_local, as DistributedVariationalMonteCarlo hands it over
+        y_full = torch.conj(e - e.mean()) / B
+        want = sr_delta(O, y_full, 0.05, iterative, 1e-12, 500)
+        y_loc = torch.conj(e[lo:hi] - e.mean()) / (hi - lo)
+        got = sr_delta(O[lo:hi], y_loc, 0.05, iterative, 1e-12, 500, distributed=True)
+        res['complex', iterative] = float((got - want).abs().max() / want.abs().max())
+        want = real_sr_delta(O.real, O.imag, e, 0.05, iterative, 1e-12, 500)
+        got = real_sr_delta(O.real[lo:hi], O.imag[lo:hi], e[lo:hi], 0.05, iterative, 1e-12, 500, distributed=True)
+        res['real', iterative] = float((got - want).abs().max() / want.abs().max())
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+def test_world_size_2_stochastic_reconfiguration_matches_single_process():
+    """SR system sharded over two ranks (means, right-hand side, P x P matrix or CG products allreduced) == the same system
+    assembled from the whole batch by one process"""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_sr_worker, args=(world, 29653, out), nprocs=world, join=True)
+    for rank in range(world):
+        for key, err in out[rank].items():
+            assert err < 1e-8, (rank, key, err)
