@@ -47,6 +47,7 @@ class Trainer(object):
         self.model, self.generator, self.optimizer, self.distributed = model, generator, optimizer, distributed
         self.machine = model.machine
         self.history = []
+        self.logs = []          # one dict per epoch, filled by the callbacks of fit()
 
     def gradient(self, x, y):
         """(1/mb) d/dtheta sum_b 2 Re(log psi_b y_b) on the device."""
@@ -74,16 +75,49 @@ class Trainer(object):
         self.history.append(energy)
         return energy
 
-    def fit(self, steps, checkpoint_path=None, checkpoint_every_seconds=None):
+    def fit(self, steps, checkpoint_path=None, checkpoint_every_seconds=None, callbacks=(), steps_per_epoch=None,
+            initial_step=0):
         """`steps` updates; with a path, a checkpoint every `checkpoint_every_seconds` of wall clock and at the end
-        (CheckpointByTime, callbacks/checkpoint.py:9-73)."""
+        (CheckpointByTime, callbacks/checkpoint.py:9-73).
+
+        `callbacks` (flowket_b200.callbacks) see what Keras' fit_generator shows the reference's callbacks
+        (experiments/train.py:117-130): `on_batch_end(batch, logs)` after every update, `on_epoch_begin/end(epoch,
+        logs)` every `steps_per_epoch` updates (default: one epoch = one update), `on_train_begin/end`; a callback
+        that sets `model.stop_training` (BadEigenStateStopping) ends the loop.  The filled `logs` dicts are kept in
+        `self.logs`."""
         import time
         last = time.time()
-        for _ in range(steps):
+        steps_per_epoch = 1 if steps_per_epoch is None else int(steps_per_epoch)
+        self.model.stop_training = False
+        for cb in callbacks:
+            cb.set_model(self.model)
+            if hasattr(cb, 'set_trainer'):
+                cb.set_trainer(self)
+            cb.on_train_begin({})
+        epoch_logs = {}
+        for step in range(initial_step, initial_step + steps):
+            epoch, batch = divmod(step, steps_per_epoch)
+            if batch == 0:
+                epoch_logs = {}
+                for cb in callbacks:
+                    cb.on_epoch_begin(epoch, epoch_logs)
             self.train_step()
+            batch_logs = {}
+            for cb in callbacks:
+                cb.on_batch_end(batch, batch_logs)
+            epoch_logs.update(batch_logs)
+            if batch == steps_per_epoch - 1:
+                for cb in callbacks:
+                    cb.on_epoch_end(epoch, epoch_logs)
+                if callbacks:
+                    self.logs.append(dict(epoch_logs))
             if checkpoint_path and checkpoint_every_seconds is not None and time.time() - last >= checkpoint_every_seconds:
                 self.save_checkpoint(checkpoint_path)
                 last = time.time()
+            if self.model.stop_training:
+                break
+        for cb in callbacks:
+            cb.on_train_end({})
         if checkpoint_path:
             self.save_checkpoint(checkpoint_path)
         return self.history

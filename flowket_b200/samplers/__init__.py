@@ -101,3 +101,12 @@ class AutoregressiveSampler(_DeviceAutoregressiveSampler):
         super(AutoregressiveSampler, self).__init__(conditional_log_probs_machine, batch_size, **kwargs)
         self.use_progress_bar = use_progress_bar
         self.zero_base = zero_base
+
+
+from .exact_sampler import ExactSampler, WaveFunctionSampler  # noqa: E402
+from .metropolis_hastings import MetropolisHastingsSampler, MetropolisHastingsLocal, MetropolisHastingsUniform, \
+    MetropolisHastingsHamiltonian, MetropolisHastingsExchange, MetropolisHastingsGlobal  # noqa: E402
+
+__all__ = ['Sampler', 'FastAutoregressiveSampler', 'AutoregressiveSampler', 'ExactSampler', 'WaveFunctionSampler',
+           'MetropolisHastingsSampler', 'MetropolisHastingsLocal', 'MetropolisHastingsUniform',
+           'MetropolisHastingsHamiltonian', 'MetropolisHastingsExchange', 'MetropolisHastingsGlobal']

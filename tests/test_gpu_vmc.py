@@ -281,3 +281,77 @@ def test_checkpoint_resume_continues_the_same_trajectory(tmp_path):
     t_b.fit(3)
     assert (m_b.flat_params_device() - m_ref.flat_params_device()).abs().max().item() < 2e-4
     assert abs(t_b.history[-1] - t_ref.history[-1]) < 1e-3
+
+
+def test_metropolis_hastings_against_exact_distribution():
+    """SURVEY 8f-4 cross-check (reference: tests/test_samplers.py:49-82): MH chains driven by the CUDA forward and the
+    device find_conn reproduce |psi|^2 of the same machine, which the exact autoregressive sampler also reproduces."""
+    from flowket_b200.exact.utils import binary_array_to_decimal_array
+    from flowket_b200.operators import Heisenberg
+    from flowket_b200.optimization import ExactVariational
+    from flowket_b200.samplers import MetropolisHastingsLocal, MetropolisHastingsHamiltonian, ExactSampler, \
+        FastAutoregressiveSampler
+    shape = (3, 2)
+    model, cond, spec, params = make_pair('conv2d', shape, 2, 8, seed=2)
+    op = Heisenberg(hilbert_state_shape=list(shape), pbc=False)
+    ev = ExactVariational(model, op, batch_size=64)
+    ev.machine_updated()
+
+    def l1(batch, probs):
+        idx = binary_array_to_decimal_array(np.asarray(batch).reshape(len(batch), -1))
+        return np.abs(np.bincount(idx, minlength=64) / float(len(batch)) - probs).sum()
+
+    local = MetropolisHastingsLocal(model, 256 * 60, num_of_chains=256, unused_sampels=5, discard_ratio=3, seed=1)
+    assert l1(next(local), ev.probs) < 0.1
+    assert l1(next(ExactSampler(ev, 1 << 14, seed=0)), ev.probs) < 0.1
+    assert l1(next(FastAutoregressiveSampler(cond, 1 << 14)), ev.probs) < 0.1
+    # Hamiltonian moves stay in the S_z = 0 sector: compare with the conditional distribution
+    ham = MetropolisHastingsHamiltonian(model, 256 * 60, op, num_of_chains=256, unused_sampels=5, discard_ratio=3, seed=1)
+    batch = next(ham)
+    assert np.all(batch.reshape(len(batch), -1).sum(axis=1) == 0)
+    in_sector = ev.states.reshape(64, -1).sum(axis=1) == 0
+    sector_probs = np.where(in_sector, ev.probs, 0.0)
+    assert l1(batch, sector_probs / sector_probs.sum()) < 0.1
+    assert 0.0 < ham.acceptance_ratio <= 1.0
+
+
+def test_fit_with_callbacks_and_evaluate(tmp_path):
+    """Trainer.fit drives the reference's callback protocol (experiments/train.py:117-130), evaluation.evaluate the
+    evaluation protocol (evaluation/evaluate.py:16-29); logged energies are the generator's device results."""
+    from flowket_b200 import Input, Model
+    from flowket_b200.callbacks import default_wave_function_stats_callbacks_factory, CheckpointByTime
+    from flowket_b200.callbacks.monte_carlo import BadEigenStateStopping
+    from flowket_b200.evaluation import evaluate
+    from flowket_b200.machines import ConvNetAutoregressive2D
+    from flowket_b200.operators import Heisenberg
+    from flowket_b200.samplers import FastAutoregressiveSampler
+    from flowket_b200.optimization import VariationalMonteCarlo
+    from flowket_b200.optimizers import Adam, Trainer
+    inp = Input(shape=(4, 4), dtype='int8')
+    m = ConvNetAutoregressive2D(inp, depth=3, num_of_channels=8, seed=11)
+    model, cond = Model(inp, m.predictions), Model(inp, m.conditional_log_probs)
+    op = Heisenberg(hilbert_state_shape=[4, 4], pbc=False)
+    vmc = VariationalMonteCarlo(model, op, FastAutoregressiveSampler(cond, 128, seed=5))
+    val = VariationalMonteCarlo(model, op, FastAutoregressiveSampler(cond, 256, seed=6))
+    callbacks = default_wave_function_stats_callbacks_factory(vmc, validation_generator=val,
+                                                              true_ground_state_energy=-36.7546)
+    ckpt = CheckpointByTime(str(tmp_path / 'ck'), save_frequency_in_minutes=1e9)
+    trainer = Trainer(model, vmc, Adam(lr=1e-2, beta_1=0.9, beta_2=0.9))
+    trainer.fit(6, callbacks=callbacks + [ckpt, BadEigenStateStopping(-36.7546, min_epoch=100)], steps_per_epoch=2)
+    assert len(trainer.logs) == 3 and ckpt.saves == 1 and (tmp_path / 'ck.npz').exists()
+    last = trainer.logs[-1]
+    for key in ('energy/energy', 'energy/local_energy_variance', 'energy/relative_error', 'observables/sigma_z',
+                'observables/abs_sigma_z', 'times/sampling', 'times/local_energy', 'times/gradients', 'times/total',
+                'val_energy/energy', 'val_observables/abs_sigma_z'):
+        assert key in last, key
+    assert last['energy/energy'] == pytest.approx(np.real(vmc.current_energy))
+    assert last['val_energy/energy'] == pytest.approx(np.real(val.current_energy))
+    assert last['observables/sigma_z'] == pytest.approx(vmc.current_batch.reshape(128, -1).sum(axis=1).mean() / 16.0)
+    res = evaluate(val, 4, callbacks[1:], verbose=False)
+    assert abs(res['energy/energy'] - last['val_energy/energy']) < 2.0
+    assert res['energy/local_energy_variance'] > 0
+    # a callback may stop the loop
+    stopper = BadEigenStateStopping(-36.7546, variance_tol=1e9, relative_error_to_stop=-1e9, min_epoch=0)
+    before = len(trainer.history)
+    trainer.fit(5, callbacks=callbacks + [stopper])
+    assert len(trainer.history) == before + 1 and stopper.stopped_epoch == 0
