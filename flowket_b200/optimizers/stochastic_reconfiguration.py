@@ -105,6 +105,90 @@ def real_sr_delta(R, I, e, diag_shift=0.05, iterative_solver=False, conjugate_gr
     return torch.cholesky_solve(F.reshape(-1, 1).to(S.dtype), L).reshape(-1)
 
 
+def sample_space_sr_delta(X, ep, diag_shift=0.05, distributed=False, gram=None, low_precision=None, timings=None):
+    """Sample-space SR, optionally with the batch sharded over the ranks of torch.distributed.
+
+    `X` = [Re Obar_r ; Im Obar_r], the rows of *this rank* ([2 B_r, P], already centred with the global means), `ep` =
+    [Re(E - Ebar) ; Im(E - Ebar)] of the same rows.  Returns delta = X_all^T (X_all X_all^T / B + lambda I)^-1 ep_all / B
+    for the concatenation over the ranks, identical on every rank (push-through form of optimizer.py:33-124).
+
+    The 2B x 2B Gram contracts over the parameter axis, which every rank holds in full for its own rows only.  One
+    all-to-all re-shards X from sample-major to parameter-major (rank g receives columns [g P/G, (g+1) P/G) of every
+    rank's rows -- as many bytes as it sends), each rank forms the partial Gram of its column slice on its tensor cores,
+    one allreduce sums the partial Grams (fp32, (2B)^2), every rank factorises the same fp64 system, and the update
+    delta = sum_r X_r^T w_r is one more allreduce of P numbers.  Shards may be ragged.
+
+    gram: callable Y [n, k] -> Y Y^T in fp32 (default: torch matmul in the rows' dtype, at least fp32); low_precision: torch dtype the rows are
+    rounded to before the all-to-all and the Gram (bf16 halves the exchange and runs the GEMM at tensor-core rate)."""
+    import torch
+    import torch.distributed as dist
+    from .trainer import allreduce_sum_
+    if gram is None:
+        def gram(Y):
+            Y = Y if Y.dtype in (torch.float32, torch.float64) else Y.float()
+            return Y @ Y.T
+    rows, P = X.shape
+    world = dist.get_world_size() if distributed and dist.is_initialized() else 1
+    dev = X.device
+    mark = (lambda: torch.cuda.Event(enable_timing=True)) if (timings is not None and X.is_cuda) else None
+    events = []
+
+    def stamp():
+        if mark is not None:
+            ev = mark()
+            ev.record()
+            events.append(ev)
+    stamp()
+    if world == 1:
+        Y = X if low_precision is None else X.to(low_precision)
+        rows_of = [rows]
+        ep_all = ep
+    else:
+        rank = dist.get_rank()
+        counts = torch.zeros(world, dtype=torch.int64, device=dev)
+        counts[rank] = rows
+        rows_of = [int(c) for c in allreduce_sum_(counts).tolist()]
+        align = 64 * world                       # every column slice starts 16-byte aligned and is a multiple of 64 wide
+        P_pad = (P + align - 1) // align * align
+        slice_cols = P_pad // world
+        dt = X.dtype if low_precision is None else low_precision
+        send = torch.zeros((world, rows, slice_cols), dtype=dt, device=dev)        # [destination][row][column of the slice]
+        for g in range(world):
+            lo, hi = g * slice_cols, min(P, (g + 1) * slice_cols)
+            if hi > lo:
+                send[g, :, :hi - lo].copy_(X[:, lo:hi])
+        Y = torch.empty((sum(rows_of), slice_cols), dtype=dt, device=dev)
+        dist.all_to_all_single(Y, send.reshape(world * rows, slice_cols), output_split_sizes=rows_of,
+                               input_split_sizes=[rows] * world)
+        del send
+        ep_all = torch.zeros(sum(rows_of), dtype=ep.dtype, device=dev)      # ragged gather = sum of disjoint slices
+        first = sum(rows_of[:rank])
+        ep_all[first:first + rows] = ep
+        allreduce_sum_(ep_all)
+    stamp()
+    T = gram(Y)
+    if world > 1:
+        allreduce_sum_(T)
+    del Y
+    stamp()
+    B = sum(rows_of) // 2
+    T = T / B
+    T.diagonal().add_(diag_shift)
+    L = torch.linalg.cholesky(T.double())              # fp64: the Gram can be badly conditioned
+    w = torch.cholesky_solve((ep_all.double() / B).reshape(-1, 1), L).reshape(-1).to(X.dtype)
+    stamp()
+    if world == 1:
+        delta = X.T @ w
+    else:
+        delta = allreduce_sum_(X.T @ w[first:first + rows])
+    stamp()
+    if events:
+        torch.cuda.synchronize()
+        names = ('exchange', 'gram', 'cholesky', 'update')
+        timings.update({n: events[i].elapsed_time(events[i + 1]) for i, n in enumerate(names)})
+    return delta
+
+
 class _SRBase(object):
     def __init__(self, model, lr=0.01, diag_shift=0.05, iterative_solver=True, conjugate_gradient_tol=1e-3,
                  iterative_solver_max_iterations=200, use_cholesky=True, distributed=False):
@@ -267,9 +351,12 @@ class StochasticReconfiguration(_SRBase):
     def compute_update(self, sigma, local_energy):
         import torch
         if self.distributed:
-            if self.sample_space:
-                raise NotImplementedError('sample-space SR builds the 2B x 2B Gram per rank; shard the batch with '
-                                          'sample_space=False (P x P system, reductions over NCCL) or run it on one GPU')
+            sample_space = self.sample_space
+            if sample_space is None:
+                net = self.machine.device_net()
+                sample_space = net.num_params > 2 * int(sigma.shape[0]) * self._world_size()   # P > 2 B_global
+            if sample_space:
+                return self._compute_update_sample_space_distributed(sigma, local_energy)
             from .._device import sr_gram
             net = self.machine.device_net()
             R, I = net.grad_per_sample(net.to_sigma(sigma), imag=True, engine=self._jacobian_engine(net))
@@ -308,6 +395,43 @@ class StochasticReconfiguration(_SRBase):
         if sample_space and ev is not None and self.gram_dtype != 'fp32':
             self.last_timings_ms.update({'convert': ev[0].elapsed_time(ev[1]), 'gram': ev[1].elapsed_time(ev[2]),
                                          'cholesky': ev[2].elapsed_time(ev[3])})
+        return delta
+
+    @staticmethod
+    def _world_size():
+        import torch.distributed as dist
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def _compute_update_sample_space_distributed(self, sigma, local_energy):
+        """Sample-space SR with the batch sharded over the ranks: per-rank Jacobians, global centring (two allreduces of
+        P numbers), then sample_space_sr_delta (all-to-all re-shard, partial Gram per rank, allreduce, replicated solve)."""
+        import torch
+        from .trainer import allreduce_sum_
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        X = self.stacked_jacobian(sigma)
+        B_local = X.shape[0] // 2
+        B = int(allreduce_sum_(torch.tensor([float(B_local)], dtype=torch.float64, device=X.device)).item())
+        if torch.is_tensor(local_energy):
+            e = local_energy.to(device=X.device, dtype=torch.complex128)
+        else:
+            e = torch.as_tensor(np.asarray(local_energy, np.complex128)).to(X.device)
+        e = e - torch.view_as_complex(allreduce_sum_(torch.view_as_real(e.sum().reshape(1)).clone())) / B
+        X[:B_local] -= allreduce_sum_(X[:B_local].sum(dim=0)) / B
+        X[B_local:] -= allreduce_sum_(X[B_local:].sum(dim=0)) / B
+        # rows of this rank stay [Re ; Im]: the Gram and its right-hand side only need a consistent row order
+        ep = torch.cat([e.real, e.imag]).float()
+        t1.record()
+        if self.gram_dtype not in ('bf16', 'fp32'):
+            raise NotImplementedError('distributed sample-space SR exchanges bf16 (default) or fp32 rows')
+        low = torch.bfloat16 if self.gram_dtype == 'bf16' else None
+        gram = (lambda Y: self._symmetric_gram(Y)) if low is not None else None
+        timings = {}
+        delta = sample_space_sr_delta(X, ep, self.diag_shift, distributed=True, gram=gram, low_precision=low,
+                                      timings=timings)
+        torch.cuda.synchronize()
+        self.last_timings_ms = dict(timings, jacobian=t0.elapsed_time(t1))
         return delta
 
     def _solve_sample_space(self, X, ep, B):

@@ -92,3 +92,50 @@ def test_world_size_2_stochastic_reconfiguration_matches_single_process():
     for rank in range(world):
         for key, err in out[rank].items():
             assert err < 1e-8, (rank, key, err)
+
+
+def _sample_space_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from flowket_b200.optimizers import real_sr_delta, sample_space_sr_delta
+    rng = np.random.default_rng(11)
+    B, P = 24, 203                                           # P >> 2B and not a multiple of the slice alignment
+    R = torch.from_numpy(rng.normal(size=(B, P)))
+    I = torch.from_numpy(rng.normal(size=(B, P)))
+    e = torch.from_numpy(rng.normal(size=B) * 2 - 5 + 1j * rng.normal(size=B))
+    want = real_sr_delta(R, I, e, 0.05)                      # P x P system, whole batch, one process
+    bounds = [0, 7, 24] if world == 2 else [0, 5, 13, 24]    # ragged shards
+    lo, hi = bounds[rank], bounds[rank + 1]
+    Rb, Ib, eb = R - R.mean(0), I - I.mean(0), e - e.mean()
+    X = torch.cat([Rb[lo:hi], Ib[lo:hi]])
+    ep = torch.cat([eb.real[lo:hi], eb.imag[lo:hi]])
+    res = {}
+    got = sample_space_sr_delta(X, ep, 0.05, distributed=True)
+    res['fp64'] = float((got - want).abs().max() / want.abs().max())
+    got = sample_space_sr_delta(X.float(), ep.float(), 0.05, distributed=True, low_precision=torch.bfloat16)
+    res['bf16'] = float((got.double() - want).abs().max() / want.abs().max())
+    # identical on every rank
+    ref = got.clone()
+    dist.broadcast(ref, 0)
+    res['replicated'] = float((got - ref).abs().max())
+    # one process, same function
+    single = sample_space_sr_delta(torch.cat([Rb, Ib]), torch.cat([eb.real, eb.imag]), 0.05)
+    res['single'] = float((single - want).abs().max() / want.abs().max())
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,port', [(2, 29655), (3, 29657)])
+def test_sample_space_stochastic_reconfiguration_sharded_matches_single_process(world, port):
+    """all-to-all re-shard of X to parameter-major, partial Grams, allreduce, replicated solve == the
+    P x P solve of the whole batch (push-through identity), for ragged shards and any world size"""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_sample_space_worker, args=(world, port, out), nprocs=world, join=True)
+    for rank in range(world):
+        res = out[rank]
+        assert res['fp64'] < 1e-9 and res['single'] < 1e-9, (rank, res)
+        assert res['bf16'] < 2e-2, (rank, res)
+        assert res['replicated'] == 0.0, (rank, res)

@@ -142,6 +142,12 @@ def test_real_sr_matches_oracle():
         sr = StochasticReconfiguration(model, diag_shift=0.05, sample_space=True, gram_dtype=gram_dtype, jacobian_chunk=40)
         got = sr.compute_update(sigma, eloc).cpu().numpy()
         assert np.linalg.norm(got - want) / np.linalg.norm(want) < tol, gram_dtype
+        # the sharded code path (global centring, re-shard, partial Gram, replicated solve) on a world of one rank
+        srd = StochasticReconfiguration(model, diag_shift=0.05, sample_space=True, gram_dtype=gram_dtype, jacobian_chunk=40,
+                                        distributed=True)
+        got = srd.compute_update(sigma, eloc).cpu().numpy()
+        assert np.linalg.norm(got - want) / np.linalg.norm(want) < tol, gram_dtype
+        assert set(srd.last_timings_ms) == {'jacobian', 'exchange', 'gram', 'cholesky', 'update'}
 
 
 def test_sr_gram_kernel():
