@@ -68,9 +68,55 @@ class StatsCallback(Callback):
             self.collect(logs, self.validation_generator, prefix='val_')
 
 
+class TensorBoard(Callback):
+    """Scalar logger with the constructor of flowket.callbacks.TensorBoard (callbacks/tensorboard.py; keras TensorBoard
+    arguments are accepted).  The TensorFlow event-file writer, histograms and graph dumps of the reference are not
+    rebuilt: every numeric entry of `logs` is appended to `<log_dir>/scalars.jsonl` as {"step": n, "tag": value, ...} --
+    per batch (`update_freq` = 'batch' or an integer period in batches) or per epoch (`update_freq='epoch'`)."""
+
+    def __init__(self, log_dir='./logs', update_freq='epoch', **_keras_arguments):
+        super(TensorBoard, self).__init__()
+        self.log_dir = log_dir
+        self.update_freq = update_freq
+        self._file = None
+        self._batches_seen = 0
+
+    def _write(self, step, logs):
+        import json
+        import os
+        import numbers
+        import numpy
+        scalars = {k: float(numpy.real(v)) for k, v in (logs or {}).items()
+                   if isinstance(v, (numbers.Number, numpy.number)) and k not in ('batch', 'size')}
+        if not scalars:
+            return
+        if self._file is None:
+            os.makedirs(self.log_dir, exist_ok=True)
+            self._file = open(os.path.join(self.log_dir, 'scalars.jsonl'), 'a')
+        self._file.write(json.dumps(dict(step=int(step), **scalars)) + '\n')
+        self._file.flush()
+
+    def on_batch_end(self, batch, logs=None):
+        self._batches_seen += 1
+        if self.update_freq == 'epoch':
+            return
+        period = 1 if self.update_freq == 'batch' else int(self.update_freq)
+        if self._batches_seen % period == 0:
+            self._write(self._batches_seen, logs)
+
+    def on_epoch_end(self, epoch, logs=None):
+        if self.update_freq == 'epoch':
+            self._write(epoch, logs)
+
+    def on_train_end(self, logs=None):
+        if self._file is not None:
+            self._file.close()
+            self._file = None
+
+
 from .checkpoint import CheckpointByTime  # noqa: E402
 from . import monte_carlo, exact  # noqa: E402,F401
 from .monte_carlo import default_wave_function_stats_callbacks_factory  # noqa: E402,F401
 
-__all__ = ['Callback', 'StatsCallback', 'CheckpointByTime', 'monte_carlo', 'exact',
+__all__ = ['Callback', 'StatsCallback', 'TensorBoard', 'CheckpointByTime', 'monte_carlo', 'exact',
            'default_wave_function_stats_callbacks_factory']

@@ -8,7 +8,7 @@ import warnings
 
 import numpy
 
-from . import Callback, StatsCallback
+from . import Callback, StatsCallback, TensorBoard
 
 
 class LocalEnergyStats(StatsCallback):
@@ -128,6 +128,15 @@ class BadEigenStateStopping(Callback):
             if self.model is not None:
                 self.model.stop_training = True
             self.stopped_epoch = epoch
+
+
+class TensorBoardWithGeneratorValidationData(TensorBoard):
+    """Constructor of callbacks/monte_carlo/tensorboard_with_generator_validation_data.py:5-17; the reference feeds the
+    generator's current batch to Keras' histogram summaries, which this scalar logger does not write."""
+
+    def __init__(self, generator, **kwargs):
+        super(TensorBoardWithGeneratorValidationData, self).__init__(**kwargs)
+        self.generator = generator
 
 
 def default_wave_function_stats_callbacks_factory(generator, validation_generator=None, true_ground_state_energy=None,

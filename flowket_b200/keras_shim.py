@@ -77,3 +77,32 @@ class Model(object):
         return self.predict_device(x, batch_size=batch_size).cpu().numpy()
 
     __call__ = predict
+
+    # ---- training (the three Keras calls the reference scripts make: compile, summary, fit_generator) ------------
+    def compile(self, optimizer, loss=None, **_unused):
+        """`loss` must be loss_for_energy_minimization (optimization/loss.py:4-5) -- the only loss of this path; its
+        gradient is the hand-written device backward, not autodiff."""
+        from .optimization.loss import loss_for_energy_minimization
+        if loss is not None and loss is not loss_for_energy_minimization:
+            raise NotImplementedError('the B200 path differentiates loss_for_energy_minimization only')
+        self.optimizer = optimizer
+        self.loss = loss
+        self._trainer = None
+
+    def summary(self, print_fn=print):
+        specs = self.machine.weight_specs()
+        print_fn('Model "%s"  input %s  output %s' % (self.name, self.input_shape, self.output_shape))
+        for name, shape, _ in specs:
+            print_fn('  %-44s %-20s %10d' % (name, tuple(shape), int(np.prod(shape))))
+        print_fn('Total params: {:,}'.format(self.count_params()))
+
+    def fit_generator(self, generator, steps_per_epoch=1, epochs=1, callbacks=(), initial_epoch=0, verbose=0, **kwargs):
+        """Keras semantics (mini-batches per epoch); see optimizers.Trainer.fit_generator."""
+        from .optimizers import Trainer
+        if getattr(self, 'optimizer', None) is None:
+            raise RuntimeError('compile(optimizer, loss) first')
+        if self._trainer is None:
+            self._trainer = Trainer(self, generator, self.optimizer)
+        self._trainer.generator = generator
+        return self._trainer.fit_generator(generator, steps_per_epoch=steps_per_epoch, epochs=epochs,
+                                           callbacks=list(callbacks), initial_epoch=initial_epoch, verbose=verbose, **kwargs)

@@ -42,12 +42,57 @@ class Adam(object):
         params.addcdiv_(self.m, self.v.sqrt().add_(self.epsilon), value=-lr_t)
 
 
+def convert_to_accumulate_gradient_optimizer(orig_optimizer, update_params_frequency, accumulate_sum_or_mean=True,
+                                             ema_decay=0, use_horovod=False):
+    """Same call as flowket/optimizers/accumulate_gradient_optimizer.py:13-88: gradients of `update_params_frequency`
+    consecutive mini-batches are summed (or averaged) and the wrapped optimizer steps once per group; with `ema_decay`
+    an exponential moving average of the parameters is tracked after every step and `set_weights_ema()` installs its
+    bias-corrected value (:28-29,66-68).  `use_horovod` asks the Trainer to sum the accumulated gradient over the ranks
+    (NCCL allreduce) before the step (:31-50).  Here the optimizer is only annotated; Trainer.train_on_batch does the
+    accumulation on the device."""
+    if update_params_frequency < 1:
+        raise ValueError('update_params_frequency must be >= 1')
+    orig_optimizer.update_params_frequency = int(update_params_frequency)
+    orig_optimizer.accumulate_sum_or_mean = bool(accumulate_sum_or_mean)
+    orig_optimizer.accumulated_iterations = 0
+    orig_optimizer.ema_decay = float(ema_decay)
+    orig_optimizer.total_iterations = 0
+    orig_optimizer.params_ema = None
+    orig_optimizer.use_horovod = bool(use_horovod)
+
+    def set_update_params_frequency(frequency):
+        orig_optimizer.update_params_frequency = int(frequency)
+
+    def track_ema(params):
+        if orig_optimizer.ema_decay <= 0:
+            return
+        if orig_optimizer.params_ema is None:
+            orig_optimizer.params_ema = params.new_zeros(params.shape)
+        orig_optimizer.total_iterations += 1
+        orig_optimizer.params_ema.mul_(orig_optimizer.ema_decay).add_(params, alpha=1 - orig_optimizer.ema_decay)
+
+    def set_weights_ema(machine=None):
+        """params <- ema / (1 - decay^t); needs the machine the optimizer trains (remembered by the Trainer)."""
+        machine = machine if machine is not None else getattr(orig_optimizer, '_machine', None)
+        if machine is None or orig_optimizer.params_ema is None:
+            raise RuntimeError('no moving average yet: train at least one step with ema_decay > 0')
+        correction = 1.0 - orig_optimizer.ema_decay ** orig_optimizer.total_iterations
+        machine.flat_params_device().copy_(orig_optimizer.params_ema / correction)
+        machine.params_updated()
+
+    orig_optimizer.set_update_params_frequency = set_update_params_frequency
+    orig_optimizer.track_ema = track_ema
+    orig_optimizer.set_weights_ema = set_weights_ema
+    return orig_optimizer
+
+
 class Trainer(object):
     def __init__(self, model, generator, optimizer, distributed=False):
         self.model, self.generator, self.optimizer, self.distributed = model, generator, optimizer, distributed
         self.machine = model.machine
         self.history = []
         self.logs = []          # one dict per epoch, filled by the callbacks of fit()
+        self._accumulator, self._accumulated = None, 0
 
     def gradient(self, x, y):
         """(1/mb) d/dtheta sum_b 2 Re(log psi_b y_b) on the device."""
@@ -57,23 +102,90 @@ class Trainer(object):
         y_t = torch.as_tensor(np.asarray(y, np.complex64)) if not hasattr(y, 'is_cuda') else y
         return net.grad_weighted(sigma, y_t, engine=getattr(self.model, 'engine', 0)) / float(sigma.shape[0])
 
-    def train_step(self):
-        """One parameter update = `update_params_frequency` mini-batches of the generator."""
-        gen = self.generator
-        freq = getattr(gen, 'update_params_frequency', 1)
-        grad = None
-        for _ in range(freq):
-            x, y = next(gen)
-            g = self.gradient(x, y)
-            grad = g if grad is None else grad.add_(g)
-        if self.distributed:
+    def _frequency(self):
+        """mini-batches per parameter update: the optimizer's (convert_to_accumulate_gradient_optimizer) or the generator's"""
+        freq = getattr(self.optimizer, 'update_params_frequency', None)
+        if freq is None:
+            freq = getattr(self.generator, 'update_params_frequency', 1)
+        return int(freq)
+
+    def train_on_batch(self, x, y):
+        """Keras' train_on_batch under an accumulate-gradient optimizer (accumulate_gradient_optimizer.py:54-82): add this
+        mini-batch's gradient to the accumulator; every `update_params_frequency`-th call allreduce (if distributed), step,
+        reset.  Returns True when the parameters moved."""
+        g = self.gradient(x, y)
+        freq = self._frequency()
+        if not getattr(self.optimizer, 'accumulate_sum_or_mean', True):
+            g = g / float(freq)
+        self._accumulator = g if self._accumulator is None else self._accumulator.add_(g)
+        self._accumulated += 1
+        if hasattr(self.optimizer, 'accumulated_iterations'):
+            self.optimizer.accumulated_iterations += 1
+        if self._accumulated % freq != 0:
+            return False
+        grad, self._accumulator, self._accumulated = self._accumulator, None, 0
+        if self.distributed or getattr(self.optimizer, 'use_horovod', False):
             allreduce_sum_(grad)
         params = self.machine.flat_params_device()
         self.optimizer.step(params, grad)
         self.machine.params_updated()
+        if getattr(self.optimizer, 'ema_decay', 0) > 0:
+            self.optimizer._machine = self.machine
+            self.optimizer.track_ema(params)
+        return True
+
+    def train_step(self):
+        """One parameter update = `update_params_frequency` mini-batches of the generator."""
+        gen = self.generator
+        updated = False
+        while not updated:
+            x, y = next(gen)
+            updated = self.train_on_batch(x, y)
         energy = getattr(gen, 'current_energy', None)
         self.history.append(energy)
         return energy
+
+    def fit_generator(self, generator=None, steps_per_epoch=1, epochs=1, callbacks=(), initial_epoch=0, verbose=0,
+                      **_keras_only):
+        """Keras' Model.fit_generator as the reference scripts call it (examples/*.py, experiments/train.py:127-128):
+        `steps_per_epoch` counts *mini-batches*, epochs run from `initial_epoch` to `epochs`, callbacks see
+        on_batch_end(batch, logs) after every mini-batch and on_epoch_end(epoch, logs) after every epoch.
+        max_queue_size / workers are accepted and ignored (the generator runs on this thread, like workers=0)."""
+        gen = self.generator if generator is None else generator
+        self.model.stop_training = False
+        for cb in callbacks:
+            cb.set_model(self.model)
+            if hasattr(cb, 'set_trainer'):
+                cb.set_trainer(self)
+            cb.set_params({'epochs': epochs, 'steps': steps_per_epoch, 'verbose': verbose})
+            cb.on_train_begin({})
+        for epoch in range(initial_epoch, epochs):
+            epoch_logs = {}
+            for cb in callbacks:
+                cb.on_epoch_begin(epoch, epoch_logs)
+            for batch in range(steps_per_epoch):
+                x, y = next(gen)
+                batch_logs = {'batch': batch, 'size': len(x)}
+                for cb in callbacks:
+                    cb.on_batch_begin(batch, batch_logs)
+                if self.train_on_batch(x, y):
+                    self.history.append(getattr(self.generator, 'current_energy', None))
+                for cb in callbacks:
+                    cb.on_batch_end(batch, batch_logs)
+                epoch_logs.update({k: v for k, v in batch_logs.items() if k not in ('batch', 'size')})
+                if self.model.stop_training:
+                    break
+            for cb in callbacks:
+                cb.on_epoch_end(epoch, epoch_logs)
+            self.logs.append(dict(epoch_logs))
+            if verbose:
+                print('epoch %d/%d  %s' % (epoch + 1, epochs, '  '.join(
+                    '%s %.6g' % (k, v) for k, v in sorted(epoch_logs.items()) if not k.startswith('times/'))), flush=True)
+            if self.model.stop_training:
+                break
+        for cb in callbacks:
+            cb.on_train_end({})
+        return self.logs
 
     def fit(self, steps, checkpoint_path=None, checkpoint_every_seconds=None, callbacks=(), steps_per_epoch=None,
             initial_step=0):

@@ -298,3 +298,90 @@ def test_checkpoint_by_time_callback(tmp_path):
     cb2.set_model(types.SimpleNamespace(save_weights=lambda p: weights.append(p)))
     cb2.on_train_end()
     assert weights == ['w']
+
+
+class _StubMachine(object):
+    def __init__(self, n=3):
+        import torch
+        self.params = torch.zeros(n, dtype=torch.float64)
+        self.updates = 0
+
+    def flat_params_device(self):
+        return self.params
+
+    def params_updated(self):
+        self.updates += 1
+
+
+def _stub_trainer(optimizer, gradients, distributed=False):
+    """Trainer whose device gradient is replaced by a scripted sequence (host logic only)."""
+    import torch
+    from flowket_b200.optimizers import Trainer
+    machine = _StubMachine()
+    model = types.SimpleNamespace(machine=machine, stop_training=False)
+    seq = iter(gradients)
+
+    def generator():
+        while True:
+            yield np.zeros((2, 3)), np.zeros(2)
+
+    trainer = Trainer(model, generator(), optimizer, distributed=distributed)
+    trainer.gradient = lambda x, y: torch.tensor(next(seq), dtype=torch.float64)
+    return trainer, machine
+
+
+def test_accumulate_gradient_optimizer_sum_mean_and_ema(tmp_path):
+    """accumulate_gradient_optimizer.py:54-82: step once per `update_params_frequency` mini-batches on the sum (or mean) of
+    their gradients; EMA of the parameters after every step with the bias-corrected read-out (:28-29,66-68)."""
+    from flowket_b200.optimizers import SGD, convert_to_accumulate_gradient_optimizer
+    grads = [[1.0, 0, 0], [0, 2.0, 0], [0, 0, 4.0], [1.0, 1.0, 1.0], [1.0, 1.0, 1.0], [1.0, 1.0, 1.0]]
+    opt = convert_to_accumulate_gradient_optimizer(SGD(lr=0.5), 3, accumulate_sum_or_mean=True, ema_decay=0.5)
+    trainer, machine = _stub_trainer(opt, grads)
+    moved = [trainer.train_on_batch(None, None) for _ in range(3)]
+    assert moved == [False, False, True] and machine.updates == 1
+    assert machine.params.tolist() == [-0.5, -1.0, -2.0]
+    trainer.train_step()                                   # three more mini-batches, one update
+    assert machine.params.tolist() == [-2.0, -2.5, -3.5] and opt.accumulated_iterations == 6
+    # ema after two steps: e1 = 0.5 p1, e2 = 0.25 p1 + 0.5 p2; corrected by 1 - 0.5^2
+    want = (0.25 * np.array([-0.5, -1.0, -2.0]) + 0.5 * np.array([-2.0, -2.5, -3.5])) / 0.75
+    opt.set_weights_ema()
+    assert np.allclose(machine.params.numpy(), want)
+    # mean mode and a changed frequency
+    opt2 = convert_to_accumulate_gradient_optimizer(SGD(lr=1.0), 2, accumulate_sum_or_mean=False)
+    trainer2, machine2 = _stub_trainer(opt2, [[2.0, 0, 0], [0, 4.0, 0], [6.0, 6.0, 6.0]])
+    trainer2.train_step()
+    assert machine2.params.tolist() == [-1.0, -2.0, 0.0]
+    opt2.set_update_params_frequency(1)
+    trainer2.train_step()
+    assert machine2.params.tolist() == [-7.0, -8.0, -6.0]
+    with pytest.raises(ValueError):
+        convert_to_accumulate_gradient_optimizer(SGD(), 0)
+    with pytest.raises(RuntimeError):
+        opt2.set_weights_ema(machine2)
+
+
+def test_fit_generator_keras_semantics_and_scalar_logger(tmp_path):
+    """steps_per_epoch counts mini-batches, callbacks see every mini-batch, epochs run initial_epoch..epochs"""
+    import json
+    from flowket_b200.callbacks import Callback, TensorBoard
+    from flowket_b200.optimizers import SGD, convert_to_accumulate_gradient_optimizer
+    opt = convert_to_accumulate_gradient_optimizer(SGD(lr=1.0), 2)
+    trainer, machine = _stub_trainer(opt, [[1.0, 0, 0]] * 12)
+    seen = []
+
+    class Probe(Callback):
+        def on_batch_end(self, batch, logs=None):
+            seen.append(('batch', batch))
+            logs['energy/energy'] = -float(len(seen))
+
+        def on_epoch_end(self, epoch, logs=None):
+            seen.append(('epoch', epoch))
+
+    board = TensorBoard(log_dir=str(tmp_path / 'tb'), update_freq=2)
+    logs = trainer.fit_generator(steps_per_epoch=4, epochs=3, initial_epoch=1, callbacks=[Probe(), board])
+    assert [s for s in seen if s[0] == 'epoch'] == [('epoch', 1), ('epoch', 2)]
+    assert [b for k, b in seen if k == 'batch'] == [0, 1, 2, 3, 0, 1, 2, 3]
+    assert machine.updates == 4 and machine.params[0].item() == -8.0        # 8 mini-batches, 2 per update
+    assert len(logs) == 2 and 'energy/energy' in logs[-1]
+    lines = [json.loads(l) for l in open(tmp_path / 'tb' / 'scalars.jsonl')]
+    assert [l['step'] for l in lines] == [2, 4, 6, 8] and all('energy/energy' in l for l in lines)

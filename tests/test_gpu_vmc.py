@@ -361,3 +361,37 @@ def test_fit_with_callbacks_and_evaluate(tmp_path):
     before = len(trainer.history)
     trainer.fit(5, callbacks=callbacks + [stopper])
     assert len(trainer.history) == before + 1 and stopper.stopped_epoch == 0
+
+
+def test_compile_and_fit_generator_exact_gradient_script_flow():
+    """The calls of the reference's examples/basic_autoregressive_exact_gradient.py (BASELINE configs[0]) on a 10-site
+    chain: compile, accumulate-gradient optimizer over one enumeration cycle, fit_generator with the exact callbacks."""
+    from flowket_b200 import Input, Model
+    from flowket_b200.callbacks.exact import default_wave_function_callbacks_factory
+    from flowket_b200.machines import SimpleConvNetAutoregressive1D
+    from flowket_b200.operators import Ising
+    from flowket_b200.optimization import ExactVariational, loss_for_energy_minimization
+    from flowket_b200.optimizers import Adam, convert_to_accumulate_gradient_optimizer
+    inputs = Input(shape=[10], dtype='int8')
+    convnet = SimpleConvNetAutoregressive1D(inputs, depth=4, num_of_channels=16, weights_normalization=False, seed=0)
+    model = Model(inputs=inputs, outputs=convnet.predictions)
+    operator = Ising(h=3.0, hilbert_state_shape=[10], pbc=False)
+    ev = ExactVariational(model, operator, 2 ** 8)
+    assert ev.num_of_batch_until_full_cycle == 4
+    optimizer = Adam(lr=0.01, beta_1=0.9, beta_2=0.999)
+    convert_to_accumulate_gradient_optimizer(optimizer, update_params_frequency=ev.num_of_batch_until_full_cycle,
+                                             accumulate_sum_or_mean=True)
+    model.compile(optimizer=optimizer, loss=loss_for_energy_minimization)
+    lines = []
+    model.summary(print_fn=lines.append)
+    assert 'Total params' in lines[-1]
+    e_ed = oexact.ground_state(oops.OracleOperator('ising', (10,), h=3.0, pbc=False), (10,))[0]
+    callbacks = default_wave_function_callbacks_factory(ev, true_ground_state_energy=e_ed)
+    logs = model.fit_generator(ev.to_generator(), steps_per_epoch=4 * 20, epochs=3, callbacks=callbacks,
+                               max_queue_size=0, workers=0)
+    assert len(logs) == 3 and optimizer.accumulated_iterations == 240 and optimizer.t == 60
+    energies = [l['energy/energy'] for l in logs]
+    assert energies[-1] < energies[0] - 0.5                       # training lowers the exact energy
+    assert all(e > e_ed - 1e-6 for e in energies)                 # variational principle
+    assert logs[-1]['energy/relative_error'] == pytest.approx((e_ed - energies[-1]) / e_ed)
+    assert 'observables/sigma_z' in logs[-1] and 'times/total' in logs[-1]
