@@ -134,7 +134,7 @@ def run_reference(args):
                                    'all connections + weighted gradient, torch-CPU fp32 oracle' % (sample_batch, args.batch_per_gpu)},
         'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 METRIC = 'vmc_step_samples_per_sec (sample + E_loc + gradient), Heisenberg 2D 10x10 OBC ConvNetAutoregressive2D d20 c32'
@@ -149,6 +149,44 @@ def workload_config(args, world):
                           if args.engine == 'tc' else 'fp32 CUDA cores'),
             'parallelism': 'samples sharded over %d GPU(s); allreduce of energy statistics and flat gradient' % world,
             'l2_policy': 'per-step working set (activation workspaces, several GB) is much larger than the 126 MB L2'}
+
+
+def sharded_sr_leg(args, world, rank, model, cond, machine, operator, obs, timed):
+    """N > 1: the north-star step with stochastic reconfiguration -- sample + local energy + sample-space SR update -- on a
+    GLOBAL batch of `--batch-per-gpu` samples sharded over the ranks (strong scaling for this leg: the 2B x 2B system is
+    a function of the global batch; 8192 per GPU x 8 would be a 131 072^2 Gram).  Exchange per update: all-to-all of the
+    bf16 Jacobian rows, allreduce of the partial Grams, two allreduces of P floats.  Every rank
+    runs it; the time is the max over ranks.  Failures are reported in the JSON instead of taking the headline down."""
+    import torch
+    from flowket_b200.samplers import FastAutoregressiveSampler
+    from flowket_b200.optimizers import StochasticReconfiguration
+    try:
+        torch.cuda.empty_cache()
+        B_sr = max(1, args.batch_per_gpu // world)
+        sampler_sr = FastAutoregressiveSampler(cond, B_sr, seed=4321, sample_offset=rank * B_sr)
+        sr = StochasticReconfiguration(model, lr=0.01, diag_shift=0.05, sample_space=True, gram_dtype='bf16',
+                                       jacobian_chunk=512, distributed=True)
+
+        def step():
+            sigma = sampler_sr.next_device()
+            eloc = obs.local_values_device(model, sigma)
+            sr.step(sigma, eloc)
+            machine.device_net()
+
+        step()                                   # warm-up (allocations, NCCL channels for the all-to-all)
+        steps = 2
+        ms = timed(step, steps, record=None) / steps
+        torch.cuda.synchronize()
+        res = {'ms_per_step': ms, 'samples_per_s': B_sr * world / (ms * 1e-3), 'global_batch': B_sr * world,
+               'batch_per_gpu': B_sr, 'scaling': 'strong', 'sr_update_ms': dict(sr.last_timings_ms),
+               'solver': 'sample space, batch sharded over %d ranks: all-to-all re-shard of the bf16 Jacobian rows to '
+                         'parameter-major, partial 2B x 2B Gram per rank, fp32 allreduce, replicated fp64 Cholesky' % world,
+               'peak_mem_gb': torch.cuda.max_memory_allocated() / 1e9}
+        del sr
+        torch.cuda.empty_cache()
+        return res
+    except Exception as exc:
+        return {'error': '%s: %s' % (type(exc).__name__, exc)}
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -275,6 +313,9 @@ def run_gpu(args):
         e2e_step()
     e2e_ms = timed(lambda: e2e_step(), args.steps, record=None)
 
+    sr_sharded = None
+    if world > 1 and not args.no_sr:
+        sr_sharded = sharded_sr_leg(args, world, rank, model, cond, machine, operator, obs, timed)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -342,15 +383,36 @@ def run_gpu(args):
             torch.cuda.empty_cache()
         except Exception as exc:  # the SR leg must never take the headline line down with it
             line['sr_step'] = {'error': '%s: %s' % (type(exc).__name__, exc)}
+    if sr_sharded is not None:
+        line['sr_step'] = sr_sharded
     if world == 1 and not args.no_cpu_baseline:
         cb = cpu_step_rate(args.cpu_batch, 2)
         line['cpu_baseline'] = {'value': cb['value'], 'unit': 'samples/s', 'cores': cb['cores'], 'kind': 'port',
                                 'sampling_samples_per_s': cb['sampling_samples_per_s'], 'eloc_evals_per_s': cb['eloc_evals_per_s'],
                                 'sample': '%d samples of the same workload, best of 2: incremental sampling + E_loc over all '
                                           'connections + weighted gradient, torch-CPU fp32 oracle port' % args.cpu_batch}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line, but native libraries write there too (NCCL prints its version banner on the
+    first communicator).  Keep a private duplicate of fd 1 for the JSON line and point fd 1 at stderr for everything else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
 
 
 def main():
@@ -367,9 +429,11 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-sr', action='store_true', help='skip the stochastic-reconfiguration variant of the step')
     args = ap.parse_args()
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if not (world == 1 and args.gpus > 1 and args.impl != 'reference'):
+        claim_stdout()      # (the torchrun re-launch below lets its children own the real stdout)
     if args.impl == 'reference':
         return run_reference(args)
-    world = int(os.environ.get('WORLD_SIZE', '1'))
     if world == 1 and args.gpus > 1:
         # convenience: re-launch under torchrun (the driver launches torchrun itself)
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
