@@ -4,7 +4,7 @@ This package is a CPU restatement (numpy + torch-CPU) of the reference's
 algorithm for the hot path named in BASELINE.json `north_star`:
 autoregressive sampling -> find_conn -> local energy -> gradients / SR.
 
-Rules (enforced by tests/test_no_oracle_in_product.py):
+Rules (enforced by tests/test_abi_and_hygiene.py::test_product_never_imports_the_oracle):
   * only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline /
     `--impl reference` legs may import anything from here;
   * nothing under `flowket_b200/` imports it; the product path has no CPU
