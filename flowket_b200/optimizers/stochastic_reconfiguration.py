@@ -105,7 +105,51 @@ def real_sr_delta(R, I, e, diag_shift=0.05, iterative_solver=False, conjugate_gr
     return torch.cholesky_solve(F.reshape(-1, 1).to(S.dtype), L).reshape(-1)
 
 
-def sample_space_sr_delta(X, ep, diag_shift=0.05, distributed=False, gram=None, low_precision=None, timings=None):
+def distributed_cholesky_solve(T, b, block=1024):
+    """w = T^-1 b (fp64) for a symmetric positive-definite `T` that is REPLICATED on every rank of torch.distributed, with
+    the factorisation shared between the ranks instead of repeated on each of them (the replicated 2B x 2B Cholesky is
+    the part of the sharded SR step that does not shrink with the number of GPUs).
+
+    Right-looking blocked Cholesky, block columns dealt round-robin to the ranks: the owner of block column k factorises
+    its diagonal block and solves the panel below it (`L_ik = A_ik L_kk^-T`), broadcasts the panel (the only
+    communication: n^2/2 numbers in total), and every rank applies the rank-`block` update to the block columns it owns.
+    Because every panel is broadcast, every rank ends up holding the whole factor L and finishes with the same two
+    triangular solves -- the result is identical on all ranks.  Only the lower triangle of T is read."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    n = T.shape[0]
+    nblk = (n + block - 1) // block
+    start = [k * block for k in range(nblk)] + [n]
+    # my block columns, rows from the diagonal block down, promoted to fp64 one column at a time
+    mine = {k: T[start[k]:, start[k]:start[k + 1]].to(dtype=torch.float64, copy=True) for k in range(nblk) if k % world == rank}
+    L = torch.zeros((n, n), dtype=torch.float64, device=T.device)
+    for k in range(nblk):
+        owner = k % world
+        width = start[k + 1] - start[k]
+        panel = L[start[k]:, start[k]:start[k + 1]]           # view into the factor: [(n - start_k), width]
+        if rank == owner:
+            col = mine.pop(k)
+            Lkk = torch.linalg.cholesky(col[:width])
+            col[:width] = Lkk
+            if col.shape[0] > width:                           # A_ik L_kk^-T  ==  solve X L_kk^T = A_ik
+                col[width:] = torch.linalg.solve_triangular(Lkk.T, col[width:], upper=True, left=False)
+            panel.copy_(col)
+        if world > 1:
+            buf = panel.contiguous()
+            dist.broadcast(buf, src=owner)
+            if rank != owner:
+                panel.copy_(buf)
+        for j in mine:                                          # trailing update of the block columns this rank still owns
+            if j > k:
+                off = start[j] - start[k]
+                mine[j] -= panel[off:] @ panel[off:off + (start[j + 1] - start[j])].T
+    return torch.cholesky_solve(b.double().reshape(-1, 1), L).reshape(-1)
+
+
+def sample_space_sr_delta(X, ep, diag_shift=0.05, distributed=False, gram=None, low_precision=None, timings=None,
+                          shared_cholesky=False):
     """Sample-space SR, optionally with the batch sharded over the ranks of torch.distributed.
 
     `X` = [Re Obar_r ; Im Obar_r], the rows of *this rank* ([2 B_r, P], already centred with the global means), `ep` =
@@ -118,6 +162,8 @@ def sample_space_sr_delta(X, ep, diag_shift=0.05, distributed=False, gram=None, 
     one allreduce sums the partial Grams (fp32, (2B)^2), every rank factorises the same fp64 system, and the update
     delta = sum_r X_r^T w_r is one more allreduce of P numbers.  Shards may be ragged.
 
+    shared_cholesky: factorise the replicated system with distributed_cholesky_solve (block columns dealt to the ranks)
+    instead of once per rank.
     gram: callable Y [n, k] -> Y Y^T in fp32 (default: torch matmul in the rows' dtype, at least fp32); low_precision: torch dtype the rows are
     rounded to before the all-to-all and the Gram (bf16 halves the exchange and runs the GEMM at tensor-core rate)."""
     import torch
@@ -174,8 +220,11 @@ def sample_space_sr_delta(X, ep, diag_shift=0.05, distributed=False, gram=None, 
     B = sum(rows_of) // 2
     T = T / B
     T.diagonal().add_(diag_shift)
-    L = torch.linalg.cholesky(T.double())              # fp64: the Gram can be badly conditioned
-    w = torch.cholesky_solve((ep_all.double() / B).reshape(-1, 1), L).reshape(-1).to(X.dtype)
+    if shared_cholesky and world > 1:
+        w = distributed_cholesky_solve(T, ep_all.double() / B).to(X.dtype)      # factorisation shared between the ranks
+    else:
+        L = torch.linalg.cholesky(T.double())          # fp64: the Gram can be badly conditioned
+        w = torch.cholesky_solve((ep_all.double() / B).reshape(-1, 1), L).reshape(-1).to(X.dtype)
     stamp()
     if world == 1:
         delta = X.T @ w
@@ -318,8 +367,9 @@ class StochasticReconfiguration(_SRBase):
                       tensor-core GEMM (cuBLAS, bf16 operands / fp32 accumulation by default) + a Cholesky of size 2B.
     `sample_space=None` picks the sample-space form when P > 2B."""
 
-    def __init__(self, model, sample_space=None, gram_dtype='bf16', jacobian_chunk=1024, **kwargs):
+    def __init__(self, model, sample_space=None, gram_dtype='bf16', jacobian_chunk=1024, shared_cholesky=False, **kwargs):
         super(StochasticReconfiguration, self).__init__(model, **kwargs)
+        self.shared_cholesky = shared_cholesky     # distributed sample-space solve: share the Cholesky between the ranks
         self.sample_space = sample_space
         self.gram_dtype = gram_dtype
         self.jacobian_chunk = jacobian_chunk
@@ -429,7 +479,7 @@ class StochasticReconfiguration(_SRBase):
         gram = (lambda Y: self._symmetric_gram(Y)) if low is not None else None
         timings = {}
         delta = sample_space_sr_delta(X, ep, self.diag_shift, distributed=True, gram=gram, low_precision=low,
-                                      timings=timings)
+                                      timings=timings, shared_cholesky=self.shared_cholesky)
         torch.cuda.synchronize()
         self.last_timings_ms = dict(timings, jacobian=t0.elapsed_time(t1))
         return delta

@@ -120,6 +120,20 @@ def _sample_space_worker(rank, world, port, out):
     ref = got.clone()
     dist.broadcast(ref, 0)
     res['replicated'] = float((got - ref).abs().max())
+    # the replicated system factorised once, block columns dealt to the ranks, instead of once per rank
+    got = sample_space_sr_delta(X, ep, 0.05, distributed=True, shared_cholesky=True)
+    res['shared_cholesky'] = float((got - want).abs().max() / want.abs().max())
+    from flowket_b200.optimizers import distributed_cholesky_solve
+    A = torch.from_numpy(rng.normal(size=(45, 60)))
+    T = A @ A.T / 60 + 0.05 * torch.eye(45, dtype=torch.float64)
+    rhs = torch.from_numpy(rng.normal(size=45))
+    T_before = T.clone()
+    w = distributed_cholesky_solve(T, rhs, block=7)            # 7 block columns (the last one ragged) over 2 or 3 ranks
+    assert torch.equal(T, T_before)                            # the replicated system is read, never written
+    res['cholesky_solve'] = float((w - torch.linalg.solve(T, rhs)).abs().max())
+    w0 = w.clone()
+    dist.broadcast(w0, 0)
+    res['cholesky_replicated'] = float((w - w0).abs().max())
     # one process, same function
     single = sample_space_sr_delta(torch.cat([Rb, Ib]), torch.cat([eb.real, eb.imag]), 0.05)
     res['single'] = float((single - want).abs().max() / want.abs().max())
@@ -139,3 +153,4 @@ def test_sample_space_stochastic_reconfiguration_sharded_matches_single_process(
         assert res['fp64'] < 1e-9 and res['single'] < 1e-9, (rank, res)
         assert res['bf16'] < 2e-2, (rank, res)
         assert res['replicated'] == 0.0, (rank, res)
+        assert res['shared_cholesky'] < 1e-9 and res['cholesky_solve'] < 1e-10 and res['cholesky_replicated'] == 0.0, (rank, res)

@@ -21,6 +21,7 @@ ap.add_argument('--depth', type=int, default=4)
 ap.add_argument('--batch', type=int, default=128, help='samples per rank')
 ap.add_argument('--lattice', type=int, default=6)
 ap.add_argument('--skip_single', action='store_true', help='timing only (the global batch may not fit one GPU)')
+ap.add_argument('--shared_cholesky', action='store_true', help='also time the solve with the factorisation shared between the ranks')
 args = ap.parse_args()
 rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
 torch.cuda.set_device(int(os.environ['LOCAL_RANK']))
@@ -50,6 +51,14 @@ if rank == 0:
     assert all((g - gathered[0]).abs().max() == 0 for g in gathered), 'ranks disagree'
     print('sharded sample-space SR, %d x %d samples, P = %d: %s' % (
         world, B, delta.numel(), {k: round(v, 2) for k, v in sr.last_timings_ms.items()}), flush=True)
+if args.shared_cholesky:
+    sr.shared_cholesky = True
+    for _ in range(2):
+        delta_shared = sr.compute_update(vmc.current_batch_device, vmc.current_local_energy)
+    if rank == 0:
+        print('shared Cholesky: %s, relative difference to the replicated solve %.3e' % (
+            {k: round(v, 2) for k, v in sr.last_timings_ms.items()}, float((delta_shared - delta).norm() / delta.norm())), flush=True)
+if rank == 0:
     if not args.skip_single:
         vmc1, sr1 = build(B * world, 0, False)
         vmc1.next_batch()
