@@ -114,9 +114,34 @@ class TensorBoard(Callback):
             self._file = None
 
 
+class TerminateOnNaN(Callback):
+    """keras.callbacks.TerminateOnNaN as the reference scripts use it (examples/j1j2_2d_monte_carlo_4.py:61): stop when
+    the monitored quantity stops being finite.  Keras watches `logs['loss']`; this path has no scalar loss on the host, so
+    the energy entries of `logs` are watched instead."""
+
+    def __init__(self, keys=('energy/energy', 'energy/local_energy_variance', 'loss'), **kwargs):
+        super(TerminateOnNaN, self).__init__(**kwargs)
+        self.keys = tuple(keys)
+        self.stopped = False
+
+    def _check(self, logs):
+        import numpy
+        for key in self.keys:
+            if key in (logs or {}) and not numpy.all(numpy.isfinite(logs[key])):
+                self.stopped = True
+                if self.model is not None:
+                    self.model.stop_training = True
+
+    def on_batch_end(self, batch, logs=None):
+        self._check(logs)
+
+    def on_epoch_end(self, epoch, logs=None):
+        self._check(logs)
+
+
 from .checkpoint import CheckpointByTime  # noqa: E402
 from . import monte_carlo, exact  # noqa: E402,F401
 from .monte_carlo import default_wave_function_stats_callbacks_factory  # noqa: E402,F401
 
-__all__ = ['Callback', 'StatsCallback', 'TensorBoard', 'CheckpointByTime', 'monte_carlo', 'exact',
+__all__ = ['Callback', 'StatsCallback', 'TensorBoard', 'TerminateOnNaN', 'CheckpointByTime', 'monte_carlo', 'exact',
            'default_wave_function_stats_callbacks_factory']

@@ -61,6 +61,9 @@ class Model(object):
         np.savez(path, **{'w%04d' % i: w for i, w in enumerate(self.get_weights())})
 
     def load_weights(self, path):
+        import os
+        if str(path).endswith('.h5') and not os.path.exists(str(path)) and os.path.exists(str(path) + '.npz'):
+            path = str(path) + '.npz'          # written by save_weights('x.h5') of this class (numpy container)
         if str(path).endswith('.h5'):
             from .utils.keras_h5 import read_keras_weights
             self.set_weights(read_keras_weights(path, self.machine.weight_specs()))

@@ -113,6 +113,8 @@ class Trainer(object):
         """Keras' train_on_batch under an accumulate-gradient optimizer (accumulate_gradient_optimizer.py:54-82): add this
         mini-batch's gradient to the accumulator; every `update_params_frequency`-th call allreduce (if distributed), step,
         reset.  Returns True when the parameters moved."""
+        if hasattr(self.optimizer, 'compute_update'):
+            return self._stochastic_reconfiguration_step(x, y)
         g = self.gradient(x, y)
         freq = self._frequency()
         if not getattr(self.optimizer, 'accumulate_sum_or_mean', True):
@@ -132,6 +134,21 @@ class Trainer(object):
         if getattr(self.optimizer, 'ema_decay', 0) > 0:
             self.optimizer._machine = self.machine
             self.optimizer.track_ema(params)
+        return True
+
+    def _stochastic_reconfiguration_step(self, x, y):
+        """`model.compile(optimizer=ComplexValuesStochasticReconfiguration(model, ...))` (the reference passes its SR
+        optimizer to Keras like any other, optimizers/stochastic_reconfiguration/optimizer.py:14-31): the optimizer owns
+        the whole update -- per-sample Jacobians, SR system, solve, W <- W - lr * delta -- from the batch (sigma, y_true).
+        SR needs the whole batch at once (the reference asserts the same through its Jacobian shapes)."""
+        if self._frequency() != 1:
+            raise ValueError('stochastic reconfiguration needs mini_batch_size == batch_size (one update per batch)')
+        opt = self.optimizer
+        if hasattr(opt, 'complex_jacobian'):
+            opt.step(x, y)                                   # complex-parameter machines: takes y_true like the reference
+        else:
+            # real-parameter SR is written in terms of the local energies; y_true = conj(E_loc - E) / B carries them
+            opt.step(x, np.conj(np.asarray(y)) * len(y))
         return True
 
     def train_step(self):

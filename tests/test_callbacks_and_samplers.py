@@ -385,3 +385,60 @@ def test_fit_generator_keras_semantics_and_scalar_logger(tmp_path):
     assert len(logs) == 2 and 'energy/energy' in logs[-1]
     lines = [json.loads(l) for l in open(tmp_path / 'tb' / 'scalars.jsonl')]
     assert [l['step'] for l in lines] == [2, 4, 6, 8] and all('energy/energy' in l for l in lines)
+
+
+def test_sr_optimizers_own_the_update_and_terminate_on_nan(tmp_path):
+    """model.compile(optimizer=<SR optimizer>) + fit_generator: the Trainer hands the batch to the optimizer
+    (optimizers/stochastic_reconfiguration/optimizer.py:14-31 is a Keras optimizer in the reference)."""
+    from flowket_b200.callbacks import TerminateOnNaN, Callback
+    calls = []
+
+    class ComplexSR(object):
+        def compute_update(self, sigma, y):
+            raise AssertionError('step() is the entry point')
+
+        def complex_jacobian(self, sigma):
+            pass
+
+        def step(self, sigma, y):
+            calls.append(('complex', np.asarray(y).copy()))
+
+    class RealSR(object):
+        def compute_update(self, sigma, e):
+            pass
+
+        def step(self, sigma, local_energy):
+            calls.append(('real', np.asarray(local_energy).copy()))
+
+    y = np.array([0.5 - 0.25j, -0.5 + 0.25j]) / 2                      # conj(E_loc - E) / B with B = 2
+    for opt in (ComplexSR(), RealSR()):
+        trainer, machine = _stub_trainer(opt, [])
+        assert trainer.train_on_batch(np.zeros((2, 3)), y) is True
+    assert calls[0][0] == 'complex' and np.allclose(calls[0][1], y)
+    assert calls[1][0] == 'real' and np.allclose(calls[1][1], [0.5 + 0.25j, -0.5 - 0.25j])     # E_loc - E recovered
+    trainer, _ = _stub_trainer(RealSR(), [])
+    trainer.generator = types.SimpleNamespace(update_params_frequency=4)
+    with pytest.raises(ValueError, match='mini_batch_size == batch_size'):
+        trainer.train_on_batch(np.zeros((2, 3)), y)
+    # TerminateOnNaN watches the energy entries of the logs
+    model = types.SimpleNamespace(stop_training=False)
+    cb = TerminateOnNaN()
+    cb.set_model(model)
+    cb.on_batch_end(0, {'energy/energy': -3.0})
+    assert not model.stop_training
+    cb.on_epoch_end(0, {'energy/energy': float('nan')})
+    assert model.stop_training and cb.stopped
+
+
+def test_save_weights_with_an_h5_name_round_trips(tmp_path):
+    from flowket_b200 import Input, Model
+    from flowket_b200.machines import ConvNetAutoregressive2D
+    inp = Input(shape=(4, 4))
+    m = ConvNetAutoregressive2D(inp, depth=2, num_of_channels=4, seed=1)
+    model = Model(inp, m.predictions)
+    path = str(tmp_path / 'final_run.h5')                              # the reference scripts save to '<name>.h5'
+    model.save_weights(path)
+    before = [w.copy() for w in model.get_weights()]
+    m.set_weights([w * 0 for w in before])
+    model.load_weights(path)
+    assert all(np.array_equal(a, b) for a, b in zip(before, model.get_weights()))

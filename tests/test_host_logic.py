@@ -196,3 +196,20 @@ def test_obc_ensemble_enumerates_the_dihedral_group():
     assert len(ens.transforms) == 8 and images == want
     assert make_up_down_invariant(inp, ens).ensemble_size == 16
     assert len(make_pbc_invariants(inp, None, apply_also_obc_invariants=False).transforms) == 16
+
+
+def test_flattened_operator_reshapes_only():
+    """FlattenedOperator: a lattice operator for 1-D machines over raster-flattened sites (configs[3])"""
+    from flowket_b200.operators import FlattenedOperator
+    rng = np.random.default_rng(0)
+    lattice = oops.OracleOperator('j1j2', (4, 3), j2=0.5, pbc=False)
+    lattice.use_state = lambda s: s.shape == (4, 3)
+    lattice.random_states = lambda k: rng.choice([-1, 1], size=(k, 4, 3))
+    flat = FlattenedOperator(lattice)
+    assert flat.hilbert_state_shape == (12,) and flat.max_number_of_local_connections == lattice.max_number_of_local_connections
+    sigma = rng.choice([-1, 1], size=(5, 4, 3)).astype(np.float64)
+    conn, mel, use = lattice.find_conn(sigma)
+    fconn, fmel, fuse = flat.find_conn(sigma.reshape(5, 12))
+    assert fconn.shape == conn.shape[:2] + (12,) and np.array_equal(fconn.reshape(conn.shape), conn)
+    assert np.array_equal(fmel, mel) and np.array_equal(fuse, use)
+    assert flat.use_state(sigma[0].reshape(12)) and flat.random_states(7).shape == (7, 12)
