@@ -1,4 +1,4 @@
-// Microbenchmark: cycles per tcgen05.mma (M=128, N, K=16, fp16, SS mode, no-swizzle K-major operands) as a
+// Microbenchmark: cycles per tcgen05.mma (M=128 or 64, N, K=16, fp16, SS mode, no-swizzle K-major operands) as a
 // function of N, to find the operand-fetch floor that bounds the N=32 implicit-GEMM kernels.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/umma_bench tools/umma_bench.cu
 #include <cuda_runtime.h>
@@ -15,7 +15,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
   return ok;
 }
 
-template <int N>
+template <int N, int M = 128>
 __global__ void bench(long long* out, int reps, int distinct_a, int nacc, int nissue) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
@@ -35,7 +35,7 @@ __global__ void bench(long long* out, int reps, int distinct_a, int nacc, int ni
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tm = tmem_slot;
-  const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
   if ((tid & 31) == 0 && (tid >> 5) < nissue) {
     const int w = tid >> 5;
     const uint32_t a_base = smem_u32(smem), b_base = smem_u32(smem + 128 * 1024);
@@ -58,19 +58,19 @@ __global__ void bench(long long* out, int reps, int distinct_a, int nacc, int ni
   if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512u) : "memory");
 }
 
-template <int N>
+template <int N, int M = 128>
 void run(long long* d_out, int grid) {
   const int reps = 4096;
-  cudaFuncSetAttribute(bench<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench<N, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   for (int nissue = 1; nissue <= 4; nissue *= 2) {
     const int distinct = 1, nacc = N <= 64 ? 2 : 1;
-    bench<N><<<grid, 128, 200 * 1024>>>(d_out, reps, distinct, nacc, nissue);
+    bench<N, M><<<grid, 128, 200 * 1024>>>(d_out, reps, distinct, nacc, nissue);
     cudaError_t e = cudaDeviceSynchronize();
     long long h[2];
     cudaMemcpy(h, d_out, sizeof(h), cudaMemcpyDeviceToHost);
-    const double bytes = 128 * 16 * 2 + N * 16 * 2;
-    printf("N=%3d grid=%3d issuers=%2d: issue %.1f cyc/MMA, complete %.1f cyc/MMA, operand %.1f B/cyc, %.0f MAC/cyc/SM  (%s)\n", N, grid,
-           nissue, (double)h[0] / reps / nissue, (double)h[1] / reps / nissue, bytes / ((double)h[1] / reps / nissue), 128.0 * N * 16 / ((double)h[1] / reps / nissue),
+    const double bytes = M * 16 * 2 + N * 16 * 2;
+    printf("M=%3d N=%3d grid=%3d issuers=%2d: issue %.1f cyc/MMA, complete %.1f cyc/MMA, operand %.1f B/cyc, %.0f MAC/cyc/SM  (%s)\n", M, N, grid,
+           nissue, (double)h[0] / reps / nissue, (double)h[1] / reps / nissue, bytes / ((double)h[1] / reps / nissue), (double)M * N * 16 / ((double)h[1] / reps / nissue),
            cudaGetErrorString(e));
   }
 }
@@ -80,6 +80,8 @@ int main() {
   cudaMalloc(&d_out, 16);
   for (int grid : {148}) {
     run<16>(d_out, grid); run<32>(d_out, grid); run<64>(d_out, grid); run<128>(d_out, grid);
+    // M = 64 (row-trimmed forward): does halving the A operand halve its fetch time?
+    run<16, 64>(d_out, grid); run<32, 64>(d_out, grid); run<64, 64>(d_out, grid);
   }
   return 0;
 }
