@@ -154,3 +154,60 @@ def test_sample_space_stochastic_reconfiguration_sharded_matches_single_process(
         assert res['bf16'] < 2e-2, (rank, res)
         assert res['replicated'] == 0.0, (rank, res)
         assert res['shared_cholesky'] < 1e-9 and res['cholesky_solve'] < 1e-10 and res['cholesky_replicated'] == 0.0, (rank, res)
+
+
+class _TableModel(object):
+    """log-amplitude table behind Model.predict / input_shape (host stand-in for the CUDA forward)"""
+
+    def __init__(self, shape, seed=0):
+        from flowket_b200.exact.utils import vector_to_machine
+        n = int(np.prod(shape))
+        rng = np.random.default_rng(seed)
+        self.vector = rng.normal(scale=0.5, size=2 ** n) + 1j * rng.uniform(-3, 3, size=2 ** n)
+        self._f = vector_to_machine(self.vector)
+        self.input_shape = (None,) + tuple(shape)
+
+    def predict(self, x, batch_size=None):
+        return self._f(np.asarray(x))
+
+
+def _exact_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from flowket_b200.optimization import ExactVariational, DistributedExactVariational
+    from oracle import operators as oops
+    shape = (3, 2)
+    model = _TableModel(shape, seed=4)
+    op = oops.OracleOperator('heisenberg', shape, pbc=False)
+    whole = ExactVariational(model, op, 16)
+    whole.machine_updated()
+    mine = DistributedExactVariational(model, op, 16)
+    assert (mine.slice_hi - mine.slice_lo) * world == 64 and mine.num_of_batch_until_full_cycle == 64 // world // 16
+    gen = mine.to_generator()
+    xs, ys = zip(*[next(gen) for _ in range(mine.num_of_batch_until_full_cycle)])
+    lo, hi = mine.slice_lo, mine.slice_hi
+    res = {
+        'energy': abs(mine.energy_observable.current_energy - whole.energy_observable.current_energy),
+        'variance': abs(mine.energy_observable.current_local_energy_variance - whole.energy_observable.current_local_energy_variance),
+        'probs': float(np.abs(mine.probs - whole.probs).max()),
+        'states': bool(np.array_equal(np.concatenate(xs), whole.states[lo:hi])),
+        'coefficients': float(np.abs(np.concatenate(ys) - whole.energy_grad_coefficients[lo:hi]).max()),
+        'tables': mine.energy_observable.states_idx_local_connections.shape[1],
+    }
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+def test_exact_variational_sharded_over_two_ranks_matches_the_whole_enumeration():
+    """the 2^N states shard over the ranks; energy, variance, probabilities and the gradient coefficients of each
+    slice equal those of the single-process enumeration, and the connection tables shrink by the number of ranks"""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_exact_worker, args=(world, 29659, out), nprocs=world, join=True)
+    for rank in range(world):
+        res = out[rank]
+        assert res['energy'] < 1e-12 and res['variance'] < 1e-10 and res['probs'] < 1e-15, (rank, res)
+        assert res['states'] and res['coefficients'] < 1e-13 and res['tables'] == 32, (rank, res)

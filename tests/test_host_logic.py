@@ -213,3 +213,22 @@ def test_flattened_operator_reshapes_only():
     assert fconn.shape == conn.shape[:2] + (12,) and np.array_equal(fconn.reshape(conn.shape), conn)
     assert np.array_equal(fmel, mel) and np.array_equal(fuse, use)
     assert flat.use_state(sigma[0].reshape(12)) and flat.random_states(7).shape == (7, 12)
+
+
+def test_distributed_exact_variational_degenerates_to_the_single_process_class():
+    from flowket_b200.exact.utils import vector_to_machine
+    from flowket_b200.optimization import ExactVariational, DistributedExactVariational
+    import types
+    rng = np.random.default_rng(2)
+    vec = rng.normal(scale=0.5, size=32) + 1j * rng.uniform(-3, 3, size=32)
+    f = vector_to_machine(vec)
+    model = types.SimpleNamespace(input_shape=(None, 5), predict=lambda x, batch_size=None: f(np.asarray(x)))
+    op = oops.OracleOperator('ising', (5,), h=0.7, pbc=True)
+    a, b = ExactVariational(model, op, 8), DistributedExactVariational(model, op, 8)
+    a.machine_updated()
+    b.machine_updated()
+    assert b.world_size == 1 and (b.slice_lo, b.slice_hi) == (0, 32)
+    assert abs(a.energy_observable.current_energy - b.energy_observable.current_energy) < 1e-13
+    assert np.allclose(a.energy_grad_coefficients, b.energy_grad_coefficients, atol=1e-14)
+    with pytest.raises(Exception, match='must divide'):
+        DistributedExactVariational(model, op, 5)
