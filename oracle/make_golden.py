@@ -113,8 +113,46 @@ def main():
     print('wrote', os.path.join(OUT, 'reference_numpy_half.npz'), len(out), 'arrays')
 
 
+EDGE_CASES = [
+    # degenerate lattices: two-site periodic dimensions (both bonds of a pair exist), singleton dimensions, tiny chains
+    ('heis_2x2_pbc', 'Heisenberg', dict(hilbert_state_shape=[2, 2], pbc=True)),
+    ('heis_1x6_obc', 'Heisenberg', dict(hilbert_state_shape=[1, 6], pbc=False)),
+    ('heis_6x1_pbc', 'Heisenberg', dict(hilbert_state_shape=[6, 1], pbc=True)),
+    ('heis_2_pbc', 'Heisenberg', dict(hilbert_state_shape=[2], pbc=True)),
+    ('heis_3x2_pbc_norot', 'Heisenberg', dict(hilbert_state_shape=[3, 2], pbc=True, unitary_rotation=False)),
+    ('heis_2x5_pbc', 'Heisenberg', dict(hilbert_state_shape=[2, 5], pbc=True)),
+    ('ising_2x3_pbc', 'Ising', dict(hilbert_state_shape=[2, 3], pbc=True, h=0.5, j=1.0)),
+    ('ising_1x4_pbc', 'Ising', dict(hilbert_state_shape=[1, 4], pbc=True, h=1.0)),
+    ('ising_2_pbc', 'Ising', dict(hilbert_state_shape=[2], pbc=True, h=1.0)),
+    ('ising_2x2_obc', 'Ising', dict(hilbert_state_shape=[2, 2], pbc=False, h=2.0, j=0.5)),
+]
+
+
+def edge_cases():
+    """tests/golden/reference_numpy_half_edge.npz: find_conn of the reference on degenerate lattices, ALL 2^N states of
+    each (they are tiny), so that every boundary branch of operators/heisenberg.py:96-120 and ising.py:19-41 is pinned."""
+    ops, mc, ex = load_reference()
+    out = {}
+    for name, cls, kw in EDGE_CASES:
+        shape = tuple(kw['hilbert_state_shape'])
+        n = int(np.prod(shape))
+        sigma = ex.decimal_array_to_binary_array(np.arange(2 ** n), n, False).reshape((2 ** n,) + shape).astype(np.int8)
+        op = getattr(ops, cls)(**kw)
+        conn, mel, use = op.find_conn(sigma.astype(np.float64) if cls == 'Heisenberg' else sigma.astype(np.int64))
+        out[name + '/sigma'] = sigma
+        out[name + '/conn'] = np.array(conn).astype(np.int8).reshape((len(conn), 2 ** n) + shape)
+        out[name + '/mel'] = np.array(mel, np.float64)
+        out[name + '/use'] = np.array(use, bool)
+        out[name + '/max_conn'] = np.int64(op.max_number_of_local_connections)
+    path = os.path.join(OUT, 'reference_numpy_half_edge.npz')
+    np.savez_compressed(path, **out)
+    print('wrote', path, len(out), 'arrays')
+
+
 if __name__ == '__main__' and len(sys.argv) == 1:
     main()
+if __name__ == '__main__' and sys.argv[1:] == ['edge']:
+    edge_cases()
 
 
 PRETRAINED = {'2': 'ising_2.h5', '2_5': 'ising_2_5.h5', '3': 'ising_3.h5', '3_5': 'ising_3_5.h5', '4': 'ising_4.h5'}

@@ -16,3 +16,9 @@ def pytest_configure(config):
 @pytest.fixture(scope='session')
 def golden():
     return np.load(os.path.join(ROOT, 'tests', 'golden', 'reference_numpy_half.npz'))
+
+
+@pytest.fixture(scope='session')
+def golden_edge():
+    """degenerate lattices (oracle/make_golden.py edge): find_conn of the reference over ALL states"""
+    return np.load(os.path.join(ROOT, 'tests', 'golden', 'reference_numpy_half_edge.npz'))

@@ -1,0 +1,56 @@
+"""GPU tier, degenerate lattices (runs last): the device find_conn against the reference's own output over ALL states of
+two-site periodic / singleton-dimension lattices (tests/golden/reference_numpy_half_edge.npz, oracle/make_golden.py edge),
+and the local energy of tiny machines on them against the oracle."""
+import numpy as np
+import pytest
+
+from oracle import local_energy as oeloc
+from oracle import nets, operators as oops
+from tests.helpers import make_pair
+
+pytestmark = pytest.mark.gpu
+
+EDGE = {
+    'heis_2x2_pbc': ('Heisenberg', dict(hilbert_state_shape=[2, 2], pbc=True)),
+    'heis_1x6_obc': ('Heisenberg', dict(hilbert_state_shape=[1, 6], pbc=False)),
+    'heis_6x1_pbc': ('Heisenberg', dict(hilbert_state_shape=[6, 1], pbc=True)),
+    'heis_2_pbc': ('Heisenberg', dict(hilbert_state_shape=[2], pbc=True)),
+    'heis_3x2_pbc_norot': ('Heisenberg', dict(hilbert_state_shape=[3, 2], pbc=True, unitary_rotation=False)),
+    'heis_2x5_pbc': ('Heisenberg', dict(hilbert_state_shape=[2, 5], pbc=True)),
+    'ising_2x3_pbc': ('Ising', dict(hilbert_state_shape=[2, 3], pbc=True, h=0.5, j=1.0)),
+    'ising_1x4_pbc': ('Ising', dict(hilbert_state_shape=[1, 4], pbc=True, h=1.0)),
+    'ising_2_pbc': ('Ising', dict(hilbert_state_shape=[2], pbc=True, h=1.0)),
+    'ising_2x2_obc': ('Ising', dict(hilbert_state_shape=[2, 2], pbc=False, h=2.0, j=0.5)),
+}
+
+
+@pytest.mark.parametrize('name', sorted(EDGE))
+def test_device_find_conn_on_degenerate_lattices(golden_edge, name):
+    import flowket_b200.operators as ops
+    cls, kw = EDGE[name]
+    op = getattr(ops, cls)(**kw)
+    conn, mel, use = op.find_conn(golden_edge[name + '/sigma'])
+    assert op.max_number_of_local_connections == int(golden_edge[name + '/max_conn'])
+    assert np.array_equal(conn.astype(np.int8), golden_edge[name + '/conn'])
+    assert np.array_equal(use, golden_edge[name + '/use'])
+    assert np.allclose(mel, golden_edge[name + '/mel'], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize('kind,shape,opkind,opkw', [
+    ('conv2d', (2, 2), 'heisenberg', dict(pbc=True)),
+    ('conv2d', (2, 5), 'heisenberg', dict(pbc=True)),
+    ('conv1d', (2,), 'ising', dict(pbc=True, h=1.0)),
+    ('conv2d', (1, 4), 'ising', dict(pbc=True, h=1.0)),
+])
+def test_local_energy_on_degenerate_lattices(kind, shape, opkind, opkw):
+    """every state of the lattice: E_loc from the device pipeline == oracle (fp32 engine, 1e-5)"""
+    from flowket_b200.exact.utils import decimal_array_to_binary_array
+    from flowket_b200.observables.monte_carlo import Observable
+    from tests.test_gpu_parity import _product_operator
+    model, _, spec, params = make_pair(kind, shape, 3, 8, seed=21)
+    n = int(np.prod(shape))
+    sigma = decimal_array_to_binary_array(np.arange(2 ** n), n, False).reshape((2 ** n,) + shape).astype(np.int8)
+    got = Observable(_product_operator(opkind, shape, opkw)).local_values_device(model, sigma).cpu().numpy()
+    want = oeloc.local_values(oops.OracleOperator(opkind, shape, **opkw), lambda c: nets.log_psi_numpy(spec, params, c),
+                              sigma.astype(np.float64))
+    assert np.abs(got - want).max() / np.abs(want).max() < 1e-5

@@ -58,7 +58,18 @@ def test_operator_term_tables_match_oracle_on_host():
              (ops.Heisenberg(hilbert_state_shape=[7], pbc=True), 'heisenberg', (7,), dict(pbc=True)),
              (ops.Ising(hilbert_state_shape=[3, 5], pbc=True, h=0.5), 'ising', (3, 5), dict(pbc=True, h=0.5)),
              (ops.Ising(hilbert_state_shape=[9], pbc=False, h=3.0), 'ising', (9,), dict(pbc=False, h=3.0)),
-             (ops.J1J2((4, 4), j2=0.5), 'j1j2', (4, 4), dict(j2=0.5))]
+             (ops.J1J2((4, 4), j2=0.5), 'j1j2', (4, 4), dict(j2=0.5)),
+             # degenerate lattices (pinned against the reference in tests/golden/reference_numpy_half_edge.npz)
+             (ops.Heisenberg(hilbert_state_shape=[2, 2], pbc=True), 'heisenberg', (2, 2), dict(pbc=True)),
+             (ops.Heisenberg(hilbert_state_shape=[1, 6], pbc=False), 'heisenberg', (1, 6), dict(pbc=False)),
+             (ops.Heisenberg(hilbert_state_shape=[6, 1], pbc=True), 'heisenberg', (6, 1), dict(pbc=True)),
+             (ops.Heisenberg(hilbert_state_shape=[2], pbc=True), 'heisenberg', (2,), dict(pbc=True)),
+             (ops.Heisenberg(hilbert_state_shape=[2, 5], pbc=True), 'heisenberg', (2, 5), dict(pbc=True)),
+             (ops.Ising(hilbert_state_shape=[2, 3], pbc=True, h=0.5), 'ising', (2, 3), dict(pbc=True, h=0.5)),
+             (ops.Ising(hilbert_state_shape=[1, 4], pbc=True, h=1.0), 'ising', (1, 4), dict(pbc=True, h=1.0)),
+             (ops.Ising(hilbert_state_shape=[2], pbc=True, h=1.0), 'ising', (2,), dict(pbc=True, h=1.0)),
+             (ops.J1J2((2, 3), j2=0.3), 'j1j2', (2, 3), dict(j2=0.3)),
+             (ops.J1J2((3, 3), j2=0.5, pbc=True), 'j1j2', (3, 3), dict(j2=0.5, pbc=True))]
     for op, kind, shape, kw in cases:
         terms, kind_id, compact, _ = op.terms()
         sigma = rng.choice([-1, 1], size=(5,) + shape)
