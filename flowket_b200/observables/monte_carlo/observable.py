@@ -1,24 +1,22 @@
-"""flowket/observables/monte_carlo/observable.py:5-23 (same protocol)."""
-import abc
-
+"""Observable protocol of flowket/observables/monte_carlo/observable.py:5-23: `local_values(psi, configurations)` gives one
+(complex) value per configuration; `estimate` adds the Monte-Carlo mean and the variance of the real part -- the triple
+VariationalMonteCarlo and the stats callbacks consume."""
 import numpy
 
 
-class BaseObservable(abc.ABC):
-    @abc.abstractmethod
+class BaseObservable(object):
     def local_values(self, wave_function, configurations):
-        pass
+        raise NotImplementedError
 
     def estimate(self, wave_function, configurations):
-        local_values = self.local_values(wave_function, configurations)
-        mean_value = numpy.mean(local_values)
-        variance = numpy.var(numpy.real(local_values))
-        return mean_value, variance, local_values
+        values = numpy.asarray(self.local_values(wave_function, configurations))
+        return values.mean(), numpy.real(values).var(), values
 
 
 class LambdaObservable(BaseObservable):
+    """observable given as a function (psi, configurations) -> per-configuration values (SigmaZ, AbsSigmaZ)"""
+
     def __init__(self, observable_function):
-        super(LambdaObservable, self).__init__()
         self.observable_function = observable_function
 
     def local_values(self, wave_function, configurations):

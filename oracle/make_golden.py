@@ -149,8 +149,59 @@ def edge_cases():
     print('wrote', path, len(out), 'arrays')
 
 
+def mcmc_diagnostics():
+    """tests/golden/reference_mcmc_diagnostics.npz: MetropolisHastingsSampler.calc_r_hat_value of the reference
+    (samplers/metropolis_hastings.py:66-91 -- numpy only, loaded through stub parent packages) on fixed inputs."""
+    import contextlib
+    import io
+
+    def stub(name, path):
+        m = types.ModuleType(name)
+        m.__path__ = [path]
+        sys.modules[name] = m
+    stub('flowket', REF)
+    stub('flowket.deepar', REF + '/deepar')
+    stub('flowket.deepar.samplers', REF + '/deepar/samplers')
+    stub('flowket.samplers', REF + '/samplers')
+    mh = importlib.import_module('flowket.samplers.metropolis_hastings')
+    if not hasattr(np, 'bool'):
+        np.bool = bool                       # alias the reference still uses (removed in numpy 1.24)
+
+    class Machine(object):
+        input_shape = (None, 4)
+
+        def predict(self, x, batch_size=None):
+            return np.zeros((len(x), 1), np.complex128)
+
+    rng = np.random.default_rng(20261017)
+    out = {}
+    for name, chains, per_chain in [('iid', 8, 200), ('ar1', 4, 300), ('stuck', 6, 50), ('short', 16, 2), ('single', 8, 1)]:
+        if name == 'ar1':
+            v = np.zeros((chains, per_chain))
+            noise = rng.normal(size=(chains, per_chain))
+            for t in range(1, per_chain):
+                v[:, t] = 0.8 * v[:, t - 1] + noise[:, t]
+        elif name == 'stuck':
+            v = np.arange(chains)[:, None] + 0.01 * rng.normal(size=(chains, per_chain))
+        else:
+            v = rng.normal(size=(chains, per_chain))
+        with contextlib.redirect_stdout(io.StringIO()):
+            sampler = mh.MetropolisHastingsLocal(Machine(), chains * per_chain, num_of_chains=chains)
+            res = sampler.calc_r_hat_value(v.reshape(-1).copy())
+        out[name + '/values'] = v.reshape(-1)
+        out[name + '/chains'] = np.int64(chains)
+        out[name + '/result'] = np.array([float(x) for x in res])
+    out['sum_correlations/input'] = rng.normal(size=12) * 0.4
+    out['sum_correlations/result'] = np.float64(mh.sum_correlations(out['sum_correlations/input']))
+    path = os.path.join(OUT, 'reference_mcmc_diagnostics.npz')
+    np.savez_compressed(path, **out)
+    print('wrote', path, len(out), 'arrays')
+
+
 if __name__ == '__main__' and len(sys.argv) == 1:
     main()
+if __name__ == '__main__' and sys.argv[1:] == ['mcmc']:
+    mcmc_diagnostics()
 if __name__ == '__main__' and sys.argv[1:] == ['edge']:
     edge_cases()
 

@@ -442,3 +442,17 @@ def test_save_weights_with_an_h5_name_round_trips(tmp_path):
     m.set_weights([w * 0 for w in before])
     model.load_weights(path)
     assert all(np.array_equal(a, b) for a, b in zip(before, model.get_weights()))
+
+
+@pytest.mark.parametrize('name', ['iid', 'ar1', 'stuck', 'short', 'single'])
+def test_r_hat_matches_the_reference_implementation(name):
+    """golden: MetropolisHastingsSampler.calc_r_hat_value of the reference itself (oracle/make_golden.py mcmc)"""
+    import os
+    from flowket_b200.samplers import MetropolisHastingsLocal
+    from flowket_b200.samplers.metropolis_hastings import sum_correlations
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_mcmc_diagnostics.npz'))
+    values, chains = g[name + '/values'], int(g[name + '/chains'])
+    sampler = MetropolisHastingsLocal(TableMachine((4,)), len(values), num_of_chains=chains, seed=0)
+    got = np.array([float(x) for x in sampler.calc_r_hat_value(values)])
+    assert np.allclose(got, g[name + '/result'], rtol=1e-12, atol=1e-12, equal_nan=True), (got, g[name + '/result'])
+    assert sum_correlations(g['sum_correlations/input']) == pytest.approx(float(g['sum_correlations/result']), rel=1e-13)
