@@ -198,8 +198,45 @@ def mcmc_diagnostics():
     print('wrote', path, len(out), 'arrays')
 
 
+def j1j2_graph():
+    """tests/golden/reference_j1j2_graph.npz: the coloured edge list and the bond operators the reference hands to netket
+    (operators/j1j2.py:7-55), captured by running the reference's own builder against a *recording stand-in* for the
+    netket package (netket itself is not installed; its internal connection ordering stays unpinned -- this pins everything
+    FlowKet itself decides: which bonds exist, their colours and order, J1 / J2 and the two-site operator)."""
+    class Recorder(object):
+        def __init__(self, *args, **kwargs):
+            self.args, self.kwargs = args, kwargs
+
+    fake = types.ModuleType('netket')
+    fake.graph = types.SimpleNamespace(CustomGraph=Recorder)
+    fake.hilbert = types.SimpleNamespace(Spin=Recorder)
+    fake.operator = types.SimpleNamespace(GraphOperator=Recorder)
+    sys.modules['netket'] = fake
+    m = types.ModuleType('flowket')
+    m.__path__ = [REF]
+    sys.modules['flowket'] = m
+    j1j2 = importlib.import_module('flowket.operators.j1j2')
+    out = {}
+    for L1, L2, j2, pbc in [(4, 4, 0.5, False), (6, 6, 0.5, False), (4, 4, 0.5, True), (2, 3, 0.3, False), (3, 3, 0.5, True),
+                            (3, 5, 0.25, False)]:
+        op = j1j2.j1j2_two_dim_netket_operator((L1, L2), j2=j2, pbc=pbc)
+        hilbert = op.args[0]
+        graph = hilbert.kwargs['graph']
+        key = '%dx%d_%s_j2_%g' % (L1, L2, 'pbc' if pbc else 'obc', j2)
+        out[key + '/edges'] = np.array(graph.args[0], dtype=np.int64)                       # [n_edges, 3] = (a, b, colour)
+        out[key + '/bondops'] = np.array(op.kwargs['bondops'], dtype=np.complex128)         # [2, 4, 4]
+        out[key + '/bondops_colors'] = np.array(op.kwargs['bondops_colors'], dtype=np.int64)
+        out[key + '/total_sz_constrained'] = np.bool_('total_sz' in hilbert.kwargs)
+    path = os.path.join(OUT, 'reference_j1j2_graph.npz')
+    np.savez_compressed(path, **out)
+    print('wrote', path, len(out), 'arrays')
+    del sys.modules['netket']
+
+
 if __name__ == '__main__' and len(sys.argv) == 1:
     main()
+if __name__ == '__main__' and sys.argv[1:] == ['j1j2']:
+    j1j2_graph()
 if __name__ == '__main__' and sys.argv[1:] == ['mcmc']:
     mcmc_diagnostics()
 if __name__ == '__main__' and sys.argv[1:] == ['edge']:
