@@ -233,8 +233,133 @@ def j1j2_graph():
     del sys.modules['netket']
 
 
+def exact_variational():
+    """tests/golden/reference_exact_variational.npz: the reference's own ExactVariational / ExactObservable
+    (optimization/exact_variational.py:10-161) run on a log-amplitude table.  The module imports tensorflow only for
+    `K.function` (the wave-function callable) and the default-graph guard; a minimal stand-in for those two lets the numpy
+    logic -- normalisation, probabilities, local energies over all states, gradient coefficients -- run unmodified."""
+    import contextlib
+
+    class Graph(object):
+        def as_default(self):
+            return contextlib.nullcontext()
+
+    backend = types.ModuleType('tensorflow.keras.backend')
+    backend.function = lambda inputs, outputs: (lambda xs: [outputs[0](xs[0])])
+    keras = types.ModuleType('tensorflow.keras')
+    keras.backend = backend
+    tf = types.ModuleType('tensorflow')
+    tf.keras = keras
+    tf.get_default_graph = lambda: Graph()
+    sys.modules.update({'tensorflow': tf, 'tensorflow.keras': keras, 'tensorflow.keras.backend': backend})
+    ops, mc, ex = load_reference()
+    m = types.ModuleType('flowket.optimization')
+    m.__path__ = [REF + '/optimization']
+    sys.modules['flowket.optimization'] = m
+    ev_mod = importlib.import_module('flowket.optimization.exact_variational')
+    rng = np.random.default_rng(20261017)
+    out = {}
+    for name, make, shape, batch in [
+        ('heis_2x3_obc', lambda: ops.Heisenberg(hilbert_state_shape=[2, 3], pbc=False), (2, 3), 16),
+        ('ising_3x3_obc', lambda: ops.Ising(hilbert_state_shape=[3, 3], pbc=False, h=3.0), (3, 3), 128),
+        ('ising_1d8_pbc', lambda: ops.Ising(hilbert_state_shape=[8], pbc=True, h=0.7), (8,), 256),
+    ]:
+        n = int(np.prod(shape))
+        vec = rng.normal(size=2 ** n) * 0.6 + 1j * rng.uniform(-np.pi, np.pi, size=2 ** n)
+        table = ex.vector_to_machine(vec)
+        model = types.SimpleNamespace(input=None, output=lambda x: table(x), input_shape=(None,) + shape)
+        ev = ev_mod.ExactVariational(model, make(), batch)
+        ev.machine_updated()
+        out[name + '/log_psi_vector'] = vec
+        out[name + '/batch_size'] = np.int64(batch)
+        out[name + '/probs'] = ev.probs.copy()
+        out[name + '/energies'] = ev.energy_observable.energies.copy()
+        out[name + '/energy_grad_coefficients'] = ev.energy_grad_coefficients.copy()
+        out[name + '/current_energy'] = np.complex128(ev.energy_observable.current_energy)
+        out[name + '/current_local_energy_variance'] = np.float64(ev.energy_observable.current_local_energy_variance)
+        out[name + '/num_of_batch_until_full_cycle'] = np.int64(ev.num_of_batch_until_full_cycle)
+    path = os.path.join(OUT, 'reference_exact_variational.npz')
+    np.savez_compressed(path, **out)
+    print('wrote', path, len(out), 'arrays')
+    for k in ('tensorflow', 'tensorflow.keras', 'tensorflow.keras.backend'):
+        del sys.modules[k]
+
+
+def variational_monte_carlo():
+    """tests/golden/reference_variational_monte_carlo.npz: the reference's own VariationalMonteCarlo + MiniBatchGenerator
+    (optimization/variational_monte_carlo.py:12-50, mini_batch_generator.py:5-45) driven by a scripted sampler and a
+    log-amplitude table; tensorflow is replaced by a stand-in for the session / graph guards it only passes through."""
+    import contextlib
+
+    class Graph(object):
+        def as_default(self):
+            return contextlib.nullcontext()
+
+    backend = types.ModuleType('tensorflow.python.keras.backend')
+    backend.get_session = lambda: None
+    backend.set_session = lambda session: None
+    tf = types.ModuleType('tensorflow')
+    tf.get_default_graph = lambda: Graph()
+    tf_python = types.ModuleType('tensorflow.python')
+    tf_python_keras = types.ModuleType('tensorflow.python.keras')
+    tf_python_keras.backend = backend
+    tf_python.keras = tf_python_keras
+    tf.python = tf_python
+    sys.modules.update({'tensorflow': tf, 'tensorflow.python': tf_python, 'tensorflow.python.keras': tf_python_keras,
+                        'tensorflow.python.keras.backend': backend})
+    ops, mc, ex = load_reference()
+    m = types.ModuleType('flowket.optimization')
+    m.__path__ = [REF + '/optimization']
+    sys.modules['flowket.optimization'] = m
+    vmc_mod = importlib.import_module('flowket.optimization.variational_monte_carlo')
+    rng = np.random.default_rng(20261018)
+    shape = (3, 4)
+    n = 12
+    vec = rng.normal(size=2 ** n) * 0.4 + 1j * rng.uniform(-np.pi, np.pi, size=2 ** n)
+    table = ex.vector_to_machine(vec)
+    batches = rng.choice([-1, 1], size=(3, 10) + shape).astype(np.float64)
+
+    class ScriptedSampler(object):
+        batch_size = 10
+
+        def __init__(self):
+            self.i = -1
+
+        def __next__(self):
+            self.i += 1
+            return batches[self.i % len(batches)]
+
+    model = types.SimpleNamespace(predict=lambda x, batch_size=None: table(x))
+    vmc = vmc_mod.VariationalMonteCarlo(model, ops.Heisenberg(hilbert_state_shape=list(shape), pbc=False), ScriptedSampler(),
+                                        mini_batch_size=4)
+    out = {'log_psi_vector': vec, 'batches': batches.astype(np.int8),
+           'update_params_frequency': np.int64(vmc.update_params_frequency)}
+    xs, ys, energies, variances = [], [], [], []
+    for step in range(7):                       # 10 samples in windows of 4: two windows per batch, the tail of 2 is dropped
+        x, y = next(vmc)
+        xs.append(np.asarray(x).astype(np.int8))
+        ys.append(np.asarray(y, np.complex128))
+        energies.append(np.complex128(vmc.current_energy))
+        variances.append(np.float64(vmc.current_local_energy_variance))
+    out['mini_batches_x'] = np.stack(xs)
+    out['mini_batches_y'] = np.stack(ys)
+    out['energies'] = np.array(energies)
+    out['variances'] = np.array(variances)
+    out['last_local_energy'] = np.asarray(vmc.current_local_energy, np.complex128)
+    out['batches_drawn'] = np.int64(vmc.sampler.i + 1)
+    path = os.path.join(OUT, 'reference_variational_monte_carlo.npz')
+    np.savez_compressed(path, **out)
+    print('wrote', path, len(out), 'arrays')
+    for k in ('tensorflow', 'tensorflow.python', 'tensorflow.python.keras', 'tensorflow.python.keras.backend'):
+        del sys.modules[k]
+
+
 if __name__ == '__main__' and len(sys.argv) == 1:
     main()
+if __name__ == '__main__' and sys.argv[1:] == ['vmc']:
+    variational_monte_carlo()
+if __name__ == '__main__' and sys.argv[1:] == ['exact']:
+    exact_variational()
 if __name__ == '__main__' and sys.argv[1:] == ['j1j2']:
     j1j2_graph()
 if __name__ == '__main__' and sys.argv[1:] == ['mcmc']:

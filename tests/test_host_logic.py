@@ -243,3 +243,74 @@ def test_distributed_exact_variational_degenerates_to_the_single_process_class()
     assert np.allclose(a.energy_grad_coefficients, b.energy_grad_coefficients, atol=1e-14)
     with pytest.raises(Exception, match='must divide'):
         DistributedExactVariational(model, op, 5)
+
+
+@pytest.mark.parametrize('name,opkind,shape,opkw', [
+    ('heis_2x3_obc', 'heisenberg', (2, 3), dict(pbc=False)),
+    ('ising_3x3_obc', 'ising', (3, 3), dict(pbc=False, h=3.0)),
+    ('ising_1d8_pbc', 'ising', (8,), dict(pbc=True, h=0.7)),
+])
+def test_exact_variational_matches_the_reference_class(name, opkind, shape, opkw):
+    """golden (oracle/make_golden.py exact): the reference's own ExactVariational / ExactObservable run on a log-amplitude
+    table; this repository's class (and the oracle's) must reproduce probabilities, per-state energies, <H>, the variance and
+    the gradient coefficients."""
+    import os
+    import types
+    from flowket_b200.exact.utils import vector_to_machine
+    from flowket_b200.optimization import ExactVariational
+    from oracle import exact as oexact
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_exact_variational.npz'))
+    vec = g[name + '/log_psi_vector']
+    f = vector_to_machine(vec)
+    model = types.SimpleNamespace(input_shape=(None,) + shape, predict=lambda x, batch_size=None: f(np.asarray(x)))
+    op = oops.OracleOperator(opkind, shape, **opkw)
+    ev = ExactVariational(model, op, int(g[name + '/batch_size']))
+    ev.machine_updated()
+    assert ev.num_of_batch_until_full_cycle == int(g[name + '/num_of_batch_until_full_cycle'])
+    assert np.allclose(ev.probs, g[name + '/probs'], rtol=1e-12, atol=1e-15)
+    assert np.allclose(ev.energy_observable.energies, g[name + '/energies'], rtol=1e-11, atol=1e-13)
+    assert np.allclose(ev.energy_grad_coefficients, g[name + '/energy_grad_coefficients'], rtol=1e-10, atol=1e-13)
+    assert ev.energy_observable.current_energy == pytest.approx(complex(g[name + '/current_energy']), rel=1e-12)
+    assert ev.energy_observable.current_local_energy_variance == pytest.approx(
+        float(g[name + '/current_local_energy_variance']), rel=1e-10)
+    oev = oexact.ExactVariationalOracle(lambda s: f(np.asarray(s))[:, 0], op, shape, int(g[name + '/batch_size']))
+    oev.machine_updated()
+    assert oev.current_energy == pytest.approx(complex(g[name + '/current_energy']), rel=1e-12)
+    assert np.allclose(oev.probs, g[name + '/probs'], rtol=1e-12, atol=1e-15)
+
+
+def test_variational_monte_carlo_matches_the_reference_class():
+    """golden (oracle/make_golden.py vmc): the reference's own VariationalMonteCarlo + MiniBatchGenerator driven by a scripted
+    sampler and a log-amplitude table -- mini-batch windows, dropped tail, loss coefficients, energy and variance per batch.
+    This repository's class runs the host observable route here (no device sampler); on the GPU the same quantities come
+    from the device route (tests/test_gpu_vmc.py)."""
+    import os
+    import types
+    from flowket_b200.exact.utils import vector_to_machine
+    from flowket_b200.optimization import VariationalMonteCarlo
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_variational_monte_carlo.npz'))
+    f = vector_to_machine(g['log_psi_vector'])
+    batches = g['batches'].astype(np.float64)
+
+    class ScriptedSampler(object):
+        batch_size = 10
+
+        def __init__(self):
+            self.i = -1
+
+        def __next__(self):
+            self.i += 1
+            return batches[self.i % len(batches)]
+
+    model = types.SimpleNamespace(predict=lambda x, batch_size=None: f(np.asarray(x)))
+    sampler = ScriptedSampler()
+    vmc = VariationalMonteCarlo(model, oops.OracleOperator('heisenberg', (3, 4), pbc=False), sampler, mini_batch_size=4)
+    assert vmc.update_params_frequency == int(g['update_params_frequency'])
+    for step in range(len(g['energies'])):
+        x, y = next(vmc)
+        assert np.array_equal(np.asarray(x).astype(np.int8), g['mini_batches_x'][step]), step
+        assert np.allclose(y, g['mini_batches_y'][step], rtol=1e-6, atol=1e-9), step      # ratios are complex64 in both
+        assert vmc.current_energy == pytest.approx(complex(g['energies'][step]), rel=1e-6)
+        assert vmc.current_local_energy_variance == pytest.approx(float(g['variances'][step]), rel=1e-5)
+    assert np.allclose(vmc.current_local_energy, g['last_local_energy'], rtol=1e-6)
+    assert sampler.i + 1 == int(g['batches_drawn'])
