@@ -354,8 +354,158 @@ def variational_monte_carlo():
         del sys.modules[k]
 
 
+class ScriptedGenerator(object):
+    """what VariationalMonteCarlo publishes after a batch (optimization/variational_monte_carlo.py:36-50), scripted:
+    energies follow a fixed list, the batch is fixed, the time stamps are fixed offsets (shared with the tests)"""
+
+    def __init__(self, energies, batch):
+        self.energies, self.i = list(energies), -1
+        self.current_batch = np.asarray(batch, dtype=np.float64)
+        self.wave_function = lambda x: np.zeros((len(x), 1), np.complex64)
+        self.sampler = None
+
+    def __next__(self):
+        self.i += 1
+        e = self.energies[self.i % len(self.energies)]
+        self.current_energy = complex(e, 0.125)
+        self.current_local_energy_variance = 0.5 * abs(e)
+        self.current_local_energy = np.full(8, e, np.complex128)
+        self.start_time, self.sampling_end_time, self.local_energy_end_time = 100.0, 101.0, 102.5
+        return self.current_batch, np.zeros(len(self.current_batch))
+
+
+SCRIPT_BATCH = [[1, 1, -1, -1, 1, -1], [1, 1, 1, -1, 1, 1], [-1, -1, -1, -1, 1, -1]]
+TIME_KEYS = ('times/gradients', 'times/total')     # depend on the wall clock at the moment of the call
+
+
+def callbacks_logs():
+    """tests/golden/reference_callbacks_logs.json: the `logs` dicts the reference's own stats callbacks and `evaluate` /
+    `exact_evaluate` produce for a scripted generator and for an ExactVariational over a log-amplitude table
+    (callbacks/monte_carlo/*.py, callbacks/exact/*.py, evaluation/evaluate.py); keras' Callback base class and the
+    tensorflow guards are replaced by minimal stand-ins, everything else is the reference's code."""
+    import contextlib
+    import json
+
+    class Callback(object):
+        def __init__(self, **kwargs):
+            self.model = None
+
+        def on_batch_end(self, batch, logs=None):
+            pass
+
+        def on_epoch_end(self, epoch, logs=None):
+            pass
+
+    class Graph(object):
+        def as_default(self):
+            return contextlib.nullcontext()
+
+    def module(name, **attrs):
+        mod = types.ModuleType(name)
+        mod.__dict__.update(attrs)
+        sys.modules[name] = mod
+        return mod
+    backend = module('tensorflow.keras.backend', function=lambda inputs, outputs: (lambda xs: [outputs[0](xs[0])]))
+    cbs = module('tensorflow.keras.callbacks', Callback=Callback)
+    keras = module('tensorflow.keras', backend=backend, callbacks=cbs)
+    module('tensorflow', keras=keras, get_default_graph=lambda: Graph())
+    ops, mc, ex = load_reference()
+    for name in ('optimization', 'callbacks', 'callbacks/monte_carlo', 'callbacks/exact', 'evaluation'):
+        pkg = types.ModuleType('flowket.' + name.replace('/', '.'))
+        pkg.__path__ = [REF + '/' + name]
+        sys.modules[pkg.__name__] = pkg
+    imp = importlib.import_module
+    les = imp('flowket.callbacks.monte_carlo.local_energy_stats').LocalEnergyStats
+    obs = imp('flowket.callbacks.monte_carlo.observable').ObservableStats
+    rts = imp('flowket.callbacks.monte_carlo.runtime_stats').RuntimeStats
+    git = imp('flowket.callbacks.monte_carlo.generator_iterator').GeneratorIterator
+    bad = imp('flowket.callbacks.monte_carlo.bad_eigen_state_stopping').BadEigenStateStopping
+    evaluate_mod = imp('flowket.evaluation.evaluate')
+    ev_mod = imp('flowket.optimization.exact_variational')
+
+    def clean(logs):
+        return {k: (float(np.real(v)) if k not in TIME_KEYS else None) for k, v in logs.items()}
+    out = {}
+    # --- Monte-Carlo stats, batch mode with a validation generator every 2nd epoch (the factory's list, built by hand
+    #     because the factory module imports the TensorFlow event writer)
+    gen, val = ScriptedGenerator([-10.0, -12.0, -11.0], SCRIPT_BATCH), ScriptedGenerator([-9.0, -13.0], SCRIPT_BATCH[:2])
+    shared = dict(validation_generator=val, log_in_batch_or_epoch=True, validation_period=2)
+    callbacks = [git(val, period=2), les(gen, true_ground_state_energy=-20.0, **shared),
+                 obs(gen, mc.SigmaZ(), 'sigma_z', **shared), obs(gen, mc.AbsSigmaZ(), 'abs_sigma_z', **shared),
+                 rts(gen, log_in_batch_or_epoch=True)]
+    trace = []
+    for epoch in range(3):
+        for batch in range(2):
+            next(gen)
+            logs = {}
+            for c in callbacks:
+                c.on_batch_end(batch, logs)
+            trace.append(['batch', epoch, batch, clean(logs)])
+        logs = {}
+        for c in callbacks:
+            c.on_epoch_end(epoch, logs)
+        trace.append(['epoch', epoch, -1, clean(logs)])
+    out['monte_carlo_batch_mode'] = trace
+    # --- epoch mode
+    gen = ScriptedGenerator([-10.0, -12.0], SCRIPT_BATCH)
+    callbacks = [les(gen, log_in_batch_or_epoch=False), obs(gen, mc.SigmaZ(), 'sigma_z', log_in_batch_or_epoch=False)]
+    next(gen)
+    b, e = {}, {}
+    for c in callbacks:
+        c.on_batch_end(0, b)
+        c.on_epoch_end(0, e)
+    out['monte_carlo_epoch_mode'] = [clean(b), clean(e)]
+    # --- evaluate(): mean of the logs over steps
+    gen = ScriptedGenerator([-10.0, -12.0, -14.0, -11.0], SCRIPT_BATCH)
+    res = evaluate_mod.evaluate(gen, 4, [les(gen, true_ground_state_energy=-24.0), obs(gen, mc.AbsSigmaZ(), 'abs_sigma_z')],
+                                verbose=False)
+    out['evaluate'] = clean(res)
+    # --- BadEigenStateStopping decisions
+    decisions = []
+    cb = bad(-100.0, variance_tol=1e-2, relative_error_to_stop=0.1, min_epoch=2)
+    cb.model = types.SimpleNamespace(stop_training=False)
+    for epoch, logs in enumerate([{'energy/energy': -80.0, 'energy/local_energy_variance': 1e-4},
+                                  {'energy/energy': -80.0, 'energy/local_energy_variance': 1e-4},
+                                  {'energy/energy': -80.0, 'energy/local_energy_variance': 1.0},
+                                  {'energy/energy': -95.0, 'energy/local_energy_variance': 1e-4},
+                                  {'energy/energy': -80.0, 'energy/local_energy_variance': 1e-4,
+                                   'val_energy/energy': -99.0, 'val_energy/local_energy_variance': 1e-4},
+                                  {'energy/energy': -80.0, 'energy/local_energy_variance': 1e-4}]):
+        cb.on_epoch_end(epoch, logs)
+        decisions.append([epoch, logs, bool(cb.model.stop_training), cb.stopped_epoch])
+    out['bad_eigen_state_stopping'] = decisions
+    # --- exact callbacks + exact_evaluate on a table machine
+    exl = imp('flowket.callbacks.exact.local_energy').ExactLocalEnergy
+    exs = imp('flowket.callbacks.exact.sigma_z').ExactSigmaZ
+    exr = imp('flowket.callbacks.exact.runtime_stats').RuntimeStats
+    rng = np.random.default_rng(20261019)
+    shape = (2, 3)
+    vec = rng.normal(size=64) * 0.5 + 1j * rng.uniform(-np.pi, np.pi, size=64)
+    table = ex.vector_to_machine(vec)
+    model = types.SimpleNamespace(input=None, output=lambda x: table(x), input_shape=(None,) + shape)
+    ev = ev_mod.ExactVariational(model, ops.Ising(hilbert_state_shape=list(shape), pbc=False, h=1.5), 16)
+    callbacks = [exl(ev, true_ground_state_energy=-12.0), exs(exact_variational=ev), exr(ev)]
+    out['exact_log_psi_vector'] = [[float(z.real), float(z.imag)] for z in vec]
+    out['exact_evaluate'] = clean(evaluate_mod.exact_evaluate(ev, callbacks))
+    gating = []
+    for batch in range(9):                      # 4 mini-batches per cycle: who reports on which batch index
+        logs = {}
+        for c in callbacks:
+            c.on_batch_end(batch, logs)
+        gating.append(sorted(logs))
+    out['exact_batch_gating'] = gating
+    path = os.path.join(OUT, 'reference_callbacks_logs.json')
+    with open(path, 'w') as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print('wrote', path)
+    for k in ('tensorflow', 'tensorflow.keras', 'tensorflow.keras.backend', 'tensorflow.keras.callbacks'):
+        del sys.modules[k]
+
+
 if __name__ == '__main__' and len(sys.argv) == 1:
     main()
+if __name__ == '__main__' and sys.argv[1:] == ['callbacks']:
+    callbacks_logs()
 if __name__ == '__main__' and sys.argv[1:] == ['vmc']:
     variational_monte_carlo()
 if __name__ == '__main__' and sys.argv[1:] == ['exact']:

@@ -456,3 +456,114 @@ def test_r_hat_matches_the_reference_implementation(name):
     got = np.array([float(x) for x in sampler.calc_r_hat_value(values)])
     assert np.allclose(got, g[name + '/result'], rtol=1e-12, atol=1e-12, equal_nan=True), (got, g[name + '/result'])
     assert sum_correlations(g['sum_correlations/input']) == pytest.approx(float(g['sum_correlations/result']), rel=1e-13)
+
+
+# ---- golden: the reference's own callbacks / evaluate on a scripted generator (oracle/make_golden.py callbacks) ------------
+class ScriptedGenerator(object):
+    """same script as oracle/make_golden.py::ScriptedGenerator (kept in sync by hand; the golden file is the arbiter)"""
+
+    def __init__(self, energies, batch):
+        self.energies, self.i = list(energies), -1
+        self.current_batch = np.asarray(batch, dtype=np.float64)
+        self.wave_function = lambda x: np.zeros((len(x), 1), np.complex64)
+        self.sampler = None
+
+    def __next__(self):
+        self.i += 1
+        e = self.energies[self.i % len(self.energies)]
+        self.current_energy = complex(e, 0.125)
+        self.current_local_energy_variance = 0.5 * abs(e)
+        self.current_local_energy = np.full(8, e, np.complex128)
+        self.start_time, self.sampling_end_time, self.local_energy_end_time = 100.0, 101.0, 102.5
+        return self.current_batch, np.zeros(len(self.current_batch))
+
+
+SCRIPT_BATCH = [[1, 1, -1, -1, 1, -1], [1, 1, 1, -1, 1, 1], [-1, -1, -1, -1, 1, -1]]
+TIME_KEYS = ('times/gradients', 'times/total')
+
+
+def _clean(logs):
+    return {k: (float(np.real(v)) if k not in TIME_KEYS else None) for k, v in logs.items()}
+
+
+def _same_logs(got, want):
+    assert set(got) == set(want), (sorted(got), sorted(want))
+    for k, v in want.items():
+        if v is None:
+            assert got[k] is None
+        else:
+            assert got[k] == pytest.approx(v, rel=1e-12, abs=1e-12), k
+
+
+@pytest.fixture(scope='module')
+def golden_logs():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_callbacks_logs.json')) as f:
+        return json.load(f)
+
+
+def test_monte_carlo_callbacks_reproduce_the_reference_logs(golden_logs):
+    from flowket_b200.callbacks import default_wave_function_stats_callbacks_factory
+    from flowket_b200.callbacks.monte_carlo import LocalEnergyStats, ObservableStats
+    from flowket_b200.observables.monte_carlo import SigmaZ
+    gen, val = ScriptedGenerator([-10.0, -12.0, -11.0], SCRIPT_BATCH), ScriptedGenerator([-9.0, -13.0], SCRIPT_BATCH[:2])
+    callbacks = default_wave_function_stats_callbacks_factory(gen, validation_generator=val, true_ground_state_energy=-20.0,
+                                                              validation_period=2)      # this repository's factory
+    trace = iter(golden_logs['monte_carlo_batch_mode'])
+    for epoch in range(3):
+        for batch in range(2):
+            next(gen)
+            logs = {}
+            for c in callbacks:
+                c.on_batch_end(batch, logs)
+            kind, e, b, want = next(trace)
+            assert (kind, e, b) == ('batch', epoch, batch)
+            _same_logs(_clean(logs), want)
+        logs = {}
+        for c in callbacks:
+            c.on_epoch_end(epoch, logs)
+        kind, e, _, want = next(trace)
+        assert (kind, e) == ('epoch', epoch)
+        _same_logs(_clean(logs), want)
+    gen = ScriptedGenerator([-10.0, -12.0], SCRIPT_BATCH)
+    callbacks = [LocalEnergyStats(gen, log_in_batch_or_epoch=False), ObservableStats(gen, SigmaZ(), 'sigma_z', log_in_batch_or_epoch=False)]
+    next(gen)
+    b, e = {}, {}
+    for c in callbacks:
+        c.on_batch_end(0, b)
+        c.on_epoch_end(0, e)
+    _same_logs(_clean(b), golden_logs['monte_carlo_epoch_mode'][0])
+    _same_logs(_clean(e), golden_logs['monte_carlo_epoch_mode'][1])
+
+
+def test_evaluate_and_bad_eigen_state_stopping_reproduce_the_reference(golden_logs):
+    from flowket_b200.callbacks.monte_carlo import LocalEnergyStats, ObservableStats, BadEigenStateStopping
+    from flowket_b200.evaluation import evaluate
+    from flowket_b200.observables.monte_carlo import AbsSigmaZ
+    gen = ScriptedGenerator([-10.0, -12.0, -14.0, -11.0], SCRIPT_BATCH)
+    res = evaluate(gen, 4, [LocalEnergyStats(gen, true_ground_state_energy=-24.0), ObservableStats(gen, AbsSigmaZ(), 'abs_sigma_z')],
+                   verbose=False)
+    _same_logs(_clean(res), golden_logs['evaluate'])
+    cb = BadEigenStateStopping(-100.0, variance_tol=1e-2, relative_error_to_stop=0.1, min_epoch=2)
+    cb.set_model(types.SimpleNamespace(stop_training=False))
+    for epoch, logs, stop, stopped_epoch in golden_logs['bad_eigen_state_stopping']:
+        cb.on_epoch_end(epoch, logs)
+        assert (bool(cb.model.stop_training), cb.stopped_epoch) == (stop, stopped_epoch), epoch
+
+
+def test_exact_callbacks_reproduce_the_reference_logs(golden_logs):
+    from flowket_b200.callbacks.exact import default_wave_function_callbacks_factory
+    from flowket_b200.evaluation import exact_evaluate
+    from flowket_b200.optimization import ExactVariational
+    vec = np.array([complex(a, b) for a, b in golden_logs['exact_log_psi_vector']])
+    f = vector_to_machine(vec)
+    model = types.SimpleNamespace(input_shape=(None, 2, 3), predict=lambda x, batch_size=None: f(np.asarray(x)))
+    ev = ExactVariational(model, oops.OracleOperator('ising', (2, 3), pbc=False, h=1.5), 16)
+    callbacks = default_wave_function_callbacks_factory(ev, true_ground_state_energy=-12.0)
+    _same_logs(_clean(exact_evaluate(ev, callbacks)), golden_logs['exact_evaluate'])
+    for batch, want_keys in enumerate(golden_logs['exact_batch_gating']):
+        logs = {}
+        for c in callbacks:
+            c.on_batch_end(batch, logs)
+        assert sorted(logs) == want_keys, batch
