@@ -14,7 +14,11 @@ Pinning status (see DESIGN.md "Oracle"):
   * operators / local energy / exact-enumeration conventions: PINNED against the
     reference's own numpy code imported from /root/reference (fixtures in
     tests/golden/, generator oracle/make_golden.py) and against the
-    exact-diagonalisation constants embedded in the reference's examples.
+    exact-diagonalisation constants embedded in the reference's examples;
+    ExactVariational, VariationalMonteCarlo + MiniBatchGenerator, the stats
+    callbacks / evaluate, the MCMC diagnostics and the AutoregressiveSampler loop
+    are PINNED by running the reference's own classes around minimal stand-ins
+    for the TensorFlow guards (make_golden.py exact | vmc | callbacks | mcmc | sampler).
   * network half (Keras graph; TensorFlow is not installable here): restated
     from the reference sources cited per function; pinned by the reference's
     own property tests (normalisation, incremental == full) and end-to-end by

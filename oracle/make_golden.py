@@ -502,8 +502,54 @@ def callbacks_logs():
         del sys.modules[k]
 
 
+def autoregressive_sampler():
+    """tests/golden/reference_autoregressive_sampler.npz: spins drawn by the reference's own AutoregressiveSampler.__next__
+    (deepar/samplers/autoregressive.py:29-48, +-1 variant) when its `conditional_log_probs_machine.predict` is the oracle's
+    fp32 network (oracle/nets.py) -- pins the sampling rule itself (raster order, `exp(log p0) > u`, unsampled sites = 0,
+    spins written back as +-1) against the reference's code, given the uniforms numpy's global generator produced."""
+    import torch
+    from oracle import nets
+
+    def stub(name, path):
+        mod = types.ModuleType(name)
+        mod.__path__ = [path]
+        sys.modules[name] = mod
+    stub('flowket', REF)
+    stub('flowket.deepar', REF + '/deepar')
+    stub('flowket.deepar.samplers', REF + '/deepar/samplers')
+    ar = importlib.import_module('flowket.deepar.samplers.autoregressive')
+    out = {}
+    for name, spec, B, seed in [
+        ('conv2d_4x3', nets.Conv2DSpec(4, 3, 2, 8), 64, 11),
+        ('conv1d_10', nets.Conv1DSpec(10, 4, 8, max_dilation_rate=2), 48, 12),
+        ('cconv1d_8', nets.ComplexConv1DSpec(8, 3, 4, max_dilation_rate=2), 32, 13),
+    ]:
+        params = nets.init_params(spec, seed=seed, dtype=torch.float32, bias_scale=0.3)
+
+        class Machine(object):
+            input_shape = (None,) + tuple(spec.input_shape)
+
+            def predict(self, batch, batch_size=None):
+                with torch.no_grad():
+                    return nets.conditional_log_probs(spec, params, np.asarray(batch)).numpy()
+
+        np.random.seed(seed)
+        sampler = ar.AutoregressiveSampler(Machine(), B, zero_base=False)
+        sigma = next(sampler)
+        np.random.seed(seed)
+        uniforms = np.random.rand(*((B,) + tuple(spec.input_shape)))       # the first draw of __next__ after seeding
+        out[name + '/params'] = nets.flatten_params(params).numpy()
+        out[name + '/uniforms'] = uniforms
+        out[name + '/sigma'] = np.asarray(sigma).astype(np.int8)
+    path = os.path.join(OUT, 'reference_autoregressive_sampler.npz')
+    np.savez_compressed(path, **out)
+    print('wrote', path, len(out), 'arrays')
+
+
 if __name__ == '__main__' and len(sys.argv) == 1:
     main()
+if __name__ == '__main__' and sys.argv[1:] == ['sampler']:
+    autoregressive_sampler()
 if __name__ == '__main__' and sys.argv[1:] == ['callbacks']:
     callbacks_logs()
 if __name__ == '__main__' and sys.argv[1:] == ['vmc']:

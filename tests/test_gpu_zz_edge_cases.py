@@ -54,3 +54,30 @@ def test_local_energy_on_degenerate_lattices(kind, shape, opkind, opkw):
     want = oeloc.local_values(oops.OracleOperator(opkind, shape, **opkw), lambda c: nets.log_psi_numpy(spec, params, c),
                               sigma.astype(np.float64))
     assert np.abs(got - want).max() / np.abs(want).max() < 1e-5
+
+
+@pytest.mark.parametrize('name,kind,shape,depth,channels,kw', [
+    ('conv2d_4x3', 'conv2d', (4, 3), 2, 8, {}),
+    ('conv1d_10', 'conv1d', (10,), 4, 8, {'max_dilation_rate': 2}),
+    ('cconv1d_8', 'cconv1d', (8,), 3, 4, {'max_dilation_rate': 2}),
+])
+def test_device_samplers_reproduce_the_reference_samplers_spins(name, kind, shape, depth, channels, kw):
+    """golden (oracle/make_golden.py sampler): spins drawn by the reference's own AutoregressiveSampler.__next__ around the
+    oracle network; the CUDA samplers get the same weights and the same uniforms.  A spin may differ only at a numerical
+    tie |p0 - u| < 1e-5 (fp32 summation order), as in tests/test_gpu_parity.py."""
+    import os
+    import torch
+    from flowket_b200.samplers import FastAutoregressiveSampler, AutoregressiveSampler
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_autoregressive_sampler.npz'))
+    model, cond_model, spec, _ = make_pair(kind, shape, depth, channels, seed=0, **kw)
+    params = nets.unflatten_params(spec, torch.from_numpy(g[name + '/params']))
+    model.machine.set_weights([p.numpy() for p in params])
+    u, want = g[name + '/uniforms'], g[name + '/sigma']
+    p0 = np.exp(nets.conditional_log_probs(spec, [p.double() for p in params], want).numpy()[..., 0])
+    B = len(u)
+    for sampler in (FastAutoregressiveSampler(cond_model, B), AutoregressiveSampler(cond_model, B)):
+        got = sampler.next_device(uniforms=u).cpu().numpy()
+        bad = np.argwhere(got != want)
+        for idx in bad:   # the first differing site of a sample must be a numerical tie
+            first = tuple(bad[bad[:, 0] == idx[0]][0])
+            assert abs(p0[first] - u[first]) < 1e-5, (type(sampler).__name__, first, p0[first], u[first])

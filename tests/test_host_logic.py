@@ -314,3 +314,27 @@ def test_variational_monte_carlo_matches_the_reference_class():
         assert vmc.current_local_energy_variance == pytest.approx(float(g['variances'][step]), rel=1e-5)
     assert np.allclose(vmc.current_local_energy, g['last_local_energy'], rtol=1e-6)
     assert sampler.i + 1 == int(g['batches_drawn'])
+
+
+@pytest.mark.parametrize('name,spec', [
+    ('conv2d_4x3', nets.Conv2DSpec(4, 3, 2, 8)),
+    ('conv1d_10', nets.Conv1DSpec(10, 4, 8, max_dilation_rate=2)),
+    ('cconv1d_8', nets.ComplexConv1DSpec(8, 3, 4, max_dilation_rate=2)),
+])
+def test_sampling_rule_matches_the_reference_sampler(name, spec):
+    """golden (oracle/make_golden.py sampler): spins drawn by the reference's own AutoregressiveSampler.__next__ around the
+    oracle network.  The oracle's sampler -- the parity contract the CUDA samplers are held to bit-exactly in
+    tests/test_gpu_parity.py -- must reproduce them from the same uniforms, both site-by-site and incrementally."""
+    import os
+    from oracle import sampler as osampler
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_autoregressive_sampler.npz'))
+    params = nets.unflatten_params(spec, torch.from_numpy(g[name + '/params']))
+    sigma, p0 = osampler.sample_with_uniforms(spec, params, g[name + '/uniforms'])
+    assert np.array_equal(sigma, g[name + '/sigma'])
+    assert set(np.unique(sigma)) <= {-1, 1}
+    if spec.kind == 'conv2d':
+        inc = osampler.IncrementalSampler2D(spec, params)
+        sigma_inc = inc.sample(g[name + '/uniforms'])
+        sigma_inc = sigma_inc[0] if isinstance(sigma_inc, tuple) else sigma_inc
+        # incremental == full up to near-ties of exp(log p0) against u (different fp32 summation order)
+        assert (np.asarray(sigma_inc) != g[name + '/sigma']).mean() < 0.01
