@@ -546,8 +546,64 @@ def autoregressive_sampler():
     print('wrote', path, len(out), 'arrays')
 
 
+def complex_ops():
+    """tests/golden/reference_complex_ops.npz: the reference's own `lncosh`, `complex_log`, `angle`
+    (layers/complex/tensorflow_ops.py:69-85) and `probabilistic_ensemble_op` / `average_ensemble_op`
+    (machines/ensemble.py:14-25) evaluated on numpy arrays.  These functions are compositions of a dozen elementwise
+    TensorFlow math functions; the stand-in below maps each of those one-to-one onto the numpy function of the same
+    meaning (real, imag, abs, exp, log, atan2, complex, cast, zeros_like, reduce_mean, reduce_logsumexp), so what is
+    pinned is the reference's *composition* -- the numerically stable lncosh, the circular-mean phase, the -log(K)/2
+    normalisation of the probabilistic ensemble."""
+    import contextlib
+    from scipy.special import logsumexp
+
+    def module(name, **attrs):
+        mod = types.ModuleType(name)
+        mod.__dict__.update(attrs)
+        sys.modules[name] = mod
+        return mod
+    tmath = types.SimpleNamespace(
+        real=np.real, imag=np.imag, abs=np.abs, exp=np.exp, log=np.log, atan2=np.arctan2,
+        reduce_mean=lambda x, axis=None, keepdims=False: np.mean(x, axis=axis, keepdims=keepdims),
+        reduce_logsumexp=lambda x, axis=None, keepdims=False: logsumexp(x, axis=axis, keepdims=keepdims))
+    backend = module('tensorflow.keras.backend')
+    models = module('tensorflow.keras.models', Model=object)
+    layers = module('tensorflow.keras.layers', Lambda=object, Input=object, Concatenate=object)
+    keras = module('tensorflow.keras', backend=backend, models=models, layers=layers)
+    module('tensorflow', math=tmath, keras=keras, complex=lambda re, im: np.asarray(re) + 1j * np.asarray(im),
+           cast=lambda x, dtype: np.asarray(x).astype(dtype), zeros_like=np.zeros_like,
+           name_scope=lambda *a, **k: contextlib.nullcontext('scope'))
+    pkg = types.ModuleType('flowket')
+    pkg.__path__ = [REF]
+    sys.modules['flowket'] = pkg
+    module('flowket.layers', Rot90=object, FlipLeftRight=object, Roll=object).__path__ = [REF + '/layers']
+    cpx = types.ModuleType('flowket.layers.complex')
+    cpx.__path__ = [REF + '/layers/complex']
+    sys.modules['flowket.layers.complex'] = cpx
+    mach = types.ModuleType('flowket.machines')
+    mach.__path__ = [REF + '/machines']
+    sys.modules['flowket.machines'] = mach
+    tops = importlib.import_module('flowket.layers.complex.tensorflow_ops')
+    ens = importlib.import_module('flowket.machines.ensemble')
+    rng = np.random.default_rng(20261020)
+    z = np.concatenate([np.array([2, 3j, 1 + 7j, 10 - 3j, -6, 0.0, 40 + 2j, -55 - 1j, 1e-3 + 1e-3j], dtype=np.complex128),
+                        rng.normal(size=64) * 4 + 1j * rng.normal(size=64) * 4])
+    x = rng.normal(size=(9, 16)) * 3 + 1j * rng.uniform(-np.pi, np.pi, size=(9, 16))
+    out = {'z': z, 'lncosh': tops.lncosh(z), 'complex_log': tops.complex_log(z[z != 0]), 'angle': tops.angle(z),
+           'ensemble_input': x,
+           'probabilistic_ensemble': ens.probabilistic_ensemble_op(x, 16),
+           'average_ensemble': ens.average_ensemble_op(x)}
+    path = os.path.join(OUT, 'reference_complex_ops.npz')
+    np.savez_compressed(path, **out)
+    print('wrote', path, len(out), 'arrays')
+    for k in [k for k in sys.modules if k == 'tensorflow' or k.startswith('tensorflow.')]:
+        del sys.modules[k]
+
+
 if __name__ == '__main__' and len(sys.argv) == 1:
     main()
+if __name__ == '__main__' and sys.argv[1:] == ['complex_ops']:
+    complex_ops()
 if __name__ == '__main__' and sys.argv[1:] == ['sampler']:
     autoregressive_sampler()
 if __name__ == '__main__' and sys.argv[1:] == ['callbacks']:

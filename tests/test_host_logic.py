@@ -338,3 +338,22 @@ def test_sampling_rule_matches_the_reference_sampler(name, spec):
         sigma_inc = sigma_inc[0] if isinstance(sigma_inc, tuple) else sigma_inc
         # incremental == full up to near-ties of exp(log p0) against u (different fp32 summation order)
         assert (np.asarray(sigma_inc) != g[name + '/sigma']).mean() < 0.01
+
+
+def test_lncosh_and_ensemble_ops_match_the_reference_functions():
+    """golden (oracle/make_golden.py complex_ops): the reference's own lncosh / complex_log / angle and the two ensemble ops
+    evaluated on numpy arrays through a one-to-one numpy stand-in for the elementwise TF math functions they compose."""
+    import os
+    from flowket_b200.machines.ensemble import probabilistic_ensemble_op, average_ensemble_op
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_complex_ops.npz'))
+    z = torch.from_numpy(g['z'])
+    got = nets.lncosh(z).numpy()
+    assert np.allclose(got.real, g['lncosh'].real, rtol=1e-12, atol=1e-12)
+    assert np.allclose(np.exp(1j * got.imag), np.exp(1j * g['lncosh'].imag), atol=1e-12)       # phase modulo 2 pi
+    x = torch.from_numpy(g['ensemble_input'])
+    got = probabilistic_ensemble_op(x).numpy()
+    assert np.allclose(got.real, g['probabilistic_ensemble'].real, rtol=1e-12, atol=1e-12)
+    assert np.allclose(np.exp(1j * got.imag), np.exp(1j * g['probabilistic_ensemble'].imag), atol=1e-12)
+    got = average_ensemble_op(x).numpy()
+    assert np.allclose(got.real, g['average_ensemble'].real, rtol=1e-11, atol=1e-12)
+    assert np.allclose(np.exp(1j * got.imag), np.exp(1j * g['average_ensemble'].imag), atol=1e-11)
