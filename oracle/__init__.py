@@ -20,7 +20,10 @@ Pinning status (see DESIGN.md "Oracle"):
     are PINNED by running the reference's own classes around minimal stand-ins
     for the TensorFlow guards (make_golden.py exact | vmc | callbacks | mcmc | sampler).
   * network half (Keras graph; TensorFlow is not installable here): restated
-    from the reference sources cited per function; pinned by the reference's
+    from the reference sources cited per function and PINNED against the
+    reference's own machine classes run on top of oracle/tf_standin.py (an eager
+    torch stand-in for the primitive TF / Keras operations; make_golden.py
+    machines -> tests/golden/reference_machines.npz, 1e-10); also pinned by the reference's
     own property tests (normalisation, incremental == full) and end-to-end by
     the reference's pretrained Keras weight files
     (experiments/weights/ising_*.h5 -> published energies).  Bit-level parity

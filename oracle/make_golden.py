@@ -600,8 +600,129 @@ def complex_ops():
         del sys.modules[k]
 
 
+def load_reference_machines():
+    """import the reference's machine classes with oracle/tf_standin.py in place of tensorflow (see that file's header)"""
+    from oracle import tf_standin
+    tf_standin.install()
+
+    def package(name, path):
+        mod = types.ModuleType(name)
+        mod.__path__ = [path]
+        sys.modules[name] = mod
+        return mod
+
+    def module(name, **attrs):
+        mod = types.ModuleType(name)
+        mod.__dict__.update(attrs)
+        sys.modules[name] = mod
+        return mod
+    package('flowket', REF)
+    package('flowket.machines', REF + '/machines')
+    layers = package('flowket.layers', REF + '/layers')
+    package('flowket.layers.complex', REF + '/layers/complex')
+    package('flowket.deepar', REF + '/deepar')
+    deepar_layers = package('flowket.deepar.layers', REF + '/deepar/layers')
+    # graph analysis (the fast sampler's topology registry) and the weight initialisers are not part of the forward pass
+
+    class TopologyManager(object):
+        def register_layer_topology(self, *args, **kwargs):
+            pass
+    ga = module('flowket.deepar.graph_analysis', TopologyManager=TopologyManager, OneToOneTopology=object)
+    module('flowket.deepar.graph_analysis.convolutional_topology', TopologyManager=TopologyManager, ConvolutionalTopology=object)
+    module('flowket.deepar.graph_analysis.dependency_graph', assert_valid_probabilistic_model=lambda model: None)
+    ga.__path__ = []
+
+    class ConjugateDecorator(object):
+        def __init__(self, initializer):
+            pass
+
+        def get_real_part_initializer(self):
+            return None
+
+        def get_imag_part_initializer(self):
+            return None
+    module('flowket.layers.complex.initializers', ConjugateDecorator=ConjugateDecorator, get=lambda identifier: identifier)
+    imp = importlib.import_module
+    for sub, names in [('autoregressive', ['NormalizeInLogSpace', 'CombineAutoregressiveConditionals']),
+                       ('casting', ['CastingLayer', 'ToFloat32', 'ToFloat64']),
+                       ('lambda_with_one_to_one_topology', ['LambdaWithOneToOneTopology']),
+                       ('masking', ['DownShiftLayer', 'RightShiftLayer']),
+                       ('one_hot', ['ToOneHot', 'PlusMinusOneToOneHot']),
+                       ('padding', ['ExpandInputDim', 'PeriodicPadding']),
+                       ('wrappers', ['WeightNormalization'])]:
+        mod = imp('flowket.deepar.layers.' + sub)
+        for n in names:
+            setattr(deepar_layers, n, getattr(mod, n))
+    casting = imp('flowket.layers.complex.casting')
+    conv = imp('flowket.layers.complex.conv')
+    spins = imp('flowket.layers.spins_invariants')
+    for mod, names in [(casting, ['VectorToComplexNumber', 'ToComplex64', 'ToComplex128']), (conv, ['ComplexConv1D']),
+                       (spins, ['EqualUpDownSpins'])]:
+        for n in names:
+            setattr(layers, n, getattr(mod, n))
+    return (imp('flowket.machines.conv_net_autoregressive_2D').ConvNetAutoregressive2D,
+            imp('flowket.machines.simple_conv_net_autoregressive_1D').SimpleConvNetAutoregressive1D,
+            imp('flowket.machines.complex_values_simple_conv_net_autoregressive_1D').ComplexValuesSimpleConvNetAutoregressive1D)
+
+
+MACHINE_CASES = [
+    # name, kind, input shape, constructor kwargs of the REFERENCE class (== oracle spec arguments)
+    ('conv2d_4x3_d3_wn', 'conv2d', (4, 3), dict(depth=3, num_of_channels=8)),
+    ('conv2d_3x4_d2_plain', 'conv2d', (3, 4), dict(depth=2, num_of_channels=6, weights_normalization=False)),
+    ('conv2d_5x5_d4_linear_g', 'conv2d', (5, 5), dict(depth=4, num_of_channels=4, exponential_norm=False)),
+    ('conv1d_12_d5_dil4_skip', 'conv1d', (12,), dict(depth=5, num_of_channels=8, max_dilation_rate=4, add_skip_connections=True)),
+    ('conv1d_10_d4_plain', 'conv1d', (10,), dict(depth=4, num_of_channels=6, weights_normalization=False)),
+    ('conv1d_9_d6_nodil', 'conv1d', (9,), dict(depth=6, num_of_channels=4, use_dilation=False, max_dilation_rate=4)),
+    ('cconv1d_10_d4_dil2', 'cconv1d', (10,), dict(depth=4, num_of_channels=6, max_dilation_rate=2)),
+    ('cconv1d_8_d3', 'cconv1d', (8,), dict(depth=3, num_of_channels=4)),
+]
+
+
+def machines():
+    """tests/golden/reference_machines.npz: log psi and the conditional log-probabilities computed by the reference's OWN
+    machine classes for random weights and random spins (8 machines covering weight norm on / off / linear g, dilation
+    rules, skip connections, the complex machine).  The oracle network (oracle/nets.py), until now pinned only by property
+    tests and by the pretrained 2-D weights, is checked against these numbers on the CPU and the CUDA engines on the GPU."""
+    import torch
+    from oracle import nets, tf_standin
+    classes = dict(zip(('conv2d', 'conv1d', 'cconv1d'), load_reference_machines()))
+    rng = np.random.default_rng(20261021)
+    out = {}
+    for name, kind, shape, kw in MACHINE_CASES:
+        if kind == 'conv2d':
+            spec = nets.Conv2DSpec(shape[0], shape[1], kw['depth'], kw['num_of_channels'],
+                                   weights_normalization=kw.get('weights_normalization', True),
+                                   exponential_norm=kw.get('exponential_norm', True))
+        elif kind == 'conv1d':
+            spec = nets.Conv1DSpec(shape[0], kw['depth'], kw['num_of_channels'], use_dilation=kw.get('use_dilation', True),
+                                   add_skip_connections=kw.get('add_skip_connections', False),
+                                   max_dilation_rate=kw.get('max_dilation_rate'),
+                                   weights_normalization=kw.get('weights_normalization', True))
+        else:
+            spec = nets.ComplexConv1DSpec(shape[0], kw['depth'], kw['num_of_channels'],
+                                          max_dilation_rate=kw.get('max_dilation_rate'))
+        # shapes and order of the weights come from the oracle's layout; the reference's add_weight calls must ask for
+        # exactly these shapes in exactly this order (asserted inside the stand-in) -- that pins the parameter layout too
+        params = [p + 0.3 * torch.randn(p.shape, dtype=torch.float64, generator=torch.Generator().manual_seed(len(out) + i))
+                  * (p.dim() == 1) for i, p in enumerate(nets.init_params(spec, seed=7, dtype=torch.float64))]
+        sigma = rng.choice([-1, 1], size=(12,) + shape).astype(np.int8)
+        tf_standin.inject_weights([p.numpy() for p in params])
+        machine = classes[kind](torch.from_numpy(sigma.astype(np.float64)), **kw)
+        assert not tf_standin._WEIGHTS, 'the reference created fewer weights than the oracle layout holds'
+        out[name + '/params'] = nets.flatten_params(params).numpy()
+        out[name + '/sigma'] = sigma
+        out[name + '/log_psi'] = machine.predictions.numpy()[:, 0]
+        out[name + '/conditional_log_probs'] = machine.conditional_log_probs.numpy()
+        out[name + '/weight_names'] = np.array([n for n, _ in tf_standin.created_weights()])
+    path = os.path.join(OUT, 'reference_machines.npz')
+    np.savez_compressed(path, **out)
+    print('wrote', path, len(out), 'arrays')
+
+
 if __name__ == '__main__' and len(sys.argv) == 1:
     main()
+if __name__ == '__main__' and sys.argv[1:] == ['machines']:
+    machines()
 if __name__ == '__main__' and sys.argv[1:] == ['complex_ops']:
     complex_ops()
 if __name__ == '__main__' and sys.argv[1:] == ['sampler']:

@@ -81,3 +81,35 @@ def test_device_samplers_reproduce_the_reference_samplers_spins(name, kind, shap
         for idx in bad:   # the first differing site of a sample must be a numerical tie
             first = tuple(bad[bad[:, 0] == idx[0]][0])
             assert abs(p0[first] - u[first]) < 1e-5, (type(sampler).__name__, first, p0[first], u[first])
+
+
+MACHINE_GOLDEN = {
+    # name -> (product machine kind, shape, depth, channels, constructor kwargs)
+    'conv2d_4x3_d3_wn': ('conv2d', (4, 3), 3, 8, {}),
+    'conv2d_3x4_d2_plain': ('conv2d', (3, 4), 2, 6, {'weights_normalization': False}),
+    'conv1d_12_d5_dil4_skip': ('conv1d', (12,), 5, 8, {'max_dilation_rate': 4, 'add_skip_connections': True}),
+    'conv1d_10_d4_plain': ('conv1d', (10,), 4, 6, {'weights_normalization': False}),
+    'cconv1d_10_d4_dil2': ('cconv1d', (10,), 4, 6, {'max_dilation_rate': 2}),
+    'cconv1d_8_d3': ('cconv1d', (8,), 3, 4, {}),
+}
+
+
+@pytest.mark.parametrize('name', sorted(MACHINE_GOLDEN))
+def test_device_wave_function_matches_the_reference_machine_classes(name):
+    """golden tests/golden/reference_machines.npz: log psi and conditional log-probabilities computed by the reference's OWN
+    machine classes (oracle/make_golden.py machines); the CUDA fp32 engine gets the same weights and spins (1e-5)."""
+    import os
+    import torch
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_machines.npz'))
+    kind, shape, depth, channels, kw = MACHINE_GOLDEN[name]
+    model, cond_model, spec, _ = make_pair(kind, shape, depth, channels, seed=0, **kw)
+    params = nets.unflatten_params(spec, torch.from_numpy(g[name + '/params']))
+    model.machine.set_weights([p.numpy().astype(np.float32) for p in params])
+    sigma = g[name + '/sigma']
+    got = model.predict(sigma)[:, 0]
+    want = g[name + '/log_psi']
+    assert np.abs(got.real - want.real).max() < 1e-5 * max(1.0, np.abs(want.real).max())
+    assert np.abs(np.exp(1j * got.imag) - np.exp(1j * want.imag)).max() < 1e-4           # phases modulo 2 pi, fp32
+    got_c = cond_model.predict(sigma)
+    want_c = g[name + '/conditional_log_probs']
+    assert np.abs(got_c - want_c).max() < 1e-5 * max(1.0, np.abs(want_c).max())
