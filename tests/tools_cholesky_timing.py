@@ -33,7 +33,7 @@ def solve32(refine=2):
     L, info = torch.linalg.cholesky_ex(T)
     w = torch.cholesky_solve(b.float().reshape(-1, 1), L).reshape(-1).double()
     for _ in range(refine):
-        r = b - torch.mv(T.double(), w) if False else b - (T @ w.float()).double()
+        r = b - (T @ w.float()).double()            # residual in fp32 (the fp64-residual variant is below)
         w = w + torch.cholesky_solve(r.float().reshape(-1, 1), L).reshape(-1).double()
     return w
 
