@@ -618,6 +618,7 @@ def load_reference_machines():
         return mod
     package('flowket', REF)
     package('flowket.machines', REF + '/machines')
+    package('flowket.optimization', REF + '/optimization')
     layers = package('flowket.layers', REF + '/layers')
     package('flowket.layers.complex', REF + '/layers/complex')
     package('flowket.deepar', REF + '/deepar')
@@ -714,6 +715,20 @@ def machines():
         out[name + '/log_psi'] = machine.predictions.numpy()[:, 0]
         out[name + '/conditional_log_probs'] = machine.conditional_log_probs.numpy()
         out[name + '/weight_names'] = np.array([n for n, _ in tf_standin.created_weights()])
+        # gradient of the reference's loss through the reference's forward (autograd over the stand-in's torch ops):
+        # loss_for_energy_minimization (optimization/loss.py:4-5) summed over the batch, and one per-sample Jacobian row
+        loss_fn = importlib.import_module('flowket.optimization.loss').loss_for_energy_minimization
+        y = torch.from_numpy(rng.normal(size=12) + 1j * rng.normal(size=12))
+        leaves = tf_standin.inject_weights([p.numpy() for p in params], requires_grad=True)
+        machine = classes[kind](torch.from_numpy(sigma.astype(np.float64)), **kw)
+        loss = loss_fn(y.reshape(-1, 1), machine.predictions).sum()
+        grads = torch.autograd.grad(loss, leaves, retain_graph=True)
+        out[name + '/y'] = y.numpy()
+        out[name + '/weighted_gradient'] = torch.cat([g.reshape(-1) for g in grads]).numpy()
+        row = torch.autograd.grad(machine.predictions[3, 0].real, leaves, retain_graph=True)
+        out[name + '/jacobian_row3_real'] = torch.cat([g.reshape(-1) for g in row]).numpy()
+        row = torch.autograd.grad(machine.predictions[3, 0].imag, leaves)
+        out[name + '/jacobian_row3_imag'] = torch.cat([g.reshape(-1) for g in row]).numpy()
     path = os.path.join(OUT, 'reference_machines.npz')
     np.savez_compressed(path, **out)
     print('wrote', path, len(out), 'arrays')

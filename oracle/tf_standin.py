@@ -27,10 +27,14 @@ _WEIGHTS = []          # injected weights, consumed by add_weight in creation or
 _CREATED = []          # (name, shape) of every weight handed out
 
 
-def inject_weights(arrays):
+def inject_weights(arrays, requires_grad=False):
+    """`requires_grad`: the handed-out weights are autograd leaves, so the reference's forward (all torch ops here) can be
+    differentiated with respect to them -- returns the leaves in injection order"""
     del _WEIGHTS[:]
     del _CREATED[:]
-    _WEIGHTS.extend(torch.as_tensor(np.asarray(a, dtype=np.float64)) for a in arrays)
+    leaves = [torch.as_tensor(np.asarray(a, dtype=np.float64)).clone().requires_grad_(requires_grad) for a in arrays]
+    _WEIGHTS.extend(leaves)
+    return leaves
 
 
 def created_weights():

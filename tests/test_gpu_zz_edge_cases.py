@@ -113,3 +113,26 @@ def test_device_wave_function_matches_the_reference_machine_classes(name):
     got_c = cond_model.predict(sigma)
     want_c = g[name + '/conditional_log_probs']
     assert np.abs(got_c - want_c).max() < 1e-5 * max(1.0, np.abs(want_c).max())
+
+
+@pytest.mark.parametrize('name', sorted(MACHINE_GOLDEN))
+def test_device_gradients_match_autograd_through_the_reference_forward(name):
+    """golden: the reference's loss differentiated through the reference machine's own forward (make_golden.py machines);
+    the hand-written CUDA backward (fk_grad_weighted, fk_grad_per_sample) gets the same weights, spins and coefficients."""
+    import os
+    import torch
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_machines.npz'))
+    kind, shape, depth, channels, kw = MACHINE_GOLDEN[name]
+    model, _, spec, _ = make_pair(kind, shape, depth, channels, seed=0, **kw)
+    params = nets.unflatten_params(spec, torch.from_numpy(g[name + '/params']))
+    model.machine.set_weights([p.numpy().astype(np.float32) for p in params])
+    net = model.machine.device_net()
+    sigma = g[name + '/sigma']
+    y = g[name + '/y'].astype(np.complex64)
+    got = net.grad_weighted(net.to_sigma(sigma), torch.from_numpy(y)).cpu().numpy()
+    want = g[name + '/weighted_gradient']
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 2e-5
+    O_re, O_im = net.grad_per_sample(net.to_sigma(sigma[3:4]), imag=True)
+    want_re, want_im = g[name + '/jacobian_row3_real'], g[name + '/jacobian_row3_imag']
+    assert np.linalg.norm(O_re.cpu().numpy()[0] - want_re) / np.linalg.norm(want_re) < 2e-5
+    assert np.linalg.norm(O_im.cpu().numpy()[0] - want_im) / max(np.linalg.norm(want_im), 1e-30) < 2e-5
