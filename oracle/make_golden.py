@@ -734,8 +734,48 @@ def machines():
     print('wrote', path, len(out), 'arrays')
 
 
+def ensembles():
+    """tests/golden/reference_ensembles.npz: the reference's own symmetrisation ensembles (machines/ensemble.py:28-69 with
+    layers/dihedral_4_invariants.py and transition_invariants.py) around the reference's own 2-D machine, run eagerly on the
+    stand-in: D4 (probabilistic and averaged), spin flip nested around D4 -- the composition of the published evaluation,
+    experiments/run_evaluation.py:17-22 -- and all lattice translations.  A Keras sub-model reused on several inputs is, in
+    eager mode, the same function called several times: `base` below re-injects the same weights for every call."""
+    import torch
+    from oracle import nets, tf_standin
+    conv2d_cls = load_reference_machines()[0]
+    package = lambda name, path: sys.modules.setdefault(name, types.ModuleType(name))     # noqa: E731
+    layers = sys.modules['flowket.layers']
+    imp = importlib.import_module
+    d4, tr = imp('flowket.layers.dihedral_4_invariants'), imp('flowket.layers.transition_invariants')
+    layers.Rot90, layers.FlipLeftRight, layers.Roll = d4.Rot90, d4.FlipLeftRight, tr.Roll
+    ens = imp('flowket.machines.ensemble')
+    spec = nets.Conv2DSpec(4, 4, 2, 8)
+    kw = dict(depth=2, num_of_channels=8)
+    params = [p + 0.3 * torch.randn(p.shape, dtype=torch.float64, generator=torch.Generator().manual_seed(100 + i)) * (p.dim() == 1)
+              for i, p in enumerate(nets.init_params(spec, seed=9, dtype=torch.float64))]
+
+    def base(x):
+        tf_standin.inject_weights([p.numpy() for p in params])
+        return conv2d_cls(x, **kw).predictions
+
+    rng = np.random.default_rng(20261022)
+    sigma = rng.choice([-1, 1], size=(10, 4, 4)).astype(np.int8)
+    x = torch.from_numpy(sigma.astype(np.float64))
+    out = {'params': nets.flatten_params(params).numpy(), 'sigma': sigma, 'base': base(x).numpy()[:, 0]}
+    out['obc'] = ens.make_2d_obc_invariants(x, base).output.numpy()[:, 0]
+    out['obc_average'] = ens.make_2d_obc_invariants(x, base, probabilistic=False).output.numpy()[:, 0]
+    obc = lambda inputs: ens.make_2d_obc_invariants(inputs, base).output                       # noqa: E731
+    out['up_down_of_obc'] = ens.make_up_down_invariant(x, obc).output.numpy()[:, 0]
+    out['translations'] = ens.make_pbc_invariants(x, base, apply_also_obc_invariants=False).output.numpy()[:, 0]
+    path = os.path.join(OUT, 'reference_ensembles.npz')
+    np.savez_compressed(path, **out)
+    print('wrote', path, len(out), 'arrays')
+
+
 if __name__ == '__main__' and len(sys.argv) == 1:
     main()
+if __name__ == '__main__' and sys.argv[1:] == ['ensembles']:
+    ensembles()
 if __name__ == '__main__' and sys.argv[1:] == ['machines']:
     machines()
 if __name__ == '__main__' and sys.argv[1:] == ['complex_ops']:

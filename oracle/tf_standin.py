@@ -290,6 +290,13 @@ class Initializer(object):
     pass
 
 
+class Model(object):
+    """a finished eager computation: `output` is already a tensor"""
+
+    def __init__(self, inputs=None, outputs=None, **_ignored):
+        self.input, self.output = inputs, outputs
+
+
 def install():
     """register the stand-in under the module names the reference imports; returns the names so that the caller can
     remove them again"""
@@ -314,8 +321,11 @@ def install():
     layers = module('tensorflow.keras.layers', Layer=Layer, Wrapper=Wrapper, InputSpec=InputSpec, Lambda=Lambda,
                     Activation=Activation, Add=Add, Concatenate=Concatenate, ZeroPadding1D=ZeroPadding1D,
                     ZeroPadding2D=ZeroPadding2D, Conv1D=Conv1D, Conv2D=Conv2D, Input=None, Dense=None)
+    # images are [n, rows, cols, channels]; rot90 turns counter-clockwise like numpy / torch
+    image = types.SimpleNamespace(rot90=lambda x, k=1, name=None: torch.rot90(x, k, dims=(1, 2)),
+                                  flip_left_right=lambda x: torch.flip(x, dims=(2,)))
     initializers = module('tensorflow.keras.initializers', Initializer=Initializer)
-    models = module('tensorflow.keras.models', Model=object)
+    models = module('tensorflow.keras.models', Model=Model)
     keras = module('tensorflow.keras', backend=backend, layers=layers, initializers=initializers, models=models)
     py_keras = module('tensorflow.python.keras', backend=backend, layers=layers)
     public = lambda mod: {k: v for k, v in mod.__dict__.items() if not k.startswith('__')}     # noqa: E731
@@ -325,6 +335,8 @@ def install():
     ops = module('tensorflow.python.ops', parallel_for=pfor)
     python = module('tensorflow.python', keras=py_keras, ops=ops)
     module('tensorflow', math=math, nn=nn, linalg=linalg, keras=keras, python=python, complex=complex_, cast=cast,
+           image=image, expand_dims=lambda x, axis=-1, name=None: _t(x).unsqueeze(axis),
+           roll=lambda x, shift, axis, name=None: torch.roll(x, shifts=tuple(shift), dims=tuple(axis)),
            reshape=reshape, unstack=unstack, stack=stack, concat=concat, slice=slice_, zeros_like=zeros_like,
            one_hot=one_hot, name_scope=scope, TensorShape=TensorShape, float32=float32, float64=float64,
            complex64=complex64, complex128=complex128, int32=int32, int64=int64)

@@ -136,3 +136,28 @@ def test_device_gradients_match_autograd_through_the_reference_forward(name):
     want_re, want_im = g[name + '/jacobian_row3_real'], g[name + '/jacobian_row3_imag']
     assert np.linalg.norm(O_re.cpu().numpy()[0] - want_re) / np.linalg.norm(want_re) < 2e-5
     assert np.linalg.norm(O_im.cpu().numpy()[0] - want_im) / max(np.linalg.norm(want_im), 1e-30) < 2e-5
+
+
+def test_device_ensembles_match_the_reference_ensembles():
+    """golden tests/golden/reference_ensembles.npz: the reference's own symmetrisation ensembles around its own 2-D machine;
+    the product's EnsembleModel (device route) gets the same weights and spins."""
+    import os
+    import torch
+    from flowket_b200.machines import make_2d_obc_invariants, make_up_down_invariant, make_pbc_invariants
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_ensembles.npz'))
+    model, _, spec, _ = make_pair('conv2d', (4, 4), 2, 8, seed=0)
+    params = nets.unflatten_params(spec, torch.from_numpy(g['params']))
+    model.machine.set_weights([p.numpy().astype(np.float32) for p in params])
+    inp = model.input
+    sigma = g['sigma']
+
+    def same(got, want):
+        got = np.asarray(got)[:, 0]
+        assert np.abs(got.real - want.real).max() < 1e-5 * max(1.0, np.abs(want.real).max())
+        assert np.abs(np.exp(1j * got.imag) - np.exp(1j * want.imag)).max() < 1e-4
+
+    same(model.predict(sigma), g['base'])
+    same(make_2d_obc_invariants(inp, model).predict(sigma), g['obc'])
+    same(make_2d_obc_invariants(inp, model, probabilistic=False).predict(sigma), g['obc_average'])
+    same(make_up_down_invariant(inp, make_2d_obc_invariants(inp, model)).predict(sigma), g['up_down_of_obc'])
+    same(make_pbc_invariants(inp, model, apply_also_obc_invariants=False).predict(sigma), g['translations'])
