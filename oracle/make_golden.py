@@ -772,8 +772,62 @@ def ensembles():
     print('wrote', path, len(out), 'arrays')
 
 
+def sr_algebra():
+    """tests/golden/reference_sr_algebra.npz: the algebra of the reference's ComplexValuesStochasticReconfiguration
+    (optimizers/stochastic_reconfiguration/optimizer.py:33-124, complex_values_optimizer.py:48-58) on given per-sample
+    derivatives O [B, P] complex, targets y_true and complex weights: centred Jacobian, right-hand side, direct solve of
+    (Obar^H Obar / B + lambda I) delta = F, and the update of the (real, imag) variables.  The class cannot be instantiated
+    without Keras (it reads model.layers / .weights in its constructor), so its METHODS are bound to a plain namespace that
+    holds what the constructor would have stored; the bodies that run are the reference's."""
+    import torch
+    from oracle import tf_standin
+    load_reference_machines()            # installs the stand-in and the flowket package stubs
+    pkg = types.ModuleType('flowket.optimizers')
+    pkg.__path__ = [REF + '/optimizers']
+    sys.modules['flowket.optimizers'] = pkg
+    sub = types.ModuleType('flowket.optimizers.stochastic_reconfiguration')
+    sub.__path__ = [REF + '/optimizers/stochastic_reconfiguration']
+    sys.modules['flowket.optimizers.stochastic_reconfiguration'] = sub
+    le = types.ModuleType('flowket.optimizers.stochastic_reconfiguration.linear_equations')
+    le.conjugate_gradient = None          # (the TF while-loop solver is not run here; the direct solve is)
+    sys.modules[le.__name__] = le
+    sr_cls = importlib.import_module('flowket.optimizers.stochastic_reconfiguration.optimizer').ComplexValuesStochasticReconfiguration
+    rng = np.random.default_rng(20261023)
+    B, shapes = 40, [(3, 2, 4), (4,), (1, 4, 2), (2,)]               # two complex convs: kernel + bias each
+    P = sum(int(np.prod(sh)) for sh in shapes)
+    O = torch.from_numpy(rng.normal(size=(B, P)) + 1j * rng.normal(size=(B, P)))
+    e_loc = rng.normal(size=B) * 2 - 7 + 1j * rng.normal(size=B)
+    y_true = torch.from_numpy(np.conj(e_loc - e_loc.mean()) / B)      # what VariationalMonteCarlo feeds as targets
+    real = [tf_standin.Variable(rng.normal(size=sh)) for sh in shapes]
+    imag = [tf_standin.Variable(rng.normal(size=sh)) for sh in shapes]
+    me = types.SimpleNamespace(
+        batch_size=torch.tensor(complex(B)), diag_shift=0.05, lr=0.01, use_cholesky=True, add_s_matrix_stats=False,
+        use_energy_loss=False, iterative_solver=False,
+        predictions_keras_model=types.SimpleNamespace(output=torch.zeros((B, 1), dtype=torch.complex128), targets=[y_true]),
+        get_predictions_jacobian=lambda: O, model_real_weights=real, model_imag_weights=imag)
+    for name in ('get_wave_function_jacobian_minus_mean', 'get_energy_grad', '_update_s_matrix_stats',
+                 'compute_wave_function_gradient_covariance_inverse_multiplication',
+                 'compute_wave_function_gradient_covariance_inverse_multiplication_directly', 'apply_complex_gradient'):
+        setattr(me, name, types.MethodType(getattr(sr_cls, name), me))
+    o_bar = me.get_wave_function_jacobian_minus_mean()
+    energy_grad = me.get_energy_grad(None, o_bar)
+    delta = me.compute_wave_function_gradient_covariance_inverse_multiplication(energy_grad, o_bar)
+    updates = me.apply_complex_gradient(delta * (-1.0 + 0j))          # as in get_updates (optimizer.py:43)
+    out = {'O': O.numpy(), 'y_true': y_true.numpy(), 'diag_shift': np.float64(0.05), 'lr': np.float64(0.01),
+           'o_bar': o_bar.numpy(), 'energy_grad': energy_grad.numpy()[:, 0], 'delta': delta.numpy()[:, 0],
+           'weights_real': np.concatenate([np.asarray(w).reshape(-1) for w in real]),
+           'weights_imag': np.concatenate([np.asarray(w).reshape(-1) for w in imag]),
+           'new_weights_real': np.concatenate([np.asarray(new).reshape(-1) for _, new in updates[:len(shapes)]]),
+           'new_weights_imag': np.concatenate([np.asarray(new).reshape(-1) for _, new in updates[len(shapes):]])}
+    path = os.path.join(OUT, 'reference_sr_algebra.npz')
+    np.savez_compressed(path, **out)
+    print('wrote', path, len(out), 'arrays')
+
+
 if __name__ == '__main__' and len(sys.argv) == 1:
     main()
+if __name__ == '__main__' and sys.argv[1:] == ['sr']:
+    sr_algebra()
 if __name__ == '__main__' and sys.argv[1:] == ['ensembles']:
     ensembles()
 if __name__ == '__main__' and sys.argv[1:] == ['machines']:

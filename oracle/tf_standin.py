@@ -290,6 +290,31 @@ class Initializer(object):
     pass
 
 
+class _Shape(list):
+    def as_list(self):
+        return list(self)
+
+
+class Variable(torch.Tensor):
+    """a weight as the optimizer code sees it: `.shape.as_list()` exists (TF 1.x), arithmetic is torch's"""
+
+    @staticmethod
+    def __new__(cls, data):
+        return torch.Tensor._make_subclass(cls, torch.as_tensor(data))
+
+    @property
+    def shape(self):
+        return _Shape(super(Variable, self).shape)
+
+
+def _matmul(a, b, adjoint_a=False, transpose_a=False, name=None):
+    if adjoint_a:
+        a = a.conj().transpose(-1, -2)
+    elif transpose_a:
+        a = a.transpose(-1, -2)
+    return a @ b
+
+
 class Model(object):
     """a finished eager computation: `output` is already a tensor"""
 
@@ -314,8 +339,11 @@ def install():
         multiply=lambda x, y, name=None: _t(x) * y,
         reduce_sum=_reduce(torch.sum), reduce_mean=_reduce(torch.mean), reduce_logsumexp=_reduce(torch.logsumexp))
     nn = types.SimpleNamespace(relu=lambda x, name=None: torch.relu(x), l2_normalize=_l2_normalize, bias_add=_bias_add)
-    linalg = types.SimpleNamespace(norm=lambda x, axis=None: torch.linalg.vector_norm(x, dim=axis))
-    backend = module('tensorflow.keras.backend', int_shape=lambda x: tuple(x.shape),
+    linalg = types.SimpleNamespace(norm=lambda x, axis=None: torch.linalg.vector_norm(x, dim=axis),
+                                   cholesky=torch.linalg.cholesky, solve=torch.linalg.solve,
+                                   cholesky_solve=lambda chol, rhs: torch.cholesky_solve(rhs, chol))
+    backend = module('tensorflow.keras.backend', int_shape=lambda x: tuple(x.shape), update=lambda ref, value: (ref, value),
+                     name_scope=scope, variable=lambda value, **k: value, epsilon=lambda: 1e-7,
                      expand_dims=lambda x, axis=-1: _t(x).unsqueeze(axis), cast=cast, conv1d=_conv(1), conv2d=_conv(2),
                      set_floatx=lambda name: None)
     layers = module('tensorflow.keras.layers', Layer=Layer, Wrapper=Wrapper, InputSpec=InputSpec, Lambda=Lambda,
@@ -326,6 +354,7 @@ def install():
                                   flip_left_right=lambda x: torch.flip(x, dims=(2,)))
     initializers = module('tensorflow.keras.initializers', Initializer=Initializer)
     models = module('tensorflow.keras.models', Model=Model)
+    module('tensorflow.keras.optimizers', Optimizer=object)
     keras = module('tensorflow.keras', backend=backend, layers=layers, initializers=initializers, models=models)
     py_keras = module('tensorflow.python.keras', backend=backend, layers=layers)
     public = lambda mod: {k: v for k, v in mod.__dict__.items() if not k.startswith('__')}     # noqa: E731
@@ -336,6 +365,10 @@ def install():
     python = module('tensorflow.python', keras=py_keras, ops=ops)
     module('tensorflow', math=math, nn=nn, linalg=linalg, keras=keras, python=python, complex=complex_, cast=cast,
            image=image, expand_dims=lambda x, axis=-1, name=None: _t(x).unsqueeze(axis),
+           shape=lambda x, name=None: list(_t(x).shape), matmul=_matmul, conj=lambda x, name=None: torch.conj(_t(x)).resolve_conj(),
+           eye=lambda n, dtype=None, name=None: torch.eye(int(n), dtype=_torch_dtype(dtype)), squeeze=lambda x, axis=None: _t(x).squeeze(),
+           control_dependencies=lambda deps: contextlib.nullcontext(), stop_gradient=lambda x, name=None: x, no_op=lambda: None,
+           __version__='1.13.1',
            roll=lambda x, shift, axis, name=None: torch.roll(x, shifts=tuple(shift), dims=tuple(axis)),
            reshape=reshape, unstack=unstack, stack=stack, concat=concat, slice=slice_, zeros_like=zeros_like,
            one_hot=one_hot, name_scope=scope, TensorShape=TensorShape, float32=float32, float64=float64,
