@@ -824,8 +824,81 @@ def sr_algebra():
     print('wrote', path, len(out), 'arrays')
 
 
+def conjugate_gradient_solver():
+    """tests/golden/reference_conjugate_gradient.npz: the reference's conjugate-gradient solver
+    (optimizers/stochastic_reconfiguration/linear_equations.py:34-137, the TF-contrib solver it vendors) on complex
+    Hermitian positive-definite systems, at the loose tolerance the SR optimizer uses (1e-3) and a tight one.  The TF
+    internals it imports are replaced by their meaning: vdot, norm, expand_dims / squeeze, and `while_loop` as a Python
+    loop."""
+    import torch
+    from oracle import tf_standin
+    tf_standin.install()
+
+    def module(name, **attrs):
+        mod = types.ModuleType(name)
+        mod.__dict__.update(attrs)
+        sys.modules[name] = mod
+        return mod
+
+    def while_loop(cond, body, loop_vars):
+        loop_vars = list(loop_vars)
+        while bool(cond(*loop_vars)):
+            loop_vars = list(body(*loop_vars))
+        return loop_vars
+    tf = sys.modules['tensorflow']
+    module('tensorflow.contrib')
+    module('tensorflow.contrib.solvers')
+    module('tensorflow.contrib.solvers.python')
+    util = module('tensorflow.contrib.solvers.python.ops.util', dot=lambda x, y: torch.sum(torch.conj(x) * y))
+    module('tensorflow.contrib.solvers.python.ops', util=util)
+    module('tensorflow.python.framework')
+    module('tensorflow.python.framework.constant_op', constant=lambda v, dtype=None: v)
+    module('tensorflow.python.framework.dtypes', int32=tf.int32)
+    module('tensorflow.python.framework.ops', name_scope=tf.name_scope)
+    module('tensorflow.python.ops.array_ops', expand_dims=lambda x, axis: x.unsqueeze(axis), squeeze=lambda x: x.squeeze(),
+           zeros=lambda n, dtype=None: torch.zeros(tuple(int(v) for v in n), dtype=dtype))
+    module('tensorflow.python.ops.control_flow_ops', while_loop=while_loop)
+    module('tensorflow.python.ops.linalg_ops', norm=lambda v: torch.linalg.vector_norm(v))
+    module('tensorflow.python.ops.math_ops', logical_and=lambda a, b: bool(a) and bool(b),
+           cast=lambda x, dtype: torch.as_tensor(x).to(torch.float32))
+    pkg = types.ModuleType('flowket')
+    pkg.__path__ = [REF]
+    sys.modules['flowket'] = pkg
+    for name, path in [('flowket.optimizers', '/optimizers'),
+                       ('flowket.optimizers.stochastic_reconfiguration', '/optimizers/stochastic_reconfiguration')]:
+        mod = types.ModuleType(name)
+        mod.__path__ = [REF + path]
+        sys.modules[name] = mod
+    le = importlib.import_module('flowket.optimizers.stochastic_reconfiguration.linear_equations')
+    Operator = __import__('collections').namedtuple('Operator', 'shape,dtype,apply')
+    rng = np.random.default_rng(20261024)
+    out = {}
+    for name, n, cond_spread, tol, max_iter in [('loose', 60, 3.0, 1e-3, 200), ('tight', 60, 3.0, 1e-6, 500),
+                                                ('capped', 80, 5.0, 1e-12, 7)]:
+        A = rng.normal(size=(n, 2 * n)) + 1j * rng.normal(size=(n, 2 * n))
+        A = A * np.logspace(0, -cond_spread, n)[:, None]
+        S = torch.from_numpy(A @ A.conj().T / (2 * n) + 0.05 * np.eye(n))
+        rhs = torch.from_numpy(rng.normal(size=n) + 1j * rng.normal(size=n))
+
+        op = Operator(shape=[n, n], dtype=torch.complex128, apply=lambda v, S=S: S @ v)
+        x0 = torch.zeros(n, dtype=torch.complex128)    # explicit start vector: the zeros() branch needs dtype.base_dtype
+        res = le.conjugate_gradient(op, rhs, x=x0, tol=tol, max_iter=max_iter)
+        out[name + '/S'] = S.numpy()
+        out[name + '/rhs'] = rhs.numpy()
+        out[name + '/tol'] = np.float64(tol)
+        out[name + '/max_iter'] = np.int64(max_iter)
+        out[name + '/x'] = res.x.numpy()
+        out[name + '/iterations'] = np.int64(int(res.i))
+        out[name + '/residual_norm'] = np.float64(float(torch.linalg.vector_norm(res.r)))
+    path = os.path.join(OUT, 'reference_conjugate_gradient.npz')
+    np.savez_compressed(path, **out)
+    print('wrote', path, len(out), 'arrays', {k: int(out[k]) for k in out if k.endswith('iterations')})
+
+
 if __name__ == '__main__' and len(sys.argv) == 1:
     main()
+if __name__ == '__main__' and sys.argv[1:] == ['cg']:
+    conjugate_gradient_solver()
 if __name__ == '__main__' and sys.argv[1:] == ['sr']:
     sr_algebra()
 if __name__ == '__main__' and sys.argv[1:] == ['ensembles']:
