@@ -395,43 +395,3 @@ def test_compile_and_fit_generator_exact_gradient_script_flow():
     assert all(e > e_ed - 1e-6 for e in energies)                 # variational principle
     assert logs[-1]['energy/relative_error'] == pytest.approx((e_ed - energies[-1]) / e_ed)
     assert 'observables/sigma_z' in logs[-1] and 'times/total' in logs[-1]
-
-
-def test_sr_optimizer_through_compile_and_flattened_operator():
-    """BASELINE configs[3] composition: J1J2 lattice operator seen through raster-flattened configurations by the complex
-    1-D machine, ComplexValuesStochasticReconfiguration passed to compile() like any Keras optimizer."""
-    from flowket_b200 import Input, Model
-    from flowket_b200.callbacks import TerminateOnNaN
-    from flowket_b200.callbacks.monte_carlo import default_wave_function_stats_callbacks_factory
-    from flowket_b200.machines import ComplexValuesSimpleConvNetAutoregressive1D
-    from flowket_b200.operators import J1J2, FlattenedOperator
-    from flowket_b200.optimization import VariationalMonteCarlo, loss_for_energy_minimization
-    from flowket_b200.optimizers import ComplexValuesStochasticReconfiguration
-    from flowket_b200.samplers import FastAutoregressiveSampler
-    lattice = J1J2(hilbert_state_shape=[4, 4], j2=0.5, pbc=False)
-    operator = FlattenedOperator(lattice)
-    sigma = random_sigma(9, (4, 4), seed=3)
-    conn, mel, use = lattice.find_conn(sigma)
-    fconn, fmel, fuse = operator.find_conn(sigma.reshape(9, 16))
-    assert np.array_equal(fconn.reshape(conn.shape), conn) and np.array_equal(fmel, mel) and np.array_equal(fuse, use)
-    inputs = Input(shape=(16,), dtype='int8')
-    convnet = ComplexValuesSimpleConvNetAutoregressive1D(inputs, depth=3, num_of_channels=8, max_dilation_rate=4, seed=0)
-    model = Model(inputs=inputs, outputs=convnet.predictions)
-    cond = Model(inputs=inputs, outputs=convnet.conditional_log_probs)
-    optimizer = ComplexValuesStochasticReconfiguration(model, lr=0.02, diag_shift=0.05, iterative_solver=False)
-    model.compile(optimizer=optimizer, loss=loss_for_energy_minimization)
-    vmc = VariationalMonteCarlo(model, operator, FastAutoregressiveSampler(cond, 512, seed=2))
-    # the flattened operator gives the same local energies as the oracle on the lattice
-    x, _ = vmc.next_batch()
-    oop = oops.OracleOperator('j1j2', (4, 4), j2=0.5, pbc=False)
-    spec = nets.ComplexConv1DSpec(16, 3, 8, max_dilation_rate=4)
-    params = [torch.from_numpy(w.astype(np.float64)) for w in convnet.get_weights()]
-    want = oeloc.local_values(oop, lambda c: nets.log_psi_numpy(spec, params, np.asarray(c).reshape(len(c), 16)),
-                              x[:32].reshape(32, 4, 4).astype(np.float64))
-    assert np.abs(vmc.current_local_energy[:32] - want).max() / np.abs(want).max() < 1e-4
-    before = convnet.flat_params_device().clone()
-    callbacks = default_wave_function_stats_callbacks_factory(vmc, log_in_batch_or_epoch=False) + [TerminateOnNaN()]
-    logs = model.fit_generator(vmc.to_generator(), steps_per_epoch=5, epochs=4, callbacks=callbacks, max_queue_size=0, workers=0)
-    assert len(logs) == 4 and all(np.isfinite(l['energy/energy']) for l in logs)
-    assert (convnet.flat_params_device() - before).abs().max().item() > 0          # SR moved the parameters
-    assert np.mean([l['energy/energy'] for l in logs[2:]]) < logs[0]['energy/energy'] + 5.0   # and not uphill (512-sample noise)
