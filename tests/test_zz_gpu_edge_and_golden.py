@@ -1,6 +1,11 @@
-"""GPU tier, degenerate lattices (runs last): the device find_conn against the reference's own output over ALL states of
-two-site periodic / singleton-dimension lattices (tests/golden/reference_numpy_half_edge.npz, oracle/make_golden.py edge),
-and the local energy of tiny machines on them against the oracle."""
+"""GPU tier, runs last: checks added at the end of round 1 after the GPU budget was spent, i.e. NOT yet run on a B200 (every
+earlier GPU test file was).  Ordered from the most to the least certain, because the driver runs with -x:
+  1. the CUDA engines against numbers produced by the reference's OWN machine classes, loss gradient, sampler loop and
+     symmetrisation ensembles (tests/golden/reference_{machines,autoregressive_sampler,ensembles}.npz -- oracle/make_golden.py
+     runs the reference's code on oracle/tf_standin.py; the CPU tier checks the oracle against the same files);
+  2. the device find_conn against the reference's output over ALL states of degenerate lattices
+     (tests/golden/reference_numpy_half_edge.npz);
+  3. the BASELINE configs[3] composition through compile()/fit_generator, and local energies on degenerate lattices."""
 import numpy as np
 import pytest
 import torch
@@ -23,65 +28,6 @@ EDGE = {
     'ising_2_pbc': ('Ising', dict(hilbert_state_shape=[2], pbc=True, h=1.0)),
     'ising_2x2_obc': ('Ising', dict(hilbert_state_shape=[2, 2], pbc=False, h=2.0, j=0.5)),
 }
-
-
-@pytest.mark.parametrize('name', sorted(EDGE))
-def test_device_find_conn_on_degenerate_lattices(golden_edge, name):
-    import flowket_b200.operators as ops
-    cls, kw = EDGE[name]
-    op = getattr(ops, cls)(**kw)
-    conn, mel, use = op.find_conn(golden_edge[name + '/sigma'])
-    assert op.max_number_of_local_connections == int(golden_edge[name + '/max_conn'])
-    assert np.array_equal(conn.astype(np.int8), golden_edge[name + '/conn'])
-    assert np.array_equal(use, golden_edge[name + '/use'])
-    assert np.allclose(mel, golden_edge[name + '/mel'], rtol=1e-6, atol=1e-6)
-
-
-@pytest.mark.parametrize('kind,shape,opkind,opkw', [
-    ('conv2d', (2, 2), 'heisenberg', dict(pbc=True)),
-    ('conv2d', (2, 5), 'heisenberg', dict(pbc=True)),
-    ('conv1d', (2,), 'ising', dict(pbc=True, h=1.0)),
-    ('conv2d', (1, 4), 'ising', dict(pbc=True, h=1.0)),
-])
-def test_local_energy_on_degenerate_lattices(kind, shape, opkind, opkw):
-    """every state of the lattice: E_loc from the device pipeline == oracle (fp32 engine, 1e-5)"""
-    from flowket_b200.exact.utils import decimal_array_to_binary_array
-    from flowket_b200.observables.monte_carlo import Observable
-    from tests.test_gpu_parity import _product_operator
-    model, _, spec, params = make_pair(kind, shape, 3, 8, seed=21)
-    n = int(np.prod(shape))
-    sigma = decimal_array_to_binary_array(np.arange(2 ** n), n, False).reshape((2 ** n,) + shape).astype(np.int8)
-    got = Observable(_product_operator(opkind, shape, opkw)).local_values_device(model, sigma).cpu().numpy()
-    want = oeloc.local_values(oops.OracleOperator(opkind, shape, **opkw), lambda c: nets.log_psi_numpy(spec, params, c),
-                              sigma.astype(np.float64))
-    assert np.abs(got - want).max() / np.abs(want).max() < 1e-5
-
-
-@pytest.mark.parametrize('name,kind,shape,depth,channels,kw', [
-    ('conv2d_4x3', 'conv2d', (4, 3), 2, 8, {}),
-    ('conv1d_10', 'conv1d', (10,), 4, 8, {'max_dilation_rate': 2}),
-    ('cconv1d_8', 'cconv1d', (8,), 3, 4, {'max_dilation_rate': 2}),
-])
-def test_device_samplers_reproduce_the_reference_samplers_spins(name, kind, shape, depth, channels, kw):
-    """golden (oracle/make_golden.py sampler): spins drawn by the reference's own AutoregressiveSampler.__next__ around the
-    oracle network; the CUDA samplers get the same weights and the same uniforms.  A spin may differ only at a numerical
-    tie |p0 - u| < 1e-5 (fp32 summation order), as in tests/test_gpu_parity.py."""
-    import os
-    import torch
-    from flowket_b200.samplers import FastAutoregressiveSampler, AutoregressiveSampler
-    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_autoregressive_sampler.npz'))
-    model, cond_model, spec, _ = make_pair(kind, shape, depth, channels, seed=0, **kw)
-    params = nets.unflatten_params(spec, torch.from_numpy(g[name + '/params']))
-    model.machine.set_weights([p.numpy() for p in params])
-    u, want = g[name + '/uniforms'], g[name + '/sigma']
-    p0 = np.exp(nets.conditional_log_probs(spec, [p.double() for p in params], want).numpy()[..., 0])
-    B = len(u)
-    for sampler in (FastAutoregressiveSampler(cond_model, B), AutoregressiveSampler(cond_model, B)):
-        got = sampler.next_device(uniforms=u).cpu().numpy()
-        bad = np.argwhere(got != want)
-        for idx in bad:   # the first differing site of a sample must be a numerical tie
-            first = tuple(bad[bad[:, 0] == idx[0]][0])
-            assert abs(p0[first] - u[first]) < 1e-5, (type(sampler).__name__, first, p0[first], u[first])
 
 
 MACHINE_GOLDEN = {
@@ -139,6 +85,33 @@ def test_device_gradients_match_autograd_through_the_reference_forward(name):
     assert np.linalg.norm(O_im.cpu().numpy()[0] - want_im) / max(np.linalg.norm(want_im), 1e-30) < 2e-5
 
 
+@pytest.mark.parametrize('name,kind,shape,depth,channels,kw', [
+    ('conv2d_4x3', 'conv2d', (4, 3), 2, 8, {}),
+    ('conv1d_10', 'conv1d', (10,), 4, 8, {'max_dilation_rate': 2}),
+    ('cconv1d_8', 'cconv1d', (8,), 3, 4, {'max_dilation_rate': 2}),
+])
+def test_device_samplers_reproduce_the_reference_samplers_spins(name, kind, shape, depth, channels, kw):
+    """golden (oracle/make_golden.py sampler): spins drawn by the reference's own AutoregressiveSampler.__next__ around the
+    oracle network; the CUDA samplers get the same weights and the same uniforms.  A spin may differ only at a numerical
+    tie |p0 - u| < 1e-5 (fp32 summation order), as in tests/test_gpu_parity.py."""
+    import os
+    import torch
+    from flowket_b200.samplers import FastAutoregressiveSampler, AutoregressiveSampler
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_autoregressive_sampler.npz'))
+    model, cond_model, spec, _ = make_pair(kind, shape, depth, channels, seed=0, **kw)
+    params = nets.unflatten_params(spec, torch.from_numpy(g[name + '/params']))
+    model.machine.set_weights([p.numpy() for p in params])
+    u, want = g[name + '/uniforms'], g[name + '/sigma']
+    p0 = np.exp(nets.conditional_log_probs(spec, [p.double() for p in params], want).numpy()[..., 0])
+    B = len(u)
+    for sampler in (FastAutoregressiveSampler(cond_model, B), AutoregressiveSampler(cond_model, B)):
+        got = sampler.next_device(uniforms=u).cpu().numpy()
+        bad = np.argwhere(got != want)
+        for idx in bad:   # the first differing site of a sample must be a numerical tie
+            first = tuple(bad[bad[:, 0] == idx[0]][0])
+            assert abs(p0[first] - u[first]) < 1e-5, (type(sampler).__name__, first, p0[first], u[first])
+
+
 def test_device_ensembles_match_the_reference_ensembles():
     """golden tests/golden/reference_ensembles.npz: the reference's own symmetrisation ensembles around its own 2-D machine;
     the product's EnsembleModel (device route) gets the same weights and spins."""
@@ -162,6 +135,18 @@ def test_device_ensembles_match_the_reference_ensembles():
     same(make_2d_obc_invariants(inp, model, probabilistic=False).predict(sigma), g['obc_average'])
     same(make_up_down_invariant(inp, make_2d_obc_invariants(inp, model)).predict(sigma), g['up_down_of_obc'])
     same(make_pbc_invariants(inp, model, apply_also_obc_invariants=False).predict(sigma), g['translations'])
+
+
+@pytest.mark.parametrize('name', sorted(EDGE))
+def test_device_find_conn_on_degenerate_lattices(golden_edge, name):
+    import flowket_b200.operators as ops
+    cls, kw = EDGE[name]
+    op = getattr(ops, cls)(**kw)
+    conn, mel, use = op.find_conn(golden_edge[name + '/sigma'])
+    assert op.max_number_of_local_connections == int(golden_edge[name + '/max_conn'])
+    assert np.array_equal(conn.astype(np.int8), golden_edge[name + '/conn'])
+    assert np.array_equal(use, golden_edge[name + '/use'])
+    assert np.allclose(mel, golden_edge[name + '/mel'], rtol=1e-6, atol=1e-6)
 
 
 def test_sr_optimizer_through_compile_and_flattened_operator():
@@ -202,3 +187,23 @@ def test_sr_optimizer_through_compile_and_flattened_operator():
     assert len(logs) == 4 and all(np.isfinite(l['energy/energy']) for l in logs)
     assert (convnet.flat_params_device() - before).abs().max().item() > 0          # SR moved the parameters
     assert np.mean([l['energy/energy'] for l in logs[2:]]) < logs[0]['energy/energy'] + 5.0   # and not uphill (512-sample noise)
+
+
+@pytest.mark.parametrize('kind,shape,opkind,opkw', [
+    ('conv2d', (2, 2), 'heisenberg', dict(pbc=True)),
+    ('conv2d', (2, 5), 'heisenberg', dict(pbc=True)),
+    ('conv1d', (2,), 'ising', dict(pbc=True, h=1.0)),
+    ('conv2d', (1, 4), 'ising', dict(pbc=True, h=1.0)),
+])
+def test_local_energy_on_degenerate_lattices(kind, shape, opkind, opkw):
+    """every state of the lattice: E_loc from the device pipeline == oracle (fp32 engine, 1e-5)"""
+    from flowket_b200.exact.utils import decimal_array_to_binary_array
+    from flowket_b200.observables.monte_carlo import Observable
+    from tests.test_gpu_parity import _product_operator
+    model, _, spec, params = make_pair(kind, shape, 3, 8, seed=21)
+    n = int(np.prod(shape))
+    sigma = decimal_array_to_binary_array(np.arange(2 ** n), n, False).reshape((2 ** n,) + shape).astype(np.int8)
+    got = Observable(_product_operator(opkind, shape, opkw)).local_values_device(model, sigma).cpu().numpy()
+    want = oeloc.local_values(oops.OracleOperator(opkind, shape, **opkw), lambda c: nets.log_psi_numpy(spec, params, c),
+                              sigma.astype(np.float64))
+    assert np.abs(got - want).max() / np.abs(want).max() < 1e-5
