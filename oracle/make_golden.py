@@ -895,32 +895,6 @@ def conjugate_gradient_solver():
     print('wrote', path, len(out), 'arrays', {k: int(out[k]) for k in out if k.endswith('iterations')})
 
 
-if __name__ == '__main__' and len(sys.argv) == 1:
-    main()
-if __name__ == '__main__' and sys.argv[1:] == ['cg']:
-    conjugate_gradient_solver()
-if __name__ == '__main__' and sys.argv[1:] == ['sr']:
-    sr_algebra()
-if __name__ == '__main__' and sys.argv[1:] == ['ensembles']:
-    ensembles()
-if __name__ == '__main__' and sys.argv[1:] == ['machines']:
-    machines()
-if __name__ == '__main__' and sys.argv[1:] == ['complex_ops']:
-    complex_ops()
-if __name__ == '__main__' and sys.argv[1:] == ['sampler']:
-    autoregressive_sampler()
-if __name__ == '__main__' and sys.argv[1:] == ['callbacks']:
-    callbacks_logs()
-if __name__ == '__main__' and sys.argv[1:] == ['vmc']:
-    variational_monte_carlo()
-if __name__ == '__main__' and sys.argv[1:] == ['exact']:
-    exact_variational()
-if __name__ == '__main__' and sys.argv[1:] == ['j1j2']:
-    j1j2_graph()
-if __name__ == '__main__' and sys.argv[1:] == ['mcmc']:
-    mcmc_diagnostics()
-if __name__ == '__main__' and sys.argv[1:] == ['edge']:
-    edge_cases()
 
 
 PRETRAINED = {'2': 'ising_2.h5', '2_5': 'ising_2_5.h5', '3': 'ising_3.h5', '3_5': 'ising_3_5.h5', '4': 'ising_4.h5'}
@@ -944,5 +918,36 @@ def export_pretrained_weights():
         print('wrote', path, sum(a.size for a in w), 'parameters')
 
 
-if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'weights':
-    export_pretrained_weights()
+
+
+COMMANDS = {
+    'numpy_half': main,                          # operators / local energy / bit conventions / ED anchors
+    'edge': edge_cases,                          # find_conn over all states of degenerate lattices
+    'mcmc': mcmc_diagnostics,                    # calc_r_hat_value / sum_correlations
+    'j1j2': j1j2_graph,                          # coloured edge list + bond operators handed to netket
+    'exact': exact_variational,                  # ExactVariational / ExactObservable
+    'vmc': variational_monte_carlo,              # VariationalMonteCarlo + MiniBatchGenerator
+    'callbacks': callbacks_logs,                 # stats callbacks, evaluate, exact_evaluate, BadEigenStateStopping
+    'sampler': autoregressive_sampler,           # AutoregressiveSampler.__next__ around the oracle network
+    'complex_ops': complex_ops,                  # lncosh / complex_log / ensemble ops
+    'machines': machines,                        # the three machine classes + gradients (oracle/tf_standin.py)
+    'ensembles': ensembles,                      # symmetrisation ensembles around the 2-D machine
+    'sr': sr_algebra,                            # ComplexValuesStochasticReconfiguration methods
+    'cg': conjugate_gradient_solver,             # the vendored conjugate-gradient solver
+    'weights': export_pretrained_weights,        # experiments/weights/ising_*.h5 -> npz
+}
+
+
+if __name__ == '__main__':
+    # every generator installs its own module stand-ins: run each in a fresh interpreter
+    #   python -m oracle.make_golden            -> numpy_half
+    #   python -m oracle.make_golden machines   -> one fixture
+    #   python -m oracle.make_golden all        -> everything, one subprocess per fixture
+    names = sys.argv[1:] or ['numpy_half']
+    if names == ['all']:
+        import subprocess
+        for name in COMMANDS:
+            subprocess.check_call([sys.executable, '-m', 'oracle.make_golden', name])
+    else:
+        for name in names:
+            COMMANDS[name]()
