@@ -676,6 +676,8 @@ MACHINE_CASES = [
     ('conv1d_9_d6_nodil', 'conv1d', (9,), dict(depth=6, num_of_channels=4, use_dilation=False, max_dilation_rate=4)),
     ('cconv1d_10_d4_dil2', 'cconv1d', (10,), dict(depth=4, num_of_channels=6, max_dilation_rate=2)),
     ('cconv1d_8_d3', 'cconv1d', (8,), dict(depth=3, num_of_channels=4)),
+    # the width the tensor-core engines are built for (32 channels)
+    ('conv2d_6x6_d3_c32', 'conv2d', (6, 6), dict(depth=3, num_of_channels=32)),
 ]
 
 

@@ -85,6 +85,34 @@ def test_device_gradients_match_autograd_through_the_reference_forward(name):
     assert np.linalg.norm(O_im.cpu().numpy()[0] - want_im) / max(np.linalg.norm(want_im), 1e-30) < 2e-5
 
 
+def test_tensor_core_engine_matches_the_reference_machine_class():
+    """the 32-channel machine of tests/golden/reference_machines.npz through the tcgen05 engines: log psi within the
+    tensor-core tolerance of tests/test_gpu_tc.py (|d| <= 0.05 + 2e-3 |log psi|), weighted gradient within 2e-2 in norm --
+    against numbers from the reference's own machine code, not only against this repository's fp32 engine"""
+    import os
+    import torch
+    from flowket_b200 import FK_ENGINE_TC, FK_ENGINE_FP32
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_machines.npz'))
+    name = 'conv2d_6x6_d3_c32'
+    model, _, spec, _ = make_pair('conv2d', (6, 6), 3, 32, seed=0)
+    params = nets.unflatten_params(spec, torch.from_numpy(g[name + '/params']))
+    model.machine.set_weights([p.numpy().astype(np.float32) for p in params])
+    sigma, want = g[name + '/sigma'], g[name + '/log_psi']
+    got32 = model.predict(sigma)[:, 0]
+    assert np.abs(got32.real - want.real).max() < 1e-5 * max(1.0, np.abs(want.real).max())
+    model.engine = FK_ENGINE_TC
+    got = model.predict(sigma)[:, 0]
+    assert np.all(np.abs(got.real - want.real) <= 0.05 + 2e-3 * np.abs(want.real))
+    assert np.abs(np.exp(1j * got.imag) - np.exp(1j * want.imag)).max() < 0.05
+    net = model.machine.device_net()
+    y = torch.from_numpy(g[name + '/y'].astype(np.complex64))
+    want_g = g[name + '/weighted_gradient']
+    g32 = net.grad_weighted(net.to_sigma(sigma), y, engine=FK_ENGINE_FP32).cpu().numpy().astype(np.float64)
+    assert np.linalg.norm(g32 - want_g) / np.linalg.norm(want_g) < 2e-5
+    gtc = net.grad_weighted(net.to_sigma(sigma), y, engine=FK_ENGINE_TC).cpu().numpy().astype(np.float64)
+    assert np.linalg.norm(gtc - want_g) / np.linalg.norm(want_g) < 2e-2
+
+
 @pytest.mark.parametrize('name,kind,shape,depth,channels,kw', [
     ('conv2d_4x3', 'conv2d', (4, 3), 2, 8, {}),
     ('conv1d_10', 'conv1d', (10,), 4, 8, {'max_dilation_rate': 2}),
