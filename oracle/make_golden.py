@@ -922,6 +922,124 @@ def export_pretrained_weights():
 
 
 
+def fast_sampler():
+    """tests/golden/reference_fast_sampler.npz: the reference's own FastAutoregressiveSampler
+    (deepar/samplers/fast_autoregressive.py:13-76) with its DependencyGraph (deepar/graph_analysis/dependency_graph.py:35-94)
+    and every layer topology it needs (convolution incl. weight-norm wrappers and complex convolutions, zero padding, down /
+    right shifts, one-to-one layers, concatenation, the +-1 sampling topology) around the reference's own machines.
+    The stand-in records which layer feeds which while the machine is built (the information Keras keeps in
+    `inbound_nodes`), evaluates the per-site operations the sampler schedules eagerly, and defines `tf.multinomial` -- the
+    one unseeded primitive -- by the explicit-uniform rule with injected uniforms, handed out in the order in which the
+    sampler visits the sites.  Result: the spins the reference's cached incremental sampler draws for given weights and
+    uniforms, to be compared with the N-forward rule (oracle) and the CUDA samplers."""
+    import networkx  # noqa: F401  (the reference's dependency graph needs it)
+    if not hasattr(np, 'product'):
+        np.product = np.prod                 # alias the reference still uses (removed in numpy 2)
+    import torch
+    from oracle import nets, tf_standin
+    tf_standin.install()
+
+    def package(name, path):
+        mod = types.ModuleType(name)
+        mod.__path__ = [path]
+        sys.modules[name] = mod
+        return mod
+    imp = importlib.import_module
+    package('flowket', REF)
+    package('flowket.machines', REF + '/machines')
+    layers = package('flowket.layers', REF + '/layers')
+    package('flowket.layers.complex', REF + '/layers/complex')
+    package('flowket.deepar', REF + '/deepar')
+    package('flowket.deepar.utils', REF + '/deepar/utils').Singleton = imp('flowket.deepar.utils.singleton').Singleton
+    deepar_layers = package('flowket.deepar.layers', REF + '/deepar/layers')
+    package('flowket.deepar.samplers', REF + '/deepar/samplers')
+    ga = package('flowket.deepar.graph_analysis', REF + '/deepar/graph_analysis')
+    for sub, names in [('autoregressive', ['NormalizeInLogSpace', 'CombineAutoregressiveConditionals']),
+                       ('casting', ['CastingLayer', 'ToFloat32', 'ToFloat64']),
+                       ('lambda_with_one_to_one_topology', ['LambdaWithOneToOneTopology']),
+                       ('masking', ['DownShiftLayer', 'RightShiftLayer']),
+                       ('one_hot', ['ToOneHot', 'PlusMinusOneToOneHot']),
+                       ('padding', ['ExpandInputDim', 'PeriodicPadding']),
+                       ('wrappers', ['WeightNormalization']),
+                       ('layer_normalization', ['LayerNormalization'])]:
+        mod = imp('flowket.deepar.layers.' + sub)
+        for n in names:
+            setattr(deepar_layers, n, getattr(mod, n))
+    for sub, names in [('topology_manager', ['TopologyManager']), ('layer_topology', ['LayerTopology']),
+                       ('data_structures', ['Dependency', 'GraphNode']),
+                       ('one_to_one_topology', ['OneToOneTopology', 'OneToOneTopologyWithIdentity']),
+                       ('convolutional_topology', ['ConvolutionalTopology']), ('padding_topology', ['PaddingTopology']),
+                       ('masking_topology', ['DownShiftTopology', 'RightShiftTopology']),
+                       ('concatenate_topology', ['ConcatenateTopology']),
+                       ('sampling_topology', ['PlusMinusOneSamplingTopology', 'CategorialSamplingTopology']),
+                       ('dependency_graph', ['DependencyGraph'])]:
+        mod = imp('flowket.deepar.graph_analysis.' + sub)
+        for n in names:
+            setattr(ga, n, getattr(mod, n))
+    module = types.ModuleType('flowket.layers.complex.initializers')
+    module.ConjugateDecorator = type('ConjugateDecorator', (), {
+        '__init__': lambda self, initializer: None, 'get_real_part_initializer': lambda self: None,
+        'get_imag_part_initializer': lambda self: None})
+    module.get = lambda identifier: identifier
+    sys.modules[module.__name__] = module
+    casting = imp('flowket.layers.complex.casting')
+    conv = imp('flowket.layers.complex.conv')
+    spins = imp('flowket.layers.spins_invariants')
+    for mod, names in [(casting, ['VectorToComplexNumber', 'ToComplex64', 'ToComplex128']), (conv, ['ComplexConv1D']),
+                       (spins, ['EqualUpDownSpins'])]:
+        for n in names:
+            setattr(layers, n, getattr(mod, n))
+    # +-1 spins: flowket/samplers/fast_autoregressive/__init__.py:8
+    ga.TopologyManager().register_layer_topology(tf_standin.InputLayer, ga.PlusMinusOneSamplingTopology)
+    fast_cls = imp('flowket.deepar.samplers.fast_autoregressive').FastAutoregressiveSampler
+    classes = {'conv2d': imp('flowket.machines.conv_net_autoregressive_2D').ConvNetAutoregressive2D,
+               'conv1d': imp('flowket.machines.simple_conv_net_autoregressive_1D').SimpleConvNetAutoregressive1D,
+               'cconv1d': imp('flowket.machines.complex_values_simple_conv_net_autoregressive_1D').ComplexValuesSimpleConvNetAutoregressive1D}
+    rng = np.random.default_rng(20261025)
+    out = {}
+    for name, kind, shape, kw, spec in [
+        ('conv2d_4x3', 'conv2d', (4, 3), dict(depth=2, num_of_channels=8), nets.Conv2DSpec(4, 3, 2, 8)),
+        ('conv2d_3x3_d3', 'conv2d', (3, 3), dict(depth=3, num_of_channels=4), nets.Conv2DSpec(3, 3, 3, 4)),
+        ('conv1d_10', 'conv1d', (10,), dict(depth=4, num_of_channels=8, max_dilation_rate=2, add_skip_connections=True),
+         nets.Conv1DSpec(10, 4, 8, max_dilation_rate=2, add_skip_connections=True)),
+        ('cconv1d_8', 'cconv1d', (8,), dict(depth=3, num_of_channels=4, max_dilation_rate=2),
+         nets.ComplexConv1DSpec(8, 3, 4, max_dilation_rate=2)),
+    ]:
+        B = 24
+        params = [p + 0.3 * torch.randn(p.shape, dtype=torch.float64, generator=torch.Generator().manual_seed(7 + i)) * (p.dim() == 1)
+                  for i, p in enumerate(nets.init_params(spec, seed=5, dtype=torch.float64))]
+        uniforms = rng.random((B,) + shape)
+
+        def build_sampler(uniform_queue):
+            tf_standin.inject_weights([p.numpy() for p in params])
+            tf_standin.BATCH[0] = B
+            del tf_standin.UNIFORMS[:]
+            tf_standin.UNIFORMS.extend(uniform_queue)
+            tf_standin.MULTINOMIAL_CALLS[0] = 0
+            x = torch.zeros((B,) + shape, dtype=torch.float64)          # the machine is built on a placeholder batch
+            tf_standin.InputLayer(x, dtype='int8')
+            tf_standin.RECORDING[0] = True
+            machine = classes[kind](x, **kw)
+            model = tf_standin.GraphModel(x, machine.conditional_log_probs)
+            tf_standin.RECORDING[0] = False
+            return fast_cls(model, B)
+
+        probe = build_sampler([])                                        # pass 1: in which order are the sites visited?
+        order = [node.spatial_location for node in probe.sampling_order if node.layer is probe.input_layer]
+        assert sorted(order) == sorted(np.ndindex(*shape)) and tf_standin.MULTINOMIAL_CALLS[0] == len(order)
+        sampler = build_sampler([uniforms[(slice(None),) + site] for site in order])          # pass 2: the real draw
+        sigma = np.asarray(next(sampler)).astype(np.int8)
+        assert sigma.shape == (B,) + shape and not tf_standin.UNIFORMS
+        out[name + '/params'] = nets.flatten_params(params).numpy()
+        out[name + '/uniforms'] = uniforms
+        out[name + '/sigma'] = sigma
+        out[name + '/site_order'] = np.array(order, dtype=np.int64)
+        out[name + '/graph_nodes'] = np.int64(probe.dependencies_graph.graph.number_of_nodes())
+    path = os.path.join(OUT, 'reference_fast_sampler.npz')
+    np.savez_compressed(path, **out)
+    print('wrote', path, len(out), 'arrays', {k: int(out[k]) for k in out if k.endswith('graph_nodes')})
+
+
 COMMANDS = {
     'numpy_half': main,                          # operators / local energy / bit conventions / ED anchors
     'edge': edge_cases,                          # find_conn over all states of degenerate lattices
@@ -933,6 +1051,7 @@ COMMANDS = {
     'sampler': autoregressive_sampler,           # AutoregressiveSampler.__next__ around the oracle network
     'complex_ops': complex_ops,                  # lncosh / complex_log / ensemble ops
     'machines': machines,                        # the three machine classes + gradients (oracle/tf_standin.py)
+    'fast_sampler': fast_sampler,                # FastAutoregressiveSampler + DependencyGraph + topologies
     'ensembles': ensembles,                      # symmetrisation ensembles around the 2-D machine
     'sr': sr_algebra,                            # ComplexValuesStochasticReconfiguration methods
     'cg': conjugate_gradient_solver,             # the vendored conjugate-gradient solver

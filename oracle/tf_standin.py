@@ -56,8 +56,8 @@ class DType(object):
 
 float32, float64 = DType('float32', torch.float64), DType('float64', torch.float64)
 complex64, complex128 = DType('complex64', torch.complex128), DType('complex128', torch.complex128)
-int32, int64 = DType('int32', torch.int64), DType('int64', torch.int64)
-_BY_NAME = {d.name: d for d in (float32, float64, complex64, complex128, int32, int64)}
+int32, int64, int8 = DType('int32', torch.int64), DType('int64', torch.int64), DType('int8', torch.int64)
+_BY_NAME = {d.name: d for d in (float32, float64, complex64, complex128, int32, int64, int8)}
 
 
 def _torch_dtype(dtype):
@@ -73,8 +73,32 @@ def _torch_dtype(dtype):
 torch.Tensor.get_shape = lambda self: self.shape           # TF 1.x spelling used by deepar/layers/masking.py
 
 
+class Opaque(object):
+    """a tensor hidden from numpy: the fast sampler fills object arrays with `numpy.full(shape, fill_value=zeros)`, which only
+    keeps `zeros` as ONE object per cell if it is not array-like (a symbolic TF tensor is not)"""
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+
+
 def _t(x):
+    if isinstance(x, Opaque):
+        return x.tensor
     return x if isinstance(x, torch.Tensor) else torch.as_tensor(x)
+
+
+# ---- graph recording (for the reference's graph analysis: which layer feeds which) ---------------------------------------
+RECORDING = [False]
+_COUNTERS = {}
+
+
+class Node(object):
+    def __init__(self, inbound_layers, tensor_indices):
+        self.inbound_layers, self.tensor_indices = inbound_layers, tensor_indices
+
+
+def _shape_of(x):
+    return (None,) + tuple(_t(x).shape[1:])
 
 
 # ---- tensorflow.* -----------------------------------------------------------------------------------------------------------
@@ -98,11 +122,11 @@ def unstack(x, axis=0, name=None):
 
 
 def stack(xs, axis=0, name=None):
-    return torch.stack(list(xs), dim=axis)
+    return torch.stack([_t(x) for x in xs], dim=axis)
 
 
 def concat(xs, axis, name=None):
-    return torch.cat(list(xs), dim=axis)
+    return torch.cat([_t(x) for x in xs], dim=axis)
 
 
 def slice_(x, begin, size, name=None):
@@ -160,9 +184,14 @@ class TensorShape(object):
 # ---- tensorflow.keras -----------------------------------------------------------------------------------------------------
 class Layer(object):
     def __init__(self, name=None, dtype=None, **_ignored):
+        if name is None:
+            base = type(self).__name__.lower()
+            _COUNTERS[base] = _COUNTERS.get(base, 0) + 1
+            name = '%s_%d' % (base, _COUNTERS[base])
         self.name, self.built = name, False
         self.dtype = dtype
         self.input_spec = None
+        self.inbound_nodes = []
 
     def add_weight(self, name=None, shape=None, initializer=None, dtype=None, trainable=True, **_ignored):
         assert _WEIGHTS, 'the injected weight list is exhausted at %r' % name
@@ -183,12 +212,61 @@ class Layer(object):
     def get_config(self):
         return {}
 
+    def get_output_shape_at(self, index):
+        return self.output_shape
+
     def __call__(self, inputs, **kwargs):
+        many = isinstance(inputs, (list, tuple))
+        inputs = [_t(i) for i in inputs] if many else _t(inputs)
         if not self.built:
-            shape = [tuple(i.shape) for i in inputs] if isinstance(inputs, (list, tuple)) else tuple(inputs.shape)
-            self.build(shape)
+            self.build([tuple(i.shape) for i in inputs] if many else tuple(inputs.shape))
             self.built = True
-        return self.call(inputs, **kwargs)
+        if self.dtype is None:          # TF 1.x Keras: a layer without an explicit dtype takes the dtype of its first input
+            self.dtype = (inputs[0] if many else inputs).dtype
+        out = self.call(inputs, **kwargs)
+        if RECORDING[0]:
+            sources = inputs if many else [inputs]
+            history = [getattr(i, '_keras_history', None) for i in sources]
+            assert all(h is not None for h in history), 'input of %s was not produced by a layer' % self.name
+            layers_in, indices = [h[0] for h in history], [h[1] for h in history]
+            self.inbound_nodes.append(Node(layers_in if many else layers_in[0], indices if many else indices[0]))
+            self.input = sources if many else inputs
+            self.input_shape = [_shape_of(i) for i in sources] if many else _shape_of(inputs)
+            self.output_shape = _shape_of(out)
+            out._keras_history = (self, 0)
+        return out
+
+
+class InputLayer(Layer):
+    """the layer behind a model input; `tensor` is the concrete batch the machine is built on"""
+
+    def __init__(self, tensor, dtype='int8', name=None):
+        super(InputLayer, self).__init__(name=name, dtype=dtype)
+        self.output_shape = self.input_shape = _shape_of(tensor)
+        self.input = tensor
+        self.inbound_nodes = [Node([], [])]
+        tensor._keras_history = (self, 0)
+
+
+class GraphModel(object):
+    """what the graph analysis reads from a Keras Model: the layers reachable from the output, their names, the shapes"""
+
+    def __init__(self, inputs, outputs):
+        self.input, self.output = inputs, outputs
+        self.layers, seen, stack = [], set(), [outputs._keras_history[0]]
+        while stack:
+            layer = stack.pop()
+            if id(layer) in seen:
+                continue
+            seen.add(id(layer))
+            self.layers.append(layer)
+            inbound = layer.inbound_nodes[-1].inbound_layers
+            stack.extend(inbound if isinstance(inbound, list) else [inbound])
+        self.input_names, self.output_names = [inputs._keras_history[0].name], [outputs._keras_history[0].name]
+        self.input_shape, self.output_shape = _shape_of(inputs), _shape_of(outputs)
+
+    def get_layer(self, name):
+        return [layer for layer in self.layers if layer.name == name][0]
 
 
 class Wrapper(Layer):
@@ -237,7 +315,7 @@ class Concatenate(Layer):
         self.axis = axis
 
     def call(self, inputs, **kwargs):
-        return torch.cat(list(inputs), dim=self.axis)
+        return torch.cat([_t(i) for i in inputs], dim=self.axis)
 
 
 class ZeroPadding1D(Layer):
@@ -253,6 +331,7 @@ class ZeroPadding2D(Layer):
     def __init__(self, padding=(1, 1), **kwargs):
         super(ZeroPadding2D, self).__init__(**kwargs)
         (self.top, self.bottom), (self.left, self.right) = [(p, p) if isinstance(p, int) else tuple(p) for p in padding]
+        self.padding = ((self.top, self.bottom), (self.left, self.right))
 
     def call(self, x, **kwargs):                       # [n, rows, cols, channels]
         return F.pad(x, (0, 0, self.left, self.right, self.top, self.bottom))
@@ -264,9 +343,10 @@ class _Conv(Layer):
     def __init__(self, filters, kernel_size, strides=1, padding='valid', dilation_rate=1, use_bias=True, **kwargs):
         super(_Conv, self).__init__(**kwargs)
         assert padding == 'valid' and kwargs.get('activation') is None
-        self.filters = filters
-        self.kernel_size = (kernel_size,) * self.rank if isinstance(kernel_size, int) else tuple(kernel_size)
-        self.strides, self.dilation_rate, self.use_bias = strides, dilation_rate, use_bias
+        as_tuple = lambda v: (v,) * self.rank if isinstance(v, int) else tuple(v)     # noqa: E731
+        self.filters, self.kernel_size = filters, as_tuple(kernel_size)
+        self.strides, self.dilation_rate, self.use_bias = as_tuple(strides), as_tuple(dilation_rate), use_bias
+        self.padding, self.activation = padding, None
 
     def build(self, input_shape):
         self.kernel = self.add_weight(name='kernel', shape=self.kernel_size + (int(input_shape[-1]), self.filters))
@@ -288,6 +368,27 @@ class Conv2D(_Conv):
 
 class Initializer(object):
     pass
+
+
+class _Unused(Layer):
+    """layer types the reference registers topologies for but these machines never instantiate"""
+
+
+# ---- sampling primitives of the fast sampler ------------------------------------------------------------------------------
+BATCH = [0]              # value of the batch-size placeholder
+UNIFORMS = []            # one [B] array of uniforms per multinomial call, consumed in call order
+MULTINOMIAL_CALLS = [0]
+
+
+def _multinomial(logits, num_samples, output_dtype=None, name=None):
+    """category 0 iff exp(logits[:, 0]) / sum exp(logits) > u -- inverse-CDF sampling of a two-class distribution with the
+    injected uniforms (the explicit-uniform rule of deepar/samplers/autoregressive.py:37-44)"""
+    logits = _t(logits).to(torch.float64)
+    assert num_samples == 1 and logits.shape[-1] == 2
+    p0 = torch.softmax(logits, dim=-1)[:, 0]
+    u = torch.as_tensor(UNIFORMS.pop(0)) if UNIFORMS else torch.full_like(p0, 0.5)
+    MULTINOMIAL_CALLS[0] += 1
+    return (~(p0 > u)).to(torch.int64).reshape(-1, 1)
 
 
 class _Shape(list):
@@ -343,12 +444,16 @@ def install():
                                    cholesky=torch.linalg.cholesky, solve=torch.linalg.solve,
                                    cholesky_solve=lambda chol, rhs: torch.cholesky_solve(rhs, chol))
     backend = module('tensorflow.keras.backend', int_shape=lambda x: tuple(x.shape), update=lambda ref, value: (ref, value),
+                     placeholder=lambda dtype=None, shape=None: BATCH[0],
+                     function=lambda inputs, outputs: (lambda feed: [_t(o) for o in outputs]),
                      name_scope=scope, variable=lambda value, **k: value, epsilon=lambda: 1e-7,
                      expand_dims=lambda x, axis=-1: _t(x).unsqueeze(axis), cast=cast, conv1d=_conv(1), conv2d=_conv(2),
                      set_floatx=lambda name: None)
     layers = module('tensorflow.keras.layers', Layer=Layer, Wrapper=Wrapper, InputSpec=InputSpec, Lambda=Lambda,
                     Activation=Activation, Add=Add, Concatenate=Concatenate, ZeroPadding1D=ZeroPadding1D,
-                    ZeroPadding2D=ZeroPadding2D, Conv1D=Conv1D, Conv2D=Conv2D, Input=None, Dense=None)
+                    ZeroPadding2D=ZeroPadding2D, Conv1D=Conv1D, Conv2D=Conv2D, Input=None, Dense=None,
+                    **{n: type(n, (_Unused,), {}) for n in ('Conv3D', 'ZeroPadding3D', 'Average', 'Subtract', 'Multiply', 'Maximum',
+                                                              'Minimum', 'LeakyReLU', 'ELU', 'ThresholdedReLU', 'Softmax')})
     # images are [n, rows, cols, channels]; rot90 turns counter-clockwise like numpy / torch
     image = types.SimpleNamespace(rot90=lambda x, k=1, name=None: torch.rot90(x, k, dims=(1, 2)),
                                   flip_left_right=lambda x: torch.flip(x, dims=(2,)))
@@ -363,12 +468,16 @@ def install():
     pfor = module('tensorflow.python.ops.parallel_for', gradients=None)
     ops = module('tensorflow.python.ops', parallel_for=pfor)
     python = module('tensorflow.python', keras=py_keras, ops=ops)
+    engine = module('tensorflow.python.keras.engine')
+    module('tensorflow.python.keras.engine.input_layer', InputLayer=InputLayer)
+    py_keras.engine = engine
     module('tensorflow', math=math, nn=nn, linalg=linalg, keras=keras, python=python, complex=complex_, cast=cast,
            image=image, expand_dims=lambda x, axis=-1, name=None: _t(x).unsqueeze(axis),
            shape=lambda x, name=None: list(_t(x).shape), matmul=_matmul, conj=lambda x, name=None: torch.conj(_t(x)).resolve_conj(),
            eye=lambda n, dtype=None, name=None: torch.eye(int(n), dtype=_torch_dtype(dtype)), squeeze=lambda x, axis=None: _t(x).squeeze(),
            control_dependencies=lambda deps: contextlib.nullcontext(), stop_gradient=lambda x, name=None: x, no_op=lambda: None,
-           __version__='1.13.1',
+           __version__='1.13.1', zeros=lambda shape, dtype=None, name=None: Opaque(torch.zeros(tuple(int(v) for v in shape), dtype=_torch_dtype(dtype))),
+           as_dtype=lambda d: d, multinomial=_multinomial, int8=int8,
            roll=lambda x, shift, axis, name=None: torch.roll(x, shifts=tuple(shift), dims=tuple(axis)),
            reshape=reshape, unstack=unstack, stack=stack, concat=concat, slice=slice_, zeros_like=zeros_like,
            one_hot=one_hot, name_scope=scope, TensorShape=TensorShape, float32=float32, float64=float64,

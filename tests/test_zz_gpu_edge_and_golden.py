@@ -140,6 +140,31 @@ def test_device_samplers_reproduce_the_reference_samplers_spins(name, kind, shap
             assert abs(p0[first] - u[first]) < 1e-5, (type(sampler).__name__, first, p0[first], u[first])
 
 
+@pytest.mark.parametrize('name,kind,shape,depth,channels,kw', [
+    ('conv2d_4x3', 'conv2d', (4, 3), 2, 8, {}),
+    ('conv2d_3x3_d3', 'conv2d', (3, 3), 3, 4, {}),
+    ('conv1d_10', 'conv1d', (10,), 4, 8, {'max_dilation_rate': 2, 'add_skip_connections': True}),
+    ('cconv1d_8', 'cconv1d', (8,), 3, 4, {'max_dilation_rate': 2}),
+])
+def test_device_samplers_reproduce_the_reference_fast_samplers_spins(name, kind, shape, depth, channels, kw):
+    """golden tests/golden/reference_fast_sampler.npz: spins drawn by the reference's OWN FastAutoregressiveSampler (dependency
+    graph + layer topologies, make_golden.py fast_sampler); the CUDA incremental samplers get the same weights and uniforms.
+    A spin may differ only at a numerical tie |p0 - u| < 1e-5."""
+    import os
+    from flowket_b200.samplers import FastAutoregressiveSampler
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_fast_sampler.npz'))
+    model, cond_model, spec, _ = make_pair(kind, shape, depth, channels, seed=0, **kw)
+    params = nets.unflatten_params(spec, torch.from_numpy(g[name + '/params']))
+    model.machine.set_weights([p.numpy().astype(np.float32) for p in params])
+    u, want = g[name + '/uniforms'], g[name + '/sigma']
+    p0 = np.exp(nets.conditional_log_probs(spec, params, want).numpy()[..., 0])
+    got = FastAutoregressiveSampler(cond_model, len(u)).next_device(uniforms=u).cpu().numpy()
+    bad = np.argwhere(got != want)
+    for idx in bad:   # the first differing site of a sample must be a numerical tie
+        first = tuple(bad[bad[:, 0] == idx[0]][0])
+        assert abs(p0[first] - u[first]) < 1e-5, (first, p0[first], u[first])
+
+
 def test_device_ensembles_match_the_reference_ensembles():
     """golden tests/golden/reference_ensembles.npz: the reference's own symmetrisation ensembles around its own 2-D machine;
     the product's EnsembleModel (device route) gets the same weights and spins."""
