@@ -16,9 +16,12 @@ Pinning status (see DESIGN.md "Oracle"):
     tests/golden/, generator oracle/make_golden.py) and against the
     exact-diagonalisation constants embedded in the reference's examples;
     ExactVariational, VariationalMonteCarlo + MiniBatchGenerator, the stats
-    callbacks / evaluate, the MCMC diagnostics and the AutoregressiveSampler loop
-    are PINNED by running the reference's own classes around minimal stand-ins
-    for the TensorFlow guards (make_golden.py exact | vmc | callbacks | mcmc | sampler).
+    callbacks / evaluate, the MCMC diagnostics, the AutoregressiveSampler loop,
+    the FastAutoregressiveSampler with its dependency graph and topologies, the
+    symmetrisation ensembles, the complex SR methods and the CG solver
+    are PINNED by running the reference's own classes around stand-ins for the
+    TensorFlow / Keras primitives (make_golden.py exact | vmc | callbacks | mcmc |
+    sampler | fast_sampler | ensembles | sr | cg).
   * network half (Keras graph; TensorFlow is not installable here): restated
     from the reference sources cited per function and PINNED against the
     reference's own machine classes run on top of oracle/tf_standin.py (an eager
@@ -29,7 +32,8 @@ Pinning status (see DESIGN.md "Oracle"):
     (experiments/weights/ising_*.h5 -> published energies).  Bit-level parity
     with TF's unseeded `tf.multinomial` stream is "parity unpinned"; the
     pinned sampling contract is the explicit-uniform rule of
-    deepar/samplers/autoregressive.py:37-44.
+    deepar/samplers/autoregressive.py:37-44, under which the reference's own
+    FastAutoregressiveSampler reproduces the oracle's spins exactly.
   * J1J2 connection *order* (netket, un-vendored, unpinned version): "parity
     unpinned"; values pinned by the ED constant of
     examples/j1j2_2d_monte_carlo_4.py:43.

@@ -14,6 +14,13 @@ reference's code.  What this file supplies is only the meaning of the primitive 
     (weights, spins); initialisers are ignored;
   * float32 / complex64 requests are served in float64 / complex128 so that the golden values carry no rounding of their own.
 
+  * while a machine is built with RECORDING on, every layer notes which layers produced its inputs and the shapes involved
+    (Keras' `inbound_nodes` / `input_shape` / `output_shape`), which is all the reference's graph analysis
+    (deepar/graph_analysis/*.py) and FastAutoregressiveSampler read; `K.placeholder` is the concrete batch size and
+    `K.function` returns what was already computed;
+  * `tf.multinomial` -- the fast sampler's only source of randomness, unseeded in the reference -- is inverse-CDF sampling
+    with injected uniforms: category 0 iff p0 > u (the explicit-uniform rule of deepar/samplers/autoregressive.py:37-44).
+
 Nothing here knows anything about autoregressive machines."""
 import contextlib
 import sys
