@@ -1040,6 +1040,62 @@ def fast_sampler():
     print('wrote', path, len(out), 'arrays', {k: int(out[k]) for k in out if k.endswith('graph_nodes')})
 
 
+def complex_sr_pipeline():
+    """tests/golden/reference_complex_sr_pipeline.npz: the stochastic-reconfiguration update of the complex 1-D machine
+    (BASELINE configs[3]) computed by the reference's own code end to end: ComplexValuesSimpleConvNetAutoregressive1D forward,
+    `Machine.predictions_jacobian` (machines/abstract_machine.py:24-28; the Jacobian primitive is autograd over the
+    stand-in's torch graph), the complex assembly of `ComplexValuesOptimizer.get_predictions_jacobian`
+    (complex_values_optimizer.py:8-9,72-76), then the SR methods as in `sr_algebra`."""
+    import torch
+    from oracle import nets, tf_standin
+    cconv_cls = load_reference_machines()[2]
+    for name, path in [('flowket.optimizers', '/optimizers'),
+                       ('flowket.optimizers.stochastic_reconfiguration', '/optimizers/stochastic_reconfiguration')]:
+        mod = types.ModuleType(name)
+        mod.__path__ = [REF + path]
+        sys.modules[name] = mod
+    le = types.ModuleType('flowket.optimizers.stochastic_reconfiguration.linear_equations')
+    le.conjugate_gradient = None
+    sys.modules[le.__name__] = le
+    sr_cls = importlib.import_module('flowket.optimizers.stochastic_reconfiguration.optimizer').ComplexValuesStochasticReconfiguration
+    rng = np.random.default_rng(20261026)
+    spec = nets.ComplexConv1DSpec(9, 3, 4, max_dilation_rate=2)
+    kw = dict(depth=3, num_of_channels=4, max_dilation_rate=2)
+    B = 30
+    params = [p + 0.3 * torch.randn(p.shape, dtype=torch.float64, generator=torch.Generator().manual_seed(11 + i)) * (p.dim() == 1)
+              for i, p in enumerate(nets.init_params(spec, seed=3, dtype=torch.float64))]
+    sigma = rng.choice([-1, 1], size=(B, 9)).astype(np.int8)
+    leaves = tf_standin.inject_weights([p.numpy() for p in params], requires_grad=True)
+    machine = cconv_cls(torch.from_numpy(sigma.astype(np.float64)), **kw)
+    e_loc = rng.normal(size=B) * 2 - 5 + 1j * rng.normal(size=B)
+    y_true = torch.from_numpy(np.conj(e_loc - e_loc.mean()) / B)
+    real = [tf_standin.Variable(w.detach()) for w in leaves[0::2]]
+    imag = [tf_standin.Variable(w.detach()) for w in leaves[1::2]]
+    me = types.SimpleNamespace(
+        batch_size=torch.tensor(complex(B)), diag_shift=0.05, lr=0.01, use_cholesky=True, add_s_matrix_stats=False,
+        use_energy_loss=False, iterative_solver=False, predictions_jacobian=machine.predictions_jacobian,
+        predictions_keras_model=types.SimpleNamespace(output=machine.predictions, targets=[y_true], weights=leaves),
+        model_real_weights=real, model_imag_weights=imag)
+    for name in ('get_predictions_jacobian', 'get_wave_function_jacobian_minus_mean', 'get_energy_grad', '_update_s_matrix_stats',
+                 'compute_wave_function_gradient_covariance_inverse_multiplication',
+                 'compute_wave_function_gradient_covariance_inverse_multiplication_directly', 'apply_complex_gradient'):
+        setattr(me, name, types.MethodType(getattr(sr_cls, name), me))
+    jac = me.get_predictions_jacobian().detach()
+    o_bar = me.get_wave_function_jacobian_minus_mean().detach()
+    energy_grad = me.get_energy_grad(None, o_bar)
+    delta = me.compute_wave_function_gradient_covariance_inverse_multiplication(energy_grad, o_bar)
+    updates = me.apply_complex_gradient(delta * (-1.0 + 0j))
+    new_flat = []
+    for (_, new_r), (_, new_i) in zip(updates[:len(real)], updates[len(real):]):
+        new_flat += [np.asarray(new_r.detach()).reshape(-1), np.asarray(new_i.detach()).reshape(-1)]
+    out = {'params': nets.flatten_params(params).numpy(), 'sigma': sigma, 'y_true': y_true.numpy(), 'local_energy': e_loc,
+           'jacobian': jac.numpy(), 'delta': delta.detach().numpy()[:, 0], 'diag_shift': np.float64(0.05), 'lr': np.float64(0.01),
+           'new_params': np.concatenate(new_flat)}
+    path = os.path.join(OUT, 'reference_complex_sr_pipeline.npz')
+    np.savez_compressed(path, **out)
+    print('wrote', path, len(out), 'arrays; complex parameters:', jac.shape[1])
+
+
 COMMANDS = {
     'numpy_half': main,                          # operators / local energy / bit conventions / ED anchors
     'edge': edge_cases,                          # find_conn over all states of degenerate lattices
@@ -1053,7 +1109,8 @@ COMMANDS = {
     'machines': machines,                        # the three machine classes + gradients (oracle/tf_standin.py)
     'fast_sampler': fast_sampler,                # FastAutoregressiveSampler + DependencyGraph + topologies
     'ensembles': ensembles,                      # symmetrisation ensembles around the 2-D machine
-    'sr': sr_algebra,                            # ComplexValuesStochasticReconfiguration methods
+    'sr': sr_algebra,
+    'sr_pipeline': complex_sr_pipeline,          # complex machine -> Jacobian -> SR update, end to end                            # ComplexValuesStochasticReconfiguration methods
     'cg': conjugate_gradient_solver,             # the vendored conjugate-gradient solver
     'weights': export_pretrained_weights,        # experiments/weights/ising_*.h5 -> npz
 }

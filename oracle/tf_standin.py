@@ -472,7 +472,17 @@ def install():
     public = lambda mod: {k: v for k, v in mod.__dict__.items() if not k.startswith('__')}     # noqa: E731
     module('tensorflow.python.keras.layers', **public(layers))
     module('tensorflow.python.keras.backend', **public(backend))
-    pfor = module('tensorflow.python.ops.parallel_for', gradients=None)
+    def jacobian(y, xs, use_pfor=False):
+        """d y[b, ...] / d x for every x in xs -> list of [B, *x.shape] (tf.python.ops.parallel_for.gradients.jacobian);
+        rows by reverse-mode autograd over the torch graph the stand-in built"""
+        y = _t(y)
+        flat = y.reshape(y.shape[0], -1)
+        assert flat.shape[1] == 1, 'per-sample scalar outputs only'
+        rows = [torch.autograd.grad(flat[b, 0], xs, retain_graph=True) for b in range(flat.shape[0])]
+        return [torch.stack([rows[b][i] for b in range(len(rows))]) for i in range(len(xs))]
+    pfor_gradients = types.SimpleNamespace(jacobian=jacobian)
+    pfor = module('tensorflow.python.ops.parallel_for', gradients=pfor_gradients)
+    module('tensorflow.python.ops.parallel_for.gradients', jacobian=jacobian)
     ops = module('tensorflow.python.ops', parallel_for=pfor)
     python = module('tensorflow.python', keras=py_keras, ops=ops)
     engine = module('tensorflow.python.keras.engine')
