@@ -190,6 +190,26 @@ def test_device_ensembles_match_the_reference_ensembles():
     same(make_pbc_invariants(inp, model, apply_also_obc_invariants=False).predict(sigma), g['translations'])
 
 
+def test_device_complex_sr_update_matches_the_reference_pipeline():
+    """golden tests/golden/reference_complex_sr_pipeline.npz: the SR update of the complex 1-D machine computed end to end by
+    the reference's own code (machine -> per-sample Jacobian -> complex assembly -> S, F -> delta -> new weights); the device
+    optimizer (fk_grad_per_sample, fk_sr_gram, Cholesky) gets the same weights, spins and targets."""
+    import os
+    from flowket_b200.optimizers import ComplexValuesStochasticReconfiguration
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_complex_sr_pipeline.npz'))
+    model, _, spec, _ = make_pair('cconv1d', (9,), 3, 4, seed=0, max_dilation_rate=2)
+    params = nets.unflatten_params(spec, torch.from_numpy(g['params']))
+    model.machine.set_weights([p.numpy().astype(np.float32) for p in params])
+    sr = ComplexValuesStochasticReconfiguration(model, lr=float(g['lr']), diag_shift=float(g['diag_shift']), iterative_solver=False)
+    O = sr.complex_jacobian(g['sigma']).cpu().numpy()
+    assert np.linalg.norm(O - g['jacobian']) / np.linalg.norm(g['jacobian']) < 2e-5
+    delta = sr.compute_update(g['sigma'], g['y_true']).cpu().numpy()
+    assert np.linalg.norm(delta - g['delta']) / np.linalg.norm(g['delta']) < 5e-4
+    sr.apply_complex_gradient(torch.from_numpy(g['delta']).to(model.machine.flat_params_device().device))
+    new = model.machine.flat_params_device().cpu().numpy()
+    assert np.abs(new - g['new_params']).max() < 1e-6
+
+
 @pytest.mark.parametrize('name', sorted(EDGE))
 def test_device_find_conn_on_degenerate_lattices(golden_edge, name):
     import flowket_b200.operators as ops
@@ -260,23 +280,3 @@ def test_local_energy_on_degenerate_lattices(kind, shape, opkind, opkw):
     want = oeloc.local_values(oops.OracleOperator(opkind, shape, **opkw), lambda c: nets.log_psi_numpy(spec, params, c),
                               sigma.astype(np.float64))
     assert np.abs(got - want).max() / np.abs(want).max() < 1e-5
-
-
-def test_device_complex_sr_update_matches_the_reference_pipeline():
-    """golden tests/golden/reference_complex_sr_pipeline.npz: the SR update of the complex 1-D machine computed end to end by
-    the reference's own code (machine -> per-sample Jacobian -> complex assembly -> S, F -> delta -> new weights); the device
-    optimizer (fk_grad_per_sample, fk_sr_gram, Cholesky) gets the same weights, spins and targets."""
-    import os
-    from flowket_b200.optimizers import ComplexValuesStochasticReconfiguration
-    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'reference_complex_sr_pipeline.npz'))
-    model, _, spec, _ = make_pair('cconv1d', (9,), 3, 4, seed=0, max_dilation_rate=2)
-    params = nets.unflatten_params(spec, torch.from_numpy(g['params']))
-    model.machine.set_weights([p.numpy().astype(np.float32) for p in params])
-    sr = ComplexValuesStochasticReconfiguration(model, lr=float(g['lr']), diag_shift=float(g['diag_shift']), iterative_solver=False)
-    O = sr.complex_jacobian(g['sigma']).cpu().numpy()
-    assert np.linalg.norm(O - g['jacobian']) / np.linalg.norm(g['jacobian']) < 2e-5
-    delta = sr.compute_update(g['sigma'], g['y_true']).cpu().numpy()
-    assert np.linalg.norm(delta - g['delta']) / np.linalg.norm(g['delta']) < 5e-4
-    sr.apply_complex_gradient(torch.from_numpy(g['delta']).to(model.machine.flat_params_device().device))
-    new = model.machine.flat_params_device().cpu().numpy()
-    assert np.abs(new - g['new_params']).max() < 1e-6
