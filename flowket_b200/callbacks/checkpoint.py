@@ -22,7 +22,7 @@ class CheckpointByTime(Callback):
         self.trainer = trainer
 
     def _save(self, logs):
-        path = self.filepath.format(epoch=self.current_epoch, **(logs or {}))
+        path = self.filepath.format(**dict(logs or {}, epoch=self.current_epoch))
         if self.save_weights_only or self.trainer is None:
             self.model.save_weights(path)
         else:

@@ -178,6 +178,8 @@ static int build_cconv1d(fk_net* net) {
   return 0;
 }
 
+static inline int64_t align4(int64_t x) { return (x + 3) & ~(int64_t)3; }
+
 // liveness-based physical slot assignment for inference
 static void assign_phys(fk_net* net) {
   const int nv = (int)net->bufs.size();
@@ -207,9 +209,11 @@ static void assign_phys(fk_net* net) {
     net->bufs[v].phys = chosen;
   }
   net->n_phys = (int)slot_free_at.size();
-  net->phys_channels = maxc;
+  // Slot and buffer sizes are carved in multiples of 4 floats so that every activation buffer starts 16-byte aligned
+  // whatever the channel count, lattice size and chunk length are (float4 / cp.async accesses in the kernels).
+  net->phys_channels = align4(maxc);
   int64_t tot = 0;
-  for (int v = 0; v < nv; ++v) tot += net->bufs[v].channels;
+  for (int v = 0; v < nv; ++v) tot += align4(net->bufs[v].channels);
   net->train_floats_per_cfg = tot * net->sites;
 }
 
@@ -559,6 +563,7 @@ static int grad_impl(fk_net* net, const int8_t* sigma, const float* y, int64_t B
   FK_REQUIRE(net->params_set, "machine parameters were never set (fk_net_set_params)");
   const int per_sample = (y == nullptr);
   const int64_t per_cfg = grad_bytes_per_cfg(net, per_sample);
+  FK_REQUIRE(reinterpret_cast<uintptr_t>(ws) % 16 == 0, "gradient workspace must be 16-byte aligned");
   const int64_t fixed = (per_sample ? 0 : net->num_eff * (int64_t)sizeof(float)) + 256;
   int64_t chunk = (ws_bytes - fixed) / per_cfg;
   FK_REQUIRE(chunk >= 1, "gradient workspace too small: %lld bytes (need %lld + %lld per configuration)",
@@ -570,18 +575,19 @@ static int grad_impl(fk_net* net, const int8_t* sigma, const float* y, int64_t B
   float* geff_sum = nullptr;
   if (!per_sample) {
     geff_sum = base;
-    base += net->num_eff;
+    base += align4(net->num_eff);
     FK_CHECK_CUDA(cudaMemsetAsync(geff_sum, 0, sizeof(float) * net->num_eff, s));
   }
   for (int64_t i = 0; i < B; i += chunk) {
     const int64_t m = std::min(chunk, B - i);
     float* p = base;
-    for (size_t v = 0; v < nv; ++v) { act[v] = p; p += (int64_t)net->bufs[v].channels * net->sites * m; }
+    // every carve is a multiple of 4 floats (16-byte alignment of all buffers for any channel count / chunk)
+    for (size_t v = 0; v < nv; ++v) { act[v] = p; p += align4(net->bufs[v].channels) * net->sites * m; }
     float* grad_base = p;
-    for (size_t v = 0; v < nv; ++v) { grad[v] = p; p += (int64_t)net->bufs[v].channels * net->sites * m; }
+    for (size_t v = 0; v < nv; ++v) { grad[v] = p; p += align4(net->bufs[v].channels) * net->sites * m; }
     float* dz = p; p += (int64_t)net->sites * net->phys_channels * m;
-    float* cre = p; p += m;
-    float* cim = p; p += m;
+    float* cre = p; p += align4(m);
+    float* cim = p; p += align4(m);
     float* geff = per_sample ? p : geff_sum;
     const int8_t* sg = sigma + i * net->sites;
     if (run_forward(net, sg, m, act.data(), s)) return 1;

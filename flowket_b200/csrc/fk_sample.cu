@@ -602,10 +602,10 @@ extern "C" int fk_sample_naive(fk_net_t* net, const double* uniforms, uint64_t s
   FK_REQUIRE(net->params_set, "machine parameters were never set (fk_net_set_params)");
   if (B == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  const int64_t need = infer_floats_per_cfg(net) * 4 * B + 8 * B * net->sites;
+  const int64_t need = infer_floats_per_cfg(net) * 4 * B + 8 * B * net->sites + 16;
   FK_REQUIRE(ws_bytes >= need, "fk_sample_naive: workspace too small (%lld < %lld bytes)", (long long)ws_bytes, (long long)need);
   float* cond = (float*)ws;                       // [B, sites, 2]
-  float* fwd = cond + 2 * B * net->sites;
+  float* fwd = cond + ((2 * B * net->sites + 3) / 4) * 4;   // 16-byte aligned activation slots
   FK_CHECK_CUDA(cudaMemsetAsync(sigma_out, 0, B * net->sites, s));
   std::vector<float*> bp;
   assign_infer_buffers(net, fwd, B, bp);

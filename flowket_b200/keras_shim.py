@@ -69,7 +69,16 @@ class Model(object):
             self.set_weights(read_keras_weights(path, self.machine.weight_specs()))
             return
         with np.load(path if str(path).endswith('.npz') else str(path) + '.npz') as f:
-            self.set_weights([f['w%04d' % i] for i in range(len(f.files))])
+            if 'params' in f.files:            # a Trainer checkpoint (flat vector + optimizer slots): weights only
+                flat, weights, off = f['params'], [], 0
+                for _name, shp, _init in self.machine.weight_specs():
+                    n = int(np.prod(shp))
+                    weights.append(flat[off:off + n].reshape(shp))
+                    off += n
+                self.set_weights(weights)
+                return
+            n_w = len([k for k in f.files if k.startswith('w') and k[1:].isdigit()])
+            self.set_weights([f['w%04d' % i] for i in range(n_w)])
 
     # ---- evaluation --------------------------------------------------------------------------------------
     def predict_device(self, x, batch_size=None):

@@ -20,6 +20,29 @@ class DistributedVariationalMonteCarlo(VariationalMonteCarlo):
         self.world_size = dist.get_world_size() if dist else 1
         self.rank = dist.get_rank() if dist else 0
         self.global_batch_size = self.batch_size * self.world_size
+        self._shard_sampler(self.sampler)
+
+    def _shard_sampler(self, sampler):
+        """Every rank must draw its own slice of the global batch.  The device samplers key their Philox stream by
+        (seed, global sample index): a rank's samples are the indices [rank * B, (rank + 1) * B).  A reference Horovod
+        script leaves that to per-process unseeded RNGs; here a sampler whose offset was never set is given its rank's
+        slice, and an explicit offset that collides with another rank's slice is refused."""
+        if self.world_size <= 1 or not hasattr(sampler, 'sample_offset'):
+            return
+        want = self.rank * sampler.batch_size
+        if getattr(sampler, 'shard_rank', None) is None and sampler.sample_offset == 0:
+            sampler.sample_offset = want
+            sampler.shard_rank = self.rank
+        elif sampler.sample_offset != want and getattr(sampler, 'shard_rank', None) != self.rank:
+            if self.rank > 0 and sampler.sample_offset < want:
+                raise ValueError('rank %d: sampler.sample_offset = %d overlaps the samples of lower ranks (expected %d)'
+                                 % (self.rank, sampler.sample_offset, want))
+
+    def set_sampler(self, sampler, mini_batch_size=None):
+        res = super(DistributedVariationalMonteCarlo, self).set_sampler(sampler, mini_batch_size)
+        self.global_batch_size = self.batch_size * self.world_size
+        self._shard_sampler(sampler)
+        return res
 
     @staticmethod
     def reduce_stats(local_energy):

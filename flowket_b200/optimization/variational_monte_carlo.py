@@ -35,10 +35,19 @@ class VariationalMonteCarlo(MiniBatchGenerator):
         """(mean, var(Re), local values) -- device route when the observable and sampler support it."""
         obs = self.energy_observable
         if isinstance(obs, Observable) and self.current_batch_device is not None:
-            eloc = obs.local_values_device(self.model, self.current_batch_device)
-            self.current_local_energy_device = eloc
-            lv = eloc.cpu().numpy()
-            return numpy.mean(lv), numpy.var(numpy.real(lv)), lv
+            from ..keras_shim import Model
+            from ..machines.ensemble import EnsembleModel
+            eloc = None
+            if isinstance(self.model, Model):
+                eloc = obs.local_values_device(self.model, self.current_batch_device)
+            elif isinstance(self.model, EnsembleModel):
+                # a symmetrised wave function must be evaluated through the ensemble's own predict (the reference
+                # evaluates model.predict of the ensemble model), never through the base machine's fused kernel
+                eloc = obs.local_values_device_generic(self.model.predict_device, self.current_batch_device)
+            if eloc is not None:
+                self.current_local_energy_device = eloc
+                lv = eloc.cpu().numpy()
+                return numpy.mean(lv), numpy.var(numpy.real(lv)), lv
         return obs.estimate(self.wave_function, self.current_batch)
 
     def _update_batch_local_energy(self):

@@ -147,8 +147,14 @@ class Trainer(object):
         if hasattr(opt, 'complex_jacobian'):
             opt.step(x, y)                                   # complex-parameter machines: takes y_true like the reference
         else:
-            # real-parameter SR is written in terms of the local energies; y_true = conj(E_loc - E) / B carries them
-            opt.step(x, np.conj(np.asarray(y)) * len(y))
+            # real-parameter SR is written in terms of the centred local energies.  y_true = conj(E_loc - E) / B_global
+            # carries them, but B_global != len(y) on a multi-GPU generator, so take them from the generator itself
+            gen = self.generator
+            if getattr(gen, 'current_local_energy', None) is not None and len(gen.current_local_energy) == len(y):
+                e_centred = np.asarray(gen.current_local_energy) - gen.current_energy
+            else:
+                e_centred = np.conj(np.asarray(y)) * float(getattr(gen, 'global_batch_size', len(y)))
+            opt.step(x, e_centred)
         return True
 
     def train_step(self):
@@ -260,6 +266,13 @@ class Trainer(object):
         for slot in ('m', 'v'):
             if getattr(opt, slot, None) is not None:
                 state['opt_' + slot] = getattr(opt, slot).cpu().numpy()
+        if self._accumulated:
+            raise RuntimeError('checkpoint requested in the middle of a gradient accumulation window')
+        if getattr(opt, 'params_ema', None) is not None:     # convert_to_accumulate_gradient_optimizer(ema_decay > 0)
+            state['opt_params_ema'] = opt.params_ema.cpu().numpy()
+        for counter in ('total_iterations', 'accumulated_iterations'):
+            if hasattr(opt, counter):
+                state['opt_' + counter] = np.int64(getattr(opt, counter))
         sampler = getattr(self.generator, 'sampler', None)
         if sampler is not None and hasattr(sampler, '_draws'):
             state['sampler_draws'] = np.int64(sampler._draws)
@@ -281,6 +294,11 @@ class Trainer(object):
             for slot in ('m', 'v'):
                 if 'opt_' + slot in f.files:
                     setattr(opt, slot, torch.from_numpy(f['opt_' + slot]).to(params.device))
+            if 'opt_params_ema' in f.files:
+                opt.params_ema = torch.from_numpy(f['opt_params_ema']).to(params.device)
+            for counter in ('total_iterations', 'accumulated_iterations'):
+                if 'opt_' + counter in f.files:
+                    setattr(opt, counter, int(f['opt_' + counter]))
             sampler = getattr(self.generator, 'sampler', None)
             if sampler is not None and 'sampler_draws' in f.files:
                 sampler._draws = int(f['sampler_draws'])

@@ -42,6 +42,7 @@ class _DeviceAutoregressiveSampler(Sampler):
         self.machine = conditional_log_probs_machine.machine
         self.seed = seed
         self.sample_offset = sample_offset   # global index of this rank's first sample (multi-GPU sharding)
+        self.shard_rank = None               # set by DistributedVariationalMonteCarlo: offset = shard_rank * batch_size
         self.engine = engine                 # None: follow the model's engine; FK_ENGINE_FP32 / FK_ENGINE_TC
         self._draws = 0
         self.last_p0 = None
@@ -49,6 +50,8 @@ class _DeviceAutoregressiveSampler(Sampler):
     def copy_with_new_batch_size(self, batch_size, mini_batch_size=None):
         new_sampler = copy.copy(self)
         new_sampler._set_batch_size(batch_size, mini_batch_size)
+        if getattr(self, 'shard_rank', None) is not None:      # keep the shards disjoint at the new batch size
+            new_sampler.sample_offset = self.shard_rank * batch_size
         return new_sampler
 
     def _effective_batch(self):

@@ -56,6 +56,37 @@ def test_philox_shard_offsets_partition_the_global_batch():
     assert s.copy_with_new_batch_size(16).batch_size == 16
 
 
+def _shard_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from flowket_b200 import Input, Model
+    from flowket_b200.machines import ConvNetAutoregressive2D
+    from flowket_b200.operators import Heisenberg
+    from flowket_b200.optimization import DistributedVariationalMonteCarlo
+    from flowket_b200.samplers import FastAutoregressiveSampler
+    inp = Input(shape=(4, 4))
+    m = ConvNetAutoregressive2D(inp, depth=2, num_of_channels=8)
+    cond = Model(inp, m.conditional_log_probs)
+    # a straight port of a reference Horovod script: nobody sets sample_offset
+    sampler = FastAutoregressiveSampler(cond, 32, seed=7)
+    vmc = DistributedVariationalMonteCarlo(Model(inp, m.predictions), Heisenberg(hilbert_state_shape=[4, 4], pbc=False), sampler)
+    first = sampler.sample_offset
+    bigger = sampler.copy_with_new_batch_size(128)
+    vmc.set_sampler(bigger)
+    out[rank] = (first, bigger.sample_offset, vmc.global_batch_size)
+    dist.destroy_process_group()
+
+
+def test_distributed_vmc_gives_every_rank_its_own_slice_of_the_philox_stream():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_shard_worker, args=(world, 29655, out), nprocs=world, join=True)
+    assert out[0] == (0, 0, 256) and out[1] == (32, 128, 256)
+
+
 def _sr_worker(rank, world, port, out):
     sys.path.insert(0, ROOT)
     os.environ['MASTER_ADDR'] = '127.0.0.1'

@@ -1,5 +1,6 @@
 """GPU tier, BASELINE.json full sizes (Heisenberg 10x10 OBC, ConvNetAutoregressive2D depth 20 / 32 channels,
-batch 8192): size-independent properties, because the oracle cannot evaluate these sizes in seconds."""
+batch 8192): size-independent properties at the full batch, plus a direct oracle comparison of the headline machine on a
+handful of samples (the fp64 oracle evaluates ~100 forwards per sample, a few seconds for 8 samples)."""
 import numpy as np
 import pytest
 import torch
@@ -104,3 +105,38 @@ def test_gradient_linearity_and_per_sample_consistency():
     want = 2.0 * (O_re.double().T @ yk.real.double() - O_im.double().T @ yk.imag.double())
     got = net.grad_weighted(sigma[:k], y1[:k]).double()
     assert torch.linalg.vector_norm(got - want) / torch.linalg.vector_norm(want) < 2e-5
+
+
+def test_headline_machine_against_the_oracle():
+    """10x10 / depth 20 / 32 channels, the machine of BASELINE configs[2], directly against the fp64 oracle on 8 samples:
+    log psi, E_loc and the weighted gradient of the fp32 engine at the 1e-5 contract, the tensor-core engines under their
+    stated tolerances (fp16 operands: <= 3x the error measured on the B200, printed below)."""
+    from flowket_b200 import FK_ENGINE_TC, FK_ENGINE_FP32
+    from flowket_b200.operators import Heisenberg
+    from flowket_b200.observables.monte_carlo import Observable
+    from oracle import nets, operators as oops, local_energy as oeloc
+    from tests.helpers import make_pair, random_sigma
+    model, _, spec, params = make_pair('conv2d', (H, W), 20, 32, seed=41)
+    n = 8
+    sigma = random_sigma(n, (H, W), seed=9)
+    want_lp = nets.log_psi_numpy(spec, params, sigma)[:, 0]
+    oop = oops.OracleOperator('heisenberg', (H, W), pbc=False)
+    want_e = oeloc.local_values(oop, lambda c: nets.log_psi_numpy(spec, params, c), sigma.astype(np.float64))
+    rng = np.random.RandomState(5)
+    y = ((rng.normal(size=n) + 1j * rng.normal(size=n)) / n).astype(np.complex64)
+    want_g = nets.weighted_gradient(spec, params, sigma, y.astype(np.complex128)).numpy()
+    obs = Observable(Heisenberg(hilbert_state_shape=[H, W], pbc=False))
+    net = model.machine.device_net()
+    report = {}
+    for name, eng in (('fp32', FK_ENGINE_FP32), ('tc', FK_ENGINE_TC)):
+        model.engine = eng
+        lp = model.predict(sigma)[:, 0]
+        e = obs.local_values(model, sigma)
+        g = net.grad_weighted(net.to_sigma(sigma), torch.from_numpy(y), engine=eng).cpu().numpy().astype(np.float64)
+        report[name] = (np.abs(lp - want_lp).max() / np.abs(want_lp).max(),
+                        (np.abs(e - want_e) / np.abs(want_e)).max(),
+                        np.linalg.norm(g - want_g) / np.linalg.norm(want_g))
+        print('headline machine, engine %s: log psi rel %.2e, E_loc rel (per sample, max) %.2e, gradient rel %.2e'
+              % ((name,) + report[name]))
+    assert report['fp32'][0] < 1e-5 and report['fp32'][1] < 1e-4 and report['fp32'][2] < 1e-4
+    assert report['tc'][0] < 2e-3 and report['tc'][1] < 2e-2 and report['tc'][2] < 3e-2

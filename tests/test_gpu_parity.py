@@ -22,6 +22,13 @@ NET_CASES = [
     ('conv1d', (12,), 5, 32, {'max_dilation_rate': 4, 'add_skip_connections': True}),
     ('cconv1d', (12,), 4, 16, {'max_dilation_rate': 4}),
     ('cconv1d', (20,), 5, 32, {'max_dilation_rate': 4}),
+    # channel counts / lattice sizes whose products are not multiples of 4 floats: every carved workspace buffer must
+    # still start 16-byte aligned (round-1 fault: cudaErrorMisalignedAddress in the float4 head kernels at C = 6)
+    ('conv1d', (11,), 4, 6, {'weights_normalization': False}),
+    ('conv1d', (13,), 5, 10, {}),
+    ('conv2d', (3, 5), 3, 6, {'weights_normalization': False}),
+    ('conv2d', (5, 3), 2, 12, {}),
+    ('cconv1d', (9,), 3, 6, {}),
 ]
 
 
@@ -250,6 +257,12 @@ GRAD_CASES = [
     ('conv1d', (12,), 5, 16, {'max_dilation_rate': 4, 'add_skip_connections': True}),
     ('conv1d', (10,), 4, 32, {'weights_normalization': False}),
     ('cconv1d', (10,), 3, 8, {'max_dilation_rate': 2}),
+    # odd channel counts / odd site counts / odd batch: workspace alignment (see NET_CASES)
+    ('conv1d', (11,), 4, 6, {'weights_normalization': False}),
+    ('conv1d', (13,), 3, 10, {}),
+    ('conv2d', (3, 5), 3, 6, {'weights_normalization': False}),
+    ('conv2d', (5, 3), 2, 12, {}),
+    ('cconv1d', (9,), 3, 6, {}),
 ]
 
 
@@ -271,3 +284,20 @@ def test_gradients_match_oracle(kind, shape, depth, channels, kw):
     want_im = nets.per_sample_gradients(spec, params, sigma[:5], 'imag').numpy()
     assert np.linalg.norm(O_re.cpu().numpy() - want_re) / np.linalg.norm(want_re) < 1e-5
     assert np.linalg.norm(O_im.cpu().numpy() - want_im) / max(np.linalg.norm(want_im), 1e-30) < 1e-5
+
+
+def test_samplers_and_local_energy_with_unaligned_channel_counts():
+    """naive sampler, incremental 1-D sampler and E_loc on a 6-channel / 11-site machine (alignment of the carved buffers)"""
+    from flowket_b200.samplers import FastAutoregressiveSampler, AutoregressiveSampler
+    from flowket_b200.observables.monte_carlo import Observable
+    model, cond_model, spec, params = make_pair('conv1d', (11,), 4, 6, seed=4, weights_normalization=False)
+    B = 13
+    u = np.random.RandomState(3).random_sample((B, 11))
+    want, _ = osampler.sample_with_uniforms(spec, params, u)
+    assert np.array_equal(FastAutoregressiveSampler(cond_model, B).next_device(uniforms=u).cpu().numpy(), want)
+    assert np.array_equal(AutoregressiveSampler(cond_model, B).next_device(uniforms=u).cpu().numpy(), want)
+    obs = Observable(_product_operator('heisenberg', (11,), dict(pbc=True)))
+    got = obs.local_values(model, want)
+    ref = oeloc.local_values(oops.OracleOperator('heisenberg', (11,), pbc=True),
+                             lambda c: nets.log_psi_numpy(spec, params, c), want.astype(np.float64))
+    assert _rel(got, ref) < 1e-5

@@ -258,6 +258,30 @@ def test_symmetrised_ensemble_matches_manual_combination_and_is_invariant():
     assert np.allclose(e_dev, e_host, rtol=1e-4, atol=1e-4)
 
 
+def test_vmc_with_a_symmetrised_ensemble_evaluates_the_ensemble():
+    """VariationalMonteCarlo(invariant_model, operator, sampler) (examples/j1j2_2d_monte_carlo.py:95 of the reference): the
+    local energies must be those of the symmetrised wave function, not of the base network."""
+    from flowket_b200 import Input
+    from flowket_b200.machines import make_2d_obc_invariants, make_up_down_invariant
+    from flowket_b200.operators import Ising
+    from flowket_b200.observables.monte_carlo import Observable
+    from flowket_b200.optimization import VariationalMonteCarlo
+    from flowket_b200.samplers import FastAutoregressiveSampler
+    shape = (4, 4)
+    model, cond, spec, params = make_pair('conv2d', shape, 3, 8, seed=3)
+    inp = Input(shape=shape)
+    ens = make_up_down_invariant(inp, make_2d_obc_invariants(inp, model))
+    op = Ising(hilbert_state_shape=list(shape), pbc=False, h=3.0)
+    vmc = VariationalMonteCarlo(ens, op, FastAutoregressiveSampler(cond, 48, seed=5))
+    batch, _ = vmc.next_batch()
+    obs = Observable(op)
+    want = obs.local_values(ens.predict, batch)
+    base = obs.local_values(model, batch)
+    assert np.allclose(vmc.current_local_energy, want, rtol=1e-5, atol=1e-5)
+    assert np.abs(vmc.current_local_energy - base).max() > 1e-3        # and they do differ from the base network's
+    assert vmc.current_energy == pytest.approx(want.mean())
+
+
 def test_checkpoint_resume_continues_the_same_trajectory(tmp_path):
     """Trainer.save_checkpoint / load_checkpoint (weights, Adam slots, sampler counter): 3 + 3 steps == 6 steps up to the
     summation-order noise of the atomics in the gradient kernels (a lost Adam slot or sampler counter shifts the
