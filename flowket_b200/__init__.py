@@ -9,6 +9,6 @@
 The arithmetic of the hot path lives in libflowket_b200.so (hand-written sm_100a CUDA, C ABI in
 include/flowket_b200.h); there is no CPU fallback."""
 from .keras_shim import Input, Model
-from ._lib import FlowketB200Error, FK_ENGINE_FP32, FK_ENGINE_TC
+from ._lib import FlowketB200Error, FK_ENGINE_FP32, FK_ENGINE_TC, FK_ENGINE_TC_EXACT
 
-__all__ = ['Input', 'Model', 'FlowketB200Error', 'FK_ENGINE_FP32', 'FK_ENGINE_TC']
+__all__ = ['Input', 'Model', 'FlowketB200Error', 'FK_ENGINE_FP32', 'FK_ENGINE_TC', 'FK_ENGINE_TC_EXACT']

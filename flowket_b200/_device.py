@@ -99,7 +99,7 @@ class DeviceNet(object):
             uniforms = uniforms.to(device=self.device, dtype=torch.float64).reshape(batch_size, self.sites).contiguous()
         if naive:
             size_fn, fn = self.lib.fk_sample_naive_workspace_bytes, self.lib.fk_sample_naive
-        elif engine == _lib.FK_ENGINE_TC:
+        elif engine in (_lib.FK_ENGINE_TC, _lib.FK_ENGINE_TC_EXACT):
             size_fn, fn = self.lib.fk_sample_tc_workspace_bytes, self.lib.fk_sample_tc
         else:
             size_fn, fn = self.lib.fk_sample_workspace_bytes, self.lib.fk_sample
@@ -134,7 +134,7 @@ class DeviceNet(object):
         B = sigma.shape[0]
         y2 = torch.view_as_real(y.to(device=self.device, dtype=torch.complex64).contiguous()).contiguous()
         grad = torch.empty(self.num_params, dtype=torch.float32, device=self.device)
-        if engine == _lib.FK_ENGINE_TC:
+        if engine in (_lib.FK_ENGINE_TC, _lib.FK_ENGINE_TC_EXACT):
             nbytes = self.lib.fk_grad_weighted_tc_workspace_bytes(self.handle, B)
             if nbytes < 0:
                 raise _lib.FlowketB200Error('the tensor-core gradient supports ConvNetAutoregressive2D (32 channels, '
@@ -153,7 +153,7 @@ class DeviceNet(object):
         B = sigma.shape[0]
         O_re = torch.empty((B, self.num_params), dtype=torch.float32, device=self.device)
         O_im = torch.empty((B, self.num_params), dtype=torch.float32, device=self.device) if imag else None
-        if engine == _lib.FK_ENGINE_TC:
+        if engine in (_lib.FK_ENGINE_TC, _lib.FK_ENGINE_TC_EXACT):
             nbytes = self.lib.fk_grad_per_sample_tc_workspace_bytes(self.handle, B)
             if nbytes < 0:
                 raise _lib.FlowketB200Error('tensor-core per-sample gradient: machine / lattice not supported')
@@ -177,7 +177,7 @@ def sr_gram(A, transpose_a, engine=_lib.FK_ENGINE_FP32, precise=True):
     M = cols if transpose_a else rows
     G = torch.empty((M, M), dtype=torch.float32, device=A.device)
     with torch.cuda.device(A.device):
-        if engine == _lib.FK_ENGINE_TC:
+        if engine in (_lib.FK_ENGINE_TC, _lib.FK_ENGINE_TC_EXACT):
             nbytes = lib.fk_sr_gram_tc_workspace_bytes(rows, cols, int(transpose_a), int(bool(precise)))
             ws = torch.empty(int(nbytes), dtype=torch.uint8, device=A.device)
             _lib.check(lib.fk_sr_gram_tc(_ptr(A), rows, cols, int(transpose_a), int(bool(precise)), _ptr(G), _ptr(ws),

@@ -15,7 +15,7 @@ FK_NET_CONV2D, FK_NET_CONV1D, FK_NET_CCONV1D = 0, 1, 2
 FK_FLAG_WEIGHT_NORM, FK_FLAG_EXP_NORM, FK_FLAG_SKIP = 1, 2, 4
 FK_OP_HEISENBERG, FK_OP_ISING, FK_OP_J1J2 = 0, 1, 2
 FK_TERM_EXCHANGE, FK_TERM_FLIP, FK_TERM_DIAG = 0, 1, 2
-FK_ENGINE_FP32, FK_ENGINE_TC = 0, 1
+FK_ENGINE_FP32, FK_ENGINE_TC, FK_ENGINE_TC_EXACT = 0, 1, 2
 
 
 class FkTerm(ctypes.Structure):
@@ -65,6 +65,16 @@ SIGNATURES = {
     'fk_sr_gram': (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     'fk_sr_gram_tc_workspace_bytes': (c_int64, [c_int64, c_int64, c_int, c_int]),
     'fk_sr_gram_tc': (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
+    'fk_sr_gram_xxt_workspace_bytes': (c_int64, [c_int64]),
+    'fk_sr_gram_xxt': (c_int, [c_void_p, c_int64, c_int64, c_int64, ctypes.c_float, c_void_p, c_int64, c_void_p, c_int64,
+                               c_void_p]),
+    'fk_sr_centre_shift_workspace_bytes': (c_int64, [c_int64]),
+    'fk_sr_centre_shift': (c_int, [c_void_p, c_int64, c_int64, ctypes.c_double, c_void_p, c_void_p, c_int64, c_void_p]),
+    'fk_sr_xt_w': (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    'fk_sr_solver_create': (c_int, [ctypes.POINTER(c_void_p)]),
+    'fk_sr_solver_destroy': (c_int, [c_void_p]),
+    'fk_sr_solve_workspace_bytes': (c_int64, [c_void_p, c_int64]),
+    'fk_sr_solve': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),
 }
 
 

@@ -425,7 +425,7 @@ extern "C" int fk_net_create(fk_net_t** out, int kind, int H, int W, int depth, 
   net->kind = kind; net->H = H; net->W = W; net->depth = depth; net->C = channels; net->k = kernel_size;
   net->max_dil = max_dilation; net->flags = flags; net->sites = H * W;
   net->d_params = net->d_weff = net->d_weffT = nullptr; net->d_optable = nullptr;
-  net->d_tc_weights = nullptr; net->tc_weight_bytes = 0; net->d_tc_bwd = nullptr; net->params_set = false;
+  net->d_tc_weights = nullptr; net->tc_weight_bytes = 0; net->d_tc_bwd = nullptr; net->d_tc_exact = nullptr; net->params_set = false;
   if (kind == FK_NET_CONV2D) build_conv2d(net);
   else if (kind == FK_NET_CONV1D) build_conv1d(net);
   else build_cconv1d(net);
@@ -450,6 +450,11 @@ extern "C" int fk_net_create(fk_net_t** out, int kind, int H, int W, int depth, 
     fk_net_destroy(net);
     return 1;
   }
+  // every device allocation of the handle happens here (the tensor-core engines' weight images and wiring tables too)
+  if (tc_prepare(net) || tc_grad_prepare(net) || tcx_prepare(net)) {
+    fk_net_destroy(net);
+    return 1;
+  }
   *out = net;
   return 0;
 }
@@ -459,6 +464,7 @@ extern "C" int fk_net_destroy(fk_net_t* net) {
   cudaFree(net->d_params); cudaFree(net->d_weff); cudaFree(net->d_weffT); cudaFree(net->d_optable);
   cudaFree(net->d_tc_weights);
   cudaFree(net->d_tc_bwd);
+  cudaFree(net->d_tc_exact);
   delete net;
   return 0;
 }
@@ -480,13 +486,14 @@ extern "C" int fk_net_set_params(fk_net_t* net, const float* params, void* strea
   if (tc_supported(net)) {
     if (tc_pack_weights(net, s)) return 1;
     if (tc_grad_supported(net) && tc_grad_pack_weights(net, s)) return 1;
+    if (tcx_supported(net) && tcx_pack_weights(net, s)) return 1;
   }
   return 0;
 }
 
 extern "C" int64_t fk_log_psi_workspace_bytes(const fk_net_t* net, int64_t n, int engine) {
   if (!net) return -1;
-  if (engine == FK_ENGINE_TC) return tc_log_psi_workspace_bytes(net, n);
+  if (engine == FK_ENGINE_TC || engine == FK_ENGINE_TC_EXACT) return tc_log_psi_workspace_bytes(net, n);
   return infer_floats_per_cfg(net) * (int64_t)sizeof(float) * std::max<int64_t>(n, 1);
 }
 
@@ -518,6 +525,11 @@ extern "C" int fk_log_psi(fk_net_t* net, const int8_t* sigma, int64_t n, float* 
     FK_REQUIRE(tc_supported(net), "fk_log_psi: the tensor-core engine supports ConvNetAutoregressive2D with 32 channels, kernel 3 only");
     return tc_log_psi(net, sigma, n, log_psi_out, ws, ws_bytes, (cudaStream_t)stream);
   }
+  if (engine == FK_ENGINE_TC_EXACT) {
+    FK_REQUIRE(tcx_supported(net), "fk_log_psi: the tc-exact engine supports ConvNetAutoregressive2D with 32 channels, kernel 3, lattices up to one 128-row tile");
+    return tcx_log_psi(net, sigma, n, log_psi_out, (cudaStream_t)stream);
+  }
+  FK_REQUIRE(engine == FK_ENGINE_FP32, "fk_log_psi: unknown engine %d", engine);
   return forward_chunks(net, sigma, n, log_psi_out, nullptr, ws, ws_bytes, (cudaStream_t)stream);
 }
 

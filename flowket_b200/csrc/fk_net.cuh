@@ -21,6 +21,7 @@ struct fk_net {
   void* d_tc_weights;
   int64_t tc_weight_bytes;
   void* d_tc_bwd;                     // transposed fp16 weight images of the tensor-core backward
+  void* d_tc_exact;                   // (hi, lo) fp16 weight images of the contract-accuracy tensor-core engine
   bool params_set;
 };
 
@@ -43,12 +44,33 @@ int tc_log_psi(fk_net* net, const int8_t* sigma, int64_t n, float* log_psi_out, 
 
 struct TcPublicGeometry { int P, p_first, npos, T, nb; };
 int tc_public_geometry(const fk_net* net, TcPublicGeometry* out);
+
+// Optional work list of the tensor-core forward kernels (the local-energy path): a work item is a connected
+// configuration given as (sample, flipped sites) -- the kernel applies the flips while it loads the sample's spins, so the
+// connected configurations never exist in memory -- and the last epilogue turns log psi into the local-energy term
+// mel * exp(log psi' - log psi(sample)) and adds it to the sample's accumulator (operator.py:20-42).
+struct TcWorkItem { int32_t sample; uint16_t site_a, site_b; };   // site 0xffff = none
+struct TcWork {
+  const long long* n_dev;    // number of items, read on the device (no host round trip); nullptr: the host-side n
+  const TcWorkItem* items;
+  const float* logpsi0;      // [B] float2: log psi of the samples
+  const float* mel;          // [items] matrix elements
+  double* eloc;              // [B] double2 accumulators (atomicAdd)
+};
 int tc_forward_launch(fk_net* net, const int8_t* sigma, int64_t n, float* log_psi_out, uint8_t* dump,
-                      uint32_t* dump_mask, float* dump_logits, cudaStream_t s);
+                      uint32_t* dump_mask, float* dump_logits, cudaStream_t s, const TcWork* work = nullptr);
+int tc_prepare(fk_net* net);        // allocations + wiring tables (fk_net_create)
+
+// contract-accuracy tensor-core engine (fk_tc_exact.cu)
+int tcx_supported(const fk_net* net);
+int tcx_prepare(fk_net* net);
+int tcx_pack_weights(fk_net* net, cudaStream_t s);
+int tcx_log_psi(fk_net* net, const int8_t* sigma, int64_t n, float* log_psi_out, cudaStream_t s, const TcWork* work = nullptr);
 
 // tensor-core gradient (fk_tc_grad.cu)
 int tc_grad_supported(const fk_net* net);
 int tc_grad_pack_weights(fk_net* net, cudaStream_t s);
+int tc_grad_prepare(fk_net* net);   // allocations + tables (fk_net_create)
 int64_t tc_grad_workspace_bytes(const fk_net* net, int64_t B);
 int tc_grad_weighted(fk_net* net, const int8_t* sigma, const float* y, int64_t B, float* grad_out, void* ws,
                      int64_t ws_bytes, cudaStream_t s);

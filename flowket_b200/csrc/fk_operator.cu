@@ -209,6 +209,74 @@ __global__ void eloc_reduce_kernel(const float* __restrict__ log_psi, const floa
   }
 }
 
+// ---- work-list pipeline of the tensor-core engines: the connected configurations are never materialised -------------
+// counts[b] = number of used connections; eloc[b] starts at the diagonal element (the k = 0 term of operator.py:20-42)
+__global__ void count_used_kernel(fk_operator_t op, const int8_t* __restrict__ sigma, long long B,
+                                  int* __restrict__ counts, double* __restrict__ eloc) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int8_t* s = sigma + b * op.num_sites;
+  int c = 0;
+  for (int t = 0; t < op.num_terms; ++t) c += term_used(op.terms[t], s) ? 1 : 0;
+  counts[b] = c;
+  eloc[2 * b] = diag_element(op.terms, op.num_terms, s, op.diag_fp32);
+  eloc[2 * b + 1] = 0.0;
+}
+
+// items[offsets[b] + r] = (b, flipped sites of the r-th used term), mel likewise; one warp per sample, term order kept
+__global__ void worklist_kernel(fk_operator_t op, const int8_t* __restrict__ sigma, long long B,
+                                const long long* __restrict__ offsets, TcWorkItem* __restrict__ items,
+                                float* __restrict__ mel) {
+  const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int8_t* s = sigma + b * op.num_sites;
+  long long pos = offsets[b];
+  for (int t0 = 0; t0 < op.num_terms; t0 += 32) {
+    const int t = t0 + lane;
+    bool used = false;
+    fk_term_t tm;
+    if (t < op.num_terms) {
+      tm = op.terms[t];
+      used = term_used(tm, s);
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, used);
+    if (used) {
+      const long long f = pos + __popc(mask & ((1u << lane) - 1u));
+      TcWorkItem wi;
+      wi.sample = (int32_t)b;
+      wi.site_a = (uint16_t)tm.site_a;
+      wi.site_b = tm.kind == FK_TERM_EXCHANGE ? (uint16_t)tm.site_b : (uint16_t)0xffffu;
+      items[f] = wi;
+      mel[f] = (float)tm.off_coef;
+    }
+    pos += __popc(mask);
+  }
+}
+
+// energy statistics for the allreduce (observable.py:10-14); fixed-order block sums, one atomic per block
+__global__ void eloc_stats_kernel(const double* __restrict__ eloc, long long B, double* __restrict__ stats) {
+  __shared__ double red[3][256];
+  double sr = 0.0, si = 0.0, s2 = 0.0;
+  for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long long)gridDim.x * blockDim.x) {
+    const double re = eloc[2 * b], im = eloc[2 * b + 1];
+    sr += re; si += im; s2 += re * re;
+  }
+  red[0][threadIdx.x] = sr; red[1][threadIdx.x] = si; red[2][threadIdx.x] = s2;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o)
+      for (int k = 0; k < 3; ++k) red[k][threadIdx.x] += red[k][threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    atomicAdd(stats + 0, red[0][0]);
+    atomicAdd(stats + 1, red[1][0]);
+    atomicAdd(stats + 2, red[2][0]);
+    if (blockIdx.x == 0) atomicAdd(stats + 3, (double)B);
+  }
+}
+
 }  // namespace fk
 
 using namespace fk;
@@ -224,20 +292,32 @@ extern "C" int fk_find_conn(const fk_operator_t* op, const int8_t* sigma, int64_
   return 0;
 }
 
-// workspace layout: counts int[B] | offsets i64[B+1] | mel0 f64[B] | melf f32[cap] | logpsi f32x2[cap] |
-//                   cfg int8[chunk*sites] | engine workspace
+// workspace layout
+//   fp32 engine:          counts int[B] | offsets i64[B+1] | mel0 f64[B] | melf f32[cap] | logpsi f32x2[cap] |
+//                         cfg int8[chunk*sites] | engine workspace                       (cap = max_conn * B)
+//   tensor-core engines:  counts int[B] | offsets i64[B+1] | logpsi0 f32x2[B] | mel f32[cap] | items 8 B[cap]
+//                                                                                        (cap = (max_conn - 1) * B)
 static int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }
 
 struct ElocLayout {
   int64_t counts, offsets, mel0, melf, logpsi, cfg, engine, total, chunk, engine_bytes;
+  int64_t logpsi0, items;
 };
 
 static ElocLayout eloc_layout(const fk_net* net, const fk_operator_t* op, int64_t B, int engine, int64_t ws_bytes) {
-  ElocLayout L;
-  const int64_t cap = (int64_t)op->max_conn * B;
+  ElocLayout L = {};
   int64_t o = 0;
   L.counts = o; o = align256(o + 4 * B);
   L.offsets = o; o = align256(o + 8 * (B + 1));
+  if (engine != FK_ENGINE_FP32) {
+    const int64_t cap = (int64_t)std::max(op->max_conn - 1, 1) * B;
+    L.logpsi0 = o; o = align256(o + 8 * B);
+    L.melf = o; o = align256(o + 4 * cap);
+    L.items = o; o = align256(o + 8 * cap);
+    L.total = o; L.chunk = cap;
+    return L;
+  }
+  const int64_t cap = (int64_t)op->max_conn * B;
   L.mel0 = o; o = align256(o + 8 * B);
   L.melf = o; o = align256(o + 4 * cap);
   L.logpsi = o; o = align256(o + 8 * cap);
@@ -245,8 +325,7 @@ static ElocLayout eloc_layout(const fk_net* net, const fk_operator_t* op, int64_
   int64_t chunk = std::min<int64_t>(cap, 65536);
   for (;;) {
     const int64_t cfg_bytes = align256(chunk * net->sites);
-    const int64_t eng = align256(engine == FK_ENGINE_TC ? tc_log_psi_workspace_bytes(net, chunk)
-                                                          : infer_floats_per_cfg(net) * 4 * chunk);
+    const int64_t eng = align256(infer_floats_per_cfg(net) * 4 * chunk);
     L.cfg = o; L.engine = o + cfg_bytes; L.engine_bytes = eng; L.total = o + cfg_bytes + eng; L.chunk = chunk;
     if (ws_bytes <= 0 || L.total <= ws_bytes || chunk <= 1) break;
     chunk = std::max<int64_t>(1, chunk / 2);
@@ -259,20 +338,66 @@ extern "C" int64_t fk_local_energy_workspace_bytes(const fk_net_t* net, const fk
   return eloc_layout(net, op, std::max<int64_t>(B, 1), engine, 0).total;
 }
 
+// Tensor-core engines: count -> scan -> work list -> log psi of the samples -> ONE persistent forward over all connected
+// configurations (flips applied in the kernel, ratio + accumulation in its last epilogue) -> statistics.  Nothing on this
+// path waits for the host; the number of work items stays on the device.
+static int local_energy_worklist(fk_net* net, const fk_operator_t* op, const int8_t* sigma, int64_t B, double* eloc_out,
+                                 double* stats_out, int64_t* n_conn_out, int engine, const ElocLayout& L, char* base,
+                                 cudaStream_t s) {
+  FK_REQUIRE(op->num_sites < 65535 && B < 2147483647LL, "fk_local_energy: work-list index range exceeded");
+  int* counts = (int*)(base + L.counts);
+  long long* offsets = (long long*)(base + L.offsets);
+  float* logpsi0 = (float*)(base + L.logpsi0);
+  float* mel = (float*)(base + L.melf);
+  TcWorkItem* items = (TcWorkItem*)(base + L.items);
+  count_used_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(*op, sigma, B, counts, eloc_out);
+  FK_CHECK_LAUNCH();
+  scan_kernel<<<1, 1024, 0, s>>>(counts, B, offsets);
+  FK_CHECK_LAUNCH();
+  worklist_kernel<<<(unsigned)((B * 32 + 255) / 256), 256, 0, s>>>(*op, sigma, B, offsets, items, mel);
+  FK_CHECK_LAUNCH();
+  TcWork wk;
+  wk.n_dev = offsets + B; wk.items = items; wk.logpsi0 = logpsi0; wk.mel = mel; wk.eloc = eloc_out;
+  const int64_t cap = L.chunk;
+  if (engine == FK_ENGINE_TC) {
+    if (tc_forward_launch(net, sigma, B, logpsi0, nullptr, nullptr, nullptr, s)) return 1;
+    if (tc_forward_launch(net, sigma, cap, nullptr, nullptr, nullptr, nullptr, s, &wk)) return 1;
+  } else {
+    if (tcx_log_psi(net, sigma, B, logpsi0, s)) return 1;
+    if (tcx_log_psi(net, sigma, cap, nullptr, s, &wk)) return 1;
+  }
+  if (stats_out) {
+    FK_CHECK_CUDA(cudaMemsetAsync(stats_out, 0, 4 * sizeof(double), s));
+    eloc_stats_kernel<<<(unsigned)std::min<int64_t>(64, (B + 255) / 256), 256, 0, s>>>(eloc_out, B, stats_out);
+    FK_CHECK_LAUNCH();
+  }
+  if (n_conn_out) {   // optional host-side count: the only reason this path would wait for the device
+    long long total = 0;
+    FK_CHECK_CUDA(cudaMemcpyAsync(&total, offsets + B, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    FK_CHECK_CUDA(cudaStreamSynchronize(s));
+    *n_conn_out = total + B;
+  }
+  return 0;
+}
+
 extern "C" int fk_local_energy(fk_net_t* net, const fk_operator_t* op, const int8_t* sigma, int64_t B, double* eloc_out,
                                double* stats_out, int64_t* n_conn_out, int engine, void* ws, int64_t ws_bytes,
                                void* stream) {
   FK_REQUIRE(net && op && sigma && eloc_out && ws, "fk_local_energy: NULL argument");
   FK_REQUIRE(op->num_sites == net->sites, "fk_local_energy: operator has %d sites, machine has %d", op->num_sites, net->sites);
   FK_REQUIRE(net->params_set, "machine parameters were never set (fk_net_set_params)");
+  FK_REQUIRE(engine == FK_ENGINE_FP32 || engine == FK_ENGINE_TC || engine == FK_ENGINE_TC_EXACT, "fk_local_energy: unknown engine %d", engine);
   if (engine == FK_ENGINE_TC)
     FK_REQUIRE(tc_supported(net), "fk_local_energy: the tensor-core engine supports ConvNetAutoregressive2D with 32 channels, kernel 3 only");
+  if (engine == FK_ENGINE_TC_EXACT)
+    FK_REQUIRE(tcx_supported(net), "fk_local_energy: the tc-exact engine supports ConvNetAutoregressive2D with 32 channels, kernel 3, lattices up to one 128-row tile");
   if (B == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   const ElocLayout L = eloc_layout(net, op, B, engine, ws_bytes);
   FK_REQUIRE(L.total <= ws_bytes, "fk_local_energy: workspace too small (%lld < %lld bytes)", (long long)ws_bytes,
              (long long)L.total);
   char* base = (char*)ws;
+  if (engine != FK_ENGINE_FP32) return local_energy_worklist(net, op, sigma, B, eloc_out, stats_out, n_conn_out, engine, L, base, s);
   int* counts = (int*)(base + L.counts);
   long long* offsets = (long long*)(base + L.offsets);
   double* mel0 = (double*)(base + L.mel0);
@@ -285,6 +410,7 @@ extern "C" int fk_local_energy(fk_net_t* net, const fk_operator_t* op, const int
   FK_CHECK_LAUNCH();
   scan_kernel<<<1, 1024, 0, s>>>(counts, B, offsets);
   FK_CHECK_LAUNCH();
+  // the fp32 (parity) engine materialises the connected configurations in chunks sized on the host
   long long total = 0;
   FK_CHECK_CUDA(cudaMemcpyAsync(&total, offsets + B, sizeof(long long), cudaMemcpyDeviceToHost, s));
   FK_CHECK_CUDA(cudaStreamSynchronize(s));
@@ -294,13 +420,9 @@ extern "C" int fk_local_energy(fk_net_t* net, const fk_operator_t* op, const int
     const long long m = std::min<long long>(L.chunk, total - f0);
     gen_conn_kernel<<<(unsigned)((m * 32 + 255) / 256), 256, 0, s>>>(*op, sigma, B, offsets, f0, m, cfg, melf);
     FK_CHECK_LAUNCH();
-    if (engine == FK_ENGINE_TC) {
-      if (tc_log_psi(net, cfg, m, logpsi + 2 * f0, eng_ws, L.engine_bytes, s)) return 1;
-    } else {
-      assign_infer_buffers(net, (float*)eng_ws, m, bp);
-      if (run_forward(net, cfg, m, bp.data(), s)) return 1;
-      if (launch_head(bp[net->logits_buf], cfg, net->sites, m, logpsi + 2 * f0, nullptr, s)) return 1;
-    }
+    assign_infer_buffers(net, (float*)eng_ws, m, bp);
+    if (run_forward(net, cfg, m, bp.data(), s)) return 1;
+    if (launch_head(bp[net->logits_buf], cfg, net->sites, m, logpsi + 2 * f0, nullptr, s)) return 1;
   }
   if (stats_out) FK_CHECK_CUDA(cudaMemsetAsync(stats_out, 0, 4 * sizeof(double), s));
   eloc_reduce_kernel<<<(unsigned)((B * 32 + 255) / 256), 256, 0, s>>>(logpsi, melf, mel0, offsets, B, eloc_out, stats_out);

@@ -103,6 +103,7 @@ struct TcArgs {
   uint8_t* dump;
   uint32_t* dump_mask;
   float* dump_logits;
+  TcWork wk;   // local-energy work list (all null: plain log psi of the configurations in `sigma`)
 };
 
 constexpr int TC_DUMP_TENSORS = 5;
@@ -197,7 +198,8 @@ __global__ void __launch_bounds__(MAXNP * 128 + 32 + TC_ISSUERS * 32, 1) tc_forw
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const long long groups = (a.n + a.np - 1) / a.np;  // configuration groups (one per CTA iteration)
+  const long long n_items = a.wk.n_dev ? *a.wk.n_dev : a.n;
+  const long long groups = (n_items + a.np - 1) / a.np;  // configuration groups (one per CTA iteration)
   const long long my_iters = (long long)blockIdx.x < groups ? (groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (is_producer) {
@@ -394,16 +396,27 @@ __global__ void __launch_bounds__(MAXNP * 128 + 32 + TC_ISSUERS * 32, 1) tc_forw
     for (long long it = 0; it < my_iters; ++it) {
       const long long group = it * gridDim.x + blockIdx.x;
       const long long cfg = group * a.np + pipe;
-      const bool active = cfg < a.n;
+      const bool active = cfg < n_items;
 
       // ---- input embedding: channel 0 = sigma, channels 1..31 = 0, padding positions = 0
+      // (work list: the configuration is the item's sample with the item's sites flipped -- an exchange of an
+      //  anti-parallel pair flips both, operators/heisenberg.py:94-95)
       float sig[TC_MAX_T];
+      long long src = cfg;
+      int flip_a = -1, flip_b = -1;
+      if (a.wk.items && active) {
+        const TcWorkItem wi = a.wk.items[cfg];
+        src = wi.sample;
+        flip_a = wi.site_a == 0xffffu ? -1 : (int)wi.site_a;
+        flip_b = wi.site_b == 0xffffu ? -1 : (int)wi.site_b;
+      }
       {
         const int in_slot = sdesc[0].in_v;
 #pragma unroll
         for (int t = 0; t < TC_MAX_T; ++t) {
           if (t >= a.T) break;
-          sig[t] = (active && site[t] >= 0) ? (float)a.sigma[cfg * HW + site[t]] : 0.f;
+          sig[t] = (active && site[t] >= 0) ? (float)a.sigma[src * HW + site[t]] : 0.f;
+          if (site[t] >= 0 && (site[t] == flip_a || site[t] == flip_b)) sig[t] = -sig[t];
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -581,8 +594,17 @@ __global__ void __launch_bounds__(MAXNP * 128 + 32 + TC_ISSUERS * 32, 1) tc_forw
               r0 += red[(pipe * 4 + w) * 2 + 0];
               r1 += red[(pipe * 4 + w) * 2 + 1];
             }
-            a.out[2 * cfg + 0] = r0;
-            a.out[2 * cfg + 1] = r1;
+            if (a.wk.eloc) {   // fused local-energy term: ratio in complex64, accumulation in complex128
+              const float dr = r0 - a.wk.logpsi0[2 * src], di = r1 - a.wk.logpsi0[2 * src + 1];
+              const float mag = expf(dr), m = a.wk.mel[cfg];
+              float sn, cs;
+              sincosf(di, &sn, &cs);
+              atomicAdd(a.wk.eloc + 2 * src, (double)m * (double)(mag * cs));
+              atomicAdd(a.wk.eloc + 2 * src + 1, (double)m * (double)(mag * sn));
+            } else {
+              a.out[2 * cfg + 0] = r0;
+              a.out[2 * cfg + 1] = r1;
+            }
           }
         }
         // this thread is done with the weight image (the block's MMAs have retired, its bias reads are behind it)
@@ -649,10 +671,11 @@ static size_t align256z(size_t x) { return (x + 255) / 256 * 256; }
 static size_t tc_desc_offset(int nb) { return align256z((size_t)nb * IMG_BYTES); }
 static size_t tc_pack_offset(int nb) { return tc_desc_offset(nb) + align256z(sizeof(TcBlockDesc) * nb); }
 
-int tc_pack_weights(fk_net* net, cudaStream_t s) {
+int tc_prepare(fk_net* net) {
+  if (!tc_supported(net)) return 0;
   const int nb = 2 * net->depth - 2;
   const size_t total = tc_pack_offset(nb) + sizeof(TcPackDesc) * nb;
-  if (!net->d_tc_weights) {
+  {
     FK_CHECK_CUDA(cudaMalloc(&net->d_tc_weights, total));
     net->tc_weight_bytes = (int64_t)total;
     // residual / buffer wiring -> shared-memory slots (reference counting; residual adds are done in place)
@@ -713,6 +736,12 @@ int tc_pack_weights(fk_net* net, cudaStream_t s) {
     FK_CHECK_CUDA(cudaMemcpy((uint8_t*)net->d_tc_weights + tc_pack_offset(nb), pd.data(), sizeof(TcPackDesc) * nb,
                              cudaMemcpyHostToDevice));
   }
+  return 0;
+}
+
+int tc_pack_weights(fk_net* net, cudaStream_t s) {
+  const int nb = 2 * net->depth - 2;
+  FK_REQUIRE(net->d_tc_weights, "tc_pack_weights: the machine was created without the tensor-core tables");
   const TcPackDesc* d_pd = reinterpret_cast<const TcPackDesc*>((uint8_t*)net->d_tc_weights + tc_pack_offset(nb));
   tc_pack_kernel<<<nb, 256, 0, s>>>(net->d_weff, d_pd, (uint8_t*)net->d_tc_weights);
   FK_CHECK_LAUNCH();
@@ -737,7 +766,7 @@ int tc_log_psi(fk_net* net, const int8_t* sigma, int64_t n, float* log_psi_out, 
 }
 
 int tc_forward_launch(fk_net* net, const int8_t* sigma, int64_t n, float* log_psi_out, uint8_t* dump,
-                      uint32_t* dump_mask, float* dump_logits, cudaStream_t s) {
+                      uint32_t* dump_mask, float* dump_logits, cudaStream_t s, const TcWork* work) {
   FK_REQUIRE(net->params_set && net->d_tc_weights, "tensor-core weights were never packed (fk_net_set_params)");
   if (n == 0) return 0;
   const TcGeometry g = tc_geometry(net);
@@ -750,6 +779,7 @@ int tc_forward_launch(fk_net* net, const int8_t* sigma, int64_t n, float* log_ps
   a.H = net->H; a.W = net->W; a.P = g.P; a.nb = nb; a.T = g.T; a.npos = g.npos; a.p_first = g.p_first; a.np = g.np;
   a.tmem_cols = g.tmem_cols; a.cst_off = (int)(g.smem_bytes - 4096); a.slots = g.slots;
   a.dump = dump; a.dump_mask = dump_mask; a.dump_logits = dump_logits;
+  if (work) a.wk = *work; else a.wk = TcWork{nullptr, nullptr, nullptr, nullptr, nullptr};
   FK_REQUIRE(dump == nullptr || g.T == 1, "tensor-core gradient: lattice needs more than one M tile");
   int dev = 0, sms = 148;
   FK_CHECK_CUDA(cudaGetDevice(&dev));

@@ -1,0 +1,648 @@
+// Tensor-core engine at the contract accuracy ("tc-exact"): the same fused ConvNetAutoregressive2D forward as fk_tc.cu
+// (machines/conv_net_autoregressive_2D.py:24-74, machines/abstract_machine.py:31-57), with every operand split into two
+// fp16 numbers, x = hi + lo (22 significant bits), and every product formed from three tensor-core passes
+//     A B  ~=  A_hi B_hi + A_hi B_lo + A_lo B_hi          (the lo x lo term is below 2^-22)
+// packed into TWO tcgen05.mma per (tap, k-step):
+//     MMA 1:  A_hi  x  [B_hi | B_lo]   N = 2n   -> accumulator columns [c, c+n) = hi*hi, [c+n, c+2n) = hi*lo
+//     MMA 2:  A_lo  x   B_hi           N = n    -> accumulated into the small-term columns [c+n, c+2n)
+// so that the A tile (the dominant shared-memory operand stream) is fetched twice, not three times, and the large and
+// the small partial sums never share an fp32 accumulator (the tensor core truncates once per MMA: keeping hi*hi alone
+// bounds that bias by the 18 MMAs of one convolution).  The epilogue adds the two column groups in fp32, applies
+// bias (via a ones x [b_hi, b_lo] MMA) / residual / relu exactly as the fp16 engine does, and writes the next layer's
+// operand as an (hi, lo) pair of fp16 tiles.  Weights and biases are pre-scaled by 2^8 so that their lo parts stay in
+// the fp16 normal range; the epilogue multiplies by 2^-8 (exact).
+//
+// Shared memory: 2 pipelines x 3 activation slots x (hi + lo tile) + ONE weight image per block, streamed in two
+// chunks (A: the phase-1 convolutions, B: phases 2-4) so that chunk A of block b+1 lands while phases 2-3 of block b
+// run and chunk B while phase 1 of block b+1 runs -- double buffering at a single image's footprint.  The horizontal
+// stack's residual input lives in fp32 registers.  Lattices that fit one 128-row tile (up to 10 x 10).
+#include <algorithm>
+
+#include "fk_net.cuh"
+#include "fk_tc_common.cuh"
+
+namespace fk {
+
+struct TcBlockDesc {   // same wiring record as fk_tc.cu
+  int8_t in_v, in_h, out_a, out_r, res_v, x1, c, out_h, res_h, last, save_h, pad1;
+};
+
+// ---- weight image (bytes).  A B tile for one (tap, k-step) is [k group 0..1][2n rows: n hi + n lo][8 el] fp16.
+constexpr int XA_X = 0;            // 3 taps x 2 k-steps x 2048 B (n = 32)
+constexpr int XA_V = 12288;        // 9 x 2 x 2048
+constexpr int XA_BT_X = 49152;     // bias tile: 32 rows x [hi, lo, 0 x 6]
+constexpr int XA_BT_V = 49664;
+constexpr int XA_BYTES = 50176;
+constexpr int XB_XX = 0;           // 2 k-steps x 1024 B (n = 16)
+constexpr int XB_Y = 2048;
+constexpr int XB_H = 4096;         // 9 x 2 x 2048
+constexpr int XB_HEAD = 40960;     // 2 x 1024 (n = 16, 4 real columns)
+constexpr int XB_BT_XX = 43008;    // 16 rows
+constexpr int XB_BT_Y = 43264;
+constexpr int XB_BT_H = 43520;     // 32 rows
+constexpr int XB_BT_HEAD = 44032;  // 16 rows
+constexpr int XB_BYTES = 44288;
+constexpr int XIMG_BYTES = XA_BYTES + XB_BYTES;
+constexpr float X_WSCALE = 256.f, X_WINV = 1.f / 256.f;
+constexpr int X_NP = 2, X_SLOTS = 3, X_ISSUERS = 3;
+
+struct XPackDesc {
+  long long w[5], b[5];  // V, X, XX, Y, H
+  long long w_head, b_head;
+  int cin;
+};
+
+__device__ __forceinline__ void split_h(float v, __half& hi, __half& lo) {
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+
+__global__ void tcx_pack_kernel(const float* __restrict__ weff, const XPackDesc* __restrict__ pd, uint8_t* __restrict__ images) {
+  const XPackDesc d = pd[blockIdx.x];
+  uint8_t* img = images + (size_t)blockIdx.x * XIMG_BYTES;
+  const int reg_off[6] = {XA_V, XA_X, XA_BYTES + XB_XX, XA_BYTES + XB_Y, XA_BYTES + XB_H, XA_BYTES + XB_HEAD};
+  const int reg_taps[6] = {9, 3, 1, 1, 9, 1};
+  const int reg_n[6] = {32, 32, 16, 16, 32, 16};
+  for (int r = 0; r < 6; ++r) {
+    const int N = reg_n[r], taps = reg_taps[r];
+    const int cin = (r == 0 || r == 1) ? d.cin : 32;
+    const int nreal = (r == 5) ? 4 : N;
+    const long long woff = (r == 5) ? d.w_head : d.w[r];
+    __half* w16 = reinterpret_cast<__half*>(img + reg_off[r]);
+    const int total = taps * 2 * 2 * N * 8;   // (tap, kstep, kgroup, n, e): one (hi, lo) pair each
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+      const int el = e & 7;
+      const int n = (e >> 3) % N;
+      const int g = ((e >> 3) / N) & 1;
+      const int ks = ((e >> 3) / N / 2) & 1;
+      const int tap = (e >> 3) / N / 4;
+      const int ci = ks * 16 + g * 8 + el;
+      float v = 0.f;
+      if (ci < cin && n < nreal) v = weff[woff + ((long long)tap * cin + ci) * nreal + n] * X_WSCALE;
+      __half hi, lo;
+      split_h(v, hi, lo);
+      const int tile = (tap * 2 + ks) * (2 * 2 * N * 8);
+      w16[tile + (g * 2 * N + n) * 8 + el] = hi;
+      w16[tile + (g * 2 * N + N + n) * 8 + el] = lo;
+    }
+  }
+  // bias tiles: per output channel one 16-byte row [hi, lo, 0 x 6] of 256 * bias
+  const int bt_off[6] = {XA_BT_V, XA_BT_X, XA_BYTES + XB_BT_XX, XA_BYTES + XB_BT_Y, XA_BYTES + XB_BT_H, XA_BYTES + XB_BT_HEAD};
+  for (int r = 0; r < 6; ++r) {
+    const int N = reg_n[r], nreal = (r == 5) ? 4 : N;
+    const long long boff = (r == 5) ? d.b_head : d.b[r];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      const float bv = i < nreal ? weff[boff + i] * X_WSCALE : 0.f;
+      __half hi, lo;
+      split_h(bv, hi, lo);
+      __half* row = reinterpret_cast<__half*>(img + bt_off[r] + 16 * i);
+      row[0] = hi; row[1] = lo;
+      for (int k = 2; k < 8; ++k) row[k] = __float2half_rn(0.f);
+    }
+  }
+}
+
+struct TcxArgs {
+  const uint8_t* images;
+  const TcBlockDesc* desc;
+  const int8_t* sigma;
+  float* out;
+  long long n;
+  int H, W, P, nb, npos, p_first, cst_off;
+  TcWork wk;   // local-energy work list (see fk_net.cuh)
+};
+
+// two 32-column TMEM loads, one wait
+__device__ __forceinline__ void tmem_ld32x2(uint32_t taddr, float (&a)[32], float (&b)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]), "=f"(a[4]), "=f"(a[5]), "=f"(a[6]), "=f"(a[7]), "=f"(a[8]),
+        "=f"(a[9]), "=f"(a[10]), "=f"(a[11]), "=f"(a[12]), "=f"(a[13]), "=f"(a[14]), "=f"(a[15]), "=f"(a[16]),
+        "=f"(a[17]), "=f"(a[18]), "=f"(a[19]), "=f"(a[20]), "=f"(a[21]), "=f"(a[22]), "=f"(a[23]), "=f"(a[24]),
+        "=f"(a[25]), "=f"(a[26]), "=f"(a[27]), "=f"(a[28]), "=f"(a[29]), "=f"(a[30]), "=f"(a[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=f"(b[0]), "=f"(b[1]), "=f"(b[2]), "=f"(b[3]), "=f"(b[4]), "=f"(b[5]), "=f"(b[6]), "=f"(b[7]), "=f"(b[8]),
+        "=f"(b[9]), "=f"(b[10]), "=f"(b[11]), "=f"(b[12]), "=f"(b[13]), "=f"(b[14]), "=f"(b[15]), "=f"(b[16]),
+        "=f"(b[17]), "=f"(b[18]), "=f"(b[19]), "=f"(b[20]), "=f"(b[21]), "=f"(b[22]), "=f"(b[23]), "=f"(b[24]),
+        "=f"(b[25]), "=f"(b[26]), "=f"(b[27]), "=f"(b[28]), "=f"(b[29]), "=f"(b[30]), "=f"(b[31])
+      : "r"(taddr + 32u)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Thread layout: X_NP pipelines x 128 epilogue threads + 1 producer warp + X_ISSUERS MMA issuer warps (see fk_tc.cu for
+// why dedicated issuer warps).  Barriers: fullA, fullB (weights landed), emptyA, emptyB (X_NP*128 arrivals),
+// mma[X_NP] (tcgen05.commit of the pipeline's current phase), ready[X_NP] (128 arrivals: operand tiles written).
+__global__ void __launch_bounds__(X_NP * 128 + 32 + X_ISSUERS * 32, 1) tcx_forward_kernel(TcxArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int pipe = tid >> 7, ltid = tid & 127;
+  const bool is_producer = warp == X_NP * 4;
+  const bool is_issuer = warp > X_NP * 4;
+  const int tile_bytes = 64 * a.npos;          // one fp16 tile: 4 channel groups x npos x 16 B
+  const int slot_bytes = 2 * tile_bytes;       // hi tile, lo tile
+  uint8_t* wA = smem;
+  uint8_t* wB = smem + XA_BYTES;
+  uint8_t* act0 = smem + XIMG_BYTES;
+  uint8_t* tail = act0 + (size_t)X_NP * X_SLOTS * slot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);   // fullA, fullB, emptyA, emptyB, mma[2], ready[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 96);
+  volatile uint32_t* issued = reinterpret_cast<volatile uint32_t*>(tail + 104);
+  float* red = reinterpret_cast<float*>(tail + 128);    // [np][4 warps][2]
+  TcBlockDesc* sdesc = reinterpret_cast<TcBlockDesc*>(tail + 384);
+  uint8_t* ones_tile = smem + a.cst_off;
+  uint8_t* zero_tile = ones_tile + 2048;
+
+  const uint32_t fullA = smem_u32(&bars[0]), fullB = smem_u32(&bars[1]);
+  const uint32_t emptyA = smem_u32(&bars[2]), emptyB = smem_u32(&bars[3]);
+  const uint32_t mbar = smem_u32(&bars[4 + ((is_producer || is_issuer) ? 0 : pipe)]);
+  const uint32_t rbar = smem_u32(&bars[6 + ((is_producer || is_issuer) ? 0 : pipe)]);
+
+  if (tid == 32) {
+    issued[0] = issued[1] = 0u;
+    mbar_init(fullA, 1);
+    mbar_init(fullB, 1);
+    mbar_init(emptyA, X_NP * 128);
+    mbar_init(emptyB, X_NP * 128);
+    for (int p = 0; p < X_NP; ++p) {
+      mbar_init(smem_u32(&bars[4 + p]), 1);
+      mbar_init(smem_u32(&bars[6 + p]), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < a.nb; i += blockDim.x) sdesc[i] = a.desc[i];
+  for (int i = tid; i < 256; i += blockDim.x)
+    reinterpret_cast<uint4*>(ones_tile)[i] = i < 128 ? make_uint4(0x3C003C00u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+  {
+    uint4* z = reinterpret_cast<uint4*>(act0);
+    const int n16 = X_NP * X_SLOTS * slot_bytes / 16;
+    for (int i = tid; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long n_items = a.wk.n_dev ? *a.wk.n_dev : a.n;
+  const long long groups = (n_items + X_NP - 1) / X_NP;
+  const long long my_iters = (long long)blockIdx.x < groups ? (groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (is_producer) {
+    const long long total = my_iters * a.nb;
+    for (long long s = 0; s < total; ++s) {
+      if (lane == 0) {
+        const uint8_t* src = a.images + (size_t)(s % a.nb) * XIMG_BYTES;
+        if (s >= 1) mbar_wait(emptyA, (uint32_t)((s - 1) & 1));
+        mbar_expect_tx(fullA, XA_BYTES);
+        bulk_g2s(smem_u32(wA), src, XA_BYTES, fullA);
+        if (s >= 1) mbar_wait(emptyB, (uint32_t)((s - 1) & 1));
+        mbar_expect_tx(fullB, XB_BYTES);
+        bulk_g2s(smem_u32(wB), src + XA_BYTES, XB_BYTES, fullB);
+      }
+      __syncwarp();
+    }
+  } else if (is_issuer) {
+    const int role = __shfl_sync(0xffffffffu, warp - (X_NP * 4 + 1), 0);
+    const uint32_t tile16 = 4u * (uint32_t)a.npos, slot16 = 8u * (uint32_t)a.npos, kstep16 = 2u * (uint32_t)a.npos;
+    const uint32_t hi = 8u | (1u << 14);                         // SBO = 8 (x16 B), descriptor version bit 46
+    const uint32_t a_lbo = (uint32_t)a.npos << 16;
+    const uint32_t act16 = smem_u32(act0) >> 4;
+    const uint32_t wA16 = smem_u32(wA) >> 4, wB16 = smem_u32(wB) >> 4;
+    const int P = a.P;
+    // one tap, both k-steps: hi x [hi | lo] (N = 2n) then lo x hi (N = n) into the small-term columns
+    auto tap_quad = [&](uint32_t d_tmem, uint32_t a16, int off, uint32_t w16, bool n32, uint32_t acc) {
+      const uint32_t n = n32 ? 32u : 16u;
+      const uint32_t ahi = ((a16 + (uint32_t)off) & 0x3FFFu) | a_lbo;
+      const uint32_t alo = ((a16 + tile16 + (uint32_t)off) & 0x3FFFu) | a_lbo;
+      const uint32_t blo = (w16 & 0x3FFFu) | ((2u * n) << 16);
+      const uint32_t id2 = make_idesc((int)(2u * n)), id1 = make_idesc((int)n);
+      const uint32_t wstep = n32 ? 128u : 64u;
+      umma_f16_lohi(d_tmem, ahi, blo, hi, id2, acc);
+      umma_f16_lohi(d_tmem + n, alo, blo, hi, id1, 1u);
+      umma_f16_lohi(d_tmem, ahi + kstep16, blo + wstep, hi, id2, 1u);
+      umma_f16_lohi(d_tmem + n, alo + kstep16, blo + wstep, hi, id1, 1u);
+    };
+    const uint32_t ones16 = smem_u32(ones_tile) >> 4, zero16 = smem_u32(zero_tile) >> 4;
+    auto bias_mma = [&](uint32_t d_tmem, uint32_t bt16, int n) {
+      const uint32_t alo = ones16 | ((zero16 - ones16) << 16);
+      const uint32_t blo = (bt16 & 0x3FFFu) | (((zero16 - bt16) & 0x3FFFu) << 16);
+      umma_f16_lohi(d_tmem, alo, blo, hi, make_idesc(n), 1u);
+    };
+    long long step = 0;
+    uint32_t turn = 0, phase_count = 0;
+    for (long long it = 0; it < my_iters; ++it) {
+      for (int b = 0; b < a.nb; ++b, ++step) {
+        const TcBlockDesc d = sdesc[b];
+        bool have_a = false, have_b = false;
+        const int last = __shfl_sync(0xffffffffu, d.last, 0);
+        const int nph = last ? 4 : 3;
+        for (int ph = 1; ph <= nph; ++ph, ++phase_count) {
+          const uint32_t s0 = __shfl_sync(0xffffffffu, (uint32_t)(ph == 1 ? d.in_h : ph == 2 ? d.x1 : ph == 3 ? d.c : d.out_h), 0);
+          const uint32_t s1 = __shfl_sync(0xffffffffu, (uint32_t)(ph == 1 ? d.in_v : d.out_a), 0);
+          for (int p = 0; p < X_NP; ++p, ++turn) {
+            if ((int)(turn % X_ISSUERS) != role) continue;
+            if (ph == 1 && !have_a) { mbar_wait(fullA, (uint32_t)(step & 1)); have_a = true; }
+            if (ph >= 2 && !have_b) { mbar_wait(fullB, (uint32_t)(step & 1)); have_b = true; }
+            {
+              uint32_t spins = 0;
+              while (issued[p] < phase_count) {
+                if (++spins > (1u << 26)) __trap();
+              }
+            }
+            mbar_wait(smem_u32(&bars[6 + p]), phase_count & 1u);
+            tc_fence_after();
+            const uint32_t row00 = act16 + (uint32_t)(p * X_SLOTS) * slot16 + (uint32_t)a.p_first;
+            const uint32_t dt = tmem_base + (uint32_t)(p * 128);
+            const uint32_t a0 = row00 + s0 * slot16, a1 = row00 + s1 * slot16;
+            if (elect_one()) {
+              if (ph == 1) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                  tap_quad(dt + 0, a0, j - 2, wA16 + XA_X / 16 + 256 * j, true, j != 0);
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                  for (int j = 0; j < 3; ++j)
+                    tap_quad(dt + 64, a1, (i - 2) * P + (j - 1), wA16 + XA_V / 16 + 256 * (i * 3 + j), true, (i | j) != 0);
+                bias_mma(dt + 0, wA16 + XA_BT_X / 16, 32);
+                bias_mma(dt + 64, wA16 + XA_BT_V / 16, 32);
+              } else if (ph == 2) {
+                tap_quad(dt + 0, a0, last ? -1 : 0, wB16 + XB_XX / 16, false, 0u);
+                tap_quad(dt + 32, a1, -P, wB16 + XB_Y / 16, false, 0u);
+                bias_mma(dt + 0, wB16 + XB_BT_XX / 16, 16);
+                bias_mma(dt + 32, wB16 + XB_BT_Y / 16, 16);
+              } else if (ph == 3) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                  for (int j = 0; j < 3; ++j)
+                    tap_quad(dt + 0, a0, (i - 2) * P + (j - 2), wB16 + XB_H / 16 + 256 * (i * 3 + j), true, (i | j) != 0);
+                bias_mma(dt + 0, wB16 + XB_BT_H / 16, 32);
+              } else {
+                tap_quad(dt + 0, a0, 0, wB16 + XB_HEAD / 16, false, 0u);
+                bias_mma(dt + 0, wB16 + XB_BT_HEAD / 16, 16);
+              }
+              umma_commit(smem_u32(&bars[4 + p]));
+              __threadfence_block();
+              issued[p] = phase_count + 1u;
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else {
+    // =============================== epilogue pipelines ===============================
+    const uint32_t tm = tmem_base + (uint32_t)(pipe * 128) + ((uint32_t)((warp & 3) * 32) << 16);
+    uint8_t* act = act0 + (size_t)pipe * X_SLOTS * slot_bytes;
+    const int HW = a.H * a.W;
+    const int bar_id = 1 + pipe;
+    const int pos = a.p_first + ltid;
+    const int prow = pos / a.P - 2, pcol = pos % a.P - 2;
+    const int site = (pcol >= 0 && prow < a.H) ? prow * a.W + pcol : -1;
+    float hres[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) hres[i] = 0.f;
+
+    // v (fp32) -> (hi, lo) fp16 rows of this thread's position in tile pair `slot`
+    auto store_row = [&](int slot, const float* v) {
+      uint8_t* bh = act + (size_t)slot * slot_bytes + (size_t)pos * 16;
+      uint8_t* bl = bh + tile_bytes;
+#pragma unroll
+      for (int cg = 0; cg < 4; ++cg) {
+        uint4 qh, ql;
+        float f[8];
+        qh.x = pack_h2(v[8 * cg + 0], v[8 * cg + 1]);
+        qh.y = pack_h2(v[8 * cg + 2], v[8 * cg + 3]);
+        qh.z = pack_h2(v[8 * cg + 4], v[8 * cg + 5]);
+        qh.w = pack_h2(v[8 * cg + 6], v[8 * cg + 7]);
+        unpack_h8(qh, f);
+        ql.x = pack_h2(v[8 * cg + 0] - f[0], v[8 * cg + 1] - f[1]);
+        ql.y = pack_h2(v[8 * cg + 2] - f[2], v[8 * cg + 3] - f[3]);
+        ql.z = pack_h2(v[8 * cg + 4] - f[4], v[8 * cg + 5] - f[5]);
+        ql.w = pack_h2(v[8 * cg + 6] - f[6], v[8 * cg + 7] - f[7]);
+        *reinterpret_cast<uint4*>(bh + (size_t)cg * a.npos * 16) = qh;
+        *reinterpret_cast<uint4*>(bl + (size_t)cg * a.npos * 16) = ql;
+      }
+    };
+    auto zero_row = [&](int slot) {
+      uint8_t* bh = act + (size_t)slot * slot_bytes + (size_t)pos * 16;
+#pragma unroll
+      for (int cg = 0; cg < 4; ++cg) {
+        *reinterpret_cast<uint4*>(bh + (size_t)cg * a.npos * 16) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(bh + tile_bytes + (size_t)cg * a.npos * 16) = make_uint4(0, 0, 0, 0);
+      }
+    };
+    auto load_row = [&](int slot, float* v) {
+      const uint8_t* bh = act + (size_t)slot * slot_bytes + (size_t)pos * 16;
+#pragma unroll
+      for (int cg = 0; cg < 4; ++cg) {
+        float fh[8], fl[8];
+        unpack_h8(*reinterpret_cast<const uint4*>(bh + (size_t)cg * a.npos * 16), fh);
+        unpack_h8(*reinterpret_cast<const uint4*>(bh + tile_bytes + (size_t)cg * a.npos * 16), fl);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[8 * cg + i] = fh[i] + fl[i];
+      }
+    };
+    uint32_t mma_phase = 0;
+    long long step = 0;
+
+    for (long long it = 0; it < my_iters; ++it) {
+      const long long group = it * gridDim.x + blockIdx.x;
+      const long long cfg = group * X_NP + pipe;
+      const bool active = cfg < n_items;
+      long long src = cfg;
+      int flip_a = -1, flip_b = -1;
+      if (a.wk.items && active) {   // connected configuration = the item's sample with the item's sites flipped
+        const TcWorkItem wi = a.wk.items[cfg];
+        src = wi.sample;
+        flip_a = wi.site_a == 0xffffu ? -1 : (int)wi.site_a;
+        flip_b = wi.site_b == 0xffffu ? -1 : (int)wi.site_b;
+      }
+      float sig = (active && site >= 0) ? (float)a.sigma[src * HW + site] : 0.f;
+      if (site >= 0 && (site == flip_a || site == flip_b)) sig = -sig;
+      {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        v[0] = sig;
+        store_row(sdesc[0].in_v, v);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(rbar);
+
+      for (int b = 0; b < a.nb; ++b, ++step) {
+        const TcBlockDesc d = sdesc[b];
+        // ================= phase 1: 1x3 conv on h (cols 0..63) and 3x3 conv on v (cols 64..127)
+        mbar_wait(mbar, mma_phase);
+        mma_phase ^= 1;
+        tc_fence_after();
+        mbar_arrive(emptyA);   // chunk A is no longer read
+        {
+          float x[32], y[32];
+          tmem_ld32x2(tm + 0, x, y);
+          if (site >= 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] = fmaxf((x[i] + y[i]) * X_WINV, 0.f);
+            store_row(d.x1, x);
+          } else {
+            zero_row(d.x1);
+          }
+          tmem_ld32x2(tm + 64, x, y);
+          if (site >= 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] = (x[i] + y[i]) * X_WINV;
+            if (d.out_r >= 0) {
+              load_row(d.res_v, y);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) y[i] = fmaxf(y[i] + x[i], 0.f);
+              store_row(d.out_r, y);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.f);
+            store_row(d.out_a, x);
+          } else {
+            if (d.out_r >= 0) zero_row(d.out_r);
+            zero_row(d.out_a);
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(rbar);
+
+        // ================= phase 2: the two 1x1 convs -> concat (XX: cols 0..31, Y: cols 32..63; 16 large + 16 small each)
+        mbar_wait(mbar, mma_phase);
+        mma_phase ^= 1;
+        tc_fence_after();
+        {
+          float x[32], y[32];
+          tmem_ld32x2(tm + 0, x, y);
+          if (site >= 0) {
+            float c[32];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              c[i] = fmaxf((x[i] + x[16 + i]) * X_WINV, 0.f);
+              c[16 + i] = fmaxf((y[i] + y[16 + i]) * X_WINV, 0.f);
+            }
+            store_row(d.c, c);
+          } else {
+            zero_row(d.c);
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(rbar);
+
+        // ================= phase 3: 3x3 conv on the concat tensor (cols 0..63), residual, relu
+        mbar_wait(mbar, mma_phase);
+        mma_phase ^= 1;
+        tc_fence_after();
+        if (!d.last) mbar_arrive(emptyB);
+        {
+          float x[32], y[32];
+          tmem_ld32x2(tm + 0, x, y);
+          if (site >= 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] = (x[i] + y[i]) * X_WINV;
+            if (d.res_h >= 0) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) x[i] += hres[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.f);
+            store_row(d.out_h, x);
+            if (d.save_h) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) hres[i] = x[i];
+            }
+          } else {
+            zero_row(d.out_h);
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(rbar);
+
+        // ================= phase 4 (last block): head 1x1 conv (C -> 4) + normalisation + combine
+        if (d.last) {
+          mbar_wait(mbar, mma_phase);
+          mma_phase ^= 1;
+          tc_fence_after();
+          mbar_arrive(emptyB);
+          float sre = 0.f, sim = 0.f;
+          {
+            float v[32];
+            tmem_ld32(tm + 0, v);
+            if (site >= 0) {
+              const float re0 = (v[0] + v[16]) * X_WINV, re1 = (v[1] + v[17]) * X_WINV;
+              const float im0 = (v[2] + v[18]) * X_WINV, im1 = (v[3] + v[19]) * X_WINV;
+              const float x = 2.f * re0, y = 2.f * re1;
+              const float m = fmaxf(x, y);
+              const float half_lse = 0.5f * (m + logf(expf(x - m) + expf(y - m)));
+              const bool up = sig > 0.f;
+              sre = (up ? re0 : re1) - half_lse;
+              sim = up ? im0 : im1;
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            sre += __shfl_xor_sync(0xffffffffu, sre, o);
+            sim += __shfl_xor_sync(0xffffffffu, sim, o);
+          }
+          if (lane == 0) {
+            red[(pipe * 4 + (warp & 3)) * 2 + 0] = sre;
+            red[(pipe * 4 + (warp & 3)) * 2 + 1] = sim;
+          }
+          tc_fence_before();
+          named_sync(bar_id, 128);
+          if (ltid == 0 && active) {
+            float r0 = 0.f, r1 = 0.f;
+            for (int w = 0; w < 4; ++w) {
+              r0 += red[(pipe * 4 + w) * 2 + 0];
+              r1 += red[(pipe * 4 + w) * 2 + 1];
+            }
+            if (a.wk.eloc) {   // fused local-energy term: ratio in complex64, accumulation in complex128
+              const float dr = r0 - a.wk.logpsi0[2 * src], di = r1 - a.wk.logpsi0[2 * src + 1];
+              const float mag = expf(dr), m = a.wk.mel[cfg];
+              float sn, cs;
+              sincosf(di, &sn, &cs);
+              atomicAdd(a.wk.eloc + 2 * src, (double)m * (double)(mag * cs));
+              atomicAdd(a.wk.eloc + 2 * src + 1, (double)m * (double)(mag * sn));
+            } else {
+              a.out[2 * cfg + 0] = r0;
+              a.out[2 * cfg + 1] = r1;
+            }
+          }
+          named_sync(bar_id, 128);   // `red` is reused by the next configuration
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+struct TcxGeometry { int P, p_first, npos; size_t smem_bytes, tail; bool ok; };
+
+static TcxGeometry tcx_geometry(const fk_net* net) {
+  TcxGeometry g;
+  g.P = net->W + 2;
+  g.p_first = 2 * g.P + 2;
+  const int p_last = (net->H + 1) * g.P + net->W + 1;
+  const int T = (p_last - g.p_first + 1 + 127) / 128;
+  g.npos = ((g.p_first + 128 + 2) + 7) / 8 * 8;
+  g.tail = (384 + sizeof(TcBlockDesc) * (size_t)(2 * net->depth - 2) + 64 + 127) / 128 * 128;
+  g.smem_bytes = (size_t)XIMG_BYTES + (size_t)X_NP * X_SLOTS * 128 * g.npos + g.tail + 4096;
+  g.ok = T == 1 && g.smem_bytes <= 227 * 1024;
+  return g;
+}
+
+int tcx_supported(const fk_net* net) {
+  if (net->kind != FK_NET_CONV2D || net->C != 32 || net->k != 3) return 0;
+  return tcx_geometry(net).ok ? 1 : 0;
+}
+
+static size_t x256(size_t x) { return (x + 255) / 256 * 256; }
+static size_t tcx_desc_offset(int nb) { return x256((size_t)nb * XIMG_BYTES); }
+static size_t tcx_pack_offset(int nb) { return tcx_desc_offset(nb) + x256(sizeof(TcBlockDesc) * nb); }
+
+// allocation + the wiring tables (called once, from fk_net_create)
+int tcx_prepare(fk_net* net) {
+  if (!tcx_supported(net)) return 0;
+  const int nb = 2 * net->depth - 2;
+  FK_CHECK_CUDA(cudaMalloc(&net->d_tc_exact, tcx_pack_offset(nb) + sizeof(XPackDesc) * nb));
+  // slot wiring with the horizontal residual in registers (3 slots): in-place rules of fk_tc.cu::tc_pack_weights
+  std::vector<TcBlockDesc> desc(nb);
+  int rc[X_SLOTS] = {0, 0, 0};
+  auto get = [&]() {
+    for (int i = 0; i < X_SLOTS; ++i)
+      if (rc[i] == 0) { rc[i] = 1; return i; }
+    return -1;
+  };
+  const int in = get();
+  rc[in]++;
+  int v = in, h = in, v_pair = -1;
+  for (int b = 0; b < nb; ++b) {
+    const bool last = (b == nb - 1);
+    const bool res2 = (b >= 2 && b % 2 == 0 && !last);
+    if (b % 2 == 1 && !last) { v_pair = v; rc[v]++; }
+    TcBlockDesc d;
+    d.in_v = (int8_t)v; d.in_h = (int8_t)h; d.last = last ? 1 : 0; d.pad1 = 0;
+    d.save_h = (int8_t)(((b + 1) % 2 == 1 && b + 1 != nb - 1) ? 1 : 0);
+    int x1;
+    if (rc[h] == 1) { x1 = h; } else { x1 = get(); rc[h]--; }
+    int a1;
+    if (rc[v] == 1) { a1 = v; } else { a1 = get(); rc[v]--; }
+    FK_REQUIRE(x1 >= 0 && a1 >= 0, "tcx_prepare: out of shared-memory activation slots");
+    d.out_r = d.res_v = (int8_t)(res2 ? v_pair : -1);
+    const int c = x1;
+    int v_next = a1;
+    d.res_h = -1;
+    if (res2) { rc[a1]--; v_next = v_pair; d.res_h = 0; }
+    d.x1 = (int8_t)x1; d.out_a = (int8_t)a1; d.c = (int8_t)c; d.out_h = (int8_t)c;
+    desc[b] = d;
+    v = v_next; h = c;
+  }
+  FK_CHECK_CUDA(cudaMemcpy((uint8_t*)net->d_tc_exact + tcx_desc_offset(nb), desc.data(), sizeof(TcBlockDesc) * nb, cudaMemcpyHostToDevice));
+  std::vector<XPackDesc> pd(nb);
+  for (int b = 0; b < nb; ++b) {
+    const ConvOp* o = &net->ops[5 * b];   // program order per block: V, X, XX, Y, H
+    for (int r = 0; r < 5; ++r) { pd[b].w[r] = o[r].w_off; pd[b].b[r] = o[r].b_off; }
+    pd[b].w_head = net->ops.back().w_off; pd[b].b_head = net->ops.back().b_off;
+    pd[b].cin = b == 0 ? 1 : 32;
+  }
+  FK_CHECK_CUDA(cudaMemcpy((uint8_t*)net->d_tc_exact + tcx_pack_offset(nb), pd.data(), sizeof(XPackDesc) * nb, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int tcx_pack_weights(fk_net* net, cudaStream_t s) {
+  if (!net->d_tc_exact) return 0;
+  const int nb = 2 * net->depth - 2;
+  const XPackDesc* d_pd = reinterpret_cast<const XPackDesc*>((uint8_t*)net->d_tc_exact + tcx_pack_offset(nb));
+  tcx_pack_kernel<<<nb, 256, 0, s>>>(net->d_weff, d_pd, (uint8_t*)net->d_tc_exact);
+  FK_CHECK_LAUNCH();
+  return 0;
+}
+
+int tcx_log_psi(fk_net* net, const int8_t* sigma, int64_t n, float* log_psi_out, cudaStream_t s, const TcWork* work) {
+  FK_REQUIRE(net->params_set && net->d_tc_exact, "tc-exact engine: not available for this machine, or parameters never set");
+  if (n == 0) return 0;
+  const TcxGeometry g = tcx_geometry(net);
+  FK_REQUIRE(g.ok, "tc-exact engine: lattice %dx%d does not fit one 128-row tile", net->H, net->W);
+  const int nb = 2 * net->depth - 2;
+  TcxArgs a;
+  a.images = (const uint8_t*)net->d_tc_exact;
+  a.desc = reinterpret_cast<const TcBlockDesc*>((const uint8_t*)net->d_tc_exact + tcx_desc_offset(nb));
+  a.sigma = sigma; a.out = log_psi_out; a.n = n;
+  a.H = net->H; a.W = net->W; a.P = g.P; a.nb = nb; a.npos = g.npos; a.p_first = g.p_first;
+  a.cst_off = (int)(g.smem_bytes - 4096);
+  if (work) a.wk = *work; else a.wk = TcWork{nullptr, nullptr, nullptr, nullptr, nullptr};
+  int dev = 0, sms = 148;
+  FK_CHECK_CUDA(cudaGetDevice(&dev));
+  FK_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long groups = (n + X_NP - 1) / X_NP;
+  const unsigned grid = (unsigned)std::min<long long>(groups, sms);
+  FK_CHECK_CUDA(cudaFuncSetAttribute(tcx_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+  tcx_forward_kernel<<<grid, X_NP * 128 + 32 + X_ISSUERS * 32, g.smem_bytes, s>>>(a);
+  FK_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace fk

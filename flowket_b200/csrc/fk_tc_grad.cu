@@ -698,11 +698,12 @@ static size_t bwd_units_offset(int nb) { return ((size_t)nb * IMGB_BYTES + 255) 
 static size_t bwd_boff_offset(int nb) { return bwd_units_offset(nb) + ((size_t)2 * nb * sizeof(DwUnit) + 255) / 256 * 256; }
 static size_t bwd_pack_offset(int nb) { return bwd_boff_offset(nb) + ((size_t)nb * 5 * sizeof(long long) + 255) / 256 * 256; }
 
-int tc_grad_pack_weights(fk_net* net, cudaStream_t s) {
+int tc_grad_prepare(fk_net* net) {
+  if (!tc_grad_supported(net)) return 0;
   TcPublicGeometry g;
   tc_public_geometry(net, &g);
   const int nb = g.nb;
-  if (!net->d_tc_bwd) {
+  {
     FK_CHECK_CUDA(cudaMalloc(&net->d_tc_bwd, bwd_pack_offset(nb) + sizeof(BwdPackDesc) * nb));
     std::vector<BwdPackDesc> pd(nb);
     std::vector<long long> boff(nb * 5);
@@ -737,6 +738,14 @@ int tc_grad_pack_weights(fk_net* net, cudaStream_t s) {
     FK_CHECK_CUDA(cudaMemcpy(base + bwd_boff_offset(nb), boff.data(), sizeof(long long) * boff.size(), cudaMemcpyHostToDevice));
     FK_CHECK_CUDA(cudaMemcpy(base + bwd_pack_offset(nb), pd.data(), sizeof(BwdPackDesc) * nb, cudaMemcpyHostToDevice));
   }
+  return 0;
+}
+
+int tc_grad_pack_weights(fk_net* net, cudaStream_t s) {
+  TcPublicGeometry g;
+  tc_public_geometry(net, &g);
+  const int nb = g.nb;
+  FK_REQUIRE(net->d_tc_bwd, "tc_grad_pack_weights: the machine was created without the tensor-core gradient tables");
   tc_pack_bwd_kernel<<<nb, 256, 0, s>>>(net->d_weff, reinterpret_cast<const BwdPackDesc*>((uint8_t*)net->d_tc_bwd + bwd_pack_offset(nb)),
                                        (uint8_t*)net->d_tc_bwd);
   FK_CHECK_LAUNCH();

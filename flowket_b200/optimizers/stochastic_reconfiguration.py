@@ -378,7 +378,7 @@ class StochasticReconfiguration(_SRBase):
     def _jacobian_engine(self, net):
         """tensor-core Jacobians when the model asks for the tensor-core engine and the machine is supported"""
         from .. import _lib
-        if getattr(self.model, 'engine', _lib.FK_ENGINE_FP32) == _lib.FK_ENGINE_TC and \
+        if getattr(self.model, 'engine', _lib.FK_ENGINE_FP32) in (_lib.FK_ENGINE_TC, _lib.FK_ENGINE_TC_EXACT) and \
                 net.lib.fk_grad_per_sample_tc_workspace_bytes(net.handle, 1) >= 0:
             return _lib.FK_ENGINE_TC
         return _lib.FK_ENGINE_FP32

@@ -53,6 +53,8 @@ typedef struct fk_net fk_net_t; /* opaque machine handle */
 /* precision / engine selector for the wave-function evaluations of fk_local_energy and fk_log_psi */
 #define FK_ENGINE_FP32 0 /* CUDA-core fp32: the 1e-5 parity contract                                   */
 #define FK_ENGINE_TC 1   /* tcgen05 fp16-operand / fp32-accumulate tensor-core fused network (ConvNetAutoregressive2D, C = 32)  */
+#define FK_ENGINE_TC_EXACT 2 /* tcgen05 at the contract accuracy: operands split into fp16 hi + lo (22 bits), three products in
+                                two MMAs per k-step, fp32 everywhere else; lattices up to one 128-row tile (10 x 10)       */
 
 typedef struct {
   int32_t site_a;    /* flattened (C-order) site index                       */
@@ -185,6 +187,32 @@ int64_t fk_sr_gram_workspace_bytes(int64_t rows, int64_t cols, int transpose_a);
 int64_t fk_sr_gram_tc_workspace_bytes(int64_t rows, int64_t cols, int transpose_a, int precise);
 int fk_sr_gram_tc(const float* A, int64_t rows, int64_t cols, int transpose_a, int precise, float* G, void* ws,
                   int64_t ws_bytes, void* stream);
+
+/* ---- sample-space stochastic reconfiguration of machines whose P x P matrix does not fit (P >> 2B): the push-through form
+ * delta = X^T (C X X^T C / B + lambda I)^-1 C e' / B of optimizer.py:55-66,100-108, X = [Re O ; Im O] (R = 2B rows, bf16),
+ * C = per-half centring (the "O - mean(O)" of optimizer.py:79-81 applied inside the Gram matrix).
+ * fk_sr_gram_xxt: G[R, ldg] (fp32) = scale * X X^T; hand-written tcgen05 GEMM (cta_group::2, 256 x 256 tiles per CTA
+ *   pair, TMA 128-byte-swizzled operands, upper block triangle computed and mirrored).  X: bf16 [R, ld], ld % 8 == 0.
+ * fk_sr_centre_shift: S[R, R] (fp64) = C G C / B + lambda I.
+ * fk_sr_xt_w: out[K] (fp32) = X^T w  (w: [R] fp32). */
+int64_t fk_sr_gram_xxt_workspace_bytes(int64_t R);
+int fk_sr_gram_xxt(const void* X, int64_t R, int64_t K, int64_t ld, float scale, float* G, int64_t ldg, void* ws,
+                   int64_t ws_bytes, void* stream);
+int64_t fk_sr_centre_shift_workspace_bytes(int64_t R);
+int fk_sr_centre_shift(const float* G, int64_t R, int64_t ldg, double lambda, double* S, void* ws, int64_t ws_bytes,
+                       void* stream);
+int fk_sr_xt_w(const void* X, int64_t R, int64_t K, int64_t ld, const float* w, float* out, void* stream);
+
+/* fk_sr_solve: replaces tf.cholesky + tf.cholesky_solve (optimizer.py:63-66).  S (fp64 [n, n], symmetric positive
+ * definite) is overwritten by its Cholesky factor, rhs [n] by the solution; info_out (device int, optional) = potrf status.
+ * The factorisation is cuSOLVER's (resolved with dlopen when the solver handle is created; the handle owns the library
+ * context, every device buffer comes from the caller). */
+typedef struct fk_sr_solver fk_sr_solver_t;
+int fk_sr_solver_create(fk_sr_solver_t** out);
+int fk_sr_solver_destroy(fk_sr_solver_t* solver);
+int64_t fk_sr_solve_workspace_bytes(fk_sr_solver_t* solver, int64_t n);
+int fk_sr_solve(fk_sr_solver_t* solver, double* S, double* rhs, int64_t n, int* info_out, void* ws, int64_t ws_bytes,
+                void* stream);
 
 #ifdef __cplusplus
 }
