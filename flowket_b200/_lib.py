@@ -65,12 +65,16 @@ SIGNATURES = {
     'fk_sr_gram': (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     'fk_sr_gram_tc_workspace_bytes': (c_int64, [c_int64, c_int64, c_int, c_int]),
     'fk_sr_gram_tc': (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
+    'fk_jacobian_rows_tc_workspace_bytes': (c_int64, [c_void_p, c_int64]),
+    'fk_jacobian_rows_tc': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64,
+                                    c_void_p]),
     'fk_sr_gram_xxt_workspace_bytes': (c_int64, [c_int64]),
-    'fk_sr_gram_xxt': (c_int, [c_void_p, c_int64, c_int64, c_int64, ctypes.c_float, c_void_p, c_int64, c_void_p, c_int64,
-                               c_void_p]),
+    'fk_sr_gram_xxt': (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, ctypes.c_float, c_void_p, c_int64,
+                               c_void_p, c_int64, c_void_p]),
     'fk_sr_centre_shift_workspace_bytes': (c_int64, [c_int64]),
-    'fk_sr_centre_shift': (c_int, [c_void_p, c_int64, c_int64, ctypes.c_double, c_void_p, c_void_p, c_int64, c_void_p]),
-    'fk_sr_xt_w': (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    'fk_sr_centre_shift': (c_int, [c_void_p, c_int64, c_int64, c_int64, ctypes.c_double, c_void_p, c_void_p, c_int64,
+                                   c_void_p]),
+    'fk_sr_xt_w': (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     'fk_sr_solver_create': (c_int, [ctypes.POINTER(c_void_p)]),
     'fk_sr_solver_destroy': (c_int, [c_void_p]),
     'fk_sr_solve_workspace_bytes': (c_int64, [c_void_p, c_int64]),

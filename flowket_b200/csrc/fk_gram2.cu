@@ -1,6 +1,12 @@
 // Sample-space stochastic-reconfiguration contraction on the headline machine: G = X X^T with X = [Re O ; Im O]
-// (R = 2B rows, K = P parameters, bf16, row-major) -- optimizers/stochastic_reconfiguration/optimizer.py:55-66 in the
-// push-through form.  One plain TN GEMM, hand-written for sm_100a:
+// (R = 2B rows, K = P parameters, bf16) -- optimizers/stochastic_reconfiguration/optimizer.py:55-66 in the
+// push-through form.  One plain TN GEMM, hand-written for sm_100a.
+//
+// Layout of X: PANEL-MAJOR, X[p / 64][r][p % 64] with `rld` rows per panel: the 64 parameters (128 bytes) of one k-block
+// are contiguous per row and all rows of a k-block are contiguous (2 MB at R = 16384).  Measured on a B200 with the
+// row-major layout (row stride 1.7 MB): every 128-row TMA box touched 128 different pages and the same kernel ran at
+// 636 TFLOP/s, L2 reuse gone; with rows 213 KB apart it ran at 1.3 PFLOP/s (profiles/r02_gram2_*.txt).  In the panel-major
+// layout a TMA box is one contiguous 16 KB block.  The Jacobian kernel (fk_tc_grad.cu) writes this layout directly.
 //
 //   * CTA pairs (cluster of 2, tcgen05 cta_group::2): one 256 x 256 output tile per pair, UMMA M = 256, N = 256, K = 16;
 //     each CTA stages its own 128 rows of the A panel and 128 rows of the B panel (the pair shares both through the
@@ -17,6 +23,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "fk_common.cuh"
 #include "fk_tc_common.cuh"
@@ -35,8 +42,10 @@ constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + 1024 /* alignment */ + 256 
 struct Gram2Args {
   float* G;
   long long ldg, R;
+  int block_rows;     // rows per row block (the rows of one rank in the sharded step); R when there is one block
   int nkb, ntiles;
   const int* tiles;   // (i << 16) | j in units of 256 rows, j >= i
+  unsigned int* wave_counter;   // arrivals of the CTAs at the wave boundaries (zeroed by gram2_tiles_kernel)
   float scale;
 };
 
@@ -56,10 +65,12 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2,
+                                                int c3) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          dst),
+      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void umma_bf16_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -80,14 +91,16 @@ __device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
-__global__ void gram2_tiles_kernel(int nt, int* __restrict__ tiles) {
+// Tile order: bands of `sb` tile rows, swept column by column.  The CTA pairs take consecutive entries (pair p: entries
+// p, p + npairs, ...), so the 74 tiles in flight are ~9 columns of one band: 8 A panels + 9 B panels serve 74 tiles.
+__global__ void gram2_tiles_kernel(int nt, int sb, int* __restrict__ tiles, unsigned int* __restrict__ wave_counter) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  *wave_counter = 0u;
   int n = 0;
-  for (int bi = 0; bi < nt; bi += 8)
-    for (int bj = bi; bj < nt; bj += 8)
-      for (int i = bi; i < bi + 8 && i < nt; ++i)
-        for (int j = bj; j < bj + 8 && j < nt; ++j)
-          if (j >= i) tiles[n++] = (i << 16) | j;
+  for (int bi = 0; bi < nt; bi += sb)
+    for (int j = bi; j < nt; ++j)
+      for (int i = bi; i < bi + sb && i < nt; ++i)
+        if (j >= i) tiles[n++] = (i << 16) | j;
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
@@ -123,15 +136,26 @@ gram2_kernel(const __grid_constant__ CUtensorMap tmap, Gram2Args a) {
     if (lane == 0) {
       const uint32_t full_leader = mapa_rank(full0, 0);
       uint32_t stage = 0, phase = 0;
-      for (int t = pair; t < a.ntiles; t += npairs) {
+      unsigned int wave = 0;
+      for (int t = pair; t < a.ntiles; t += npairs, ++wave) {
+        // Wave alignment (a performance hint, not a correctness requirement -- hence the bounded wait): the tiles of one
+        // wave share operand panels, and they only find each other's fetches in L2 if they stream through K together
+        // (measured: without it 70 % of the operand bytes came from DRAM and the power cap held the SMs at 795 MHz).
+        if (wave > 0) {
+          atomicAdd(a.wave_counter, 1u);
+          const unsigned int target = wave * gridDim.x;
+          const long long t0 = clock64();
+          while (*reinterpret_cast<volatile unsigned int*>(a.wave_counter) < target && clock64() - t0 < 400000LL) __nanosleep(200);
+        }
         const int tile = a.tiles[t];
         const int rowA = (tile >> 16) * 256 + (int)rank * 128, rowB = (tile & 0xffff) * 256 + (int)rank * 128;
+        const int qA = rowA / a.block_rows, rA = rowA % a.block_rows, qB = rowB / a.block_rows, rB = rowB % a.block_rows;
         for (int kb = 0; kb < a.nkb; ++kb) {
           mbar_wait(empty0 + 8 * stage, phase ^ 1u);
           if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * G2_STAGE_BYTES);
           const uint32_t sa = smem0 + stage * G2_STAGE_BYTES;
-          tma_load_2d_2sm(sa, &tmap, full_leader + 8 * stage, kb * G2_BK, rowA);
-          tma_load_2d_2sm(sa + G2_TILE_BYTES, &tmap, full_leader + 8 * stage, kb * G2_BK, rowB);
+          tma_load_4d_2sm(sa, &tmap, full_leader + 8 * stage, 0, rA, kb, qA);
+          tma_load_4d_2sm(sa + G2_TILE_BYTES, &tmap, full_leader + 8 * stage, 0, rB, kb, qB);
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -230,33 +254,41 @@ gram2_kernel(const __grid_constant__ CUtensorMap tmap, Gram2Args a) {
 // ---- the rest of the sample-space system (HBM-bound passes over the 2B x 2B matrix / the 2B x P rows) ---------------
 // centring inside the Gram: with C = blockdiag(I - 11^T/B, I - 11^T/B), (C X)(C X)^T = C (X X^T) C.
 // Pass 1: column means of each B-row half (the matrix is symmetric, so these are also the row means of the halves).
-__global__ void gram_colmean_kernel(const float* __restrict__ G, long long R, long long ldg, long long B, float* __restrict__ cm) {
-  // cm[h * R + j] = mean_{r in half h} G[r][j];  grid (R / 256, 2 * splits), block 256
+// Rows come in blocks of `br` rows (one block per rank in the sharded step): the first half of a block holds the Re rows,
+// the second half the Im rows; half(r) = (r % br) >= br / 2.  B = R / 2 rows per half in total.
+__global__ void gram_colmean_kernel(const float* __restrict__ G, long long R, long long ldg, long long br, double* __restrict__ cm) {
+  // cm[h * R + j] = mean_{r in half h} G[r][j];  grid (R / 256, splits), block 256
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int h = blockIdx.y & 1, split = blockIdx.y >> 1, nsplit = gridDim.y >> 1;
   if (j >= R) return;
-  const long long r0 = h * B + B * split / nsplit, r1 = h * B + B * (split + 1) / nsplit;
-  float s = 0.f;
-  for (long long r = r0; r < r1; ++r) s += G[r * ldg + j];
-  atomicAdd(cm + h * R + j, s / (float)B);
+  const long long r0 = R * blockIdx.y / gridDim.y, r1 = R * (blockIdx.y + 1) / gridDim.y;
+  double s0 = 0.0, s1 = 0.0;
+  for (long long r = r0; r < r1; ++r) {
+    const double v = (double)G[r * ldg + j];
+    if ((r % br) * 2 >= br) s1 += v; else s0 += v;
+  }
+  atomicAdd(cm + j, s0 / (double)(R / 2));
+  atomicAdd(cm + R + j, s1 / (double)(R / 2));
 }
 // Pass 2: S = C G C / B + lambda I in fp64 (the factorisation runs in fp64), block means m[hr][hc] from cm.
-__global__ void gram_centre_shift_kernel(const float* __restrict__ G, long long R, long long ldg, long long B,
-                                         const float* __restrict__ cm, const double* __restrict__ blockmean, double inv_b,
+__global__ void gram_centre_shift_kernel(const float* __restrict__ G, long long R, long long ldg, long long br,
+                                         const double* __restrict__ cm, const double* __restrict__ blockmean, double inv_b,
                                          double lambda, double* __restrict__ S) {
   const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long i = blockIdx.y;
   if (j >= R) return;
-  const int hi = i >= B, hj = j >= B;
+  const int hi = (i % br) * 2 >= br, hj = (j % br) * 2 >= br;
   // (C G C)[i][j] = G[i][j] - mean_{r in half(i)} G[r][j] - mean_{c in half(j)} G[i][c] + mean over the block
-  const double v = (double)G[i * ldg + j] - (double)cm[hi * R + j] - (double)cm[hj * R + i] + blockmean[hi * 2 + hj];
+  const double v = (double)G[i * ldg + j] - (cm[hi * R + j] + cm[hj * R + i]) + blockmean[hi * 2 + hj];
   S[i * R + j] = v * inv_b + (i == j ? lambda : 0.0);
 }
-__global__ void gram_blockmean_kernel(const float* __restrict__ cm, long long R, long long B, double* __restrict__ blockmean) {
-  // blockmean[hr * 2 + hc] = mean_{j in half hc} cm[hr][j]; one block of 256 threads per entry
-  const int hr = blockIdx.x >> 1, hc = blockIdx.x & 1;
+__global__ void gram_blockmean_kernel(const double* __restrict__ cm, long long R, long long br, double* __restrict__ blockmean) {
+  // blockmean[hr * 2 + hc] = mean_{j in half hc} cm[hr][j]; one block of 256 threads per entry (the two off-diagonal
+  // entries are equal by symmetry: both are computed from the same half so that S comes out exactly symmetric)
+  int hr = blockIdx.x >> 1, hc = blockIdx.x & 1;
+  if (hr == 1 && hc == 0) { hr = 0; hc = 1; }
   double s = 0.0;
-  for (long long j = hc * B + threadIdx.x; j < (hc + 1) * B; j += blockDim.x) s += (double)cm[hr * R + j];
+  for (long long j = threadIdx.x; j < R; j += blockDim.x)
+    if (((j % br) * 2 >= br) == (hc == 1)) s += cm[hr * R + j];
   __shared__ double red[256];
   red[threadIdx.x] = s;
   __syncthreads();
@@ -264,30 +296,41 @@ __global__ void gram_blockmean_kernel(const float* __restrict__ cm, long long R,
     if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) blockmean[blockIdx.x] = red[0] / (double)B;
+  if (threadIdx.x == 0) blockmean[blockIdx.x] = red[0] / (double)(R / 2);
 }
 
-// delta[p] = sum_r w[r] X[r][p]  (X bf16 rows; read once, 16 bytes per thread per row)
-__global__ void xt_w_kernel(const __nv_bfloat16* __restrict__ X, long long R, long long K, long long ld,
-                            const float* __restrict__ w, float* __restrict__ out) {
-  const long long p8 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  if (p8 >= K) return;
-  const long long r0 = R * blockIdx.y / gridDim.y, r1 = R * (blockIdx.y + 1) / gridDim.y;
+// out[p] = sum_r w[r] X[r][p] over the panel-major rows: one CTA per 64-parameter panel (R x 128 contiguous bytes), a warp
+// reads 4 rows x 128 B per step, the 32 row lanes are summed through shared memory
+__global__ void xt_w_kernel(const __nv_bfloat16* __restrict__ X, long long br, long long nblocks, long long block_stride_el,
+                            long long K, long long rld, const float* __restrict__ w, float* __restrict__ out) {
+  const long long kb = blockIdx.x;
+  const int cg = threadIdx.x & 7, rl = threadIdx.x >> 3;   // 256 threads: 8 column groups x 32 row lanes
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long q = 0; q < nblocks; ++q) {
+    const __nv_bfloat16* base = X + q * block_stride_el + kb * rld * 64 + cg * 8;
+    const float* wq = w + q * br;
 #pragma unroll 4
-  for (long long r = r0; r < r1; ++r) {
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(X + r * ld + p8));
-    const float wr = __ldg(w + r);
-    const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+    for (long long r = rl; r < br; r += 32) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + r * 64));
+      const float wr = __ldg(wq + r);
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      acc[2 * i] += wr * __uint_as_float(u[i] << 16);
-      acc[2 * i + 1] += wr * __uint_as_float(u[i] & 0xffff0000u);
+      for (int i = 0; i < 4; ++i) {
+        acc[2 * i] += wr * __uint_as_float(u[i] << 16);
+        acc[2 * i + 1] += wr * __uint_as_float(u[i] & 0xffff0000u);
+      }
     }
   }
+  __shared__ float red[32][65];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if (p8 + i < K) atomicAdd(out + p8 + i, acc[i]);
+  for (int i = 0; i < 8; ++i) red[rl][cg * 8 + i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+    for (int l = 0; l < 32; ++l) s += red[l][threadIdx.x];
+    const long long p = kb * 64 + threadIdx.x;
+    if (p < K) out[p] = s;
+  }
 }
 
 }  // namespace fk
@@ -296,7 +339,8 @@ typedef CUresult (*fk_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint
                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int gram2_tensor_map(CUtensorMap* map, const void* X, int64_t R, int64_t K, int64_t ld) {
+static int gram2_tensor_map(CUtensorMap* map, const void* X, int64_t block_rows, int64_t nblocks, int64_t K, int64_t rld,
+                            int64_t block_stride) {
   static fk_encode_tiled_fn encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -305,11 +349,13 @@ static int gram2_tensor_map(CUtensorMap* map, const void* X, int64_t R, int64_t 
     FK_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "fk_sr_gram_xxt: cuTensorMapEncodeTiled is not available");
     encode = (fk_encode_tiled_fn)fn;
   }
-  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)R};
-  const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)fk::G2_BK, 128u};
-  const cuuint32_t estr[2] = {1u, 1u};
-  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(X), dims, strides, box, estr,
+  const cuuint64_t dims[4] = {(cuuint64_t)fk::G2_BK, (cuuint64_t)block_rows, (cuuint64_t)((K + fk::G2_BK - 1) / fk::G2_BK),
+                              (cuuint64_t)nblocks};
+  const cuuint64_t strides[3] = {(cuuint64_t)fk::G2_BK * 2, (cuuint64_t)rld * fk::G2_BK * 2,
+                                 (cuuint64_t)(nblocks > 1 ? block_stride : rld * fk::G2_BK * 2 * ((K + fk::G2_BK - 1) / fk::G2_BK)) };
+  const cuuint32_t box[4] = {(cuuint32_t)fk::G2_BK, 128u, 1u, 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(X), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FK_REQUIRE(r == CUDA_SUCCESS, "fk_sr_gram_xxt: cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -321,23 +367,31 @@ extern "C" int64_t fk_sr_gram_xxt_workspace_bytes(int64_t R) {
   return 256 + 4 * nt * (nt + 1) / 2;
 }
 
-extern "C" int fk_sr_gram_xxt(const void* X, int64_t R, int64_t K, int64_t ld, float scale, float* G, int64_t ldg, void* ws,
-                              int64_t ws_bytes, void* stream) {
+extern "C" int fk_sr_gram_xxt(const void* X, int64_t R, int64_t K, int64_t rld, int64_t nblocks, int64_t block_stride, float scale,
+                              float* G, int64_t ldg, void* ws, int64_t ws_bytes, void* stream) {
   FK_REQUIRE(X && G && ws, "fk_sr_gram_xxt: NULL argument");
   if (R == 0) return 0;
-  FK_REQUIRE(K >= 1 && ld >= K && ld % 8 == 0 && ((uintptr_t)X & 15) == 0, "fk_sr_gram_xxt: rows must be 16-byte aligned (ld %% 8 == 0)");
+  FK_REQUIRE(nblocks >= 1 && R % nblocks == 0, "fk_sr_gram_xxt: R must be a multiple of the number of row blocks");
+  const int64_t block_rows = R / nblocks;
+  FK_REQUIRE(K >= 1 && rld >= block_rows && ((uintptr_t)X & 127) == 0, "fk_sr_gram_xxt: X must be 128-byte aligned, rld >= rows per block");
+  FK_REQUIRE(nblocks == 1 || (block_rows % 128 == 0 && block_stride % 128 == 0 &&
+                              block_stride >= rld * 128 * ((K + 63) / 64)),
+             "fk_sr_gram_xxt: row blocks must hold a multiple of 128 rows and must not overlap");
   FK_REQUIRE(ldg >= R, "fk_sr_gram_xxt: ldg < R");
   FK_REQUIRE(R <= 256 * 32768, "fk_sr_gram_xxt: too many rows");
   FK_REQUIRE(ws_bytes >= fk_sr_gram_xxt_workspace_bytes(R), "fk_sr_gram_xxt: workspace too small");
   cudaStream_t s = (cudaStream_t)stream;
   CUtensorMap map;
-  if (gram2_tensor_map(&map, X, R, K, ld)) return 1;
+  if (gram2_tensor_map(&map, X, block_rows, nblocks, K, rld, block_stride)) return 1;
   const int nt = (int)((R + 255) / 256);
   int* tiles = reinterpret_cast<int*>((uint8_t*)ws + 256);
-  fk::gram2_tiles_kernel<<<1, 32, 0, s>>>(nt, tiles);
+  unsigned int* wave_counter = reinterpret_cast<unsigned int*>(ws);
+  int sb = 8;
+  if (const char* e = getenv("FK_GRAM2_SUPER")) sb = std::max(1, atoi(e));   // (tuning knob of tests/tools_gram2.py)
+  fk::gram2_tiles_kernel<<<1, 32, 0, s>>>(nt, sb, tiles, wave_counter);
   FK_CHECK_LAUNCH();
   fk::Gram2Args a;
-  a.G = G; a.ldg = ldg; a.R = R; a.nkb = (int)((K + fk::G2_BK - 1) / fk::G2_BK); a.ntiles = nt * (nt + 1) / 2; a.tiles = tiles;
+  a.G = G; a.ldg = ldg; a.R = R; a.block_rows = (int)block_rows; a.nkb = (int)((K + fk::G2_BK - 1) / fk::G2_BK); a.ntiles = nt * (nt + 1) / 2; a.tiles = tiles; a.wave_counter = wave_counter;
   a.scale = scale;
   int dev = 0, sms = 148;
   FK_CHECK_CUDA(cudaGetDevice(&dev));
@@ -349,39 +403,40 @@ extern "C" int fk_sr_gram_xxt(const void* X, int64_t R, int64_t K, int64_t ld, f
   return 0;
 }
 
-// S[R,R] (fp64) = C (G) C / B + lambda I with C the per-half centring projector; G fp32 [R, ldg], R = 2B.
-// ws: 2R floats + 4 doubles.
-extern "C" int64_t fk_sr_centre_shift_workspace_bytes(int64_t R) { return 8 * R + 64 + 256; }
-extern "C" int fk_sr_centre_shift(const float* G, int64_t R, int64_t ldg, double lambda, double* S, void* ws, int64_t ws_bytes,
-                                  void* stream) {
+// S[R,R] (fp64) = C (G) C / B + lambda I with C the per-half centring projector; G fp32 [R, ldg], R = 2B rows in `nblocks`
+// row blocks of [Re rows ; Im rows].
+// ws: 4 doubles + 2R doubles.
+extern "C" int64_t fk_sr_centre_shift_workspace_bytes(int64_t R) { return 16 * R + 64 + 256; }
+extern "C" int fk_sr_centre_shift(const float* G, int64_t R, int64_t ldg, int64_t nblocks, double lambda, double* S, void* ws,
+                                  int64_t ws_bytes, void* stream) {
   FK_REQUIRE(G && S && ws, "fk_sr_centre_shift: NULL argument");
-  FK_REQUIRE(R % 2 == 0 && R > 0, "fk_sr_centre_shift: R must be 2B");
+  FK_REQUIRE(R > 0 && nblocks >= 1 && R % (2 * nblocks) == 0, "fk_sr_centre_shift: R must be nblocks x 2 x (rows per half)");
+  const int64_t br = R / nblocks;
   FK_REQUIRE(ws_bytes >= fk_sr_centre_shift_workspace_bytes(R), "fk_sr_centre_shift: workspace too small");
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t B = R / 2;
   double* blockmean = reinterpret_cast<double*>(ws);
-  float* cm = reinterpret_cast<float*>((uint8_t*)ws + 64);
-  FK_CHECK_CUDA(cudaMemsetAsync(cm, 0, 8 * R, s));
+  double* cm = reinterpret_cast<double*>((uint8_t*)ws + 64);
+  FK_CHECK_CUDA(cudaMemsetAsync(cm, 0, 16 * R, s));
   const unsigned gx = (unsigned)((R + 255) / 256);
-  fk::gram_colmean_kernel<<<dim3(gx, 2 * 16), 256, 0, s>>>(G, R, ldg, B, cm);
+  fk::gram_colmean_kernel<<<dim3(gx, 32), 256, 0, s>>>(G, R, ldg, br, cm);
   FK_CHECK_LAUNCH();
-  fk::gram_blockmean_kernel<<<4, 256, 0, s>>>(cm, R, B, blockmean);
+  fk::gram_blockmean_kernel<<<4, 256, 0, s>>>(cm, R, br, blockmean);
   FK_CHECK_LAUNCH();
-  fk::gram_centre_shift_kernel<<<dim3(gx, (unsigned)R), 256, 0, s>>>(G, R, ldg, B, cm, blockmean, 1.0 / (double)B, lambda, S);
+  fk::gram_centre_shift_kernel<<<dim3(gx, (unsigned)R), 256, 0, s>>>(G, R, ldg, br, cm, blockmean, 1.0 / (double)B, lambda, S);
   FK_CHECK_LAUNCH();
   return 0;
 }
 
-// out[K] (fp32, zeroed here) = X^T w, X bf16 [R, ld]
-extern "C" int fk_sr_xt_w(const void* X, int64_t R, int64_t K, int64_t ld, const float* w, float* out, void* stream) {
+// out[K] (fp32) = X^T w, X bf16 panel-major [ceil(K / 64)][rld][64]
+extern "C" int fk_sr_xt_w(const void* X, int64_t R, int64_t K, int64_t rld, int64_t nblocks, int64_t block_stride, const float* w,
+                          float* out, void* stream) {
   FK_REQUIRE(X && w && out, "fk_sr_xt_w: NULL argument");
-  FK_REQUIRE(ld % 8 == 0 && ((uintptr_t)X & 15) == 0, "fk_sr_xt_w: rows must be 16-byte aligned");
+  FK_REQUIRE(nblocks >= 1 && R % nblocks == 0 && rld >= R / nblocks && ((uintptr_t)X & 15) == 0 && block_stride % 16 == 0,
+             "fk_sr_xt_w: X must be 16-byte aligned, rld >= rows per block");
   cudaStream_t s = (cudaStream_t)stream;
-  FK_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * K, s));
-  if (R == 0) return 0;
-  const unsigned gx = (unsigned)((K + 8 * 128 - 1) / (8 * 128));
-  const unsigned gy = (unsigned)std::max<int64_t>(1, std::min<int64_t>(R, std::max<int64_t>(1, 148 * 16 / gx)));
-  fk::xt_w_kernel<<<dim3(gx, gy), 128, 0, s>>>((const __nv_bfloat16*)X, R, K, ld, w, out);
+  if (K == 0) return 0;
+  fk::xt_w_kernel<<<(unsigned)((K + 63) / 64), 256, 0, s>>>((const __nv_bfloat16*)X, R / nblocks, nblocks, block_stride / 2, K, rld, w, out);
   FK_CHECK_LAUNCH();
   return 0;
 }

@@ -233,8 +233,11 @@ struct OpParam {
   int ntaps, cin, cout, raw_cin, raw_cout, mode;  // mode 0 plain, 1 WN linear g, 2 WN exp g, 3 complex
 };
 
+// wn_dir (optional, [num_eff], layout of weff): v / |v| of the weight-normalised kernels; wn_coef (optional, [op][2][64]):
+// a[co] = s / |v| and gs[co] = d w / d g over v_hat -- what the fused Jacobian flush of fk_tc_grad.cu needs per output channel
 __global__ void build_weff_kernel(const OpParam* __restrict__ table, const float* __restrict__ params,
-                                  float* __restrict__ weff, float* __restrict__ weffT) {
+                                  float* __restrict__ weff, float* __restrict__ weffT, float* __restrict__ wn_dir,
+                                  float* __restrict__ wn_coef) {
   const OpParam o = table[blockIdx.x];
   __shared__ float scale[128];
   const int K = o.ntaps * o.cin;
@@ -269,7 +272,14 @@ __global__ void build_weff_kernel(const OpParam* __restrict__ table, const float
         sq = fmaf(v, v, sq);
       }
       const float g = params[o.p_g + co];
-      sc = rsqrtf(fmaxf(sq, 1e-12f)) * (o.mode == 2 ? expf(g) : g);
+      const float inv = rsqrtf(fmaxf(sq, 1e-12f)), sg = (o.mode == 2 ? expf(g) : g);
+      sc = inv * sg;
+      if (wn_coef && co < 64) {
+        wn_coef[(blockIdx.x * 2 + 0) * 64 + co] = sc;
+        wn_coef[(blockIdx.x * 2 + 1) * 64 + co] = o.mode == 2 ? sg : 1.f;
+      }
+      if (wn_dir)
+        for (int kk = 0; kk < K; ++kk) wn_dir[o.w_off + (long long)kk * o.cout + co] = params[o.p_kernel + (long long)kk * o.cout + co] * inv;
     }
     scale[co] = sc;
     weff[o.b_off + co] = params[o.p_bias + co];
@@ -424,7 +434,7 @@ extern "C" int fk_net_create(fk_net_t** out, int kind, int H, int W, int depth, 
   fk_net* net = new fk_net();
   net->kind = kind; net->H = H; net->W = W; net->depth = depth; net->C = channels; net->k = kernel_size;
   net->max_dil = max_dilation; net->flags = flags; net->sites = H * W;
-  net->d_params = net->d_weff = net->d_weffT = nullptr; net->d_optable = nullptr;
+  net->d_params = net->d_weff = net->d_weffT = nullptr; net->d_optable = nullptr; net->d_wn_dir = net->d_wn_coef = nullptr;
   net->d_tc_weights = nullptr; net->tc_weight_bytes = 0; net->d_tc_bwd = nullptr; net->d_tc_exact = nullptr; net->params_set = false;
   if (kind == FK_NET_CONV2D) build_conv2d(net);
   else if (kind == FK_NET_CONV1D) build_conv1d(net);
@@ -445,6 +455,12 @@ extern "C" int fk_net_create(fk_net_t** out, int kind, int H, int W, int depth, 
   if (e == cudaSuccess) e = cudaMalloc(&net->d_optable, sizeof(OpParam) * table.size());
   if (e == cudaSuccess) e = cudaMemcpy(net->d_optable, table.data(), sizeof(OpParam) * table.size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemset(net->d_weffT, 0, sizeof(float) * net->num_eff);
+  if (e == cudaSuccess && kind == FK_NET_CONV2D) {   // tables of the fused per-sample Jacobian flush (fk_tc_grad.cu)
+    e = cudaMalloc(&net->d_wn_dir, sizeof(float) * net->num_eff);
+    if (e == cudaSuccess) e = cudaMalloc(&net->d_wn_coef, sizeof(float) * 128 * net->ops.size());
+    if (e == cudaSuccess) e = cudaMemset(net->d_wn_dir, 0, sizeof(float) * net->num_eff);
+    if (e == cudaSuccess) e = cudaMemset(net->d_wn_coef, 0, sizeof(float) * 128 * net->ops.size());
+  }
   if (e != cudaSuccess) {
     set_error("fk_net_create: CUDA allocation failed: %s", cudaGetErrorString(e));
     fk_net_destroy(net);
@@ -465,6 +481,7 @@ extern "C" int fk_net_destroy(fk_net_t* net) {
   cudaFree(net->d_tc_weights);
   cudaFree(net->d_tc_bwd);
   cudaFree(net->d_tc_exact);
+  cudaFree(net->d_wn_dir); cudaFree(net->d_wn_coef);
   delete net;
   return 0;
 }
@@ -480,7 +497,7 @@ extern "C" int fk_net_set_params(fk_net_t* net, const float* params, void* strea
   cudaStream_t s = (cudaStream_t)stream;
   FK_CHECK_CUDA(cudaMemcpyAsync(net->d_params, params, sizeof(float) * net->num_params, cudaMemcpyDeviceToDevice, s));
   build_weff_kernel<<<(unsigned)net->ops.size(), 128, 0, s>>>((const OpParam*)net->d_optable, net->d_params,
-                                                               net->d_weff, net->d_weffT);
+                                                               net->d_weff, net->d_weffT, net->d_wn_dir, net->d_wn_coef);
   FK_CHECK_LAUNCH();
   net->params_set = true;
   if (tc_supported(net)) {
@@ -674,6 +691,20 @@ extern "C" int fk_grad_per_sample_tc(fk_net_t* net, const int8_t* sigma, int64_t
   FK_REQUIRE(tc_grad_supported(net), "fk_grad_per_sample_tc: supports ConvNetAutoregressive2D, 32 channels, kernel 3, lattices that fit one M tile");
   if (B == 0) return 0;
   return tc_grad_per_sample(net, sigma, B, O_re, O_im, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int64_t fk_jacobian_rows_tc_workspace_bytes(const fk_net_t* net, int64_t B) {
+  if (!net || !tc_grad_supported(net)) return -1;
+  return tc_jacobian_rows_workspace_bytes(net, B);
+}
+
+extern "C" int fk_jacobian_rows_tc(fk_net_t* net, const int8_t* sigma, int64_t B, void* X, int64_t rld, int64_t row_re,
+                                   int64_t row_im, void* ws, int64_t ws_bytes, void* stream) {
+  FK_REQUIRE(net && sigma && X && ws, "fk_jacobian_rows_tc: NULL argument");
+  FK_REQUIRE(tc_grad_supported(net), "fk_jacobian_rows_tc: supports ConvNetAutoregressive2D, 32 channels, kernel 3, lattices that fit one M tile");
+  FK_REQUIRE(row_re >= 0 && row_re + B <= rld && (row_im < 0 || row_im + B <= rld), "fk_jacobian_rows_tc: rows out of range");
+  if (B == 0) return 0;
+  return tc_jacobian_rows(net, sigma, B, X, rld, row_re, row_im, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 // tensor-core engine of the weighted gradient (fk_tc_grad.cu)

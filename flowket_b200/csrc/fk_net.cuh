@@ -16,6 +16,8 @@ struct fk_net {
   float* d_weff;                      // effective weights/biases  [num_eff]   w: [t][ci][co]
   float* d_weffT;                     // transposed kernels        [num_eff]   w: [t][co][ci]
   void* d_optable;                    // device copy of the per-op parameter mapping
+  float* d_wn_dir;                    // v / |v| of the weight-normalised kernels (weff layout); 2-D machines
+  float* d_wn_coef;                   // [op][2][64]: s / |v| and d w / d g over v_hat per output channel
   int64_t train_floats_per_cfg;       // sum over virtual buffers of channels * sites
   // tensor-core engine (ConvNetAutoregressive2D only): bf16 UMMA-canonical weight image
   void* d_tc_weights;
@@ -80,6 +82,10 @@ int grad_transform_rows_launch(fk_net* net, const float* geff, float* graw, int6
 int64_t tc_grad_per_sample_workspace_bytes(const fk_net* net, int64_t B);
 int tc_grad_per_sample(fk_net* net, const int8_t* sigma, int64_t B, float* O_re, float* O_im, void* ws, int64_t ws_bytes,
                        cudaStream_t s);
+// Jacobian rows straight into the panel-major bf16 operand of the sample-space Gram (see fk_jacobian_rows_tc)
+int64_t tc_jacobian_rows_workspace_bytes(const fk_net* net, int64_t B);
+int tc_jacobian_rows(fk_net* net, const int8_t* sigma, int64_t B, void* X, int64_t rld, int64_t row_re, int64_t row_im,
+                     void* ws, int64_t ws_bytes, cudaStream_t s);
 
 // tensor-core sampler (fk_tc_sample.cu)
 int64_t tc_sample_workspace_bytes(const fk_net* net, int64_t B);

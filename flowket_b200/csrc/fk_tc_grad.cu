@@ -16,6 +16,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <cuda_bf16.h>
+
 #include "fk_net.cuh"
 #include "fk_tc_common.cuh"
 
@@ -354,6 +356,8 @@ struct DwConv {
   int col0;         // first TMEM column
   int cin;          // forward input channels (1 for the first block's V and X convs)
   long long w_off;  // offset of dW in the effective-weight gradient
+  long long p_kernel, p_g;   // offsets of the raw kernel / weight-norm g in the parameter vector (p_g < 0: no weight norm)
+  int op;                    // index of the convolution in the layer program (row of the weight-norm coefficient table)
 };
 struct DwUnit { int b, nconv; DwConv conv[3]; };
 
@@ -364,7 +368,111 @@ struct DwArgs2 {
   // plain stores, values multiplied by out_scale); row_stride == 0: one shared gradient, atomics
   long long row_stride;
   float out_scale;
+  // Jacobian rows for the sample-space SR Gram (xrows != nullptr, cfg_chunk == 1): configuration cfg writes row
+  // row_base + cfg of the panel-major bf16 matrix X[p / 64][rld rows][p % 64] in RAW parameters -- the weight-norm
+  // transform (fk_net.cu::grad_transform_kernel) is applied in the flush, nothing passes through fp32 rows
+  __nv_bfloat16* xrows;
+  long long rld, row_base;
+  const float* wn_dir;
+  const float* wn_coef;
 };
+
+// address (in elements) of parameter p of row r in the panel-major layout
+__device__ __forceinline__ long long xrow_index(long long rld, long long r, long long p) {
+  return ((p >> 6) * rld + r) * 64 + (p & 63);
+}
+
+// Fused flush of one convolution of a per-sample item: TMEM lane = ci, columns col0 + t*N + co.  Weight-normalised
+// kernels (w = v_hat * s, wrappers.py:123-134): d/dv = (s / |v|) (dw - (dw . v_hat) v_hat), d/dg = (dw . v_hat) * gs.
+template <int N>
+__device__ __forceinline__ void dw_flush_conv_rows(uint32_t tmem, const DwConv& c, const DwArgs2& a, long long row, int lane,
+                                                   float* stage) {
+  const bool wn = c.p_g >= 0;
+  const bool live = lane < c.cin;
+  float dot[N], coef[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) { dot[i] = 0.f; coef[i] = 1.f; }
+  if (wn) {
+    for (int t = 0; t < c.ntaps; ++t) {
+      float v[N];
+      if (N == 32) tmem_ld32(tmem + (uint32_t)(c.col0 + t * N), reinterpret_cast<float(&)[32]>(v));
+      else tmem_ld16(tmem + (uint32_t)(c.col0 + t * N), reinterpret_cast<float(&)[16]>(v));
+      if (live) {
+        const float4* vh = reinterpret_cast<const float4*>(a.wn_dir + c.w_off + ((long long)t * c.cin + lane) * N);
+#pragma unroll
+        for (int q = 0; q < N / 4; ++q) {
+          const float4 h = __ldg(vh + q);
+          dot[4 * q] = fmaf(v[4 * q], h.x, dot[4 * q]);
+          dot[4 * q + 1] = fmaf(v[4 * q + 1], h.y, dot[4 * q + 1]);
+          dot[4 * q + 2] = fmaf(v[4 * q + 2], h.z, dot[4 * q + 2]);
+          dot[4 * q + 3] = fmaf(v[4 * q + 3], h.w, dot[4 * q + 3]);
+        }
+      }
+    }
+    // sum over the input channels (lanes) through the transpose buffer: lane co adds column co
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q)
+      *reinterpret_cast<float4*>(stage + lane * 36 + 4 * q) = make_float4(dot[4 * q], dot[4 * q + 1], dot[4 * q + 2], dot[4 * q + 3]);
+    __syncwarp();
+    float mine = 0.f;
+    if (lane < N)
+      for (int l = 0; l < 32; ++l) mine += stage[l * 36 + lane];
+    mine *= a.out_scale;
+    __syncwarp();
+    if (lane < N) {
+      stage[lane] = mine;
+      const float gs = a.wn_coef[(c.op * 2 + 1) * 64 + lane];
+      a.xrows[xrow_index(a.rld, row, c.p_g + lane)] = __float2bfloat16_rn(mine * gs);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) {
+      const float4 d4 = *reinterpret_cast<const float4*>(stage + 4 * q);
+      const float4 c4 = __ldg(reinterpret_cast<const float4*>(a.wn_coef + (c.op * 2) * 64) + q);
+      dot[4 * q] = d4.x; dot[4 * q + 1] = d4.y; dot[4 * q + 2] = d4.z; dot[4 * q + 3] = d4.w;
+      coef[4 * q] = c4.x; coef[4 * q + 1] = c4.y; coef[4 * q + 2] = c4.z; coef[4 * q + 3] = c4.w;
+    }
+    __syncwarp();
+  }
+  for (int t = 0; t < c.ntaps; ++t) {
+    float v[N];
+    if (N == 32) tmem_ld32(tmem + (uint32_t)(c.col0 + t * N), reinterpret_cast<float(&)[32]>(v));
+    else tmem_ld16(tmem + (uint32_t)(c.col0 + t * N), reinterpret_cast<float(&)[16]>(v));
+    if (!live) continue;
+    if (wn) {
+      const float4* vh = reinterpret_cast<const float4*>(a.wn_dir + c.w_off + ((long long)t * c.cin + lane) * N);
+#pragma unroll
+      for (int q = 0; q < N / 4; ++q) {
+        const float4 h = __ldg(vh + q);
+        v[4 * q] = coef[4 * q] * (v[4 * q] * a.out_scale - h.x * dot[4 * q]);
+        v[4 * q + 1] = coef[4 * q + 1] * (v[4 * q + 1] * a.out_scale - h.y * dot[4 * q + 1]);
+        v[4 * q + 2] = coef[4 * q + 2] * (v[4 * q + 2] * a.out_scale - h.z * dot[4 * q + 2]);
+        v[4 * q + 3] = coef[4 * q + 3] * (v[4 * q + 3] * a.out_scale - h.w * dot[4 * q + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] *= a.out_scale;
+    }
+    const long long p0 = c.p_kernel + ((long long)t * c.cin + lane) * N;   // multiple of 16: a 16-element piece never
+#pragma unroll                                                              // straddles a 64-element panel
+    for (int h16 = 0; h16 < N / 16; ++h16) {
+      uint4 q0, q1;
+      const float* w = v + 16 * h16;
+      __nv_bfloat162 b;
+      b = __floats2bfloat162_rn(w[0], w[1]); q0.x = *reinterpret_cast<uint32_t*>(&b);
+      b = __floats2bfloat162_rn(w[2], w[3]); q0.y = *reinterpret_cast<uint32_t*>(&b);
+      b = __floats2bfloat162_rn(w[4], w[5]); q0.z = *reinterpret_cast<uint32_t*>(&b);
+      b = __floats2bfloat162_rn(w[6], w[7]); q0.w = *reinterpret_cast<uint32_t*>(&b);
+      b = __floats2bfloat162_rn(w[8], w[9]); q1.x = *reinterpret_cast<uint32_t*>(&b);
+      b = __floats2bfloat162_rn(w[10], w[11]); q1.y = *reinterpret_cast<uint32_t*>(&b);
+      b = __floats2bfloat162_rn(w[12], w[13]); q1.z = *reinterpret_cast<uint32_t*>(&b);
+      b = __floats2bfloat162_rn(w[14], w[15]); q1.w = *reinterpret_cast<uint32_t*>(&b);
+      uint4* dst = reinterpret_cast<uint4*>(a.xrows + xrow_index(a.rld, row, p0 + 16 * h16));
+      dst[0] = q0;
+      dst[1] = q1;
+    }
+  }
+}
 
 // Flush of one tap's (ci, co) accumulator tile: TMEM lane = ci, N columns = co.  Compile-time N keeps the row in registers
 // (a runtime trip count turns v[] into local memory -- measured: 1400 cycles per tap).
@@ -457,8 +565,10 @@ __global__ void __launch_bounds__(128, 1) tc_dw_kernel(DwArgs2 a) {
       uint32_t empty_phase = 0;   // bit i = parity of stage i
       long long prod_count = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        const DwUnit u = a.units[item % a.num_units];   // by value: the asm memory clobbers / global stores would force reloads
-        const long long c_beg = (long long)(item / a.num_units) * a.cfg_chunk;
+        // Jacobian rows: unit-major item order, so that the CTAs in flight write adjacent rows of the same panels
+        const int ui = a.xrows ? item / chunks : item % a.num_units, ch = a.xrows ? item % chunks : item / a.num_units;
+        const DwUnit u = a.units[ui];   // by value: the asm memory clobbers / global stores would force reloads
+        const long long c_beg = (long long)ch * a.cfg_chunk;
         const long long c_end = c_beg + a.cfg_chunk < a.n ? c_beg + a.cfg_chunk : a.n;
         for (long long cfg = c_beg; cfg < c_end; ++cfg) {
           const int st = (int)(prod_count % DW_STAGES);
@@ -481,8 +591,9 @@ __global__ void __launch_bounds__(128, 1) tc_dw_kernel(DwArgs2 a) {
     uint32_t full_phase = 0;
     long long cons_count = 0, item_count = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_count) {
-      const DwUnit u = a.units[item % a.num_units];   // by value: the asm memory clobbers / global stores would force reloads
-      const long long c_beg = (long long)(item / a.num_units) * a.cfg_chunk;
+      const int ui = a.xrows ? item / chunks : item % a.num_units, ch = a.xrows ? item % chunks : item / a.num_units;
+      const DwUnit u = a.units[ui];   // by value: the asm memory clobbers / global stores would force reloads
+      const long long c_beg = (long long)ch * a.cfg_chunk;
       const long long c_end = c_beg + a.cfg_chunk < a.n ? c_beg + a.cfg_chunk : a.n;
       DWTRACE(item_count, 0);
       mbar_wait(tfree, (uint32_t)((item_count & 1) ^ 1));   // previous item flushed (passes at once for the first item)
@@ -524,12 +635,18 @@ __global__ void __launch_bounds__(128, 1) tc_dw_kernel(DwArgs2 a) {
     uint32_t done_phase = 0;
     long long fitem = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++fitem) {
-      const DwUnit u = a.units[item % a.num_units];   // by value: the asm memory clobbers / global stores would force reloads
-      const long long c_beg = (long long)(item / a.num_units) * a.cfg_chunk;
+      const int ui = a.xrows ? item / chunks : item % a.num_units, ch = a.xrows ? item % chunks : item / a.num_units;
+      const DwUnit u = a.units[ui];   // by value: the asm memory clobbers / global stores would force reloads
+      const long long c_beg = (long long)ch * a.cfg_chunk;
       mbar_wait(done, done_phase); done_phase ^= 1;
       tc_fence_after();
       DWTRACE(fitem, 4);
       for (int k = 0; k < u.nconv; ++k) {
+        if (a.xrows) {
+          if (u.conv[k].n == 32) dw_flush_conv_rows<32>(tmem, u.conv[k], a, a.row_base + c_beg, lane, flush_stage);
+          else dw_flush_conv_rows<16>(tmem, u.conv[k], a, a.row_base + c_beg, lane, flush_stage);
+          continue;
+        }
         const int ntaps = u.conv[k].ntaps, n = u.conv[k].n, col0 = u.conv[k].col0, cin = u.conv[k].cin;
         const long long w_off = u.conv[k].w_off;
         for (int t = 0; t < ntaps; ++t) {
@@ -654,6 +771,68 @@ __global__ void tc_head_dw_ps_kernel(const uint8_t* __restrict__ dump, const flo
     __syncthreads();
   }
 }
+// the same two reductions writing bf16 Jacobian rows (panel-major layout, RAW parameter offsets; biases and the head are
+// never weight-normalised)
+__global__ void tc_db_rows_kernel(const uint8_t* __restrict__ dz, long long n, int nb, const long long* __restrict__ pb_off,
+                                  __nv_bfloat16* __restrict__ xrows, long long rld, long long row_base, float out_scale) {
+  const int b = blockIdx.x >> 2, tile = blockIdx.x & 3;
+  const int ch = threadIdx.x & 31, part = threadIdx.x >> 5;
+  __shared__ float red[8][32];
+  for (long long cfg = blockIdx.y; cfg < n; cfg += gridDim.y) {
+    const __half* t = reinterpret_cast<const __half*>(dz + (((size_t)cfg * nb + b) * 4 + tile) * DZ_TILE);
+    float acc = 0.f;
+    for (int r = part; r < 128; r += 8) acc += __half2float(t[((ch >> 3) * 128 + r) * 8 + (ch & 7)]);
+    red[part][ch] = acc;
+    __syncthreads();
+    if (part == 0) {
+      float s = 0.f;
+      for (int i = 0; i < 8; ++i) s += red[i][ch];
+      long long off;
+      if (tile == 0) off = pb_off[b * 5 + 4] + ch;
+      else if (tile == 1) off = ch < 16 ? pb_off[b * 5 + 2] + ch : pb_off[b * 5 + 3] + ch - 16;
+      else if (tile == 2) off = pb_off[b * 5 + 1] + ch;
+      else off = pb_off[b * 5 + 0] + ch;
+      xrows[xrow_index(rld, row_base + cfg, off)] = __float2bfloat16_rn(s * out_scale);
+    }
+    __syncthreads();
+  }
+}
+__global__ void tc_head_dw_rows_kernel(const uint8_t* __restrict__ dump, const float* __restrict__ glog, long long n, int nb, int npos,
+                                       int p_first, long long pw_off, long long pb_off, __nv_bfloat16* __restrict__ xrows,
+                                       long long rld, long long row_base, float out_scale, long long num_params) {
+  const int ci = threadIdx.x & 31, part = threadIdx.x >> 5;   // 256 threads
+  const size_t xt = (size_t)64 * npos, cfg_bytes = (size_t)(nb * NDUMP + 1) * xt;
+  __shared__ float red[8][32][4], bred[8][4];
+  for (long long cfg = blockIdx.x; cfg < n; cfg += gridDim.x) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, bacc[4] = {0.f, 0.f, 0.f, 0.f};
+    const __half* t = reinterpret_cast<const __half*>(dump + (size_t)cfg * cfg_bytes + (size_t)((nb - 1) * NDUMP + 4) * xt);
+    for (int r = part; r < 128; r += 8) {
+      const float4 g = *reinterpret_cast<const float4*>(glog + ((size_t)cfg * 128 + r) * 4);
+      const float h = __half2float(t[((size_t)(ci >> 3) * npos + p_first + r) * 8 + (ci & 7)]);
+      acc[0] += h * g.x; acc[1] += h * g.y; acc[2] += h * g.z; acc[3] += h * g.w;
+      if (ci == 0) { bacc[0] += g.x; bacc[1] += g.y; bacc[2] += g.z; bacc[3] += g.w; }
+    }
+    for (int k = 0; k < 4; ++k) { red[part][ci][k] = acc[k]; if (ci == 0) bred[part][k] = bacc[k]; }
+    __syncthreads();
+    if (part == 0) {
+      for (int k = 0; k < 4; ++k) {
+        float sacc = 0.f;
+        for (int i = 0; i < 8; ++i) sacc += red[i][ci][k];
+        xrows[xrow_index(rld, row_base + cfg, pw_off + ci * 4 + k)] = __float2bfloat16_rn(sacc * out_scale);
+      }
+      if (ci < 4) {
+        float sb = 0.f;
+        for (int i = 0; i < 8; ++i) sb += bred[i][ci];
+        xrows[xrow_index(rld, row_base + cfg, pb_off + ci)] = __float2bfloat16_rn(sb * out_scale);
+      }
+      // zero padding of the last panel (columns num_params .. next multiple of 64)
+      const long long pad0 = num_params + ci;
+      if (pad0 < ((num_params + 63) & ~63LL)) xrows[xrow_index(rld, row_base + cfg, pad0)] = __float2bfloat16_rn(0.f);
+      if (pad0 + 32 < ((num_params + 63) & ~63LL)) xrows[xrow_index(rld, row_base + cfg, pad0 + 32)] = __float2bfloat16_rn(0.f);
+    }
+    __syncthreads();
+  }
+}
 __global__ void tc_const_coef_kernel(long long n, float re, float im, float* __restrict__ coef) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -696,7 +875,8 @@ int tc_grad_supported(const fk_net* net) {
 
 static size_t bwd_units_offset(int nb) { return ((size_t)nb * IMGB_BYTES + 255) / 256 * 256; }
 static size_t bwd_boff_offset(int nb) { return bwd_units_offset(nb) + ((size_t)2 * nb * sizeof(DwUnit) + 255) / 256 * 256; }
-static size_t bwd_pack_offset(int nb) { return bwd_boff_offset(nb) + ((size_t)nb * 5 * sizeof(long long) + 255) / 256 * 256; }
+static size_t bwd_pboff_offset(int nb) { return bwd_boff_offset(nb) + ((size_t)nb * 5 * sizeof(long long) + 255) / 256 * 256; }
+static size_t bwd_pack_offset(int nb) { return bwd_pboff_offset(nb) + ((size_t)nb * 5 * sizeof(long long) + 255) / 256 * 256; }
 
 int tc_grad_prepare(fk_net* net) {
   if (!tc_grad_supported(net)) return 0;
@@ -706,12 +886,12 @@ int tc_grad_prepare(fk_net* net) {
   {
     FK_CHECK_CUDA(cudaMalloc(&net->d_tc_bwd, bwd_pack_offset(nb) + sizeof(BwdPackDesc) * nb));
     std::vector<BwdPackDesc> pd(nb);
-    std::vector<long long> boff(nb * 5);
+    std::vector<long long> boff(nb * 5), pboff(nb * 5);
     std::vector<DwUnit> units(2 * nb);
     auto res2 = [&](int b) { return b >= 2 && b % 2 == 0 && b != nb - 1; };
     for (int b = 0; b < nb; ++b) {
       const ConvOp* o = &net->ops[5 * b];
-      for (int r = 0; r < 5; ++r) { pd[b].w[r] = o[r].w_off; boff[b * 5 + r] = o[r].b_off; }
+      for (int r = 0; r < 5; ++r) { pd[b].w[r] = o[r].w_off; boff[b * 5 + r] = o[r].b_off; pboff[b * 5 + r] = o[r].p_bias; }
       pd[b].w_head = net->ops.back().w_off;
       pd[b].cin = b == 0 ? 1 : 32;
       const bool last = b == nb - 1;
@@ -720,22 +900,23 @@ int tc_grad_prepare(fk_net* net) {
       const int hin = b == 0 ? in_tile : (b - 1) * NDUMP + 4;
       DwUnit& A = units[2 * b];        // pass A: H, XX, Y
       A.b = b; A.nconv = 3;
-      A.conv[0] = DwConv{b * NDUMP + 3, 0, 0, 9, 32, {0}, 0, 32, o[4].w_off};
+      A.conv[0] = DwConv{b * NDUMP + 3, 0, 0, 9, 32, {0}, 0, 32, o[4].w_off, o[4].p_kernel, o[4].p_g, 5 * b + 4};
       for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) A.conv[0].off[i * 3 + j] = g.p_first + (i - 2) * g.P + (j - 2);
-      A.conv[1] = DwConv{b * NDUMP + 0, 1, 0, 1, 16, {0}, 288, 32, o[2].w_off};
+      A.conv[1] = DwConv{b * NDUMP + 0, 1, 0, 1, 16, {0}, 288, 32, o[2].w_off, o[2].p_kernel, o[2].p_g, 5 * b + 2};
       A.conv[1].off[0] = g.p_first + (last ? -1 : 0);
-      A.conv[2] = DwConv{b * NDUMP + 1, 1, 2, 1, 16, {0}, 304, 32, o[3].w_off};
+      A.conv[2] = DwConv{b * NDUMP + 1, 1, 2, 1, 16, {0}, 304, 32, o[3].w_off, o[3].p_kernel, o[3].p_g, 5 * b + 3};
       A.conv[2].off[0] = g.p_first - g.P;
       DwUnit& Bu = units[2 * b + 1];   // pass B: V, X
       Bu.b = b; Bu.nconv = 2;
-      Bu.conv[0] = DwConv{vin, 3, 0, 9, 32, {0}, 0, pd[b].cin, o[0].w_off};
+      Bu.conv[0] = DwConv{vin, 3, 0, 9, 32, {0}, 0, pd[b].cin, o[0].w_off, o[0].p_kernel, o[0].p_g, 5 * b + 0};
       for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Bu.conv[0].off[i * 3 + j] = g.p_first + (i - 2) * g.P + (j - 1);
-      Bu.conv[1] = DwConv{hin, 2, 0, 3, 32, {0}, 288, pd[b].cin, o[1].w_off};
+      Bu.conv[1] = DwConv{hin, 2, 0, 3, 32, {0}, 288, pd[b].cin, o[1].w_off, o[1].p_kernel, o[1].p_g, 5 * b + 1};
       for (int j = 0; j < 3; ++j) Bu.conv[1].off[j] = g.p_first + (j - 2);
     }
     uint8_t* base = (uint8_t*)net->d_tc_bwd;
     FK_CHECK_CUDA(cudaMemcpy(base + bwd_units_offset(nb), units.data(), sizeof(DwUnit) * units.size(), cudaMemcpyHostToDevice));
     FK_CHECK_CUDA(cudaMemcpy(base + bwd_boff_offset(nb), boff.data(), sizeof(long long) * boff.size(), cudaMemcpyHostToDevice));
+    FK_CHECK_CUDA(cudaMemcpy(base + bwd_pboff_offset(nb), pboff.data(), sizeof(long long) * pboff.size(), cudaMemcpyHostToDevice));
     FK_CHECK_CUDA(cudaMemcpy(base + bwd_pack_offset(nb), pd.data(), sizeof(BwdPackDesc) * nb, cudaMemcpyHostToDevice));
   }
   return 0;
@@ -825,6 +1006,7 @@ int tc_grad_weighted(fk_net* net, const int8_t* sigma, const float* y, int64_t B
     da.geff = geff; da.n = m; da.nb = nb; da.npos = g.npos; da.num_units = 2 * nb;
     da.cfg_chunk = (int)std::max<int64_t>(1, (m + 7) / 8);
     da.row_stride = 0; da.out_scale = 1.f;
+    da.xrows = nullptr; da.rld = 0; da.row_base = 0; da.wn_dir = nullptr; da.wn_coef = nullptr;
     const int items = da.num_units * (int)((m + da.cfg_chunk - 1) / da.cfg_chunk);
     tc_dw_kernel<<<(unsigned)std::min(items, sms), 128, dw_smem, s>>>(da);
     FK_CHECK_LAUNCH();
@@ -911,6 +1093,7 @@ int tc_grad_per_sample(fk_net* net, const int8_t* sigma, int64_t B, float* O_re,
       da.dump = base + L.dump; da.dz = base + L.dz; da.units = reinterpret_cast<const DwUnit*>(wb + bwd_units_offset(nb));
       da.geff = geff; da.n = m; da.nb = nb; da.npos = g.npos; da.num_units = 2 * nb;
       da.cfg_chunk = 1; da.row_stride = net->num_eff; da.out_scale = 1.f / seed_scale;
+      da.xrows = nullptr; da.rld = 0; da.row_base = 0; da.wn_dir = nullptr; da.wn_coef = nullptr;
       const long long items = (long long)da.num_units * m;
       tc_dw_kernel<<<(unsigned)std::min<long long>(items, sms), 128, dw_smem, s>>>(da);
       FK_CHECK_LAUNCH();
@@ -922,6 +1105,92 @@ int tc_grad_per_sample(fk_net* net, const int8_t* sigma, int64_t B, float* O_re,
           net->num_eff, 1.f / seed_scale);
       FK_CHECK_LAUNCH();
       if (grad_transform_rows_launch(net, geff, (pass == 0 ? O_re : O_im) + i * net->num_params, m, s)) return 1;
+    }
+  }
+  return 0;
+}
+
+// ---- Jacobian rows straight into the Gram operand -------------------------------------------------------------------
+// X: bf16, panel-major [ceil(P / 64)][rld rows][64]; sample b writes row row_re + b (d Re log psi / d theta) and, when
+// row_im >= 0, row row_im + b (d Im log psi / d theta), in RAW parameters (weight-norm transform fused into the flush).
+struct RowsLayout { size_t dump, mask, logits, dz, glog, coef, lp, total; };
+static RowsLayout rows_layout(const fk_net* net, int64_t chunk) {
+  TcPublicGeometry g;
+  tc_public_geometry(net, &g);
+  RowsLayout L;
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  size_t o = 0;
+  L.dump = o; o = al(o + (size_t)chunk * (g.nb * NDUMP + 1) * 64 * g.npos);
+  L.mask = o; o = al(o + (size_t)chunk * g.nb * NDUMP * 128 * 4);
+  L.logits = o; o = al(o + (size_t)chunk * 128 * 16);
+  L.dz = o; o = al(o + (size_t)chunk * g.nb * 4 * DZ_TILE);
+  L.glog = o; o = al(o + (size_t)chunk * 128 * 16);
+  L.coef = o; o = al(o + (size_t)chunk * 8);
+  L.lp = o; o = al(o + (size_t)chunk * 8);
+  L.total = o;
+  return L;
+}
+
+int64_t tc_jacobian_rows_workspace_bytes(const fk_net* net, int64_t B) {
+  return (int64_t)rows_layout(net, std::max<int64_t>(1, std::min<int64_t>(B, 1024))).total;
+}
+
+int tc_jacobian_rows(fk_net* net, const int8_t* sigma, int64_t B, void* X, int64_t rld, int64_t row_re, int64_t row_im,
+                     void* ws, int64_t ws_bytes, cudaStream_t s) {
+  FK_REQUIRE(net->params_set && net->d_tc_bwd && net->d_wn_dir, "tensor-core gradient weights were never packed (fk_net_set_params)");
+  for (const ConvOp& op : net->ops)
+    FK_REQUIRE(op.p_kernel % 16 == 0 && op.w_off % 4 == 0, "tc_jacobian_rows: kernel offsets must be multiples of 16 parameters");
+  TcPublicGeometry g;
+  tc_public_geometry(net, &g);
+  int64_t chunk = std::min<int64_t>(B, 1024);
+  while (chunk > 1 && (int64_t)rows_layout(net, chunk).total > ws_bytes) chunk /= 2;
+  const RowsLayout L = rows_layout(net, chunk);
+  FK_REQUIRE((int64_t)L.total <= ws_bytes, "tc_jacobian_rows: workspace too small (%lld < %zu bytes)", (long long)ws_bytes, L.total);
+  uint8_t* base = (uint8_t*)ws;
+  const int nb = g.nb;
+  const int npos_g = ((g.p_first + 128 + 2 * g.P + 4) + 7) / 8 * 8;
+  int dev = 0, sms = 148;
+  FK_CHECK_CUDA(cudaGetDevice(&dev));
+  FK_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const size_t bwd_smem = 2 * (size_t)IMGB_BYTES + (size_t)BWD_NP * 4 * 64 * npos_g + 256;
+  const size_t dw_smem = (size_t)DW_STAGES * 3 * (64 * g.npos + DZ_TILE) + (size_t)16 * g.npos * 16 + 256 + 4608;
+  FK_REQUIRE(bwd_smem <= 227 * 1024 && dw_smem <= 227 * 1024, "tensor-core gradient: lattice too large for shared memory");
+  FK_CHECK_CUDA(cudaFuncSetAttribute(tc_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem));
+  FK_CHECK_CUDA(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem));
+  const uint8_t* wb = (const uint8_t*)net->d_tc_bwd;
+  const float seed_scale = 64.f;
+  __nv_bfloat16* xr = (__nv_bfloat16*)X;
+  for (int64_t i = 0; i < B; i += chunk) {
+    const int64_t m = std::min(chunk, B - i);
+    const int8_t* sg = sigma + i * net->sites;
+    if (tc_forward_launch(net, sg, m, (float*)(base + L.lp), base + L.dump, (uint32_t*)(base + L.mask), (float*)(base + L.logits), s)) return 1;
+    for (int pass = 0; pass < (row_im >= 0 ? 2 : 1); ++pass) {
+      const long long row_base = (pass == 0 ? row_re : row_im) + i;
+      tc_const_coef_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(m, pass == 0 ? seed_scale : 0.f, pass == 0 ? 0.f : seed_scale,
+                                                                        (float*)(base + L.coef));
+      FK_CHECK_LAUNCH();
+      BwdArgs ba;
+      ba.images = wb; ba.mask = (const uint32_t*)(base + L.mask); ba.logits = (const float*)(base + L.logits);
+      ba.sigma = sg; ba.coef = (const float*)(base + L.coef); ba.dz = base + L.dz; ba.glog = (float*)(base + L.glog);
+      ba.n = m; ba.H = net->H; ba.W = net->W; ba.P = g.P; ba.nb = nb; ba.npos_g = npos_g; ba.p_first = g.p_first;
+      const long long groups = (m + BWD_NP - 1) / BWD_NP;
+      tc_backward_kernel<<<(unsigned)std::min<long long>(groups, sms), BWD_NP * 128 + 32, bwd_smem, s>>>(ba);
+      FK_CHECK_LAUNCH();
+      DwArgs2 da;
+      da.dump = base + L.dump; da.dz = base + L.dz; da.units = reinterpret_cast<const DwUnit*>(wb + bwd_units_offset(nb));
+      da.geff = nullptr; da.n = m; da.nb = nb; da.npos = g.npos; da.num_units = 2 * nb;
+      da.cfg_chunk = 1; da.row_stride = 1; da.out_scale = 1.f / seed_scale;
+      da.xrows = xr; da.rld = rld; da.row_base = row_base; da.wn_dir = net->d_wn_dir; da.wn_coef = net->d_wn_coef;
+      const long long items = (long long)da.num_units * m;
+      tc_dw_kernel<<<(unsigned)std::min<long long>(items, sms), 128, dw_smem, s>>>(da);
+      FK_CHECK_LAUNCH();
+      tc_db_rows_kernel<<<dim3((unsigned)(nb * 4), (unsigned)std::min<int64_t>(m, 64)), 256, 0, s>>>(
+          base + L.dz, m, nb, reinterpret_cast<const long long*>(wb + bwd_pboff_offset(nb)), xr, rld, row_base, 1.f / seed_scale);
+      FK_CHECK_LAUNCH();
+      tc_head_dw_rows_kernel<<<(unsigned)std::min<int64_t>(m, 1024), 256, 0, s>>>(
+          base + L.dump, (const float*)(base + L.glog), m, nb, g.npos, g.p_first, net->ops.back().p_kernel, net->ops.back().p_bias, xr,
+          rld, row_base, 1.f / seed_scale, net->num_params);
+      FK_CHECK_LAUNCH();
     }
   }
   return 0;

@@ -1,0 +1,182 @@
+"""Sample-space stochastic reconfiguration of the headline machine, device-resident end to end.
+
+The reference's SR (flowket/optimizers/stochastic_reconfiguration/optimizer.py:33-124) forms S = Obar^H Obar / B + lambda I
+over the parameters; for the 854 k-parameter 10x10 machine the same update is computed in sample space,
+
+    delta = X^T C (C X X^T C / B + lambda I)^-1 e' / B,      X = [Re O ; Im O]  (2B x P),  e' = [Re(E - Ebar) ; Im(E - Ebar)],
+
+with C the per-half centring projector (the "O - mean(O)" of optimizer.py:79-81 applied inside the Gram matrix).  Every
+stage is a call into the C ABI:
+
+    fk_jacobian_rows_tc   per-sample Jacobian rows on the tensor cores, weight-norm transform fused, written as bf16 in the
+                          panel-major layout the Gram kernel's TMA boxes want (no fp32 copy of X ever exists)
+    fk_sr_gram_xxt        hand-written cta_group::2 tcgen05 GEMM, upper block triangle + mirror
+    fk_sr_centre_shift    S = C G C / B + lambda I in fp64
+    fk_sr_solve           fp64 Cholesky + triangular solves (cuSOLVER behind the ABI)
+    fk_sr_xt_w            delta = X^T (C w), one pass over X at HBM speed
+
+Sharded over the ranks of torch.distributed: each rank produces the rows of its own samples; ONE all-to-all
+re-shards X from sample-major to parameter-major (in the panel-major layout a parameter slice is a contiguous range of
+panels, so the exchange needs no packing; the received per-rank blocks are consumed in place through the Gram kernel's
+row-block tensor map); the partial Gram matrices are summed with one fp32 allreduce, every rank solves the same system, and
+the slices of delta are gathered."""
+import ctypes
+
+import numpy as np
+
+from .. import _lib
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class DeviceSampleSpaceSR(object):
+    def __init__(self, net, diag_shift):
+        import torch
+        self.torch = torch
+        self.net = net
+        self.lib = net.lib
+        self.diag_shift = float(diag_shift)
+        self._solver = None
+        self.timings_ms = {}
+
+    @staticmethod
+    def supported(net):
+        return net.lib.fk_jacobian_rows_tc_workspace_bytes(net.handle, 1) >= 0
+
+    def __del__(self):
+        try:
+            if self._solver is not None:
+                self.lib.fk_sr_solver_destroy(self._solver)
+                self._solver = None
+        except Exception:
+            pass
+
+    def _solver_handle(self):
+        if self._solver is None:
+            h = ctypes.c_void_p()
+            _lib.check(self.lib.fk_sr_solver_create(ctypes.byref(h)))
+            self._solver = h
+        return self._solver
+
+    def _world(self, distributed):
+        import torch.distributed as dist
+        if distributed and dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(), dist.get_rank()
+        return 1, 0
+
+    def delta(self, sigma, local_energy, distributed=False):
+        """-> delta [P] fp32 (identical on every rank).  sigma: int8 CUDA tensor [B_local, sites] (this rank's samples),
+        local_energy: complex128 CUDA tensor [B_local]."""
+        torch, net, lib = self.torch, self.net, self.lib
+        import torch.distributed as dist
+        world, rank = self._world(distributed)
+        dev = net.device
+        sig = net.to_sigma(sigma)
+        Bl = sig.shape[0]
+        P = net.num_params
+        nkb = (P + 63) // 64
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+        stream = _lib.stream_ptr()
+        if world > 1:
+            sizes = torch.tensor([float(Bl)], dtype=torch.float64, device=dev)
+            gathered = [torch.zeros_like(sizes) for _ in range(world)]
+            dist.all_gather(gathered, sizes)
+            if any(int(g.item()) != Bl for g in gathered):
+                raise ValueError('the device sample-space SR needs the same number of samples on every rank')
+            if (2 * Bl) % 128 != 0:
+                raise ValueError('the sharded device sample-space SR needs a multiple of 64 samples per rank')
+        B = Bl * world
+        R, Rl = 2 * B, 2 * Bl
+        nkb_r = (nkb + world - 1) // world          # panels per rank after the exchange
+        nkb_pad = nkb_r * world
+        panel_bytes = Rl * 128
+        ev[0].record()
+        # ---- X rows of this rank: [nkb_pad][Rl][64] bf16 (padding panels zero)
+        X = net.workspace('sr_x', nkb_pad * panel_bytes)
+        if nkb_pad > nkb:
+            X[nkb * panel_bytes:nkb_pad * panel_bytes].zero_()
+        wsb = lib.fk_jacobian_rows_tc_workspace_bytes(net.handle, Bl)
+        ws = net.workspace('sr_rows', wsb)
+        with torch.cuda.device(dev):
+            _lib.check(lib.fk_jacobian_rows_tc(net.handle, _ptr(sig), Bl, _ptr(X), Rl, 0, Bl, _ptr(ws), ws.numel(), stream))
+        ev[1].record()
+        # ---- re-shard: rank g receives panels [g nkb_r, (g + 1) nkb_r) of every rank as one row block each
+        if world > 1:
+            Xg = net.workspace('sr_xg', nkb_pad * panel_bytes)
+            dist.all_to_all_single(Xg[:nkb_pad * panel_bytes], X[:nkb_pad * panel_bytes])
+            Kg = min(P, (rank + 1) * nkb_r * 64) - rank * nkb_r * 64
+            Kg = max(Kg, 0)
+            block_stride = nkb_r * panel_bytes
+        else:
+            Xg, Kg, block_stride = X, P, 0
+        ev[2].record()
+        # ---- Gram of this rank's parameter slice over all samples
+        G = net.workspace('sr_g', R * R * 4).view(torch.float32)[:R * R]
+        gws_b = lib.fk_sr_gram_xxt_workspace_bytes(R)
+        gws = net.workspace('sr_gram_ws', gws_b)
+        with torch.cuda.device(dev):
+            if Kg > 0:
+                _lib.check(lib.fk_sr_gram_xxt(_ptr(Xg), R, Kg, Rl, world, block_stride, 1.0, _ptr(G), R, _ptr(gws), gws.numel(),
+                                              stream))
+            else:
+                G.zero_()
+        if world > 1:
+            dist.all_reduce(G)
+        ev[3].record()
+        # ---- S = C G C / B + lambda I, right-hand side, solve
+        S = net.workspace('sr_s', R * R * 8).view(torch.float64)[:R * R]
+        cws_b = lib.fk_sr_centre_shift_workspace_bytes(R)
+        cws = net.workspace('sr_centre_ws', cws_b)
+        e = local_energy.to(device=dev, dtype=torch.complex128) if torch.is_tensor(local_energy) else \
+            torch.as_tensor(np.asarray(local_energy, np.complex128)).to(dev)
+        esum = torch.view_as_real(e.sum().reshape(1)).clone()
+        if world > 1:
+            dist.all_reduce(esum)
+        e = e - torch.view_as_complex(esum) / B
+        if world > 1:
+            parts = [torch.empty_like(e) for _ in range(world)]
+            dist.all_gather(parts, e)
+            rhs = torch.cat([torch.cat([p.real, p.imag]) for p in parts]) / B      # row order of the blocks: [Re ; Im] per rank
+        else:
+            rhs = torch.cat([e.real, e.imag]) / B
+        rhs = rhs.contiguous()
+        info = torch.zeros(1, dtype=torch.int32, device=dev)
+        solver = self._solver_handle()
+        sws_b = lib.fk_sr_solve_workspace_bytes(solver, R)
+        if sws_b < 0:
+            raise _lib.FlowketB200Error('fk_sr_solve_workspace_bytes failed')
+        sws = net.workspace('sr_solve_ws', sws_b)
+        with torch.cuda.device(dev):
+            _lib.check(lib.fk_sr_centre_shift(_ptr(G), R, R, world, self.diag_shift, _ptr(S), _ptr(cws), cws.numel(), stream))
+            ev[4].record()
+            _lib.check(lib.fk_sr_solve(solver, _ptr(S), _ptr(rhs), R, _ptr(info), _ptr(sws), sws.numel(), stream))
+        ev[5].record()
+        # ---- delta = X^T (C w): centre w per half, one pass over the parameter slice, gather the slices
+        w = rhs.view(world, 2, Bl)
+        w = (w - w.mean(dim=(0, 2), keepdim=True)).reshape(-1).float().contiguous()
+        Kpad = nkb_r * 64
+        d_loc = torch.zeros(Kpad, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            if Kg > 0:
+                _lib.check(lib.fk_sr_xt_w(_ptr(Xg), R, Kg, Rl, world, block_stride, _ptr(w), _ptr(d_loc), stream))
+        if world > 1:
+            parts = [torch.empty_like(d_loc) for _ in range(world)]
+            dist.all_gather(parts, d_loc)
+            delta = torch.cat(parts)[:P]
+        else:
+            delta = d_loc[:P]
+        ev[6].record()
+        self._events = ev
+        self._info = info
+        return delta
+
+    def read_timings(self):
+        """after a synchronise: phase times of the last delta() in ms (+ the potrf status)"""
+        ev = self._events
+        names = ['jacobian', 'exchange', 'gram', 'centre', 'cholesky', 'update']
+        self.timings_ms = {n: ev[i].elapsed_time(ev[i + 1]) for i, n in enumerate(names)}
+        self.timings_ms['solve'] = sum(self.timings_ms[n] for n in names[1:])
+        self.potrf_info = int(self._info.item())
+        return self.timings_ms

@@ -367,8 +367,11 @@ class StochasticReconfiguration(_SRBase):
                       tensor-core GEMM (cuBLAS, bf16 operands / fp32 accumulation by default) + a Cholesky of size 2B.
     `sample_space=None` picks the sample-space form when P > 2B."""
 
-    def __init__(self, model, sample_space=None, gram_dtype='bf16', jacobian_chunk=1024, shared_cholesky=False, **kwargs):
+    def __init__(self, model, sample_space=None, gram_dtype='bf16', jacobian_chunk=1024, shared_cholesky=False,
+                 device_pipeline=True, read_timings=True, **kwargs):
         super(StochasticReconfiguration, self).__init__(model, **kwargs)
+        self.device_pipeline = device_pipeline   # False: the torch route below (fp32 rows, torch.mm Gram) -- kept as a cross-check
+        self.read_timings = read_timings         # False: no synchronise after the update (timings / potrf status unread)
         self.shared_cholesky = shared_cholesky     # distributed sample-space solve: share the Cholesky between the ranks
         self.sample_space = sample_space
         self.gram_dtype = gram_dtype
@@ -398,13 +401,38 @@ class StochasticReconfiguration(_SRBase):
             del O_re, O_im
         return X
 
+    def _device_pipeline(self):
+        """The device-resident sample-space pipeline (sample_space_sr.py: bf16 Jacobian rows -> hand-written tcgen05 Gram ->
+        fp64 solve -> X^T w, all behind the C ABI) when the machine has tensor-core Jacobians and the defaults are kept."""
+        from .sample_space_sr import DeviceSampleSpaceSR
+        from .. import _lib
+        if self.gram_dtype != 'bf16' or self.shared_cholesky or not self.device_pipeline:
+            return None
+        net = self.machine.device_net()
+        if self._jacobian_engine(net) != _lib.FK_ENGINE_TC or not DeviceSampleSpaceSR.supported(net):
+            return None
+        if getattr(self, '_pipeline', None) is None or self._pipeline.net is not net:
+            self._pipeline = DeviceSampleSpaceSR(net, self.diag_shift)
+        self._pipeline.diag_shift = float(self.diag_shift)
+        return self._pipeline
+
     def compute_update(self, sigma, local_energy):
         import torch
+        net0 = self.machine.device_net()
+        sample_space = self.sample_space
+        if sample_space is None:
+            world = self._world_size() if self.distributed else 1
+            sample_space = net0.num_params > 2 * int(sigma.shape[0]) * world   # P > 2 B_global
+        pipe = self._device_pipeline() if sample_space else None
+        if pipe is not None and (not self.distributed or (2 * int(sigma.shape[0])) % 128 == 0):
+            delta = pipe.delta(sigma, local_energy, distributed=self.distributed)
+            if self.read_timings:
+                torch.cuda.synchronize()
+                self.last_timings_ms = dict(pipe.read_timings())
+                if pipe.potrf_info != 0:
+                    raise RuntimeError('sample-space SR: the Cholesky factorisation failed (potrf info %d)' % pipe.potrf_info)
+            return delta
         if self.distributed:
-            sample_space = self.sample_space
-            if sample_space is None:
-                net = self.machine.device_net()
-                sample_space = net.num_params > 2 * int(sigma.shape[0]) * self._world_size()   # P > 2 B_global
             if sample_space:
                 return self._compute_update_sample_space_distributed(sigma, local_energy)
             from .._device import sr_gram

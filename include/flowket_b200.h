@@ -191,17 +191,30 @@ int fk_sr_gram_tc(const float* A, int64_t rows, int64_t cols, int transpose_a, i
 /* ---- sample-space stochastic reconfiguration of machines whose P x P matrix does not fit (P >> 2B): the push-through form
  * delta = X^T (C X X^T C / B + lambda I)^-1 C e' / B of optimizer.py:55-66,100-108, X = [Re O ; Im O] (R = 2B rows, bf16),
  * C = per-half centring (the "O - mean(O)" of optimizer.py:79-81 applied inside the Gram matrix).
+ * X is bf16 in the PANEL-MAJOR layout X[p / 64][r][p % 64] with `rld` (>= R) rows per 64-parameter panel, 128-byte
+ * aligned, the unused columns of the last panel zero (a TMA box is then one contiguous 16 KB block; with row-major rows
+ * 1.7 MB apart the same GEMM lost half its speed to TLB / L2 misses).
+ * fk_jacobian_rows_tc: the producer of X -- per-sample Jacobian rows of ConvNetAutoregressive2D on the tensor cores
+ *   (machines/abstract_machine.py:24-28), weight-norm transform fused, written as bf16 straight into that layout:
+ *   sample b -> row row_re + b (d Re log psi / d theta) and row row_im + b (d Im log psi / d theta; row_im < 0: skip).
  * fk_sr_gram_xxt: G[R, ldg] (fp32) = scale * X X^T; hand-written tcgen05 GEMM (cta_group::2, 256 x 256 tiles per CTA
- *   pair, TMA 128-byte-swizzled operands, upper block triangle computed and mirrored).  X: bf16 [R, ld], ld % 8 == 0.
+ *   pair, TMA 128-byte-swizzled operands, upper block triangle computed and mirrored, partial sums of 16 k parameters
+ *   added in fp32 registers because the tensor core truncates once per MMA).
  * fk_sr_centre_shift: S[R, R] (fp64) = C G C / B + lambda I.
  * fk_sr_xt_w: out[K] (fp32) = X^T w  (w: [R] fp32). */
+int64_t fk_jacobian_rows_tc_workspace_bytes(const fk_net_t* net, int64_t B);
+int fk_jacobian_rows_tc(fk_net_t* net, const int8_t* sigma, int64_t B, void* X, int64_t rld, int64_t row_re,
+                        int64_t row_im, void* ws, int64_t ws_bytes, void* stream);
 int64_t fk_sr_gram_xxt_workspace_bytes(int64_t R);
-int fk_sr_gram_xxt(const void* X, int64_t R, int64_t K, int64_t ld, float scale, float* G, int64_t ldg, void* ws,
-                   int64_t ws_bytes, void* stream);
+/* Row blocks (the sharded step): X may consist of `nblocks` panel-major blocks `block_stride` BYTES apart (one per
+ * rank, as the all-to-all delivers them), each holding R / nblocks rows, [Re rows ; Im rows]; nblocks = 1: one block. */
+int fk_sr_gram_xxt(const void* X, int64_t R, int64_t K, int64_t rld, int64_t nblocks, int64_t block_stride, float scale,
+                   float* G, int64_t ldg, void* ws, int64_t ws_bytes, void* stream);
 int64_t fk_sr_centre_shift_workspace_bytes(int64_t R);
-int fk_sr_centre_shift(const float* G, int64_t R, int64_t ldg, double lambda, double* S, void* ws, int64_t ws_bytes,
-                       void* stream);
-int fk_sr_xt_w(const void* X, int64_t R, int64_t K, int64_t ld, const float* w, float* out, void* stream);
+int fk_sr_centre_shift(const float* G, int64_t R, int64_t ldg, int64_t nblocks, double lambda, double* S, void* ws,
+                       int64_t ws_bytes, void* stream);
+int fk_sr_xt_w(const void* X, int64_t R, int64_t K, int64_t rld, int64_t nblocks, int64_t block_stride, const float* w,
+               float* out, void* stream);
 
 /* fk_sr_solve: replaces tf.cholesky + tf.cholesky_solve (optimizer.py:63-66).  S (fp64 [n, n], symmetric positive
  * definite) is overwritten by its Cholesky factor, rhs [n] by the solution; info_out (device int, optional) = potrf status.

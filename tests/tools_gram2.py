@@ -13,12 +13,23 @@ import torch
 from flowket_b200 import _lib
 
 
-def gram_xxt(lib, X, K, scale=1.0):
-    R, ld = X.shape
-    G = torch.empty((R, R), dtype=torch.float32, device=X.device)
+def to_panels(Xrow, K, rld):
+    """row-major [R, >= K] bf16 -> panel-major [ceil(K/64)][rld][64] (zero padded columns / junk padding rows)"""
+    R = Xrow.shape[0]
+    nkb = (K + 63) // 64
+    Xp = torch.full((nkb, rld, 64), 3.0, dtype=torch.bfloat16, device=Xrow.device)
+    pad = torch.zeros((R, nkb * 64), dtype=torch.bfloat16, device=Xrow.device)
+    pad[:, :K] = Xrow[:, :K]
+    Xp[:, :R, :] = pad.view(R, nkb, 64).permute(1, 0, 2)
+    return Xp
+
+
+def gram_xxt(lib, Xp, R, K, scale=1.0):
+    rld = Xp.shape[1]
+    G = torch.empty((R, R), dtype=torch.float32, device=Xp.device)
     wsb = lib.fk_sr_gram_xxt_workspace_bytes(R)
-    ws = torch.empty(wsb, dtype=torch.uint8, device=X.device)
-    _lib.check(lib.fk_sr_gram_xxt(X.data_ptr(), R, K, ld, scale, G.data_ptr(), R, ws.data_ptr(), wsb, _lib.stream_ptr()))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=Xp.device)
+    _lib.check(lib.fk_sr_gram_xxt(Xp.data_ptr(), R, K, rld, 1, 0, scale, G.data_ptr(), R, ws.data_ptr(), wsb, _lib.stream_ptr()))
     return G
 
 
@@ -44,21 +55,21 @@ def main():
     for (R, K, ld) in [(512, 1000, 1000), (256, 64, 64), (700, 4100, 4104), (2048, 70000, 70016), (1300, 33000, 33008)]:
         X = torch.zeros((R, ld), dtype=torch.bfloat16, device=dev)
         X[:, :K] = (torch.randn((R, K), device=dev) * (1 + torch.rand((R, 1), device=dev))).to(torch.bfloat16)
-        X[:, K:] = 7.0          # junk beyond K must be ignored (TMA extent = K)
-        G = gram_xxt(lib, X, K, 0.5)
+        Xp = to_panels(X, K, ld % 977 + R)      # rld > R: padding rows must be ignored
+        G = gram_xxt(lib, Xp, R, K, 0.5)
         ref = 0.5 * (X[:, :K].double() @ X[:, :K].double().T)
         err = ((G.double() - ref).abs().max() / ref.abs().max()).item()
         sym = (G - G.T).abs().max().item()
         print('gram_xxt R=%d K=%d ld=%d: max err / max |G| = %.2e, asymmetry %.1e' % (R, K, ld, err, sym), flush=True)
         out['gram_%d_%d' % (R, K)] = err
-        assert err < 1e-5 and sym == 0.0, (err, sym)
+        assert err < 1e-4 and sym == 0.0, (err, sym)
         # centring + shift
         B = R // 2
         if R % 2 == 0:
             wsb = lib.fk_sr_centre_shift_workspace_bytes(R)
             ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
             S = torch.empty((R, R), dtype=torch.float64, device=dev)
-            _lib.check(lib.fk_sr_centre_shift(G.data_ptr(), R, R, 0.05, S.data_ptr(), ws.data_ptr(), wsb, _lib.stream_ptr()))
+            _lib.check(lib.fk_sr_centre_shift(G.data_ptr(), R, R, 1, 0.05, S.data_ptr(), ws.data_ptr(), wsb, _lib.stream_ptr()))
             C = torch.eye(B, dtype=torch.float64, device=dev) - 1.0 / B
             Cf = torch.block_diag(C, C)
             Sref = Cf @ G.double() @ Cf / B + 0.05 * torch.eye(R, dtype=torch.float64, device=dev)
@@ -77,17 +88,56 @@ def main():
             _lib.check(lib.fk_sr_solve(h, Sf.data_ptr(), x.data_ptr(), R, info.data_ptr(), ws.data_ptr(), wsb, _lib.stream_ptr()))
             xref = torch.linalg.solve(S, rhs)
             e3 = ((x - xref).abs().max() / xref.abs().max()).item()
-            print('  solve: %.2e info %d' % (e3, info.item()), flush=True)
-            assert e3 < 1e-8 and info.item() == 0
+            r_mine = ((S @ x - rhs).abs().max() / rhs.abs().max()).item()
+            r_ref = ((S @ xref - rhs).abs().max() / rhs.abs().max()).item()
+            print('  solve: %.2e info %d; residuals: fk_sr_solve %.1e, torch.linalg.solve %.1e' % (e3, info.item(), r_mine, r_ref), flush=True)
+            assert r_mine < 1e-10 and info.item() == 0
             _lib.check(lib.fk_sr_solver_destroy(h))
         # X^T w
         w = torch.randn(R, device=dev)
         o = torch.empty(K, dtype=torch.float32, device=dev)
-        _lib.check(lib.fk_sr_xt_w(X.data_ptr(), R, K, ld, w.data_ptr(), o.data_ptr(), _lib.stream_ptr()))
+        _lib.check(lib.fk_sr_xt_w(Xp.data_ptr(), R, K, Xp.shape[1], 1, 0, w.data_ptr(), o.data_ptr(), _lib.stream_ptr()))
         oref = X[:, :K].double().T @ w.double()
         e4 = ((o.double() - oref).abs().max() / oref.abs().max()).item()
         print('  xt_w: %.2e' % e4, flush=True)
         assert e4 < 1e-5, e4
+
+    # row blocks (the sharded step): 3 blocks of 256 rows [Re ; Im] each, in separate buffers of one allocation
+    nbk, br, K = 3, 256, 5000
+    R = nbk * br
+    X = (torch.randn((R, K), device=dev) + 0.3).to(torch.bfloat16)
+    nkb = (K + 63) // 64
+    rld = br + 128
+    buf = torch.full((nbk, nkb + 2, rld, 64), 5.0, dtype=torch.bfloat16, device=dev)      # (+ 2 junk panels between the blocks)
+    for q in range(nbk):
+        buf[q, :nkb] = to_panels(X[q * br:(q + 1) * br], K, rld)
+    stride = buf.stride(0) * 2
+    G = torch.empty((R, R), dtype=torch.float32, device=dev)
+    wsb = lib.fk_sr_gram_xxt_workspace_bytes(R)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    _lib.check(lib.fk_sr_gram_xxt(buf.data_ptr(), R, K, rld, nbk, stride, 1.0, G.data_ptr(), R, ws.data_ptr(), wsb, _lib.stream_ptr()))
+    ref = X.double() @ X.double().T
+    err = ((G.double() - ref).abs().max() / ref.abs().max()).item()
+    print('gram_xxt with 3 row blocks: %.2e' % err, flush=True)
+    assert err < 1e-4
+    wsb = lib.fk_sr_centre_shift_workspace_bytes(R)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    S = torch.empty((R, R), dtype=torch.float64, device=dev)
+    _lib.check(lib.fk_sr_centre_shift(G.data_ptr(), R, R, nbk, 0.05, S.data_ptr(), ws.data_ptr(), wsb, _lib.stream_ptr()))
+    half = ((torch.arange(R, device=dev) % br) >= br // 2)
+    Cf = torch.eye(R, dtype=torch.float64, device=dev)
+    for hsel in (half, ~half):
+        idx = hsel.nonzero().reshape(-1)
+        Cf[idx[:, None], idx[None, :]] -= 1.0 / idx.numel()
+    Sref = Cf @ G.double() @ Cf / (R // 2) + 0.05 * torch.eye(R, dtype=torch.float64, device=dev)
+    e2 = ((S - Sref).abs().max() / Sref.abs().max()).item()
+    w = torch.randn(R, device=dev)
+    o = torch.empty(K, dtype=torch.float32, device=dev)
+    _lib.check(lib.fk_sr_xt_w(buf.data_ptr(), R, K, rld, nbk, stride, w.data_ptr(), o.data_ptr(), _lib.stream_ptr()))
+    oref = X.double().T @ w.double()
+    e4 = ((o.double() - oref).abs().max() / oref.abs().max()).item()
+    print('  centre_shift (blocks): %.2e, xt_w (blocks): %.2e' % (e2, e4), flush=True)
+    assert e2 < 1e-12 and e4 < 1e-5
 
     if '--big' in sys.argv:
         R, K = 16384, 854016
@@ -96,7 +146,10 @@ def main():
         for r in range(0, R, 1024):
             X[r:r + 1024] = (torch.randn((1024, ld), device=dev) * 0.3 + 0.1).to(torch.bfloat16)
         X[:, K:] = 0
-        G = gram_xxt(lib, X, K)
+        Xp = torch.empty((ld // 64, R, 64), dtype=torch.bfloat16, device=dev)
+        for r in range(0, R, 1024):
+            Xp[:, r:r + 1024, :] = X[r:r + 1024].view(1024, ld // 64, 64).permute(1, 0, 2)
+        G = gram_xxt(lib, Xp, R, K)
         torch.cuda.synchronize()
         # exact fp64 reference on two 256 x 256 blocks (diagonal and off-diagonal)
         for (i0, j0) in [(0, 0), (512, 9216), (16128, 16128), (1024, 16000)]:
@@ -119,7 +172,7 @@ def main():
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
 
         def mine():
-            _lib.check(lib.fk_sr_gram_xxt(X.data_ptr(), R, K, ld, 1.0, G.data_ptr(), R, ws.data_ptr(), wsb, _lib.stream_ptr()))
+            _lib.check(lib.fk_sr_gram_xxt(Xp.data_ptr(), R, K, R, 1, 0, 1.0, G.data_ptr(), R, ws.data_ptr(), wsb, _lib.stream_ptr()))
         t_mine = timed(mine)
         nt = R // 256
         flops_tri = 2.0 * (nt * (nt + 1) / 2) * 256 * 256 * K
@@ -136,14 +189,14 @@ def main():
         out['cublas_tflops'] = flops_cb / t_cublas / 1e9
         w = torch.randn(R, device=dev)
         o = torch.empty(K, dtype=torch.float32, device=dev)
-        t_xtw = timed(lambda: _lib.check(lib.fk_sr_xt_w(X.data_ptr(), R, K, ld, w.data_ptr(), o.data_ptr(), _lib.stream_ptr())))
+        t_xtw = timed(lambda: _lib.check(lib.fk_sr_xt_w(Xp.data_ptr(), R, K, R, 1, 0, w.data_ptr(), o.data_ptr(), _lib.stream_ptr())))
         print('fk_sr_xt_w: %.2f ms, %.0f GB/s' % (t_xtw, R * K * 2 / t_xtw / 1e6), flush=True)
         out['xtw_ms'] = t_xtw
         out['xtw_gbs'] = R * K * 2 / t_xtw / 1e6
         S = torch.empty((R, R), dtype=torch.float64, device=dev)
         wsb2 = lib.fk_sr_centre_shift_workspace_bytes(R)
         ws2 = torch.empty(wsb2, dtype=torch.uint8, device=dev)
-        t_cs = timed(lambda: _lib.check(lib.fk_sr_centre_shift(G.data_ptr(), R, R, 0.05, S.data_ptr(), ws2.data_ptr(), wsb2, _lib.stream_ptr())))
+        t_cs = timed(lambda: _lib.check(lib.fk_sr_centre_shift(G.data_ptr(), R, R, 1, 0.05, S.data_ptr(), ws2.data_ptr(), wsb2, _lib.stream_ptr())))
         print('fk_sr_centre_shift: %.2f ms' % t_cs, flush=True)
         out['centre_ms'] = t_cs
         h = ctypes.c_void_p()
