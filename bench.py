@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Headline benchmark: one VMC step (exact autoregressive sampling -> local energy -> weighted gradient + Adam)
-of Heisenberg 2-D 10x10 OBC, ConvNetAutoregressive2D(depth 20, 32 channels), synthetic random-init weights.
+"""Headline benchmark: one VMC step of the north-star target -- exact autoregressive sampling -> local energy ->
+stochastic-reconfiguration update -- of Heisenberg 2-D 10x10 OBC, ConvNetAutoregressive2D(depth 20, 32 channels),
+global batch 8192 sharded over the GPUs (strong scaling), synthetic random-init weights.
 
   python bench.py --gpus N --steps K --warmup W            # this repository (CUDA, one process per GPU)
   python bench.py --impl reference --gpus N ...            # reference-equivalent CPU path (oracle port) on the host cores
@@ -82,33 +83,51 @@ class ClockSampler(object):
 # ----------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (reference-equivalent CPU path; TensorFlow is not installable)
 # ----------------------------------------------------------------------------------------------------------
-def cpu_step_rate(sample_batch, repeats, seed=0):
-    """samples/s of one VMC step (incremental sampling + E_loc + weighted gradient) on the host cores."""
+def cpu_step(sample_batch, seed=0, diag_shift=0.05, weights=None):
+    """One north-star step on the host cores: incremental sampling + E_loc over all connections + stochastic
+    reconfiguration (per-sample Jacobians by autograd, sample-space solve in fp64).  Returns the timings and the
+    samples / local energies (the GPU arm checks its engines against them)."""
     import torch
     from oracle import nets, operators as oops, local_energy as oeloc, sampler as osampler
     cores = os.cpu_count()
     torch.set_num_threads(cores)
     spec = nets.Conv2DSpec(H, W, DEPTH, CHANNELS)
-    params = nets.init_params(spec, seed=seed, dtype=torch.float32)
+    if weights is None:
+        params = nets.init_params(spec, seed=0, dtype=torch.float32)
+    else:                                                           # the GPU arm's machine, same bytes
+        params = [torch.from_numpy(np.asarray(w, np.float32)) for w in weights]
     op = oops.OracleOperator('heisenberg', (H, W), pbc=False)
     inc = osampler.IncrementalSampler2D(spec, params)
     rng = np.random.default_rng(seed)
-    times, n_conn = [], 0
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        sigma, _ = inc.sample(rng.random((sample_batch, H, W)))
-        t1 = time.perf_counter()
-        lv = oeloc.local_values(op, lambda c: nets.log_psi_numpy(spec, params, c, batch_size=256), sigma.astype(np.float64))
-        t2 = time.perf_counter()
-        y = oeloc.loss_coefficients(lv, lv.mean(), sample_batch)
-        nets.weighted_gradient(spec, params, sigma, y)
-        t3 = time.perf_counter()
-        times.append((t1 - t0, t2 - t1, t3 - t2))
-    t = np.array(times)
-    best = t.sum(axis=1).min()
-    return {'value': sample_batch / best, 'sampling_samples_per_s': sample_batch / t[:, 0].min(),
-            'eloc_evals_per_s': sample_batch / t[:, 1].min(), 'grad_samples_per_s': sample_batch / t[:, 2].min(),
-            'cores': cores, 'ms_per_step': best * 1e3}
+    t0 = time.perf_counter()
+    sigma, _ = inc.sample(rng.random((sample_batch, H, W)))
+    t1 = time.perf_counter()
+    lv = oeloc.local_values(op, lambda c: nets.log_psi_numpy(spec, params, c, batch_size=256), sigma.astype(np.float64))
+    t2 = time.perf_counter()
+    O_re = nets.per_sample_gradients(spec, params, sigma, 'real').double().numpy()
+    O_im = nets.per_sample_gradients(spec, params, sigma, 'imag').double().numpy()
+    X = np.concatenate([O_re - O_re.mean(0), O_im - O_im.mean(0)])
+    e = np.asarray(lv).reshape(-1) - np.mean(lv)
+    ep = np.concatenate([e.real, e.imag])
+    T = X @ X.T / sample_batch + diag_shift * np.eye(2 * sample_batch)
+    delta = X.T @ np.linalg.solve(T, ep / sample_batch)
+    t3 = time.perf_counter()
+    return {'sample_s': t1 - t0, 'eloc_s': t2 - t1, 'sr_s': t3 - t2, 'total_s': t3 - t0, 'cores': cores,
+            'sigma': sigma, 'local_values': np.asarray(lv).reshape(-1), 'delta_norm': float(np.linalg.norm(delta))}
+
+
+def cpu_step_rate(sample_batch, repeats, weights=None):
+    runs = [cpu_step(sample_batch, seed=i, weights=weights) for i in range(repeats)]
+    best = min(runs, key=lambda r: r['total_s'])
+    return {'value': sample_batch / best['total_s'], 'sampling_samples_per_s': sample_batch / min(r['sample_s'] for r in runs),
+            'eloc_evals_per_s': sample_batch / min(r['eloc_s'] for r in runs),
+            'sr_samples_per_s': sample_batch / min(r['sr_s'] for r in runs), 'cores': best['cores'],
+            'ms_per_step': best['total_s'] * 1e3, 'last': runs[-1]}
+
+
+CPU_SAMPLE = ('%d samples per step of the same workload (the step is linear in the batch up to the 2B x 2B solve): incremental '
+              'sampling + E_loc over all connections + per-sample Jacobians and sample-space SR solve, torch-CPU fp32 oracle port '
+              '(fp64 solve), all host threads')
 
 
 def run_reference(args):
@@ -116,77 +135,43 @@ def run_reference(args):
     if rank != 0:
         return
     sample_batch = args.cpu_batch
-    t_all = []
-    res = None
+    t_all, res = [], None
     for i in range(args.warmup + args.steps):
-        res = cpu_step_rate(sample_batch, 1, seed=i)
+        res = cpu_step(sample_batch, seed=i)
         if i >= args.warmup:
-            t_all.append(res['ms_per_step'])
+            t_all.append(res['total_s'] * 1e3)
     ms = float(np.mean(t_all))
     value = sample_batch / (ms * 1e-3)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': workload_config(args, 1),
         'cpu_baseline': {'value': value, 'unit': 'samples/s', 'cores': res['cores'], 'kind': 'port',
-                         'sample': '%d samples per step (of the %d-sample workload): incremental sampling + E_loc over '
-                                   'all connections + weighted gradient, torch-CPU fp32 oracle' % (sample_batch, args.batch_per_gpu)},
+                         'sample': CPU_SAMPLE % sample_batch},
         'e2e': {'value': value, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     emit(line)
 
 
-METRIC = 'vmc_step_samples_per_sec (sample + E_loc + gradient), Heisenberg 2D 10x10 OBC ConvNetAutoregressive2D d20 c32'
+METRIC = ('vmc_sr_step_samples_per_sec (exact autoregressive sampling + local energy + stochastic-reconfiguration update), '
+          'Heisenberg 2D 10x10 OBC ConvNetAutoregressive2D d20 c32, global batch 8192')
 
 
 def workload_config(args, world):
-    return {'workload': 'Heisenberg 2-D 10x10 OBC, ConvNetAutoregressive2D depth 20 / 32 channels, fast sampling, '
-                        'batch %d per GPU (BASELINE.json configs[2])' % args.batch_per_gpu,
-            'lattice': [H, W], 'depth': DEPTH, 'channels': CHANNELS, 'global_batch': args.batch_per_gpu * world,
-            'batch_per_gpu': args.batch_per_gpu, 'engine': args.engine,
-            'precision': ('tcgen05: fp16 operands, fp32 accumulation (sampling, E_loc, gradient with power-of-two loss scaling)'
-                          if args.engine == 'tc' else 'fp32 CUDA cores'),
-            'parallelism': 'samples sharded over %d GPU(s); allreduce of energy statistics and flat gradient' % world,
-            'l2_policy': 'per-step working set (activation workspaces, several GB) is much larger than the 126 MB L2'}
-
-
-def sharded_sr_leg(args, world, rank, model, cond, machine, operator, obs, timed):
-    """N > 1: the north-star step with stochastic reconfiguration -- sample + local energy + sample-space SR update -- on a
-    GLOBAL batch of `--batch-per-gpu` samples sharded over the ranks (strong scaling for this leg: the 2B x 2B system is
-    a function of the global batch; 8192 per GPU x 8 would be a 131 072^2 Gram).  Exchange per update: all-to-all of the
-    bf16 Jacobian rows, allreduce of the partial Grams, two allreduces of P floats.  Every rank
-    runs it; the time is the max over ranks.  Failures are reported in the JSON instead of taking the headline down."""
-    import torch
-    from flowket_b200.samplers import FastAutoregressiveSampler
-    from flowket_b200.optimizers import StochasticReconfiguration
-    try:
-        torch.cuda.empty_cache()
-        B_sr = max(1, args.batch_per_gpu // world)
-        sampler_sr = FastAutoregressiveSampler(cond, B_sr, seed=4321, sample_offset=rank * B_sr)
-        sr = StochasticReconfiguration(model, lr=0.01, diag_shift=0.05, sample_space=True, gram_dtype='bf16',
-                                       jacobian_chunk=512, distributed=True)
-
-        def step():
-            sigma = sampler_sr.next_device()
-            eloc = obs.local_values_device(model, sigma)
-            sr.step(sigma, eloc)
-            machine.device_net()
-
-        step()                                   # warm-up (allocations, NCCL channels for the all-to-all)
-        steps = 2
-        ms = timed(step, steps, record=None) / steps
-        torch.cuda.synchronize()
-        res = {'ms_per_step': ms, 'samples_per_s': B_sr * world / (ms * 1e-3), 'global_batch': B_sr * world,
-               'batch_per_gpu': B_sr, 'scaling': 'strong', 'sr_update_ms': dict(sr.last_timings_ms),
-               'solver': 'sample space, batch sharded over %d ranks: all-to-all re-shard of the bf16 Jacobian rows to '
-                         'parameter-major, partial 2B x 2B Gram per rank, fp32 allreduce, replicated fp64 Cholesky' % world,
-               'peak_mem_gb': torch.cuda.max_memory_allocated() / 1e9}
-        del sr
-        torch.cuda.empty_cache()
-        return res
-    except Exception as exc:
-        return {'error': '%s: %s' % (type(exc).__name__, exc)}
+    return {'workload': 'Heisenberg 2-D 10x10 OBC, ConvNetAutoregressive2D depth 20 / 32 channels, fast sampling, global '
+                        'batch %d sharded over the GPUs (BASELINE.json configs[2]: "batch 8192 on 8xB200")' % args.global_batch,
+            'lattice': [H, W], 'depth': DEPTH, 'channels': CHANNELS, 'global_batch': args.global_batch,
+            'batch_per_gpu': args.global_batch // world,
+            'step': 'sample + E_loc + SR update (diag_shift 0.05, lr 0.01, sample-space form of optimizer.py:55-108)',
+            'engines': {'sampler': 'tcgen05 fp16 operands / fp32 accumulate (fk_sample_tc)',
+                        'local_energy': 'value: tc-exact (fp16 hi+lo split operands, 22 bits, fp32 accumulate); value_fast: fp16 operands',
+                        'jacobian': 'tcgen05 fp16 operands / fp32 accumulate, rows stored in bf16',
+                        'gram': 'hand-written cta_group::2 tcgen05 GEMM, bf16 operands, fp32 accumulate',
+                        'solve': 'fp64 Cholesky (cuSOLVER behind fk_sr_solve)'},
+            'parallelism': 'samples sharded over %d GPU(s); all-to-all of the bf16 Jacobian rows, fp32 allreduce of the partial '
+                           'Gram matrices, allgather of the update slices' % world,
+            'l2_policy': 'per-step working set (28 GB of Jacobian rows, 1 GB Gram) is much larger than the 126 MB L2'}
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -195,13 +180,13 @@ def sharded_sr_leg(args, world, rank, model, cond, machine, operator, obs, timed
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    from flowket_b200 import Input, Model, _lib, FK_ENGINE_FP32, FK_ENGINE_TC
+    from flowket_b200 import Input, Model, _lib, FK_ENGINE_FP32, FK_ENGINE_TC, FK_ENGINE_TC_EXACT
     from flowket_b200.machines import ConvNetAutoregressive2D
     from flowket_b200.operators import Heisenberg
     from flowket_b200.samplers import FastAutoregressiveSampler
     from flowket_b200.optimization import VariationalMonteCarlo, DistributedVariationalMonteCarlo
     from flowket_b200.observables.monte_carlo import Observable
-    from flowket_b200.optimizers import Adam, Trainer, allreduce_sum_
+    from flowket_b200.optimizers import Adam, StochasticReconfiguration
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -211,82 +196,47 @@ def run_gpu(args):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     lib = _lib.require_cuda()
-    B = args.batch_per_gpu
-    engine = FK_ENGINE_TC if args.engine == 'tc' else FK_ENGINE_FP32
+    GB = args.global_batch
+    assert GB % world == 0, 'the global batch must divide over the ranks'
+    B = GB // world
 
     inp = Input(shape=(H, W), dtype='int8')
     machine = ConvNetAutoregressive2D(inp, depth=DEPTH, num_of_channels=CHANNELS, seed=0)
     model = Model(inputs=inp, outputs=machine.predictions)
-    model.engine = engine
     cond = Model(inputs=inp, outputs=machine.conditional_log_probs)
-    cond.engine = engine          # the sampler follows the engine of the conditional-log-probs model
+    cond.engine = FK_ENGINE_TC          # the sampler follows the engine of the conditional-log-probs model
     net = machine.device_net()
+    params0 = machine.flat_params_device().clone()
     if world > 1:   # rank-0 broadcast of the initial variables (BroadcastGlobalVariablesCallback(0))
-        dist.broadcast(machine.flat_params_device(), src=0)
-        machine.params_updated()
+        dist.broadcast(params0, src=0)
     sampler = FastAutoregressiveSampler(cond, B, seed=1234, sample_offset=rank * B)
     operator = Heisenberg(hilbert_state_shape=[H, W], pbc=False)
     obs = Observable(operator)
-    opt = Adam(lr=1e-3, beta_1=0.9, beta_2=0.9)
-    phase_ms = {'sample': [], 'eloc': [], 'grad': []}
-    conn_count = [0]
+    obs.count_connections = False        # nothing on the timed path reads a count back from the device
+    sr = StochasticReconfiguration(model, lr=0.01, diag_shift=0.05, sample_space=True, distributed=world > 1,
+                                   read_timings=False)
 
-    def device_step(record):
-        """inputs and outputs stay in HBM"""
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        ev[0].record()
-        sigma = sampler.next_device()
-        ev[1].record()
-        eloc = obs.local_values_device(model, sigma)
-        ev[2].record()
-        stats = obs.last_stats.clone()
-        if world > 1:
-            dist.all_reduce(stats)
-        mean = torch.complex(stats[0], stats[1]) / stats[3]
-        y = (torch.conj(eloc - mean) / (B * world)).to(torch.complex64)
-        grad = net.grad_weighted(net.to_sigma(sigma), y, engine=engine) / float(B)
-        if world > 1:
-            dist.all_reduce(grad)
-        opt.step(machine.flat_params_device(), grad)
-        machine.params_updated()
-        machine.device_net()          # re-derive the effective (weight-normalised) kernels
-        ev[3].record()
-        if record:
-            torch.cuda.synchronize()
-            phase_ms['sample'].append(ev[0].elapsed_time(ev[1]))
-            phase_ms['eloc'].append(ev[1].elapsed_time(ev[2]))
-            phase_ms['grad'].append(ev[2].elapsed_time(ev[3]))
-            conn_count[0] = obs.last_num_connections
-        return mean
-
-    vmc_cls = DistributedVariationalMonteCarlo if world > 1 else VariationalMonteCarlo
-    vmc = vmc_cls(model, operator, sampler)
-    trainer = Trainer(model, vmc, opt, distributed=world > 1)
-    h2d = [0]
-    d2h = [0]
-
-    def e2e_step():
-        """public API, host buffers: next_batch() returns host ndarrays, train_on_batch takes host ndarrays"""
-        x, y = next(vmc)            # D2H: sigma (int8) + E_loc (complex128)
-        g = trainer.gradient(x, y)  # H2D: sigma (int8) + y (complex64)
-        if world > 1:
-            allreduce_sum_(g)
-        opt.step(machine.flat_params_device(), g)
+    def reset():
+        machine.flat_params_device().copy_(params0)
         machine.params_updated()
         machine.device_net()
-        e = complex(vmc.current_energy)   # D2H read of the step's result
-        h2d[0] = x.nbytes + np.asarray(y, np.complex64).nbytes
-        d2h[0] = x.nbytes + vmc.current_local_energy.nbytes
-        return e
 
-    def timed(fn, steps, record=False):
+    def sr_step(engine):
+        """sample -> local energy -> SR update; inputs and outputs stay in HBM"""
+        model.engine = engine
+        sigma = sampler.next_device()
+        eloc = obs.local_values_device(model, sigma)
+        sr.step(sigma, eloc)
+        machine.device_net()              # re-derive the effective (weight-normalised) kernels, repack the operand images
+
+    def timed(fn, steps):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
         t0.record()
         for _ in range(steps):
-            fn(record) if record is not None else fn()
+            fn()
         t1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -296,101 +246,172 @@ def run_gpu(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(max(args.warmup, 3)):
-        device_step(False)
+    warm = max(args.warmup, 3)
+    # ---- headline: tc-exact local energy
+    reset()
+    for _ in range(warm):
+        sr_step(FK_ENGINE_TC_EXACT)
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
     launches0 = lib.fk_launch_count()
-    total_ms = timed(device_step, args.steps, record=False)
+    total_ms = timed(lambda: sr_step(FK_ENGINE_TC_EXACT), args.steps)
     launches = lib.fk_launch_count() - launches0
     clk = clocks.stop() if rank == 0 else None
-    # per-phase device times (separate pass so the per-phase synchronisation does not pollute `value`)
-    for _ in range(min(args.steps, 2)):
-        device_step(True)
-    # end-to-end through the public API with host buffers
+    # ---- the same step with the fp16 local-energy engine
+    reset()
+    for _ in range(2):
+        sr_step(FK_ENGINE_TC)
+    fast_ms = timed(lambda: sr_step(FK_ENGINE_TC), args.steps)
+    # ---- per-phase device times (separate pass: the per-phase synchronisation must not pollute `value`)
+    reset()
+    sr.read_timings = True
+    obs.count_connections = True
+    phases = {}
+    for engine, tag in ((FK_ENGINE_TC_EXACT, 'exact'), (FK_ENGINE_TC, 'fast')):
+        model.engine = engine
+        best = None
+        for _ in range(2):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
+            sigma = sampler.next_device()
+            ev[1].record()
+            eloc = obs.local_values_device(model, sigma)
+            ev[2].record()
+            sr.step(sigma, eloc)
+            machine.device_net()
+            ev[3].record()
+            torch.cuda.synchronize()
+            cur = {'sample': ev[0].elapsed_time(ev[1]), 'eloc': ev[1].elapsed_time(ev[2]), 'sr_update': ev[2].elapsed_time(ev[3])}
+            cur.update({'sr_' + k: v for k, v in sr.last_timings_ms.items() if k != 'solve'})
+            if best is None or cur['eloc'] < best['eloc']:
+                best = cur
+        phases[tag] = best
+    n_conn = obs.last_num_connections           # sum_b (1 + n_conn_b) on this rank
+    sr.read_timings = False
+    obs.count_connections = False
+
+    # ---- end to end through the public FlowKet-shaped API with host buffers
+    reset()
+    model.engine = FK_ENGINE_TC_EXACT
+    vmc_cls = DistributedVariationalMonteCarlo if world > 1 else VariationalMonteCarlo
+    vmc = vmc_cls(model, operator, sampler)
+    h2d, d2h = [0], [0]
+
+    def e2e_step():
+        x, y = vmc.next_batch()                      # D2H: sigma (int8 host ndarray) + E_loc (complex128 host ndarray)
+        sr.step(x, vmc.current_local_energy)          # H2D: sigma + local energies as host ndarrays
+        machine.device_net()
+        e = complex(vmc.current_energy)               # the step's result on the host
+        h2d[0] = x.nbytes + vmc.current_local_energy.nbytes
+        d2h[0] = x.nbytes + vmc.current_local_energy.nbytes + 16
+        return e
+
     for _ in range(2):
         e2e_step()
-    e2e_ms = timed(lambda: e2e_step(), args.steps, record=None)
+    e2e_ms = timed(e2e_step, args.steps)
 
-    sr_sharded = None
-    if world > 1 and not args.no_sr:
-        sr_sharded = sharded_sr_leg(args, world, rank, model, cond, machine, operator, obs, timed)
+    # ---- secondary: the Adam step of round 1 (sample + E_loc + weighted gradient + Adam), weak scaling, fp16 engines
+    adam = None
+    if not args.no_adam:
+        reset()
+        model.engine = FK_ENGINE_TC
+        Bw = args.batch_per_gpu
+        sampler_w = FastAutoregressiveSampler(cond, Bw, seed=99, sample_offset=rank * Bw)
+        opt = Adam(lr=1e-3, beta_1=0.9, beta_2=0.9)
+
+        def adam_step():
+            sigma = sampler_w.next_device()
+            eloc = obs.local_values_device(model, sigma)
+            stats = obs.last_stats.clone()
+            if world > 1:
+                dist.all_reduce(stats)
+            mean = torch.complex(stats[0], stats[1]) / stats[3]
+            y = (torch.conj(eloc - mean) / (Bw * world)).to(torch.complex64)
+            grad = net.grad_weighted(net.to_sigma(sigma), y, engine=FK_ENGINE_TC) / float(Bw)
+            if world > 1:
+                dist.all_reduce(grad)
+            opt.step(machine.flat_params_device(), grad)
+            machine.params_updated()
+            machine.device_net()
+
+        for _ in range(2):
+            adam_step()
+        adam_ms = timed(adam_step, 2) / 2
+        adam = {'ms_per_step': adam_ms, 'samples_per_s': Bw * world / (adam_ms * 1e-3), 'batch_per_gpu': Bw, 'scaling': 'weak',
+                'engines': 'fp16 tensor-core sampler, local energy and gradient; Adam(beta 0.9, 0.9)'}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     pk = peaks()
+    peak_tf = pk['bf16_sustained'] or pk['bf16']
     ms_per_step = total_ms / args.steps
-    value = B * world / (ms_per_step * 1e-3)
-    n_conn = conn_count[0]                       # sum_b (1 + n_conn_b) on this rank
-    eloc_ms = float(np.min(phase_ms['eloc']))
-    flops_eloc = n_conn * F_FWD                   # algorithmic: (1 + n_conn) * F_fwd per sample, SURVEY 8(d)
-    achieved_tf = flops_eloc / (eloc_ms * 1e-3) / 1e12
+    value = GB / (ms_per_step * 1e-3)
+    fast_step = fast_ms / args.steps
+    flops_eloc = n_conn * F_FWD                   # algorithmic: (1 + n_conn) * F_fwd per sample, SURVEY 8(d), this rank's share
+    eloc_exact_ms, eloc_fast_ms = phases['exact']['eloc'], phases['fast']['eloc']
+    tf_exact = flops_eloc / (eloc_exact_ms * 1e-3) / 1e12
+    tf_fast = flops_eloc / (eloc_fast_ms * 1e-3) / 1e12
+    P = net.num_params
+    Kg = (P + world - 1) // world
+    nt = (2 * GB + 255) // 256
+    gram_flops = 2.0 * (nt * (nt + 1) / 2) * 65536 * Kg          # computed upper block triangle, this rank's parameter slice
+    gram_ms = phases['exact'].get('sr_gram')
     line = {
-        'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
-        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f16' if args.engine == 'tc' else 'f32', 'data': 'synthetic',
+        'metric': METRIC, 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps, 'warmup': warm,
+        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'f16 hi+lo split (22-bit) forward, f16 Jacobian, bf16 Gram, f64 solve', 'data': 'synthetic',
         'config': workload_config(args, world),
-        'phases_ms': {k: float(np.min(v)) for k, v in phase_ms.items()},
-        'sampling_samples_per_s': B * world / (float(np.min(phase_ms['sample'])) * 1e-3),
-        'eloc_evals_per_s': B * world / (eloc_ms * 1e-3),
-        'psi_evals_per_s': n_conn * world / (eloc_ms * 1e-3),
+        'value_fast': GB / (fast_step * 1e-3), 'ms_per_step_fast': fast_step,
+        'phases_ms': phases,
+        'sampling_samples_per_s': GB / (phases['exact']['sample'] * 1e-3),
+        'eloc_evals_per_s': GB / (eloc_exact_ms * 1e-3), 'eloc_evals_per_s_fast': GB / (eloc_fast_ms * 1e-3),
+        'psi_evals_per_s': n_conn * world / (eloc_exact_ms * 1e-3), 'psi_evals_per_s_fast': n_conn * world / (eloc_fast_ms * 1e-3),
         'connections_per_sample': n_conn / float(B),
-        'e2e': {'value': B * world / (e2e_ms / args.steps * 1e-3), 'unit': 'samples/s', 'h2d_bytes_per_step': int(h2d[0]),
+        'e2e': {'value': GB / (e2e_ms / args.steps * 1e-3), 'unit': 'samples/s', 'h2d_bytes_per_step': int(h2d[0]),
                 'd2h_bytes_per_step': int(d2h[0])},
         'gpu_launches': int(launches),
         'clocks': clk,
-        'roofline': {'bound': 'tensor', 'achieved': achieved_tf, 'peak': pk['bf16_sustained'] or pk['bf16'], 'unit': 'TFLOP/s',
-                     'frac': achieved_tf / (pk['bf16_sustained'] or pk['bf16']),
-                     # dram__bytes_read + dram__bytes_write of one tc_forward_kernel launch (65 536 configurations), ncu capture
-                     # profiles/r01_ncu_tc_forward_v10.txt: the kernel lives in shared memory / TMEM, HBM sees the weights once
-                     'traffic': 8863232 if args.engine == 'tc' else None,
-                     'kernel': 'local-energy wave-function evaluations (%s engine)' % args.engine,
+        # dominant kernel of the step: the tc-exact wave-function evaluations of the local energy (tcx_forward_kernel)
+        'roofline': {'bound': 'tensor', 'achieved': tf_exact, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': tf_exact / peak_tf,
+                     # dram__bytes_read + dram__bytes_write of the launch: profiles/r02_ncu_tcx_forward.txt (weights once, spins, E_loc)
+                     'traffic': None,
+                     'kernel': 'tcx_forward_kernel: local-energy wave-function evaluations, 3 tensor-core products per MAC '
+                               '(hi*hi, hi*lo, lo*hi) counted as ONE algorithmic MAC',
                      'peak_source': pk['source'] + ' bf16 sustained (kernel timed inside a long step)',
-                     'flops_per_launch': flops_eloc,
-                     # measured: with 32 output channels per MMA the forward kernel is bounded by the
-                     # shared-memory operand stream (128 B/cycle/SM), not by tensor math; ~300 KB per configuration and block
-                     'smem_roofline': {'bytes_per_cfg_block': 300e3, 'peak_bytes_per_cycle_per_sm': 128,
-                                       'frac': ((n_conn / (eloc_ms * 1e-3)) * 38 * 300e3 / (148 * 128 * 1.965e9)) if args.engine == 'tc' else None}},
+                     'flops_per_launch': flops_eloc, 'launch_ms': eloc_exact_ms,
+                     'fast_engine': {'achieved': tf_fast, 'frac': tf_fast / peak_tf, 'launch_ms': eloc_fast_ms,
+                                     'kernel': 'tc_forward_kernel (fp16 operands)'},
+                     'gram': ({'achieved': gram_flops / (gram_ms * 1e-3) / 1e12, 'frac': gram_flops / (gram_ms * 1e-3) / 1e12 / peak_tf,
+                               'launch_ms': gram_ms, 'flops_per_launch': gram_flops,
+                               'kernel': 'gram2_kernel (cta_group::2 tcgen05, bf16), upper block triangle of the 2B x 2B Gram'}
+                              if gram_ms else None)},
     }
-    if world == 1 and not args.no_sr:
-        # The same step with stochastic reconfiguration instead of Adam (north_star: sample + local energy + SR): per-sample
-        # Jacobians of the 854 k parameters, sample-space Gram (2B x 2B, K = P) as one tensor-core GEMM, Cholesky, update.
-        try:
-            from flowket_b200.optimizers import StochasticReconfiguration
-            sr = StochasticReconfiguration(model, lr=0.01, diag_shift=0.05, sample_space=True, gram_dtype='bf16',
-                                           jacobian_chunk=512)
-            times = []
-            for i in range(3):
-                torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                sigma = sampler.next_device()
-                eloc = obs.local_values_device(model, sigma)
-                sr.step(sigma, eloc)
-                machine.device_net()
-                e1.record()
-                torch.cuda.synchronize()
-                if i > 0:
-                    times.append(e0.elapsed_time(e1))
-            ms = float(np.mean(times))
-            line['sr_step'] = {'ms_per_step': ms, 'samples_per_s': B / (ms * 1e-3), 'sr_update_ms': dict(sr.last_timings_ms),
-                               'solver': 'sample space: delta = X^T (X X^T / B + lambda)^-1 e / B, X = [Re O; Im O] (2B x P), '
-                                         'bf16 Gram / fp32 accumulate, fp64 Cholesky',
-                               'peak_mem_gb': torch.cuda.max_memory_allocated() / 1e9}
-            del sr
-            torch.cuda.empty_cache()
-        except Exception as exc:  # the SR leg must never take the headline line down with it
-            line['sr_step'] = {'error': '%s: %s' % (type(exc).__name__, exc)}
-    if sr_sharded is not None:
-        line['sr_step'] = sr_sharded
+    if adam is not None:
+        line['adam_step_weak'] = adam
     if world == 1 and not args.no_cpu_baseline:
-        cb = cpu_step_rate(args.cpu_batch, 2)
+        reset()
+        cb = cpu_step_rate(args.cpu_batch, args.cpu_repeats, weights=machine.get_weights())
         line['cpu_baseline'] = {'value': cb['value'], 'unit': 'samples/s', 'cores': cb['cores'], 'kind': 'port',
                                 'sampling_samples_per_s': cb['sampling_samples_per_s'], 'eloc_evals_per_s': cb['eloc_evals_per_s'],
-                                'sample': '%d samples of the same workload, best of 2: incremental sampling + E_loc over all '
-                                          'connections + weighted gradient, torch-CPU fp32 oracle port' % args.cpu_batch}
+                                'sr_samples_per_s': cb['sr_samples_per_s'],
+                                'sample': (CPU_SAMPLE % args.cpu_batch) + ', best of %d' % args.cpu_repeats}
+        # accuracy of the device engines on the CPU leg's own samples: E_loc against the fp32 oracle's local values
+        try:
+            reset()
+            last = cb['last']
+            sg = net.to_sigma(last['sigma'])
+            want = torch.as_tensor(last['local_values']).to(sg.device)
+            acc = {}
+            for engine, tag in ((FK_ENGINE_FP32, 'fp32_engine'), (FK_ENGINE_TC_EXACT, 'tc_exact'), (FK_ENGINE_TC, 'tc_fp16')):
+                got, _, _ = net.local_energy(operator.device_desc(), sg, engine=engine, count=False)
+                acc[tag] = float(((got - want).abs().max() / want.abs().max()).item())
+            line['accuracy'] = {'what': 'max_b |E_loc(b) - oracle| / max_b |E_loc| on the %d samples of the CPU leg '
+                                        '(oracle = torch-CPU fp32 restatement)' % args.cpu_batch, 'eloc': acc}
+        except Exception as exc:
+            line['accuracy'] = {'error': '%s: %s' % (type(exc).__name__, exc)}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -421,13 +442,12 @@ def main():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--engine', default=os.environ.get('FK_BENCH_ENGINE', 'tc'), choices=['fp32', 'tc'],
-                    help='tc: tcgen05 engines for sampling, E_loc and the gradient (fp16 operands / fp32 accumulate); '
-                         'fp32: CUDA-core exact engines everywhere')
-    ap.add_argument('--batch-per-gpu', type=int, default=8192)
-    ap.add_argument('--cpu-batch', type=int, default=8)
+    ap.add_argument('--global-batch', type=int, default=8192, help='samples per step, sharded over the GPUs (strong scaling)')
+    ap.add_argument('--batch-per-gpu', type=int, default=8192, help='batch of the secondary weak-scaling Adam step')
+    ap.add_argument('--cpu-batch', type=int, default=64)
+    ap.add_argument('--cpu-repeats', type=int, default=3)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-sr', action='store_true', help='skip the stochastic-reconfiguration variant of the step')
+    ap.add_argument('--no-adam', action='store_true', help='skip the secondary weak-scaling Adam step')
     args = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if not (world == 1 and args.gpus > 1 and args.impl != 'reference'):

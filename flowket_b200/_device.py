@@ -112,21 +112,22 @@ class DeviceNet(object):
                           ws.numel(), _lib.stream_ptr()))
         return (sigma, p0) if return_p0 else sigma
 
-    def local_energy(self, op_desc, sigma, engine=_lib.FK_ENGINE_FP32):
-        """-> (E_loc complex128 [B], stats float64 [4] = (sum Re, sum Im, sum Re^2, count), n_conn)"""
+    def local_energy(self, op_desc, sigma, engine=_lib.FK_ENGINE_FP32, count=True):
+        """-> (E_loc complex128 [B], stats float64 [4] = (sum Re, sum Im, sum Re^2, count), n_conn).
+        count=False: n_conn is None and, on the tensor-core engines, the call never waits for the device."""
         torch = self.torch
         B = sigma.shape[0]
         eloc = torch.empty((B, 2), dtype=torch.float64, device=self.device)
         stats = torch.zeros(4, dtype=torch.float64, device=self.device)
-        n_conn = ctypes.c_int64(0)
+        n_conn = ctypes.c_int64(0) if count else None
         if B:
             nbytes = self.lib.fk_local_energy_workspace_bytes(self.handle, ctypes.byref(op_desc), B, engine)
             ws = self.workspace('eloc', nbytes)
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.fk_local_energy(self.handle, ctypes.byref(op_desc), _ptr(sigma), B, _ptr(eloc),
-                                                    _ptr(stats), ctypes.byref(n_conn), engine, _ptr(ws), ws.numel(),
-                                                    _lib.stream_ptr()))
-        return torch.view_as_complex(eloc), stats, n_conn.value
+                                                    _ptr(stats), ctypes.byref(n_conn) if count else None, engine, _ptr(ws),
+                                                    ws.numel(), _lib.stream_ptr()))
+        return torch.view_as_complex(eloc), stats, (n_conn.value if count else None)
 
     def grad_weighted(self, sigma, y, engine=_lib.FK_ENGINE_FP32):
         """sum_b 2 Re(log psi_b y_b) differentiated w.r.t. the flat parameter vector; y complex64 [B]"""

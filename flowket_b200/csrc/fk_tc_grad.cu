@@ -375,6 +375,7 @@ struct DwArgs2 {
   long long rld, row_base;
   const float* wn_dir;
   const float* wn_coef;
+  int stages;      // operand ring depth (3; 2 in the row mode, whose v_hat cache takes the room)
 };
 
 // address (in elements) of parameter p of row r in the panel-major layout
@@ -384,24 +385,28 @@ __device__ __forceinline__ long long xrow_index(long long rld, long long r, long
 
 // Fused flush of one convolution of a per-sample item: TMEM lane = ci, columns col0 + t*N + co.  Weight-normalised
 // kernels (w = v_hat * s, wrappers.py:123-134): d/dv = (s / |v|) (dw - (dw . v_hat) v_hat), d/dg = (dw . v_hat) * gs.
+// `nflush` warps (all of TMEM lane quadrant 0) share the taps of the convolution; v_hat and the per-channel coefficients of
+// the unit are cached in shared memory (rows padded to N + 4 floats: conflict-free 128-bit reads with lane = ci).
+constexpr int DW_VH_FLOATS = 13824;   // largest unit: V (9 taps) + X (3 taps), 32 x (32 + 4) floats per tap
 template <int N>
-__device__ __forceinline__ void dw_flush_conv_rows(uint32_t tmem, const DwConv& c, const DwArgs2& a, long long row, int lane,
-                                                   float* stage) {
+__device__ __forceinline__ void dw_flush_conv_rows(uint32_t tmem, const DwConv& c, const DwArgs2& a, long long row, int lane, int f,
+                                                   int nflush, float* stage, float* xdot, const float* vhc, const float* cfc) {
+  constexpr int RS = N + 4;
   const bool wn = c.p_g >= 0;
   const bool live = lane < c.cin;
   float dot[N], coef[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) { dot[i] = 0.f; coef[i] = 1.f; }
   if (wn) {
-    for (int t = 0; t < c.ntaps; ++t) {
+    for (int t = f; t < c.ntaps; t += nflush) {
       float v[N];
       if (N == 32) tmem_ld32(tmem + (uint32_t)(c.col0 + t * N), reinterpret_cast<float(&)[32]>(v));
       else tmem_ld16(tmem + (uint32_t)(c.col0 + t * N), reinterpret_cast<float(&)[16]>(v));
       if (live) {
-        const float4* vh = reinterpret_cast<const float4*>(a.wn_dir + c.w_off + ((long long)t * c.cin + lane) * N);
+        const float4* vh = reinterpret_cast<const float4*>(vhc + (t * c.cin + lane) * RS);
 #pragma unroll
         for (int q = 0; q < N / 4; ++q) {
-          const float4 h = __ldg(vh + q);
+          const float4 h = vh[q];
           dot[4 * q] = fmaf(v[4 * q], h.x, dot[4 * q]);
           dot[4 * q + 1] = fmaf(v[4 * q + 1], h.y, dot[4 * q + 1]);
           dot[4 * q + 2] = fmaf(v[4 * q + 2], h.z, dot[4 * q + 2]);
@@ -409,7 +414,7 @@ __device__ __forceinline__ void dw_flush_conv_rows(uint32_t tmem, const DwConv& 
         }
       }
     }
-    // sum over the input channels (lanes) through the transpose buffer: lane co adds column co
+    // sum over the input channels (lanes) through the warp's transpose buffer, then over the flush warps
 #pragma unroll
     for (int q = 0; q < N / 4; ++q)
       *reinterpret_cast<float4*>(stage + lane * 36 + 4 * q) = make_float4(dot[4 * q], dot[4 * q + 1], dot[4 * q + 2], dot[4 * q + 3]);
@@ -417,33 +422,35 @@ __device__ __forceinline__ void dw_flush_conv_rows(uint32_t tmem, const DwConv& 
     float mine = 0.f;
     if (lane < N)
       for (int l = 0; l < 32; ++l) mine += stage[l * 36 + lane];
-    mine *= a.out_scale;
-    __syncwarp();
+    if (lane < N) xdot[f * 32 + lane] = mine;
+    if (nflush > 1) named_sync(3, 32 * nflush); else __syncwarp();
     if (lane < N) {
-      stage[lane] = mine;
-      const float gs = a.wn_coef[(c.op * 2 + 1) * 64 + lane];
-      a.xrows[xrow_index(a.rld, row, c.p_g + lane)] = __float2bfloat16_rn(mine * gs);
+      float tot = 0.f;
+      for (int w = 0; w < nflush; ++w) tot += xdot[w * 32 + lane];
+      tot *= a.out_scale;
+      stage[lane] = tot;
+      if (f == 0) a.xrows[xrow_index(a.rld, row, c.p_g + lane)] = __float2bfloat16_rn(tot * cfc[32 + lane]);
     }
     __syncwarp();
 #pragma unroll
     for (int q = 0; q < N / 4; ++q) {
       const float4 d4 = *reinterpret_cast<const float4*>(stage + 4 * q);
-      const float4 c4 = __ldg(reinterpret_cast<const float4*>(a.wn_coef + (c.op * 2) * 64) + q);
+      const float4 c4 = *reinterpret_cast<const float4*>(cfc + 4 * q);
       dot[4 * q] = d4.x; dot[4 * q + 1] = d4.y; dot[4 * q + 2] = d4.z; dot[4 * q + 3] = d4.w;
       coef[4 * q] = c4.x; coef[4 * q + 1] = c4.y; coef[4 * q + 2] = c4.z; coef[4 * q + 3] = c4.w;
     }
     __syncwarp();
   }
-  for (int t = 0; t < c.ntaps; ++t) {
+  for (int t = f; t < c.ntaps; t += nflush) {
     float v[N];
     if (N == 32) tmem_ld32(tmem + (uint32_t)(c.col0 + t * N), reinterpret_cast<float(&)[32]>(v));
     else tmem_ld16(tmem + (uint32_t)(c.col0 + t * N), reinterpret_cast<float(&)[16]>(v));
     if (!live) continue;
     if (wn) {
-      const float4* vh = reinterpret_cast<const float4*>(a.wn_dir + c.w_off + ((long long)t * c.cin + lane) * N);
+      const float4* vh = reinterpret_cast<const float4*>(vhc + (t * c.cin + lane) * RS);
 #pragma unroll
       for (int q = 0; q < N / 4; ++q) {
-        const float4 h = __ldg(vh + q);
+        const float4 h = vh[q];
         v[4 * q] = coef[4 * q] * (v[4 * q] * a.out_scale - h.x * dot[4 * q]);
         v[4 * q + 1] = coef[4 * q + 1] * (v[4 * q + 1] * a.out_scale - h.y * dot[4 * q + 1]);
         v[4 * q + 2] = coef[4 * q + 2] * (v[4 * q + 2] * a.out_scale - h.z * dot[4 * q + 2]);
@@ -510,6 +517,9 @@ __device__ __forceinline__ void dw_flush_tap(uint32_t taddr, float* dst, int cin
 }
 
 constexpr int DW_STAGES = 3;
+// after the operand ring and the slack rows: barriers (128 B), 3 transpose buffers, cross-warp dots + coefficients, v_hat cache
+constexpr int DW_TAIL_BYTES = 128 + 3 * 4608 + 4 * (192 + 192) + 256;
+constexpr int DW_ROWS_STAGES = 2;
 #ifdef FK_DW_TRACE
 __device__ long long fk_dw_trace_buf[64 * 8];
 #define DWTRACE(i, k) do { if (blockIdx.x == 0 && (i) < 64 && (threadIdx.x & 31) == 0) fk_dw_trace_buf[(i) * 8 + (k)] = clock64(); } while (0)
@@ -517,20 +527,28 @@ __device__ long long fk_dw_trace_buf[64 * 8];
 #define DWTRACE(i, k) do {} while (0)
 #endif
 
-__global__ void __launch_bounds__(128, 1) tc_dw_kernel(DwArgs2 a) {
+__global__ void __launch_bounds__(384, 1) tc_dw_kernel(DwArgs2 a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int xt_bytes = 64 * a.npos;
   const int stage_bytes = 3 * (xt_bytes + DZ_TILE);
-  uint8_t* tail = smem + (size_t)DW_STAGES * stage_bytes + 16 * a.npos * 16;   // slack: M rows 32..127 read past the tile
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);      // full[0..2], empty[3..5], done[6]
+  const int NST = a.stages;
+  uint8_t* tail = smem + (size_t)NST * stage_bytes + 16 * a.npos * 16;   // slack: M rows 32..127 read past the tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);      // full[0..2], empty[3..5], done[6], tfree[7]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 64);
-  float* flush_stage = reinterpret_cast<float*>(tail + 128);   // 32 x 36 floats: transpose buffer of the per-sample flush
+  // flush warps: 0 (always), 4 and 8 (row mode, 384 threads) -- all in TMEM lane quadrant 0 = the input channels
+  const int nflush = blockDim.x >= 288 ? 3 : 1;
+  const int fidx = warp >> 2;
+  const bool is_flush = (warp & 3) == 0 && fidx < nflush;
+  float* flush_stage = reinterpret_cast<float*>(tail + 128) + fidx * 1152;   // 32 x 36 floats per flush warp: transpose buffer
+  float* xdot = reinterpret_cast<float*>(tail + 128 + 3 * 4608);             // [2][3][32] cross-warp partial dots
+  float* cf_s = xdot + 192;                                                   // [3 convs][a[32] | gs[32]]
+  float* vh_s = cf_s + 192;                                                   // v_hat cache of the current unit (row mode)
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[DW_STAGES]), done = smem_u32(&bars[2 * DW_STAGES]);
   if (tid == 32) {
     for (int i = 0; i < DW_STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
     mbar_init(done, 1);
-    mbar_init(smem_u32(&bars[2 * DW_STAGES + 1]), 1);   // tfree
+    mbar_init(smem_u32(&bars[2 * DW_STAGES + 1]), nflush);   // tfree
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -539,7 +557,7 @@ __global__ void __launch_bounds__(128, 1) tc_dw_kernel(DwArgs2 a) {
   }
   {  // the slack region is read as garbage M rows: keep it finite
     uint4* z = reinterpret_cast<uint4*>(smem);
-    const int n16 = (DW_STAGES * stage_bytes + 16 * a.npos * 16) / 16;
+    const int n16 = (NST * stage_bytes + 16 * a.npos * 16) / 16;
     for (int i = tid; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
   }
   fence_proxy_async();
@@ -571,8 +589,8 @@ __global__ void __launch_bounds__(128, 1) tc_dw_kernel(DwArgs2 a) {
         const long long c_beg = (long long)ch * a.cfg_chunk;
         const long long c_end = c_beg + a.cfg_chunk < a.n ? c_beg + a.cfg_chunk : a.n;
         for (long long cfg = c_beg; cfg < c_end; ++cfg) {
-          const int st = (int)(prod_count % DW_STAGES);
-          if (prod_count >= DW_STAGES) { mbar_wait(empty0 + 8 * st, (empty_phase >> st) & 1u); empty_phase ^= 1u << st; }
+          const int st = (int)(prod_count % NST);
+          if (prod_count >= NST) { mbar_wait(empty0 + 8 * st, (empty_phase >> st) & 1u); empty_phase ^= 1u << st; }
           uint8_t* sb = smem + (size_t)st * stage_bytes;
           mbar_expect_tx(full0 + 8 * st, (uint32_t)u.nconv * (xt_bytes + DZ_TILE));
           for (int k = 0; k < u.nconv; ++k) {
@@ -600,7 +618,7 @@ __global__ void __launch_bounds__(128, 1) tc_dw_kernel(DwArgs2 a) {
       tc_fence_after();
       DWTRACE(item_count, 1);
       for (long long cfg = c_beg; cfg < c_end; ++cfg) {
-        const int st = (int)(cons_count % DW_STAGES);
+        const int st = (int)(cons_count % NST);
         mbar_wait(full0 + 8 * st, (full_phase >> st) & 1u); full_phase ^= 1u << st;
         tc_fence_after();
         DWTRACE(item_count, 2);
@@ -630,21 +648,49 @@ __global__ void __launch_bounds__(128, 1) tc_dw_kernel(DwArgs2 a) {
         ++cons_count;
       }
     }
-  } else if (warp == 0) {
-    // ---- flush: warp 0 owns TMEM lanes 0..31 = input channels
+  } else if (is_flush) {
+    // ---- flush: the flush warps own TMEM lanes 0..31 = input channels
     uint32_t done_phase = 0;
     long long fitem = 0;
+    int cur_unit = -1;
+    uint32_t wn_count = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++fitem) {
       const int ui = a.xrows ? item / chunks : item % a.num_units, ch = a.xrows ? item % chunks : item / a.num_units;
       const DwUnit u = a.units[ui];   // by value: the asm memory clobbers / global stores would force reloads
       const long long c_beg = (long long)ch * a.cfg_chunk;
+      if (a.xrows && ui != cur_unit) {   // new unit: refresh the v_hat / coefficient cache (all flush warps together)
+        if (nflush > 1) named_sync(2, 32 * nflush); else __syncwarp();
+        int off = 0;
+        for (int k = 0; k < u.nconv; ++k) {
+          const DwConv& c = u.conv[k];
+          const int rs = c.n + 4, rows = c.ntaps * c.cin;
+          if (c.p_g >= 0) {
+            const int n4 = c.n / 4;
+            for (int e = fidx * 32 + lane; e < rows * n4; e += 32 * nflush) {
+              const int r = e / n4, q = e - r * n4;
+              *reinterpret_cast<float4*>(vh_s + off + r * rs + 4 * q) =
+                  __ldg(reinterpret_cast<const float4*>(a.wn_dir + c.w_off + (long long)r * c.n) + q);
+            }
+            for (int e = fidx * 32 + lane; e < 64; e += 32 * nflush)
+              cf_s[k * 64 + e] = (e & 31) < c.n ? a.wn_coef[(c.op * 2 + (e >> 5)) * 64 + (e & 31)] : 0.f;
+          }
+          off += rows * rs;
+        }
+        if (nflush > 1) named_sync(2, 32 * nflush); else __syncwarp();
+        cur_unit = ui;
+      }
       mbar_wait(done, done_phase); done_phase ^= 1;
       tc_fence_after();
       DWTRACE(fitem, 4);
+      int off = 0;
       for (int k = 0; k < u.nconv; ++k) {
         if (a.xrows) {
-          if (u.conv[k].n == 32) dw_flush_conv_rows<32>(tmem, u.conv[k], a, a.row_base + c_beg, lane, flush_stage);
-          else dw_flush_conv_rows<16>(tmem, u.conv[k], a, a.row_base + c_beg, lane, flush_stage);
+          const DwConv& c = u.conv[k];
+          float* xd = xdot + (wn_count & 1u) * 96;
+          if (c.n == 32) dw_flush_conv_rows<32>(tmem, c, a, a.row_base + c_beg, lane, fidx, nflush, flush_stage, xd, vh_s + off, cf_s + k * 64);
+          else dw_flush_conv_rows<16>(tmem, c, a, a.row_base + c_beg, lane, fidx, nflush, flush_stage, xd, vh_s + off, cf_s + k * 64);
+          if (c.p_g >= 0) ++wn_count;
+          off += c.ntaps * c.cin * (c.n + 4);
           continue;
         }
         const int ntaps = u.conv[k].ntaps, n = u.conv[k].n, col0 = u.conv[k].col0, cin = u.conv[k].cin;
@@ -983,7 +1029,7 @@ int tc_grad_weighted(fk_net* net, const int8_t* sigma, const float* y, int64_t B
   FK_CHECK_CUDA(cudaGetDevice(&dev));
   FK_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const size_t bwd_smem = 2 * (size_t)IMGB_BYTES + (size_t)BWD_NP * 4 * 64 * npos_g + 256;
-  const size_t dw_smem = (size_t)DW_STAGES * 3 * (64 * g.npos + DZ_TILE) + (size_t)16 * g.npos * 16 + 256 + 4608;
+  const size_t dw_smem = (size_t)DW_STAGES * 3 * (64 * g.npos + DZ_TILE) + (size_t)16 * g.npos * 16 + DW_TAIL_BYTES;
   FK_REQUIRE(bwd_smem <= 227 * 1024 && dw_smem <= 227 * 1024, "tensor-core gradient: lattice too large for shared memory");
   FK_CHECK_CUDA(cudaFuncSetAttribute(tc_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem));
   FK_CHECK_CUDA(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem));
@@ -1006,7 +1052,7 @@ int tc_grad_weighted(fk_net* net, const int8_t* sigma, const float* y, int64_t B
     da.geff = geff; da.n = m; da.nb = nb; da.npos = g.npos; da.num_units = 2 * nb;
     da.cfg_chunk = (int)std::max<int64_t>(1, (m + 7) / 8);
     da.row_stride = 0; da.out_scale = 1.f;
-    da.xrows = nullptr; da.rld = 0; da.row_base = 0; da.wn_dir = nullptr; da.wn_coef = nullptr;
+    da.xrows = nullptr; da.rld = 0; da.row_base = 0; da.wn_dir = nullptr; da.wn_coef = nullptr; da.stages = DW_STAGES;
     const int items = da.num_units * (int)((m + da.cfg_chunk - 1) / da.cfg_chunk);
     tc_dw_kernel<<<(unsigned)std::min(items, sms), 128, dw_smem, s>>>(da);
     FK_CHECK_LAUNCH();
@@ -1067,7 +1113,7 @@ int tc_grad_per_sample(fk_net* net, const int8_t* sigma, int64_t B, float* O_re,
   FK_CHECK_CUDA(cudaGetDevice(&dev));
   FK_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const size_t bwd_smem = 2 * (size_t)IMGB_BYTES + (size_t)BWD_NP * 4 * 64 * npos_g + 256;
-  const size_t dw_smem = (size_t)DW_STAGES * 3 * (64 * g.npos + DZ_TILE) + (size_t)16 * g.npos * 16 + 256 + 4608;
+  const size_t dw_smem = (size_t)DW_STAGES * 3 * (64 * g.npos + DZ_TILE) + (size_t)16 * g.npos * 16 + DW_TAIL_BYTES;
   FK_REQUIRE(bwd_smem <= 227 * 1024 && dw_smem <= 227 * 1024, "tensor-core gradient: lattice too large for shared memory");
   FK_CHECK_CUDA(cudaFuncSetAttribute(tc_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem));
   FK_CHECK_CUDA(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem));
@@ -1093,7 +1139,7 @@ int tc_grad_per_sample(fk_net* net, const int8_t* sigma, int64_t B, float* O_re,
       da.dump = base + L.dump; da.dz = base + L.dz; da.units = reinterpret_cast<const DwUnit*>(wb + bwd_units_offset(nb));
       da.geff = geff; da.n = m; da.nb = nb; da.npos = g.npos; da.num_units = 2 * nb;
       da.cfg_chunk = 1; da.row_stride = net->num_eff; da.out_scale = 1.f / seed_scale;
-      da.xrows = nullptr; da.rld = 0; da.row_base = 0; da.wn_dir = nullptr; da.wn_coef = nullptr;
+      da.xrows = nullptr; da.rld = 0; da.row_base = 0; da.wn_dir = nullptr; da.wn_coef = nullptr; da.stages = DW_STAGES;
       const long long items = (long long)da.num_units * m;
       tc_dw_kernel<<<(unsigned)std::min<long long>(items, sms), 128, dw_smem, s>>>(da);
       FK_CHECK_LAUNCH();
@@ -1153,7 +1199,8 @@ int tc_jacobian_rows(fk_net* net, const int8_t* sigma, int64_t B, void* X, int64
   FK_CHECK_CUDA(cudaGetDevice(&dev));
   FK_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const size_t bwd_smem = 2 * (size_t)IMGB_BYTES + (size_t)BWD_NP * 4 * 64 * npos_g + 256;
-  const size_t dw_smem = (size_t)DW_STAGES * 3 * (64 * g.npos + DZ_TILE) + (size_t)16 * g.npos * 16 + 256 + 4608;
+  const size_t dw_smem = (size_t)DW_ROWS_STAGES * 3 * (64 * g.npos + DZ_TILE) + (size_t)16 * g.npos * 16 + DW_TAIL_BYTES +
+                         (size_t)DW_VH_FLOATS * 4;
   FK_REQUIRE(bwd_smem <= 227 * 1024 && dw_smem <= 227 * 1024, "tensor-core gradient: lattice too large for shared memory");
   FK_CHECK_CUDA(cudaFuncSetAttribute(tc_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem));
   FK_CHECK_CUDA(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem));
@@ -1181,8 +1228,9 @@ int tc_jacobian_rows(fk_net* net, const int8_t* sigma, int64_t B, void* X, int64
       da.geff = nullptr; da.n = m; da.nb = nb; da.npos = g.npos; da.num_units = 2 * nb;
       da.cfg_chunk = 1; da.row_stride = 1; da.out_scale = 1.f / seed_scale;
       da.xrows = xr; da.rld = rld; da.row_base = row_base; da.wn_dir = net->d_wn_dir; da.wn_coef = net->d_wn_coef;
+      da.stages = DW_ROWS_STAGES;
       const long long items = (long long)da.num_units * m;
-      tc_dw_kernel<<<(unsigned)std::min<long long>(items, sms), 128, dw_smem, s>>>(da);
+      tc_dw_kernel<<<(unsigned)std::min<long long>(items, sms), 384, dw_smem, s>>>(da);
       FK_CHECK_LAUNCH();
       tc_db_rows_kernel<<<dim3((unsigned)(nb * 4), (unsigned)std::min<int64_t>(m, 64)), 256, 0, s>>>(
           base + L.dz, m, nb, reinterpret_cast<const long long*>(wb + bwd_pboff_offset(nb)), xr, rld, row_base, 1.f / seed_scale);

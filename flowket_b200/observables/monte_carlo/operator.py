@@ -42,13 +42,15 @@ class Observable(BaseObservable):
         self.operator = operator
         self.last_stats = None
         self.last_num_connections = None
+        self.count_connections = True    # False: the device route never reads the connection count back (no host sync)
 
     # ---- device route -------------------------------------------------------------------------------------
     def local_values_device(self, model, configurations):
         """-> complex128 CUDA tensor [B]; also records the fp64 statistics for the multi-GPU allreduce."""
         net = model.machine.device_net()
         sigma = net.to_sigma(configurations)
-        eloc, stats, n_conn = net.local_energy(self.operator.device_desc(), sigma, engine=model.engine)
+        eloc, stats, n_conn = net.local_energy(self.operator.device_desc(), sigma, engine=model.engine,
+                                               count=self.count_connections)
         self.last_stats, self.last_num_connections = stats, n_conn
         return eloc
 
