@@ -65,8 +65,14 @@ def test_sampler_probabilities_multiply_to_psi_squared(engine):
     assert set(np.unique(s.cpu().numpy())) == {-1, 1}
     model.engine = FK_ENGINE_FP32
     lp = model.predict(sigma.cpu().numpy())[:, 0]
-    tol = 2e-3 if engine == 'fp32' else 0.15     # fp16 caches: |d log p| ~ 1e-3 per site, 100 sites
-    assert np.abs(logp - 2.0 * lp.real).max() < tol
+    # fp16 caches: measured max 1.6e-2 / rms 3.6e-3 over 8192 samples of 100 sites (fp32 sampler: 1.2e-5).  As importance
+    # weights |psi|^2 / p_sampler this is a relative spread of 0.4 %: the effective sample size stays at 1 - 1.3e-5.
+    tol = 1e-4 if engine == 'fp32' else 5e-2
+    dlp = np.abs(logp - 2.0 * lp.real)
+    print('MEASURED sampler %s: |sum log p - log |psi|^2|: max %.3e mean %.3e rms %.3e' % (engine, dlp.max(), dlp.mean(), np.sqrt((dlp ** 2).mean())))
+    assert dlp.max() < tol
+    if engine == 'tc':
+        assert np.sqrt((dlp ** 2).mean()) < 1.1e-2
     # Philox shard invariance at full size: two half batches == the full batch
     lo = FastAutoregressiveSampler(cond, B // 2, seed=11, engine=eng).next_device()
     hi = FastAutoregressiveSampler(cond, B // 2, seed=11, sample_offset=B // 2, engine=eng).next_device()
@@ -85,7 +91,11 @@ def test_tc_and_fp32_wave_functions_agree_on_connected_configurations():
     model.engine = FK_ENGINE_TC
     etc = obs.local_values(model, sigma)
     rel = np.abs(etc - e32) / np.abs(e32)
-    assert rel.max() < 5e-2 and abs(etc.mean() - e32.mean()) / abs(e32.mean()) < 2e-3
+    print('MEASURED E_loc tc vs fp32 on 512 samples: per-sample max %.3e mean %.3e; batch mean %.3e; variance %.6f vs %.6f'
+          % (rel.max(), rel.mean(), abs(etc.mean() - e32.mean()) / abs(e32.mean()), etc.real.var(), e32.real.var()))
+    # measured on a B200: 6.8e-3 per sample, 1.0e-4 on the batch mean, +1.0e-1 of 759.5 on the variance of E_loc
+    assert rel.max() < 2e-2 and abs(etc.mean() - e32.mean()) / abs(e32.mean()) < 4e-4
+    assert abs(etc.real.var() - e32.real.var()) / e32.real.var() < 5e-4
 
 
 def test_gradient_linearity_and_per_sample_consistency():
@@ -139,4 +149,5 @@ def test_headline_machine_against_the_oracle():
         print('headline machine, engine %s: log psi rel %.2e, E_loc rel (per sample, max) %.2e, gradient rel %.2e'
               % ((name,) + report[name]))
     assert report['fp32'][0] < 1e-5 and report['fp32'][1] < 1e-4 and report['fp32'][2] < 1e-4
-    assert report['tc'][0] < 2e-3 and report['tc'][1] < 2e-2 and report['tc'][2] < 3e-2
+    # measured: 2.1e-4, 3.8e-3, 7.2e-3
+    assert report['tc'][0] < 7e-4 and report['tc'][1] < 1.2e-2 and report['tc'][2] < 2.2e-2

@@ -1,5 +1,7 @@
-"""Tensor-core (tcgen05, bf16 operands / fp32 accumulation) engine vs the fp32 engine and the fp64 oracle.
-Stated tolerance of the bf16 path (north_star allows a separately stated tolerance): see TOL below."""
+"""Tensor-core (tcgen05, fp16 operands / fp32 accumulation) engines vs the fp32 engine and the fp64 oracle.
+Stated tolerances of the fp16 path (north_star allows a separately stated tolerance): every bound below is <= 3x the
+error measured on a B200 (profiles/r02_tc_measured_errors.txt); the contract-accuracy tensor-core engine (tc-exact) is
+tested in tests/test_gpu_round2.py."""
 import numpy as np
 import pytest
 import torch
@@ -9,8 +11,9 @@ from tests.helpers import make_pair, random_sigma
 
 pytestmark = pytest.mark.gpu
 
-# |log psi_tc - log psi_fp64| <= TOL_ABS + TOL_REL * |log psi|   (bf16 rounding of activations and weights)
-TOL_ABS, TOL_REL = 0.05, 2e-3
+# |log psi_tc - log psi_fp64| <= TOL_ABS + TOL_REL * |log psi|   (fp16 rounding of activations and weights; measured:
+# <= 3.9e-4 |log psi| over the cases below, worst 0.041 at depth 20 with |log psi| ~ 112)
+TOL_ABS, TOL_REL = 2e-3, 1.2e-3
 
 # (12, 12): two M tiles, register-resident residual input (two pipelines); (16, 16): three tiles, one pipeline
 CASES = [((4, 4), 3), ((6, 6), 4), ((10, 10), 5), ((10, 10), 20), ((12, 12), 3), ((12, 12), 10), ((16, 16), 2), ((5, 7), 2),
@@ -46,14 +49,14 @@ def test_tc_local_energy():
     etc = obs.local_values(model, sigma)
     rel = np.abs(etc - e32) / np.abs(e32)
     print('E_loc: max rel |tc - fp32| =', rel.max(), 'mean', rel.mean())
-    assert rel.max() < 5e-2
-    assert abs(etc.mean() - e32.mean()) / abs(e32.mean()) < 5e-3
+    assert rel.max() < 1.2e-2          # measured 3.8e-3
+    assert abs(etc.mean() - e32.mean()) / abs(e32.mean()) < 2e-3
 
 
 @pytest.mark.parametrize('shape,depth,B', [((4, 5), 3, 300), ((10, 10), 5, 200), ((6, 6), 20, 128)])
 def test_tc_sampler_matches_fp32_sampler_given_uniforms(shape, depth, B):
     """Same uniforms -> same spins, except where |p0 - u| is inside the fp16 error of p0 (then the first differing
-    site must be such a near-tie); p0 of the agreeing prefix within 5e-3."""
+    site must be such a near-tie); p0 of the agreeing prefix within 3e-3."""
     from flowket_b200 import FK_ENGINE_TC, FK_ENGINE_FP32
     from flowket_b200.samplers import FastAutoregressiveSampler
     model, cond, spec, params = make_pair('conv2d', shape, depth, 32, seed=31)
@@ -74,10 +77,10 @@ def test_tc_sampler_matches_fp32_sampler_given_uniforms(shape, depth, B):
         worst = max(worst, np.abs(p_got[b, :upto + 1] - p_ref[b, :upto + 1]).max())
         if len(diff):
             n_diff_samples += 1
-            assert abs(p_ref[b, diff[0]] - uf[b, diff[0]]) < 5e-3, (b, diff[0], p_ref[b, diff[0]], uf[b, diff[0]])
+            assert abs(p_ref[b, diff[0]] - uf[b, diff[0]]) < 3e-3, (b, diff[0], p_ref[b, diff[0]], uf[b, diff[0]])
     print('tc sampler', shape, depth, ': samples differing', n_diff_samples, '/', B, ' max |dp0| on agreeing prefix', worst)
-    assert worst < 5e-3
-    assert n_diff_samples <= max(2, 0.15 * B)
+    assert worst < 3e-3                      # measured <= 9.6e-4
+    assert n_diff_samples <= max(2, 0.02 * B)   # measured: 0, 1 and 0 samples
 
 
 def test_tc_sampler_distribution_and_shards():
@@ -103,7 +106,8 @@ def test_tc_sampler_distribution_and_shards():
 
 @pytest.mark.parametrize('shape,depth,B', [((4, 4), 2, 37), ((4, 5), 3, 64), ((6, 6), 5, 130), ((10, 10), 20, 96)])
 def test_tc_gradient_matches_fp32_gradient(shape, depth, B):
-    """tensor-core weighted gradient (fp16 operands, loss-scaled) vs the fp32 engine: stated tolerance 2e-2 in norm"""
+    """tensor-core weighted gradient (fp16 operands, loss-scaled) vs the fp32 engine: stated tolerance 2.5e-2 in norm
+    (measured 8.8e-3 at depth 20), cosine >= 0.99988 (measured 0.99996)"""
     from flowket_b200 import FK_ENGINE_TC, FK_ENGINE_FP32
     model, _, spec, params = make_pair('conv2d', shape, depth, 32, seed=17)
     net = model.machine.device_net()
@@ -126,14 +130,14 @@ def test_tc_gradient_matches_fp32_gradient(shape, depth, B):
         off += n
     print('tc gradient', shape, depth, 'rel err', rel, 'cos', cos, 'worst tensor', worst)
     assert np.isfinite(gtc).all()
-    assert rel < 2e-2 and cos > 0.9995
+    assert rel < 2.5e-2 and cos > 0.99988
 
 
 @pytest.mark.parametrize('shape,depth,B', [((4, 4), 2, 19), ((6, 6), 5, 70), ((10, 10), 20, 24)])
 def test_tc_per_sample_jacobian_matches_fp32(shape, depth, B):
     """tensor-core per-sample Jacobians (rows of O for stochastic reconfiguration) vs the fp32 engine, row by row:
-    stated tolerance: 3e-2 in the Frobenius norm, 2e-2 median / 0.25 worst single row (same kernels and operand precision as
-    the weighted gradient)"""
+    stated tolerance: 3e-2 in the Frobenius norm, 2e-2 median / 0.2 worst single row (measured 1.3e-2, 1.1e-2, 6.6e-2; same
+    kernels and operand precision as the weighted gradient)"""
     from flowket_b200 import FK_ENGINE_TC, FK_ENGINE_FP32
     model, _, spec, params = make_pair('conv2d', shape, depth, 32, seed=23)
     net = model.machine.device_net()
@@ -148,7 +152,7 @@ def test_tc_per_sample_jacobian_matches_fp32(shape, depth, B):
             np.median(rel), np.percentile(rel, 90), rel.max(), fro))
         # single rows can be off by several per cent when an fp16 pre-activation lands on the other side of a relu;
         # the matrix as a whole (what the Gram sees) is tight
-        assert np.median(rel) < 2e-2 and rel.max() < 0.25 and fro < 3e-2, (name, rel.max(), fro)
+        assert np.median(rel) < 2e-2 and rel.max() < 0.2 and fro < 3e-2, (name, rel.max(), fro)
     # the rows must add up to the weighted gradient of the same engine: sum_b 2 Re(y_b O_b)
     rng = np.random.RandomState(2)
     y = (rng.normal(size=B) + 1j * rng.normal(size=B)) / B
