@@ -20,6 +20,10 @@ struct SolverApi {
   cusolverStatus_t (*potrf_buffer)(cusolverDnHandle_t, int, int, double*, int, int*) = nullptr;
   cusolverStatus_t (*potrf)(cusolverDnHandle_t, int, int, double*, int, double*, int, int*) = nullptr;
   cusolverStatus_t (*potrs)(cusolverDnHandle_t, int, int, int, const double*, int, double*, int, int*) = nullptr;
+  // single precision (the factor of fk_sr_solve_mixed)
+  cusolverStatus_t (*spotrf_buffer)(cusolverDnHandle_t, int, int, float*, int, int*) = nullptr;
+  cusolverStatus_t (*spotrf)(cusolverDnHandle_t, int, int, float*, int, float*, int, int*) = nullptr;
+  cusolverStatus_t (*spotrs)(cusolverDnHandle_t, int, int, int, const float*, int, float*, int, int*) = nullptr;
 };
 
 int load_api(SolverApi* api) {
@@ -36,7 +40,11 @@ int load_api(SolverApi* api) {
   api->potrf_buffer = (decltype(api->potrf_buffer))dlsym(api->dl, "cusolverDnDpotrf_bufferSize");
   api->potrf = (decltype(api->potrf))dlsym(api->dl, "cusolverDnDpotrf");
   api->potrs = (decltype(api->potrs))dlsym(api->dl, "cusolverDnDpotrs");
-  FK_REQUIRE(api->create && api->destroy && api->set_stream && api->potrf_buffer && api->potrf && api->potrs,
+  api->spotrf_buffer = (decltype(api->spotrf_buffer))dlsym(api->dl, "cusolverDnSpotrf_bufferSize");
+  api->spotrf = (decltype(api->spotrf))dlsym(api->dl, "cusolverDnSpotrf");
+  api->spotrs = (decltype(api->spotrs))dlsym(api->dl, "cusolverDnSpotrs");
+  FK_REQUIRE(api->create && api->destroy && api->set_stream && api->potrf_buffer && api->potrf && api->potrs &&
+                 api->spotrf_buffer && api->spotrf && api->spotrs,
              "fk_sr_solver_create: libcusolver lacks the dense Cholesky entry points");
   return 0;
 }
@@ -97,5 +105,116 @@ extern "C" int fk_sr_solve(fk_sr_solver* s, double* S, double* rhs, int64_t n, i
   if (info_out) FK_CHECK_CUDA(cudaMemcpyAsync(info_out, info, sizeof(int), cudaMemcpyDeviceToDevice, st));
   rc = s->api.potrs(s->handle, FK_CUBLAS_FILL_MODE_LOWER, (int)n, 1, S, (int)n, rhs, (int)n, info);
   FK_REQUIRE(rc == 0, "fk_sr_solve: cusolverDnDpotrs failed (%d)", rc);
+  return 0;
+}
+
+// ---- mixed precision: fp32 factor + fp64 iterative refinement -----------------------------------------------------
+// The factorisation is 2/3 n^3 flops on the FP64 pipe in fk_sr_solve; the SR matrix S = C G C / B + lambda I has a
+// condition number of (lambda_max + lambda) / lambda ~ 1e4 (measured on the headline machine: eigenvalues 0.05 .. 600),
+// so an fp32 factor is a contraction of ~1e-3 per refinement step and three steps reach fp64 round-off of the
+// residual.  Each step: r = b - S x in fp64 against the untouched fp64 S (one HBM pass, 8 n^2 bytes), d = L^-T L^-1
+// fp32(r), x += d.
+namespace fk {
+
+__global__ void to_f32_kernel(const double* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long i0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 2;
+  const long long step = (long long)gridDim.x * blockDim.x * 2;
+  for (long long i = i0; i + 1 < n; i += step) {
+    const double2 v = *reinterpret_cast<const double2*>(src + i);
+    *reinterpret_cast<float2*>(dst + i) = make_float2((float)v.x, (float)v.y);
+  }
+  if (i0 == 0 && (n & 1)) dst[n - 1] = (float)src[n - 1];
+}
+
+// one warp per row: r_i = b_i - sum_j S_ij x_j  (x == nullptr: r = b); d_i = (float) r_i; norms[slot] += r_i^2
+__global__ void residual_kernel(const double* __restrict__ S, const double* __restrict__ x, const double* __restrict__ b,
+                                long long n, double* __restrict__ r, float* __restrict__ d, double* __restrict__ norm2) {
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  double acc = 0.0;
+  if (x) {
+    const double* srow = S + row * n;
+    if ((n & 1) == 0) {
+      for (long long j = 2 * lane; j < n; j += 64) {
+        const double2 sv = *reinterpret_cast<const double2*>(srow + j);
+        const double2 xv = *reinterpret_cast<const double2*>(x + j);
+        acc += sv.x * xv.x + sv.y * xv.y;
+      }
+    } else {
+      for (long long j = lane; j < n; j += 32) acc += srow[j] * x[j];
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  }
+  if (lane == 0) {
+    const double ri = b[row] - acc;
+    r[row] = ri;
+    d[row] = (float)ri;
+    atomicAdd(norm2, ri * ri);
+  }
+}
+
+__global__ void refine_update_kernel(double* __restrict__ x, const float* __restrict__ d, long long n) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) x[i] += (double)d[i];
+}
+
+}  // namespace fk
+
+static int64_t mixed_align(int64_t v) { return (v + 255) / 256 * 256; }
+
+// workspace: [info 256 B][norms 256 B][L fp32 n*n][potrf scratch][b f64 n][x f64 n][r f64 n][d f32 n]
+extern "C" int64_t fk_sr_solve_mixed_workspace_bytes(fk_sr_solver* s, int64_t n) {
+  if (!s || n <= 0 || n > 2147483647LL) return -1;
+  int lwork = 0;
+  if (s->api.spotrf_buffer(s->handle, FK_CUBLAS_FILL_MODE_LOWER, (int)n, nullptr, (int)n, &lwork) != 0) return -1;
+  return 512 + mixed_align(n * n * 4) + mixed_align((int64_t)lwork * 4) + 3 * mixed_align(n * 8) + mixed_align(n * 4);
+}
+
+extern "C" int fk_sr_solve_mixed(fk_sr_solver* s, const double* S, double* rhs, int64_t n, int refinements, int* info_out,
+                                 double* resid_out, void* ws, int64_t ws_bytes, void* stream) {
+  FK_REQUIRE(s && S && rhs && ws, "fk_sr_solve_mixed: NULL argument");
+  FK_REQUIRE(n > 0 && n <= 2147483647LL, "fk_sr_solve_mixed: bad dimension");
+  FK_REQUIRE(refinements >= 0 && refinements <= 30, "fk_sr_solve_mixed: refinements must be in 0..30");
+  int lwork = 0;
+  FK_REQUIRE(s->api.spotrf_buffer(s->handle, FK_CUBLAS_FILL_MODE_LOWER, (int)n, nullptr, (int)n, &lwork) == 0,
+             "fk_sr_solve_mixed: cusolverDnSpotrf_bufferSize failed");
+  const int64_t need = 512 + mixed_align(n * n * 4) + mixed_align((int64_t)lwork * 4) + 3 * mixed_align(n * 8) + mixed_align(n * 4);
+  FK_REQUIRE(ws_bytes >= need, "fk_sr_solve_mixed: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)need);
+  cudaStream_t st = (cudaStream_t)stream;
+  FK_REQUIRE(s->api.set_stream(s->handle, st) == 0, "fk_sr_solve_mixed: cusolverDnSetStream failed");
+  uint8_t* p = (uint8_t*)ws;
+  int* info = reinterpret_cast<int*>(p);
+  double* norms = reinterpret_cast<double*>(p + 256);         // up to 32 doubles
+  p += 512;
+  float* L = reinterpret_cast<float*>(p); p += mixed_align(n * n * 4);
+  float* work = reinterpret_cast<float*>(p); p += mixed_align((int64_t)lwork * 4);
+  double* b = reinterpret_cast<double*>(p); p += mixed_align(n * 8);
+  double* x = reinterpret_cast<double*>(p); p += mixed_align(n * 8);
+  double* r = reinterpret_cast<double*>(p); p += mixed_align(n * 8);
+  float* d = reinterpret_cast<float*>(p);
+  FK_CHECK_CUDA(cudaMemsetAsync(norms, 0, 256, st));
+  FK_CHECK_CUDA(cudaMemcpyAsync(b, rhs, n * 8, cudaMemcpyDeviceToDevice, st));
+  FK_CHECK_CUDA(cudaMemsetAsync(x, 0, n * 8, st));
+  fk::to_f32_kernel<<<148 * 8, 256, 0, st>>>(S, L, n * n);
+  FK_CHECK_LAUNCH();
+  cusolverStatus_t rc = s->api.spotrf(s->handle, FK_CUBLAS_FILL_MODE_LOWER, (int)n, L, (int)n, work, lwork, info);
+  FK_REQUIRE(rc == 0, "fk_sr_solve_mixed: cusolverDnSpotrf failed (%d)", rc);
+  if (info_out) FK_CHECK_CUDA(cudaMemcpyAsync(info_out, info, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  const unsigned row_blocks = (unsigned)((n + 7) / 8);
+  for (int k = 0; k <= refinements; ++k) {
+    fk::residual_kernel<<<row_blocks, 256, 0, st>>>(S, k == 0 ? nullptr : x, b, n, r, d, norms + k);
+    FK_CHECK_LAUNCH();
+    rc = s->api.spotrs(s->handle, FK_CUBLAS_FILL_MODE_LOWER, (int)n, 1, L, (int)n, d, (int)n, info);
+    FK_REQUIRE(rc == 0, "fk_sr_solve_mixed: cusolverDnSpotrs failed (%d)", rc);
+    fk::refine_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, d, n);
+    FK_CHECK_LAUNCH();
+  }
+  // the residual of the returned solution
+  fk::residual_kernel<<<row_blocks, 256, 0, st>>>(S, x, b, n, r, d, norms + refinements + 1);
+  FK_CHECK_LAUNCH();
+  if (resid_out)
+    FK_CHECK_CUDA(cudaMemcpyAsync(resid_out, norms, sizeof(double) * (refinements + 2), cudaMemcpyDeviceToDevice, st));
+  FK_CHECK_CUDA(cudaMemcpyAsync(rhs, x, n * 8, cudaMemcpyDeviceToDevice, st));
   return 0;
 }

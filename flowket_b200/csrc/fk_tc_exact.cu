@@ -338,14 +338,10 @@ __global__ void __launch_bounds__(X_NP * 128 + 32 + X_ISSUERS * 32, 1) tcx_forwa
         *reinterpret_cast<uint4*>(bl + (size_t)cg * a.npos * 16) = ql;
       }
     };
-    auto zero_row = [&](int slot) {
-      uint8_t* bh = act + (size_t)slot * slot_bytes + (size_t)pos * 16;
-#pragma unroll
-      for (int cg = 0; cg < 4; ++cg) {
-        *reinterpret_cast<uint4*>(bh + (size_t)cg * a.npos * 16) = make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(bh + tile_bytes + (size_t)cg * a.npos * 16) = make_uint4(0, 0, 0, 0);
-      }
-    };
+    // Padding positions (site < 0) are never written: every slot was zeroed once at kernel start, an epilogue thread
+    // only ever writes its own position, and the padding rows of every tensor are zero -- so they stay zero for the
+    // whole kernel (the per-phase zero stores this replaces were 34 % of the LSU shared-memory wavefronts and all of the
+    // store bank conflicts, profiles/r02_ncu_step_kernels.txt).
     auto load_row = [&](int slot, float* v) {
       const uint8_t* bh = act + (size_t)slot * slot_bytes + (size_t)pos * 16;
 #pragma unroll
@@ -399,8 +395,6 @@ __global__ void __launch_bounds__(X_NP * 128 + 32 + X_ISSUERS * 32, 1) tcx_forwa
 #pragma unroll
             for (int i = 0; i < 32; ++i) x[i] = fmaxf((x[i] + y[i]) * X_WINV, 0.f);
             store_row(d.x1, x);
-          } else {
-            zero_row(d.x1);
           }
           tmem_ld32x2(tm + 64, x, y);
           if (site >= 0) {
@@ -415,9 +409,6 @@ __global__ void __launch_bounds__(X_NP * 128 + 32 + X_ISSUERS * 32, 1) tcx_forwa
 #pragma unroll
             for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.f);
             store_row(d.out_a, x);
-          } else {
-            if (d.out_r >= 0) zero_row(d.out_r);
-            zero_row(d.out_a);
           }
         }
         fence_proxy_async();
@@ -439,8 +430,6 @@ __global__ void __launch_bounds__(X_NP * 128 + 32 + X_ISSUERS * 32, 1) tcx_forwa
               c[16 + i] = fmaxf((y[i] + y[16 + i]) * X_WINV, 0.f);
             }
             store_row(d.c, c);
-          } else {
-            zero_row(d.c);
           }
         }
         fence_proxy_async();
@@ -469,8 +458,6 @@ __global__ void __launch_bounds__(X_NP * 128 + 32 + X_ISSUERS * 32, 1) tcx_forwa
 #pragma unroll
               for (int i = 0; i < 32; ++i) hres[i] = x[i];
             }
-          } else {
-            zero_row(d.out_h);
           }
         }
         fence_proxy_async();

@@ -12,7 +12,8 @@ stage is a call into the C ABI:
                           panel-major layout the Gram kernel's TMA boxes want (no fp32 copy of X ever exists)
     fk_sr_gram_xxt        hand-written cta_group::2 tcgen05 GEMM, upper block triangle + mirror
     fk_sr_centre_shift    S = C G C / B + lambda I in fp64
-    fk_sr_solve           fp64 Cholesky + triangular solves (cuSOLVER behind the ABI)
+    fk_sr_solve_mixed     fp32 Cholesky factor + fp64 iterative refinement (cuSOLVER potrf/potrs behind the ABI; residuals
+                          and updates are this library's kernels); `solver='fp64'` selects the plain fp64 fk_sr_solve
     fk_sr_xt_w            delta = X^T (C w), one pass over X at HBM speed
 
 Sharded over the ranks of torch.distributed: each rank produces the rows of its own samples; ONE all-to-all
@@ -32,12 +33,15 @@ def _ptr(t):
 
 
 class DeviceSampleSpaceSR(object):
-    def __init__(self, net, diag_shift):
+    def __init__(self, net, diag_shift, solver='mixed', refinements=2):
         import torch
         self.torch = torch
         self.net = net
         self.lib = net.lib
         self.diag_shift = float(diag_shift)
+        self.solver = solver                 # 'mixed': fp32 factor + fp64 refinement;  'fp64': fp64 factor
+        self.refinements = int(refinements)   # measured at n = 16384: 2.6e-6 -> 8e-12 -> 3e-15 relative residual
+        self.refinement_tol = 1e-8           # |S x - rhs| / |rhs| the refined solution must reach (checked in read_timings)
         self._solver = None
         self.timings_ms = {}
 
@@ -144,14 +148,20 @@ class DeviceSampleSpaceSR(object):
         rhs = rhs.contiguous()
         info = torch.zeros(1, dtype=torch.int32, device=dev)
         solver = self._solver_handle()
-        sws_b = lib.fk_sr_solve_workspace_bytes(solver, R)
+        mixed = self.solver == 'mixed'
+        sws_b = lib.fk_sr_solve_mixed_workspace_bytes(solver, R) if mixed else lib.fk_sr_solve_workspace_bytes(solver, R)
         if sws_b < 0:
             raise _lib.FlowketB200Error('fk_sr_solve_workspace_bytes failed')
         sws = net.workspace('sr_solve_ws', sws_b)
+        resid = torch.zeros(self.refinements + 2, dtype=torch.float64, device=dev) if mixed else None
         with torch.cuda.device(dev):
             _lib.check(lib.fk_sr_centre_shift(_ptr(G), R, R, world, self.diag_shift, _ptr(S), _ptr(cws), cws.numel(), stream))
             ev[4].record()
-            _lib.check(lib.fk_sr_solve(solver, _ptr(S), _ptr(rhs), R, _ptr(info), _ptr(sws), sws.numel(), stream))
+            if mixed:
+                _lib.check(lib.fk_sr_solve_mixed(solver, _ptr(S), _ptr(rhs), R, self.refinements, _ptr(info), _ptr(resid),
+                                                 _ptr(sws), sws.numel(), stream))
+            else:
+                _lib.check(lib.fk_sr_solve(solver, _ptr(S), _ptr(rhs), R, _ptr(info), _ptr(sws), sws.numel(), stream))
         ev[5].record()
         # ---- delta = X^T (C w): centre w per half, one pass over the parameter slice, gather the slices
         w = rhs.view(world, 2, Bl)
@@ -170,6 +180,7 @@ class DeviceSampleSpaceSR(object):
         ev[6].record()
         self._events = ev
         self._info = info
+        self._resid = resid
         return delta
 
     def read_timings(self):
@@ -179,4 +190,11 @@ class DeviceSampleSpaceSR(object):
         self.timings_ms = {n: ev[i].elapsed_time(ev[i + 1]) for i, n in enumerate(names)}
         self.timings_ms['solve'] = sum(self.timings_ms[n] for n in names[1:])
         self.potrf_info = int(self._info.item())
+        if self._resid is not None and self.potrf_info == 0:
+            r2 = self._resid.cpu().numpy()
+            self.refinement_residuals = list(np.sqrt(r2[1:] / r2[0])) if r2[0] > 0 else [0.0]
+            if not self.refinement_residuals[-1] < self.refinement_tol:
+                raise RuntimeError('sample-space SR: iterative refinement of the fp32 Cholesky solve stalled at a relative '
+                                   'residual of %.2e (history %s); use solver="fp64"'
+                                   % (self.refinement_residuals[-1], ['%.1e' % v for v in self.refinement_residuals]))
         return self.timings_ms

@@ -368,8 +368,9 @@ class StochasticReconfiguration(_SRBase):
     `sample_space=None` picks the sample-space form when P > 2B."""
 
     def __init__(self, model, sample_space=None, gram_dtype='bf16', jacobian_chunk=1024, shared_cholesky=False,
-                 device_pipeline=True, read_timings=True, **kwargs):
+                 device_pipeline=True, read_timings=True, solver='mixed', **kwargs):
         super(StochasticReconfiguration, self).__init__(model, **kwargs)
+        self.solver = solver                     # device pipeline: 'mixed' (fp32 Cholesky + fp64 refinement) or 'fp64'
         self.device_pipeline = device_pipeline   # False: the torch route below (fp32 rows, torch.mm Gram) -- kept as a cross-check
         self.read_timings = read_timings         # False: no synchronise after the update (timings / potrf status unread)
         self.shared_cholesky = shared_cholesky     # distributed sample-space solve: share the Cholesky between the ranks
@@ -412,7 +413,8 @@ class StochasticReconfiguration(_SRBase):
         if self._jacobian_engine(net) != _lib.FK_ENGINE_TC or not DeviceSampleSpaceSR.supported(net):
             return None
         if getattr(self, '_pipeline', None) is None or self._pipeline.net is not net:
-            self._pipeline = DeviceSampleSpaceSR(net, self.diag_shift)
+            self._pipeline = DeviceSampleSpaceSR(net, self.diag_shift, solver=self.solver)
+        self._pipeline.solver = self.solver
         self._pipeline.diag_shift = float(self.diag_shift)
         return self._pipeline
 

@@ -226,6 +226,31 @@ int fk_sr_solver_destroy(fk_sr_solver_t* solver);
 int64_t fk_sr_solve_workspace_bytes(fk_sr_solver_t* solver, int64_t n);
 int fk_sr_solve(fk_sr_solver_t* solver, double* S, double* rhs, int64_t n, int* info_out, void* ws, int64_t ws_bytes,
                 void* stream);
+/* fk_sr_solve_mixed: the same system with an fp32 Cholesky factor and `refinements` steps of iterative refinement whose
+ * residual is formed in fp64 against S (S is NOT overwritten; rhs is overwritten by the solution).  The SR matrix has a
+ * condition number ~ (lambda_max + diag_shift) / diag_shift ~ 1e4, so each step gains ~3 digits.  resid_out (device,
+ * optional, refinements + 2 doubles) = |rhs - S x_k|^2 for x_0 = 0, after the first solve, ..., of the returned solution. */
+int64_t fk_sr_solve_mixed_workspace_bytes(fk_sr_solver_t* solver, int64_t n);
+int fk_sr_solve_mixed(fk_sr_solver_t* solver, const double* S, double* rhs, int64_t n, int refinements, int* info_out,
+                      double* resid_out, void* ws, int64_t ws_bytes, void* stream);
+
+/* ---- exact enumeration (BASELINE configs[0]; flowket/optimization/exact_variational.py:24-66, exact/utils.py:18-50) ------
+ * State index <-> configuration: bit k of the index is flattened site k, bit 1 = spin +1.
+ * fk_exact_states:      sigma_out[n, num_sites] (int8, +-1) = the states first .. first + n - 1.
+ * fk_exact_index:       index_out[n] = index of each configuration of sigma[n, num_sites].
+ * fk_exact_conn_table:  for the states first .. first + n - 1 the find_conn connections AS INDICES into the 2^N table:
+ *                       index_out[max_conn, n], mel_out[max_conn, n] (slot 0 = the state itself with the diagonal element;
+ *                       same slot rules as fk_find_conn) -- replaces find_conn + binary_array_to_decimal_array
+ *                       (exact_variational.py:31-40) without materialising the configurations.
+ * fk_exact_local_energy: log_psi = the whole table ([2^N] double2, device), index/mel = a [max_conn, n] table;
+ *                       weighted_out[n] double2 = sum_c H exp(conj(l_c) + l_0 - log_norm)  (exact_variational.py:52-55),
+ *                       naive_out[n] double2 (optional) = sum_c H exp(l_c - l_0)           (exact_variational.py:56-58). */
+int fk_exact_states(int64_t first, int64_t n, int num_sites, int8_t* sigma_out, void* stream);
+int fk_exact_index(const int8_t* sigma, int64_t n, int num_sites, int64_t* index_out, void* stream);
+int fk_exact_conn_table(const fk_operator_t* op, int64_t first, int64_t n, int64_t* index_out, double* mel_out,
+                        void* stream);
+int fk_exact_local_energy(const double* log_psi, const int64_t* index, const double* mel, int64_t max_conn, int64_t n,
+                          double log_norm, double* weighted_out, double* naive_out, void* stream);
 
 #ifdef __cplusplus
 }

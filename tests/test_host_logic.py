@@ -172,6 +172,22 @@ def test_sr_algebra_against_pinv():
     assert np.linalg.norm(xt.numpy() - want) / np.linalg.norm(want) < 1e-5
 
 
+def test_sample_space_identity_equals_the_parameter_space_system():
+    """the push-through identity behind the device SR pipeline (optimizers/sample_space_sr.py): with X = [Re Obar ; Im Obar]
+    delta = X^T (X X^T / B + lambda I)^-1 e' / B solves the oracle's P x P real-parameter system exactly, for P > 2B and P < 2B"""
+    from oracle import sr as osr
+    rng = np.random.default_rng(5)
+    for B, P in ((24, 200), (64, 40)):
+        o_re, o_im = rng.normal(size=(B, P)), rng.normal(size=(B, P))
+        eloc = rng.normal(size=B) * 3 - 7 + 1j * rng.normal(size=B)
+        S, F = osr.real_sr_system(o_re, o_im, eloc, 0.05)
+        want = np.linalg.solve(S, F)
+        X = np.concatenate([o_re - o_re.mean(0), o_im - o_im.mean(0)])
+        ec = eloc - eloc.mean()
+        got = X.T @ np.linalg.solve(X @ X.T / B + 0.05 * np.eye(2 * B), np.concatenate([ec.real, ec.imag]) / B)
+        assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-10
+
+
 def test_lncosh_known_answers():
     """tests/test_tensorflow_complex_numbers_ops.py:6-33 of the reference (oracle restatement, complex128)."""
     for z in [2, 3j, 1 + 7j, 10 - 3j, -6]:
