@@ -45,7 +45,8 @@ struct Gram2Args {
   int block_rows;     // rows per row block (the rows of one rank in the sharded step); R when there is one block
   int nkb, ntiles;
   const int* tiles;   // (i << 16) | j in units of 256 rows, j >= i
-  unsigned int* wave_counter;   // arrivals of the CTAs at the wave boundaries (zeroed by gram2_tiles_kernel)
+  unsigned int* wave_counter;   // [0]: arrivals of the CTAs at the wave boundaries, [1]: at the in-tile K checkpoints (zeroed by gram2_tiles_kernel)
+  int sync_kb;                  // k-blocks between K checkpoints inside a full wave (0 = none)
   float scale;
 };
 
@@ -95,7 +96,8 @@ __device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {
 // p, p + npairs, ...), so the 74 tiles in flight are ~9 columns of one band: 8 A panels + 9 B panels serve 74 tiles.
 __global__ void gram2_tiles_kernel(int nt, int sb, int* __restrict__ tiles, unsigned int* __restrict__ wave_counter) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  *wave_counter = 0u;
+  wave_counter[0] = 0u;
+  wave_counter[1] = 0u;
   int n = 0;
   for (int bi = 0; bi < nt; bi += sb)
     for (int j = bi; j < nt; ++j)
@@ -150,7 +152,18 @@ gram2_kernel(const __grid_constant__ CUtensorMap tmap, Gram2Args a) {
         const int tile = a.tiles[t];
         const int rowA = (tile >> 16) * 256 + (int)rank * 128, rowB = (tile & 0xffff) * 256 + (int)rank * 128;
         const int qA = rowA / a.block_rows, rA = rowA % a.block_rows, qB = rowB / a.block_rows, rB = rowB % a.block_rows;
+        const bool full_wave = (long long)(wave + 1) * npairs <= (long long)a.ntiles;
+        const int nsync = a.sync_kb > 0 ? (a.nkb - 1) / a.sync_kb : 0;
         for (int kb = 0; kb < a.nkb; ++kb) {
+          // K checkpoints: the pairs of a wave drift apart while they stream through K (a pair that takes the DRAM misses
+          // falls behind the pairs that hit its lines); re-aligning them every sync_kb k-blocks keeps the shared panels of
+          // the wave inside the L2 window.  Bounded wait, full waves only (performance hint, not a correctness requirement).
+          if (nsync > 0 && full_wave && kb > 0 && kb % a.sync_kb == 0) {
+            atomicAdd(a.wave_counter + 1, 1u);
+            const unsigned int target = (wave * (unsigned int)nsync + (unsigned int)(kb / a.sync_kb)) * gridDim.x;
+            const long long t0 = clock64();
+            while (*reinterpret_cast<volatile unsigned int*>(a.wave_counter + 1) < target && clock64() - t0 < 400000LL) __nanosleep(100);
+          }
           mbar_wait(empty0 + 8 * stage, phase ^ 1u);
           if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * G2_STAGE_BYTES);
           const uint32_t sa = smem0 + stage * G2_STAGE_BYTES;
@@ -393,6 +406,8 @@ extern "C" int fk_sr_gram_xxt(const void* X, int64_t R, int64_t K, int64_t rld, 
   fk::Gram2Args a;
   a.G = G; a.ldg = ldg; a.R = R; a.block_rows = (int)block_rows; a.nkb = (int)((K + fk::G2_BK - 1) / fk::G2_BK); a.ntiles = nt * (nt + 1) / 2; a.tiles = tiles; a.wave_counter = wave_counter;
   a.scale = scale;
+  a.sync_kb = 0;
+  if (const char* e = getenv("FK_GRAM2_SYNC")) a.sync_kb = std::max(0, atoi(e));   // (tuning knob of tests/tools_gram2_prof.py)
   int dev = 0, sms = 148;
   FK_CHECK_CUDA(cudaGetDevice(&dev));
   FK_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

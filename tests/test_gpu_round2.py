@@ -287,10 +287,10 @@ def test_jacobian_rows_bf16_and_device_sr_pipeline(shape, depth, wn, B):
     ref_delta = ref.compute_update(sg, eloc).cpu().numpy()
     perr = np.linalg.norm(got_delta - ref_delta) / np.linalg.norm(ref_delta)
     print('device SR delta vs oracle', shape, depth, wn, derr, 'cos', cos, '; vs the torch route on the same fp16-engine rows', perr)
-    # measured on a B200: 5.6e-2 vs the oracle (the fp16 Jacobian engine's 1e-2 row error amplified by the solve; cos 0.998),
-    # 6e-3 .. 9e-3 vs the torch route
-    assert derr < 0.15 and cos > 0.99
-    assert perr < 2.5e-2
+    # measured on a B200: 5.6e-2 / 9.9e-2 / 6.5e-2 vs the oracle (the fp16 Jacobian engine's 1e-2 row error amplified by the
+    # solve at diag_shift 0.05; cosine 0.998 / 0.995 / 0.998), 1.6e-2 .. 2.4e-2 vs the torch route on the same rows (bf16 storage)
+    assert derr < 0.2 and cos > 0.99
+    assert perr < 5e-2
     # fp64 Cholesky instead of the mixed-precision solve: same update to the refinement tolerance
     sr64 = StochasticReconfiguration(model, diag_shift=0.05, sample_space=True, solver='fp64')
     d64 = sr64.compute_update(sg, eloc).cpu().numpy()
