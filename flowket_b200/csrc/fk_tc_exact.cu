@@ -45,6 +45,7 @@ constexpr int XB_BYTES = 44288;
 constexpr int XIMG_BYTES = XA_BYTES + XB_BYTES;
 constexpr float X_WSCALE = 256.f, X_WINV = 1.f / 256.f;
 constexpr int X_NP = 2, X_SLOTS = 3, X_ISSUERS = 3;
+constexpr int X_EPI = 256;   // epilogue threads per pipeline: TWO per lattice position, 16 channels each (see the kernel header)
 
 struct XPackDesc {
   long long w[5], b[5];  // V, X, XX, Y, H
@@ -137,16 +138,27 @@ __device__ __forceinline__ void tmem_ld32x2(uint32_t taddr, float (&a)[32], floa
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// Thread layout: X_NP pipelines x 128 epilogue threads + 1 producer warp + X_ISSUERS MMA issuer warps (see fk_tc.cu for
-// why dedicated issuer warps).  Barriers: fullA, fullB (weights landed), emptyA, emptyB (X_NP*128 arrivals),
-// mma[X_NP] (tcgen05.commit of the pipeline's current phase), ready[X_NP] (128 arrivals: operand tiles written).
-__global__ void __launch_bounds__(X_NP * 128 + 32 + X_ISSUERS * 32, 1) tcx_forward_kernel(TcxArgs a) {
+// two 16-column TMEM loads (this thread's lane), one wait
+__device__ __forceinline__ void tmem_ld16x2(uint32_t ta, uint32_t tb, float (&a)[16], float (&b)[16]) {
+  tmem_ld16_nowait(ta, a);
+  tmem_ld16_nowait(tb, b);
+  tmem_wait_ld();
+}
+
+// Thread layout: X_NP pipelines x X_EPI epilogue threads + 1 producer warp + X_ISSUERS MMA issuer warps (see fk_tc.cu for
+// why dedicated issuer warps).  A lattice position (TMEM lane) is served by TWO epilogue threads -- thread ltid of the
+// pipeline's first 128 and thread ltid of its second 128 (same TMEM lane quadrant, warp % 4) -- which take channels 0..15
+// and 16..31: the hi/lo split makes this epilogue twice as long as the fp16 engine's, with two pipelines the tensor pipe sat
+// idle 46 % of the time waiting for epilogues (profiles/r02_ncu_step_kernels.txt), and halving the per-thread instruction
+// stream is what shortens them.  Barriers: fullA, fullB (weights landed), emptyA, emptyB (X_NP*X_EPI arrivals),
+// mma[X_NP] (tcgen05.commit of the pipeline's current phase), ready[X_NP] (X_EPI arrivals: operand tiles written).
+__global__ void __launch_bounds__(X_NP * X_EPI + 32 + X_ISSUERS * 32, 1) tcx_forward_kernel(TcxArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int pipe = tid >> 7, ltid = tid & 127;
-  const bool is_producer = warp == X_NP * 4;
-  const bool is_issuer = warp > X_NP * 4;
+  const int pipe = tid / X_EPI, ltid = tid & 127, half = (tid >> 7) & 1;   // half: channels [16 half, 16 half + 16)
+  const bool is_producer = warp == X_NP * (X_EPI / 32);
+  const bool is_issuer = warp > X_NP * (X_EPI / 32);
   const int tile_bytes = 64 * a.npos;          // one fp16 tile: 4 channel groups x npos x 16 B
   const int slot_bytes = 2 * tile_bytes;       // hi tile, lo tile
   uint8_t* wA = smem;
@@ -170,11 +182,11 @@ __global__ void __launch_bounds__(X_NP * 128 + 32 + X_ISSUERS * 32, 1) tcx_forwa
     issued[0] = issued[1] = 0u;
     mbar_init(fullA, 1);
     mbar_init(fullB, 1);
-    mbar_init(emptyA, X_NP * 128);
-    mbar_init(emptyB, X_NP * 128);
+    mbar_init(emptyA, X_NP * X_EPI);
+    mbar_init(emptyB, X_NP * X_EPI);
     for (int p = 0; p < X_NP; ++p) {
       mbar_init(smem_u32(&bars[4 + p]), 1);
-      mbar_init(smem_u32(&bars[6 + p]), 128);
+      mbar_init(smem_u32(&bars[6 + p]), X_EPI);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -215,7 +227,7 @@ __global__ void __launch_bounds__(X_NP * 128 + 32 + X_ISSUERS * 32, 1) tcx_forwa
       __syncwarp();
     }
   } else if (is_issuer) {
-    const int role = __shfl_sync(0xffffffffu, warp - (X_NP * 4 + 1), 0);
+    const int role = __shfl_sync(0xffffffffu, warp - (X_NP * (X_EPI / 32) + 1), 0);
     const uint32_t tile16 = 4u * (uint32_t)a.npos, slot16 = 8u * (uint32_t)a.npos, kstep16 = 2u * (uint32_t)a.npos;
     const uint32_t hi = 8u | (1u << 14);                         // SBO = 8 (x16 B), descriptor version bit 46
     const uint32_t a_lbo = (uint32_t)a.npos << 16;
@@ -313,16 +325,17 @@ __global__ void __launch_bounds__(X_NP * 128 + 32 + X_ISSUERS * 32, 1) tcx_forwa
     const int pos = a.p_first + ltid;
     const int prow = pos / a.P - 2, pcol = pos % a.P - 2;
     const int site = (pcol >= 0 && prow < a.H) ? prow * a.W + pcol : -1;
-    float hres[32];
+    float hres[16];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) hres[i] = 0.f;
+    for (int i = 0; i < 16; ++i) hres[i] = 0.f;
+    const uint32_t tmh = tm + (uint32_t)(16 * half);   // this thread's 16 columns inside a 32-column group
 
-    // v (fp32) -> (hi, lo) fp16 rows of this thread's position in tile pair `slot`
+    // v (fp32, this thread's 16 channels) -> (hi, lo) fp16 rows of this thread's position in tile pair `slot`
     auto store_row = [&](int slot, const float* v) {
-      uint8_t* bh = act + (size_t)slot * slot_bytes + (size_t)pos * 16;
+      uint8_t* bh = act + (size_t)slot * slot_bytes + (size_t)pos * 16 + (size_t)(2 * half) * a.npos * 16;
       uint8_t* bl = bh + tile_bytes;
 #pragma unroll
-      for (int cg = 0; cg < 4; ++cg) {
+      for (int cg = 0; cg < 2; ++cg) {
         uint4 qh, ql;
         float f[8];
         qh.x = pack_h2(v[8 * cg + 0], v[8 * cg + 1]);
@@ -343,9 +356,9 @@ __global__ void __launch_bounds__(X_NP * 128 + 32 + X_ISSUERS * 32, 1) tcx_forwa
     // whole kernel (the per-phase zero stores this replaces were 34 % of the LSU shared-memory wavefronts and all of the
     // store bank conflicts, profiles/r02_ncu_step_kernels.txt).
     auto load_row = [&](int slot, float* v) {
-      const uint8_t* bh = act + (size_t)slot * slot_bytes + (size_t)pos * 16;
+      const uint8_t* bh = act + (size_t)slot * slot_bytes + (size_t)pos * 16 + (size_t)(2 * half) * a.npos * 16;
 #pragma unroll
-      for (int cg = 0; cg < 4; ++cg) {
+      for (int cg = 0; cg < 2; ++cg) {
         float fh[8], fl[8];
         unpack_h8(*reinterpret_cast<const uint4*>(bh + (size_t)cg * a.npos * 16), fh);
         unpack_h8(*reinterpret_cast<const uint4*>(bh + tile_bytes + (size_t)cg * a.npos * 16), fl);
@@ -371,10 +384,10 @@ __global__ void __launch_bounds__(X_NP * 128 + 32 + X_ISSUERS * 32, 1) tcx_forwa
       float sig = (active && site >= 0) ? (float)a.sigma[src * HW + site] : 0.f;
       if (site >= 0 && (site == flip_a || site == flip_b)) sig = -sig;
       {
-        float v[32];
+        float v[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0.f;
-        v[0] = sig;
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        if (half == 0) v[0] = sig;
         store_row(sdesc[0].in_v, v);
       }
       fence_proxy_async();
@@ -389,25 +402,25 @@ __global__ void __launch_bounds__(X_NP * 128 + 32 + X_ISSUERS * 32, 1) tcx_forwa
         tc_fence_after();
         mbar_arrive(emptyA);   // chunk A is no longer read
         {
-          float x[32], y[32];
-          tmem_ld32x2(tm + 0, x, y);
+          float x[16], y[16];
+          tmem_ld16x2(tmh + 0, tmh + 32, x, y);
           if (site >= 0) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = fmaxf((x[i] + y[i]) * X_WINV, 0.f);
+            for (int i = 0; i < 16; ++i) x[i] = fmaxf((x[i] + y[i]) * X_WINV, 0.f);
             store_row(d.x1, x);
           }
-          tmem_ld32x2(tm + 64, x, y);
+          tmem_ld16x2(tmh + 64, tmh + 96, x, y);
           if (site >= 0) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = (x[i] + y[i]) * X_WINV;
+            for (int i = 0; i < 16; ++i) x[i] = (x[i] + y[i]) * X_WINV;
             if (d.out_r >= 0) {
               load_row(d.res_v, y);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) y[i] = fmaxf(y[i] + x[i], 0.f);
+              for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i] + x[i], 0.f);
               store_row(d.out_r, y);
             }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.f);
+            for (int i = 0; i < 16; ++i) x[i] = fmaxf(x[i], 0.f);
             store_row(d.out_a, x);
           }
         }
@@ -415,21 +428,18 @@ __global__ void __launch_bounds__(X_NP * 128 + 32 + X_ISSUERS * 32, 1) tcx_forwa
         tc_fence_before();
         mbar_arrive(rbar);
 
-        // ================= phase 2: the two 1x1 convs -> concat (XX: cols 0..31, Y: cols 32..63; 16 large + 16 small each)
+        // ================= phase 2: the two 1x1 convs -> concat (XX: cols 0..31, Y: cols 32..63; 16 large + 16 small each).
+        // The first thread of a position takes XX = concat channels 0..15, the second Y = channels 16..31.
         mbar_wait(mbar, mma_phase);
         mma_phase ^= 1;
         tc_fence_after();
         {
-          float x[32], y[32];
-          tmem_ld32x2(tm + 0, x, y);
+          float x[16], y[16];
+          tmem_ld16x2(tm + (uint32_t)(32 * half), tm + (uint32_t)(32 * half + 16), x, y);
           if (site >= 0) {
-            float c[32];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              c[i] = fmaxf((x[i] + x[16 + i]) * X_WINV, 0.f);
-              c[16 + i] = fmaxf((y[i] + y[16 + i]) * X_WINV, 0.f);
-            }
-            store_row(d.c, c);
+            for (int i = 0; i < 16; ++i) x[i] = fmaxf((x[i] + y[i]) * X_WINV, 0.f);
+            store_row(d.c, x);
           }
         }
         fence_proxy_async();
@@ -442,21 +452,21 @@ __global__ void __launch_bounds__(X_NP * 128 + 32 + X_ISSUERS * 32, 1) tcx_forwa
         tc_fence_after();
         if (!d.last) mbar_arrive(emptyB);
         {
-          float x[32], y[32];
-          tmem_ld32x2(tm + 0, x, y);
+          float x[16], y[16];
+          tmem_ld16x2(tmh + 0, tmh + 32, x, y);
           if (site >= 0) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = (x[i] + y[i]) * X_WINV;
+            for (int i = 0; i < 16; ++i) x[i] = (x[i] + y[i]) * X_WINV;
             if (d.res_h >= 0) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) x[i] += hres[i];
+              for (int i = 0; i < 16; ++i) x[i] += hres[i];
             }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.f);
+            for (int i = 0; i < 16; ++i) x[i] = fmaxf(x[i], 0.f);
             store_row(d.out_h, x);
             if (d.save_h) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) hres[i] = x[i];
+              for (int i = 0; i < 16; ++i) hres[i] = x[i];
             }
           }
         }
@@ -470,6 +480,7 @@ __global__ void __launch_bounds__(X_NP * 128 + 32 + X_ISSUERS * 32, 1) tcx_forwa
           mma_phase ^= 1;
           tc_fence_after();
           mbar_arrive(emptyB);
+          if (half == 0) {   // 4 real logit columns: the first thread of every position finishes the configuration
           float sre = 0.f, sim = 0.f;
           {
             float v[32];
@@ -515,6 +526,7 @@ __global__ void __launch_bounds__(X_NP * 128 + 32 + X_ISSUERS * 32, 1) tcx_forwa
             }
           }
           named_sync(bar_id, 128);   // `red` is reused by the next configuration
+          }
         }
       }
     }
@@ -627,7 +639,7 @@ int tcx_log_psi(fk_net* net, const int8_t* sigma, int64_t n, float* log_psi_out,
   const long long groups = (n + X_NP - 1) / X_NP;
   const unsigned grid = (unsigned)std::min<long long>(groups, sms);
   FK_CHECK_CUDA(cudaFuncSetAttribute(tcx_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-  tcx_forward_kernel<<<grid, X_NP * 128 + 32 + X_ISSUERS * 32, g.smem_bytes, s>>>(a);
+  tcx_forward_kernel<<<grid, X_NP * X_EPI + 32 + X_ISSUERS * 32, g.smem_bytes, s>>>(a);
   FK_CHECK_LAUNCH();
   return 0;
 }
