@@ -712,6 +712,310 @@ __global__ void __launch_bounds__(384, 1) tc_dw_kernel(DwArgs2 a) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
+// ================================================================================================================
+// Jacobian-row variant of the weight-gradient kernel (fk_jacobian_rows_tc): one configuration per item, its accumulators
+// leave TMEM as one bf16 row of X.  In tc_dw_kernel the MMAs of item i + 1 cannot start before item i has been flushed
+// (one unit fills up to 384 of the 512 TMEM columns, so there is no second accumulator set), and the flush -- two passes
+// over TMEM for the weight-norm transform, by the three warps that own lane quadrant 0 -- took as long as the MMAs
+// (measured with tools/dw_rows_trace.py: 8.9 k + 9.7 k cycles per item).  Here the accumulators are first DRAINED to a
+// shared-memory staging buffer (three warps, ~0.6 k cycles), which frees TMEM for the next item at once; seven worker
+// warps then turn the staged tile into the row -- any warp can read shared memory, TMEM lanes 0..31 only quadrant 0 --
+// while the tensor core already works on the next item.
+//   roles (384 threads): warp 2 producer | warp 1 MMA issuer | warps 0, 4, 8 drainers | warps 3, 5, 6, 7, 9, 10, 11 workers
+//   barriers: full/empty[stage] (operand ring), done (MMAs of the item retired), tfree (TMEM drained, 3 arrivals),
+//             sfull (staging written, 3 arrivals), sfree (staging consumed, 7 arrivals)
+// ================================================================================================================
+constexpr int DWR_WORKERS = 7;
+constexpr int DWR_SLOTS = 12;                            // taps of the largest unit (V: 9 + X: 3)
+constexpr int DWR_STAGING_FLOATS = DWR_SLOTS * 32 * 36;  // [tap slot][ci][36]: rows padded for conflict-free 128-bit access
+// after the operand ring: barriers (128 B) | staging | v_hat cache | coefficients [3][64] | partial dots [2][3][7][32] |
+// per-worker totals [7][3][32]
+constexpr int DWR_TAIL_BYTES = 128 + 4 * (DWR_STAGING_FLOATS + DW_VH_FLOATS + 192 + 2 * 3 * DWR_WORKERS * 32 + DWR_WORKERS * 3 * 32);
+
+__global__ void __launch_bounds__(384, 1) tc_dw_rows_kernel(DwArgs2 a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int xt_bytes = 64 * a.npos;
+  const int stage_bytes = 3 * (xt_bytes + DZ_TILE);
+  const int NST = DW_ROWS_STAGES;
+  // no slack region: the M rows 32..127 of an A tile (channel groups 4..15) read whatever follows the tile -- the other
+  // stage, the staging buffer, the v_hat cache; they only reach TMEM lanes 32..127, which nobody reads
+  uint8_t* tail = smem + (size_t)NST * stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);      // full[0..1], empty[2..3], done[4], tfree[5], sfull[6], sfree[7]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 64);
+  float* stg = reinterpret_cast<float*>(tail + 128);
+  float* vh_s = stg + DWR_STAGING_FLOATS;
+  float* cf_s = vh_s + DW_VH_FLOATS;                        // [3 convs][a[32] | gs[32]]
+  float* xdot = cf_s + 192;                                 // [2 parities][3 convs][workers][32]
+  float* wdot = xdot + 2 * 3 * DWR_WORKERS * 32;            // [workers][3 convs][32]
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2]), done = smem_u32(&bars[4]), tfree = smem_u32(&bars[5]),
+                 sfull = smem_u32(&bars[6]), sfree = smem_u32(&bars[7]);
+  if (tid == 32) {
+    for (int i = 0; i < 2; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+    mbar_init(done, 1);
+    mbar_init(tfree, 3);
+    mbar_init(sfull, 3);
+    mbar_init(sfree, DWR_WORKERS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {  // everything an A tile can alias must be finite-or-harmless and initialised: zero the ring, the staging buffer and the cache
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    const int n16 = NST * stage_bytes / 16;
+    for (int i = tid; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    uint4* z2 = reinterpret_cast<uint4*>(stg);
+    const int m16 = (DWR_STAGING_FLOATS + DW_VH_FLOATS) / 4;
+    for (int i = tid; i < m16; i += blockDim.x) z2[i] = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const size_t dump_cfg_bytes = (size_t)(a.nb * NDUMP + 1) * xt_bytes;
+  const uint64_t adesc0 = make_desc(0, 8, a.npos);
+  const uint64_t bdesc0 = make_desc(0, 8, 128);
+  const long long items = (long long)a.num_units * a.n;    // unit-major: the CTAs in flight write adjacent rows of the same panels
+
+  const int fidx = warp >> 2;
+  const bool is_drain = (warp & 3) == 0;
+  int widx = -1;                                            // worker index 0..6
+  if (warp == 3) widx = 0; else if (warp >= 5 && warp <= 7) widx = warp - 4; else if (warp >= 9) widx = warp - 5;
+
+  if (warp == 2) {
+    // ---- producer: one stage per item
+    if (lane == 0) {
+      uint32_t empty_phase = 0;
+      long long count = 0;
+      for (long long item = blockIdx.x; item < items; item += gridDim.x, ++count) {
+        const DwUnit u = a.units[item / a.n];
+        const long long cfg = item % a.n;
+        const int st = (int)(count % NST);
+        if (count >= NST) { mbar_wait(empty0 + 8 * st, (empty_phase >> st) & 1u); empty_phase ^= 1u << st; }
+        uint8_t* sb = smem + (size_t)st * stage_bytes;
+        mbar_expect_tx(full0 + 8 * st, (uint32_t)u.nconv * (xt_bytes + DZ_TILE));
+        for (int k = 0; k < u.nconv; ++k) {
+          bulk_g2s(smem_u32(sb + (size_t)k * xt_bytes), a.dump + (size_t)cfg * dump_cfg_bytes + (size_t)u.conv[k].x_tile * xt_bytes,
+                   xt_bytes, full0 + 8 * st);
+          bulk_g2s(smem_u32(sb + (size_t)3 * xt_bytes + (size_t)k * DZ_TILE),
+                   a.dz + (((size_t)cfg * a.nb + u.b) * 4 + u.conv[k].dz_tile) * DZ_TILE, DZ_TILE, full0 + 8 * st);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---- MMA issuer (elected lane of the converged warp)
+    uint32_t full_phase = 0;
+    long long count = 0;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x, ++count) {
+      const DwUnit u = a.units[item / a.n];
+      DWTRACE(count, 0);
+      mbar_wait(tfree, (uint32_t)((count & 1) ^ 1));   // accumulators of the previous item drained (passes at once for the first)
+      tc_fence_after();
+      DWTRACE(count, 1);
+      const int st = (int)(count % NST);
+      mbar_wait(full0 + 8 * st, (full_phase >> st) & 1u); full_phase ^= 1u << st;
+      tc_fence_after();
+      DWTRACE(count, 2);
+      if (elect_one()) {
+        const uint32_t sb16 = smem_u32(smem + (size_t)st * stage_bytes) >> 4;
+        for (int k = 0; k < u.nconv; ++k) {
+          const int ntaps = u.conv[k].ntaps, n = u.conv[k].n, col0 = u.conv[k].col0;
+          const uint32_t idesc = make_idesc(n) | (1u << 15) | (1u << 16);   // A and B MN-major
+          const uint32_t x16 = sb16 + (uint32_t)k * (uint32_t)(xt_bytes >> 4);
+          const uint64_t bd0 = bdesc0 + (uint64_t)(sb16 + (uint32_t)(3 * (xt_bytes >> 4)) + (uint32_t)k * (DZ_TILE >> 4) +
+                                                   (uint32_t)u.conv[k].dz_cg * 128u);
+          for (int t = 0; t < ntaps; ++t) {
+            const uint32_t dcol = tmem + (uint32_t)(col0 + t * n);
+            const uint64_t ad0 = adesc0 + (uint64_t)(x16 + (uint32_t)u.conv[k].off[t]);
+            umma_f16(dcol, ad0, bd0, idesc, 0u);
+#pragma unroll
+            for (int ks = 1; ks < 8; ++ks) umma_f16(dcol, ad0 + (uint64_t)(16 * ks), bd0 + (uint64_t)(16 * ks), idesc, 1u);
+          }
+        }
+        umma_commit(empty0 + 8 * st);
+        umma_commit(done);
+      }
+      __syncwarp();
+      DWTRACE(count, 3);
+    }
+  } else if (is_drain) {
+    // ---- drainers (TMEM lane quadrant 0 = the input channels): accumulators -> staging, then TMEM is free
+    long long count = 0;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x, ++count) {
+      const DwUnit u = a.units[item / a.n];
+      mbar_wait(done, (uint32_t)(count & 1));
+      tc_fence_after();
+      mbar_wait(sfree, (uint32_t)((count & 1) ^ 1));   // the workers are through with the previous item's staging
+#ifndef FK_DW_TRACE_WORKER
+      DWTRACE(count, 4);
+#endif
+      int slot = 0;
+      for (int k = 0; k < u.nconv; ++k) {
+        const int ntaps = u.conv[k].ntaps, n = u.conv[k].n, col0 = u.conv[k].col0;
+        for (int t = 0; t < ntaps; ++t, ++slot) {
+          if (slot % 3 != fidx) continue;
+          float* dst = stg + ((size_t)slot * 32 + lane) * 36;
+          if (n == 32) {
+            float v[32];
+            tmem_ld32(tmem + (uint32_t)(col0 + t * 32), v);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          } else {
+            float v[16];
+            tmem_ld16(tmem + (uint32_t)(col0 + t * 16), v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+#ifndef FK_DW_TRACE_WORKER
+      DWTRACE(count, 5);
+#endif
+      if (lane == 0) { mbar_arrive(tfree); mbar_arrive(sfull); }
+    }
+  } else if (widx >= 0) {
+    // ---- workers: staged accumulators -> weight-norm transform -> bf16 row of X
+    long long count = 0;
+    int cur_unit = -1;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x, ++count) {
+      const int ui = (int)(item / a.n);
+      const DwUnit u = a.units[ui];
+      const long long row = a.row_base + item % a.n;
+      if (ui != cur_unit) {   // new unit: refresh the v_hat / coefficient cache (all workers together)
+        named_sync(2, 32 * DWR_WORKERS);
+        int off = 0;
+        for (int k = 0; k < u.nconv; ++k) {
+          const DwConv& c = u.conv[k];
+          const int rs = c.n + 4, rows = c.ntaps * c.cin;
+          if (c.p_g >= 0) {
+            const int n4 = c.n / 4;
+            for (int e = widx * 32 + lane; e < rows * n4; e += 32 * DWR_WORKERS) {
+              const int r = e / n4, q = e - r * n4;
+              *reinterpret_cast<float4*>(vh_s + off + r * rs + 4 * q) =
+                  __ldg(reinterpret_cast<const float4*>(a.wn_dir + c.w_off + (long long)r * c.n) + q);
+            }
+            for (int e = widx * 32 + lane; e < 64; e += 32 * DWR_WORKERS)
+              cf_s[k * 64 + e] = (e & 31) < c.n ? a.wn_coef[(c.op * 2 + (e >> 5)) * 64 + (e & 31)] : 0.f;
+          }
+          off += rows * rs;
+        }
+        named_sync(2, 32 * DWR_WORKERS);
+        cur_unit = ui;
+      }
+      mbar_wait(sfull, (uint32_t)(count & 1));
+      if (widx == 0) DWTRACE(count, 6);
+      // pass 1 (lane = output channel): partial dots dW . v_hat over this worker's taps
+      float* xd = xdot + (size_t)(count & 1) * 3 * DWR_WORKERS * 32;
+      {
+        int slot = 0, off = 0;
+        for (int k = 0; k < u.nconv; ++k) {
+          const DwConv& c = u.conv[k];
+          const int rs = c.n + 4;
+          if (c.p_g >= 0) {
+            float acc = 0.f;
+            if (lane < c.n)
+              for (int t = 0; t < c.ntaps; ++t) {
+                if ((slot + t) % DWR_WORKERS != widx) continue;
+                const float* sp = stg + (size_t)(slot + t) * 32 * 36 + lane;
+                const float* vp = vh_s + off + (size_t)t * c.cin * rs + lane;
+                for (int ci = 0; ci < c.cin; ++ci) acc = fmaf(sp[ci * 36], vp[ci * rs], acc);
+              }
+            xd[(k * DWR_WORKERS + widx) * 32 + lane] = acc;
+          }
+          slot += c.ntaps;
+          off += c.ntaps * c.cin * rs;
+        }
+      }
+#ifdef FK_DW_TRACE_WORKER
+      if (widx == 0) DWTRACE(count, 4);
+#endif
+      named_sync(3, 32 * DWR_WORKERS);
+#ifdef FK_DW_TRACE_WORKER
+      if (widx == 0) DWTRACE(count, 5);
+#endif
+      for (int k = 0; k < u.nconv; ++k) {
+        const DwConv& c = u.conv[k];
+        if (c.p_g < 0) continue;
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < DWR_WORKERS; ++w) tot += xd[(k * DWR_WORKERS + w) * 32 + lane];
+        tot *= a.out_scale;
+        wdot[(widx * 3 + k) * 32 + lane] = tot;
+        if (widx == k % DWR_WORKERS && lane < c.n)
+          a.xrows[xrow_index(a.rld, row, c.p_g + lane)] = __float2bfloat16_rn(tot * cf_s[k * 64 + 32 + lane]);
+      }
+      __syncwarp();
+      // pass 2 (lane = input channel): transform and store this worker's taps
+      {
+        int slot = 0, off = 0;
+        for (int k = 0; k < u.nconv; ++k) {
+          const DwConv& c = u.conv[k];
+          const int rs = c.n + 4;
+          const bool wn = c.p_g >= 0;
+          const float* dk = wdot + (widx * 3 + k) * 32;
+          const float* ck = cf_s + k * 64;
+          for (int t = 0; t < c.ntaps; ++t) {
+            if ((slot + t) % DWR_WORKERS != widx || lane >= c.cin) continue;
+            const float* sp = stg + ((size_t)(slot + t) * 32 + lane) * 36;
+            const float* vp = vh_s + off + ((size_t)t * c.cin + lane) * rs;
+            const long long p0 = c.p_kernel + ((long long)t * c.cin + lane) * c.n;
+            for (int h16 = 0; h16 < c.n / 16; ++h16) {
+              float w[16];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 v4 = *reinterpret_cast<const float4*>(sp + 16 * h16 + 4 * q);
+                if (wn) {
+                  const float4 h4 = *reinterpret_cast<const float4*>(vp + 16 * h16 + 4 * q);
+                  const float4 d4 = *reinterpret_cast<const float4*>(dk + 16 * h16 + 4 * q);
+                  const float4 c4 = *reinterpret_cast<const float4*>(ck + 16 * h16 + 4 * q);
+                  w[4 * q + 0] = c4.x * (v4.x * a.out_scale - h4.x * d4.x);
+                  w[4 * q + 1] = c4.y * (v4.y * a.out_scale - h4.y * d4.y);
+                  w[4 * q + 2] = c4.z * (v4.z * a.out_scale - h4.z * d4.z);
+                  w[4 * q + 3] = c4.w * (v4.w * a.out_scale - h4.w * d4.w);
+                } else {
+                  w[4 * q + 0] = v4.x * a.out_scale; w[4 * q + 1] = v4.y * a.out_scale;
+                  w[4 * q + 2] = v4.z * a.out_scale; w[4 * q + 3] = v4.w * a.out_scale;
+                }
+              }
+              uint4 q0, q1;
+              __nv_bfloat162 b;
+              b = __floats2bfloat162_rn(w[0], w[1]); q0.x = *reinterpret_cast<uint32_t*>(&b);
+              b = __floats2bfloat162_rn(w[2], w[3]); q0.y = *reinterpret_cast<uint32_t*>(&b);
+              b = __floats2bfloat162_rn(w[4], w[5]); q0.z = *reinterpret_cast<uint32_t*>(&b);
+              b = __floats2bfloat162_rn(w[6], w[7]); q0.w = *reinterpret_cast<uint32_t*>(&b);
+              b = __floats2bfloat162_rn(w[8], w[9]); q1.x = *reinterpret_cast<uint32_t*>(&b);
+              b = __floats2bfloat162_rn(w[10], w[11]); q1.y = *reinterpret_cast<uint32_t*>(&b);
+              b = __floats2bfloat162_rn(w[12], w[13]); q1.z = *reinterpret_cast<uint32_t*>(&b);
+              b = __floats2bfloat162_rn(w[14], w[15]); q1.w = *reinterpret_cast<uint32_t*>(&b);
+              uint4* dst = reinterpret_cast<uint4*>(a.xrows + xrow_index(a.rld, row, p0 + 16 * h16));   // a 16-element piece
+#ifdef FK_DW_NOSTORE
+              if (q0.x == 0x12345678u && q1.y == 0x9abcdef0u) { dst[0] = q0; dst[1] = q1; }   // (timing experiment: keep the math alive)
+#else
+              dst[0] = q0;                                                                                // never straddles a panel
+              dst[1] = q1;
+#endif
+            }
+          }
+          slot += c.ntaps;
+          off += c.ntaps * c.cin * rs;
+        }
+      }
+      __syncwarp();
+      if (widx == 0) DWTRACE(count, 7);
+      if (lane == 0) mbar_arrive(sfree);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
 // bias gradients: db[op][co] = sum_{cfg, rows} dz;  grid (nb * 4 dz tiles, splits)
 __global__ void tc_db_kernel(const uint8_t* __restrict__ dz, long long n, int nb, const long long* __restrict__ b_off,
                              float* __restrict__ geff) {
@@ -1199,11 +1503,13 @@ int tc_jacobian_rows(fk_net* net, const int8_t* sigma, int64_t B, void* X, int64
   FK_CHECK_CUDA(cudaGetDevice(&dev));
   FK_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const size_t bwd_smem = 2 * (size_t)IMGB_BYTES + (size_t)BWD_NP * 4 * 64 * npos_g + 256;
-  const size_t dw_smem = (size_t)DW_ROWS_STAGES * 3 * (64 * g.npos + DZ_TILE) + (size_t)16 * g.npos * 16 + DW_TAIL_BYTES +
-                         (size_t)DW_VH_FLOATS * 4;
+  const size_t dw_smem = (size_t)DW_ROWS_STAGES * 3 * (64 * g.npos + DZ_TILE) + DWR_TAIL_BYTES;
   FK_REQUIRE(bwd_smem <= 227 * 1024 && dw_smem <= 227 * 1024, "tensor-core gradient: lattice too large for shared memory");
+  // the garbage M rows of the last A tile read up to 16 channel groups past its start: that must stay inside the allocation
+  FK_REQUIRE((size_t)DW_ROWS_STAGES * 3 * (64 * g.npos + DZ_TILE) - 3 * DZ_TILE - 64 * g.npos + (size_t)16 * g.npos * 16 + 4096 <= dw_smem,
+             "tc_jacobian_rows: operand ring + staging layout does not cover the slack rows");
   FK_CHECK_CUDA(cudaFuncSetAttribute(tc_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem));
-  FK_CHECK_CUDA(cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem));
+  FK_CHECK_CUDA(cudaFuncSetAttribute(tc_dw_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dw_smem));
   const uint8_t* wb = (const uint8_t*)net->d_tc_bwd;
   const float seed_scale = 64.f;
   __nv_bfloat16* xr = (__nv_bfloat16*)X;
@@ -1230,7 +1536,7 @@ int tc_jacobian_rows(fk_net* net, const int8_t* sigma, int64_t B, void* X, int64
       da.xrows = xr; da.rld = rld; da.row_base = row_base; da.wn_dir = net->d_wn_dir; da.wn_coef = net->d_wn_coef;
       da.stages = DW_ROWS_STAGES;
       const long long items = (long long)da.num_units * m;
-      tc_dw_kernel<<<(unsigned)std::min<long long>(items, sms), 384, dw_smem, s>>>(da);
+      tc_dw_rows_kernel<<<(unsigned)std::min<long long>(items, sms), 384, dw_smem, s>>>(da);
       FK_CHECK_LAUNCH();
       tc_db_rows_kernel<<<dim3((unsigned)(nb * 4), (unsigned)std::min<int64_t>(m, 64)), 256, 0, s>>>(
           base + L.dz, m, nb, reinterpret_cast<const long long*>(wb + bwd_pboff_offset(nb)), xr, rld, row_base, 1.f / seed_scale);

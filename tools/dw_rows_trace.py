@@ -22,9 +22,9 @@ buf = (ctypes.c_longlong * (64 * 8))()
 lib.fk_dw_trace_read(buf)
 t = np.array(buf[:], dtype=np.int64).reshape(64, 8)
 t0 = t[0, 0]
-print('item: issuer start | tfree seen | full seen | issued+committed || flusher: done seen | flush end   (cycles since start)')
+print('item: issuer start | tfree seen | full seen | issued+committed || drainer: done+sfree seen | drain end || worker 0: sfull seen | row written   (cycles since start)')
 for i in range(8, 24):
-    print(i, ' '.join('%8d' % (x - t0) for x in t[i, :6]))
+    print(i, ' '.join('%8d' % (x - t0) for x in t[i, :8]))
 d = t[8:60]
 print('means: wait tfree %.0f, wait full %.0f, issue %.0f, issue->done seen %.0f, flush %.0f, item period %.0f' % (
     (d[:, 1] - d[:, 0]).mean(), (d[:, 2] - d[:, 1]).mean(), (d[:, 3] - d[:, 2]).mean(), (d[:, 4] - d[:, 3]).mean(),
