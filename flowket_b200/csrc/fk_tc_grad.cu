@@ -718,9 +718,14 @@ __global__ void __launch_bounds__(384, 1) tc_dw_kernel(DwArgs2 a) {
 // (one unit fills up to 384 of the 512 TMEM columns, so there is no second accumulator set), and the flush -- two passes
 // over TMEM for the weight-norm transform, by the three warps that own lane quadrant 0 -- took as long as the MMAs
 // (measured with tools/dw_rows_trace.py: 8.9 k + 9.7 k cycles per item).  Here the accumulators are first DRAINED to a
-// shared-memory staging buffer (three warps, ~0.6 k cycles), which frees TMEM for the next item at once; seven worker
-// warps then turn the staged tile into the row -- any warp can read shared memory, TMEM lanes 0..31 only quadrant 0 --
-// while the tensor core already works on the next item.
+// shared-memory staging buffer (three warps), which frees TMEM for the next item at once; seven worker warps then turn
+// the staged tile into the row -- any warp can read shared memory, TMEM lanes 0..31 only quadrant 0 -- while the tensor
+// core already works on the next item.  Measured: 125.0 -> 115.8 ms per 8192 samples (Re + Im rows).  The overlap is
+// worth less than the trace suggested because both halves live on the shared-memory data pipe: the MN-major operand
+// fetch of the M = 128 MMAs (of which only the 32 input-channel rows are real) keeps it busy ~8 k cycles per item and
+// starves the workers' loads (their two passes stretch from ~1.5 k to ~14 k cycles, tools/dw_rows_trace.py).  What would
+// help is less operand traffic per configuration -- e.g. four configurations stacked along M and N (block-diagonal
+// product, 2 KB instead of 5 KB per configuration and k-step) -- which needs a different TMEM budget; not built.
 //   roles (384 threads): warp 2 producer | warp 1 MMA issuer | warps 0, 4, 8 drainers | warps 3, 5, 6, 7, 9, 10, 11 workers
 //   barriers: full/empty[stage] (operand ring), done (MMAs of the item retired), tfree (TMEM drained, 3 arrivals),
 //             sfull (staging written, 3 arrivals), sfree (staging consumed, 7 arrivals)
@@ -994,12 +999,8 @@ __global__ void __launch_bounds__(384, 1) tc_dw_rows_kernel(DwArgs2 a) {
               b = __floats2bfloat162_rn(w[12], w[13]); q1.z = *reinterpret_cast<uint32_t*>(&b);
               b = __floats2bfloat162_rn(w[14], w[15]); q1.w = *reinterpret_cast<uint32_t*>(&b);
               uint4* dst = reinterpret_cast<uint4*>(a.xrows + xrow_index(a.rld, row, p0 + 16 * h16));   // a 16-element piece
-#ifdef FK_DW_NOSTORE
-              if (q0.x == 0x12345678u && q1.y == 0x9abcdef0u) { dst[0] = q0; dst[1] = q1; }   // (timing experiment: keep the math alive)
-#else
               dst[0] = q0;                                                                                // never straddles a panel
               dst[1] = q1;
-#endif
             }
           }
           slot += c.ntaps;
