@@ -383,103 +383,7 @@ __device__ __forceinline__ long long xrow_index(long long rld, long long r, long
   return ((p >> 6) * rld + r) * 64 + (p & 63);
 }
 
-// Fused flush of one convolution of a per-sample item: TMEM lane = ci, columns col0 + t*N + co.  Weight-normalised
-// kernels (w = v_hat * s, wrappers.py:123-134): d/dv = (s / |v|) (dw - (dw . v_hat) v_hat), d/dg = (dw . v_hat) * gs.
-// `nflush` warps (all of TMEM lane quadrant 0) share the taps of the convolution; v_hat and the per-channel coefficients of
-// the unit are cached in shared memory (rows padded to N + 4 floats: conflict-free 128-bit reads with lane = ci).
-constexpr int DW_VH_FLOATS = 13824;   // largest unit: V (9 taps) + X (3 taps), 32 x (32 + 4) floats per tap
-template <int N>
-__device__ __forceinline__ void dw_flush_conv_rows(uint32_t tmem, const DwConv& c, const DwArgs2& a, long long row, int lane, int f,
-                                                   int nflush, float* stage, float* xdot, const float* vhc, const float* cfc) {
-  constexpr int RS = N + 4;
-  const bool wn = c.p_g >= 0;
-  const bool live = lane < c.cin;
-  float dot[N], coef[N];
-#pragma unroll
-  for (int i = 0; i < N; ++i) { dot[i] = 0.f; coef[i] = 1.f; }
-  if (wn) {
-    for (int t = f; t < c.ntaps; t += nflush) {
-      float v[N];
-      if (N == 32) tmem_ld32(tmem + (uint32_t)(c.col0 + t * N), reinterpret_cast<float(&)[32]>(v));
-      else tmem_ld16(tmem + (uint32_t)(c.col0 + t * N), reinterpret_cast<float(&)[16]>(v));
-      if (live) {
-        const float4* vh = reinterpret_cast<const float4*>(vhc + (t * c.cin + lane) * RS);
-#pragma unroll
-        for (int q = 0; q < N / 4; ++q) {
-          const float4 h = vh[q];
-          dot[4 * q] = fmaf(v[4 * q], h.x, dot[4 * q]);
-          dot[4 * q + 1] = fmaf(v[4 * q + 1], h.y, dot[4 * q + 1]);
-          dot[4 * q + 2] = fmaf(v[4 * q + 2], h.z, dot[4 * q + 2]);
-          dot[4 * q + 3] = fmaf(v[4 * q + 3], h.w, dot[4 * q + 3]);
-        }
-      }
-    }
-    // sum over the input channels (lanes) through the warp's transpose buffer, then over the flush warps
-#pragma unroll
-    for (int q = 0; q < N / 4; ++q)
-      *reinterpret_cast<float4*>(stage + lane * 36 + 4 * q) = make_float4(dot[4 * q], dot[4 * q + 1], dot[4 * q + 2], dot[4 * q + 3]);
-    __syncwarp();
-    float mine = 0.f;
-    if (lane < N)
-      for (int l = 0; l < 32; ++l) mine += stage[l * 36 + lane];
-    if (lane < N) xdot[f * 32 + lane] = mine;
-    if (nflush > 1) named_sync(3, 32 * nflush); else __syncwarp();
-    if (lane < N) {
-      float tot = 0.f;
-      for (int w = 0; w < nflush; ++w) tot += xdot[w * 32 + lane];
-      tot *= a.out_scale;
-      stage[lane] = tot;
-      if (f == 0) a.xrows[xrow_index(a.rld, row, c.p_g + lane)] = __float2bfloat16_rn(tot * cfc[32 + lane]);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int q = 0; q < N / 4; ++q) {
-      const float4 d4 = *reinterpret_cast<const float4*>(stage + 4 * q);
-      const float4 c4 = *reinterpret_cast<const float4*>(cfc + 4 * q);
-      dot[4 * q] = d4.x; dot[4 * q + 1] = d4.y; dot[4 * q + 2] = d4.z; dot[4 * q + 3] = d4.w;
-      coef[4 * q] = c4.x; coef[4 * q + 1] = c4.y; coef[4 * q + 2] = c4.z; coef[4 * q + 3] = c4.w;
-    }
-    __syncwarp();
-  }
-  for (int t = f; t < c.ntaps; t += nflush) {
-    float v[N];
-    if (N == 32) tmem_ld32(tmem + (uint32_t)(c.col0 + t * N), reinterpret_cast<float(&)[32]>(v));
-    else tmem_ld16(tmem + (uint32_t)(c.col0 + t * N), reinterpret_cast<float(&)[16]>(v));
-    if (!live) continue;
-    if (wn) {
-      const float4* vh = reinterpret_cast<const float4*>(vhc + (t * c.cin + lane) * RS);
-#pragma unroll
-      for (int q = 0; q < N / 4; ++q) {
-        const float4 h = vh[q];
-        v[4 * q] = coef[4 * q] * (v[4 * q] * a.out_scale - h.x * dot[4 * q]);
-        v[4 * q + 1] = coef[4 * q + 1] * (v[4 * q + 1] * a.out_scale - h.y * dot[4 * q + 1]);
-        v[4 * q + 2] = coef[4 * q + 2] * (v[4 * q + 2] * a.out_scale - h.z * dot[4 * q + 2]);
-        v[4 * q + 3] = coef[4 * q + 3] * (v[4 * q + 3] * a.out_scale - h.w * dot[4 * q + 3]);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < N; ++i) v[i] *= a.out_scale;
-    }
-    const long long p0 = c.p_kernel + ((long long)t * c.cin + lane) * N;   // multiple of 16: a 16-element piece never
-#pragma unroll                                                              // straddles a 64-element panel
-    for (int h16 = 0; h16 < N / 16; ++h16) {
-      uint4 q0, q1;
-      const float* w = v + 16 * h16;
-      __nv_bfloat162 b;
-      b = __floats2bfloat162_rn(w[0], w[1]); q0.x = *reinterpret_cast<uint32_t*>(&b);
-      b = __floats2bfloat162_rn(w[2], w[3]); q0.y = *reinterpret_cast<uint32_t*>(&b);
-      b = __floats2bfloat162_rn(w[4], w[5]); q0.z = *reinterpret_cast<uint32_t*>(&b);
-      b = __floats2bfloat162_rn(w[6], w[7]); q0.w = *reinterpret_cast<uint32_t*>(&b);
-      b = __floats2bfloat162_rn(w[8], w[9]); q1.x = *reinterpret_cast<uint32_t*>(&b);
-      b = __floats2bfloat162_rn(w[10], w[11]); q1.y = *reinterpret_cast<uint32_t*>(&b);
-      b = __floats2bfloat162_rn(w[12], w[13]); q1.z = *reinterpret_cast<uint32_t*>(&b);
-      b = __floats2bfloat162_rn(w[14], w[15]); q1.w = *reinterpret_cast<uint32_t*>(&b);
-      uint4* dst = reinterpret_cast<uint4*>(a.xrows + xrow_index(a.rld, row, p0 + 16 * h16));
-      dst[0] = q0;
-      dst[1] = q1;
-    }
-  }
-}
+constexpr int DW_VH_FLOATS = 13824;   // v_hat cache of the largest unit: V (9 taps) + X (3 taps), 32 x (32 + 4) floats per tap (tc_dw_rows_kernel)
 
 // Flush of one tap's (ci, co) accumulator tile: TMEM lane = ci, N columns = co.  Compile-time N keeps the row in registers
 // (a runtime trip count turns v[] into local memory -- measured: 1400 cycles per tap).
@@ -541,9 +445,6 @@ __global__ void __launch_bounds__(384, 1) tc_dw_kernel(DwArgs2 a) {
   const int fidx = warp >> 2;
   const bool is_flush = (warp & 3) == 0 && fidx < nflush;
   float* flush_stage = reinterpret_cast<float*>(tail + 128) + fidx * 1152;   // 32 x 36 floats per flush warp: transpose buffer
-  float* xdot = reinterpret_cast<float*>(tail + 128 + 3 * 4608);             // [2][3][32] cross-warp partial dots
-  float* cf_s = xdot + 192;                                                   // [3 convs][a[32] | gs[32]]
-  float* vh_s = cf_s + 192;                                                   // v_hat cache of the current unit (row mode)
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[DW_STAGES]), done = smem_u32(&bars[2 * DW_STAGES]);
   if (tid == 32) {
     for (int i = 0; i < DW_STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
@@ -652,47 +553,14 @@ __global__ void __launch_bounds__(384, 1) tc_dw_kernel(DwArgs2 a) {
     // ---- flush: the flush warps own TMEM lanes 0..31 = input channels
     uint32_t done_phase = 0;
     long long fitem = 0;
-    int cur_unit = -1;
-    uint32_t wn_count = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++fitem) {
       const int ui = a.xrows ? item / chunks : item % a.num_units, ch = a.xrows ? item % chunks : item / a.num_units;
       const DwUnit u = a.units[ui];   // by value: the asm memory clobbers / global stores would force reloads
       const long long c_beg = (long long)ch * a.cfg_chunk;
-      if (a.xrows && ui != cur_unit) {   // new unit: refresh the v_hat / coefficient cache (all flush warps together)
-        if (nflush > 1) named_sync(2, 32 * nflush); else __syncwarp();
-        int off = 0;
-        for (int k = 0; k < u.nconv; ++k) {
-          const DwConv& c = u.conv[k];
-          const int rs = c.n + 4, rows = c.ntaps * c.cin;
-          if (c.p_g >= 0) {
-            const int n4 = c.n / 4;
-            for (int e = fidx * 32 + lane; e < rows * n4; e += 32 * nflush) {
-              const int r = e / n4, q = e - r * n4;
-              *reinterpret_cast<float4*>(vh_s + off + r * rs + 4 * q) =
-                  __ldg(reinterpret_cast<const float4*>(a.wn_dir + c.w_off + (long long)r * c.n) + q);
-            }
-            for (int e = fidx * 32 + lane; e < 64; e += 32 * nflush)
-              cf_s[k * 64 + e] = (e & 31) < c.n ? a.wn_coef[(c.op * 2 + (e >> 5)) * 64 + (e & 31)] : 0.f;
-          }
-          off += rows * rs;
-        }
-        if (nflush > 1) named_sync(2, 32 * nflush); else __syncwarp();
-        cur_unit = ui;
-      }
       mbar_wait(done, done_phase); done_phase ^= 1;
       tc_fence_after();
       DWTRACE(fitem, 4);
-      int off = 0;
       for (int k = 0; k < u.nconv; ++k) {
-        if (a.xrows) {
-          const DwConv& c = u.conv[k];
-          float* xd = xdot + (wn_count & 1u) * 96;
-          if (c.n == 32) dw_flush_conv_rows<32>(tmem, c, a, a.row_base + c_beg, lane, fidx, nflush, flush_stage, xd, vh_s + off, cf_s + k * 64);
-          else dw_flush_conv_rows<16>(tmem, c, a, a.row_base + c_beg, lane, fidx, nflush, flush_stage, xd, vh_s + off, cf_s + k * 64);
-          if (c.p_g >= 0) ++wn_count;
-          off += c.ntaps * c.cin * (c.n + 4);
-          continue;
-        }
         const int ntaps = u.conv[k].ntaps, n = u.conv[k].n, col0 = u.conv[k].col0, cin = u.conv[k].cin;
         const long long w_off = u.conv[k].w_off;
         for (int t = 0; t < ntaps; ++t) {
