@@ -376,8 +376,13 @@ def run_gpu(args):
         'clocks': clk,
         # dominant kernel of the step: the tc-exact wave-function evaluations of the local energy (tcx_forward_kernel)
         'roofline': {'bound': 'tensor', 'achieved': tf_exact, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': tf_exact / peak_tf,
-                     # dram__bytes_read + dram__bytes_write of the launch: profiles/r02_ncu_tcx_forward.txt (weights once, spins, E_loc)
-                     'traffic': None,
+                     # dram__bytes_read + dram__bytes_write of the work-list launch of this kernel at this batch, from the ncu
+                     # capture profiles/r02_ncu_traffic_B8192.txt (spins, work list, matrix elements, weights once; activations never
+                     # leave shared memory / TMEM).  Only quoted for the configuration the capture was taken on.
+                     'traffic': (13.10e6 + 64e3) if (world == 1 and GB == 8192) else None,
+                     'traffic_source': 'ncu capture of the same launch (profiles/r02_ncu_traffic_B8192.txt); algorithmic operand bytes '
+                                       'move shared memory -> tensor core, not through HBM',
+                     'frac_issued': 3.0 * tf_exact / peak_tf,
                      'kernel': 'tcx_forward_kernel: local-energy wave-function evaluations, 3 tensor-core products per MAC '
                                '(hi*hi, hi*lo, lo*hi) counted as ONE algorithmic MAC',
                      'peak_source': pk['source'] + ' bf16 sustained (kernel timed inside a long step)',

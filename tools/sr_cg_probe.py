@@ -63,3 +63,36 @@ xd = torch.linalg.solve(S, rhs)
 print('CG(1e-6) vs direct:', ((x.double() - xd).norm() / xd.norm()).item())
 ev = torch.linalg.eigvalsh(S[:4096, :4096])
 print('eig range of a 4096 principal block: %.3g .. %.3g' % (ev.min().item(), ev.max().item()))
+
+
+# ---- preconditioned CG: block-Jacobi with the diagonal blocks a rank would own in the sharded step (fp32 Cholesky of each block)
+def pcg(Sd, b, Minv, tol, max_iter=2000):
+    x = torch.zeros_like(b); r = b.clone(); z = Minv(r); p = z.clone(); rz = torch.dot(r, z)
+    r0 = r.norm().item()
+    for it in range(1, max_iter + 1):
+        q = Sd @ p
+        alpha = rz / torch.dot(p, q)
+        x += alpha * p; r -= alpha * q
+        if r.norm().item() <= tol * r0:
+            return x, it
+        z = Minv(r); rz2 = torch.dot(r, z); p = z + (rz2 / rz) * p; rz = rz2
+    return x, max_iter
+
+
+b64 = rhs.double()
+for nblk in (2, 4, 8, 16, 64):
+    bs = R // nblk
+    Ls = [torch.linalg.cholesky(S[i * bs:(i + 1) * bs, i * bs:(i + 1) * bs].float()).double() for i in range(nblk)]
+
+    def Minv(r, Ls=Ls, bs=bs):
+        out = torch.empty_like(r)
+        for i, L in enumerate(Ls):
+            out[i * bs:(i + 1) * bs] = torch.cholesky_solve(r[i * bs:(i + 1) * bs].reshape(-1, 1), L).reshape(-1)
+        return out
+    res = []
+    for tol in (1e-3, 1e-6, 1e-9):
+        x, it = pcg(S, b64, Minv, tol)
+        res.append((tol, it, ((x - xd).norm() / xd.norm()).item()))
+    print('block-Jacobi PCG, %d blocks of %d: ' % (nblk, bs) + ', '.join('tol %.0e: %d its (err %.1e)' % t for t in res), flush=True)
+x, it = pcg(S, b64, lambda r: r / S.diagonal(), 1e-6)
+print('Jacobi PCG: %d its to 1e-6' % it)
