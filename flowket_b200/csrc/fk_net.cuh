@@ -68,6 +68,11 @@ int tcx_supported(const fk_net* net);
 int tcx_prepare(fk_net* net);
 int tcx_pack_weights(fk_net* net, cudaStream_t s);
 int tcx_log_psi(fk_net* net, const int8_t* sigma, int64_t n, float* log_psi_out, cudaStream_t s, const TcWork* work = nullptr);
+// local energy with prefix reuse (row-trimmed connected configurations packed two per tile, fk_tc_exact.cu)
+int tcx_prefix_supported(const fk_net* net);
+int64_t tcx_prefix_workspace_bytes(const fk_net* net, int64_t B, int64_t cap);
+int tcx_local_energy_prefix(fk_net* net, const int8_t* sigma, int64_t B, int64_t cap, const TcWork* work, void* ws, int64_t ws_bytes,
+                            cudaStream_t s);
 
 // tensor-core gradient (fk_tc_grad.cu)
 int tc_grad_supported(const fk_net* net);

@@ -302,7 +302,17 @@ static int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }
 struct ElocLayout {
   int64_t counts, offsets, mel0, melf, logpsi, cfg, engine, total, chunk, engine_bytes;
   int64_t logpsi0, items;
+  int64_t prefix, prefix_bytes, sample_chunk;   // tc-exact with prefix reuse: activation cache + tiles for `sample_chunk` samples
 };
+
+// prefix reuse of the tc-exact local energy (fk_tc_exact.cu) is on unless FK_TCX_PREFIX=0; its cache costs 2.3 MB per sample,
+// so the samples are processed in chunks
+constexpr int64_t XP_SAMPLE_CHUNK = 8192;
+static bool prefix_enabled(const fk_net* net) {
+  const char* e = getenv("FK_TCX_PREFIX");
+  if (e && atoi(e) == 0) return false;
+  return tcx_prefix_supported(net) != 0;
+}
 
 static ElocLayout eloc_layout(const fk_net* net, const fk_operator_t* op, int64_t B, int engine, int64_t ws_bytes) {
   ElocLayout L = {};
@@ -314,6 +324,13 @@ static ElocLayout eloc_layout(const fk_net* net, const fk_operator_t* op, int64_
     L.logpsi0 = o; o = align256(o + 8 * B);
     L.melf = o; o = align256(o + 4 * cap);
     L.items = o; o = align256(o + 8 * cap);
+    L.sample_chunk = B;
+    if (engine == FK_ENGINE_TC_EXACT && prefix_enabled(net)) {
+      L.sample_chunk = std::min<int64_t>(B, XP_SAMPLE_CHUNK);
+      L.prefix = o;
+      L.prefix_bytes = tcx_prefix_workspace_bytes(net, L.sample_chunk, (int64_t)std::max(op->max_conn - 1, 1) * L.sample_chunk);
+      o = align256(o + L.prefix_bytes);
+    }
     L.total = o; L.chunk = cap;
     return L;
   }
@@ -362,6 +379,8 @@ static int local_energy_worklist(fk_net* net, const fk_operator_t* op, const int
   if (engine == FK_ENGINE_TC) {
     if (tc_forward_launch(net, sigma, B, logpsi0, nullptr, nullptr, nullptr, s)) return 1;
     if (tc_forward_launch(net, sigma, cap, nullptr, nullptr, nullptr, nullptr, s, &wk)) return 1;
+  } else if (L.prefix_bytes > 0 && B <= L.sample_chunk) {
+    if (tcx_local_energy_prefix(net, sigma, B, cap, &wk, base + L.prefix, L.prefix_bytes, s)) return 1;
   } else {
     if (tcx_log_psi(net, sigma, B, logpsi0, s)) return 1;
     if (tcx_log_psi(net, sigma, cap, nullptr, s, &wk)) return 1;
@@ -397,7 +416,30 @@ extern "C" int fk_local_energy(fk_net_t* net, const fk_operator_t* op, const int
   FK_REQUIRE(L.total <= ws_bytes, "fk_local_energy: workspace too small (%lld < %lld bytes)", (long long)ws_bytes,
              (long long)L.total);
   char* base = (char*)ws;
-  if (engine != FK_ENGINE_FP32) return local_energy_worklist(net, op, sigma, B, eloc_out, stats_out, n_conn_out, engine, L, base, s);
+  if (engine != FK_ENGINE_FP32) {
+    if (L.prefix_bytes > 0 && B > L.sample_chunk) {
+      // prefix reuse keeps a 2.3 MB activation cache per sample: run the samples in chunks (everything is chunk-local; the
+      // statistics are taken over all samples at the end)
+      int64_t total_conn = 0;
+      for (int64_t b0 = 0; b0 < B; b0 += L.sample_chunk) {
+        const int64_t m = std::min<int64_t>(L.sample_chunk, B - b0);
+        const ElocLayout Lc = eloc_layout(net, op, m, engine, ws_bytes);
+        int64_t nc = 0;
+        if (local_energy_worklist(net, op, sigma + b0 * net->sites, m, eloc_out + 2 * b0, nullptr, n_conn_out ? &nc : nullptr, engine,
+                                  Lc, base, s))
+          return 1;
+        total_conn += nc;
+      }
+      if (n_conn_out) *n_conn_out = total_conn;
+      if (stats_out) {
+        FK_CHECK_CUDA(cudaMemsetAsync(stats_out, 0, 4 * sizeof(double), s));
+        eloc_stats_kernel<<<(unsigned)std::min<int64_t>(64, (B + 255) / 256), 256, 0, s>>>(eloc_out, B, stats_out);
+        FK_CHECK_LAUNCH();
+      }
+      return 0;
+    }
+    return local_energy_worklist(net, op, sigma, B, eloc_out, stats_out, n_conn_out, engine, L, base, s);
+  }
   int* counts = (int*)(base + L.counts);
   long long* offsets = (long long*)(base + L.offsets);
   double* mel0 = (double*)(base + L.mel0);

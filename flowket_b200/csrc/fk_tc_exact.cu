@@ -103,6 +103,30 @@ __global__ void tcx_pack_kernel(const float* __restrict__ weff, const XPackDesc*
   }
 }
 
+// ---- prefix reuse (dependency analysis pinned by oracle/prefix_reuse.py) ----------------------------
+// A connected configuration equals its sample on every lattice row above the first flipped site (row r0), and every
+// convolution of the machine looks up and sideways only, so rows >= r0 can be recomputed from the new spins plus a halo
+// taken from the SAMPLE's own activations: rows r0-2, r0-1 of each block's vertical input (= relu(v') or the residual
+// sum of the previous block) and of its concat tensor, row r0-1 of relu(v'); log psi(sigma') = (the sample's selected
+// log-amplitude terms of rows < r0) + (the recomputed terms of rows >= r0).
+//   dump pass   the ordinary forward over the samples also writes, per block, the (hi, lo) tiles of relu(v'), of the
+//               residual sum and of the concat tensor to `dump` (the cache) and the selected term of every site to `siteterm`;
+//   tile pass   a work item is a TILE holding one or two row-trimmed configurations ("segments"): segment A occupies tile
+//               rows [0, kA) with its halo in the two rows above the MMA range (written by otherwise idle threads),
+//               segment B tile rows [kA + 2, kA + 2 + kB) with its halo in rows kA, kA + 1 (written by the threads that own
+//               those positions instead of their MMA results).  The MMA issue does not change at all -- taps are relative
+//               offsets, a segment is just a translated lattice -- so two configurations share one M = 128 tile.
+struct TcxPrefix {
+  const int2* tiles;            // (work-list index of segment A, of segment B or -1); nullptr: not the tile pass
+  const long long* n_tiles;     // device-side count
+  const uint8_t* cache;         // tile pass: the samples' activation cache
+  const float* rowcum;          // tile pass: [sample][H + 1] float2, sum of the selected terms of rows < r
+  uint8_t* dump;                // dump pass: cache to write (configuration i = sample i); nullptr otherwise
+  float* siteterm;              // dump pass: [sample][sites] float2
+  long long cache_stride;       // bytes per sample = nb * 3 tensors * 2 (hi, lo) * 64 * npos
+  int rcap;                     // tile rows that lie completely inside the MMA range
+};
+
 struct TcxArgs {
   const uint8_t* images;
   const TcBlockDesc* desc;
@@ -111,6 +135,7 @@ struct TcxArgs {
   long long n;
   int H, W, P, nb, npos, p_first, cst_off;
   TcWork wk;   // local-energy work list (see fk_net.cuh)
+  TcxPrefix px;   // prefix reuse (see below); all-null = off
 };
 
 // two 32-column TMEM loads, one wait
@@ -208,7 +233,8 @@ __global__ void __launch_bounds__(X_NP * X_EPI + 32 + X_ISSUERS * 32, 1) tcx_for
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const long long n_items = a.wk.n_dev ? *a.wk.n_dev : a.n;
+  const bool tile_mode = a.px.tiles != nullptr;
+  const long long n_items = tile_mode ? *a.px.n_tiles : (a.wk.n_dev ? *a.wk.n_dev : a.n);
   const long long groups = (n_items + X_NP - 1) / X_NP;
   const long long my_iters = (long long)blockIdx.x < groups ? (groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
@@ -331,9 +357,11 @@ __global__ void __launch_bounds__(X_NP * X_EPI + 32 + X_ISSUERS * 32, 1) tcx_for
     const uint32_t tmh = tm + (uint32_t)(16 * half);   // this thread's 16 columns inside a 32-column group
 
     // v (fp32, this thread's 16 channels) -> (hi, lo) fp16 rows of this thread's position in tile pair `slot`
-    auto store_row = [&](int slot, const float* v) {
+    // `gd` (dump pass): the same (hi, lo) rows also go to the sample's cache tile pair at gd
+    auto store_row = [&](int slot, const float* v, uint8_t* gd = nullptr) {
       uint8_t* bh = act + (size_t)slot * slot_bytes + (size_t)pos * 16 + (size_t)(2 * half) * a.npos * 16;
       uint8_t* bl = bh + tile_bytes;
+      if (gd) gd += (size_t)pos * 16 + (size_t)(2 * half) * a.npos * 16;
 #pragma unroll
       for (int cg = 0; cg < 2; ++cg) {
         uint4 qh, ql;
@@ -349,6 +377,10 @@ __global__ void __launch_bounds__(X_NP * X_EPI + 32 + X_ISSUERS * 32, 1) tcx_for
         ql.w = pack_h2(v[8 * cg + 6] - f[6], v[8 * cg + 7] - f[7]);
         *reinterpret_cast<uint4*>(bh + (size_t)cg * a.npos * 16) = qh;
         *reinterpret_cast<uint4*>(bl + (size_t)cg * a.npos * 16) = ql;
+        if (gd) {
+          *reinterpret_cast<uint4*>(gd + (size_t)cg * a.npos * 16) = qh;
+          *reinterpret_cast<uint4*>(gd + tile_bytes + (size_t)cg * a.npos * 16) = ql;
+        }
       }
     };
     // Padding positions (site < 0) are never written: every slot was zeroed once at kernel start, an epilogue thread
@@ -369,10 +401,260 @@ __global__ void __launch_bounds__(X_NP * X_EPI + 32 + X_ISSUERS * 32, 1) tcx_for
     uint32_t mma_phase = 0;
     long long step = 0;
 
+    if (tile_mode) {
+      // =========================== tile pass of the prefix reuse (see TcxPrefix) ===========================
+      const int W = a.W, H = a.H, P = a.P;
+      const bool real_pos = pcol >= 0 && prow < a.px.rcap;          // a lattice column of a tile row inside the MMA range
+      // idle positions (padding columns, rows past rcap) serve as loaders of segment A's halo, which lies above the MMA
+      // range: idle thread number q < 2 W owns halo row q / W, column q % W
+      int hq = -1;
+      if (!real_pos) {
+        int q = 0;
+        for (int j = 0; j < ltid; ++j) {
+          const int pj = a.p_first + j;
+          const int rj = pj / P - 2, cj = pj % P - 2;
+          q += (cj >= 0 && rj < a.px.rcap) ? 0 : 1;
+        }
+        if (q < 2 * W) hq = q;
+      }
+      const size_t half_off = (size_t)(2 * half) * a.npos * 16;
+      // cached (hi, lo) rows of this thread's 16 channels at natural position lpos of tensor t of block b of sample smp
+      auto halo_fetch = [&](int smp, int b, int t, int lpos, uint4 (&q)[4]) {
+        const uint8_t* g = a.px.cache + (size_t)smp * a.px.cache_stride + (size_t)((b * 3 + t) * 2) * tile_bytes + half_off +
+                           (size_t)lpos * 16;
+        q[0] = __ldg(reinterpret_cast<const uint4*>(g));
+        q[1] = __ldg(reinterpret_cast<const uint4*>(g + (size_t)a.npos * 16));
+        q[2] = __ldg(reinterpret_cast<const uint4*>(g + tile_bytes));
+        q[3] = __ldg(reinterpret_cast<const uint4*>(g + tile_bytes + (size_t)a.npos * 16));
+      };
+      auto halo_put = [&](int slot, int dpos, const uint4 (&q)[4]) {
+        uint8_t* bh = act + (size_t)slot * slot_bytes + (size_t)dpos * 16 + half_off;
+        *reinterpret_cast<uint4*>(bh) = q[0];
+        *reinterpret_cast<uint4*>(bh + (size_t)a.npos * 16) = q[1];
+        *reinterpret_cast<uint4*>(bh + tile_bytes) = q[2];
+        *reinterpret_cast<uint4*>(bh + tile_bytes + (size_t)a.npos * 16) = q[3];
+      };
+      for (long long it = 0; it < my_iters; ++it) {
+        const long long group = it * gridDim.x + blockIdx.x;
+        const long long tix = group * X_NP + pipe;
+        const bool active = tix < n_items;
+        int cfgs[2] = {-1, -1}, smp[2] = {0, 0}, fa[2] = {-1, -1}, fb[2] = {-1, -1}, r0[2] = {0, 0}, kk[2] = {0, 0};
+        if (active) {
+          const int2 t = a.px.tiles[tix];
+          cfgs[0] = t.x; cfgs[1] = t.y;
+        }
+#pragma unroll
+        for (int sgi = 0; sgi < 2; ++sgi)
+          if (cfgs[sgi] >= 0) {
+            const TcWorkItem wi = a.wk.items[cfgs[sgi]];
+            smp[sgi] = wi.sample;
+            fa[sgi] = (int)wi.site_a;
+            fb[sgi] = wi.site_b == 0xffffu ? -1 : (int)wi.site_b;
+            const int ra = fa[sgi] / W, rb = fb[sgi] >= 0 ? fb[sgi] / W : ra;
+            r0[sgi] = ra < rb ? ra : rb;
+            kk[sgi] = H - r0[sgi];
+          }
+        // ---- role of this thread in this tile
+        int seg = -1, lrow = 0;          // seg >= 0: this position is lattice site (lrow, pcol) of segment seg
+        int h_smp = -1, h_row = 0, h_col = 0, h_dst = 0;   // halo duty: write the cached row of sample h_smp to position h_dst
+        if (real_pos && cfgs[0] >= 0) {
+          const int rowB0 = kk[0] + 2;
+          if (prow < kk[0]) { seg = 0; lrow = prow + r0[0]; }
+          else if (cfgs[1] >= 0) {
+            if (prow < rowB0) { h_smp = smp[1]; h_row = r0[1] - 2 + (prow - kk[0]); h_col = pcol; h_dst = pos; }
+            else if (prow < rowB0 + kk[1]) { seg = 1; lrow = prow - rowB0 + r0[1]; }
+          }
+        } else if (hq >= 0 && cfgs[0] >= 0) {
+          h_smp = smp[0]; h_row = r0[0] - 2 + hq / W; h_col = hq % W; h_dst = (hq / W) * P + 2 + h_col;
+        }
+        const bool is_site = seg >= 0;
+        const bool is_halo = h_smp >= 0;
+        const bool halo_zero = is_halo && h_row < 0;               // above the lattice: the zero padding
+        const int h_lpos = (h_row + 2) * P + h_col + 2;
+        const int lsite = is_site ? lrow * W + pcol : -1;
+        float sig = is_site ? (float)a.sigma[(size_t)smp[seg] * HW + lsite] : 0.f;
+        if (is_site && (lsite == fa[seg] || lsite == fb[seg])) sig = -sig;
+        {
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+          if (half == 0) v[0] = sig;
+          if (is_site) store_row(sdesc[0].in_v, v);
+          if (is_halo) {   // the sample's own spins above r0 (exact in fp16: hi = +-1, lo = 0)
+            const float hs = (!halo_zero && half == 0) ? (float)a.sigma[(size_t)h_smp * HW + h_row * W + h_col] : 0.f;
+            uint4 q[4];
+            q[0] = make_uint4(pack_h2(hs, 0.f), 0u, 0u, 0u);
+            q[1] = q[2] = q[3] = make_uint4(0u, 0u, 0u, 0u);
+            halo_put(sdesc[0].in_v, h_dst, q);
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(rbar);
+
+        for (int b = 0; b < a.nb; ++b, ++step) {
+          const TcBlockDesc d = sdesc[b];
+          // ================= phase 1 (halo rows: relu(v') and the residual sum come from the sample's cache)
+          uint4 qa[4], qr[4];
+          if (is_halo && !halo_zero) {
+            halo_fetch(h_smp, b, 0, h_lpos, qa);
+            if (d.out_r >= 0) halo_fetch(h_smp, b, 1, h_lpos, qr);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) qa[i] = qr[i] = make_uint4(0u, 0u, 0u, 0u);
+          }
+          mbar_wait(mbar, mma_phase);
+          mma_phase ^= 1;
+          tc_fence_after();
+          mbar_arrive(emptyA);
+          if (is_halo) {
+            if (d.out_r >= 0) halo_put(d.out_r, h_dst, qr);
+            halo_put(d.out_a, h_dst, qa);
+          }
+          {
+            float x[16], y[16];
+            tmem_ld16x2(tmh + 0, tmh + 32, x, y);
+            if (is_site) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) x[i] = fmaxf((x[i] + y[i]) * X_WINV, 0.f);
+              store_row(d.x1, x);
+            }
+            tmem_ld16x2(tmh + 64, tmh + 96, x, y);
+            if (is_site) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) x[i] = (x[i] + y[i]) * X_WINV;
+              if (d.out_r >= 0) {
+                load_row(d.res_v, y);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i] + x[i], 0.f);
+                store_row(d.out_r, y);
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) x[i] = fmaxf(x[i], 0.f);
+              store_row(d.out_a, x);
+            }
+          }
+          // prefetch the concat halo while the phase-2 MMAs run
+          if (is_halo && !halo_zero) halo_fetch(h_smp, b, 2, h_lpos, qa);
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(rbar);
+
+          // ================= phase 2
+          mbar_wait(mbar, mma_phase);
+          mma_phase ^= 1;
+          tc_fence_after();
+          if (is_halo) halo_put(d.c, h_dst, qa);
+          {
+            float x[16], y[16];
+            tmem_ld16x2(tm + (uint32_t)(32 * half), tm + (uint32_t)(32 * half + 16), x, y);
+            if (is_site) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) x[i] = fmaxf((x[i] + y[i]) * X_WINV, 0.f);
+              store_row(d.c, x);
+            }
+          }
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(rbar);
+
+          // ================= phase 3
+          mbar_wait(mbar, mma_phase);
+          mma_phase ^= 1;
+          tc_fence_after();
+          if (!d.last) mbar_arrive(emptyB);
+          {
+            float x[16], y[16];
+            tmem_ld16x2(tmh + 0, tmh + 32, x, y);
+            if (is_site) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) x[i] = (x[i] + y[i]) * X_WINV;
+              if (d.res_h >= 0) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) x[i] += hres[i];
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) x[i] = fmaxf(x[i], 0.f);
+              store_row(d.out_h, x);
+              if (d.save_h) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) hres[i] = x[i];
+              }
+            }
+          }
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(rbar);
+
+          // ================= phase 4 (last block): head, per-segment sums, local-energy terms
+          if (d.last) {
+            mbar_wait(mbar, mma_phase);
+            mma_phase ^= 1;
+            tc_fence_after();
+            mbar_arrive(emptyB);
+            if (half == 0) {
+              float sre = 0.f, sim = 0.f;
+              {
+                float v[32];
+                tmem_ld32(tm + 0, v);
+                if (is_site) {
+                  const float re0 = (v[0] + v[16]) * X_WINV, re1 = (v[1] + v[17]) * X_WINV;
+                  const float im0 = (v[2] + v[18]) * X_WINV, im1 = (v[3] + v[19]) * X_WINV;
+                  const float x = 2.f * re0, y = 2.f * re1;
+                  const float m = fmaxf(x, y);
+                  const float half_lse = 0.5f * (m + logf(expf(x - m) + expf(y - m)));
+                  const bool up = sig > 0.f;
+                  sre = (up ? re0 : re1) - half_lse;
+                  sim = up ? im0 : im1;
+                }
+              }
+              float s_re[2], s_im[2];
+#pragma unroll
+              for (int sgi = 0; sgi < 2; ++sgi) {
+                s_re[sgi] = seg == sgi ? sre : 0.f;
+                s_im[sgi] = seg == sgi ? sim : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                  s_re[sgi] += __shfl_xor_sync(0xffffffffu, s_re[sgi], o);
+                  s_im[sgi] += __shfl_xor_sync(0xffffffffu, s_im[sgi], o);
+                }
+              }
+              if (lane == 0) {
+#pragma unroll
+                for (int sgi = 0; sgi < 2; ++sgi) {
+                  red[((pipe * 4 + (warp & 3)) * 2 + sgi) * 2 + 0] = s_re[sgi];
+                  red[((pipe * 4 + (warp & 3)) * 2 + sgi) * 2 + 1] = s_im[sgi];
+                }
+              }
+              tc_fence_before();
+              named_sync(bar_id, 128);
+              if (ltid < 2 && cfgs[ltid] >= 0) {   // thread 0 finishes segment A, thread 1 segment B
+                const int sgi = ltid;
+                float t0 = 0.f, t1 = 0.f;
+                for (int w = 0; w < 4; ++w) {
+                  t0 += red[((pipe * 4 + w) * 2 + sgi) * 2 + 0];
+                  t1 += red[((pipe * 4 + w) * 2 + sgi) * 2 + 1];
+                }
+                const float2 pre = *reinterpret_cast<const float2*>(a.px.rowcum + 2 * ((size_t)smp[sgi] * (H + 1) + r0[sgi]));
+                const float lr = pre.x + t0, li = pre.y + t1;      // log psi of the connected configuration
+                const float dr = lr - a.wk.logpsi0[2 * smp[sgi]], di = li - a.wk.logpsi0[2 * smp[sgi] + 1];
+                const float mag = expf(dr), m = a.wk.mel[cfgs[sgi]];
+                float sn, cs;
+                sincosf(di, &sn, &cs);
+                atomicAdd(a.wk.eloc + 2 * smp[sgi], (double)m * (double)(mag * cs));
+                atomicAdd(a.wk.eloc + 2 * smp[sgi] + 1, (double)m * (double)(mag * sn));
+              }
+              named_sync(bar_id, 128);   // `red` is reused by the next tile
+            }
+          }
+        }
+      }
+    } else
     for (long long it = 0; it < my_iters; ++it) {
       const long long group = it * gridDim.x + blockIdx.x;
       const long long cfg = group * X_NP + pipe;
       const bool active = cfg < n_items;
+      uint8_t* dump_cfg = (a.px.dump && active) ? a.px.dump + (size_t)cfg * a.px.cache_stride : nullptr;
       long long src = cfg;
       int flip_a = -1, flip_b = -1;
       if (a.wk.items && active) {   // connected configuration = the item's sample with the item's sites flipped
@@ -417,11 +699,11 @@ __global__ void __launch_bounds__(X_NP * X_EPI + 32 + X_ISSUERS * 32, 1) tcx_for
               load_row(d.res_v, y);
 #pragma unroll
               for (int i = 0; i < 16; ++i) y[i] = fmaxf(y[i] + x[i], 0.f);
-              store_row(d.out_r, y);
+              store_row(d.out_r, y, dump_cfg ? dump_cfg + (size_t)((b * 3 + 1) * 2) * tile_bytes : nullptr);
             }
 #pragma unroll
             for (int i = 0; i < 16; ++i) x[i] = fmaxf(x[i], 0.f);
-            store_row(d.out_a, x);
+            store_row(d.out_a, x, dump_cfg ? dump_cfg + (size_t)((b * 3 + 0) * 2) * tile_bytes : nullptr);
           }
         }
         fence_proxy_async();
@@ -439,7 +721,7 @@ __global__ void __launch_bounds__(X_NP * X_EPI + 32 + X_ISSUERS * 32, 1) tcx_for
           if (site >= 0) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) x[i] = fmaxf((x[i] + y[i]) * X_WINV, 0.f);
-            store_row(d.c, x);
+            store_row(d.c, x, dump_cfg ? dump_cfg + (size_t)((b * 3 + 2) * 2) * tile_bytes : nullptr);
           }
         }
         fence_proxy_async();
@@ -494,6 +776,8 @@ __global__ void __launch_bounds__(X_NP * X_EPI + 32 + X_ISSUERS * 32, 1) tcx_for
               const bool up = sig > 0.f;
               sre = (up ? re0 : re1) - half_lse;
               sim = up ? im0 : im1;
+              if (a.px.siteterm && active)
+                *reinterpret_cast<float2*>(a.px.siteterm + 2 * ((size_t)cfg * HW + site)) = make_float2(sre, sim);
             }
           }
 #pragma unroll
@@ -611,6 +895,131 @@ int tcx_prepare(fk_net* net) {
   return 0;
 }
 
+// ---- prefix reuse: work list -> tiles ------------------------------------------------------------------------------------
+constexpr int XP_MAXK = 64;    // row classes (k = rows to recompute = H - r0)
+constexpr int XP_MAXRUN = 2 * XP_MAXK + 2;
+struct TcxPlan {
+  int count[XP_MAXK + 1];      // configurations per class
+  int off[XP_MAXK + 2];        // class k occupies list[off[k] .. off[k + 1])
+  int cursor[XP_MAXK + 1];     // scatter cursors
+  int nruns;
+  int run_a[XP_MAXRUN], run_sa[XP_MAXRUN], run_b[XP_MAXRUN], run_sb[XP_MAXRUN], run_tile0[XP_MAXRUN + 1];
+  long long n_tiles;
+};
+
+__device__ __forceinline__ int xp_rows(const TcWorkItem& wi, int W, int H) {
+  const int ra = (int)wi.site_a / W, rb = wi.site_b == 0xffffu ? ra : (int)wi.site_b / W;
+  return H - (ra < rb ? ra : rb);
+}
+
+__global__ void tcx_plan_zero_kernel(TcxPlan* plan) {
+  for (int i = threadIdx.x; i <= XP_MAXK; i += blockDim.x) { plan->count[i] = 0; plan->cursor[i] = 0; }
+}
+
+__global__ void tcx_class_count_kernel(const TcWorkItem* __restrict__ items, const long long* __restrict__ n_dev, int W, int H,
+                                       TcxPlan* plan) {
+  __shared__ int hist[XP_MAXK + 1];
+  for (int i = threadIdx.x; i <= XP_MAXK; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  const long long n = *n_dev;
+  for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += (long long)gridDim.x * blockDim.x)
+    atomicAdd(&hist[xp_rows(items[f], W, H)], 1);
+  __syncthreads();
+  for (int i = threadIdx.x; i <= XP_MAXK; i += blockDim.x)
+    if (hist[i]) atomicAdd(&plan->count[i], hist[i]);
+}
+
+// one thread: class offsets and the pairing of the classes.  Two segments of kA and kB rows share a tile when
+// kA + 2 + kB <= rcap (two halo rows between them); greedy: the smallest non-empty class takes partners from the largest class
+// that still fits, classes that fit with nobody become single-segment tiles.
+__global__ void tcx_plan_kernel(TcxPlan* plan, int H, int rcap) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int rem[XP_MAXK + 1], cur[XP_MAXK + 1];
+  int o = 0;
+  for (int k = 0; k <= XP_MAXK; ++k) {
+    plan->off[k] = o;
+    o += plan->count[k];
+    rem[k] = plan->count[k];
+    cur[k] = 0;
+  }
+  plan->off[XP_MAXK + 1] = o;
+  const int T = rcap - 2;
+  int nr = 0, tile = 0;
+  auto add = [&](int ca, int sa, int cb, int sb, int m) {
+    if (m <= 0) return;
+    plan->run_a[nr] = ca; plan->run_sa[nr] = sa; plan->run_b[nr] = cb; plan->run_sb[nr] = sb; plan->run_tile0[nr] = tile;
+    ++nr;
+    tile += m;
+  };
+  int lo = 1, hi = H < XP_MAXK ? H : XP_MAXK;
+  for (;;) {
+    while (lo <= hi && rem[lo] == 0) ++lo;
+    while (hi >= lo && rem[hi] == 0) --hi;
+    if (lo > hi) break;
+    if (lo == hi) {
+      if (2 * lo <= T) {
+        const int m = rem[lo] / 2;
+        add(lo, cur[lo], lo, cur[lo] + m, m);
+        cur[lo] += 2 * m; rem[lo] -= 2 * m;
+      }
+      add(lo, cur[lo], -1, 0, rem[lo]);
+      rem[lo] = 0;
+      break;
+    }
+    if (lo + hi <= T) {
+      const int m = rem[lo] < rem[hi] ? rem[lo] : rem[hi];
+      add(lo, cur[lo], hi, cur[hi], m);
+      cur[lo] += m; rem[lo] -= m; cur[hi] += m; rem[hi] -= m;
+    } else {
+      add(hi, cur[hi], -1, 0, rem[hi]);
+      cur[hi] += rem[hi]; rem[hi] = 0;
+    }
+  }
+  plan->run_tile0[nr] = tile;
+  plan->nruns = nr;
+  plan->n_tiles = tile;
+}
+
+__global__ void tcx_class_scatter_kernel(const TcWorkItem* __restrict__ items, const long long* __restrict__ n_dev, int W, int H,
+                                         TcxPlan* plan, int* __restrict__ list) {
+  const long long n = *n_dev;
+  for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += (long long)gridDim.x * blockDim.x) {
+    const int k = xp_rows(items[f], W, H);
+    list[plan->off[k] + atomicAdd(&plan->cursor[k], 1)] = (int)f;
+  }
+}
+
+__global__ void tcx_tiles_kernel(const TcxPlan* __restrict__ plan, const int* __restrict__ list, int2* __restrict__ tiles) {
+  const long long n = plan->n_tiles;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    int r = 0;
+    while (r + 1 < plan->nruns && plan->run_tile0[r + 1] <= t) ++r;
+    const int i = (int)(t - plan->run_tile0[r]);
+    const int ca = plan->run_a[r], cb = plan->run_b[r];
+    int2 out;
+    out.x = list[plan->off[ca] + plan->run_sa[r] + i];
+    out.y = cb >= 0 ? list[plan->off[cb] + plan->run_sb[r] + i] : -1;
+    tiles[t] = out;
+  }
+}
+
+// rowcum[b][r] = sum of the selected log-amplitude terms of the sites of rows < r (fixed order: deterministic)
+__global__ void tcx_rowcum_kernel(const float* __restrict__ siteterm, long long B, int H, int W, float* __restrict__ rowcum) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float2* st = reinterpret_cast<const float2*>(siteterm) + b * (long long)(H * W);
+  float2* rc = reinterpret_cast<float2*>(rowcum) + b * (long long)(H + 1);
+  float re = 0.f, im = 0.f;
+  rc[0] = make_float2(0.f, 0.f);
+  for (int r = 0; r < H; ++r) {
+    for (int c = 0; c < W; ++c) {
+      const float2 t = st[r * W + c];
+      re += t.x; im += t.y;
+    }
+    rc[r + 1] = make_float2(re, im);
+  }
+}
+
 int tcx_pack_weights(fk_net* net, cudaStream_t s) {
   if (!net->d_tc_exact) return 0;
   const int nb = 2 * net->depth - 2;
@@ -620,7 +1029,15 @@ int tcx_pack_weights(fk_net* net, cudaStream_t s) {
   return 0;
 }
 
+static int tcx_launch(fk_net* net, const int8_t* sigma, int64_t n, float* log_psi_out, cudaStream_t s, const TcWork* work,
+                      const TcxPrefix* px);
+
 int tcx_log_psi(fk_net* net, const int8_t* sigma, int64_t n, float* log_psi_out, cudaStream_t s, const TcWork* work) {
+  return tcx_launch(net, sigma, n, log_psi_out, s, work, nullptr);
+}
+
+static int tcx_launch(fk_net* net, const int8_t* sigma, int64_t n, float* log_psi_out, cudaStream_t s, const TcWork* work,
+                      const TcxPrefix* px) {
   FK_REQUIRE(net->params_set && net->d_tc_exact, "tc-exact engine: not available for this machine, or parameters never set");
   if (n == 0) return 0;
   const TcxGeometry g = tcx_geometry(net);
@@ -633,6 +1050,7 @@ int tcx_log_psi(fk_net* net, const int8_t* sigma, int64_t n, float* log_psi_out,
   a.H = net->H; a.W = net->W; a.P = g.P; a.nb = nb; a.npos = g.npos; a.p_first = g.p_first;
   a.cst_off = (int)(g.smem_bytes - 4096);
   if (work) a.wk = *work; else a.wk = TcWork{nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (px) a.px = *px; else a.px = TcxPrefix{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
   int dev = 0, sms = 148;
   FK_CHECK_CUDA(cudaGetDevice(&dev));
   FK_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -642,6 +1060,71 @@ int tcx_log_psi(fk_net* net, const int8_t* sigma, int64_t n, float* log_psi_out,
   tcx_forward_kernel<<<grid, X_NP * X_EPI + 32 + X_ISSUERS * 32, g.smem_bytes, s>>>(a);
   FK_CHECK_LAUNCH();
   return 0;
+}
+
+// ---- local energy with prefix reuse: dump pass over the samples, tiles from the work list, tile pass -------------------------
+static int xp_rcap(const fk_net* net) { return (128 - net->W) / (net->W + 2) + 1; }
+
+int tcx_prefix_supported(const fk_net* net) {
+  if (!tcx_supported(net)) return 0;
+  const int rcap = xp_rcap(net);
+  if (net->H > XP_MAXK || net->H > rcap) return 0;
+  if (128 - rcap * net->W < 2 * net->W) return 0;      // not enough idle positions to load segment A's halo
+  return 1;
+}
+
+struct XpLayout { size_t cache, siteterm, rowcum, plan, list, tiles, total, stride; };
+static XpLayout xp_layout(const fk_net* net, int64_t B, int64_t cap) {
+  const TcxGeometry g = tcx_geometry(net);
+  const int nb = 2 * net->depth - 2;
+  XpLayout L;
+  L.stride = (size_t)nb * 3 * 2 * 64 * g.npos;
+  size_t o = 0;
+  L.cache = o; o = x256(o + (size_t)B * L.stride);
+  L.siteterm = o; o = x256(o + (size_t)B * net->sites * 8);
+  L.rowcum = o; o = x256(o + (size_t)B * (net->H + 1) * 8);
+  L.plan = o; o = x256(o + sizeof(TcxPlan));
+  L.list = o; o = x256(o + (size_t)cap * 4);
+  L.tiles = o; o = x256(o + (size_t)cap * 8);
+  L.total = o;
+  return L;
+}
+
+int64_t tcx_prefix_workspace_bytes(const fk_net* net, int64_t B, int64_t cap) { return (int64_t)xp_layout(net, B, cap).total; }
+
+// `work` holds the device work list of the B samples (items, count, matrix elements), eloc accumulators initialised with the
+// diagonal terms; log psi of the samples is written to work->logpsi0 by the dump pass
+int tcx_local_energy_prefix(fk_net* net, const int8_t* sigma, int64_t B, int64_t cap, const TcWork* work, void* ws, int64_t ws_bytes,
+                            cudaStream_t s) {
+  FK_REQUIRE(tcx_prefix_supported(net), "tc-exact prefix reuse: machine outside the envelope");
+  const XpLayout L = xp_layout(net, B, cap);
+  FK_REQUIRE((int64_t)L.total <= ws_bytes, "tc-exact prefix reuse: workspace too small (%lld < %zu)", (long long)ws_bytes, L.total);
+  uint8_t* base = (uint8_t*)ws;
+  TcxPlan* plan = reinterpret_cast<TcxPlan*>(base + L.plan);
+  int* list = reinterpret_cast<int*>(base + L.list);
+  int2* tiles = reinterpret_cast<int2*>(base + L.tiles);
+  float* siteterm = reinterpret_cast<float*>(base + L.siteterm);
+  float* rowcum = reinterpret_cast<float*>(base + L.rowcum);
+  const int rcap = xp_rcap(net);
+  // dump pass: log psi of the samples + their activation cache + per-site terms
+  TcxPrefix pd = {nullptr, nullptr, nullptr, nullptr, base + L.cache, siteterm, (long long)L.stride, rcap};
+  if (tcx_launch(net, sigma, B, const_cast<float*>(work->logpsi0), s, nullptr, &pd)) return 1;
+  tcx_rowcum_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(siteterm, B, net->H, net->W, rowcum);
+  FK_CHECK_LAUNCH();
+  // tiles
+  tcx_plan_zero_kernel<<<1, 128, 0, s>>>(plan);
+  FK_CHECK_LAUNCH();
+  tcx_class_count_kernel<<<296, 256, 0, s>>>(work->items, work->n_dev, net->W, net->H, plan);
+  FK_CHECK_LAUNCH();
+  tcx_plan_kernel<<<1, 32, 0, s>>>(plan, net->H, rcap);
+  FK_CHECK_LAUNCH();
+  tcx_class_scatter_kernel<<<296, 256, 0, s>>>(work->items, work->n_dev, net->W, net->H, plan, list);
+  FK_CHECK_LAUNCH();
+  tcx_tiles_kernel<<<296, 256, 0, s>>>(plan, list, tiles);
+  FK_CHECK_LAUNCH();
+  // tile pass
+  TcxPrefix pt = {tiles, &plan->n_tiles, base + L.cache, rowcum, nullptr, nullptr, (long long)L.stride, rcap};
+  return tcx_launch(net, sigma, cap, nullptr, s, work, &pt);
 }
 
 }  // namespace fk
