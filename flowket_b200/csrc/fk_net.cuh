@@ -59,8 +59,45 @@ struct TcWork {
   const float* mel;          // [items] matrix elements
   double* eloc;              // [B] double2 accumulators (atomicAdd)
 };
+// ---- prefix reuse (dependency analysis pinned by oracle/prefix_reuse.py) ----------------------------
+// A connected configuration equals its sample on every lattice row above the first flipped site (row r0), and every
+// convolution of the machine looks up and sideways only, so rows >= r0 can be recomputed from the new spins plus a halo
+// taken from the SAMPLE's own activations: rows r0-2, r0-1 of each block's vertical input (= relu(v') or the residual
+// sum of the previous block) and of its concat tensor, row r0-1 of relu(v'); log psi(sigma') = (the sample's selected
+// log-amplitude terms of rows < r0) + (the recomputed terms of rows >= r0).
+//   dump pass   the ordinary forward over the samples also writes, per block, the (hi, lo) tiles of relu(v'), of the
+//               residual sum and of the concat tensor to `dump` (the cache) and the selected term of every site to `siteterm`;
+//   tile pass   a work item is a TILE holding one or two row-trimmed configurations ("segments"): segment A occupies tile
+//               rows [0, kA) with its halo in the two rows above the MMA range (written by otherwise idle threads),
+//               segment B tile rows [kA + 2, kA + 2 + kB) with its halo in rows kA, kA + 1 (written by the threads that own
+//               those positions instead of their MMA results).  The MMA issue does not change at all -- taps are relative
+//               offsets, a segment is just a translated lattice -- so two configurations share one M = 128 tile.
+struct TcxPrefix {
+  const int2* tiles;            // (work-list index of segment A, of segment B or -1); nullptr: not the tile pass
+  const long long* n_tiles;     // device-side count
+  const uint8_t* cache;         // tile pass: the samples' activation cache
+  const float* rowcum;          // tile pass: [sample][H + 1] float2, sum of the selected terms of rows < r
+  uint8_t* dump;                // dump pass: cache to write (configuration i = sample i); nullptr otherwise
+  float* siteterm;              // dump pass: [sample][sites] float2
+  long long cache_stride;       // bytes per sample = nb * 3 tensors * 2 (hi, lo) * 64 * npos
+  int rcap;                     // tile rows that lie completely inside the MMA range
+};
+
+// tiles from a device work list (fk_tc_exact.cu): row classes -> greedy pairing -> (cfgA, cfgB) list; everything stays on the device
+int xp_rcap(const fk_net* net);                      // tile rows completely inside the MMA range
+int xp_geometry_ok(const fk_net* net);               // one M tile, enough idle positions for the top halo
+int64_t xp_tiles_workspace_bytes(int64_t cap);
+int xp_build_tiles(const fk_net* net, const TcWork* work, int64_t cap, void* ws, const int2** tiles_out, const long long** n_tiles_out,
+                   cudaStream_t s);
+
 int tc_forward_launch(fk_net* net, const int8_t* sigma, int64_t n, float* log_psi_out, uint8_t* dump,
-                      uint32_t* dump_mask, float* dump_logits, cudaStream_t s, const TcWork* work = nullptr);
+                      uint32_t* dump_mask, float* dump_logits, cudaStream_t s, const TcWork* work = nullptr,
+                      const TcxPrefix* px = nullptr);
+// fp16 tensor-core local energy with prefix reuse (fk_tc.cu)
+int tc_prefix_supported(const fk_net* net);
+int64_t tc_prefix_workspace_bytes(const fk_net* net, int64_t B, int64_t cap);
+int tc_local_energy_prefix(fk_net* net, const int8_t* sigma, int64_t B, int64_t cap, const TcWork* work, void* ws, int64_t ws_bytes,
+                           cudaStream_t s);
 int tc_prepare(fk_net* net);        // allocations + wiring tables (fk_net_create)
 
 // contract-accuracy tensor-core engine (fk_tc_exact.cu)

@@ -305,13 +305,13 @@ struct ElocLayout {
   int64_t prefix, prefix_bytes, sample_chunk;   // tc-exact with prefix reuse: activation cache + tiles for `sample_chunk` samples
 };
 
-// prefix reuse of the tc-exact local energy (fk_tc_exact.cu) is on unless FK_TCX_PREFIX=0; its cache costs 2.3 MB per sample,
+// prefix reuse of the tc-exact local energy (fk_tc_exact.cu, fk_tc.cu) is on unless FK_PREFIX_REUSE=0; its cache costs 2.0 - 2.3 MB per sample,
 // so the samples are processed in chunks
 constexpr int64_t XP_SAMPLE_CHUNK = 8192;
-static bool prefix_enabled(const fk_net* net) {
-  const char* e = getenv("FK_TCX_PREFIX");
+static bool prefix_enabled(const fk_net* net, int engine) {
+  const char* e = getenv("FK_PREFIX_REUSE");
   if (e && atoi(e) == 0) return false;
-  return tcx_prefix_supported(net) != 0;
+  return engine == FK_ENGINE_TC_EXACT ? tcx_prefix_supported(net) != 0 : (engine == FK_ENGINE_TC ? tc_prefix_supported(net) != 0 : false);
 }
 
 static ElocLayout eloc_layout(const fk_net* net, const fk_operator_t* op, int64_t B, int engine, int64_t ws_bytes) {
@@ -325,10 +325,12 @@ static ElocLayout eloc_layout(const fk_net* net, const fk_operator_t* op, int64_
     L.melf = o; o = align256(o + 4 * cap);
     L.items = o; o = align256(o + 8 * cap);
     L.sample_chunk = B;
-    if (engine == FK_ENGINE_TC_EXACT && prefix_enabled(net)) {
+    if (prefix_enabled(net, engine)) {
       L.sample_chunk = std::min<int64_t>(B, XP_SAMPLE_CHUNK);
       L.prefix = o;
-      L.prefix_bytes = tcx_prefix_workspace_bytes(net, L.sample_chunk, (int64_t)std::max(op->max_conn - 1, 1) * L.sample_chunk);
+      const int64_t ccap = (int64_t)std::max(op->max_conn - 1, 1) * L.sample_chunk;
+      L.prefix_bytes = engine == FK_ENGINE_TC_EXACT ? tcx_prefix_workspace_bytes(net, L.sample_chunk, ccap)
+                                                    : tc_prefix_workspace_bytes(net, L.sample_chunk, ccap);
       o = align256(o + L.prefix_bytes);
     }
     L.total = o; L.chunk = cap;
@@ -376,11 +378,15 @@ static int local_energy_worklist(fk_net* net, const fk_operator_t* op, const int
   TcWork wk;
   wk.n_dev = offsets + B; wk.items = items; wk.logpsi0 = logpsi0; wk.mel = mel; wk.eloc = eloc_out;
   const int64_t cap = L.chunk;
-  if (engine == FK_ENGINE_TC) {
+  if (L.prefix_bytes > 0 && B <= L.sample_chunk) {
+    if (engine == FK_ENGINE_TC) {
+      if (tc_local_energy_prefix(net, sigma, B, cap, &wk, base + L.prefix, L.prefix_bytes, s)) return 1;
+    } else {
+      if (tcx_local_energy_prefix(net, sigma, B, cap, &wk, base + L.prefix, L.prefix_bytes, s)) return 1;
+    }
+  } else if (engine == FK_ENGINE_TC) {
     if (tc_forward_launch(net, sigma, B, logpsi0, nullptr, nullptr, nullptr, s)) return 1;
     if (tc_forward_launch(net, sigma, cap, nullptr, nullptr, nullptr, nullptr, s, &wk)) return 1;
-  } else if (L.prefix_bytes > 0 && B <= L.sample_chunk) {
-    if (tcx_local_energy_prefix(net, sigma, B, cap, &wk, base + L.prefix, L.prefix_bytes, s)) return 1;
   } else {
     if (tcx_log_psi(net, sigma, B, logpsi0, s)) return 1;
     if (tcx_log_psi(net, sigma, cap, nullptr, s, &wk)) return 1;

@@ -104,6 +104,8 @@ struct TcArgs {
   uint32_t* dump_mask;
   float* dump_logits;
   TcWork wk;   // local-energy work list (all null: plain log psi of the configurations in `sigma`)
+  TcxPrefix px; // prefix reuse, tile pass (fk_net.cuh); the cache is the gradient dump of the samples (tiles relu(v'), residual v,
+                // concat = tensors 1, 2, 3 of every block); all null = off
 };
 
 constexpr int TC_DUMP_TENSORS = 5;
@@ -198,7 +200,8 @@ __global__ void __launch_bounds__(MAXNP * 128 + 32 + TC_ISSUERS * 32, 1) tc_forw
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const long long n_items = a.wk.n_dev ? *a.wk.n_dev : a.n;
+  const bool tile_mode = !DUMP && a.px.tiles != nullptr;    // (T == 1 only, checked by the launcher)
+  const long long n_items = tile_mode ? *a.px.n_tiles : (a.wk.n_dev ? *a.wk.n_dev : a.n);
   const long long groups = (n_items + a.np - 1) / a.np;  // configuration groups (one per CTA iteration)
   const long long my_iters = (long long)blockIdx.x < groups ? (groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
@@ -393,6 +396,245 @@ __global__ void __launch_bounds__(MAXNP * 128 + 32 + TC_ISSUERS * 32, 1) tc_forw
     uint32_t mma_phase = 0;
     long long step = 0;  // weight-pipeline step: block (step % nb) lives in buffer (step & 1)
 
+    if (tile_mode) {
+      // =========================== tile pass of the prefix reuse (TcxPrefix, fk_net.cuh; one M tile) ===========================
+      const int W = a.W, H = a.H, P = a.P;
+      const int p0 = pos[0];
+      const int prow = p0 / P - 2, pcol = p0 % P - 2;
+      const bool real_pos = pcol >= 0 && prow < a.px.rcap;
+      int hq = -1;            // idle positions load segment A's halo (two rows above the MMA range): halo row hq / W, column hq % W
+      if (!real_pos) {
+        int q = 0;
+        for (int j = 0; j < ltid; ++j) {
+          const int pj = a.p_first + j;
+          q += (pj % P - 2 >= 0 && pj / P - 2 < a.px.rcap) ? 0 : 1;
+        }
+        if (q < 2 * W) hq = q;
+      }
+      const size_t tile_b = (size_t)64 * a.npos;
+      auto halo_fetch = [&](int smp, int b, int tensor, int lpos, uint4 (&q)[4]) {
+        const uint8_t* g = a.px.cache + (size_t)smp * a.px.cache_stride + (size_t)(b * TC_DUMP_TENSORS + tensor) * tile_b + (size_t)lpos * 16;
+#pragma unroll
+        for (int cg = 0; cg < 4; ++cg) q[cg] = __ldg(reinterpret_cast<const uint4*>(g + (size_t)cg * a.npos * 16));
+      };
+      auto put_q = [&](int slot, int dpos, const uint4 (&q)[4]) {
+        uint8_t* base = act + (size_t)slot * buf_bytes + (size_t)dpos * 16;
+#pragma unroll
+        for (int cg = 0; cg < 4; ++cg) *reinterpret_cast<uint4*>(base + (size_t)cg * a.npos * 16) = q[cg];
+      };
+      for (long long it = 0; it < my_iters; ++it) {
+        const long long group = it * gridDim.x + blockIdx.x;
+        const long long tix = group * a.np + pipe;
+        const bool active = tix < n_items;
+        int cfgs[2] = {-1, -1}, smp[2] = {0, 0}, fa[2] = {-1, -1}, fb[2] = {-1, -1}, r0[2] = {0, 0}, kk[2] = {0, 0};
+        if (active) {
+          const int2 t = a.px.tiles[tix];
+          cfgs[0] = t.x; cfgs[1] = t.y;
+        }
+#pragma unroll
+        for (int sgi = 0; sgi < 2; ++sgi)
+          if (cfgs[sgi] >= 0) {
+            const TcWorkItem wi = a.wk.items[cfgs[sgi]];
+            smp[sgi] = wi.sample;
+            fa[sgi] = (int)wi.site_a;
+            fb[sgi] = wi.site_b == 0xffffu ? -1 : (int)wi.site_b;
+            const int ra = fa[sgi] / W, rb = fb[sgi] >= 0 ? fb[sgi] / W : ra;
+            r0[sgi] = ra < rb ? ra : rb;
+            kk[sgi] = H - r0[sgi];
+          }
+        int seg = -1, lrow = 0;
+        int h_smp = -1, h_row = 0, h_col = 0, h_dst = 0;
+        if (real_pos && cfgs[0] >= 0) {
+          const int rowB0 = kk[0] + 2;
+          if (prow < kk[0]) { seg = 0; lrow = prow + r0[0]; }
+          else if (cfgs[1] >= 0) {
+            if (prow < rowB0) { h_smp = smp[1]; h_row = r0[1] - 2 + (prow - kk[0]); h_col = pcol; h_dst = p0; }
+            else if (prow < rowB0 + kk[1]) { seg = 1; lrow = prow - rowB0 + r0[1]; }
+          }
+        } else if (hq >= 0 && cfgs[0] >= 0) {
+          h_smp = smp[0]; h_row = r0[0] - 2 + hq / W; h_col = hq % W; h_dst = (hq / W) * P + 2 + h_col;
+        }
+        const bool is_site = seg >= 0;
+        const bool is_halo = h_smp >= 0;
+        const bool halo_zero = is_halo && h_row < 0;
+        const bool own_halo = is_halo && h_dst == p0;               // in-tile halo row (segment B): replaces this position's own store
+        const int h_lpos = (h_row + 2) * P + h_col + 2;
+        const int lsite = is_site ? lrow * W + pcol : -1;
+        float sg1 = is_site ? (float)a.sigma[(size_t)smp[seg] * HW + lsite] : 0.f;
+        if (is_site && (lsite == fa[seg] || lsite == fb[seg])) sg1 = -sg1;
+        uint4 qa[4], qr[4];
+        {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          v[0] = sg1;
+          if (!own_halo) store_row(sdesc[0].in_v, p0, v);
+          if (is_halo) {
+            const float hs = halo_zero ? 0.f : (float)a.sigma[(size_t)h_smp * HW + h_row * W + h_col];
+            qa[0] = make_uint4(pack_h2(hs, 0.f), 0u, 0u, 0u);
+            qa[1] = qa[2] = qa[3] = make_uint4(0u, 0u, 0u, 0u);
+            put_q(sdesc[0].in_v, h_dst, qa);
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(rbar);
+
+        for (int b = 0; b < a.nb; ++b, ++step) {
+          const TcBlockDesc d = sdesc[b];
+          const uint32_t wsel = (uint32_t)(step & 1);
+          mbar_wait(full0 + 8 * wsel, (uint32_t)((step >> 1) & 1));
+          // ================= phase 1
+          if (is_halo && !halo_zero) {
+            halo_fetch(h_smp, b, 1, h_lpos, qa);
+            if (d.out_r >= 0) halo_fetch(h_smp, b, 2, h_lpos, qr);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) qa[i] = qr[i] = make_uint4(0u, 0u, 0u, 0u);
+          }
+          mbar_wait(mbar, mma_phase);
+          mma_phase ^= 1;
+          tc_fence_after();
+          if (is_halo) {
+            if (d.out_r >= 0) put_q(d.out_r, h_dst, qr);
+            put_q(d.out_a, h_dst, qa);
+          }
+          {
+            float v[32];
+            tmem_ld32(tm_pipe + lane_sel + 0, v);
+            if (is_site) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            }
+            store_row(d.x1, p0, v);
+            tmem_ld32(tm_pipe + lane_sel + 32, v);
+            if (is_site) {
+              if (d.out_r >= 0) {
+                float r[32];
+                load_row(d.res_v, p0, r);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r[i] = fmaxf(r[i] + v[i], 0.f);
+                store_row(d.out_r, p0, r);
+              }
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+              store_row(d.out_a, p0, v);
+            } else if (!own_halo) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = 0.f;
+              if (d.out_r >= 0) store_row(d.out_r, p0, v);
+              store_row(d.out_a, p0, v);
+            }
+          }
+          if (is_halo && !halo_zero) halo_fetch(h_smp, b, 3, h_lpos, qa);   // concat halo, prefetched during the phase-2 MMAs
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(rbar);
+
+          // ================= phase 2
+          mbar_wait(mbar, mma_phase);
+          mma_phase ^= 1;
+          tc_fence_after();
+          if (is_halo) put_q(d.c, h_dst, qa);
+          {
+            float v[32];
+            tmem_ld32(tm_pipe + lane_sel + 64, v);
+            if (is_site) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            }
+            if (!own_halo) store_row(d.c, p0, v);
+          }
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(rbar);
+
+          // ================= phase 3
+          mbar_wait(mbar, mma_phase);
+          mma_phase ^= 1;
+          tc_fence_after();
+          {
+            float v[32];
+            tmem_ld32(tm_pipe + lane_sel + 96, v);
+            if (is_site) {
+              if (d.res_h >= 0) {
+                float r[32];
+                load_row(d.res_h, p0, r);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += r[i];
+              }
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            }
+            store_row(d.out_h, p0, v);
+          }
+          fence_proxy_async();
+          tc_fence_before();
+          mbar_arrive(rbar);
+
+          // ================= phase 4 (last block): head, per-segment sums, local-energy terms
+          if (d.last) {
+            mbar_wait(mbar, mma_phase);
+            mma_phase ^= 1;
+            tc_fence_after();
+            float sre = 0.f, sim = 0.f;
+            {
+              float v[16];
+              tmem_ld16(tm_pipe + lane_sel + 0, v);
+              if (is_site) {
+                const float re0 = v[0], re1 = v[1], im0 = v[2], im1 = v[3];
+                const float x = 2.f * re0, y = 2.f * re1;
+                const float m = fmaxf(x, y);
+                const float half_lse = 0.5f * (m + logf(expf(x - m) + expf(y - m)));
+                const bool up = sg1 > 0.f;
+                sre = (up ? re0 : re1) - half_lse;
+                sim = up ? im0 : im1;
+              }
+            }
+#pragma unroll
+            for (int sgi = 0; sgi < 2; ++sgi) {
+              float tr = seg == sgi ? sre : 0.f, ti = seg == sgi ? sim : 0.f;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                tr += __shfl_xor_sync(0xffffffffu, tr, o);
+                ti += __shfl_xor_sync(0xffffffffu, ti, o);
+              }
+              if (lane == 0) {
+                red[(pipe * 4 + (warp & 3)) * 2 + 0] = tr;
+                red[(pipe * 4 + (warp & 3)) * 2 + 1] = ti;
+              }
+              tc_fence_before();
+              named_sync(bar_id, 128);
+              if (ltid == 0 && cfgs[sgi] >= 0) {
+                float t0 = 0.f, t1 = 0.f;
+                for (int w = 0; w < 4; ++w) {
+                  t0 += red[(pipe * 4 + w) * 2 + 0];
+                  t1 += red[(pipe * 4 + w) * 2 + 1];
+                }
+                const float2 pre = *reinterpret_cast<const float2*>(a.px.rowcum + 2 * ((size_t)smp[sgi] * (H + 1) + r0[sgi]));
+                const float dr = pre.x + t0 - a.wk.logpsi0[2 * smp[sgi]], di = pre.y + t1 - a.wk.logpsi0[2 * smp[sgi] + 1];
+                const float mag = expf(dr), m = a.wk.mel[cfgs[sgi]];
+                float sn, cs;
+                sincosf(di, &sn, &cs);
+                atomicAdd(a.wk.eloc + 2 * smp[sgi], (double)m * (double)(mag * cs));
+                atomicAdd(a.wk.eloc + 2 * smp[sgi] + 1, (double)m * (double)(mag * sn));
+              }
+              named_sync(bar_id, 128);   // `red` is reused by the next segment / tile
+            }
+          }
+          mbar_arrive(empty0 + 8 * wsel);
+        }
+      }
+    } else
     for (long long it = 0; it < my_iters; ++it) {
       const long long group = it * gridDim.x + blockIdx.x;
       const long long cfg = group * a.np + pipe;
@@ -766,7 +1008,7 @@ int tc_log_psi(fk_net* net, const int8_t* sigma, int64_t n, float* log_psi_out, 
 }
 
 int tc_forward_launch(fk_net* net, const int8_t* sigma, int64_t n, float* log_psi_out, uint8_t* dump,
-                      uint32_t* dump_mask, float* dump_logits, cudaStream_t s, const TcWork* work) {
+                      uint32_t* dump_mask, float* dump_logits, cudaStream_t s, const TcWork* work, const TcxPrefix* px) {
   FK_REQUIRE(net->params_set && net->d_tc_weights, "tensor-core weights were never packed (fk_net_set_params)");
   if (n == 0) return 0;
   const TcGeometry g = tc_geometry(net);
@@ -780,7 +1022,9 @@ int tc_forward_launch(fk_net* net, const int8_t* sigma, int64_t n, float* log_ps
   a.tmem_cols = g.tmem_cols; a.cst_off = (int)(g.smem_bytes - 4096); a.slots = g.slots;
   a.dump = dump; a.dump_mask = dump_mask; a.dump_logits = dump_logits;
   if (work) a.wk = *work; else a.wk = TcWork{nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (px) a.px = *px; else a.px = TcxPrefix{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
   FK_REQUIRE(dump == nullptr || g.T == 1, "tensor-core gradient: lattice needs more than one M tile");
+  FK_REQUIRE(px == nullptr || (g.T == 1 && !g.hreg && dump == nullptr), "prefix reuse: one-tile lattices only");
   int dev = 0, sms = 148;
   FK_CHECK_CUDA(cudaGetDevice(&dev));
   FK_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -799,6 +1043,77 @@ int tc_forward_launch(fk_net* net, const int8_t* sigma, int64_t n, float* log_ps
   if (rc) return rc;
   FK_CHECK_LAUNCH();
   return 0;
+}
+
+// ---- fp16 local energy with prefix reuse (see TcxPrefix in fk_net.cuh): the activation cache is the gradient dump ----------
+// rowcum[b][r] = sum over the sites of rows < r of the selected log-amplitude term, from the dumped logits (fixed order)
+__global__ void tc_rowcum_kernel(const float* __restrict__ logits, const int8_t* __restrict__ sigma, long long B, int H, int W, int P,
+                                 float* __restrict__ rowcum) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float4* lg = reinterpret_cast<const float4*>(logits) + b * 128;
+  float2* rc = reinterpret_cast<float2*>(rowcum) + b * (long long)(H + 1);
+  float re = 0.f, im = 0.f;
+  rc[0] = make_float2(0.f, 0.f);
+  for (int r = 0; r < H; ++r) {
+    for (int c = 0; c < W; ++c) {
+      const float4 l4 = lg[r * P + c];
+      const float x = 2.f * l4.x, y = 2.f * l4.y;
+      const float m = fmaxf(x, y);
+      const float half_lse = 0.5f * (m + logf(expf(x - m) + expf(y - m)));
+      const bool up = sigma[b * (long long)(H * W) + r * W + c] > 0;
+      re += (up ? l4.x : l4.y) - half_lse;
+      im += up ? l4.z : l4.w;
+    }
+    rc[r + 1] = make_float2(re, im);
+  }
+}
+
+int tc_prefix_supported(const fk_net* net) {
+  if (!tc_supported(net)) return 0;
+  const TcGeometry g = tc_geometry(net);
+  return g.ok && g.T == 1 && !g.hreg && xp_geometry_ok(net) ? 1 : 0;
+}
+
+struct TcPrefixLayout { size_t dump, mask, logits, rowcum, tiles_ws, total, stride; };
+static TcPrefixLayout tc_prefix_layout(const fk_net* net, int64_t B, int64_t cap) {
+  const TcGeometry g = tc_geometry(net);
+  const int nb = 2 * net->depth - 2;
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  TcPrefixLayout L;
+  L.stride = (size_t)(nb * TC_DUMP_TENSORS + 1) * 64 * g.npos;
+  size_t o = 0;
+  L.dump = o; o = al(o + (size_t)B * L.stride);
+  L.mask = o; o = al(o + (size_t)B * nb * TC_DUMP_TENSORS * 128 * 4);
+  L.logits = o; o = al(o + (size_t)B * 128 * 16);
+  L.rowcum = o; o = al(o + (size_t)B * (net->H + 1) * 8);
+  L.tiles_ws = o; o = al(o + (size_t)xp_tiles_workspace_bytes(cap));
+  L.total = o;
+  return L;
+}
+
+int64_t tc_prefix_workspace_bytes(const fk_net* net, int64_t B, int64_t cap) { return (int64_t)tc_prefix_layout(net, B, cap).total; }
+
+int tc_local_energy_prefix(fk_net* net, const int8_t* sigma, int64_t B, int64_t cap, const TcWork* work, void* ws, int64_t ws_bytes,
+                           cudaStream_t s) {
+  FK_REQUIRE(tc_prefix_supported(net), "fp16 prefix reuse: machine outside the envelope");
+  const TcPrefixLayout L = tc_prefix_layout(net, B, cap);
+  FK_REQUIRE((int64_t)L.total <= ws_bytes, "fp16 prefix reuse: workspace too small (%lld < %zu)", (long long)ws_bytes, L.total);
+  uint8_t* base = (uint8_t*)ws;
+  const TcGeometry g = tc_geometry(net);
+  float* rowcum = reinterpret_cast<float*>(base + L.rowcum);
+  // dump pass = the gradient's dump-mode forward over the samples (log psi of the samples, activation tiles, logits)
+  if (tc_forward_launch(net, sigma, B, const_cast<float*>(work->logpsi0), base + L.dump, reinterpret_cast<uint32_t*>(base + L.mask),
+                        reinterpret_cast<float*>(base + L.logits), s))
+    return 1;
+  tc_rowcum_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(reinterpret_cast<const float*>(base + L.logits), sigma, B, net->H, net->W,
+                                                                g.P, rowcum);
+  FK_CHECK_LAUNCH();
+  const int2* tiles = nullptr;
+  const long long* n_tiles = nullptr;
+  if (xp_build_tiles(net, work, cap, base + L.tiles_ws, &tiles, &n_tiles, s)) return 1;
+  TcxPrefix pt = {tiles, n_tiles, base + L.dump, rowcum, nullptr, nullptr, (long long)L.stride, xp_rcap(net)};
+  return tc_forward_launch(net, sigma, cap, nullptr, nullptr, nullptr, nullptr, s, work, &pt);
 }
 
 }  // namespace fk

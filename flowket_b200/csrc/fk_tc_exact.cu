@@ -103,30 +103,6 @@ __global__ void tcx_pack_kernel(const float* __restrict__ weff, const XPackDesc*
   }
 }
 
-// ---- prefix reuse (dependency analysis pinned by oracle/prefix_reuse.py) ----------------------------
-// A connected configuration equals its sample on every lattice row above the first flipped site (row r0), and every
-// convolution of the machine looks up and sideways only, so rows >= r0 can be recomputed from the new spins plus a halo
-// taken from the SAMPLE's own activations: rows r0-2, r0-1 of each block's vertical input (= relu(v') or the residual
-// sum of the previous block) and of its concat tensor, row r0-1 of relu(v'); log psi(sigma') = (the sample's selected
-// log-amplitude terms of rows < r0) + (the recomputed terms of rows >= r0).
-//   dump pass   the ordinary forward over the samples also writes, per block, the (hi, lo) tiles of relu(v'), of the
-//               residual sum and of the concat tensor to `dump` (the cache) and the selected term of every site to `siteterm`;
-//   tile pass   a work item is a TILE holding one or two row-trimmed configurations ("segments"): segment A occupies tile
-//               rows [0, kA) with its halo in the two rows above the MMA range (written by otherwise idle threads),
-//               segment B tile rows [kA + 2, kA + 2 + kB) with its halo in rows kA, kA + 1 (written by the threads that own
-//               those positions instead of their MMA results).  The MMA issue does not change at all -- taps are relative
-//               offsets, a segment is just a translated lattice -- so two configurations share one M = 128 tile.
-struct TcxPrefix {
-  const int2* tiles;            // (work-list index of segment A, of segment B or -1); nullptr: not the tile pass
-  const long long* n_tiles;     // device-side count
-  const uint8_t* cache;         // tile pass: the samples' activation cache
-  const float* rowcum;          // tile pass: [sample][H + 1] float2, sum of the selected terms of rows < r
-  uint8_t* dump;                // dump pass: cache to write (configuration i = sample i); nullptr otherwise
-  float* siteterm;              // dump pass: [sample][sites] float2
-  long long cache_stride;       // bytes per sample = nb * 3 tensors * 2 (hi, lo) * 64 * npos
-  int rcap;                     // tile rows that lie completely inside the MMA range
-};
-
 struct TcxArgs {
   const uint8_t* images;
   const TcBlockDesc* desc;
@@ -1063,17 +1039,42 @@ static int tcx_launch(fk_net* net, const int8_t* sigma, int64_t n, float* log_ps
 }
 
 // ---- local energy with prefix reuse: dump pass over the samples, tiles from the work list, tile pass -------------------------
-static int xp_rcap(const fk_net* net) { return (128 - net->W) / (net->W + 2) + 1; }
+int xp_rcap(const fk_net* net) { return (128 - net->W) / (net->W + 2) + 1; }
 
-int tcx_prefix_supported(const fk_net* net) {
-  if (!tcx_supported(net)) return 0;
+int xp_geometry_ok(const fk_net* net) {
   const int rcap = xp_rcap(net);
   if (net->H > XP_MAXK || net->H > rcap) return 0;
   if (128 - rcap * net->W < 2 * net->W) return 0;      // not enough idle positions to load segment A's halo
   return 1;
 }
 
-struct XpLayout { size_t cache, siteterm, rowcum, plan, list, tiles, total, stride; };
+int tcx_prefix_supported(const fk_net* net) { return tcx_supported(net) && xp_geometry_ok(net) ? 1 : 0; }
+
+// workspace: plan | class lists (cap ints) | tiles (cap int2)
+int64_t xp_tiles_workspace_bytes(int64_t cap) { return (int64_t)(x256(sizeof(TcxPlan)) + x256((size_t)cap * 4) + x256((size_t)cap * 8)); }
+
+int xp_build_tiles(const fk_net* net, const TcWork* work, int64_t cap, void* ws, const int2** tiles_out, const long long** n_tiles_out,
+                   cudaStream_t s) {
+  uint8_t* base = (uint8_t*)ws;
+  TcxPlan* plan = reinterpret_cast<TcxPlan*>(base);
+  int* list = reinterpret_cast<int*>(base + x256(sizeof(TcxPlan)));
+  int2* tiles = reinterpret_cast<int2*>(base + x256(sizeof(TcxPlan)) + x256((size_t)cap * 4));
+  tcx_plan_zero_kernel<<<1, 128, 0, s>>>(plan);
+  FK_CHECK_LAUNCH();
+  tcx_class_count_kernel<<<296, 256, 0, s>>>(work->items, work->n_dev, net->W, net->H, plan);
+  FK_CHECK_LAUNCH();
+  tcx_plan_kernel<<<1, 32, 0, s>>>(plan, net->H, xp_rcap(net));
+  FK_CHECK_LAUNCH();
+  tcx_class_scatter_kernel<<<296, 256, 0, s>>>(work->items, work->n_dev, net->W, net->H, plan, list);
+  FK_CHECK_LAUNCH();
+  tcx_tiles_kernel<<<296, 256, 0, s>>>(plan, list, tiles);
+  FK_CHECK_LAUNCH();
+  *tiles_out = tiles;
+  *n_tiles_out = &plan->n_tiles;
+  return 0;
+}
+
+struct XpLayout { size_t cache, siteterm, rowcum, tiles_ws, total, stride; };
 static XpLayout xp_layout(const fk_net* net, int64_t B, int64_t cap) {
   const TcxGeometry g = tcx_geometry(net);
   const int nb = 2 * net->depth - 2;
@@ -1083,9 +1084,7 @@ static XpLayout xp_layout(const fk_net* net, int64_t B, int64_t cap) {
   L.cache = o; o = x256(o + (size_t)B * L.stride);
   L.siteterm = o; o = x256(o + (size_t)B * net->sites * 8);
   L.rowcum = o; o = x256(o + (size_t)B * (net->H + 1) * 8);
-  L.plan = o; o = x256(o + sizeof(TcxPlan));
-  L.list = o; o = x256(o + (size_t)cap * 4);
-  L.tiles = o; o = x256(o + (size_t)cap * 8);
+  L.tiles_ws = o; o = x256(o + (size_t)xp_tiles_workspace_bytes(cap));
   L.total = o;
   return L;
 }
@@ -1100,9 +1099,6 @@ int tcx_local_energy_prefix(fk_net* net, const int8_t* sigma, int64_t B, int64_t
   const XpLayout L = xp_layout(net, B, cap);
   FK_REQUIRE((int64_t)L.total <= ws_bytes, "tc-exact prefix reuse: workspace too small (%lld < %zu)", (long long)ws_bytes, L.total);
   uint8_t* base = (uint8_t*)ws;
-  TcxPlan* plan = reinterpret_cast<TcxPlan*>(base + L.plan);
-  int* list = reinterpret_cast<int*>(base + L.list);
-  int2* tiles = reinterpret_cast<int2*>(base + L.tiles);
   float* siteterm = reinterpret_cast<float*>(base + L.siteterm);
   float* rowcum = reinterpret_cast<float*>(base + L.rowcum);
   const int rcap = xp_rcap(net);
@@ -1111,19 +1107,11 @@ int tcx_local_energy_prefix(fk_net* net, const int8_t* sigma, int64_t B, int64_t
   if (tcx_launch(net, sigma, B, const_cast<float*>(work->logpsi0), s, nullptr, &pd)) return 1;
   tcx_rowcum_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(siteterm, B, net->H, net->W, rowcum);
   FK_CHECK_LAUNCH();
-  // tiles
-  tcx_plan_zero_kernel<<<1, 128, 0, s>>>(plan);
-  FK_CHECK_LAUNCH();
-  tcx_class_count_kernel<<<296, 256, 0, s>>>(work->items, work->n_dev, net->W, net->H, plan);
-  FK_CHECK_LAUNCH();
-  tcx_plan_kernel<<<1, 32, 0, s>>>(plan, net->H, rcap);
-  FK_CHECK_LAUNCH();
-  tcx_class_scatter_kernel<<<296, 256, 0, s>>>(work->items, work->n_dev, net->W, net->H, plan, list);
-  FK_CHECK_LAUNCH();
-  tcx_tiles_kernel<<<296, 256, 0, s>>>(plan, list, tiles);
-  FK_CHECK_LAUNCH();
+  const int2* tiles = nullptr;
+  const long long* n_tiles = nullptr;
+  if (xp_build_tiles(net, work, cap, base + L.tiles_ws, &tiles, &n_tiles, s)) return 1;
   // tile pass
-  TcxPrefix pt = {tiles, &plan->n_tiles, base + L.cache, rowcum, nullptr, nullptr, (long long)L.stride, rcap};
+  TcxPrefix pt = {tiles, n_tiles, base + L.cache, rowcum, nullptr, nullptr, (long long)L.stride, rcap};
   return tcx_launch(net, sigma, cap, nullptr, s, work, &pt);
 }
 

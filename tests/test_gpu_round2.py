@@ -88,26 +88,28 @@ def test_tc_exact_local_energy_matches_oracle(opkind, opkw, shape, depth):
     ('ising', dict(pbc=False, h=1.0), (5, 7), 3, 128), ('j1j2', dict(pbc=False, j2=0.5), (6, 6), 2, 200),
     ('heisenberg', dict(pbc=False), (4, 4), 2, 8192 + 77), ('ising', dict(pbc=True, h=3.0), (3, 10), 2, 64),
     ('heisenberg', dict(pbc=False), (9, 2), 2, 100)])
-def test_tc_exact_prefix_reuse_equals_the_full_evaluation(opkind, opkw, shape, depth, B, monkeypatch):
+@pytest.mark.parametrize('engine_name', ['tc_exact', 'tc_fp16'])
+def test_prefix_reuse_equals_the_full_evaluation(opkind, opkw, shape, depth, B, engine_name, monkeypatch):
     """prefix reuse (rows above the first flipped site come from the sample's cached activations, two row-trimmed
     configurations per tile) against the same engine evaluating every connected configuration in full: identical arithmetic on
     the recomputed rows, so the two agree to the fp32 round-off of the log psi sums, which are taken in a different order
     (measured <= 4e-6 of max |E_loc|; both are within 1e-5 of the fp64 oracle, test above); the 4x4
     Heisenberg case crosses the 8192-sample chunk boundary of the activation cache"""
-    from flowket_b200 import FK_ENGINE_TC_EXACT
+    from flowket_b200 import FK_ENGINE_TC_EXACT, FK_ENGINE_TC
     from tests.test_gpu_parity import _product_operator
+    engine = FK_ENGINE_TC_EXACT if engine_name == 'tc_exact' else FK_ENGINE_TC
     model, _, spec, params = _perturbed(shape, depth, True, seed=3)
     net = model.machine.device_net()
     op = _product_operator(opkind, shape, opkw)
     sg = net.sample(B, seed=5)          # fp32 sampler: samples of the machine itself (total S_z is whatever it draws)
     res = {}
     for flag in ('1', '0'):
-        monkeypatch.setenv('FK_TCX_PREFIX', flag)
-        e, stats, n_conn = net.local_energy(op.device_desc(), sg, engine=FK_ENGINE_TC_EXACT)
+        monkeypatch.setenv('FK_PREFIX_REUSE', flag)
+        e, stats, n_conn = net.local_energy(op.device_desc(), sg, engine=engine)
         res[flag] = (e.cpu().numpy(), stats.cpu().numpy(), n_conn)
     scale = np.abs(res['0'][0]).max()
     err = np.abs(res['1'][0] - res['0'][0]).max() / scale
-    print('prefix reuse vs full evaluation', opkind, shape, depth, B, 'err', err)
+    print('prefix reuse vs full evaluation', engine_name, opkind, shape, depth, B, 'err', err)
     assert res['1'][2] == res['0'][2]
     assert err < 2e-5
     assert np.allclose(res["1"][1], res["0"][1], rtol=1e-5, atol=1e-5 * scale * scale * B)
