@@ -379,16 +379,17 @@ def run_gpu(args):
                      # dram__bytes_read + dram__bytes_write of the work-list launch of this kernel at this batch, from the ncu
                      # capture profiles/r02_ncu_traffic_B8192.txt (spins, work list, matrix elements, weights once; activations never
                      # leave shared memory / TMEM).  Only quoted for the configuration the capture was taken on.
-                     'traffic': (13.10e6 + 64e3) if (world == 1 and GB == 8192) else None,
-                     'traffic_source': 'ncu capture of the same launch (profiles/r02_ncu_traffic_B8192.txt); algorithmic operand bytes '
-                                       'move shared memory -> tensor core, not through HBM',
-                     'frac_issued': 3.0 * tf_exact / peak_tf,
-                     'kernel': 'tcx_forward_kernel: local-energy wave-function evaluations, 3 tensor-core products per MAC '
-                               '(hi*hi, hi*lo, lo*hi) counted as ONE algorithmic MAC',
+                     'traffic': None,
+                     'traffic_source': 'see profiles/r02_ncu_traffic_prefix_B8192.txt (ncu capture of the same launches)',
+                     'note': 'algorithmic FLOPs = one full forward per connected configuration (what the reference evaluates); with prefix '
+                             'reuse the kernel issues the MMAs of 62 tiles per sample instead of 85 full evaluations, each product as '
+                             'three fp16 tensor-core passes',
+                     'kernel': 'tcx_forward_kernel (tile pass of the prefix reuse): local-energy wave-function evaluations, 3 tensor-core '
+                               'products per MAC (hi*hi, hi*lo, lo*hi) counted as ONE algorithmic MAC',
                      'peak_source': pk['source'] + ' bf16 sustained (kernel timed inside a long step)',
                      'flops_per_launch': flops_eloc, 'launch_ms': eloc_exact_ms,
                      'fast_engine': {'achieved': tf_fast, 'frac': tf_fast / peak_tf, 'launch_ms': eloc_fast_ms,
-                                     'kernel': 'tc_forward_kernel (fp16 operands)'},
+                                     'kernel': 'tc_forward_kernel (fp16 operands, prefix reuse)'},
                      'gram': ({'achieved': gram_flops / (gram_ms * 1e-3) / 1e12, 'frac': gram_flops / (gram_ms * 1e-3) / 1e12 / peak_tf,
                                'launch_ms': gram_ms, 'flops_per_launch': gram_flops,
                                'kernel': 'gram2_kernel (cta_group::2 tcgen05, bf16), upper block triangle of the 2B x 2B Gram'}

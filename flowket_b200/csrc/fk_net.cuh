@@ -63,8 +63,8 @@ struct TcWork {
 // A connected configuration equals its sample on every lattice row above the first flipped site (row r0), and every
 // convolution of the machine looks up and sideways only, so rows >= r0 can be recomputed from the new spins plus a halo
 // taken from the SAMPLE's own activations: rows r0-2, r0-1 of each block's vertical input (= relu(v') or the residual
-// sum of the previous block) and of its concat tensor, row r0-1 of relu(v'); log psi(sigma') = (the sample's selected
-// log-amplitude terms of rows < r0) + (the recomputed terms of rows >= r0).
+// sum of the previous block) and of its concat tensor, row r0-1 of relu(v'); log psi(sigma') - log psi(sigma) = the sum over
+// the recomputed sites of (new selected log-amplitude term - the sample's term): the rows above r0 cancel exactly.
 //   dump pass   the ordinary forward over the samples also writes, per block, the (hi, lo) tiles of relu(v'), of the
 //               residual sum and of the concat tensor to `dump` (the cache) and the selected term of every site to `siteterm`;
 //   tile pass   a work item is a TILE holding one or two row-trimmed configurations ("segments"): segment A occupies tile
@@ -76,7 +76,8 @@ struct TcxPrefix {
   const int2* tiles;            // (work-list index of segment A, of segment B or -1); nullptr: not the tile pass
   const long long* n_tiles;     // device-side count
   const uint8_t* cache;         // tile pass: the samples' activation cache
-  const float* rowcum;          // tile pass: [sample][H + 1] float2, sum of the selected terms of rows < r
+  const float* rowcum;          // tile pass: [sample][sites] float2, the sample's own selected log-amplitude term of every site
+                                // (log psi(sigma') - log psi(sigma) = sum over the recomputed sites of (new term - sample's term))
   uint8_t* dump;                // dump pass: cache to write (configuration i = sample i); nullptr otherwise
   float* siteterm;              // dump pass: [sample][sites] float2
   long long cache_stride;       // bytes per sample = nb * 3 tensors * 2 (hi, lo) * 64 * npos

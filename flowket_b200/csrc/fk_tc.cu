@@ -596,8 +596,9 @@ __global__ void __launch_bounds__(MAXNP * 128 + 32 + TC_ISSUERS * 32, 1) tc_forw
                 const float m = fmaxf(x, y);
                 const float half_lse = 0.5f * (m + logf(expf(x - m) + expf(y - m)));
                 const bool up = sg1 > 0.f;
-                sre = (up ? re0 : re1) - half_lse;
-                sim = up ? im0 : im1;
+                const float2 base = *reinterpret_cast<const float2*>(a.px.rowcum + 2 * ((size_t)smp[seg] * HW + lsite));
+                sre = (up ? re0 : re1) - half_lse - base.x;      // difference to the sample's own term of this site
+                sim = (up ? im0 : im1) - base.y;
               }
             }
 #pragma unroll
@@ -620,8 +621,7 @@ __global__ void __launch_bounds__(MAXNP * 128 + 32 + TC_ISSUERS * 32, 1) tc_forw
                   t0 += red[(pipe * 4 + w) * 2 + 0];
                   t1 += red[(pipe * 4 + w) * 2 + 1];
                 }
-                const float2 pre = *reinterpret_cast<const float2*>(a.px.rowcum + 2 * ((size_t)smp[sgi] * (H + 1) + r0[sgi]));
-                const float dr = pre.x + t0 - a.wk.logpsi0[2 * smp[sgi]], di = pre.y + t1 - a.wk.logpsi0[2 * smp[sgi] + 1];
+                const float dr = t0, di = t1;      // log psi(sigma') - log psi(sigma): the rows above r0 cancel exactly
                 const float mag = expf(dr), m = a.wk.mel[cfgs[sgi]];
                 float sn, cs;
                 sincosf(di, &sn, &cs);
@@ -1046,27 +1046,20 @@ int tc_forward_launch(fk_net* net, const int8_t* sigma, int64_t n, float* log_ps
 }
 
 // ---- fp16 local energy with prefix reuse (see TcxPrefix in fk_net.cuh): the activation cache is the gradient dump ----------
-// rowcum[b][r] = sum over the sites of rows < r of the selected log-amplitude term, from the dumped logits (fixed order)
-__global__ void tc_rowcum_kernel(const float* __restrict__ logits, const int8_t* __restrict__ sigma, long long B, int H, int W, int P,
-                                 float* __restrict__ rowcum) {
-  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const float4* lg = reinterpret_cast<const float4*>(logits) + b * 128;
-  float2* rc = reinterpret_cast<float2*>(rowcum) + b * (long long)(H + 1);
-  float re = 0.f, im = 0.f;
-  rc[0] = make_float2(0.f, 0.f);
-  for (int r = 0; r < H; ++r) {
-    for (int c = 0; c < W; ++c) {
-      const float4 l4 = lg[r * P + c];
-      const float x = 2.f * l4.x, y = 2.f * l4.y;
-      const float m = fmaxf(x, y);
-      const float half_lse = 0.5f * (m + logf(expf(x - m) + expf(y - m)));
-      const bool up = sigma[b * (long long)(H * W) + r * W + c] > 0;
-      re += (up ? l4.x : l4.y) - half_lse;
-      im += up ? l4.z : l4.w;
-    }
-    rc[r + 1] = make_float2(re, im);
-  }
+// the samples' own selected log-amplitude term of every site, from the dumped logits: [b][site] float2
+__global__ void tc_siteterm_kernel(const float* __restrict__ logits, const int8_t* __restrict__ sigma, long long B, int H, int W, int P,
+                                   float* __restrict__ siteterm) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int HW = H * W;
+  if (e >= B * HW) return;
+  const long long b = e / HW;
+  const int site = (int)(e - b * HW), r = site / W, c = site - r * W;
+  const float4 l4 = reinterpret_cast<const float4*>(logits)[b * 128 + r * P + c];
+  const float x = 2.f * l4.x, y = 2.f * l4.y;
+  const float m = fmaxf(x, y);
+  const float half_lse = 0.5f * (m + logf(expf(x - m) + expf(y - m)));
+  const bool up = sigma[e] > 0;
+  reinterpret_cast<float2*>(siteterm)[e] = make_float2((up ? l4.x : l4.y) - half_lse, up ? l4.z : l4.w);
 }
 
 int tc_prefix_supported(const fk_net* net) {
@@ -1086,7 +1079,7 @@ static TcPrefixLayout tc_prefix_layout(const fk_net* net, int64_t B, int64_t cap
   L.dump = o; o = al(o + (size_t)B * L.stride);
   L.mask = o; o = al(o + (size_t)B * nb * TC_DUMP_TENSORS * 128 * 4);
   L.logits = o; o = al(o + (size_t)B * 128 * 16);
-  L.rowcum = o; o = al(o + (size_t)B * (net->H + 1) * 8);
+  L.rowcum = o; o = al(o + (size_t)B * net->sites * 8);
   L.tiles_ws = o; o = al(o + (size_t)xp_tiles_workspace_bytes(cap));
   L.total = o;
   return L;
@@ -1106,8 +1099,8 @@ int tc_local_energy_prefix(fk_net* net, const int8_t* sigma, int64_t B, int64_t 
   if (tc_forward_launch(net, sigma, B, const_cast<float*>(work->logpsi0), base + L.dump, reinterpret_cast<uint32_t*>(base + L.mask),
                         reinterpret_cast<float*>(base + L.logits), s))
     return 1;
-  tc_rowcum_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(reinterpret_cast<const float*>(base + L.logits), sigma, B, net->H, net->W,
-                                                                g.P, rowcum);
+  tc_siteterm_kernel<<<(unsigned)((B * net->sites + 255) / 256), 256, 0, s>>>(reinterpret_cast<const float*>(base + L.logits), sigma, B,
+                                                                               net->H, net->W, g.P, rowcum);
   FK_CHECK_LAUNCH();
   const int2* tiles = nullptr;
   const long long* n_tiles = nullptr;

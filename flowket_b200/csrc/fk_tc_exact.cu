@@ -580,8 +580,9 @@ __global__ void __launch_bounds__(X_NP * X_EPI + 32 + X_ISSUERS * 32, 1) tcx_for
                   const float m = fmaxf(x, y);
                   const float half_lse = 0.5f * (m + logf(expf(x - m) + expf(y - m)));
                   const bool up = sig > 0.f;
-                  sre = (up ? re0 : re1) - half_lse;
-                  sim = up ? im0 : im1;
+                  const float2 base = *reinterpret_cast<const float2*>(a.px.rowcum + 2 * ((size_t)smp[seg] * HW + lsite));
+                  sre = (up ? re0 : re1) - half_lse - base.x;      // difference to the sample's own term of this site
+                  sim = (up ? im0 : im1) - base.y;
                 }
               }
               float s_re[2], s_im[2];
@@ -611,9 +612,7 @@ __global__ void __launch_bounds__(X_NP * X_EPI + 32 + X_ISSUERS * 32, 1) tcx_for
                   t0 += red[((pipe * 4 + w) * 2 + sgi) * 2 + 0];
                   t1 += red[((pipe * 4 + w) * 2 + sgi) * 2 + 1];
                 }
-                const float2 pre = *reinterpret_cast<const float2*>(a.px.rowcum + 2 * ((size_t)smp[sgi] * (H + 1) + r0[sgi]));
-                const float lr = pre.x + t0, li = pre.y + t1;      // log psi of the connected configuration
-                const float dr = lr - a.wk.logpsi0[2 * smp[sgi]], di = li - a.wk.logpsi0[2 * smp[sgi] + 1];
+                const float dr = t0, di = t1;      // log psi(sigma') - log psi(sigma): the rows above r0 cancel exactly
                 const float mag = expf(dr), m = a.wk.mel[cfgs[sgi]];
                 float sn, cs;
                 sincosf(di, &sn, &cs);
@@ -979,23 +978,6 @@ __global__ void tcx_tiles_kernel(const TcxPlan* __restrict__ plan, const int* __
   }
 }
 
-// rowcum[b][r] = sum of the selected log-amplitude terms of the sites of rows < r (fixed order: deterministic)
-__global__ void tcx_rowcum_kernel(const float* __restrict__ siteterm, long long B, int H, int W, float* __restrict__ rowcum) {
-  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const float2* st = reinterpret_cast<const float2*>(siteterm) + b * (long long)(H * W);
-  float2* rc = reinterpret_cast<float2*>(rowcum) + b * (long long)(H + 1);
-  float re = 0.f, im = 0.f;
-  rc[0] = make_float2(0.f, 0.f);
-  for (int r = 0; r < H; ++r) {
-    for (int c = 0; c < W; ++c) {
-      const float2 t = st[r * W + c];
-      re += t.x; im += t.y;
-    }
-    rc[r + 1] = make_float2(re, im);
-  }
-}
-
 int tcx_pack_weights(fk_net* net, cudaStream_t s) {
   if (!net->d_tc_exact) return 0;
   const int nb = 2 * net->depth - 2;
@@ -1074,7 +1056,7 @@ int xp_build_tiles(const fk_net* net, const TcWork* work, int64_t cap, void* ws,
   return 0;
 }
 
-struct XpLayout { size_t cache, siteterm, rowcum, tiles_ws, total, stride; };
+struct XpLayout { size_t cache, siteterm, tiles_ws, total, stride; };
 static XpLayout xp_layout(const fk_net* net, int64_t B, int64_t cap) {
   const TcxGeometry g = tcx_geometry(net);
   const int nb = 2 * net->depth - 2;
@@ -1083,7 +1065,6 @@ static XpLayout xp_layout(const fk_net* net, int64_t B, int64_t cap) {
   size_t o = 0;
   L.cache = o; o = x256(o + (size_t)B * L.stride);
   L.siteterm = o; o = x256(o + (size_t)B * net->sites * 8);
-  L.rowcum = o; o = x256(o + (size_t)B * (net->H + 1) * 8);
   L.tiles_ws = o; o = x256(o + (size_t)xp_tiles_workspace_bytes(cap));
   L.total = o;
   return L;
@@ -1100,18 +1081,15 @@ int tcx_local_energy_prefix(fk_net* net, const int8_t* sigma, int64_t B, int64_t
   FK_REQUIRE((int64_t)L.total <= ws_bytes, "tc-exact prefix reuse: workspace too small (%lld < %zu)", (long long)ws_bytes, L.total);
   uint8_t* base = (uint8_t*)ws;
   float* siteterm = reinterpret_cast<float*>(base + L.siteterm);
-  float* rowcum = reinterpret_cast<float*>(base + L.rowcum);
   const int rcap = xp_rcap(net);
   // dump pass: log psi of the samples + their activation cache + per-site terms
   TcxPrefix pd = {nullptr, nullptr, nullptr, nullptr, base + L.cache, siteterm, (long long)L.stride, rcap};
   if (tcx_launch(net, sigma, B, const_cast<float*>(work->logpsi0), s, nullptr, &pd)) return 1;
-  tcx_rowcum_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(siteterm, B, net->H, net->W, rowcum);
-  FK_CHECK_LAUNCH();
   const int2* tiles = nullptr;
   const long long* n_tiles = nullptr;
   if (xp_build_tiles(net, work, cap, base + L.tiles_ws, &tiles, &n_tiles, s)) return 1;
   // tile pass
-  TcxPrefix pt = {tiles, n_tiles, base + L.cache, rowcum, nullptr, nullptr, (long long)L.stride, rcap};
+  TcxPrefix pt = {tiles, n_tiles, base + L.cache, siteterm, nullptr, nullptr, (long long)L.stride, rcap};
   return tcx_launch(net, sigma, cap, nullptr, s, work, &pt);
 }
 
