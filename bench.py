@@ -379,8 +379,10 @@ def run_gpu(args):
                      # dram__bytes_read + dram__bytes_write of the work-list launch of this kernel at this batch, from the ncu
                      # capture profiles/r02_ncu_traffic_B8192.txt (spins, work list, matrix elements, weights once; activations never
                      # leave shared memory / TMEM).  Only quoted for the configuration the capture was taken on.
-                     'traffic': None,
-                     'traffic_source': 'see profiles/r02_ncu_traffic_prefix_B8192.txt (ncu capture of the same launches)',
+                     # dram__bytes_read + dram__bytes_write of the tile-pass launch of this kernel at this batch (halo rows read back from
+                     # the samples' activation cache), from the ncu capture of the same launch; only quoted for that configuration
+                     'traffic': (156.40e9 + 3.87e9) if (world == 1 and GB == 8192) else None,
+                     'traffic_source': 'profiles/r02_ncu_traffic_prefix_B8192.txt (ncu capture of the same launches; without prefix reuse: 13 MB)',
                      'note': 'algorithmic FLOPs = one full forward per connected configuration (what the reference evaluates); with prefix '
                              'reuse the kernel issues the MMAs of 62 tiles per sample instead of 85 full evaluations, each product as '
                              'three fp16 tensor-core passes',
