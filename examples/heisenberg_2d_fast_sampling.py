@@ -14,11 +14,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-from flowket_b200 import Input, Model, FK_ENGINE_TC, FK_ENGINE_FP32  # noqa: E402
+from flowket_b200 import Input, Model, FK_ENGINE_TC, FK_ENGINE_TC_EXACT, FK_ENGINE_FP32  # noqa: E402
 from flowket_b200.machines import ConvNetAutoregressive2D  # noqa: E402
 from flowket_b200.operators import Heisenberg  # noqa: E402
 from flowket_b200.optimization import VariationalMonteCarlo, DistributedVariationalMonteCarlo  # noqa: E402
-from flowket_b200.optimizers import Adam, Trainer  # noqa: E402
+from flowket_b200.optimizers import Adam, StochasticReconfiguration, Trainer  # noqa: E402
 from flowket_b200.samplers import FastAutoregressiveSampler  # noqa: E402
 
 
@@ -34,7 +34,11 @@ def main():
     ap.add_argument('--depth', type=int, default=20)
     ap.add_argument('--width', type=int, default=32)
     ap.add_argument('--lr', type=float, default=1e-3)
-    ap.add_argument('--engine', default='tc', choices=['tc', 'fp32'])
+    ap.add_argument('--engine', default='tc', choices=['tc', 'tc_exact', 'fp32'],
+                    help='local-energy engine (the sampler and the gradient use the fp16 tensor-core engine unless fp32)')
+    ap.add_argument('--optimizer', default='adam', choices=['adam', 'sr'],
+                    help="sr: stochastic reconfiguration in sample space, device pipeline (north_star's target step)")
+    ap.add_argument('--diag_shift', type=float, default=0.05)
     args = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -48,7 +52,8 @@ def main():
     convnet = ConvNetAutoregressive2D(inputs, depth=args.depth, num_of_channels=args.width, weights_normalization=False, seed=0)
     model = Model(inputs=inputs, outputs=convnet.predictions)
     conditional_log_probs_model = Model(inputs=inputs, outputs=convnet.conditional_log_probs)
-    model.engine = conditional_log_probs_model.engine = FK_ENGINE_TC if args.engine == 'tc' else FK_ENGINE_FP32
+    conditional_log_probs_model.engine = FK_ENGINE_FP32 if args.engine == 'fp32' else FK_ENGINE_TC
+    model.engine = {'tc': FK_ENGINE_TC, 'tc_exact': FK_ENGINE_TC_EXACT, 'fp32': FK_ENGINE_FP32}[args.engine]
     if world > 1:
         dist.broadcast(convnet.flat_params_device(), src=0)
         convnet.params_updated()
@@ -56,7 +61,11 @@ def main():
     operator = Heisenberg(hilbert_state_shape=(10, 10), pbc=False)
     vmc_cls = DistributedVariationalMonteCarlo if world > 1 else VariationalMonteCarlo
     variational_monte_carlo = vmc_cls(model, operator, sampler)
-    trainer = Trainer(model, variational_monte_carlo, Adam(lr=args.lr, beta_1=0.9, beta_2=args.beta_2), distributed=world > 1)
+    if args.optimizer == 'sr':
+        optimizer = StochasticReconfiguration(model, lr=args.lr, diag_shift=args.diag_shift, sample_space=True, distributed=world > 1)
+    else:
+        optimizer = Adam(lr=args.lr, beta_1=0.9, beta_2=args.beta_2)
+    trainer = Trainer(model, variational_monte_carlo, optimizer, distributed=world > 1)
     if args.checkpoint and os.path.exists(args.checkpoint + '.npz'):
         trainer.load_checkpoint(args.checkpoint)
         if rank == 0:

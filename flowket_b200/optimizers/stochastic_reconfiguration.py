@@ -364,7 +364,8 @@ class StochasticReconfiguration(_SRBase):
       * sample space  delta = X^T (X X^T / B + lambda I)^-1 e' / B -- the push-through identity, exact, with a
                       2B x 2B Gram whose K dimension is the parameter axis.  This is the form that fits the 850 k
                       parameter machine of the headline configuration (P x P would be 2.9 TB): the Gram is one
-                      tensor-core GEMM (cuBLAS, bf16 operands / fp32 accumulation by default) + a Cholesky of size 2B.
+                      tensor-core GEMM (hand-written tcgen05 kernel behind fk_sr_gram_xxt, bf16 operands / fp32 accumulation;
+                      sample_space_sr.py) + a Cholesky of size 2B.
     `sample_space=None` picks the sample-space form when P > 2B."""
 
     def __init__(self, model, sample_space=None, gram_dtype='bf16', jacobian_chunk=1024, shared_cholesky=False,
