@@ -432,6 +432,8 @@ class StochasticReconfiguration(_SRBase):
             if self.read_timings:
                 torch.cuda.synchronize()
                 self.last_timings_ms = dict(pipe.read_timings())
+                if pipe.needs_fp64_solve:
+                    delta = pipe.refine_with_fp64()
                 if pipe.potrf_info != 0:
                     raise RuntimeError('sample-space SR: the Cholesky factorisation failed (potrf info %d)' % pipe.potrf_info)
             return delta

@@ -327,6 +327,11 @@ def test_jacobian_rows_bf16_and_device_sr_pipeline(shape, depth, wn, B):
     sr64 = StochasticReconfiguration(model, diag_shift=0.05, sample_space=True, solver='fp64')
     d64 = sr64.compute_update(sg, eloc).cpu().numpy()
     assert np.linalg.norm(d64 - got_delta) / np.linalg.norm(d64) < 1e-5
+    # a refinement that does not reach its tolerance is repeated in fp64 automatically (forced here with a tolerance of zero)
+    sr._pipeline.refinement_tol = 0.0
+    d_fb = sr.compute_update(sg, eloc).cpu().numpy()
+    assert sr._pipeline.fp64_fallbacks == 1
+    assert np.linalg.norm(d_fb - d64) / np.linalg.norm(d64) < 1e-6
 
 
 # ---------------------------------------------------------------------------------------------------------------------
