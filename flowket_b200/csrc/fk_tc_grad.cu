@@ -594,11 +594,19 @@ __global__ void __launch_bounds__(384, 1) tc_dw_kernel(DwArgs2 a) {
 // starves the workers' loads (their two passes stretch from ~1.5 k to ~14 k cycles, tools/dw_rows_trace.py).  What would
 // help is less operand traffic per configuration -- e.g. four configurations stacked along M and N (block-diagonal
 // product, 2 KB instead of 5 KB per configuration and k-step) -- which needs a different TMEM budget; not built.
-//   roles (384 threads): warp 2 producer | warp 1 MMA issuer | warps 0, 4, 8 drainers | warps 3, 5, 6, 7, 9, 10, 11 workers
+//   roles (384 threads): warp 2 producer | warp 1 MMA issuer | drainers: warps 0, 4 (TMEM quadrant 0) and 5, 9 (quadrant 1) |
+//                        workers: warps 3, 6, 7, 8, 10, 11      (M = 128 variant: drainers 0, 4, 8, workers 3, 5, 6, 7, 9, 10, 11)
 //   barriers: full/empty[stage] (operand ring), done (MMAs of the item retired), tfree (TMEM drained, 3 arrivals),
 //             sfull (staging written, 3 arrivals), sfree (staging consumed, 7 arrivals)
 // ================================================================================================================
-constexpr int DWR_WORKERS = 7;
+// M = 64 MMAs: the A tile is the input-channel axis, of which 32 rows are real -- M = 64 halves the operand bytes the
+// tensor core fetches for it (8 channel groups instead of 16).  Accumulator layout of a cta_group::1 M = 64 MMA: row r lives
+// in TMEM lane 32 (r / 16) + r % 16, so the 32 real rows sit in lanes 0..15 of quadrants 0 and 1 -- two drainers per quadrant.
+// Measured: 116.0 ms per 8192 samples with either M (the MN-major MMAs retire at ~75 cycles each regardless of the A bytes), so
+// this only takes load off the shared-memory pipe; both variants pass the parity tests.
+constexpr bool DWR_M64 = true;
+constexpr int DWR_DRAINERS = DWR_M64 ? 4 : 3;
+constexpr int DWR_WORKERS = DWR_M64 ? 6 : 7;
 constexpr int DWR_SLOTS = 12;                            // taps of the largest unit (V: 9 + X: 3)
 constexpr int DWR_STAGING_FLOATS = DWR_SLOTS * 32 * 36;  // [tap slot][ci][36]: rows padded for conflict-free 128-bit access
 // after the operand ring: barriers (128 B) | staging | v_hat cache | coefficients [3][64] | partial dots [2][3][7][32] |
@@ -626,8 +634,8 @@ __global__ void __launch_bounds__(384, 1) tc_dw_rows_kernel(DwArgs2 a) {
   if (tid == 32) {
     for (int i = 0; i < 2; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
     mbar_init(done, 1);
-    mbar_init(tfree, 3);
-    mbar_init(sfull, 3);
+    mbar_init(tfree, DWR_DRAINERS);
+    mbar_init(sfull, DWR_DRAINERS);
     mbar_init(sfree, DWR_WORKERS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -653,10 +661,19 @@ __global__ void __launch_bounds__(384, 1) tc_dw_rows_kernel(DwArgs2 a) {
   const uint64_t bdesc0 = make_desc(0, 8, 128);
   const long long items = (long long)a.num_units * a.n;    // unit-major: the CTAs in flight write adjacent rows of the same panels
 
-  const int fidx = warp >> 2;
-  const bool is_drain = (warp & 3) == 0;
-  int widx = -1;                                            // worker index 0..6
-  if (warp == 3) widx = 0; else if (warp >= 5 && warp <= 7) widx = warp - 4; else if (warp >= 9) widx = warp - 5;
+  // drainer (quadrant dq, index dd among the drainers of the quadrant) / worker index
+  bool is_drain;
+  int dq = 0, dd = 0, dn = 1, widx = -1;
+  if (DWR_M64) {
+    is_drain = warp == 0 || warp == 4 || warp == 5 || warp == 9;
+    dq = warp & 3; dd = (warp == 0 || warp == 5) ? 0 : 1; dn = 2;
+    const int wmap[12] = {-1, -1, -1, 0, -1, -1, 1, 2, 3, -1, 4, 5};
+    widx = wmap[warp];
+  } else {
+    is_drain = (warp & 3) == 0;
+    dd = warp >> 2; dn = 3;
+    if (warp == 3) widx = 0; else if (warp >= 5 && warp <= 7) widx = warp - 4; else if (warp >= 9) widx = warp - 5;
+  }
 
   if (warp == 2) {
     // ---- producer: one stage per item
@@ -697,7 +714,8 @@ __global__ void __launch_bounds__(384, 1) tc_dw_rows_kernel(DwArgs2 a) {
         const uint32_t sb16 = smem_u32(smem + (size_t)st * stage_bytes) >> 4;
         for (int k = 0; k < u.nconv; ++k) {
           const int ntaps = u.conv[k].ntaps, n = u.conv[k].n, col0 = u.conv[k].col0;
-          const uint32_t idesc = make_idesc(n) | (1u << 15) | (1u << 16);   // A and B MN-major
+          uint32_t idesc = make_idesc(n) | (1u << 15) | (1u << 16);   // A and B MN-major
+          if (DWR_M64) idesc = (idesc & ~(0x1Fu << 24)) | ((64u >> 4) << 24);
           const uint32_t x16 = sb16 + (uint32_t)k * (uint32_t)(xt_bytes >> 4);
           const uint64_t bd0 = bdesc0 + (uint64_t)(sb16 + (uint32_t)(3 * (xt_bytes >> 4)) + (uint32_t)k * (DZ_TILE >> 4) +
                                                    (uint32_t)u.conv[k].dz_cg * 128u);
@@ -730,18 +748,25 @@ __global__ void __launch_bounds__(384, 1) tc_dw_rows_kernel(DwArgs2 a) {
       for (int k = 0; k < u.nconv; ++k) {
         const int ntaps = u.conv[k].ntaps, n = u.conv[k].n, col0 = u.conv[k].col0;
         for (int t = 0; t < ntaps; ++t, ++slot) {
-          if (slot % 3 != fidx) continue;
-          float* dst = stg + ((size_t)slot * 32 + lane) * 36;
+          if (slot % dn != dd) continue;
+          const uint32_t tq = tmem + ((uint32_t)(dq * 32) << 16);          // this warp's TMEM lane quadrant
+          const int row = DWR_M64 ? dq * 16 + lane : lane;                  // input channel held by this lane
+          const bool live = !DWR_M64 || lane < 16;
+          float* dst = stg + ((size_t)slot * 32 + row) * 36;
           if (n == 32) {
             float v[32];
-            tmem_ld32(tmem + (uint32_t)(col0 + t * 32), v);
+            tmem_ld32(tq + (uint32_t)(col0 + t * 32), v);
+            if (live) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
           } else {
             float v[16];
-            tmem_ld16(tmem + (uint32_t)(col0 + t * 16), v);
+            tmem_ld16(tq + (uint32_t)(col0 + t * 16), v);
+            if (live) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
           }
         }
       }

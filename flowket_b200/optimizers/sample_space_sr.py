@@ -192,7 +192,6 @@ class DeviceSampleSpaceSR(object):
         ev[6].record()
         self._events = ev
         self._info = info
-        self._resid = resid
         return delta
 
     def read_timings(self):
