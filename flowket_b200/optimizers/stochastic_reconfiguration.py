@@ -427,7 +427,10 @@ class StochasticReconfiguration(_SRBase):
             world = self._world_size() if self.distributed else 1
             sample_space = net0.num_params > 2 * int(sigma.shape[0]) * world   # P > 2 B_global
         pipe = self._device_pipeline() if sample_space else None
-        if pipe is not None and (not self.distributed or (2 * int(sigma.shape[0])) % 128 == 0):
+        use_pipe = pipe is not None and (not self.distributed or (2 * int(sigma.shape[0])) % 128 == 0)
+        if callable(local_energy) and not use_pipe:      # only the device pipeline can defer the local energies
+            local_energy = local_energy()
+        if use_pipe:
             delta = pipe.delta(sigma, local_energy, distributed=self.distributed)
             if self.read_timings:
                 torch.cuda.synchronize()
