@@ -163,7 +163,7 @@ def workload_config(args, world):
                         'batch %d sharded over the GPUs (BASELINE.json configs[2]: "batch 8192 on 8xB200")' % args.global_batch,
             'lattice': [H, W], 'depth': DEPTH, 'channels': CHANNELS, 'global_batch': args.global_batch,
             'batch_per_gpu': args.global_batch // world,
-            'step': 'sample + E_loc + SR update (diag_shift 0.05, lr 0.01, sample-space form of optimizer.py:55-108); order on the device: sample, Jacobian rows, Gram, E_loc, centring, solve, update',
+            'step': 'sample + E_loc + SR update (diag_shift 0.05, lr 0.01, sample-space form of optimizer.py:55-108)',
             'engines': {'sampler': 'tcgen05 fp16 operands / fp32 accumulate (fk_sample_tc)',
                         'local_energy': 'value: tc-exact (fp16 hi+lo split operands, 22 bits, fp32 accumulate); value_fast: fp16 operands',
                         'jacobian': 'tcgen05 fp16 operands / fp32 accumulate, rows stored in bf16',
@@ -225,9 +225,8 @@ def run_gpu(args):
         """sample -> local energy -> SR update; inputs and outputs stay in HBM"""
         model.engine = engine
         sigma = sampler.next_device()
-        # the local energies are handed over as a callable: the SR pipeline evaluates them between its Gram and its solve (same
-        # work, different order -- the factorisation then does not start on the clock the power-capped Gram leaves behind)
-        sr.step(sigma, lambda: obs.local_values_device(model, sigma))
+        eloc = obs.local_values_device(model, sigma)
+        sr.step(sigma, eloc)
         machine.device_net()              # re-derive the effective (weight-normalised) kernels, repack the operand images
 
     def timed(fn, steps):
@@ -277,14 +276,14 @@ def run_gpu(args):
             ev[0].record()
             sigma = sampler.next_device()
             ev[1].record()
-            sr.step(sigma, lambda: obs.local_values_device(model, sigma))
+            eloc = obs.local_values_device(model, sigma)
             ev[2].record()
+            sr.step(sigma, eloc)
             machine.device_net()
             ev[3].record()
             torch.cuda.synchronize()
-            cur = {'sample': ev[0].elapsed_time(ev[1]), 'eloc': sr.last_timings_ms['eloc'],
-                   'sr_update': ev[1].elapsed_time(ev[2]) - sr.last_timings_ms['eloc'], 'repack': ev[2].elapsed_time(ev[3])}
-            cur.update({'sr_' + k: v for k, v in sr.last_timings_ms.items() if k not in ('solve', 'eloc')})
+            cur = {'sample': ev[0].elapsed_time(ev[1]), 'eloc': ev[1].elapsed_time(ev[2]), 'sr_total': ev[2].elapsed_time(ev[3])}
+            cur.update({'sr_' + k: v for k, v in sr.last_timings_ms.items() if k != 'solve'})
             if best is None or cur['eloc'] < best['eloc']:
                 best = cur
         phases[tag] = best

@@ -135,9 +135,10 @@ class DeviceSampleSpaceSR(object):
         cws_b = lib.fk_sr_centre_shift_workspace_bytes(R)
         cws = net.workspace('sr_centre_ws', cws_b)
         # `local_energy` may be a callable: the local energies do not depend on the Jacobian or the Gram matrix, so they can be
-        # evaluated HERE, between the Gram and the solve.  That is not only a matter of taste: the Gram runs the GPU into its
-        # power cap (SM clock ~1.2 GHz), and the factorisation that used to follow it inherited the throttled clock (57-70 ms
-        # against 41 ms standalone); with the local-energy kernel in between it starts at full clock.
+        # evaluated HERE, between the Gram and the solve.  The Gram runs the GPU into its power cap (SM clock ~1.2 GHz) and whatever
+        # follows it inherits the throttled clock for a while: measured at B = 8192, the factorisation drops from 57-70 ms to
+        # 43 ms (standalone: 41) when the local-energy kernel sits in between -- and the local-energy kernel pays 20-30 ms
+        # instead, so the step time is the same within the box-to-box spread.  Kept as an option; bench.py uses the plain order.
         self._eloc_events = None
         if callable(local_energy):
             ee = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
