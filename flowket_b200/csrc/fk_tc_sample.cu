@@ -34,6 +34,14 @@ __device__ __forceinline__ double tcs_philox_uniform(uint64_t seed, uint64_t sam
   return (double)((hi << 26) | lo) * (1.0 / 9007199254740992.0);
 }
 
+#ifdef FK_TS_TRACE
+// clock64 timeline of CTA 0 at site (5, 5): [block step kb][slot]  (tools/sampler_trace.py)
+__device__ long long fk_ts_trace_buf[40 * 16];
+#define TSTRACE(slot) do { if (blockIdx.x == 0 && tid == 0 && i == 5 && j == 5 && kb < 40) fk_ts_trace_buf[kb * 16 + (slot)] = clock64(); } while (0)
+#else
+#define TSTRACE(slot) do {} while (0)
+#endif
+
 constexpr int TS_TILE = 8192;       // bytes of one activation tile
 constexpr int TS_NLOAD = 12;        // loaded-tile slots
 
@@ -215,6 +223,7 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
             ++nc;
           }
         const int nxa = count_xa(i, j, b);
+        TSTRACE(0);
         if (tid == 0) {
           if (!xa_prefetched) issue_xa(i, j, b);
           if (nc > 0) {
@@ -228,6 +237,7 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
         }
         mbar_wait(wfull0 + 8 * wsel, (uint32_t)((step >> 1) & 1));
         if (nxa > 0) { mbar_wait(tfull, tile_phase); tile_phase ^= 1; }
+        TSTRACE(1);
         const uint8_t* wimg = wbuf + (size_t)wsel * IMG_CORE_BYTES;
         const uint32_t wimg16 = smem_u32(wimg) >> 4;
         const float* bias = reinterpret_cast<const float*>(wimg + IMG_BIAS);
@@ -248,6 +258,7 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
           }
         }
         if (have_x) commit_and_wait();
+        TSTRACE(2);
         {
           float v[32];
           if (have_x) {
@@ -261,6 +272,7 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
           store_tile_row(xc, nullptr, v);
         }
         end_phase();
+        TSTRACE(3);
 
         // ================= phase 2: 1x1 convs: x1 -> concat[0:16], DownShift(relu(v')) = a(i-1, j) -> concat[16:32]
         if (mma_warp) {
@@ -273,6 +285,7 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
           }
         }
         commit_and_wait();
+        TSTRACE(4);
         // the x/a slots are free now: prefetch the next step's x/a tiles (same row only; the vertical pass reuses the slots)
         {
           int ni = i, nj = j, nkb = kb + 1;
@@ -290,9 +303,11 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
           store_tile_row(xc, cache + (size_t)ts_c(W, b, i % 3, j) * TS_TILE, v);
         }
         end_phase();
+        TSTRACE(5);
 
         // ================= phase 3: 3x3 conv on the concat tensor -> h'
         if (nc > 0) { mbar_wait(cfull, c_phase); c_phase ^= 1; }
+        TSTRACE(6);
         if (mma_warp) {
           tc_fence_after();
           uint32_t acc = 0;
@@ -303,6 +318,7 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
           }
         }
         commit_and_wait();
+        TSTRACE(7);
         {
           float v[32];
           tmem_ld32(tmem + lane_sel + 64, v);
@@ -317,6 +333,7 @@ __global__ void __launch_bounds__(128, 1) tc_sample_kernel(TcSampleArgs a) {
           store_tile_row(h_out, last ? nullptr : cache + (size_t)ts_hin(W, b + 1, j) * TS_TILE, v);
         }
         end_phase(kb == nb - 1);   // end of the site: publish this site's cache tiles to the async proxy
+        TSTRACE(8);
 
         // ================= phase 4 (last block): head + normalisation + draw sigma(i,j)
         if (last) {
@@ -459,3 +476,9 @@ int tc_sample(fk_net* net, const double* uniforms, uint64_t seed, int64_t sample
 }
 
 }  // namespace fk
+
+#ifdef FK_TS_TRACE
+extern "C" int fk_ts_trace_read(long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, fk::fk_ts_trace_buf, sizeof(long long) * 40 * 16);
+}
+#endif
