@@ -360,6 +360,7 @@ struct DwConv {
   int op;                    // index of the convolution in the layer program (row of the weight-norm coefficient table)
 };
 struct DwUnit { int b, nconv; DwConv conv[3]; };
+static_assert(sizeof(DwUnit) <= 320 && sizeof(DwUnit) % 8 == 0, "tc_dw_rows_kernel stages DwUnit in 320-byte shared-memory slots");
 
 struct DwArgs2 {
   const uint8_t* dump; const uint8_t* dz; const DwUnit* units; float* geff;
@@ -594,8 +595,8 @@ __global__ void __launch_bounds__(384, 1) tc_dw_kernel(DwArgs2 a) {
 // starves the workers' loads (their two passes stretch from ~1.5 k to ~14 k cycles, tools/dw_rows_trace.py).  What would
 // help is less operand traffic per configuration -- e.g. four configurations stacked along M and N (block-diagonal
 // product, 2 KB instead of 5 KB per configuration and k-step) -- which needs a different TMEM budget; not built.
-//   roles (384 threads): warp 2 producer | warp 1 MMA issuer | drainers: warps 0, 4 (TMEM quadrant 0) and 5, 9 (quadrant 1) |
-//                        workers: warps 3, 6, 7, 8, 10, 11      (M = 128 variant: drainers 0, 4, 8, workers 3, 5, 6, 7, 9, 10, 11)
+//   roles (512 threads): warp 2 producer | MMA issuers: warps 1, 12 | drainers: warps 0, 4 (TMEM quadrant 0) and 5, 9 (quadrant 1) |
+//                        workers: warps 3, 6, 7, 8, 10, 11, 13, 14, 15
 //   barriers: full/empty[stage] (operand ring), done (MMAs of the item retired), tfree (TMEM drained, 3 arrivals),
 //             sfull (staging written, 3 arrivals), sfree (staging consumed, 7 arrivals)
 // ================================================================================================================
@@ -606,14 +607,16 @@ __global__ void __launch_bounds__(384, 1) tc_dw_kernel(DwArgs2 a) {
 // this only takes load off the shared-memory pipe; both variants pass the parity tests.
 constexpr bool DWR_M64 = true;
 constexpr int DWR_DRAINERS = DWR_M64 ? 4 : 3;
-constexpr int DWR_WORKERS = DWR_M64 ? 6 : 7;
+constexpr int DWR_WORKERS = DWR_M64 ? 9 : 7;
+constexpr int DWR_ISSUERS = 2;                           // warps 1, 12 (.. 11 + DWR_ISSUERS - 1)
+constexpr int DWR_THREADS = 512;
 constexpr int DWR_SLOTS = 12;                            // taps of the largest unit (V: 9 + X: 3)
 constexpr int DWR_STAGING_FLOATS = DWR_SLOTS * 32 * 36;  // [tap slot][ci][36]: rows padded for conflict-free 128-bit access
 // after the operand ring: barriers (128 B) | staging | v_hat cache | coefficients [3][64] | partial dots [2][3][7][32] |
-// per-worker totals [7][3][32]
-constexpr int DWR_TAIL_BYTES = 128 + 4 * (DWR_STAGING_FLOATS + DW_VH_FLOATS + 192 + 2 * 3 * DWR_WORKERS * 32 + DWR_WORKERS * 3 * 32);
+// dot totals [2][3][32]
+constexpr int DWR_TAIL_BYTES = 128 + 4 * (DWR_STAGING_FLOATS + DW_VH_FLOATS + 192 + 2 * 3 * DWR_WORKERS * 32 + 2 * 3 * 32) + 4 * 320;   // + 4 unit descriptors
 
-__global__ void __launch_bounds__(384, 1) tc_dw_rows_kernel(DwArgs2 a) {
+__global__ void __launch_bounds__(DWR_THREADS, 1) tc_dw_rows_kernel(DwArgs2 a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int xt_bytes = 64 * a.npos;
@@ -628,12 +631,17 @@ __global__ void __launch_bounds__(384, 1) tc_dw_rows_kernel(DwArgs2 a) {
   float* vh_s = stg + DWR_STAGING_FLOATS;
   float* cf_s = vh_s + DW_VH_FLOATS;                        // [3 convs][a[32] | gs[32]]
   float* xdot = cf_s + 192;                                 // [2 parities][3 convs][workers][32]
-  float* wdot = xdot + 2 * 3 * DWR_WORKERS * 32;            // [workers][3 convs][32]
+  float* wdot = xdot + 2 * 3 * DWR_WORKERS * 32;            // [2 parities][3 convs][32]: the dot totals of the item
+  // Unit descriptors in shared memory, one slot per item in flight (worker on item i - 1 ... producer on item i + 2).  A by-value
+  // copy per thread (as in tc_dw_kernel) lives on the local-memory stack because conv[k] / off[t] are indexed at run time, and with
+  // 223 KB of the SM's 256 KB carved out as shared memory the L1 that backs the stack is almost gone: every field read in the
+  // workers' inner loops went to L2 (measured: 14 k cycles per item in the two worker passes, tools/dw_rows_trace.py).
+  DwUnit* sunit = reinterpret_cast<DwUnit*>(wdot + 2 * 3 * 32);
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2]), done = smem_u32(&bars[4]), tfree = smem_u32(&bars[5]),
                  sfull = smem_u32(&bars[6]), sfree = smem_u32(&bars[7]);
   if (tid == 32) {
-    for (int i = 0; i < 2; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
-    mbar_init(done, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, DWR_ISSUERS); }
+    mbar_init(done, DWR_ISSUERS);   // every issuer commits its own MMAs
     mbar_init(tfree, DWR_DRAINERS);
     mbar_init(sfull, DWR_DRAINERS);
     mbar_init(sfree, DWR_WORKERS);
@@ -667,24 +675,31 @@ __global__ void __launch_bounds__(384, 1) tc_dw_rows_kernel(DwArgs2 a) {
   if (DWR_M64) {
     is_drain = warp == 0 || warp == 4 || warp == 5 || warp == 9;
     dq = warp & 3; dd = (warp == 0 || warp == 5) ? 0 : 1; dn = 2;
-    const int wmap[12] = {-1, -1, -1, 0, -1, -1, 1, 2, 3, -1, 4, 5};
+    const int wmap[16] = {-1, -1, -1, 0, -1, -1, 1, 2, 3, -1, 4, 5, -1, 6, 7, 8};
     widx = wmap[warp];
   } else {
     is_drain = (warp & 3) == 0;
     dd = warp >> 2; dn = 3;
-    if (warp == 3) widx = 0; else if (warp >= 5 && warp <= 7) widx = warp - 4; else if (warp >= 9) widx = warp - 5;
+    if (warp == 3) widx = 0; else if (warp >= 5 && warp <= 7) widx = warp - 4; else if (warp >= 9 && warp <= 11) widx = warp - 5;
   }
 
   if (warp == 2) {
     // ---- producer: one stage per item
-    if (lane == 0) {
-      uint32_t empty_phase = 0;
-      long long count = 0;
-      for (long long item = blockIdx.x; item < items; item += gridDim.x, ++count) {
-        const DwUnit u = a.units[item / a.n];
-        const long long cfg = item % a.n;
-        const int st = (int)(count % NST);
-        if (count >= NST) { mbar_wait(empty0 + 8 * st, (empty_phase >> st) & 1u); empty_phase ^= 1u << st; }
+    uint32_t empty_phase = 0;
+    long long count = 0;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x, ++count) {
+      const long long cfg = item % a.n;
+      const int st = (int)(count % NST);
+      if (count >= NST) { mbar_wait(empty0 + 8 * st, (empty_phase >> st) & 1u); empty_phase ^= 1u << st; }
+      // the item's unit descriptor -> its shared-memory slot (whole warp), visible to the other roles through the `full` barrier
+      {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(a.units + item / a.n);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(sunit + (count & 3));
+        for (int w = lane; w < (int)(sizeof(DwUnit) / 4); w += 32) dst[w] = __ldg(src + w);
+        __syncwarp();
+      }
+      if (lane == 0) {
+        const DwUnit& u = sunit[count & 3];
         uint8_t* sb = smem + (size_t)st * stage_bytes;
         mbar_expect_tx(full0 + 8 * st, (uint32_t)u.nconv * (xt_bytes + DZ_TILE));
         for (int k = 0; k < u.nconv; ++k) {
@@ -694,24 +709,29 @@ __global__ void __launch_bounds__(384, 1) tc_dw_rows_kernel(DwArgs2 a) {
                    a.dz + (((size_t)cfg * a.nb + u.b) * 4 + u.conv[k].dz_tile) * DZ_TILE, DZ_TILE, full0 + 8 * st);
         }
       }
+      __syncwarp();
     }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ---- MMA issuer (elected lane of the converged warp)
+  } else if (warp == 1 || (warp >= 12 && warp < 11 + DWR_ISSUERS)) {
+    // ---- MMA issuers (elected lane of a converged warp each).  One thread issues one tcgen05.mma per ~82 cycles whatever the
+    // operands (tools/umma_bench3.cu: 82 / 41 / 24 cycles per M = 64, N = 32 MMA with 1 / 2 / 4 issuing warps -- the last is
+    // the 128 B/clk operand stream), so the taps of an item are dealt to DWR_ISSUERS warps; a tap's eight k-steps stay with
+    // one issuer (same accumulator columns, program order), every issuer commits its own MMAs to `empty` and `done`.
+    const int iss = __shfl_sync(0xffffffffu, warp == 1 ? 0 : warp - 11, 0);
     uint32_t full_phase = 0;
     long long count = 0;
     for (long long item = blockIdx.x; item < items; item += gridDim.x, ++count) {
-      const DwUnit u = a.units[item / a.n];
-      DWTRACE(count, 0);
+      const DwUnit& u = sunit[count & 3];   // (written by the producer before the item's TMA: valid once `full` has been seen)
+      if (iss == 0) DWTRACE(count, 0);
       mbar_wait(tfree, (uint32_t)((count & 1) ^ 1));   // accumulators of the previous item drained (passes at once for the first)
       tc_fence_after();
-      DWTRACE(count, 1);
+      if (iss == 0) DWTRACE(count, 1);
       const int st = (int)(count % NST);
       mbar_wait(full0 + 8 * st, (full_phase >> st) & 1u); full_phase ^= 1u << st;
       tc_fence_after();
-      DWTRACE(count, 2);
+      if (iss == 0) DWTRACE(count, 2);
       if (elect_one()) {
         const uint32_t sb16 = smem_u32(smem + (size_t)st * stage_bytes) >> 4;
+        int tap_index = 0;
         for (int k = 0; k < u.nconv; ++k) {
           const int ntaps = u.conv[k].ntaps, n = u.conv[k].n, col0 = u.conv[k].col0;
           uint32_t idesc = make_idesc(n) | (1u << 15) | (1u << 16);   // A and B MN-major
@@ -719,7 +739,8 @@ __global__ void __launch_bounds__(384, 1) tc_dw_rows_kernel(DwArgs2 a) {
           const uint32_t x16 = sb16 + (uint32_t)k * (uint32_t)(xt_bytes >> 4);
           const uint64_t bd0 = bdesc0 + (uint64_t)(sb16 + (uint32_t)(3 * (xt_bytes >> 4)) + (uint32_t)k * (DZ_TILE >> 4) +
                                                    (uint32_t)u.conv[k].dz_cg * 128u);
-          for (int t = 0; t < ntaps; ++t) {
+          for (int t = 0; t < ntaps; ++t, ++tap_index) {
+            if (tap_index % DWR_ISSUERS != iss) continue;
             const uint32_t dcol = tmem + (uint32_t)(col0 + t * n);
             const uint64_t ad0 = adesc0 + (uint64_t)(x16 + (uint32_t)u.conv[k].off[t]);
             umma_f16(dcol, ad0, bd0, idesc, 0u);
@@ -731,13 +752,13 @@ __global__ void __launch_bounds__(384, 1) tc_dw_rows_kernel(DwArgs2 a) {
         umma_commit(done);
       }
       __syncwarp();
-      DWTRACE(count, 3);
+      if (iss == 0) DWTRACE(count, 3);
     }
   } else if (is_drain) {
     // ---- drainers (TMEM lane quadrant 0 = the input channels): accumulators -> staging, then TMEM is free
     long long count = 0;
     for (long long item = blockIdx.x; item < items; item += gridDim.x, ++count) {
-      const DwUnit u = a.units[item / a.n];
+      const DwUnit& u = sunit[count & 3];
       mbar_wait(done, (uint32_t)(count & 1));
       tc_fence_after();
       mbar_wait(sfree, (uint32_t)((count & 1) ^ 1));   // the workers are through with the previous item's staging
@@ -783,8 +804,9 @@ __global__ void __launch_bounds__(384, 1) tc_dw_rows_kernel(DwArgs2 a) {
     int cur_unit = -1;
     for (long long item = blockIdx.x; item < items; item += gridDim.x, ++count) {
       const int ui = (int)(item / a.n);
-      const DwUnit u = a.units[ui];
       const long long row = a.row_base + item % a.n;
+      mbar_wait(sfull, (uint32_t)(count & 1));   // (also orders this thread after the producer's write of the unit descriptor)
+      const DwUnit& u = sunit[count & 3];
       if (ui != cur_unit) {   // new unit: refresh the v_hat / coefficient cache (all workers together)
         named_sync(2, 32 * DWR_WORKERS);
         int off = 0;
@@ -806,7 +828,6 @@ __global__ void __launch_bounds__(384, 1) tc_dw_rows_kernel(DwArgs2 a) {
         named_sync(2, 32 * DWR_WORKERS);
         cur_unit = ui;
       }
-      mbar_wait(sfull, (uint32_t)(count & 1));
       if (widx == 0) DWTRACE(count, 6);
       // pass 1 (lane = output channel): partial dots dW . v_hat over this worker's taps
       float* xd = xdot + (size_t)(count & 1) * 3 * DWR_WORKERS * 32;
@@ -837,18 +858,20 @@ __global__ void __launch_bounds__(384, 1) tc_dw_rows_kernel(DwArgs2 a) {
 #ifdef FK_DW_TRACE_WORKER
       if (widx == 0) DWTRACE(count, 5);
 #endif
-      for (int k = 0; k < u.nconv; ++k) {
+      float* dt = wdot + (size_t)(count & 1) * 3 * 32;
+      if (widx < u.nconv) {   // worker k sums the partial dots of convolution k and writes the weight-norm gain gradient
+        const int k = widx;
         const DwConv& c = u.conv[k];
-        if (c.p_g < 0) continue;
-        float tot = 0.f;
+        if (c.p_g >= 0) {
+          float tot = 0.f;
 #pragma unroll
-        for (int w = 0; w < DWR_WORKERS; ++w) tot += xd[(k * DWR_WORKERS + w) * 32 + lane];
-        tot *= a.out_scale;
-        wdot[(widx * 3 + k) * 32 + lane] = tot;
-        if (widx == k % DWR_WORKERS && lane < c.n)
-          a.xrows[xrow_index(a.rld, row, c.p_g + lane)] = __float2bfloat16_rn(tot * cf_s[k * 64 + 32 + lane]);
+          for (int w = 0; w < DWR_WORKERS; ++w) tot += xd[(k * DWR_WORKERS + w) * 32 + lane];
+          tot *= a.out_scale;
+          dt[k * 32 + lane] = tot;
+          if (lane < c.n) a.xrows[xrow_index(a.rld, row, c.p_g + lane)] = __float2bfloat16_rn(tot * cf_s[k * 64 + 32 + lane]);
+        }
       }
-      __syncwarp();
+      named_sync(3, 32 * DWR_WORKERS);
       // pass 2 (lane = input channel): transform and store this worker's taps
       {
         int slot = 0, off = 0;
@@ -856,7 +879,7 @@ __global__ void __launch_bounds__(384, 1) tc_dw_rows_kernel(DwArgs2 a) {
           const DwConv& c = u.conv[k];
           const int rs = c.n + 4;
           const bool wn = c.p_g >= 0;
-          const float* dk = wdot + (widx * 3 + k) * 32;
+          const float* dk = dt + k * 32;
           const float* ck = cf_s + k * 64;
           for (int t = 0; t < c.ntaps; ++t) {
             if ((slot + t) % DWR_WORKERS != widx || lane >= c.cin) continue;
@@ -1430,7 +1453,7 @@ int tc_jacobian_rows(fk_net* net, const int8_t* sigma, int64_t B, void* X, int64
       da.xrows = xr; da.rld = rld; da.row_base = row_base; da.wn_dir = net->d_wn_dir; da.wn_coef = net->d_wn_coef;
       da.stages = DW_ROWS_STAGES;
       const long long items = (long long)da.num_units * m;
-      tc_dw_rows_kernel<<<(unsigned)std::min<long long>(items, sms), 384, dw_smem, s>>>(da);
+      tc_dw_rows_kernel<<<(unsigned)std::min<long long>(items, sms), DWR_THREADS, dw_smem, s>>>(da);
       FK_CHECK_LAUNCH();
       tc_db_rows_kernel<<<dim3((unsigned)(nb * 4), (unsigned)std::min<int64_t>(m, 64)), 256, 0, s>>>(
           base + L.dz, m, nb, reinterpret_cast<const long long*>(wb + bwd_pboff_offset(nb)), xr, rld, row_base, 1.f / seed_scale);
