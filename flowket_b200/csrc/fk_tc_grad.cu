@@ -423,7 +423,7 @@ __device__ __forceinline__ void dw_flush_tap(uint32_t taddr, float* dst, int cin
 
 constexpr int DW_STAGES = 3;
 // after the operand ring and the slack rows: barriers (128 B), 3 transpose buffers, cross-warp dots + coefficients, v_hat cache
-constexpr int DW_TAIL_BYTES = 128 + 3 * 4608 + 4 * (192 + 192) + 256;
+constexpr int DW_TAIL_BYTES = 128 + 3 * 4608 + 4 * (192 + 192) + 256 + 8 * 320;   // ... + 8 unit-descriptor slots
 constexpr int DW_ROWS_STAGES = 2;
 #ifdef FK_DW_TRACE
 __device__ long long fk_dw_trace_buf[64 * 8];
@@ -446,6 +446,9 @@ __global__ void __launch_bounds__(384, 1) tc_dw_kernel(DwArgs2 a) {
   const int fidx = warp >> 2;
   const bool is_flush = (warp & 3) == 0 && fidx < nflush;
   float* flush_stage = reinterpret_cast<float*>(tail + 128) + fidx * 1152;   // 32 x 36 floats per flush warp: transpose buffer
+  // unit descriptors of the items in flight, in shared memory (slot = item counter & 7): a by-value copy per thread would live on
+  // the local-memory stack (conv[k] / off[t] are indexed at run time), whose L1 is all but gone at this shared-memory carve-out
+  DwUnit* sunit = reinterpret_cast<DwUnit*>(tail + DW_TAIL_BYTES - 8 * 320);
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[DW_STAGES]), done = smem_u32(&bars[2 * DW_STAGES]);
   if (tid == 32) {
     for (int i = 0; i < DW_STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
@@ -481,13 +484,19 @@ __global__ void __launch_bounds__(384, 1) tc_dw_kernel(DwArgs2 a) {
   const uint32_t tfree = smem_u32(&bars[2 * DW_STAGES + 1]);
   if (warp == 2) {
     // ---- producer: one stage per configuration
-    if (lane == 0) {
+    {
       uint32_t empty_phase = 0;   // bit i = parity of stage i
-      long long prod_count = 0;
-      for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        // Jacobian rows: unit-major item order, so that the CTAs in flight write adjacent rows of the same panels
-        const int ui = a.xrows ? item / chunks : item % a.num_units, ch = a.xrows ? item % chunks : item / a.num_units;
-        const DwUnit u = a.units[ui];   // by value: the asm memory clobbers / global stores would force reloads
+      long long prod_count = 0, pitem = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++pitem) {
+        const int ui = item % a.num_units, ch = item / a.num_units;
+        {   // the item's unit descriptor -> its shared-memory slot (whole warp); the other roles see it through `full`
+          const uint32_t* src = reinterpret_cast<const uint32_t*>(a.units + ui);
+          uint32_t* dst = reinterpret_cast<uint32_t*>(sunit + (pitem & 7));
+          for (int w = lane; w < (int)(sizeof(DwUnit) / 4); w += 32) dst[w] = __ldg(src + w);
+          __syncwarp();
+        }
+        if (lane != 0) continue;
+        const DwUnit& u = sunit[pitem & 7];
         const long long c_beg = (long long)ch * a.cfg_chunk;
         const long long c_end = c_beg + a.cfg_chunk < a.n ? c_beg + a.cfg_chunk : a.n;
         for (long long cfg = c_beg; cfg < c_end; ++cfg) {
@@ -511,8 +520,8 @@ __global__ void __launch_bounds__(384, 1) tc_dw_kernel(DwArgs2 a) {
     uint32_t full_phase = 0;
     long long cons_count = 0, item_count = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_count) {
-      const int ui = a.xrows ? item / chunks : item % a.num_units, ch = a.xrows ? item % chunks : item / a.num_units;
-      const DwUnit u = a.units[ui];   // by value: the asm memory clobbers / global stores would force reloads
+      const int ch = item / a.num_units;
+      const DwUnit& u = sunit[item_count & 7];   // (valid once the item's first `full` barrier has been seen)
       const long long c_beg = (long long)ch * a.cfg_chunk;
       const long long c_end = c_beg + a.cfg_chunk < a.n ? c_beg + a.cfg_chunk : a.n;
       DWTRACE(item_count, 0);
@@ -555,8 +564,8 @@ __global__ void __launch_bounds__(384, 1) tc_dw_kernel(DwArgs2 a) {
     uint32_t done_phase = 0;
     long long fitem = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++fitem) {
-      const int ui = a.xrows ? item / chunks : item % a.num_units, ch = a.xrows ? item % chunks : item / a.num_units;
-      const DwUnit u = a.units[ui];   // by value: the asm memory clobbers / global stores would force reloads
+      const int ch = item / a.num_units;
+      const DwUnit& u = sunit[fitem & 7];
       const long long c_beg = (long long)ch * a.cfg_chunk;
       mbar_wait(done, done_phase); done_phase ^= 1;
       tc_fence_after();
