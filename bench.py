@@ -158,6 +158,9 @@ METRIC = ('vmc_sr_step_samples_per_sec (exact autoregressive sampling + local en
           'Heisenberg 2D 10x10 OBC ConvNetAutoregressive2D d20 c32, global batch 8192')
 
 
+SPLIT_SOLVE_DEFAULT = False     # (flipped once the split solve is validated on 2 and 4 GPUs)
+
+
 def workload_config(args, world):
     return {'workload': 'Heisenberg 2-D 10x10 OBC, ConvNetAutoregressive2D depth 20 / 32 channels, fast sampling, global '
                         'batch %d sharded over the GPUs (BASELINE.json configs[2]: "batch 8192 on 8xB200")' % args.global_batch,
@@ -168,9 +171,13 @@ def workload_config(args, world):
                         'local_energy': 'value: tc-exact (fp16 hi+lo split operands, 22 bits, fp32 accumulate); value_fast: fp16 operands',
                         'jacobian': 'tcgen05 fp16 operands / fp32 accumulate, rows stored in bf16',
                         'gram': 'hand-written cta_group::2 tcgen05 GEMM, bf16 operands, fp32 accumulate',
-                        'solve': 'fp64 Cholesky (cuSOLVER behind fk_sr_solve)'},
+                        'solve': 'fp32 Cholesky factor (cuSOLVER behind fk_sr_factor_mixed) + fp64 iterative refinement; automatic fp64 re-solve'},
             'parallelism': 'samples sharded over %d GPU(s); all-to-all of the bf16 Jacobian rows, fp32 allreduce of the partial '
-                           'Gram matrices, allgather of the update slices' % world,
+                           'Gram matrices, allgather of the update slices' % world +
+                           ('' if world == 1 or args.no_split_solve else
+                            '; split solve: rank 0 factors the SR matrix while the other ranks evaluate local energies (the samples '
+                            'are gathered and dealt so that all ranks finish together), one allreduce of the local energies, one '
+                            'broadcast of the solution'),
             'l2_policy': 'per-step working set (28 GB of Jacobian rows, 1 GB Gram) is much larger than the 126 MB L2'}
 
 
@@ -221,11 +228,16 @@ def run_gpu(args):
         machine.params_updated()
         machine.device_net()
 
+    # world > 1: split solve -- the optimizer gets the local-energy FUNCTION; after the Gram allreduce one rank factors the
+    # (local-energy independent) matrix while the others evaluate local energies, the samples dealt so that all finish together
+    # (flowket_b200/optimizers/sample_space_sr.py); --no-split-solve: every rank evaluates its own samples and factors
+    split = world > 1 and not args.no_split_solve
+
     def sr_step(engine):
         """sample -> local energy -> SR update; inputs and outputs stay in HBM"""
         model.engine = engine
         sigma = sampler.next_device()
-        eloc = obs.local_values_device(model, sigma)
+        eloc = obs.per_sample_device(model) if split else obs.local_values_device(model, sigma)
         sr.step(sigma, eloc)
         machine.device_net()              # re-derive the effective (weight-normalised) kernels, repack the operand images
 
@@ -276,14 +288,19 @@ def run_gpu(args):
             ev[0].record()
             sigma = sampler.next_device()
             ev[1].record()
-            eloc = obs.local_values_device(model, sigma)
+            eloc = obs.per_sample_device(model) if split else obs.local_values_device(model, sigma)
             ev[2].record()
             sr.step(sigma, eloc)
             machine.device_net()
             ev[3].record()
             torch.cuda.synchronize()
             cur = {'sample': ev[0].elapsed_time(ev[1]), 'eloc': ev[1].elapsed_time(ev[2]), 'sr_total': ev[2].elapsed_time(ev[3])}
-            cur.update({'sr_' + k: v for k, v in sr.last_timings_ms.items() if k != 'solve'})
+            tm = dict(sr.last_timings_ms)
+            if split:      # rank 0's view: its share of the local energies and the factorisation sit inside the update
+                cur['eloc'] = tm.pop('eloc', 0.0)
+                cur['sr_total'] -= cur['eloc']
+                cur['eloc_samples_rank0'] = tm.pop('eloc_samples', 0)
+            cur.update({'sr_' + k: v for k, v in tm.items() if k != 'solve'})
             if best is None or cur['eloc'] < best['eloc']:
                 best = cur
         phases[tag] = best
@@ -299,11 +316,16 @@ def run_gpu(args):
     h2d, d2h = [0], [0]
 
     def e2e_step():
-        x, y = vmc.next_batch()                      # D2H: sigma (int8 host ndarray) + E_loc (complex128 host ndarray)
-        sr.step(x, vmc.current_local_energy)          # H2D: sigma + local energies as host ndarrays
+        if split:
+            sr.step_generator(vmc)                       # D2H: sigma; H2D: sigma; D2H: this rank's E_loc + the energy
+            x = vmc.current_batch
+            h2d[0] = x.nbytes
+        else:
+            x, y = vmc.next_batch()                      # D2H: sigma (int8 host ndarray) + E_loc (complex128 host ndarray)
+            sr.step(x, vmc.current_local_energy)          # H2D: sigma + local energies as host ndarrays
+            h2d[0] = x.nbytes + vmc.current_local_energy.nbytes
         machine.device_net()
         e = complex(vmc.current_energy)               # the step's result on the host
-        h2d[0] = x.nbytes + vmc.current_local_energy.nbytes
         d2h[0] = x.nbytes + vmc.current_local_energy.nbytes + 16
         return e
 
@@ -350,10 +372,21 @@ def run_gpu(args):
     ms_per_step = total_ms / args.steps
     value = GB / (ms_per_step * 1e-3)
     fast_step = fast_ms / args.steps
-    flops_eloc = n_conn * F_FWD                   # algorithmic: (1 + n_conn) * F_fwd per sample, SURVEY 8(d), this rank's share
     eloc_exact_ms, eloc_fast_ms = phases['exact']['eloc'], phases['fast']['eloc']
-    tf_exact = flops_eloc / (eloc_exact_ms * 1e-3) / 1e12
-    tf_fast = flops_eloc / (eloc_fast_ms * 1e-3) / 1e12
+    # samples whose local energies rank 0 evaluated in the phase pass (split solve: its share of the global batch, which may
+    # be empty when the factorisation alone takes as long as the other ranks' local energies)
+    n_exact = phases['exact'].get('eloc_samples_rank0', B)
+    n_fast = phases['fast'].get('eloc_samples_rank0', B)
+    conn_per_sample = n_conn / float(n_fast) if n_fast else None        # (the last phase pass was the fp16 engine's)
+    if conn_per_sample is None:
+        conn_per_sample = 85.3                                            # measured at N = 1 on this workload
+    flops_eloc = conn_per_sample * n_exact * F_FWD     # algorithmic: (1 + n_conn) * F_fwd per sample, SURVEY 8(d), this rank's share
+
+    def rate(x, ms):
+        return x / (ms * 1e-3) if ms and ms > 0 else None
+
+    tf_exact = (rate(flops_eloc, eloc_exact_ms) or 0.0) / 1e12
+    tf_fast = (rate(conn_per_sample * n_fast * F_FWD, eloc_fast_ms) or 0.0) / 1e12
     P = net.num_params
     Kg = (P + world - 1) // world
     nt = (2 * GB + 255) // 256
@@ -367,9 +400,12 @@ def run_gpu(args):
         'value_fast': GB / (fast_step * 1e-3), 'ms_per_step_fast': fast_step,
         'phases_ms': phases,
         'sampling_samples_per_s': GB / (phases['exact']['sample'] * 1e-3),
-        'eloc_evals_per_s': GB / (eloc_exact_ms * 1e-3), 'eloc_evals_per_s_fast': GB / (eloc_fast_ms * 1e-3),
-        'psi_evals_per_s': n_conn * world / (eloc_exact_ms * 1e-3), 'psi_evals_per_s_fast': n_conn * world / (eloc_fast_ms * 1e-3),
-        'connections_per_sample': n_conn / float(B),
+        # (rank 0's rate x the number of GPUs)
+        'eloc_evals_per_s': rate(n_exact * world, eloc_exact_ms), 'eloc_evals_per_s_fast': rate(n_fast * world, eloc_fast_ms),
+        'psi_evals_per_s': rate(conn_per_sample * n_exact * world, eloc_exact_ms),
+        'psi_evals_per_s_fast': rate(conn_per_sample * n_fast * world, eloc_fast_ms),
+        'connections_per_sample': conn_per_sample,
+        'split_solve': bool(split),
         'e2e': {'value': GB / (e2e_ms / args.steps * 1e-3), 'unit': 'samples/s', 'h2d_bytes_per_step': int(h2d[0]),
                 'd2h_bytes_per_step': int(d2h[0])},
         'gpu_launches': int(launches),
@@ -456,6 +492,10 @@ def main():
     ap.add_argument('--cpu-repeats', type=int, default=3)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-adam', action='store_true', help='skip the secondary weak-scaling Adam step')
+    ap.add_argument('--no-split-solve', action='store_true', default=not SPLIT_SOLVE_DEFAULT,
+                    help='N > 1: every rank evaluates the local energies of its own samples and factors the SR matrix itself')
+    ap.add_argument('--split-solve', dest='no_split_solve', action='store_false',
+                    help='N > 1: one rank factors the SR matrix while the others evaluate local energies')
     args = ap.parse_args()
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if not (world == 1 and args.gpus > 1 and args.impl != 'reference'):

@@ -82,6 +82,8 @@ SIGNATURES = {
     'fk_sr_solve_mixed_workspace_bytes': (c_int64, [c_void_p, c_int64]),
     'fk_sr_solve_mixed': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64,
                                   c_void_p]),
+    'fk_sr_factor_mixed': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),
+    'fk_sr_solve_factored': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     'fk_exact_states': (c_int, [c_int64, c_int64, c_int, c_void_p, c_void_p]),
     'fk_exact_index': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     'fk_exact_conn_table': (c_int, [ctypes.POINTER(FkOperator), c_int64, c_int64, c_void_p, c_void_p, c_void_p]),

@@ -171,50 +171,85 @@ extern "C" int64_t fk_sr_solve_mixed_workspace_bytes(fk_sr_solver* s, int64_t n)
   return 512 + mixed_align(n * n * 4) + mixed_align((int64_t)lwork * 4) + 3 * mixed_align(n * 8) + mixed_align(n * 4);
 }
 
-extern "C" int fk_sr_solve_mixed(fk_sr_solver* s, const double* S, double* rhs, int64_t n, int refinements, int* info_out,
-                                 double* resid_out, void* ws, int64_t ws_bytes, void* stream) {
-  FK_REQUIRE(s && S && rhs && ws, "fk_sr_solve_mixed: NULL argument");
-  FK_REQUIRE(n > 0 && n <= 2147483647LL, "fk_sr_solve_mixed: bad dimension");
-  FK_REQUIRE(refinements >= 0 && refinements <= 30, "fk_sr_solve_mixed: refinements must be in 0..30");
+namespace {
+struct MixedWs {
+  int* info; double* norms; float* L; float* work; double* b; double* x; double* r; float* d; int lwork;
+};
+// carve the workspace of fk_sr_solve_mixed_workspace_bytes (the factor phase and the solve phase see the same layout)
+int mixed_carve(fk_sr_solver* s, int64_t n, void* ws, int64_t ws_bytes, MixedWs* m, const char* who) {
+  FK_REQUIRE(n > 0 && n <= 2147483647LL, "%s: bad dimension", who);
   int lwork = 0;
   FK_REQUIRE(s->api.spotrf_buffer(s->handle, FK_CUBLAS_FILL_MODE_LOWER, (int)n, nullptr, (int)n, &lwork) == 0,
-             "fk_sr_solve_mixed: cusolverDnSpotrf_bufferSize failed");
+             "%s: cusolverDnSpotrf_bufferSize failed", who);
   const int64_t need = 512 + mixed_align(n * n * 4) + mixed_align((int64_t)lwork * 4) + 3 * mixed_align(n * 8) + mixed_align(n * 4);
-  FK_REQUIRE(ws_bytes >= need, "fk_sr_solve_mixed: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)need);
-  cudaStream_t st = (cudaStream_t)stream;
-  FK_REQUIRE(s->api.set_stream(s->handle, st) == 0, "fk_sr_solve_mixed: cusolverDnSetStream failed");
+  FK_REQUIRE(ws_bytes >= need, "%s: workspace too small (%lld < %lld)", who, (long long)ws_bytes, (long long)need);
   uint8_t* p = (uint8_t*)ws;
-  int* info = reinterpret_cast<int*>(p);
-  double* norms = reinterpret_cast<double*>(p + 256);         // up to 32 doubles
+  m->lwork = lwork;
+  m->info = reinterpret_cast<int*>(p);
+  m->norms = reinterpret_cast<double*>(p + 256);         // up to 32 doubles
   p += 512;
-  float* L = reinterpret_cast<float*>(p); p += mixed_align(n * n * 4);
-  float* work = reinterpret_cast<float*>(p); p += mixed_align((int64_t)lwork * 4);
-  double* b = reinterpret_cast<double*>(p); p += mixed_align(n * 8);
-  double* x = reinterpret_cast<double*>(p); p += mixed_align(n * 8);
-  double* r = reinterpret_cast<double*>(p); p += mixed_align(n * 8);
-  float* d = reinterpret_cast<float*>(p);
-  FK_CHECK_CUDA(cudaMemsetAsync(norms, 0, 256, st));
-  FK_CHECK_CUDA(cudaMemcpyAsync(b, rhs, n * 8, cudaMemcpyDeviceToDevice, st));
-  FK_CHECK_CUDA(cudaMemsetAsync(x, 0, n * 8, st));
-  fk::to_f32_kernel<<<148 * 8, 256, 0, st>>>(S, L, n * n);
+  m->L = reinterpret_cast<float*>(p); p += mixed_align(n * n * 4);
+  m->work = reinterpret_cast<float*>(p); p += mixed_align((int64_t)lwork * 4);
+  m->b = reinterpret_cast<double*>(p); p += mixed_align(n * 8);
+  m->x = reinterpret_cast<double*>(p); p += mixed_align(n * 8);
+  m->r = reinterpret_cast<double*>(p); p += mixed_align(n * 8);
+  m->d = reinterpret_cast<float*>(p);
+  return 0;
+}
+}  // namespace
+
+// Phase 1: the fp32 Cholesky factor of S into the workspace (does not need the right-hand side: in the sharded step one
+// rank factors while the others still evaluate local energies -- sample_space_sr.py).
+extern "C" int fk_sr_factor_mixed(fk_sr_solver* s, const double* S, int64_t n, int* info_out, void* ws, int64_t ws_bytes,
+                                  void* stream) {
+  FK_REQUIRE(s && S && ws, "fk_sr_factor_mixed: NULL argument");
+  MixedWs m;
+  if (mixed_carve(s, n, ws, ws_bytes, &m, "fk_sr_factor_mixed")) return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  FK_REQUIRE(s->api.set_stream(s->handle, st) == 0, "fk_sr_factor_mixed: cusolverDnSetStream failed");
+  fk::to_f32_kernel<<<148 * 8, 256, 0, st>>>(S, m.L, n * n);
   FK_CHECK_LAUNCH();
-  cusolverStatus_t rc = s->api.spotrf(s->handle, FK_CUBLAS_FILL_MODE_LOWER, (int)n, L, (int)n, work, lwork, info);
-  FK_REQUIRE(rc == 0, "fk_sr_solve_mixed: cusolverDnSpotrf failed (%d)", rc);
-  if (info_out) FK_CHECK_CUDA(cudaMemcpyAsync(info_out, info, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  cusolverStatus_t rc = s->api.spotrf(s->handle, FK_CUBLAS_FILL_MODE_LOWER, (int)n, m.L, (int)n, m.work, m.lwork, m.info);
+  FK_REQUIRE(rc == 0, "fk_sr_factor_mixed: cusolverDnSpotrf failed (%d)", rc);
+  if (info_out) FK_CHECK_CUDA(cudaMemcpyAsync(info_out, m.info, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// Phase 2: rhs <- S^-1 rhs with the factor fk_sr_factor_mixed left in the workspace: fp32 triangular solves + `refinements`
+// fp64 refinement steps against the untouched fp64 S.  resid_out[0] = |rhs|^2, [k] = |rhs - S x_k|^2.
+extern "C" int fk_sr_solve_factored(fk_sr_solver* s, const double* S, double* rhs, int64_t n, int refinements, double* resid_out,
+                                    void* ws, int64_t ws_bytes, void* stream) {
+  FK_REQUIRE(s && S && rhs && ws, "fk_sr_solve_factored: NULL argument");
+  FK_REQUIRE(refinements >= 0 && refinements <= 30, "fk_sr_solve_factored: refinements must be in 0..30");
+  MixedWs m;
+  if (mixed_carve(s, n, ws, ws_bytes, &m, "fk_sr_solve_factored")) return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  FK_REQUIRE(s->api.set_stream(s->handle, st) == 0, "fk_sr_solve_factored: cusolverDnSetStream failed");
+  FK_CHECK_CUDA(cudaMemsetAsync(m.norms, 0, 256, st));
+  FK_CHECK_CUDA(cudaMemcpyAsync(m.b, rhs, n * 8, cudaMemcpyDeviceToDevice, st));
+  FK_CHECK_CUDA(cudaMemsetAsync(m.x, 0, n * 8, st));
   const unsigned row_blocks = (unsigned)((n + 7) / 8);
   for (int k = 0; k <= refinements; ++k) {
-    fk::residual_kernel<<<row_blocks, 256, 0, st>>>(S, k == 0 ? nullptr : x, b, n, r, d, norms + k);
+    fk::residual_kernel<<<row_blocks, 256, 0, st>>>(S, k == 0 ? nullptr : m.x, m.b, n, m.r, m.d, m.norms + k);
     FK_CHECK_LAUNCH();
-    rc = s->api.spotrs(s->handle, FK_CUBLAS_FILL_MODE_LOWER, (int)n, 1, L, (int)n, d, (int)n, info);
-    FK_REQUIRE(rc == 0, "fk_sr_solve_mixed: cusolverDnSpotrs failed (%d)", rc);
-    fk::refine_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, d, n);
+    // (the status word of potrs goes to a scratch slot: m.info keeps the factorisation's)
+    cusolverStatus_t rc = s->api.spotrs(s->handle, FK_CUBLAS_FILL_MODE_LOWER, (int)n, 1, m.L, (int)n, m.d, (int)n, m.info + 1);
+    FK_REQUIRE(rc == 0, "fk_sr_solve_factored: cusolverDnSpotrs failed (%d)", rc);
+    fk::refine_update_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m.x, m.d, n);
     FK_CHECK_LAUNCH();
   }
   // the residual of the returned solution
-  fk::residual_kernel<<<row_blocks, 256, 0, st>>>(S, x, b, n, r, d, norms + refinements + 1);
+  fk::residual_kernel<<<row_blocks, 256, 0, st>>>(S, m.x, m.b, n, m.r, m.d, m.norms + refinements + 1);
   FK_CHECK_LAUNCH();
   if (resid_out)
-    FK_CHECK_CUDA(cudaMemcpyAsync(resid_out, norms, sizeof(double) * (refinements + 2), cudaMemcpyDeviceToDevice, st));
-  FK_CHECK_CUDA(cudaMemcpyAsync(rhs, x, n * 8, cudaMemcpyDeviceToDevice, st));
+    FK_CHECK_CUDA(cudaMemcpyAsync(resid_out, m.norms, sizeof(double) * (refinements + 2), cudaMemcpyDeviceToDevice, st));
+  FK_CHECK_CUDA(cudaMemcpyAsync(rhs, m.x, n * 8, cudaMemcpyDeviceToDevice, st));
   return 0;
+}
+
+extern "C" int fk_sr_solve_mixed(fk_sr_solver* s, const double* S, double* rhs, int64_t n, int refinements, int* info_out,
+                                 double* resid_out, void* ws, int64_t ws_bytes, void* stream) {
+  FK_REQUIRE(s && S && rhs && ws, "fk_sr_solve_mixed: NULL argument");
+  if (fk_sr_factor_mixed(s, S, n, info_out, ws, ws_bytes, stream)) return 1;
+  return fk_sr_solve_factored(s, S, rhs, n, refinements, resid_out, ws, ws_bytes, stream);
 }

@@ -54,6 +54,12 @@ class Observable(BaseObservable):
         self.last_stats, self.last_num_connections = stats, n_conn
         return eloc
 
+    def per_sample_device(self, model):
+        """The local energies as a function of the samples, for the split solve of the sharded SR step
+        (optimizers/sample_space_sr.py): the pipeline decides which rank evaluates which samples of the global batch."""
+        from ...optimizers.sample_space_sr import PerSampleLocalEnergy
+        return PerSampleLocalEnergy(lambda configurations: self.local_values_device(model, configurations))
+
     def local_values_device_generic(self, predict_device, configurations, chunk=1 << 18):
         """Any device wave function (e.g. a symmetrisation ensemble): connections materialised on the device by
         fk_find_conn, log psi of the used ones through `predict_device`, ratios in complex64 and the segmented sum in

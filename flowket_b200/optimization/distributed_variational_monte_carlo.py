@@ -65,6 +65,10 @@ class DistributedVariationalMonteCarlo(VariationalMonteCarlo):
         self.current_energy, self.current_local_energy_variance, self.global_count = \
             self.reduce_stats(self.current_local_energy)
 
+    def _accept_local_values(self, lv):
+        self.current_local_energy = lv
+        self.current_energy, self.current_local_energy_variance, self.global_count = self.reduce_stats(lv)
+
     def next_batch(self):
         batch, _ = super(DistributedVariationalMonteCarlo, self).next_batch()
         return batch, self.loss_coefficients() / self.global_batch_size

@@ -56,7 +56,7 @@ class VariationalMonteCarlo(MiniBatchGenerator):
     def loss_coefficients(self):
         return numpy.conj(self.current_local_energy - self.current_energy)
 
-    def next_batch(self):
+    def _draw(self):
         self.start_time = time.time()
         if hasattr(self.sampler, 'next_device'):
             self.current_batch_device = self.sampler.next_device()
@@ -65,6 +65,31 @@ class VariationalMonteCarlo(MiniBatchGenerator):
             self.current_batch_device = None
             self.current_batch = next(self.sampler)
         self.sampling_end_time = time.time()
+
+    # ---- split solve of the sharded SR step (optimizers/sample_space_sr.py): the optimizer evaluates the local energies
+    # itself, dealt over the ranks next to the factorisation, and hands this rank's values back
+    def next_samples(self):
+        """sampling only -> the batch (host ndarray); the local energies follow through set_local_energy"""
+        self._draw()
+        self.current_local_energy = None
+        return self.current_batch
+
+    def local_energy_function(self):
+        """the local energies of THIS generator's model and operator as a function of the samples (PerSampleLocalEnergy)"""
+        return self.energy_observable.per_sample_device(self.model)
+
+    def _accept_local_values(self, lv):
+        self.current_energy, self.current_local_energy_variance, self.current_local_energy = \
+            numpy.mean(lv), numpy.var(numpy.real(lv)), lv
+
+    def set_local_energy(self, local_energy_device):
+        """the local energies of the current batch, evaluated elsewhere (complex128 device tensor [batch])"""
+        self.current_local_energy_device = local_energy_device
+        self._accept_local_values(local_energy_device.cpu().numpy())
+        self.local_energy_end_time = time.time()
+
+    def next_batch(self):
+        self._draw()
         self._update_batch_local_energy()
         self.local_energy_end_time = time.time()
         return self.current_batch, self.loss_coefficients() / self.batch_size

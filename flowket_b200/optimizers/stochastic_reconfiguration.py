@@ -428,10 +428,14 @@ class StochasticReconfiguration(_SRBase):
             sample_space = net0.num_params > 2 * int(sigma.shape[0]) * world   # P > 2 B_global
         pipe = self._device_pipeline() if sample_space else None
         use_pipe = pipe is not None and (not self.distributed or (2 * int(sigma.shape[0])) % 128 == 0)
-        if callable(local_energy) and not use_pipe:      # only the device pipeline can defer the local energies
-            local_energy = local_energy()
+        self._last_local_energy = None
+        if callable(local_energy) and not use_pipe:      # only the device pipeline can defer / re-deal the local energies
+            from .sample_space_sr import PerSampleLocalEnergy
+            local_energy = local_energy(net0.to_sigma(sigma)) if isinstance(local_energy, PerSampleLocalEnergy) else local_energy()
+            self._last_local_energy = local_energy
         if use_pipe:
             delta = pipe.delta(sigma, local_energy, distributed=self.distributed)
+            self._last_local_energy = pipe.last_local_energy
             if self.read_timings:
                 torch.cuda.synchronize()
                 self.last_timings_ms = dict(pipe.read_timings())
@@ -592,4 +596,22 @@ class StochasticReconfiguration(_SRBase):
         params = self.machine.flat_params_device()
         params.add_(delta.float(), alpha=-self.lr)
         self.machine.params_updated()
+        return delta
+
+    @property
+    def last_local_energy(self):
+        """this rank's local energies of the last device-pipeline update (they are evaluated inside the update when a
+        callable / PerSampleLocalEnergy was passed)"""
+        return getattr(self, '_last_local_energy', None)
+
+    def step_generator(self, generator):
+        """One SR update driven from a VariationalMonteCarlo generator with the local energies evaluated INSIDE the update
+        (split solve of the sharded step): samples from the generator, local energies dealt over the ranks by the pipeline,
+        this rank's values handed back to the generator for its energy statistics."""
+        x = generator.next_samples()
+        delta = self.step(x, generator.local_energy_function())
+        e = self.last_local_energy
+        if e is None or not hasattr(e, 'is_cuda'):     # the routes that evaluated the function up front do not keep the values
+            e = generator.local_energy_function()(self.machine.device_net().to_sigma(x))
+        generator.set_local_energy(e)
         return delta

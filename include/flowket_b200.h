@@ -233,6 +233,13 @@ int fk_sr_solve(fk_sr_solver_t* solver, double* S, double* rhs, int64_t n, int* 
 int64_t fk_sr_solve_mixed_workspace_bytes(fk_sr_solver_t* solver, int64_t n);
 int fk_sr_solve_mixed(fk_sr_solver_t* solver, const double* S, double* rhs, int64_t n, int refinements, int* info_out,
                       double* resid_out, void* ws, int64_t ws_bytes, void* stream);
+/* The two phases of fk_sr_solve_mixed as separate calls over the same workspace: the factorisation needs S only (the
+ * 2B x 2B matrix of optimizer.py:55-66 does not depend on the local energies), so in the sharded step one rank factors while
+ * the other ranks still evaluate local energies, and the right-hand side arrives afterwards. */
+int fk_sr_factor_mixed(fk_sr_solver_t* solver, const double* S, int64_t n, int* info_out, void* ws, int64_t ws_bytes,
+                       void* stream);
+int fk_sr_solve_factored(fk_sr_solver_t* solver, const double* S, double* rhs, int64_t n, int refinements, double* resid_out,
+                         void* ws, int64_t ws_bytes, void* stream);
 
 /* ---- exact enumeration (BASELINE configs[0]; flowket/optimization/exact_variational.py:24-66, exact/utils.py:18-50) ------
  * State index <-> configuration: bit k of the index is flattened site k, bit 1 = spin +1.

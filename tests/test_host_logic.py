@@ -373,3 +373,65 @@ def test_lncosh_and_ensemble_ops_match_the_reference_functions():
     got = average_ensemble_op(x).numpy()
     assert np.allclose(got.real, g['average_ensemble'].real, rtol=1e-11, atol=1e-12)
     assert np.allclose(np.exp(1j * got.imag), np.exp(1j * g['average_ensemble'].imag), atol=1e-11)
+
+
+def test_split_solve_shares():
+    """sample_space_sr.split_solve_shares: the solver rank's share balances T_factor + s0 T_E against (1 - s0) T_E / (N - 1);
+    the shares always cover the batch exactly, whatever the ratio"""
+    from flowket_b200.optimizers.sample_space_sr import split_solve_shares
+    assert split_solve_shares(1, 100, 0.3) == [100]
+    for world in (2, 3, 4, 8):
+        for batch in (64, 1000, 8192):
+            for rho in (0.0, 0.05, 0.087, 0.21, 1.0, 50.0):
+                for solver_rank in (0, world - 1):
+                    c = split_solve_shares(world, batch, rho, solver_rank)
+                    assert len(c) == world and sum(c) == batch and min(c) >= 0
+                    others = [v for r, v in enumerate(c) if r != solver_rank]
+                    assert max(others) - min(others) <= 1
+                    # balance: T_E = 1, T_c = rho
+                    t_solver = rho + c[solver_rank] / batch
+                    t_other = max(others) / batch
+                    if c[solver_rank] > 0:
+                        assert abs(t_solver - t_other) <= 2.0 / batch + 1e-12
+                    else:
+                        assert t_solver >= t_other - 2.0 / batch
+    assert split_solve_shares(8, 8192, 0.0) == [1024] * 8
+
+
+def test_generator_accepts_local_energies_evaluated_elsewhere():
+    """VariationalMonteCarlo.next_samples / set_local_energy (split solve of the sharded SR step): the statistics are those of
+    next_batch on the same values"""
+    import torch
+    from flowket_b200.optimization import VariationalMonteCarlo
+
+    class Sampler(object):
+        batch_size = 6
+
+        def __iter__(self):
+            return self
+
+        def __next__(self):
+            return np.ones((6, 4), np.int8)
+
+    class Obs(object):
+        pass
+
+    from flowket_b200.observables.monte_carlo import BaseObservable
+
+    class Fixed(BaseObservable):
+        def estimate(self, wave_function, configurations):
+            lv = np.arange(6) * (1.0 + 0.5j)
+            return np.mean(lv), np.var(np.real(lv)), lv
+
+    class Net(object):
+        def predict(self, x, batch_size=None):
+            return np.zeros(len(x), np.complex64)
+
+    vmc = VariationalMonteCarlo(Net(), Fixed(), Sampler())
+    vmc.next_batch()
+    want = (vmc.current_energy, vmc.current_local_energy_variance, vmc.current_local_energy.copy())
+    x = vmc.next_samples()
+    assert x.shape == (6, 4) and vmc.current_local_energy is None
+    vmc.set_local_energy(torch.as_tensor(want[2]))
+    assert vmc.current_energy == want[0] and vmc.current_local_energy_variance == want[1]
+    assert np.array_equal(vmc.current_local_energy, want[2])
