@@ -301,7 +301,7 @@ def run_gpu(args):
                 cur['sr_total'] -= cur['eloc']
                 cur['eloc_samples_rank0'] = tm.pop('eloc_samples', 0)
             cur.update({'sr_' + k: v for k, v in tm.items() if k != 'solve'})
-            if best is None or cur['eloc'] < best['eloc']:
+            if best is None or cur['eloc'] + cur['sr_total'] < best['eloc'] + best['sr_total']:
                 best = cur
         phases[tag] = best
     n_conn = obs.last_num_connections           # sum_b (1 + n_conn_b) on this rank

@@ -52,13 +52,17 @@ class PerSampleLocalEnergy(object):
         return self.fn(sigma)
 
 
-def split_solve_shares(world, batch, rho, solver_rank=0):
-    """Samples per rank for the local energies of a global batch when `solver_rank` also factors the matrix:
-    s0 T_E + T_c = (1 - s0) T_E / (N - 1) with rho = T_c / T_E  ->  s0 = (1 - (N - 1) rho) / N, clipped at 0; the other
-    ranks share the rest evenly (the first ones take the remainder).  -> list of `world` ints summing to `batch`."""
+def split_solve_shares(world, batch, rho, solver_rank=0, kappa=1.0):
+    """Samples per rank for the local energies of a global batch when `solver_rank` also factors the matrix.  With T_E the
+    time of the whole batch's local energies at the other ranks' per-sample rate, rho = T_factor / T_E and kappa = (per-sample
+    time on the solver rank) / (per-sample time on the others; the solver rank's clocks differ: it comes out of the
+    factorisation, the others out of the power-capped Gram):  s0 kappa T_E + T_factor = (1 - s0) T_E / (N - 1)
+    ->  s0 = (1 / (N - 1) - rho) / (kappa + 1 / (N - 1)), clipped at 0 (kappa = 1: (1 - (N - 1) rho) / N); the other ranks
+    share the rest evenly (the first ones take the remainder).  -> list of `world` ints summing to `batch`."""
     if world == 1:
         return [int(batch)]
-    s0 = max(0.0, (1.0 - (world - 1) * float(rho)) / world)
+    inv = 1.0 / (world - 1)
+    s0 = max(0.0, (inv - float(rho)) / (max(float(kappa), 1e-3) + inv))
     n0 = min(int(batch), int(round(s0 * batch)))
     rest, others = int(batch) - n0, world - 1
     counts, k = [], 0
@@ -85,6 +89,7 @@ class DeviceSampleSpaceSR(object):
         self.split_solve = bool(split_solve)   # world > 1 and a PerSampleLocalEnergy: one rank factors, the others take its samples
         self.solver_rank = int(solver_rank)
         self.split_rho = 0.1                   # T_factor / T_eloc(whole batch): prior, replaced by the measurement of the last step
+        self.split_kappa = 1.0                 # per-sample local-energy time on the solver rank relative to the other ranks
         self._split_events = None
         self._solver = None
         self.timings_ms = {}
@@ -156,9 +161,13 @@ class DeviceSampleSpaceSR(object):
                 raise ValueError('the device sample-space SR needs the same number of samples on every rank')
             if (2 * Bl) % 128 != 0:
                 raise ValueError('the sharded device sample-space SR needs a multiple of 64 samples per rank')
-            if split and gathered[:, 2].sum() > 0 and gathered[self.solver_rank, 3] > 0:
-                per_sample_ms = gathered[:, 1].sum() / gathered[:, 2].sum()
-                self.split_rho = float(gathered[self.solver_rank, 3] / (per_sample_ms * Bl * world))
+            if split and gathered[self.solver_rank, 3] > 0:
+                other = [r for r in range(world) if r != self.solver_rank and gathered[r, 2] > 0]
+                if other:      # per-sample time of the other ranks, of the solver rank relative to it, factorisation relative to both
+                    tau = gathered[other, 1].sum() / gathered[other, 2].sum()
+                    self.split_rho = float(gathered[self.solver_rank, 3] / (tau * Bl * world))
+                    if gathered[self.solver_rank, 2] > 0:
+                        self.split_kappa = float(gathered[self.solver_rank, 1] / gathered[self.solver_rank, 2] / tau)
         self._split_events = None
         B = Bl * world
         R, Rl = 2 * B, 2 * Bl
@@ -222,7 +231,7 @@ class DeviceSampleSpaceSR(object):
             # its share of the local energies of the GLOBAL batch, one allreduce assembles them
             sig_all = torch.empty((B, sig.shape[1]), dtype=torch.int8, device=dev)
             dist.all_gather_into_tensor(sig_all, sig)
-            counts = split_solve_shares(world, B, self.split_rho, self.solver_rank)
+            counts = split_solve_shares(world, B, self.split_rho, self.solver_rank, self.split_kappa)
             lo = sum(counts[:rank])
             hi = lo + counts[rank]
             events = {'n': hi - lo, 'eloc': None, 'factor': None}

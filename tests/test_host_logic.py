@@ -396,6 +396,12 @@ def test_split_solve_shares():
                     else:
                         assert t_solver >= t_other - 2.0 / batch
     assert split_solve_shares(8, 8192, 0.0) == [1024] * 8
+    # a solver rank whose local energies run at a different per-sample speed (kappa = its time per sample / the others')
+    for world in (2, 4, 8):
+        for kappa in (0.8, 1.0, 1.3):
+            c = split_solve_shares(world, 8192, 0.05, 0, kappa)
+            assert sum(c) == 8192
+            assert abs((0.05 + kappa * c[0] / 8192.0) - c[1] / 8192.0) <= 3.0 / 8192
 
 
 def test_generator_accepts_local_energies_evaluated_elsewhere():

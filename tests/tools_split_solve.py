@@ -57,7 +57,7 @@ report = []
 for rho in (None, 0.0, 0.3, 10.0):      # measured split, equal shares, a small solver share, an empty solver share
     for _ in range(2):
         if rho is not None:
-            pipe.split_rho, pipe._split_events = rho, None
+            pipe.split_rho, pipe.split_kappa, pipe._split_events = rho, 1.0, None
         got = sr.compute_update(sigma, fn)
     assert pipe._split_events is not None, 'the split solve did not run'
     same_on_every_rank(got, 'split update')
