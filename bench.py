@@ -158,7 +158,7 @@ METRIC = ('vmc_sr_step_samples_per_sec (exact autoregressive sampling + local en
           'Heisenberg 2D 10x10 OBC ConvNetAutoregressive2D d20 c32, global batch 8192')
 
 
-SPLIT_SOLVE_DEFAULT = False     # (flipped once the split solve is validated on 2 and 4 GPUs)
+SPLIT_SOLVE_DEFAULT = True      # validated against the plain sharded step on 2 and 4 GPUs (tests/tools_split_solve.py, profiles/r02_split_solve_probe_2gpu.txt)
 
 
 def workload_config(args, world):
