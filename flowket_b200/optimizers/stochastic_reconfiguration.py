@@ -369,8 +369,9 @@ class StochasticReconfiguration(_SRBase):
     `sample_space=None` picks the sample-space form when P > 2B."""
 
     def __init__(self, model, sample_space=None, gram_dtype='bf16', jacobian_chunk=1024, shared_cholesky=False,
-                 device_pipeline=True, read_timings=True, solver='mixed', **kwargs):
+                 device_pipeline=True, read_timings=True, solver='mixed', split_solve=True, **kwargs):
         super(StochasticReconfiguration, self).__init__(model, **kwargs)
+        self.split_solve = split_solve           # sharded device pipeline, local energies passed as a function: one rank factors while the others evaluate them
         self.solver = solver                     # device pipeline: 'mixed' (fp32 Cholesky + fp64 refinement) or 'fp64'
         self.device_pipeline = device_pipeline   # False: the torch route below (fp32 rows, torch.mm Gram) -- kept as a cross-check
         self.read_timings = read_timings         # False: no synchronise after the update (timings / potrf status unread)
@@ -416,6 +417,7 @@ class StochasticReconfiguration(_SRBase):
         if getattr(self, '_pipeline', None) is None or self._pipeline.net is not net:
             self._pipeline = DeviceSampleSpaceSR(net, self.diag_shift, solver=self.solver)
         self._pipeline.solver = self.solver
+        self._pipeline.split_solve = bool(self.split_solve)
         self._pipeline.diag_shift = float(self.diag_shift)
         return self._pipeline
 

@@ -136,6 +136,20 @@ class Trainer(object):
             self.optimizer.track_ema(params)
         return True
 
+    def _split_solve_route(self):
+        opt, gen = self.optimizer, self.generator
+        if not (hasattr(opt, 'step_generator') and getattr(opt, 'distributed', False) and getattr(opt, 'split_solve', True)):
+            return False
+        if not (hasattr(gen, 'next_samples') and hasattr(getattr(gen, 'sampler', None), 'next_device')):
+            return False
+        try:
+            import torch.distributed as dist
+            world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        except Exception:
+            world = 1
+        from ..keras_shim import Model
+        return world > 1 and self._frequency() == 1 and isinstance(getattr(gen, 'model', None), Model)
+
     def _stochastic_reconfiguration_step(self, x, y):
         """`model.compile(optimizer=ComplexValuesStochasticReconfiguration(model, ...))` (the reference passes its SR
         optimizer to Keras like any other, optimizers/stochastic_reconfiguration/optimizer.py:14-31): the optimizer owns
@@ -160,6 +174,13 @@ class Trainer(object):
     def train_step(self):
         """One parameter update = `update_params_frequency` mini-batches of the generator."""
         gen = self.generator
+        if self._split_solve_route():
+            # sharded real-parameter SR: the optimizer evaluates the local energies itself, dealt over the ranks next to the
+            # factorisation of the SR matrix (optimizers/sample_space_sr.py), and hands this rank's values back to the generator
+            self.optimizer.step_generator(gen)
+            energy = getattr(gen, 'current_energy', None)
+            self.history.append(energy)
+            return energy
         updated = False
         while not updated:
             x, y = next(gen)
