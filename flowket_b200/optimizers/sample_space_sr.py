@@ -75,6 +75,33 @@ def split_solve_shares(world, batch, rho, solver_rank=0, kappa=1.0):
     return counts
 
 
+def deal_local_energies(sigma, fn, counts, rank, world, events=None, after_gather=None):
+    """Local energies of the GLOBAL batch with the samples dealt over the ranks: all-gather the ranks' samples (equal
+    counts per rank, rank-major = global sample order), evaluate `fn` on samples [sum(counts[:rank]), + counts[rank]) of the
+    global batch, assemble with one allreduce.  -> complex128 [B_global], identical on every rank.  `events`: two CUDA events
+    recorded around the evaluation (split-solve bookkeeping); `after_gather`: called once the sample gather is enqueued and
+    before the evaluation (the solver rank factors there: a collective enqueued behind the factorisation would make every
+    other rank wait for it).  Backend-agnostic (NCCL on the device, gloo in the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+    Bl = sigma.shape[0]
+    sig_all = torch.empty((Bl * world,) + tuple(sigma.shape[1:]), dtype=sigma.dtype, device=sigma.device)
+    dist.all_gather_into_tensor(sig_all, sigma.contiguous())
+    if after_gather is not None:
+        after_gather()
+    lo = sum(counts[:rank])
+    hi = lo + counts[rank]
+    e_all = torch.zeros(Bl * world, dtype=torch.complex128, device=sigma.device)
+    if hi > lo:
+        if events is not None:
+            events[0].record()
+        e_all[lo:hi] = fn(sig_all[lo:hi]).to(torch.complex128)
+        if events is not None:
+            events[1].record()
+    dist.all_reduce(torch.view_as_real(e_all))
+    return e_all
+
+
 class DeviceSampleSpaceSR(object):
     def __init__(self, net, diag_shift, solver='mixed', refinements=3, split_solve=True, solver_rank=0):
         import torch
@@ -229,13 +256,10 @@ class DeviceSampleSpaceSR(object):
         if split:
             # the samples of every rank (B x sites bytes), then: the solver rank centres and factors S, everybody evaluates
             # its share of the local energies of the GLOBAL batch, one allreduce assembles them
-            sig_all = torch.empty((B, sig.shape[1]), dtype=torch.int8, device=dev)
-            dist.all_gather_into_tensor(sig_all, sig)
             counts = split_solve_shares(world, B, self.split_rho, self.solver_rank, self.split_kappa)
-            lo = sum(counts[:rank])
-            hi = lo + counts[rank]
-            events = {'n': hi - lo, 'eloc': None, 'factor': None}
-            if is_solver:
+            events = {'n': counts[rank], 'eloc': None, 'factor': None}
+
+            def factor():
                 fe = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
                 centre()
                 fe[0].record()
@@ -244,15 +268,12 @@ class DeviceSampleSpaceSR(object):
                     _lib.check(lib.fk_sr_factor_mixed(solver, _ptr(S), R, _ptr(info), _ptr(sws), sws.numel(), stream))
                 fe[1].record()
                 events['factor'] = fe
-            e_all = torch.zeros(B, dtype=torch.complex128, device=dev)
-            if hi > lo:
-                ee = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-                ee[0].record()
-                e_all[lo:hi] = local_energy(sig_all[lo:hi]).to(torch.complex128)
-                ee[1].record()
+
+            ee = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if counts[rank] > 0 else None
+            e_all = deal_local_energies(sig, local_energy, counts, rank, world, ee, after_gather=factor if is_solver else None)
+            if ee is not None:
                 events['eloc'] = ee
                 self._eloc_events = ee
-            dist.all_reduce(torch.view_as_real(e_all))
             self._split_events = events
             self.split_counts = counts
             self.last_local_energy = e_all[rank * Bl:(rank + 1) * Bl]

@@ -242,3 +242,55 @@ def test_exact_variational_sharded_over_two_ranks_matches_the_whole_enumeration(
         res = out[rank]
         assert res['energy'] < 1e-12 and res['variance'] < 1e-10 and res['probs'] < 1e-15, (rank, res)
         assert res['states'] and res['coefficients'] < 1e-13 and res['tables'] == 32, (rank, res)
+
+
+def _deal_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from flowket_b200.optimizers.sample_space_sr import deal_local_energies, split_solve_shares
+    from oracle import operators as oops, local_energy as oeloc
+    shape = (3, 3)
+    op = oops.OracleOperator('heisenberg', shape, pbc=False)
+    rng = np.random.default_rng(5)
+    Bl = 12
+    full = rng.choice([-1, 1], size=(Bl * world, 9)).astype(np.int8)      # the global batch, rank-major
+    w = rng.normal(size=9) + 1j * rng.normal(size=9) * 0.3
+
+    def log_psi(x):       # any deterministic wave function of the configuration
+        x = np.asarray(x, np.float64).reshape(len(x), -1)
+        return x @ w + 0.1 * (x[:, :-1] * x[:, 1:]).sum(axis=1)
+
+    def fn(sig):          # the local energies of the samples it is handed (oracle: local_energy.py)
+        x = sig.numpy().reshape((-1,) + shape)
+        return torch.as_tensor(np.asarray(oeloc.local_values(op, lambda c: log_psi(c)[:, None], x), np.complex128))
+
+    calls = []
+    mine = torch.as_tensor(full[rank * Bl:(rank + 1) * Bl])
+    want = fn(torch.as_tensor(full))
+    res = {}
+    for rho in (0.0, 0.2, 0.6, 5.0):
+        counts = split_solve_shares(world, Bl * world, rho, solver_rank=0, kappa=1.2)
+        got = deal_local_energies(mine, fn, counts, rank, world, after_gather=lambda: calls.append(rank))
+        res[rho] = (counts, float((got - want).abs().max()))
+    res['calls'] = len(calls)
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_split_solve_deals_the_local_energies_over_the_ranks(world):
+    """sample_space_sr.deal_local_energies (the N > 1 half of the split solve): whatever the shares -- equal, small or empty
+    solver share, remainders -- every rank ends up with the local energies of the whole global batch in global order, equal
+    to evaluating them in one process"""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_deal_worker, args=(world, 29663 + world, out), nprocs=world, join=True)
+    for rank in range(world):
+        res = out[rank]
+        assert res['calls'] == 4
+        for rho in (0.0, 0.2, 0.6, 5.0):
+            counts, err = res[rho]
+            assert sum(counts) == 12 * world and err < 1e-12, (rank, rho, counts, err)
+        assert res[5.0][0][0] == 0 and res[0.0][0][0] > 0
