@@ -148,7 +148,9 @@ class Trainer(object):
         except Exception:
             world = 1
         from ..keras_shim import Model
-        return world > 1 and self._frequency() == 1 and isinstance(getattr(gen, 'model', None), Model)
+        from ..observables.monte_carlo import Observable
+        return world > 1 and self._frequency() == 1 and isinstance(getattr(gen, 'model', None), Model) and \
+            isinstance(getattr(gen, 'energy_observable', None), Observable)
 
     def _stochastic_reconfiguration_step(self, x, y):
         """`model.compile(optimizer=ComplexValuesStochasticReconfiguration(model, ...))` (the reference passes its SR

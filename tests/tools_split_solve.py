@@ -53,6 +53,18 @@ plain_ms = dict(sr.last_timings_ms)
 same_on_every_rank(want, 'plain update')
 pipe = sr._pipeline
 fn = vmc.local_energy_function()
+# the sharded update against ONE process holding the whole global batch (rank-major order = the global sample order)
+sig_all = torch.empty((world * B,) + tuple(sigma.shape[1:]), dtype=sigma.dtype, device=sigma.device)
+dist.all_gather_into_tensor(sig_all, sigma.contiguous())
+eloc_all = torch.empty(world * B, dtype=eloc.dtype, device=eloc.device)
+dist.all_gather_into_tensor(eloc_all, eloc.contiguous())
+rel_single = 0.0
+if rank == 0:
+    sr1 = StochasticReconfiguration(model, diag_shift=0.05, sample_space=True, distributed=False)
+    single = sr1.compute_update(sig_all, eloc_all)
+    rel_single = float((want - single).norm() / single.norm())
+    assert rel_single < 2e-3, rel_single      # (bf16 rows, fp32 Gram accumulated in a different order: partial Grams per rank)
+dist.barrier()
 report = []
 for rho in (None, 0.0, 0.3, 10.0):      # measured split, equal shares, a small solver share, an empty solver share
     for _ in range(2):
@@ -81,6 +93,7 @@ moved = float((m.flat_params_device() - params0).abs().max())
 assert moved > 0
 if rank == 0:
     print('plain sharded step: %s' % {k: round(v, 2) for k, v in plain_ms.items()}, flush=True)
+    print('plain sharded step vs ONE process on the global batch of %d samples: relative difference of the update %.2e' % (world * B, rel_single), flush=True)
     for rho, counts, rel, tm in report:
         print('split solve, rho %s: samples per rank %s, relative difference of the update %.2e, %s' % (rho, counts, rel, tm), flush=True)
     print('fp64 re-solve through the solver rank: relative difference %.2e' % rel64, flush=True)
