@@ -34,7 +34,8 @@ def main():
     print('local-memory instructions: %d static, %d executed (%.2f %% of all), %d samples on themselves' % (
         len(lm), sum(int(R[i][ie]) for i in lm), 100.0 * sum(int(R[i][ie]) for i in lm) / sum(int(r[ie]) for r in R),
         sum(int(R[i][si]) for i in lm)))
-    for spec in sys.argv[4:]:
+    specs = sys.argv[4:] or ['whole kernel:0:%d' % len(R)]
+    for spec in specs:
         name, lo, hi = spec.rsplit(':', 2)
         lo, hi = int(lo), int(hi)
         reg = R[lo:hi]
