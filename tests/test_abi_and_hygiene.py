@@ -74,3 +74,35 @@ def test_missing_library_is_reported(tmp_path):
     from flowket_b200 import _lib
     with pytest.raises(_lib.FlowketB200Error):
         _lib.load(str(tmp_path / 'does_not_exist.so'))
+
+
+def test_integration_guide_calls_match_the_abi():
+    """every `lib.fk_*(...)` call shown in INTEGRATION.md names a function of include/flowket_b200.h and passes as many
+    arguments as its ctypes signature (the binding a maintainer would copy must not rot)"""
+    import re
+    from flowket_b200 import _lib
+    text = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    header = open(os.path.join(ROOT, 'include', 'flowket_b200.h')).read()
+    seen = 0
+    for m in re.finditer(r'lib\.(fk_\w+)\(', text):
+        name, i, depth, args, cur = m.group(1), m.end(), 1, [], ''
+        while i < len(text):
+            c = text[i]
+            if c in '([{':
+                depth += 1
+            if c in ')]}':
+                depth -= 1
+                if depth == 0:
+                    break
+            if c == ',' and depth == 1:
+                args.append(cur)
+                cur = ''
+            else:
+                cur += c
+            i += 1
+        if cur.strip():
+            args.append(cur)
+        assert name in _lib.SIGNATURES and re.search(r'\b%s\s*\(' % name, header), name
+        assert len(args) == len(_lib.SIGNATURES[name][1]), (name, len(args), len(_lib.SIGNATURES[name][1]))
+        seen += 1
+    assert seen >= 12
