@@ -41,7 +41,8 @@ def ptxas_info():
     return info
 
 
-def main():
+def collect():
+    """-> (opcode counts per mangled kernel name, instruction totals, demangled names)"""
     sass = subprocess.run(['cuobjdump', '-sass', SO], stdout=subprocess.PIPE, universal_newlines=True).stdout
     counts, total, cur = collections.defaultdict(collections.Counter), collections.Counter(), None
     for line in sass.split('\n'):
@@ -54,7 +55,11 @@ def main():
             op = m.group(1)
             total[cur] += 1
             counts[cur][op] += 1
-    names = demangle(list(total))
+    return counts, total, demangle(list(total))
+
+
+def main():
+    counts, total, names = collect()
     pt = ptxas_info()
     print('# cuobjdump -sass flowket_b200/libflowket_b200.so: opcode counts per kernel (tcgen05.mma = UTCHMMA, tcgen05.ld/st = LDTM/STTM,')
     print('# cp.async.bulk = UBLKCP, cp.async.bulk.tensor = UTMALDG, tcgen05.commit = UTCBAR, mbarrier = SYNCS; no HMMA = no legacy mma.sync')

@@ -106,3 +106,35 @@ def test_integration_guide_calls_match_the_abi():
         assert len(args) == len(_lib.SIGNATURES[name][1]), (name, len(args), len(_lib.SIGNATURES[name][1]))
         seen += 1
     assert seen >= 12
+
+
+def test_hot_kernels_keep_off_the_local_memory_stack():
+    """At a ~223 KB shared-memory carve-out the L1 that backs the local-memory stack is nearly gone: by-value descriptor copies
+    with run-time indexing cost the Jacobian rows kernel 36 ms per step.  The kernels that were cleaned
+    must stay clean, and every tensor-core kernel must keep issuing tcgen05 / bulk-copy instructions (SASS of the built library)."""
+    import importlib.util
+    import shutil
+    if shutil.which('cuobjdump') is None:
+        pytest.skip('cuobjdump not on PATH')
+    spec = importlib.util.spec_from_file_location('sass_histogram', os.path.join(ROOT, 'profiles', 'sass_histogram.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    counts, total, names = mod.collect()
+    by_name = {}
+    for k, n in names.items():
+        by_name.setdefault(n.split('(')[0].replace('void ', ''), []).append(k)
+
+    def one(name):
+        ks = by_name.get(name)
+        assert ks, (name, sorted(by_name)[:50])
+        return counts[ks[0]]
+
+    for name, limit in (('fk::tc_dw_rows_kernel', 8), ('fk::tc_dw_kernel', 0), ('fk::tc_sample_kernel', 0), ('fk::gram2_kernel', 2)):
+        c = one(name)
+        assert c['LDL'] + c['STL'] <= limit, (name, c['LDL'], c['STL'])
+    for name in ('fk::tc_dw_rows_kernel', 'fk::tc_dw_kernel', 'fk::tc_sample_kernel', 'fk::gram2_kernel', 'fk::tcx_forward_kernel',
+                 'fk::tc_backward_kernel', 'fk::gram_tc_kernel'):
+        c = one(name)
+        assert c['UTCHMMA'] > 0 and c['HMMA'] == 0, (name, dict(c))
+    assert one('fk::gram2_kernel')['UTMALDG'] > 0          # TMA tensor-map loads
+    assert one('fk::tcx_forward_kernel')['UBLKCP'] > 0      # bulk copies of the weight images
